@@ -1,0 +1,3 @@
+class CSVLogger:
+    def __init__(self, *a, **k):
+        raise RuntimeError("stub")

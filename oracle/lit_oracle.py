@@ -1,0 +1,402 @@
+"""ORACLE — test infrastructure, NOT product code.
+
+A functional CPU restatement (torch ops on plain tensors, no nn.Module) of the reference's
+inference hot path: ``lit_gpt.model.GPT.forward`` with KV caches and ``generate/base.py::generate``.
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this module, and only as the checker / CPU baseline.  The product
+(``lit_parrot_b200``) never does.
+
+Pinning: the reference is Python, so this restatement is pinned against the *unmodified* reference
+imported from ``/root/reference`` in the build container (``oracle/check_against_reference.py``) and
+against the golden vectors that run produced (``tests/golden/*.npz``, made by ``oracle/make_golden.py``).
+The bitsandbytes NF4/int8 arithmetic is NOT in the reference tree (third-party ``bitsandbytes>=0.40.0``,
+unpinned, requirements.txt:5): for those two functions the header below each says "parity unpinned".
+
+Every function cites the reference lines it follows.  State dict keys are the reference's
+(``transformer.h.{i}.attn.attn.weight`` ...), so a reference ``state_dict()`` can be fed in unchanged.
+"""
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+
+# ----------------------------------------------------------------------------------------------
+# rope / norm / mlp pieces
+# ----------------------------------------------------------------------------------------------
+def rope_tables(block_size: int, n_elem: int, dtype: torch.dtype, condense_ratio: int = 1,
+                base: int = 10000) -> Tuple[Tensor, Tensor]:
+    """model.py:304-327.  theta_i = base^(-2i/n_elem); angle = (pos/condense)*theta, duplicated to
+    n_elem columns; tables are cast to fp16 when the working dtype is 16-bit (model.py:325-326)."""
+    theta = 1.0 / (base ** (torch.arange(0, n_elem, 2) / n_elem))
+    pos = torch.arange(block_size) / condense_ratio
+    ang = torch.outer(pos, theta).repeat(1, 2)
+    cos, sin = torch.cos(ang), torch.sin(ang)
+    if dtype in (torch.float16, torch.bfloat16, torch.int8):
+        return cos.half(), sin.half()
+    return cos, sin
+
+
+def rotate(x: Tensor, cos: Tensor, sin: Tensor) -> Tensor:
+    """model.py:330-336: rotate-half; pair is (i, i + n/2); result cast back to x's dtype."""
+    half = x.size(-1) // 2
+    swapped = torch.cat((-x[..., half:], x[..., :half]), dim=-1)
+    return ((x * cos) + (swapped * sin)).type_as(x)
+
+
+def rms_norm(x: Tensor, weight: Tensor, eps: float) -> Tensor:
+    """lit_gpt/rmsnorm.py:17-21 — all arithmetic in the input dtype."""
+    ms = torch.mean(x * x, dim=-1, keepdim=True)
+    return weight * (x * torch.rsqrt(ms + eps))
+
+
+def norm(cfg, x: Tensor, sd: Dict[str, Tensor], prefix: str) -> Tensor:
+    """config.py:85-92 picks RMSNorm or torch.nn.LayerNorm (weight + bias)."""
+    if cfg._norm_class == "RMSNorm":
+        return rms_norm(x, sd[prefix + ".weight"], cfg.norm_eps)
+    return F.layer_norm(x, (x.size(-1),), sd[prefix + ".weight"], sd[prefix + ".bias"], cfg.norm_eps)
+
+
+def linear(x: Tensor, sd: Dict[str, Tensor], prefix: str) -> Tensor:
+    """nn.Linear, or the GPTQ fall-back `get_weight(dtype)+F.linear` (quantize/gptq.py:263-264) when the
+    state dict holds `quant_weight/scales/zeros` for this layer."""
+    if prefix + ".quant_weight" in sd:
+        w = gptq_dequant(sd[prefix + ".quant_weight"], sd[prefix + ".scales"], sd[prefix + ".zeros"], dtype=x.dtype)
+        return F.linear(x, w, sd.get(prefix + ".bias"))
+    return F.linear(x, sd[prefix + ".weight"], sd.get(prefix + ".bias"))
+
+
+def mlp(cfg, x: Tensor, sd: Dict[str, Tensor], prefix: str) -> Tensor:
+    """GptNeoxMLP model.py:284-287 (exact-erf GELU) / LLaMAMLP model.py:297-301 (SwiGLU)."""
+    if cfg._mlp_class == "LLaMAMLP":
+        return linear(F.silu(linear(x, sd, prefix + ".fc_1")) * linear(x, sd, prefix + ".fc_2"), sd, prefix + ".proj")
+    return linear(F.gelu(linear(x, sd, prefix + ".fc")), sd, prefix + ".proj")
+
+
+# ----------------------------------------------------------------------------------------------
+# attention with the reference's cache semantics
+# ----------------------------------------------------------------------------------------------
+def attention(cfg, x: Tensor, sd: Dict[str, Tensor], prefix: str, cos: Tensor, sin: Tensor, max_seq_length: int,
+              mask: Optional[Tensor], input_pos: Optional[Tensor], kv: Optional[Tuple[Tensor, Tensor]]):
+    """CausalSelfAttention.forward, model.py:194-254."""
+    B, T, C = x.shape
+    H, G, hs = cfg.n_head, cfg.n_query_groups, cfg.n_embd // cfg.n_head
+    qpk = H // G
+    qkv = linear(x, sd, prefix + ".attn")  # (B, T, (H+2G)*hs), rows group-interleaved [q*qpk, k, v]
+    qkv = qkv.view(B, T, G, qpk + 2, hs).permute(0, 2, 3, 1, 4)  # (B, G, qpk+2, T, hs)   model.py:210-211
+    q, k, v = qkv.split((qpk, 1, 1), dim=2)  # model.py:214
+    if G != 1:  # model.py:217-220: MHA/GQA replicate k,v per query head; MQA keeps one head
+        k = k.repeat_interleave(qpk, dim=2)
+        v = v.repeat_interleave(qpk, dim=2)
+    q = q.reshape(B, -1, T, hs)
+    k = k.reshape(B, -1, T, hs)
+    v = v.reshape(B, -1, T, hs)
+    n_elem = int(cfg.rotary_percentage * hs)  # model.py:222
+    q = torch.cat((rotate(q[..., :n_elem], cos, sin), q[..., n_elem:]), dim=-1)  # model.py:225-232
+    k = torch.cat((rotate(k[..., :n_elem], cos, sin), k[..., n_elem:]), dim=-1)
+    if kv is not None:  # model.py:234-245
+        ck, cv = kv
+        ck, cv = ck.to(dtype=k.dtype), cv.to(dtype=v.dtype)
+        if input_pos[-1] >= max_seq_length:  # sliding window by physical roll, model.py:238-242
+            input_pos = torch.tensor(max_seq_length - 1)
+            ck = torch.roll(ck, -1, dims=2)
+            cv = torch.roll(cv, -1, dims=2)
+        k = ck.index_copy_(2, input_pos, k)
+        v = cv.index_copy_(2, input_pos, v)
+        kv = (k, v)
+    scale = 1.0 / math.sqrt(hs)  # model.py:259
+    y = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=0.0, scale=scale, is_causal=mask is None)
+    y = y.transpose(1, 2).contiguous().view(B, T, C)  # model.py:249
+    return linear(y, sd, prefix + ".proj"), kv
+
+
+def block(cfg, x, sd, i, cos, sin, max_seq_length, mask, input_pos, kv):
+    """Block.forward, model.py:158-180."""
+    p = f"transformer.h.{i}"
+    n1 = norm(cfg, x, sd, p + ".norm_1")
+    h, kv = attention(cfg, n1, sd, p + ".attn", cos, sin, max_seq_length, mask, input_pos, kv)
+    if cfg.parallel_residual:
+        n2 = n1 if cfg.shared_attention_norm else norm(cfg, x, sd, p + ".norm_2")
+        x = x + h + mlp(cfg, n2, sd, p + ".mlp")  # (x + h) + mlp, model.py:171
+    else:
+        if cfg.shared_attention_norm:
+            raise NotImplementedError("non-parallel residual with shared attention norm")
+        x = x + h
+        x = x + mlp(cfg, norm(cfg, x, sd, p + ".norm_2"), sd, p + ".mlp")
+    return x, kv
+
+
+class OracleGPT:
+    """Holds the lazily built rope/mask/kv caches exactly like the reference module (model.py:37-39,
+    79-85, 105) so it can be driven call-for-call like ``GPT.forward``."""
+
+    def __init__(self, cfg, state_dict: Dict[str, Tensor], dtype: Optional[torch.dtype] = None) -> None:
+        self.config = cfg
+        self.dtype = dtype or state_dict["transformer.wte.weight"].dtype
+        self.sd = {k: (v.to(self.dtype) if v.is_floating_point() and not k.endswith("quant_weight") else v)
+                   for k, v in state_dict.items()}
+        self.rope = None
+        self.mask = None
+        self.kv: List[Tuple[Tensor, Tensor]] = []
+
+    def reset_cache(self) -> None:
+        self.kv.clear()
+
+    def __call__(self, idx: Tensor, max_seq_length: Optional[int] = None, input_pos: Optional[Tensor] = None):
+        """GPT.forward, model.py:63-111."""
+        cfg = self.config
+        B, T = idx.shape
+        bs = cfg.block_size
+        use_cache = input_pos is not None
+        if max_seq_length is None:
+            max_seq_length = bs
+        if use_cache:
+            assert max_seq_length >= T, f"Cannot forward sequence of length {T}, max seq length is only {max_seq_length}"
+        assert max_seq_length <= bs, f"Cannot attend to {max_seq_length}, block size is only {bs}"
+        assert bs >= T, f"Cannot forward sequence of length {T}, block size is only {bs}"
+        hs = cfg.n_embd // cfg.n_head
+        if self.rope is None:
+            self.rope = rope_tables(bs, int(cfg.rotary_percentage * hs), self.dtype, cfg.condense_ratio)
+        if use_cache and self.mask is None:  # dense tril bool, model.py:126-128
+            self.mask = torch.tril(torch.ones((bs, bs), dtype=torch.bool))[None, None]
+        cos, sin = self.rope
+        if use_cache:
+            cos, sin = cos.index_select(0, input_pos), sin.index_select(0, input_pos)
+            mask = self.mask.index_select(2, input_pos)[:, :, :, :max_seq_length]
+        else:
+            cos, sin, mask = cos[:T], sin[:T], None
+        x = F.embedding(idx, self.sd["transformer.wte.weight"])  # model.py:99
+        if not use_cache:
+            for i in range(cfg.n_layer):
+                x, _ = block(cfg, x, self.sd, i, cos, sin, max_seq_length, None, None, None)
+        else:
+            if not self.kv:  # model.py:130-144: zero caches; MQA keeps one head, otherwise n_head heads
+                heads = 1 if cfg.n_query_groups == 1 else cfg.n_head
+                shape = (B, heads, max_seq_length, hs)
+                self.kv = [(torch.zeros(shape, dtype=self.dtype), torch.zeros(shape, dtype=self.dtype))
+                           for _ in range(cfg.n_layer)]
+            for i in range(cfg.n_layer):
+                x, self.kv[i] = block(cfg, x, self.sd, i, cos, sin, max_seq_length, mask, input_pos, self.kv[i])
+        x = norm(cfg, x, self.sd, "transformer.ln_f")
+        return linear(x, self.sd, "lm_head")  # all T positions, model.py:111
+
+
+# ----------------------------------------------------------------------------------------------
+# generate
+# ----------------------------------------------------------------------------------------------
+def topk_filter(logits: Tensor, top_k: Optional[int]) -> Tensor:
+    """generate/base.py:139-141: keep everything >= the k-th largest value (ties survive)."""
+    if top_k is None:
+        return logits
+    kth = torch.topk(logits, min(top_k, logits.size(-1))).values[-1]
+    return torch.where(logits < kth, torch.full_like(logits, -float("inf")), logits)
+
+
+@torch.no_grad()
+def generate(model, idx: Tensor, max_returned_tokens: int, max_seq_length: Optional[int] = None, *,
+             temperature: float = 1.0, top_k: Optional[int] = None, eos_id: Optional[int] = None,
+             argmax_ties: bool = False, logits_out: Optional[list] = None) -> Tensor:
+    """generate/base.py:92-159.  ``argmax_ties=True`` replaces ``multinomial`` by lowest-index arg-max
+    over the filtered logits — the deterministic reading of "greedy" (top_k=1) used for token parity
+    (the reference samples uniformly among exact ties)."""
+    if max_seq_length is None:
+        max_seq_length = max_returned_tokens
+    T = idx.size(0)
+    assert max_returned_tokens > T
+    out = torch.empty(max_returned_tokens, dtype=idx.dtype)
+    out[:T] = idx
+    input_pos = torch.arange(0, T)
+    for _ in range(max_returned_tokens - T):
+        x = out.index_select(0, input_pos).view(1, -1)
+        logits = model(x, max_seq_length, input_pos)
+        logits = logits[0, -1] / temperature
+        if logits_out is not None:
+            logits_out.append(logits.float().clone())
+        logits = topk_filter(logits, top_k)
+        if argmax_ties:
+            nxt = torch.argmax(logits.float()).view(1).to(idx.dtype)
+        else:
+            probs = F.softmax(logits, dim=-1)
+            nxt = torch.multinomial(probs, num_samples=1).to(idx.dtype)
+        input_pos = input_pos[-1:] + 1
+        out = out.index_copy(0, input_pos, nxt)
+        if eos_id is not None and nxt.item() == eos_id:
+            return out[: int(input_pos)]
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# weight-only quantisation formats
+# ----------------------------------------------------------------------------------------------
+def gptq_find_params(w: Tensor, bits: int = 4) -> Tuple[Tensor, Tensor]:
+    """Asymmetric per-row min/max grid of one column tile: quantize/gptq.py:317-347
+    (perchannel=True, sym=False).  Returns (scale, zero) of shape (rows, 1); zero is an integer-valued float."""
+    maxq = 2 ** bits - 1
+    z = torch.zeros(w.shape[0])
+    lo = torch.minimum(w.min(1)[0], z)
+    hi = torch.maximum(w.max(1)[0], z)
+    dead = (lo == 0) & (hi == 0)
+    lo[dead], hi[dead] = -1, +1
+    scale = (hi - lo) / maxq
+    zero = torch.round(-lo / scale)
+    return scale.reshape(-1, 1), zero.reshape(-1, 1)
+
+
+def gptq_pack(w: Tensor, scales: Tensor, zeros: Tensor, tile_cols: int, bits: int = 4) -> Tensor:
+    """quantize/gptq.py:233-241: q = clamp(w/scale + zero, 0, 15) truncated to uint8 (a float->uint8
+    cast, i.e. NOT round-to-nearest); column 2j in the low nibble, 2j+1 in the high nibble; stored
+    (out, in/2) with strides (1, out) (gptq.py:216-222)."""
+    w = w.clone().float()
+    for j in range(scales.size(1)):
+        sl = slice(j * tile_cols, (j + 1) * tile_cols)
+        w[:, sl] /= scales[:, j : j + 1]
+        w[:, sl] += zeros[:, j : j + 1]
+    q = w.clamp_(min=0, max=2 ** bits - 1).to(torch.uint8)
+    per = 8 // bits
+    packed = torch.zeros((w.shape[0], w.shape[1] // per), dtype=torch.uint8).t().contiguous().t()
+    for nr in range(per):
+        packed += q[:, nr::per] << (nr * bits)
+    return packed
+
+
+def gptq_rtn_quantize(w: Tensor, tile_cols: int, bits: int = 4):
+    """Round-to-nearest group quantiser built from the reference's own grid (find_params_weight) and
+    its own quantise step q = clamp(round(w/scale) + zero, 0, maxq) (gptq.py:313-315), packed with the
+    reference's nibble layout.  (The GPTQ error-propagation solver, gptq.py:365-445, is offline and out
+    of scope; calibration data is not available offline.)"""
+    if tile_cols == -1:
+        tile_cols = w.shape[1]
+    n_tiles = (w.shape[1] + tile_cols - 1) // tile_cols
+    scales = torch.empty(w.shape[0], n_tiles)
+    zeros = torch.empty(w.shape[0], n_tiles)
+    maxq = 2 ** bits - 1
+    q = torch.empty_like(w, dtype=torch.float32)
+    for j in range(n_tiles):
+        sl = slice(j * tile_cols, (j + 1) * tile_cols)
+        s, z = gptq_find_params(w[:, sl].float(), bits)
+        scales[:, j : j + 1], zeros[:, j : j + 1] = s, z
+        q[:, sl] = torch.clamp(torch.round(w[:, sl].float() / s) + z, 0, maxq)
+    per = 8 // bits
+    qi = q.to(torch.uint8)
+    packed = torch.zeros((w.shape[0], w.shape[1] // per), dtype=torch.uint8).t().contiguous().t()
+    for nr in range(per):
+        packed += qi[:, nr::per] << (nr * bits)
+    return packed, scales, zeros
+
+
+def gptq_dequant(quant_weight: Tensor, scales: Tensor, zeros: Tensor, dtype=torch.float32, bits: int = 4) -> Tensor:
+    """quantize/gptq.py:243-252: nibble -> float, then `-= zero`, `*= scale` evaluated in `dtype`
+    (so in bf16 the dequantised weight is rounded to bf16 before the matmul)."""
+    out_f, per = quant_weight.shape[0], 8 // bits
+    in_f = quant_weight.shape[1] * per
+    tile_cols = -(-in_f // scales.shape[1])
+    w = torch.empty((out_f, in_f), dtype=dtype)
+    m = (1 << bits) - 1
+    for nr in range(per):
+        w[:, nr::per] = ((quant_weight >> (nr * bits)) & m).float()
+    for j in range(scales.size(1)):
+        sl = slice(j * tile_cols, (j + 1) * tile_cols)
+        w[:, sl] -= zeros[:, j : j + 1]
+        w[:, sl] *= scales[:, j : j + 1]
+    return w
+
+
+# NF4 code book of bitsandbytes (third-party, un-vendored; values re-derived from the published
+# construction: normal quantiles).  PARITY UNPINNED: no reference source/tests here.
+NF4_CODE = torch.tensor([
+    -1.0, -0.6961928009986877, -0.5250730514526367, -0.39491748809814453, -0.28444138169288635,
+    -0.18477343022823334, -0.09105003625154495, 0.0, 0.07958029955625534, 0.16093020141124725,
+    0.24611230194568634, 0.33791524171829224, 0.44070982933044434, 0.5626170039176941,
+    0.7229568362236023, 1.0], dtype=torch.float32)
+
+
+def nf4_quantize(w: Tensor, blocksize: int = 64) -> Tuple[Tensor, Tensor]:
+    """PARITY UNPINNED (bitsandbytes `quantize_4bit(quant_type="nf4")`, called through
+    quantize/bnb.py:62-75 / lit_gpt/utils.py:53-60).  Published algorithm: flatten, blocks of 64,
+    absmax per block (fp32), code = nearest NF4 entry of w/absmax, two codes per byte with the FIRST
+    element in the HIGH nibble.  Returns (packed uint8 (n/2,), absmax fp32 (n/blocksize,))."""
+    flat = w.float().reshape(-1, blocksize)
+    absmax = flat.abs().amax(dim=1)
+    normed = flat / absmax.clamp_min(1e-30)[:, None]
+    codes = (normed.reshape(-1, 1) - NF4_CODE[None, :]).abs().argmin(dim=1).to(torch.uint8)
+    packed = (codes[0::2] << 4) | codes[1::2]
+    return packed, absmax
+
+
+def nf4_dequantize(packed: Tensor, absmax: Tensor, shape, blocksize: int = 64, dtype=torch.float32) -> Tensor:
+    """PARITY UNPINNED: w = NF4_CODE[nibble] * absmax[block] (fp32), cast to dtype."""
+    codes = torch.stack(((packed >> 4) & 0xF, packed & 0xF), dim=1).reshape(-1).long()
+    vals = NF4_CODE[codes].reshape(-1, blocksize) * absmax[:, None]
+    return vals.reshape(shape).to(dtype)
+
+
+def int8_quantize(w: Tensor) -> Tuple[Tensor, Tensor]:
+    """PARITY UNPINNED (bitsandbytes row-wise `double_quant`, quantize/bnb.py:52-60): per output row
+    SCB = max|w|, CB = round(127*w/SCB) as int8.  Weight-only restatement: activations stay float,
+    bnb's per-token activation quantisation and >6.0 outlier split are NOT modelled (documented)."""
+    wf = w.float()
+    scb = wf.abs().amax(dim=1).clamp_min(1e-30)
+    cb = torch.round(127.0 * wf / scb[:, None]).clamp_(-127, 127).to(torch.int8)
+    return cb, scb
+
+
+def int8_dequantize(cb: Tensor, scb: Tensor, dtype=torch.float32) -> Tensor:
+    return (cb.float() * (scb[:, None] / 127.0)).to(dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic weights (shared by tests and bench so oracle and product see identical tensors)
+# ----------------------------------------------------------------------------------------------
+def state_dict_shapes(cfg) -> Dict[str, Tuple[int, ...]]:
+    """Key -> shape of the reference ``GPT(config).state_dict()`` (model.py:24-36, 147-156, 183-192, 278-295)."""
+    E, V, I = cfg.n_embd, cfg.padded_vocab_size, cfg.intermediate_size
+    hs = E // cfg.n_head
+    ln = cfg._norm_class == "LayerNorm"
+    out: Dict[str, Tuple[int, ...]] = {"lm_head.weight": (V, E), "transformer.wte.weight": (V, E)}
+
+    def add_norm(p):
+        out[p + ".weight"] = (E,)
+        if ln:
+            out[p + ".bias"] = (E,)
+
+    def add_linear(p, o, i):
+        out[p + ".weight"] = (o, i)
+        if cfg.bias:
+            out[p + ".bias"] = (o,)
+
+    for l in range(cfg.n_layer):
+        p = f"transformer.h.{l}"
+        add_norm(p + ".norm_1")
+        add_linear(p + ".attn.attn", (cfg.n_head + 2 * cfg.n_query_groups) * hs, E)
+        add_linear(p + ".attn.proj", E, E)
+        if not cfg.shared_attention_norm:
+            add_norm(p + ".norm_2")
+        if cfg._mlp_class == "LLaMAMLP":
+            add_linear(p + ".mlp.fc_1", I, E)
+            add_linear(p + ".mlp.fc_2", I, E)
+        else:
+            add_linear(p + ".mlp.fc", I, E)
+        add_linear(p + ".mlp.proj", E, I)
+    add_norm("transformer.ln_f")
+    return out
+
+
+def random_state_dict(cfg, seed: int = 1234, dtype=torch.float32, perturb_norm: bool = False) -> Dict[str, Tensor]:
+    """Random-init weights following ``GPT._init_weights`` (model.py:41-54): Linear/Embedding N(0, 0.02),
+    biases 0, norm weight 1.  With ``perturb_norm`` the norm affine params and linear biases are drawn
+    randomly as well so that tests exercise them."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+    for k, shp in state_dict_shapes(cfg).items():
+        is_norm = ".norm_" in k or ".ln_f." in k
+        if len(shp) == 2:
+            t = torch.randn(shp, generator=g) * 0.02
+        elif is_norm and k.endswith(".weight"):
+            t = 1.0 + (0.1 * torch.randn(shp, generator=g) if perturb_norm else torch.zeros(shp))
+        else:
+            t = 0.02 * torch.randn(shp, generator=g) if perturb_norm else torch.zeros(shp)
+        sd[k] = t.to(dtype)
+    return sd

@@ -1,0 +1,276 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference and pin the oracle restatement to it.
+
+Runs only in the build container (needs /root/reference):
+
+    python oracle/make_golden.py
+
+It imports the reference's `lit_gpt`, `generate.base` and `quantize.gptq` through the stubs in
+oracle/_shims (lightning / lightning_utilities / nltk are not installed), drives them on seeded
+random-init weights, stores inputs + reference outputs as small fixtures, and asserts that
+oracle/lit_oracle.py reproduces every stored output (bit-for-bit where the op order is identical).
+The GPU box has no /root/reference: tests there only read the committed fixtures.
+"""
+import hashlib
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+REF = "/root/reference"
+# the reference's `lit_gpt`/`generate`/`quantize` must win over this repo's drop-in packages
+sys.path = [p for p in sys.path if os.path.abspath(p or ".") != REPO]
+sys.path[:0] = [os.path.join(HERE, "_shims"), REF]
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import generate.base as ref_generate  # noqa: E402  (reference)
+import lit_gpt  # noqa: E402  (reference)
+import quantize.gptq as ref_gptq  # noqa: E402  (reference)
+
+assert lit_gpt.__file__.startswith(REF), lit_gpt.__file__
+
+import importlib.util  # noqa: E402
+
+_spec = importlib.util.spec_from_file_location("lit_oracle", os.path.join(HERE, "lit_oracle.py"))
+oracle = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(oracle)
+
+OUT = os.path.join(REPO, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+TINY = {
+    # NeoX family: parallel residual, two LayerNorms, biases, partial rotary 25 %, MHA
+    "neox": dict(block_size=48, vocab_size=96, padding_multiple=32, n_layer=2, n_head=4, n_embd=64,
+                 rotary_percentage=0.25, parallel_residual=True, bias=True),
+    # RedPajama-like: NeoX with sequential residual and full rotary
+    "neox_seq": dict(block_size=48, vocab_size=96, padding_multiple=32, n_layer=2, n_head=4, n_embd=64,
+                     rotary_percentage=1.0, parallel_residual=False, bias=True),
+    # Falcon-7b-like: MQA, one shared LayerNorm, parallel residual, no linear biases
+    "falcon_mqa": dict(block_size=48, padded_vocab_size=80, n_layer=2, n_head=5, n_embd=80, rotary_percentage=1.0,
+                       parallel_residual=True, n_query_groups=1, bias=False, shared_attention_norm=True),
+    # Falcon-40b-like: GQA, two norms, parallel residual
+    "falcon_gqa": dict(block_size=48, padded_vocab_size=80, n_layer=2, n_head=8, n_embd=128, rotary_percentage=1.0,
+                       parallel_residual=True, n_query_groups=2, bias=False),
+    # Llama-2-7b-like: RMSNorm, SwiGLU, sequential residual, MHA
+    "llama_mha": dict(block_size=48, vocab_size=96, padding_multiple=32, n_layer=2, n_head=4, n_embd=64,
+                      rotary_percentage=1.0, parallel_residual=False, bias=False, _norm_class="RMSNorm",
+                      norm_eps=1e-5, _mlp_class="LLaMAMLP", intermediate_size=176),
+    # Llama-2-70b-like: GQA with 2 groups
+    "llama_gqa": dict(block_size=48, vocab_size=96, padding_multiple=32, n_layer=3, n_head=8, n_embd=128,
+                      n_query_groups=2, rotary_percentage=1.0, parallel_residual=False, bias=False,
+                      _norm_class="RMSNorm", norm_eps=1e-5, _mlp_class="LLaMAMLP", intermediate_size=352),
+    # LongChat-like: condense_ratio
+    "llama_condense": dict(block_size=64, vocab_size=96, padding_multiple=32, n_layer=1, n_head=2, n_embd=64,
+                           rotary_percentage=1.0, parallel_residual=False, bias=False, _norm_class="RMSNorm",
+                           norm_eps=1e-6, _mlp_class="LLaMAMLP", intermediate_size=96, condense_ratio=8),
+}
+
+
+def sd_digest(sd) -> str:
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(sd[k].contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def build_reference(cfg_kwargs, seed, perturb=True):
+    cfg = lit_gpt.Config(**cfg_kwargs)
+    model = lit_gpt.GPT(cfg)
+    sd = oracle.random_state_dict(cfg, seed=seed, perturb_norm=perturb)
+    missing = model.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    model.eval()
+    return cfg, model, sd
+
+
+def check(name, a, b, atol):
+    d = (a.float() - b.float()).abs().max().item()
+    assert d <= atol, f"{name}: oracle differs from reference by {d}"
+    return d
+
+
+@torch.no_grad()
+def tiny_cases():
+    for name, kw in TINY.items():
+        seed = 1234
+        cfg, model, sd = build_reference(kw, seed)
+        g = torch.Generator().manual_seed(1)
+        B, T, steps = 2, 7, 12
+        idx = torch.randint(0, cfg.padded_vocab_size, (B, T), generator=g)
+        max_seq = 32
+        # 1) no-cache forward
+        ref_full = model(idx)
+        # 2) cached prefill + teacher-forced decode steps (B=2 lock-step, model.py:66,131)
+        model.reset_cache()
+        pos = torch.arange(T)
+        ref_prefill = model(idx, max_seq, pos)
+        forced = torch.randint(0, cfg.padded_vocab_size, (steps, B, 1), generator=g)
+        ref_steps = []
+        for s in range(steps):
+            pos = pos[-1:] + 1
+            ref_steps.append(model(forced[s], max_seq, pos))
+        ref_steps = torch.stack(ref_steps)
+        ref_k = torch.stack([kv[0] for kv in model.kv_caches])
+        ref_v = torch.stack([kv[1] for kv in model.kv_caches])
+        # 3) greedy generate (top_k=1 -> a single non-zero probability unless exact ties) incl. the
+        #    sliding-window overflow branch (max_seq_length < tokens generated, model.py:238-242)
+        model.reset_cache()
+        prompt = torch.randint(0, cfg.padded_vocab_size, (5,), generator=g, dtype=torch.int64).to(torch.int32)
+        ref_gen = ref_generate.generate(model, prompt, 30, 30, temperature=1.0, top_k=1)
+        model.reset_cache()
+        ref_gen_overflow = ref_generate.generate(model, prompt, 30, 12, temperature=1.0, top_k=1)
+        model.reset_cache()
+
+        # ---- oracle must reproduce all of it
+        om = oracle.OracleGPT(oracle_cfg(kw), sd)
+        d1 = check(name + "/full", om(idx), ref_full, 0.0)
+        om.reset_cache()
+        pos = torch.arange(T)
+        d2 = check(name + "/prefill", om(idx, max_seq, pos), ref_prefill, 0.0)
+        for s in range(steps):
+            pos = pos[-1:] + 1
+            check(name + f"/step{s}", om(forced[s], max_seq, pos), ref_steps[s], 0.0)
+        check(name + "/kcache", torch.stack([kv[0] for kv in om.kv]), ref_k, 0.0)
+        om.reset_cache()
+        og = oracle.generate(om, prompt, 30, 30, temperature=1.0, top_k=1, argmax_ties=True)
+        assert torch.equal(og, ref_gen), (name, og, ref_gen)
+        om.reset_cache()
+        og2 = oracle.generate(om, prompt, 30, 12, temperature=1.0, top_k=1, argmax_ties=True)
+        assert torch.equal(og2, ref_gen_overflow), (name, og2, ref_gen_overflow)
+        print(f"[golden] {name}: oracle == reference (max diff {max(d1, d2):.1e}); tokens equal")
+
+        G = cfg.n_query_groups
+        qpk = cfg.n_head // G
+        # compact view of the reference cache (one head per query group) for the product's layout
+        kc = ref_k if G == 1 else ref_k[:, :, ::qpk]
+        vc = ref_v if G == 1 else ref_v[:, :, ::qpk]
+        np.savez_compressed(
+            os.path.join(OUT, f"tiny_{name}.npz"),
+            cfg_keys=np.array(list(kw.keys())), cfg_vals=np.array([repr(v) for v in kw.values()]),
+            seed=seed, sd_sha256=sd_digest(sd), idx=idx.numpy(), max_seq=max_seq, forced=forced.numpy(),
+            ref_full=ref_full.numpy(), ref_prefill=ref_prefill.numpy(), ref_steps=ref_steps.numpy(),
+            ref_k_compact=kc.numpy(), ref_v_compact=vc.numpy(), prompt=prompt.numpy(), ref_gen=ref_gen.numpy(),
+            ref_gen_overflow=ref_gen_overflow.numpy(),
+        )
+
+
+def oracle_cfg(kw):
+    """The oracle only needs attribute access; reuse the product's Config (same fields) without importing
+    the product's CUDA side."""
+    spec = importlib.util.spec_from_file_location("lp_config", os.path.join(REPO, "lit_parrot_b200", "config.py"))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules["lp_config"] = m
+    spec.loader.exec_module(m)
+    return m.Config(**kw)
+
+
+@torch.no_grad()
+def preset_table():
+    """Every preset: derived values from the reference Config, to pin lit_parrot_b200.config."""
+    rows = {}
+    for name in lit_gpt.config.name_to_config:
+        c = lit_gpt.Config.from_name(name)
+        rows[name] = [c.block_size, c.vocab_size, c.padded_vocab_size, c.n_layer, c.n_head, c.n_embd,
+                      c.n_query_groups, c.intermediate_size, int(c.rotary_percentage * 1000), int(c.parallel_residual),
+                      int(c.bias), int(c.shared_attention_norm), int(c._norm_class == "RMSNorm"),
+                      int(c._mlp_class == "LLaMAMLP"), c.condense_ratio, int(round(c.norm_eps * 1e9)), c.head_size]
+    names = sorted(rows)
+    np.savez_compressed(os.path.join(OUT, "presets.npz"), names=np.array(names),
+                        table=np.array([rows[n] for n in names], dtype=np.int64),
+                        orgs=np.array([lit_gpt.config.name_to_config[n]["org"] for n in names]))
+    print(f"[golden] presets: {len(names)} configs")
+
+
+@torch.no_grad()
+def pythia70m():
+    """BASELINE config 1: pythia-70m random init, fp32, greedy generate 16 -> 128 tokens on CPU."""
+    cfg = lit_gpt.Config.from_name("pythia-70m")
+    model = lit_gpt.GPT(cfg)
+    sd = oracle.random_state_dict(cfg, seed=1234)
+    model.load_state_dict(sd)
+    model.eval()
+    prompt = torch.randint(0, cfg.vocab_size, (16,), generator=torch.Generator().manual_seed(1)).to(torch.int32)
+    toks = ref_generate.generate(model, prompt, 128, 128, temperature=1.0, top_k=1)
+    # logits of the reference at every decode step (teacher-forced by its own tokens), last row only
+    model.reset_cache()
+    pos = torch.arange(16)
+    lg = [model(toks[:16].view(1, -1).long(), 128, pos)[0, -1]]
+    for t in range(16, 127):
+        pos = pos[-1:] + 1
+        lg.append(model(toks[t].view(1, 1).long(), 128, pos)[0, -1])
+    lg = torch.stack(lg)  # (112, V)
+    top2 = torch.topk(lg, 2, dim=-1).values
+    gaps = (top2[:, 0] - top2[:, 1])
+    assert torch.equal(lg.argmax(-1).to(torch.int32), toks[16:])
+    om = oracle.OracleGPT(oracle_cfg(dict(lit_gpt.config.name_to_config["pythia-70m"])), sd)
+    otoks = oracle.generate(om, prompt, 128, 128, temperature=1.0, top_k=1, argmax_ties=True)
+    assert torch.equal(otoks, toks)
+    # keep the fixture small: logits at 8 probe steps + per-step top-8 (ids + values) + gaps
+    probe = [0, 1, 2, 15, 31, 63, 95, 111]
+    t8 = torch.topk(lg, 8, dim=-1)
+    np.savez_compressed(os.path.join(OUT, "pythia70m_greedy.npz"), seed=1234, prompt=prompt.numpy(),
+                        tokens=toks.numpy(), probe_steps=np.array(probe), probe_logits=lg[probe].numpy(),
+                        top8_ids=t8.indices.numpy().astype(np.int32), top8_vals=t8.values.numpy(),
+                        gaps=gaps.numpy(), sd_sha256=sd_digest(sd))
+    print(f"[golden] pythia-70m: 112 greedy tokens, min top1-top2 gap {gaps.min():.3e}; oracle tokens equal")
+
+
+@torch.no_grad()
+def gptq_cases():
+    """ColBlockQuantizedLinear storage + dequant + forward (quantize/gptq.py:205-264), g=128 and per-row."""
+    g = torch.Generator().manual_seed(7)
+    for tag, tile in (("g128", 128), ("perrow", -1)):
+        out_f, in_f = 48, 384
+        w = torch.randn(out_f, in_f, generator=g) * 0.02
+        lin = ref_gptq.ColBlockQuantizedLinear(in_f, out_f, True, bits=4, tile_cols=tile)
+        packed, scales, zeros = oracle.gptq_rtn_quantize(w, tile)
+        # cross-check the grid against the reference's own find_params_weight on each tile
+        dummy = torch.nn.Linear(in_f, out_f)
+        qz = ref_gptq.GPTQQuantizer(dummy, bits=4, groupsize=tile)
+        tc = in_f if tile == -1 else tile
+        for j in range(scales.shape[1]):
+            s, z = qz.find_params_weight(w[:, j * tc:(j + 1) * tc])
+            assert torch.equal(s, scales[:, j:j + 1]) and torch.equal(z, zeros[:, j:j + 1])
+        lin.scales.copy_(scales)
+        lin.zeros.copy_(zeros)
+        lin.bias.copy_(torch.randn(out_f, generator=g) * 0.02)
+        # the reference packer applied to the on-grid weights must give the same bytes
+        wq = oracle.gptq_dequant(packed, scales, zeros)
+        lin.pack_weight(wq + 1e-4 * scales.repeat_interleave(tc, dim=1)[:, :in_f])  # nudge off truncation edges
+        assert torch.equal(lin.quant_weight, packed), "nibble packing differs from reference pack_weight"
+        assert lin.quant_weight.stride() == (1, out_f)
+        ref_w = lin.get_weight(torch.float32)
+        check(f"gptq/{tag}/dequant", wq, ref_w, 0.0)
+        x = torch.randn(3, in_f, generator=g)
+        y = lin(x)
+        oy = oracle.linear(x, {"l.quant_weight": packed, "l.scales": scales, "l.zeros": zeros, "l.bias": lin.bias}, "l")
+        check(f"gptq/{tag}/forward", oy, y, 0.0)
+        ref_w_bf16 = lin.get_weight(torch.bfloat16)
+        check(f"gptq/{tag}/dequant_bf16", oracle.gptq_dequant(packed, scales, zeros, dtype=torch.bfloat16), ref_w_bf16, 0.0)
+        np.savez_compressed(os.path.join(OUT, f"gptq_{tag}.npz"), w=w.numpy(), quant_weight=packed.contiguous().numpy(),
+                            scales=scales.numpy(), zeros=zeros.numpy(), bias=lin.bias.numpy(), x=x.numpy(), y=y.numpy(),
+                            dequant=ref_w.numpy(), dequant_bf16_as_f32=ref_w_bf16.float().numpy(), tile_cols=tile)
+        print(f"[golden] gptq {tag}: packing, dequant (fp32+bf16) and forward equal to reference")
+
+    # the operator plug-in switch builds a fully quantised GPT (lit_gpt/utils.py:26-83)
+    from lit_gpt.utils import quantization
+
+    with quantization("gptq.int4"):
+        m = lit_gpt.GPT(lit_gpt.Config(**TINY["llama_mha"]))
+    keys = sorted(m.state_dict().keys())
+    assert torch.nn.Linear is not ref_gptq.ColBlockQuantizedLinear
+    np.savez_compressed(os.path.join(OUT, "gptq_statedict_keys.npz"), keys=np.array(keys),
+                        shapes=np.array([repr(tuple(m.state_dict()[k].shape)) for k in keys]))
+    print(f"[golden] gptq plug-in: {len(keys)} state-dict keys recorded")
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    preset_table()
+    tiny_cases()
+    gptq_cases()
+    pythia70m()
+    print("[golden] all fixtures written to", OUT)
