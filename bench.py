@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py — decode throughput of the hot path on B200 (contract: see the task prompt / DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME] [--no-extras]
+
+A "step" is ONE decode step of the hot path (embed -> n_layer blocks -> ln_f -> lm_head -> sampling) over one
+batch; `value` is decoded tokens per second with everything resident in HBM (captured-graph replay, CUDA events);
+`e2e` is the same metric through the public drop-in API (`model(idx, max_seq_length, input_pos)` + `sample`) driven
+from the host with pinned-host token buffers: H2D copy of the token ids and D2H read of the sampled ids every step.
+
+Default workload (N = 1): BASELINE.json configs[1] — stablelm-base-alpha-3b, bf16, batch 1, 2k context.
+N > 1: N independent replicas of the same workload (weak scaling, no collective; the models of configs 1-4 do not
+shard).  Weights are random-init (`_init_weights`: N(0, 0.02)), prompts/KV contents synthetic.
+
+`--impl reference` times the CPU oracle port of the reference (`oracle/lit_oracle.py`, torch CPU ops, all host
+threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    # name: (preset, quantization mode, gptq tile, batch, context)
+    "stablelm-3b-bf16-b1": ("stablelm-base-alpha-3b", None, 0, 1, 2048),
+    "stablelm-3b-bf16-b32": ("stablelm-base-alpha-3b", None, 0, 32, 2048),
+    "llama2-7b-int4g128-b1": ("Llama-2-7b-hf", "gptq.int4", 128, 1, 2048),
+    "llama2-7b-nf4-b1": ("Llama-2-7b-hf", "bnb.nf4", 0, 1, 2048),
+    "llama2-7b-bf16-b1": ("Llama-2-7b-hf", None, 0, 1, 2048),
+    "falcon-7b-bf16-b1": ("falcon-7b", None, 0, 1, 2048),
+    "pythia-70m-bf16-b1": ("pythia-70m", None, 0, 1, 2048),
+}
+DEFAULT = "stablelm-3b-bf16-b1"
+EXTRAS = ["llama2-7b-int4g128-b1", "stablelm-3b-bf16-b32"]
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def build_model(workload: str, device):
+    import torch
+
+    import lit_parrot_b200 as lp
+
+    preset, quant, tile, B, ctx = WORKLOADS[workload]
+    cfg = lp.Config.from_name(preset)
+    torch.manual_seed(1234)
+    with torch.device(device):
+        prev = torch.get_default_dtype()
+        torch.set_default_dtype(torch.bfloat16)
+        try:
+            dense = lp.GPT(cfg)
+        finally:
+            torch.set_default_dtype(prev)
+    dense.apply(dense._init_weights)
+    if quant is None:
+        return dense.eval(), cfg, B, ctx
+    # quantise the same random weights layer by layer (round-to-nearest on the reference grid / NF4 code book)
+    with torch.device(device):
+        with lp.quantization(quant, **({"gptq_tile_cols": tile} if quant == "gptq.int4" else {})):
+            q = lp.GPT(cfg)
+    qmods, dmods = dict(q.named_modules()), dict(dense.named_modules())
+    for name, mod in qmods.items():
+        src = dmods[name]
+        if hasattr(mod, "quantize_rtn_"):
+            mod.quantize_rtn_(src.weight.data.float())
+            src.weight.data = torch.empty(0, device=device)
+        elif isinstance(mod, (torch.nn.Linear, torch.nn.Embedding)) or type(mod).__name__ in ("RMSNorm", "LayerNorm"):
+            for pn, p in mod.named_parameters(recurse=False):
+                p.data = getattr(src, pn).data.to(torch.bfloat16)
+    q = q.to(torch.bfloat16) if quant != "gptq.int4" else q
+    del dense
+    torch.cuda.empty_cache()
+    return q.eval(), cfg, B, ctx
+
+
+def algorithmic_bytes_per_step(eng, cfg, B, kv_len_avg, kv_elem_bytes):
+    """weights of every linear at stored width (+scales/zeros/absmax) + one embedding row per sequence
+    + compact KV read B*2*L*G*hs*bytes*(pos+1) + KV write."""
+    w = eng.weight_bytes_per_token() + (B - 1) * cfg.n_embd * eng.wte.element_size()
+    kv_row = 2 * cfg.n_layer * cfg.n_query_groups * cfg.head_size * kv_elem_bytes
+    return w, B * kv_row * kv_len_avg + B * kv_row
+
+
+def run_workload(workload, steps, warmup, device, rank=0, world=1, with_e2e=True, with_kernel=True):
+    import torch
+    import torch.distributed as dist
+
+    import lit_parrot_b200 as lp
+    from lit_parrot_b200 import _lib
+
+    model, cfg, B, ctx = build_model(workload, device)
+    lib = _lib.init(device.index)
+    V = cfg.padded_vocab_size
+    start = ctx - steps - warmup - 1
+    assert start > 0, "context too short for steps + warmup"
+    # synthetic KV cache filled up to `start` positions; decoding continues from there
+    model.kv_caches = model.build_kv_caches(torch.zeros(B, 1, device=device), ctx)
+    for k, v in model.kv_caches:
+        k[:, :, :start].normal_(0, 1)
+        v[:, :, :start].normal_(0, 1)
+    gen = torch.Generator(device="cpu").manual_seed(1 + rank)
+    tok0 = torch.randint(0, cfg.vocab_size, (B, 1), generator=gen)
+
+    def sync_barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---- device-resident loop: ONE captured graph per step (forward + on-device greedy sampling for B == 1) -------
+    count0 = lib.lp_launch_count()
+    pos = torch.tensor([start], device=device)
+    model(tok0.to(device), ctx, pos)  # builds engine + rope, warm-up run + graph capture of one forward step
+    eng = model._get_engine(device)
+    launches_per_step = (lib.lp_launch_count() - count0) // 2 + 1  # (warm-up + capture) / 2, + the sampling kernel
+    st = eng.gen_state(cfg.block_size)
+    st["seq"].zero_()
+    st["seq"][start + 1] = int(tok0[0, 0])
+    st["pos"].fill_(start + 1)
+    replay = eng.decode_step(model.kv_caches, 1.0, 1, 1234, B)
+    if B > 1:
+        st["tok"][:B].copy_(tok0[:, 0])
+    for _ in range(warmup):
+        replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_barrier()
+    with ClockSampler(device.index) as clk:
+        e0.record()
+        for _ in range(steps):
+            replay()
+        e1.record()
+        sync_barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tms = torch.tensor([ms], device=device)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms)
+    kv_b = model.kv_caches[0][0].element_size()
+    wbytes, kvbytes = algorithmic_bytes_per_step(eng, cfg, B, start + warmup + steps / 2 + 1, kv_b)
+    res = {"workload": workload, "ms_per_step": ms / steps, "tok_s": world * B * steps / (ms / 1e3),
+           "launches_per_step": int(launches_per_step), "bytes_per_step": {"weights": int(wbytes), "kv": int(kvbytes)},
+           "step_gbs": (wbytes + kvbytes) / (ms / steps) / 1e6, "clocks": clk.summary(), "B": B, "ctx": ctx}
+
+    # ---- e2e: public API driven from the host; H2D token ids + D2H sampled ids every step -----------------------
+    if with_e2e:
+        model.reset_cache()
+        model.kv_caches = model.build_kv_caches(torch.zeros(B, 1, device=device), ctx)
+        for k, v in model.kv_caches:
+            k[:, :, :start].normal_(0, 1)
+            v[:, :, :start].normal_(0, 1)
+        h_idx = tok0.clone().pin_memory()
+        h_pos = torch.tensor([start], dtype=torch.int64).pin_memory()
+        h_out = torch.empty(B, dtype=torch.int32).pin_memory()
+
+        def e2e_step():
+            x = h_idx.to(device, non_blocking=True)
+            p = h_pos.to(device, non_blocking=True)
+            lg = model(x, ctx, p)
+            t = lp.sample(lg[:, -1], 1.0, 1)
+            h_out.copy_(t, non_blocking=True)
+            torch.cuda.current_stream(device).synchronize()
+            h_idx[:, 0] = h_out.long()
+            h_pos += 1
+
+        for _ in range(warmup):
+            e2e_step()
+        sync_barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            e2e_step()
+        sync_barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tdt = torch.tensor([dt], device=device)
+            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+            dt = float(tdt)
+        res["e2e"] = {"value": world * B * steps / dt, "unit": "tok/s", "h2d_bytes_per_step": int(B * 8 + 8),
+                      "d2h_bytes_per_step": int(B * 4)}
+
+    # ---- dominant kernel alone: lp_linear on the MLP up-projection, rotating over the layers' weights (>> L2) ------
+    if with_kernel:
+        res["kernel"] = time_dominant_kernel(eng, cfg, B, device)
+    del model
+    torch.cuda.empty_cache()
+    return res
+
+
+def time_dominant_kernel(eng, cfg, B, device, iters=64):
+    import torch
+
+    from lit_parrot_b200 import _lib
+
+    lib = eng.lib
+    x = torch.randn(B, cfg.n_embd, device=device)
+    out = torch.empty(B, cfg.intermediate_size * (1 if eng.act != _lib.LP_EPI_SWIGLU else 1), device=device)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    layers = eng.layers
+    for i in range(8):
+        L = layers[i % len(layers)]
+        _lib.check(lib.lp_linear(x.data_ptr(), B, L.fc.ref, eng.act, None, out.data_ptr(), eng.round, stream))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(device)
+    e0.record()
+    for i in range(iters):
+        L = layers[i % len(layers)]
+        _lib.check(lib.lp_linear(x.data_ptr(), B, L.fc.ref, eng.act, None, out.data_ptr(), eng.round, stream))
+    e1.record()
+    torch.cuda.synchronize(device)
+    us = e0.elapsed_time(e1) * 1e3 / iters
+    nbytes = layers[0].fc.stored_bytes
+    return {"name": "lp_linear(mlp.fc)", "N": layers[0].fc.N, "K": layers[0].fc.K, "us": us, "bytes": int(nbytes),
+            "gbs": nbytes / us / 1e3}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_oracle_decode(workload, max_steps, warmup, budget_s=75.0):
+    """The reference's CPU path (oracle port, torch CPU fp32, all host threads) on a bounded sample: short prefill,
+    then decode steps at short context.  Returns (tok/s, steps timed, threads, description)."""
+    import torch
+
+    import lit_parrot_b200 as lp
+    from oracle import lit_oracle as O
+
+    preset, quant, tile, B, ctx = WORKLOADS[workload]
+    cfg = lp.Config.from_name(preset)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    t_build = time.perf_counter()
+    g = torch.Generator().manual_seed(1234)
+    pool = torch.empty(1 << 24).normal_(0, 0.02, generator=g)  # timing does not depend on the values: cycle a random pool
+    sd = {}
+    for k, shp in O.state_dict_shapes(cfg).items():
+        if len(shp) == 2:
+            n = shp[0] * shp[1]
+            sd[k] = pool.repeat(-(-n // pool.numel()))[:n].view(shp).clone() if n > pool.numel() else pool[:n].view(shp).clone()
+        else:
+            sd[k] = torch.ones(shp) if k.endswith("weight") else torch.zeros(shp)
+    if quant == "gptq.int4":
+        for k in [k for k in sd if sd[k].dim() == 2 and "wte" not in k]:
+            base = k[: -len(".weight")]
+            sd[base + ".quant_weight"], sd[base + ".scales"], sd[base + ".zeros"] = O.gptq_rtn_quantize(sd.pop(k), tile)
+    m = O.OracleGPT(cfg, sd)
+    t_build = time.perf_counter() - t_build
+    T0 = 16
+    idx = torch.randint(0, cfg.vocab_size, (B, T0), generator=g)
+    pos = torch.arange(T0)
+    with torch.no_grad():
+        lg = m(idx, 64, pos)
+        tok = lg[:, -1].argmax(-1, keepdim=True)
+        for _ in range(max(1, min(warmup, 2))):
+            pos = pos[-1:] + 1
+            tok = m(tok, 64, pos)[:, -1].argmax(-1, keepdim=True)
+        n, t0 = 0, time.perf_counter()
+        while n < max_steps and pos[-1] < 62 and (time.perf_counter() - t0) < budget_s:
+            pos = pos[-1:] + 1
+            tok = m(tok, 64, pos)[:, -1].argmax(-1, keepdim=True)
+            n += 1
+        dt = time.perf_counter() - t0
+    desc = (f"{preset} fp32 weights on CPU ({'int4 g128 dequant+F.linear per call, ' if quant else ''}oracle port of the reference, "
+            f"torch {torch.__version__}), batch {B}, 16-token prefill then {n} greedy decode steps at context 17-{17 + n} "
+            f"(not 2k: bounded sample), {threads} threads; weight build {t_build:.0f}s not timed")
+    return B * n / dt, n, threads, desc
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    preset, quant, tile, B, ctx = WORKLOADS[args.workload]
+    base = {"metric": "decode_tokens_per_second", "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if quant is None else f"bf16 activations-in-fp32 / {quant} weights", "data": "synthetic",
+            "config": {"workload": f"{preset} {'bf16' if quant is None else quant} decode, batch {B}, context {ctx} "
+                                   f"(positions {ctx - args.steps - args.warmup - 1}..{ctx - 1})",
+                       "weights": "random init N(0,0.02) (_init_weights), seed 1234", "kv_cache": "synthetic N(0,1) prefix, bf16, compact (B,G,ctx,hs)",
+                       "l2": "inputs larger than L2 (weights streamed per step >> 126 MB)",
+                       "parallelism": "1 GPU" if args.gpus == 1 else f"{args.gpus} independent replicas (no collective)"}}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        v, n, threads, desc = cpu_oracle_decode(args.workload, args.steps, args.warmup)
+        line = dict(base, impl="reference", value=v, steps=n, ms_per_step=1e3 * B / v, n_gpus=args.gpus,
+                    cpu_baseline={"value": v, "unit": "tok/s", "cores": threads, "kind": "port", "sample": desc},
+                    e2e={"value": v, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0)
+        line["dtype"] = "f32"
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (use --impl reference for the CPU arm)"
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    res = run_workload(args.workload, args.steps, args.warmup, device, rank, world)
+    extras = []
+    if not args.no_extras and world == 1:
+        for w in EXTRAS:
+            if w != args.workload:
+                try:
+                    extras.append(run_workload(w, args.steps, args.warmup, device, with_e2e=False))
+                except Exception as e:  # an extra must never cost the headline line
+                    extras.append({"workload": w, "error": repr(e)[:200]})
+    if rank == 0:
+        peak, peak_src = peaks()
+        k = res["kernel"]
+        line = dict(base, value=res["tok_s"], ms_per_step=res["ms_per_step"], e2e=res["e2e"],
+                    gpu_launches=res["launches_per_step"] * args.steps, clocks=res["clocks"],
+                    roofline={"bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s", "frac": k["gbs"] / peak,
+                              "traffic": None, "kernel": f"{k['name']} N={k['N']} K={k['K']}: {k['bytes']} B in {k['us']:.2f} us",
+                              "peak_source": peak_src,
+                              "whole_step": {"achieved": res["step_gbs"], "frac": res["step_gbs"] / peak,
+                                             "bytes": res["bytes_per_step"], "launches": res["launches_per_step"]}})
+        if extras:
+            line["also"] = [{kk: e[kk] for kk in e if kk in ("workload", "tok_s", "ms_per_step", "step_gbs", "launches_per_step",
+                                                              "bytes_per_step", "kernel", "error")} for e in extras]
+            for e in line["also"]:
+                if "step_gbs" in e:
+                    e["step_frac"] = e["step_gbs"] / peak
+        if not args.no_cpu_baseline and world == 1:
+            v, n, threads, desc = cpu_oracle_decode(args.workload, 24, 2, budget_s=25.0)
+            line["cpu_baseline"] = {"value": v, "unit": "tok/s", "cores": threads, "kind": "port", "sample": desc}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

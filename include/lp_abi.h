@@ -1,0 +1,147 @@
+/*
+ * lp_abi.h — C ABI of liblitparrot_b200.so: hand-written sm_100a CUDA kernels for the Lit-GPT
+ * inference hot path (lit_gpt.model.GPT.forward with KV caches + generate/base.py::generate).
+ *
+ * The reference (griff4692/lit-parrot) is pure Python and has NO FFI: every device operation on
+ * this path is an aten / library call issued from lit_gpt/model.py and generate/base.py.  Each entry
+ * point below therefore cites the reference *Python* lines whose device work it replaces; the
+ * Python-side binding a maintainer adds is the ctypes stub in INTEGRATION.md
+ * (lit_parrot_b200/_lib.py is that stub, in full).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch tensors on the Python side);
+ *     the library never allocates, frees or synchronises, so every call is CUDA-graph capturable;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - activations are fp32 row-major [rows, dim]; `round_bf16 != 0` rounds results to bf16 precision
+ *     at exactly the points where the reference's `bf16-true` mode rounds (values stay in fp32 storage);
+ *   - return value: 0 (LP_OK) or a negative lp_status; lp_status_str() names it.  No exceptions,
+ *     no global mutable state apart from the one-time attribute setup in lp_init().
+ */
+#ifndef LP_ABI_H
+#define LP_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LP_ABI_VERSION 1
+
+typedef enum {
+  LP_OK = 0,
+  LP_ERR_INVALID_ARG = -1,   /* bad enum / null pointer / non-positive size                 */
+  LP_ERR_UNSUPPORTED = -2,   /* shape or alignment the kernels do not cover                 */
+  LP_ERR_CUDA = -3,          /* a CUDA runtime call failed (see lp_last_cuda_error)          */
+  LP_ERR_WORKSPACE = -4      /* caller-provided workspace too small                          */
+} lp_status;
+
+/* storage types of tensors that are not fp32 activations */
+typedef enum { LP_F32 = 0, LP_BF16 = 1 } lp_dtype;
+
+/* weight formats of a linear layer, W is logically [N, K] (out_features, in_features) */
+typedef enum {
+  LP_W_F32 = 0,   /* float  [N,K] row-major (nn.Linear.weight)                                          */
+  LP_W_BF16 = 1,  /* bf16   [N,K] row-major (nn.Linear.weight)                                          */
+  LP_W_INT4 = 2,  /* GPTQ int4, repacked by lp_repack_gptq_int4: [N, Kp/2] bytes row-major, byte j of a
+                     row holds column 2j (low nibble) and 2j+1 (high nibble); Kp = K rounded up to 128;
+                     scales/zeros fp32 [N, n_groups]; w = (q - zero) * scale   (quantize/gptq.py:243-252) */
+  LP_W_NF4 = 3,   /* bitsandbytes NF4: bytes [N*K/2], first element in the HIGH nibble, absmax fp32 per
+                     `group` (=blocksize 64) consecutive elements of the flattened weight               */
+  LP_W_INT8 = 4   /* int8 [N,K] row-major, scales fp32 [N] = SCB/127 (row-wise absmax quantisation)      */
+} lp_wfmt;
+
+typedef enum {
+  LP_EPI_NONE = 0,      /* out[M,N]   = y                                                               */
+  LP_EPI_GELU = 1,      /* out[M,N]   = gelu_erf(y)                      (model.py:285-286)              */
+  LP_EPI_SWIGLU = 2,    /* out[M,N/2] = silu(y[2i]) * y[2i+1]; W rows interleaved fc_1/fc_2 (model.py:298-300) */
+  LP_EPI_RESIDUAL = 3   /* out[M,N]   = residual + y                     (model.py:171, 178-179)         */
+} lp_epilogue;
+
+typedef enum { LP_NORM_LAYERNORM = 0, LP_NORM_RMS = 1 } lp_norm_kind;
+
+/* One linear layer's weights.  `aux0`/`aux1`: INT4 -> scales/zeros; NF4 -> absmax/unused; INT8 -> row scales. */
+typedef struct {
+  const void* w;
+  const float* aux0;
+  const float* aux1;
+  const float* bias;   /* fp32 [N] or NULL                                                              */
+  int32_t fmt;         /* lp_wfmt                                                                       */
+  int32_t N, K;
+  int32_t group;       /* INT4: columns per scale/zero group (K for per-row); NF4: blocksize            */
+} lp_weight;
+
+int lp_abi_version(void);
+const char* lp_status_str(int status);
+const char* lp_last_cuda_error(void);
+
+/* Number of kernels this library has launched (or recorded into a graph under stream capture) since load. */
+unsigned long long lp_launch_count(void);
+
+/* Programmatic Dependent Launch on/off (default on; env LP_PDL=0 disables).  Debug aid. */
+int lp_set_pdl(int enabled);
+
+/* Which kernel family lp_linear uses: 0 = auto (tensor-core MMA family where it applies, else FMA), 1 = FMA family
+ * only (exact fp32 CUDA-core math), 2 = MMA family only (LP_ERR_UNSUPPORTED where it does not apply).  Test aid. */
+int lp_set_linear_path(int path);
+
+/* One-time per-device setup (cudaFuncSetAttribute for large dynamic shared memory).  Idempotent, thread-safe. */
+int lp_init(int device);
+
+/* replaces nn.Embedding `self.transformer.wte(idx)` (model.py:99).  idx: int32 or int64 [rows]; if idx_offset is
+ * non-NULL the rows are idx[*idx_offset + r] (device-side position, so a captured decode step can be replayed). */
+int lp_embed(const void* idx, int idx_is_int64, const int32_t* idx_offset, const void* wte, int wte_dtype, float* out,
+             int rows, int E, int round_bf16, void* stream);
+
+/* replaces `config.norm_class` forward: torch.nn.LayerNorm / lit_gpt/rmsnorm.py:17-21 (model.py:109,167,169,179).
+ * weight/bias fp32 [E] (bias NULL for RMSNorm).  round_bf16: LayerNorm output rounded; RMSNorm evaluated with
+ * the reference's input-dtype roundings (x*x, mean, +eps, rsqrt, x*r, w*xn each rounded to bf16). */
+int lp_norm(int kind, const float* x, const float* weight, const float* bias, float eps, float* y, int rows, int E,
+            int round_bf16, void* stream);
+
+/* replaces nn.Linear / ColBlockQuantizedLinear.forward (quantize/gptq.py:254-264) / bnb Linear4bit, Linear8bitLt
+ * (quantize/bnb.py:18-75) at model.py:111,205,252,285-287,298-301, with the elementwise tail fused:
+ *   y = x[M,K] . W[N,K]^T + bias ; out = epilogue(y [, residual]).
+ * Weight-streaming kernel for small M (decode, M = batch); M > LP_LINEAR_MAX_M is processed in row chunks. */
+int lp_linear(const float* x, int M, const lp_weight* W, int epilogue, const float* residual, float* out,
+              int round_bf16, void* stream);
+
+/* replaces the q/k regroup + apply_rope + torch.cat + cache index_copy_ of CausalSelfAttention.forward
+ * (model.py:208-245, 330-336).  qkv [B*T, (H+2G)*hs] rows group-interleaved [q x q_per_kv, k, v] (model.py:210-214);
+ * cos/sin fp32 [block_size, n_elem]; pos int32 [T] (shared by the batch, model.py:88-92).
+ * q_out [B*T, H*hs] (head-major, rotated).  k/v cache [B, G, max_seq, hs] in kv_dtype, compact (one head per
+ * query group); slot = pos % max_seq — a ring index replaces the reference's physical roll (model.py:238-242). */
+int lp_rope_kv_append(const float* qkv, const float* cos, const float* sin, const int32_t* pos, float* q_out,
+                      void* k_cache, void* v_cache, int kv_dtype, int B, int T, int H, int G, int hs, int n_elem,
+                      int max_seq, int round_bf16, void* stream);
+
+/* replaces `scaled_dot_product_attention(q, k_cache, v_cache, attn_mask)` (model.py:247, 256-275) for queries
+ * against the KV cache: split-K over sequence blocks, warp-shuffle online softmax, all q heads of one KV group in
+ * one CTA (MHA/GQA/MQA).  Query row r = b*T + t attends to min(pos[t]+1, max_seq) cache slots.
+ * out [B*T, H*hs].  workspace: lp_attn_workspace_bytes(). */
+size_t lp_attn_workspace_bytes(int B, int T, int H, int hs, int max_seq);
+int lp_attn_decode(const float* q, const void* k_cache, const void* v_cache, int kv_dtype, const int32_t* pos,
+                   float* out, void* workspace, size_t workspace_bytes, int B, int T, int H, int G, int hs,
+                   int max_seq, float scale, int round_bf16, void* stream);
+
+/* replaces the sampling tail of generate() (generate/base.py:136-153): logits/temperature, top-k threshold
+ * (ties with the k-th value survive), softmax, one multinomial draw (exponential race, Philox keyed by
+ * (seed, *step)).  top_k == 1 is lowest-index arg-max.  logits fp32 [rows, V] -> token_out int32 [rows].
+ * If pos_inout != NULL the kernel advances the device-side position: *pos_inout += 1 (and, when seq_buf != NULL,
+ * rows == 1: seq_buf[*pos_inout + 1] = token first), and for rows == 1 *step += 1 — so a captured decode step can be
+ * replayed without host round trips (generate/base.py:147-153). */
+int lp_sample(const float* logits, int rows, int V, float temperature, int top_k, uint64_t seed, int32_t* step,
+              int32_t* token_out, int32_t* seq_buf, int32_t* pos_inout, void* stream);
+
+/* load-time: reference GPTQ storage (uint8 (N, K/2) with strides (1, N), quantize/gptq.py:216-222) ->
+ * LP_W_INT4 layout.  dst holds N * lp_int4_row_bytes(K) bytes. */
+size_t lp_int4_row_bytes(int K);
+int lp_repack_gptq_int4(const uint8_t* quant_weight_colmajor, uint8_t* dst, int N, int K, void* stream);
+
+#define LP_LINEAR_MAX_M 8
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LP_ABI_H */

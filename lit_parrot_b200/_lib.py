@@ -1,0 +1,91 @@
+"""ctypes binding of liblitparrot_b200.so (the C ABI declared in include/lp_abi.h).
+
+This file is the complete "reference-side binding": the reference is Python, so what a maintainer adds to
+call the library is exactly these ctypes prototypes.  There is NO fallback: if the
+shared library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+import threading
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblitparrot_b200.so")
+
+# enums of lp_abi.h
+LP_F32, LP_BF16 = 0, 1
+LP_W_F32, LP_W_BF16, LP_W_INT4, LP_W_NF4, LP_W_INT8 = 0, 1, 2, 3, 4
+LP_EPI_NONE, LP_EPI_GELU, LP_EPI_SWIGLU, LP_EPI_RESIDUAL = 0, 1, 2, 3
+LP_NORM_LAYERNORM, LP_NORM_RMS = 0, 1
+LP_ABI_VERSION = 1
+
+c_void_p, c_int, c_float, c_size_t, c_u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_uint64
+
+
+class LpWeight(ctypes.Structure):
+    """struct lp_weight"""
+
+    _fields_ = [("w", c_void_p), ("aux0", c_void_p), ("aux1", c_void_p), ("bias", c_void_p), ("fmt", ctypes.c_int32),
+                ("N", ctypes.c_int32), ("K", ctypes.c_int32), ("group", ctypes.c_int32)]
+
+
+# name -> (restype, argtypes); every symbol declared in include/lp_abi.h
+PROTOTYPES = {
+    "lp_abi_version": (c_int, []),
+    "lp_status_str": (ctypes.c_char_p, [c_int]),
+    "lp_last_cuda_error": (ctypes.c_char_p, []),
+    "lp_launch_count": (ctypes.c_ulonglong, []),
+    "lp_set_pdl": (c_int, [c_int]),
+    "lp_set_linear_path": (c_int, [c_int]),
+    "lp_init": (c_int, [c_int]),
+    "lp_embed": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "lp_norm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "lp_linear": (c_int, [c_void_p, c_int, ctypes.POINTER(LpWeight), c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "lp_rope_kv_append": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                  c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "lp_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "lp_attn_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int,
+                               c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "lp_sample": (c_int, [c_void_p, c_int, c_int, c_float, c_int, c_u64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lp_int4_row_bytes": (c_size_t, [c_int]),
+    "lp_repack_gptq_int4": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+}
+
+_lock = threading.Lock()
+_lib: Optional[ctypes.CDLL] = None
+_inited_devices = set()
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the library and bind every prototype.  Does not touch the GPU."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: build it with `python -m lit_parrot_b200.build` (needs nvcc, sm_100a). "
+                    "lit_parrot_b200 has no CPU or PyTorch fallback.")
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in PROTOTYPES.items():
+                fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+                fn.restype, fn.argtypes = res, args
+            if lib.lp_abi_version() != LP_ABI_VERSION:
+                raise RuntimeError(f"ABI mismatch: library {lib.lp_abi_version()} vs binding {LP_ABI_VERSION}")
+            _lib = lib
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        lib = load()
+        msg = lib.lp_status_str(status).decode()
+        detail = lib.lp_last_cuda_error().decode() if status == -3 else ""
+        raise RuntimeError(f"liblitparrot_b200: {what} failed with {msg} {detail}".rstrip())
+
+
+def init(device_index: int) -> ctypes.CDLL:
+    lib = load()
+    if device_index not in _inited_devices:
+        check(lib.lp_init(device_index), "lp_init")
+        _inited_devices.add(device_index)
+    return lib

@@ -1,0 +1,136 @@
+// On-device sampling tail of generate() (generate/base.py:136-153).
+//
+//   logits / temperature -> keep everything >= the k-th largest value (ties survive, base.py:139-141)
+//   -> softmax -> one multinomial draw.
+// torch.multinomial on CUDA is an exponential race: argmax(p_i / E_i), E_i ~ Exp(1).  Taking logs, that
+// is argmax(l_i - log E_i) over the kept logits — the softmax normalisation cancels, so the kernel never
+// forms probabilities.  E_i comes from Philox4x32-10 keyed by (seed, step, i).  top_k == 1 (the
+// reference's "greedy") is a plain arg-max with lowest-index tie-break.
+// One CTA per row; the k-th value is found by an 8-bit radix select over order-preserving keys.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace lp {
+
+constexpr int SAMPLE_THREADS = 1024;
+
+__device__ __forceinline__ uint32_t float_key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+struct Best {
+  float v;
+  int i;
+};
+__device__ __forceinline__ Best better(Best a, Best b) {
+  if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+  return a;
+}
+
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+sample_kernel(const float* __restrict__ logits, int V, float temperature, int top_k, uint64_t seed, int* __restrict__ step,
+              int* __restrict__ token_out, int* __restrict__ seq_buf, int* __restrict__ pos_inout) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int s_prefix, s_krem;
+  __shared__ Best s_best[SAMPLE_THREADS / 32];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const float* lg = logits + (size_t)row * V;
+  const bool greedy = (top_k == 1);
+
+  uint32_t thr_key = 0;  // keep everything
+  if (!greedy && top_k > 0 && top_k < V) {
+    // radix select of the top_k-th largest key, 8 bits per pass from the top
+    if (tid == 0) {
+      s_prefix = 0;
+      s_krem = (unsigned)top_k;
+    }
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      for (int i = tid; i < 256; i += SAMPLE_THREADS) hist[i] = 0;
+      __syncthreads();
+      const uint32_t prefix = s_prefix;
+      const uint32_t mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+      for (int i = tid; i < V; i += SAMPLE_THREADS) {
+        const uint32_t k = float_key(lg[i] / temperature);
+        if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 0xff], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        unsigned krem = s_krem, cum = 0;
+        int d = 255;
+        for (; d > 0; --d) {
+          if (cum + hist[d] >= krem) break;
+          cum += hist[d];
+        }
+        s_krem = krem - cum;
+        s_prefix = prefix | ((uint32_t)d << shift);
+      }
+      __syncthreads();
+    }
+    thr_key = s_prefix;
+  }
+
+  const int st = step ? *step : 0;
+  Best best = {-CUDART_INF_F, 0x7fffffff};
+  for (int i = tid; i < V; i += SAMPLE_THREADS) {
+    float l = lg[i] / temperature;
+    if (!greedy) {
+      if (float_key(l) < thr_key) continue;
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)st, (uint32_t)row, 0u),
+                                    make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+      const float u = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0, 1)
+      l = l - logf(-logf(u));
+    }
+    best = better(best, Best{l, i});
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Best other = {__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
+    best = better(best, other);
+  }
+  if ((tid & 31) == 0) s_best[tid >> 5] = best;
+  __syncthreads();
+  if (tid < 32) {
+    best = s_best[tid];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      Best other = {__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
+      best = better(best, other);
+    }
+    if (tid == 0) {
+      token_out[row] = best.i;
+      if (row == 0 && pos_inout) {  // no other CTA of this kernel reads *pos_inout
+        const int p = *pos_inout;
+        if (seq_buf) seq_buf[p + 1] = best.i;
+        *pos_inout = p + 1;
+      }
+      if (step && gridDim.x == 1) *step = st + 1;  // multi-row callers advance the Philox step themselves
+    }
+  }
+}
+
+}  // namespace lp
+
+extern "C" int lp_sample(const float* logits, int rows, int V, float temperature, int top_k, uint64_t seed, int32_t* step,
+                         int32_t* token_out, int32_t* seq_buf, int32_t* pos_inout, void* stream) {
+  if (!logits || !token_out || rows <= 0 || V <= 0 || !(temperature > 0.f) || top_k < 0) return LP_ERR_INVALID_ARG;
+  if (seq_buf && (rows != 1 || !pos_inout)) return LP_ERR_INVALID_ARG;  // pos_inout alone (any rows): just advance
+  return lp::launch(lp::sample_kernel, dim3(rows), dim3(lp::SAMPLE_THREADS), 0, stream, logits, V, temperature, top_k, seed, step,
+                    token_out, seq_buf, pos_inout);
+}

@@ -1,0 +1,343 @@
+"""Host-side driver: packs a GPT's parameters into `lp_weight` records and issues the C-ABI calls of one
+forward pass (reference call order: GPT.forward model.py:63-111 -> Block.forward 158-180 ->
+CausalSelfAttention.forward 194-254 -> MLP 284-301).  PyTorch is used for device memory, streams and CUDA-graph
+capture only; every arithmetic operation on the path is a kernel of liblitparrot_b200.so.
+"""
+import ctypes
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from lit_parrot_b200 import _lib
+from lit_parrot_b200._lib import LpWeight
+
+_FMT_OF_DTYPE = {torch.float32: _lib.LP_W_F32, torch.bfloat16: _lib.LP_W_BF16}
+_KV_OF_DTYPE = {torch.float32: _lib.LP_F32, torch.bfloat16: _lib.LP_BF16}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class PackedLinear:
+    """One linear layer as the kernels see it.  Keeps the tensors alive that the raw pointers refer to."""
+
+    def __init__(self, w: torch.Tensor, fmt: int, N: int, K: int, bias: Optional[torch.Tensor] = None,
+                 aux0: Optional[torch.Tensor] = None, aux1: Optional[torch.Tensor] = None, group: int = 0) -> None:
+        assert w.is_contiguous()
+        self.keep = (w, bias, aux0, aux1)
+        self.N, self.K, self.fmt = N, K, fmt
+        self.rec = LpWeight(_ptr(w), _ptr(aux0), _ptr(aux1), _ptr(bias), fmt, N, K, group)
+        self.ref = ctypes.byref(self.rec)
+
+    @property
+    def stored_bytes(self) -> int:
+        """Bytes a decode step must stream for this layer (weights + scales/zeros/absmax)."""
+        w, _bias, aux0, aux1 = self.keep
+        return sum(t.numel() * t.element_size() for t in (w, aux0, aux1) if t is not None)
+
+
+def _f32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    return None if t is None else t.detach().to(torch.float32).contiguous()
+
+
+def pack_linear(mod: torch.nn.Module) -> PackedLinear:
+    """nn.Linear (fp32 / bf16) is used in place; quantised modules provide their own packing."""
+    if hasattr(mod, "lp_pack"):
+        return mod.lp_pack()
+    w = mod.weight.data
+    if w.dtype not in _FMT_OF_DTYPE:
+        raise RuntimeError(f"unsupported parameter dtype {w.dtype}: use float32 or bfloat16")
+    if not w.is_contiguous():
+        w = w.contiguous()
+        mod.weight.data = w
+    return PackedLinear(w, _FMT_OF_DTYPE[w.dtype], w.shape[0], w.shape[1], bias=_f32(getattr(mod, "bias", None)))
+
+
+def pack_swiglu(fc_1: torch.nn.Module, fc_2: torch.nn.Module) -> PackedLinear:
+    """fc_1 / fc_2 (model.py:293-300) as ONE weight with interleaved rows (2i = fc_1 row i, 2i+1 = fc_2 row i) so a warp
+    produces silu(a)*b without a round trip.  The parameters are re-pointed at strided views of the interleaved
+    storage, so nothing is duplicated and `state_dict()` / `load_state_dict()` keep working."""
+    if hasattr(fc_1, "lp_pack_pair"):
+        return fc_1.lp_pack_pair(fc_2)
+    w1, w2 = fc_1.weight.data, fc_2.weight.data
+    if w1.dtype not in _FMT_OF_DTYPE:
+        raise RuntimeError(f"unsupported parameter dtype {w1.dtype}: use float32 or bfloat16")
+    I, E = w1.shape
+    already = (w1.stride() == (2 * E, 1) and w2.stride() == (2 * E, 1)
+               and w2.data_ptr() == w1.data_ptr() + E * w1.element_size())
+    if already:
+        inter = torch.as_strided(w1, (2 * I, E), (E, 1))
+    else:
+        inter = torch.empty((2 * I, E), dtype=w1.dtype, device=w1.device)
+        inter[0::2].copy_(w1)
+        inter[1::2].copy_(w2)
+        fc_1.weight.data = inter[0::2]
+        fc_2.weight.data = inter[1::2]
+    bias = None
+    if getattr(fc_1, "bias", None) is not None:
+        bias = torch.stack((fc_1.bias.data.float(), fc_2.bias.data.float()), dim=1).reshape(-1).contiguous()
+    return PackedLinear(inter, _FMT_OF_DTYPE[inter.dtype], 2 * I, E, bias=bias)
+
+
+class _Layer:
+    pass
+
+
+class Engine:
+    def __init__(self, model, device: torch.device) -> None:
+        self.device = device
+        self.precision = model.precision
+        self.use_graph = bool(model.use_cuda_graph)
+        self.round = 1 if model.precision == "bf16" else 0
+        self.cfg = cfg = model.config
+        self.lib = _lib.init(device.index if device.index is not None else torch.cuda.current_device())
+        self.param_dtype = model.transformer.wte.weight.dtype
+        if self.param_dtype not in _FMT_OF_DTYPE:
+            raise RuntimeError(f"unsupported parameter dtype {self.param_dtype}: use float32 or bfloat16")
+        for p in model.parameters():
+            if p.device != device:
+                raise RuntimeError(f"all parameters must live on {device}; found one on {p.device}")
+        self.norm_kind = _lib.LP_NORM_RMS if cfg._norm_class == "RMSNorm" else _lib.LP_NORM_LAYERNORM
+        self.act = _lib.LP_EPI_SWIGLU if cfg._mlp_class == "LLaMAMLP" else _lib.LP_EPI_GELU
+        self.wte = model.transformer.wte.weight.data
+        self.layers: List[_Layer] = []
+        for blk in model.transformer.h:
+            L = _Layer()
+            L.n1_w, L.n1_b = _f32(blk.norm_1.weight), _f32(getattr(blk.norm_1, "bias", None))
+            if cfg.shared_attention_norm:
+                L.n2_w = L.n2_b = None
+            else:
+                L.n2_w, L.n2_b = _f32(blk.norm_2.weight), _f32(getattr(blk.norm_2, "bias", None))
+            L.qkv = pack_linear(blk.attn.attn)
+            L.proj = pack_linear(blk.attn.proj)
+            if cfg._mlp_class == "LLaMAMLP":
+                L.fc = pack_swiglu(blk.mlp.fc_1, blk.mlp.fc_2)
+            else:
+                L.fc = pack_linear(blk.mlp.fc)
+            L.mlp_proj = pack_linear(blk.mlp.proj)
+            self.layers.append(L)
+        self.lnf_w, self.lnf_b = _f32(model.transformer.ln_f.weight), _f32(getattr(model.transformer.ln_f, "bias", None))
+        self.lm_head = pack_linear(model.lm_head)
+        self.cos = self.sin = None
+        self._bufs: Dict[int, Dict[str, torch.Tensor]] = {}
+        self._graphs: Dict[Tuple, Tuple] = {}
+        self._scratch: Optional[Tuple] = None
+
+    # ------------------------------------------------------------------ bookkeeping
+    def set_rope(self, rope) -> None:
+        self.cos, self.sin = (t.to(self.device, torch.float32).contiguous() for t in rope)
+
+    def drop_graphs(self) -> None:
+        self._graphs.clear()
+
+    def scratch_cache(self, B: int, T: int):
+        key = (B, T)
+        if self._scratch is None or self._scratch[0] != key:
+            cfg = self.cfg
+            store = torch.empty((cfg.n_layer, 2, B, cfg.n_query_groups, T, cfg.head_size), device=self.device,
+                                dtype=self.param_dtype)
+            self._scratch = (key, [(store[l, 0], store[l, 1]) for l in range(cfg.n_layer)])
+        return self._scratch[1]
+
+    def weight_bytes_per_token(self) -> int:
+        """Algorithmic bytes of weights one decode step streams (all linears incl. lm_head + one embedding row)."""
+        n = self.lm_head.stored_bytes + self.cfg.n_embd * self.wte.element_size()
+        for L in self.layers:
+            n += L.qkv.stored_bytes + L.proj.stored_bytes + L.fc.stored_bytes + L.mlp_proj.stored_bytes
+        return n
+
+    def buffers(self, rows: int, B: int, T: int, max_seq: int) -> Dict[str, torch.Tensor]:
+        key = (rows, max_seq)
+        b = self._bufs.get(key)
+        if b is None:
+            cfg, dev = self.cfg, self.device
+            f = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)  # noqa: E731
+            E, I, V = cfg.n_embd, cfg.intermediate_size, cfg.padded_vocab_size
+            ws_bytes = self.lib.lp_attn_workspace_bytes(B, T, cfg.n_head, cfg.head_size, max_seq)
+            b = dict(x=f(rows, E), n1=f(rows, E), n2=f(rows, E), qkv=f(rows, cfg.qkv_rows), q=f(rows, E), att=f(rows, E),
+                     xmid=f(rows, E), u=f(rows, I), xf=f(rows, E), logits=f(rows, V),
+                     ws=torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8))
+            if len(self._bufs) > 8:
+                self._bufs.clear()
+            self._bufs[key] = b
+        return b
+
+    # ------------------------------------------------------------------ one forward pass = a fixed list of C-ABI calls
+    def _run(self, b: Dict[str, torch.Tensor], idx_ptr: int, idx64: int, idx_off: Optional[int], pos_ptr: int,
+             caches, B: int, T: int, stream: int, last_only: bool = False) -> None:
+        lib, cfg, r, chk = self.lib, self.cfg, self.round, _lib.check
+        rows = B * T
+        E, H, G, hs = cfg.n_embd, cfg.n_head, cfg.n_query_groups, cfg.head_size
+        max_seq = caches[0][0].size(2)
+        kvd = _KV_OF_DTYPE[caches[0][0].dtype]
+        x, n1, n2, qkv, q, att, xmid, u = (b[k].data_ptr() for k in ("x", "n1", "n2", "qkv", "q", "att", "xmid", "u"))
+        ws, ws_bytes = b["ws"].data_ptr(), b["ws"].numel()
+        scale = 1.0 / math.sqrt(hs)
+        wte_dt = _KV_OF_DTYPE[self.wte.dtype]
+        chk(lib.lp_embed(idx_ptr, idx64, idx_off, self.wte.data_ptr(), wte_dt, x, rows, E, r, stream), "lp_embed")
+        for li, L in enumerate(self.layers):
+            kc, vc = caches[li][0].data_ptr(), caches[li][1].data_ptr()
+            chk(lib.lp_norm(self.norm_kind, x, _ptr(L.n1_w), _ptr(L.n1_b), cfg.norm_eps, n1, rows, E, r, stream), "lp_norm")
+            chk(lib.lp_linear(n1, rows, L.qkv.ref, _lib.LP_EPI_NONE, None, qkv, r, stream), "lp_linear(qkv)")
+            chk(lib.lp_rope_kv_append(qkv, _ptr(self.cos), _ptr(self.sin), pos_ptr, q, kc, vc, kvd, B, T, H, G, hs,
+                                      cfg.rope_n_elem, max_seq, r, stream), "lp_rope_kv_append")
+            chk(lib.lp_attn_decode(q, kc, vc, kvd, pos_ptr, att, ws, ws_bytes, B, T, H, G, hs, max_seq, scale, r, stream),
+                "lp_attn_decode")
+            if cfg.parallel_residual:
+                if cfg.shared_attention_norm:
+                    mlp_in = n1
+                else:
+                    chk(lib.lp_norm(self.norm_kind, x, _ptr(L.n2_w), _ptr(L.n2_b), cfg.norm_eps, n2, rows, E, r, stream),
+                        "lp_norm")
+                    mlp_in = n2
+                chk(lib.lp_linear(att, rows, L.proj.ref, _lib.LP_EPI_RESIDUAL, x, xmid, r, stream), "lp_linear(proj)")
+                chk(lib.lp_linear(mlp_in, rows, L.fc.ref, self.act, None, u, r, stream), "lp_linear(fc)")
+                chk(lib.lp_linear(u, rows, L.mlp_proj.ref, _lib.LP_EPI_RESIDUAL, xmid, x, r, stream), "lp_linear(mlp.proj)")
+            else:
+                if cfg.shared_attention_norm:
+                    raise NotImplementedError("No checkpoint amongst the ones we support uses this configuration"
+                                              " (non-parallel residual and shared attention norm).")
+                chk(lib.lp_linear(att, rows, L.proj.ref, _lib.LP_EPI_RESIDUAL, x, x, r, stream), "lp_linear(proj)")
+                chk(lib.lp_norm(self.norm_kind, x, _ptr(L.n2_w), _ptr(L.n2_b), cfg.norm_eps, n2, rows, E, r, stream), "lp_norm")
+                chk(lib.lp_linear(n2, rows, L.fc.ref, self.act, None, u, r, stream), "lp_linear(fc)")
+                chk(lib.lp_linear(u, rows, L.mlp_proj.ref, _lib.LP_EPI_RESIDUAL, x, x, r, stream), "lp_linear(mlp.proj)")
+        xf, logits = b["xf"].data_ptr(), b["logits"].data_ptr()
+        if last_only and T > 1:
+            # only the last position of each sequence feeds the sampler (generate/base.py:136)
+            for bi in range(B):
+                off = ((bi + 1) * T - 1) * E * 4
+                chk(lib.lp_norm(self.norm_kind, x + off, _ptr(self.lnf_w), _ptr(self.lnf_b), cfg.norm_eps, xf + bi * E * 4, 1, E, r,
+                                stream), "lp_norm")
+            chk(lib.lp_linear(xf, B, self.lm_head.ref, _lib.LP_EPI_NONE, None, logits, r, stream), "lp_linear(lm_head)")
+        else:
+            chk(lib.lp_norm(self.norm_kind, x, _ptr(self.lnf_w), _ptr(self.lnf_b), cfg.norm_eps, xf, rows, E, r, stream), "lp_norm")
+            chk(lib.lp_linear(xf, rows, self.lm_head.ref, _lib.LP_EPI_NONE, None, logits, r, stream), "lp_linear(lm_head)")
+
+    # ------------------------------------------------------------------ public entry used by GPT.forward
+    def _check_caches(self, caches, B: int) -> None:
+        k = caches[0][0]
+        cfg = self.cfg
+        if k.dim() != 4 or k.size(0) != B or k.size(1) != cfg.n_query_groups or k.size(3) != cfg.head_size:
+            raise RuntimeError(f"kv cache shape {tuple(k.shape)} does not match (B={B}, G={cfg.n_query_groups}, max_seq, "
+                               f"hs={cfg.head_size}); call model.reset_cache() when the batch size changes")
+        if k.dtype not in _KV_OF_DTYPE or not k.is_contiguous():
+            raise RuntimeError("kv cache must be a contiguous float32 / bfloat16 tensor")
+
+    def forward(self, idx: torch.Tensor, pos: torch.Tensor, caches, allow_graph: bool = True,
+                last_only: bool = False, raw_logits: bool = False) -> torch.Tensor:
+        B, T = idx.shape
+        cfg = self.cfg
+        self._check_caches(caches, B)
+        if pos.numel() != T:
+            raise ValueError(f"input_pos has {pos.numel()} entries for a sequence of length {T}")
+        max_seq = caches[0][0].size(2)
+        V = cfg.padded_vocab_size
+        if T == 1 and allow_graph:
+            return self._forward_graph(idx, pos, caches, B, max_seq)
+        b = self.buffers(B * T, B, T, max_seq)
+        if idx.dtype not in (torch.int32, torch.int64):
+            idx = idx.long()
+        idx = idx.contiguous()
+        pos32 = pos.to(device=self.device, dtype=torch.int32).contiguous()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._run(b, idx.data_ptr(), int(idx.dtype == torch.int64), None, pos32.data_ptr(), caches, B, T, stream, last_only)
+        out = b["logits"][:B].view(B, 1, V) if (last_only and T > 1) else b["logits"].view(B, T, V)
+        return out if raw_logits else out.to(self.param_dtype, copy=True)
+
+    # ------------------------------------------------------------------ device-resident generate loop
+    def gen_state(self, capacity: int) -> Dict[str, torch.Tensor]:
+        st = getattr(self, "_gen", None)
+        if st is None or st["seq"].numel() < capacity:
+            i32 = lambda n: torch.zeros(n, dtype=torch.int32, device=self.device)  # noqa: E731
+            st = dict(seq=i32(capacity + 1), pos=i32(1), step=i32(1), tok=i32(1))
+            self._gen = st
+            self._graphs = {k: v for k, v in self._graphs.items() if k[0] != "gen"}
+        return st
+
+    def decode_step(self, caches, temperature: float, top_k: int, seed: int, B: int = 1):
+        """Returns a callable that runs ONE decode step: embed(seq[pos]) .. lm_head -> sample -> seq[pos+1], pos += 1.
+        Captured once per (cache, sampling parameters); position, tokens and the Philox step live in device memory.
+        B > 1 (lock-step batch, model.py:66): the B sampled ids in `tok` are the next step's input; no history is kept."""
+        self._check_caches(caches, B)
+        max_seq = caches[0][0].size(2)
+        st = self._gen
+        if st["tok"].numel() < B:
+            st["tok"] = torch.zeros(B, dtype=torch.int32, device=self.device)
+        key = ("gen", B, max_seq, caches[0][0].data_ptr(), temperature, top_k, seed, st["seq"].data_ptr(), st["tok"].data_ptr())
+        g = self._graphs.get(key)
+        if g is None:
+            b = self.buffers(B, B, 1, max_seq)
+            V = self.cfg.padded_vocab_size
+
+            def step_fn(stream: int) -> None:
+                if B == 1:
+                    self._run(b, st["seq"].data_ptr(), 0, st["pos"].data_ptr(), st["pos"].data_ptr(), caches, 1, 1, stream)
+                    seq = st["seq"].data_ptr()
+                else:
+                    self._run(b, st["tok"].data_ptr(), 0, None, st["pos"].data_ptr(), caches, B, 1, stream)
+                    seq = None
+                _lib.check(self.lib.lp_sample(b["logits"].data_ptr(), B, V, temperature, top_k, seed, st["step"].data_ptr(),
+                                              st["tok"].data_ptr(), seq, st["pos"].data_ptr(), stream), "lp_sample")
+
+            if self.use_graph:
+                # warm-up = one real step (loads the M=1 kernels before capture); it is then undone by restoring the
+                # device-side position / Philox step, so the first replay recomputes exactly the same token and KV slot
+                saved = (st["pos"].clone(), st["step"].clone(), st["tok"].clone())
+                side = torch.cuda.Stream(self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    step_fn(side.cuda_stream)
+                    st["pos"].copy_(saved[0])
+                    st["step"].copy_(saved[1])
+                    st["tok"].copy_(saved[2])
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                torch.cuda.synchronize(self.device)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    step_fn(torch.cuda.current_stream(self.device).cuda_stream)
+                g = graph.replay
+            else:
+                g = lambda: step_fn(torch.cuda.current_stream(self.device).cuda_stream)  # noqa: E731
+            self._graphs[key] = g
+        return g
+
+    def _forward_graph(self, idx, pos, caches, B: int, max_seq: int) -> torch.Tensor:
+        """T == 1: the whole step (embed .. lm_head) is captured once per (B, cache) and replayed."""
+        V = self.cfg.padded_vocab_size
+        key = ("fwd", B, max_seq, caches[0][0].data_ptr())
+        g = self._graphs.get(key)
+        if g is None:
+            b = self.buffers(B, B, 1, max_seq)
+            s_idx = torch.zeros(B, dtype=torch.int64, device=self.device)
+            s_pos = torch.zeros(1, dtype=torch.int32, device=self.device)
+            # the warm-up run inside _capture executes the real step (it writes this position's KV slot)
+            s_idx.copy_(idx.reshape(-1))
+            s_pos.copy_(pos.reshape(-1))
+            graph = self._capture(lambda st: self._run(b, s_idx.data_ptr(), 1, None, s_pos.data_ptr(), caches, B, 1, st))
+            g = (graph, b, s_idx, s_pos)
+            self._graphs[key] = g
+        graph, b, s_idx, s_pos = g
+        s_idx.copy_(idx.reshape(-1))
+        s_pos.copy_(pos.reshape(-1))
+        if graph is None:
+            self._run(b, s_idx.data_ptr(), 1, None, s_pos.data_ptr(), caches, B, 1, torch.cuda.current_stream(self.device).cuda_stream)
+        else:
+            graph.replay()
+        return b["logits"].view(B, 1, V).to(self.param_dtype, copy=True)
+
+    def _capture(self, fn):
+        """Warm up on a side stream, then capture `fn(stream)` into a CUDA graph (None if graphs are disabled)."""
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            fn(side.cuda_stream)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        if not self.use_graph:
+            return None
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            fn(torch.cuda.current_stream(self.device).cuda_stream)
+        return graph

@@ -175,8 +175,9 @@ class OracleGPT:
         else:
             if not self.kv:  # model.py:130-144: zero caches; MQA keeps one head, otherwise n_head heads
                 heads = 1 if cfg.n_query_groups == 1 else cfg.n_head
-                shape = (B, heads, max_seq_length, hs)
-                self.kv = [(torch.zeros(shape, dtype=self.dtype), torch.zeros(shape, dtype=self.dtype))
+                k_width = cos.size(-1) + hs - int(cfg.rotary_percentage * hs)  # model.py:134-139
+                k_shape, v_shape = (B, heads, max_seq_length, k_width), (B, heads, max_seq_length, hs)
+                self.kv = [(torch.zeros(k_shape, dtype=self.dtype), torch.zeros(v_shape, dtype=self.dtype))
                            for _ in range(cfg.n_layer)]
             for i in range(cfg.n_layer):
                 x, self.kv[i] = block(cfg, x, self.sd, i, cos, sin, max_seq_length, mask, input_pos, self.kv[i])

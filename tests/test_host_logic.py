@@ -1,0 +1,128 @@
+"""Host-side logic that needs no GPU: module tree / state-dict contract, plug-in switch, error behaviour,
+generate() driving a foreign (CPU) model with the reference's semantics."""
+from unittest import mock
+
+import numpy as np
+import pytest
+import torch
+
+import lit_parrot_b200 as lp
+from oracle import lit_oracle as O
+from helpers import TINY_NAMES, load_tiny, t
+
+
+@pytest.mark.parametrize("name", TINY_NAMES + ["pythia-70m", "falcon-7b"])
+def test_state_dict_contract(name):
+    if name in TINY_NAMES:
+        _, _, cfg = load_tiny(name)
+    else:
+        cfg = lp.Config.from_name(name, n_layer=1)
+    with torch.device("meta"):
+        m = lp.GPT(cfg)
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == O.state_dict_shapes(cfg)
+
+
+def test_drop_in_import_surface():
+    import generate.base
+    import lit_gpt
+    import lit_gpt.model
+    import lit_gpt.utils
+    import quantize.bnb
+    import quantize.gptq
+
+    assert lit_gpt.GPT is lp.GPT and lit_gpt.Config is lp.Config
+    assert generate.base.generate is lp.generate
+    assert lit_gpt.utils.quantization is lp.quantization
+    assert lit_gpt.utils.find_multiple(50254, 512) == 50688
+    assert hasattr(lit_gpt.model, "build_rope_cache") and hasattr(quantize.gptq, "ColBlockQuantizedLinear")
+    assert hasattr(quantize.bnb, "Linear4bit") and hasattr(quantize.bnb, "InferenceLinear8bitLt")
+
+
+def test_quantization_plugin_switch(golden_dir):
+    """lit_gpt/utils.py:26-83: torch.nn.Linear is swapped during construction (lm_head included) and restored after;
+    the GPTQ state-dict keys/shapes equal the reference's."""
+    _, kw, cfg = load_tiny("llama_mha")
+    linear = torch.nn.Linear
+    with lp.quantization("gptq.int4"):
+        assert torch.nn.Linear is not linear
+        m = lp.GPT(cfg)
+    assert torch.nn.Linear is linear
+    z = np.load(f"{golden_dir}/gptq_statedict_keys.npz")
+    ref = dict(zip(z["keys"].tolist(), z["shapes"].tolist()))
+    got = {k: repr(tuple(v.shape)) for k, v in m.state_dict().items()}
+    assert got == ref
+    qw = m.lm_head.quant_weight
+    assert qw.dtype == torch.uint8 and qw.stride() == (1, qw.shape[0])  # reference storage order (gptq.py:216-222)
+    with pytest.raises(ValueError, match="Unknown quantization mode"):
+        with lp.quantization("nope"):
+            pass
+    assert torch.nn.Linear is linear
+    with lp.quantization(None):
+        assert torch.nn.Linear is linear
+    for mode, cls in (("bnb.nf4", "Linear4bit"), ("bnb.int8", "InferenceLinear8bitLt")):
+        with lp.quantization(mode):
+            m = lp.GPT(lp.Config(block_size=16, vocab_size=64, padding_multiple=64, n_layer=1, n_head=2, n_embd=64))
+        assert cls in [c.__name__ for c in type(m.lm_head).__mro__]
+        assert torch.nn.Linear is linear
+
+
+def test_gptq_module_matches_reference_fixture(golden_dir):
+    """ColBlockQuantizedLinear: RTN quantiser, nibble order and get_weight equal the reference fixture (CPU, torch ops)."""
+    from lit_parrot_b200.quantize import ColBlockQuantizedLinear
+
+    for tag in ("g128", "perrow"):
+        z = np.load(f"{golden_dir}/gptq_{tag}.npz")
+        w = t(z["w"])
+        lin = ColBlockQuantizedLinear(w.shape[1], w.shape[0], True, bits=4, tile_cols=int(z["tile_cols"]))
+        lin.quantize_rtn_(w)
+        assert torch.equal(lin.quant_weight, t(z["quant_weight"]))
+        assert torch.equal(lin.scales, t(z["scales"])) and torch.equal(lin.zeros, t(z["zeros"]))
+        assert torch.equal(lin.get_weight(torch.float32), t(z["dequant"]))
+
+
+def test_cpu_is_refused_loudly():
+    cfg = lp.Config(block_size=16, vocab_size=32, padding_multiple=32, n_layer=1, n_head=2, n_embd=16)
+    m = lp.GPT(cfg)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 4, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        lp.generate(m, torch.zeros(4, dtype=torch.int32), 8)
+    # the reference's assertions come first (model.py:72-77)
+    with pytest.raises(AssertionError, match="block size is only"):
+        m(torch.zeros(1, 17, dtype=torch.long))
+    with pytest.raises(AssertionError, match="max seq length is only"):
+        m(torch.zeros(1, 8, dtype=torch.long), 4, torch.arange(8))
+
+
+@pytest.mark.parametrize("max_seq_length", (10, 20 + 5))
+def test_generate_foreign_model_reference_semantics(max_seq_length):
+    """reference tests/test_generate.py:14-42, with the oracle as the (foreign, CPU) model: output == prompt ++ samples."""
+    T = 5
+    input_idx = torch.randint(10, size=(T,))
+    cfg = lp.Config(block_size=128, vocab_size=16, n_layer=1, n_head=4, n_embd=8)
+    model = O.OracleGPT(cfg, O.random_state_dict(cfg, seed=3))
+    results = []
+    original = torch.multinomial
+
+    def multinomial(*args, **kwargs):
+        out = original(*args, **kwargs)
+        results.append(out)
+        return out
+
+    with mock.patch("torch.multinomial", multinomial):
+        out = lp.generate(model, input_idx, T + 20, max_seq_length=max_seq_length, top_k=4)
+    assert out.size(0) == T + 20
+    torch.testing.assert_close(out, torch.cat((input_idx, torch.hstack(results))))
+
+
+def test_generate_foreign_eos_cut():
+    cfg = lp.Config(block_size=64, vocab_size=16, n_layer=1, n_head=2, n_embd=16)
+    model = O.OracleGPT(cfg, O.random_state_dict(cfg, seed=5))
+    prompt = torch.tensor([1, 2, 3], dtype=torch.int32)
+    full = lp.generate(model, prompt, 20, top_k=1)
+    model.reset_cache()
+    eos = int(full[7])
+    first = int((full[3:] == eos).nonzero()[0]) + 3
+    cut = lp.generate(model, prompt, 20, top_k=1, eos_id=eos)
+    assert torch.equal(cut, full[:first])  # idx[:input_pos] excludes the EOS itself (generate/base.py:156-157)

@@ -1,0 +1,275 @@
+"""Per-kernel parity on a B200: every C-ABI entry point against a torch/oracle restatement of the reference op."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from lit_parrot_b200 import _lib
+from lit_parrot_b200._lib import LpWeight
+from oracle import lit_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return _lib.init(0)
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def f32(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def bf16r(x):
+    return x.to(torch.bfloat16).float()
+
+
+def run_linear(lib, x, wt, fmt, N, K, *, bias=None, aux0=None, aux1=None, group=0, epi=0, residual=None, rnd=0, path=0):
+    M = x.shape[0]
+    out = torch.full((M, N // 2 if epi == _lib.LP_EPI_SWIGLU else N), float("nan"), device=DEV)
+    p = lambda a: None if a is None else a.data_ptr()  # noqa: E731
+    rec = LpWeight(wt.data_ptr(), p(aux0), p(aux1), p(bias), fmt, N, K, group)
+    _lib.check(lib.lp_set_linear_path(path))
+    try:
+        rc = lib.lp_linear(x.data_ptr(), M, ctypes.byref(rec), epi, p(residual), out.data_ptr(), rnd, stream())
+    finally:
+        lib.lp_set_linear_path(0)
+    _lib.check(rc, "lp_linear")
+    torch.cuda.synchronize()
+    return out
+
+
+def ref_epilogue(y, epi, residual):
+    if epi == _lib.LP_EPI_GELU:
+        return F.gelu(y)
+    if epi == _lib.LP_EPI_SWIGLU:
+        return F.silu(y[:, 0::2]) * y[:, 1::2]
+    if epi == _lib.LP_EPI_RESIDUAL:
+        return residual + y
+    return y
+
+
+PATHS = [1, 0]  # 1 = FMA family only, 0 = auto (MMA family where it applies)
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("wdtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(1, 64, 64), (1, 50, 136), (3, 256, 512), (8, 96, 1024), (13, 128, 256), (1, 4672, 4544), (32, 512, 1024)])
+def test_linear_dense(lib, path, wdtype, M, N, K):
+    w = f32(N, K, seed=1, scale=0.05).to(wdtype)
+    x, b = f32(M, K, seed=2), f32(N, seed=3)
+    if wdtype == torch.float32 and K % 4 or wdtype == torch.bfloat16 and K % 8:
+        pytest.skip("alignment")
+    fmt = _lib.LP_W_F32 if wdtype == torch.float32 else _lib.LP_W_BF16
+    ref = F.linear(x.double(), w.double(), b.double())
+    for epi in (0, 1, 2, 3):
+        if epi == 2 and N % 2:
+            continue
+        res = f32(M, N, seed=4)
+        got = run_linear(lib, x, w, fmt, N, K, bias=b, epi=epi, residual=res, path=path)
+        want = ref_epilogue(ref, epi, res.double()).float()
+        torch.testing.assert_close(got, want, rtol=2e-5, atol=2e-5 * math.sqrt(K))
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("group", [128, -1])
+@pytest.mark.parametrize("M,N,K", [(1, 64, 256), (2, 48, 384), (5, 256, 1024), (1, 96, 4544), (16, 128, 512)])
+def test_linear_gptq_int4(lib, path, group, M, N, K):
+    """quant_weight in the reference's column-major storage -> lp_repack_gptq_int4 -> lp_linear, against the reference
+    fall-back `get_weight()+F.linear` restated by the oracle (quantize/gptq.py:243-252, 263-264)."""
+    w = (torch.randn(N, K, generator=torch.Generator().manual_seed(5)) * 0.02)
+    packed, scales, zeros = O.gptq_rtn_quantize(w, group)
+    assert packed.stride() == (1, N)
+    src = torch.empty((K // 2, N), dtype=torch.uint8, device=DEV).t()
+    src.copy_(packed)
+    rb = lib.lp_int4_row_bytes(K)
+    rows = torch.empty((N, rb), dtype=torch.uint8, device=DEV)
+    _lib.check(lib.lp_repack_gptq_int4(src.data_ptr(), rows.data_ptr(), N, K, stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(rows[:, : K // 2].cpu(), packed.contiguous())  # bit-exact transpose
+    assert int(rows[:, K // 2:].sum()) == 0
+    x = f32(M, K, seed=6)
+    g = K if group == -1 else group
+    wd = O.gptq_dequant(packed, scales, zeros)  # fp32 dequant, as the reference does for fp32 activations
+    want = F.linear(x.cpu().double(), wd.double()).float().to(DEV)
+    got = run_linear(lib, x, rows, _lib.LP_W_INT4, N, K, aux0=scales.to(DEV).contiguous(), aux1=zeros.to(DEV).contiguous(),
+                     group=g, path=path)
+    torch.testing.assert_close(got, want, rtol=2e-5, atol=3e-5 * math.sqrt(K) * 0.3)
+    # bf16-faithful mode: dequantised weight and output rounded to bf16 like the reference's bf16 run
+    xb = bf16r(x)
+    wdb = O.gptq_dequant(packed, scales, zeros, dtype=torch.bfloat16).double()
+    wantb = bf16r(F.linear(xb.cpu().double(), wdb).float()).to(DEV)
+    gotb = run_linear(lib, xb, rows, _lib.LP_W_INT4, N, K, aux0=scales.to(DEV).contiguous(), aux1=zeros.to(DEV).contiguous(),
+                      group=g, rnd=1, path=1)
+    mism = (gotb != wantb)
+    # identical except where the fp32 sum lands within rounding noise of a bf16 tie: at most 1 ulp, rarely
+    assert mism.float().mean() < 0.02
+    torch.testing.assert_close(gotb, wantb, rtol=2 ** -7, atol=1e-6)
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("M,N,K", [(1, 64, 128), (4, 96, 512), (1, 128, 4544 - 64)])
+def test_linear_nf4_int8(lib, path, M, N, K):
+    w = torch.randn(N, K, generator=torch.Generator().manual_seed(8)) * 0.02
+    x = f32(M, K, seed=9)
+    packed, absmax = O.nf4_quantize(w)
+    want = F.linear(x.cpu().double(), O.nf4_dequantize(packed, absmax, w.shape).double()).float().to(DEV)
+    got = run_linear(lib, x, packed.to(DEV), _lib.LP_W_NF4, N, K, aux0=absmax.to(DEV), group=64, path=path)
+    torch.testing.assert_close(got, want, rtol=2e-5, atol=1e-5 * math.sqrt(K))
+    cb, scb = O.int8_quantize(w)
+    want = F.linear(x.cpu().double(), O.int8_dequantize(cb, scb).double()).float().to(DEV)
+    got = run_linear(lib, x, cb.to(DEV), _lib.LP_W_INT8, N, K, aux0=(scb / 127.0).to(DEV), path=path)
+    torch.testing.assert_close(got, want, rtol=2e-5, atol=1e-5 * math.sqrt(K))
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("rows,E", [(1, 64), (5, 512), (2, 4544), (3, 8192)])
+def test_norm(lib, kind, rows, E):
+    x, w, b = f32(rows, E, seed=1), 1 + 0.1 * f32(E, seed=2), 0.1 * f32(E, seed=3)
+    y = torch.empty_like(x)
+    _lib.check(lib.lp_norm(kind, x.data_ptr(), w.data_ptr(), b.data_ptr() if kind == 0 else None, 1e-5, y.data_ptr(), rows, E, 0,
+                           stream()))
+    want = F.layer_norm(x, (E,), w, b, 1e-5) if kind == 0 else O.rms_norm(x, w, 1e-5)
+    torch.testing.assert_close(y, want, rtol=1e-5, atol=1e-5)
+    # bf16-faithful mode against the reference ops evaluated in bf16 on the same (bf16-valued) inputs
+    xb, wb, bb = bf16r(x), bf16r(w), bf16r(b)
+    _lib.check(lib.lp_norm(kind, xb.data_ptr(), wb.data_ptr(), bb.data_ptr() if kind == 0 else None, 1e-5, y.data_ptr(), rows, E, 1,
+                           stream()))
+    if kind == 0:
+        want = F.layer_norm(xb.bfloat16(), (E,), wb.bfloat16(), bb.bfloat16(), 1e-5).float()
+    else:
+        want = O.rms_norm(xb.bfloat16(), wb.bfloat16(), 1e-5).float()
+    assert (y != want).float().mean() < 0.02  # identical up to rare 1-ulp flips from the reduction order
+    torch.testing.assert_close(y, want, rtol=2 ** -7, atol=1e-6)
+
+
+@pytest.mark.parametrize("wdtype", [torch.float32, torch.bfloat16])
+def test_embed(lib, wdtype):
+    V, E = 300, 96
+    wte = f32(V, E, seed=1).to(wdtype)
+    for idt in (torch.int32, torch.int64):
+        idx = torch.randint(0, V, (7,), device=DEV).to(idt)
+        out = torch.empty(7, E, device=DEV)
+        _lib.check(lib.lp_embed(idx.data_ptr(), int(idt == torch.int64), None, wte.data_ptr(), int(wdtype == torch.bfloat16),
+                                out.data_ptr(), 7, E, 0, stream()))
+        assert torch.equal(out, wte[idx.long()].float())
+    off = torch.tensor([3], dtype=torch.int32, device=DEV)
+    idx = torch.randint(0, V, (9,), device=DEV, dtype=torch.int32)
+    out = torch.empty(1, E, device=DEV)
+    _lib.check(lib.lp_embed(idx.data_ptr(), 0, off.data_ptr(), wte.data_ptr(), int(wdtype == torch.bfloat16), out.data_ptr(), 1, E, 0,
+                            stream()))
+    assert torch.equal(out[0], wte[idx[3].long()].float())
+
+
+@pytest.mark.parametrize("kvdt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,T,H,G,hs,n_elem", [(1, 1, 8, 8, 64, 16), (2, 5, 8, 2, 128, 128), (1, 3, 71, 1, 64, 64), (3, 4, 4, 4, 16, 4)])
+def test_rope_kv_append(lib, kvdt, B, T, H, G, hs, n_elem):
+    max_seq, block = 16, 64
+    qpk = H // G
+    qkv = f32(B * T, (H + 2 * G) * hs, seed=1)
+    cos, sin = O.rope_tables(block, n_elem, torch.float32)
+    cos, sin = cos.to(DEV).contiguous(), sin.to(DEV).contiguous()
+    pos = torch.tensor([7 + t for t in range(T)], dtype=torch.int32, device=DEV)
+    q_out = torch.empty(B * T, H * hs, device=DEV)
+    kc = torch.zeros(B, G, max_seq, hs, device=DEV, dtype=kvdt)
+    vc = torch.zeros_like(kc)
+    _lib.check(lib.lp_rope_kv_append(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), pos.data_ptr(), q_out.data_ptr(), kc.data_ptr(),
+                                     vc.data_ptr(), int(kvdt == torch.bfloat16), B, T, H, G, hs, n_elem, max_seq, 0, stream()))
+    # restatement of model.py:208-232 on the same tensor
+    v5 = qkv.view(B, T, G, qpk + 2, hs).permute(0, 2, 3, 1, 4)
+    q, k, v = v5.split((qpk, 1, 1), dim=2)
+    c, s = cos[pos.long()], sin[pos.long()]
+    rot = lambda z: torch.cat((O.rotate(z[..., :n_elem], c, s), z[..., n_elem:]), dim=-1)  # noqa: E731
+    q, k = rot(q), rot(k)
+    want_q = q.permute(0, 3, 1, 2, 4).reshape(B * T, H * hs)
+    assert torch.equal(q_out, want_q)  # same fp32 op order: bit-exact
+    want_k = torch.zeros(B, G, max_seq, hs, device=DEV)
+    want_v = torch.zeros_like(want_k)
+    want_k[:, :, pos.long()] = k[:, :, 0]
+    want_v[:, :, pos.long()] = v[:, :, 0]
+    assert torch.equal(kc.float(), want_k.to(kvdt).float()) and torch.equal(vc.float(), want_v.to(kvdt).float())
+
+
+@pytest.mark.parametrize("kvdt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,T,H,G,hs,max_seq,p0", [
+    (1, 1, 8, 8, 64, 64, 0), (1, 1, 8, 8, 64, 64, 63), (2, 1, 32, 32, 128, 2048, 1500), (1, 1, 71, 1, 64, 512, 300),
+    (2, 1, 64, 8, 128, 1024, 1023), (1, 7, 4, 2, 16, 32, 0), (3, 5, 8, 8, 32, 40, 9), (1, 1, 8, 8, 64, 48, 200)])
+def test_attention_against_sdpa(lib, kvdt, B, T, H, G, hs, max_seq, p0):
+    """lp_attn_decode against masked SDPA over the zero-filled cache, as the reference runs it (model.py:91-92, 273-275).
+    p0 >= max_seq exercises the ring (sliding-window) case: all max_seq slots are attended."""
+    qpk = H // G
+    q = f32(B * T, H * hs, seed=1)
+    pos = torch.arange(p0, p0 + T, dtype=torch.int32, device=DEV)
+    kc = torch.zeros(B, G, max_seq, hs, device=DEV, dtype=kvdt)
+    vc = torch.zeros_like(kc)
+    n_valid = min(p0 + T, max_seq)
+    kc[:, :, :n_valid] = f32(B, G, n_valid, hs, seed=2).to(kvdt)
+    vc[:, :, :n_valid] = f32(B, G, n_valid, hs, seed=3).to(kvdt)
+    out = torch.empty(B * T, H * hs, device=DEV)
+    ws = torch.empty(lib.lp_attn_workspace_bytes(B, T, H, hs, max_seq) + 16, dtype=torch.uint8, device=DEV)
+    scale = 1.0 / math.sqrt(hs)
+    _lib.check(lib.lp_attn_decode(q.data_ptr(), kc.data_ptr(), vc.data_ptr(), int(kvdt == torch.bfloat16), pos.data_ptr(), out.data_ptr(),
+                                  ws.data_ptr(), ws.numel(), B, T, H, G, hs, max_seq, scale, 0, stream()))
+    qq = q.view(B, T, H, hs).transpose(1, 2).double()
+    kk = kc.double().repeat_interleave(qpk, dim=1)
+    vv = vc.double().repeat_interleave(qpk, dim=1)
+    kpos = torch.arange(max_seq, device=DEV)
+    mask = kpos[None, :] <= torch.clamp(pos.long(), max=max_seq - 1)[:, None]  # row t sees min(pos+1, max_seq) slots
+    want = F.scaled_dot_product_attention(qq, kk, vv, attn_mask=mask[None, None], scale=scale)
+    want = want.transpose(1, 2).reshape(B * T, H * hs).float()
+    torch.testing.assert_close(out, want, rtol=1e-4, atol=2e-5)
+
+
+def test_sample_greedy_and_topk(lib):
+    V = 50304
+    logits = f32(2, V, seed=1)
+    logits[0, 777] = logits[0, 12345] = 9.0  # exact tie -> lowest index
+    tok = torch.full((2,), -1, dtype=torch.int32, device=DEV)
+    step = torch.zeros(1, dtype=torch.int32, device=DEV)
+    _lib.check(lib.lp_sample(logits.data_ptr(), 2, V, 1.0, 1, 1234, step.data_ptr(), tok.data_ptr(), None, None, stream()))
+    assert tok.tolist() == [777, int(logits[1].argmax())]
+    # top-k: every draw must come from the k best logits (ties with the k-th value survive, generate/base.py:139-141)
+    k = 5
+    lg = f32(1, V, seed=2)
+    kth = torch.topk(lg[0], k).values[-1]
+    lg[0, 4242] = kth  # a tie with the k-th value must stay eligible
+    allowed = set((lg[0] >= kth).nonzero().flatten().tolist())
+    assert len(allowed) == k + 1
+    seen = set()
+    one = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for i in range(300):
+        _lib.check(lib.lp_sample(lg.data_ptr(), 1, V, 2.0, k, 99, step.data_ptr(), one.data_ptr(), None, None, stream()))
+        seen.add(int(one))
+    assert seen <= allowed and len(seen) == k + 1 and int(step) == 300
+    # device-side append used by the captured decode step
+    seq = torch.zeros(8, dtype=torch.int32, device=DEV)
+    pos = torch.tensor([2], dtype=torch.int32, device=DEV)
+    _lib.check(lib.lp_sample(lg.data_ptr(), 1, V, 1.0, 1, 0, step.data_ptr(), one.data_ptr(), seq.data_ptr(), pos.data_ptr(), stream()))
+    assert int(pos) == 3 and int(seq[3]) == int(lg[0].argmax()) == int(one)
+
+
+def test_sample_distribution(lib):
+    """temperature sampling follows softmax(logits / T) (chi-square over 20k draws on a small vocabulary)."""
+    V, n, T = 12, 20000, 0.7
+    lg = f32(1, V, seed=4)
+    p = F.softmax(lg[0].double() / T, dim=-1).cpu().numpy()
+    rows = 500
+    big = lg.repeat(rows, 1).contiguous()
+    tok = torch.zeros(rows, dtype=torch.int32, device=DEV)
+    step = torch.zeros(1, dtype=torch.int32, device=DEV)
+    counts = np.zeros(V)
+    for i in range(n // rows):
+        step.fill_(i)
+        _lib.check(lib.lp_sample(big.data_ptr(), rows, V, T, 0, 7, step.data_ptr(), tok.data_ptr(), None, None, stream()))
+        counts += np.bincount(tok.cpu().numpy(), minlength=V)
+    chi2 = float(((counts - n * p) ** 2 / (n * p)).sum())
+    assert chi2 < 45.0, chi2  # 11 dof: P(chi2 > 45) ~ 5e-6

@@ -1,0 +1,246 @@
+"""End-to-end parity on a B200: lit_parrot_b200.GPT / generate against the reference golden vectors and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import lit_parrot_b200 as lp
+from oracle import lit_oracle as O
+from helpers import TINY_NAMES, cosine, load_tiny, t
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+# north-star tolerance for logits vs the reference: max-abs 2e-2, cosine > 0.999.  fp32-activation mode is far
+# inside it; the tight bound below is what we actually hold it to.
+TIGHT = dict(rtol=0, atol=2e-5)
+
+
+def build(cfg, sd, dtype=torch.float32, precision="fp32"):
+    m = lp.GPT(cfg)
+    m.load_state_dict(sd)
+    m = m.to(device=DEV, dtype=dtype)
+    m.set_precision(precision)
+    return m.eval()
+
+
+@pytest.mark.parametrize("graph", [True, False])
+@pytest.mark.parametrize("name", TINY_NAMES)
+def test_tiny_models_match_reference_golden(name, graph):
+    z, kw, cfg = load_tiny(name)
+    sd = O.random_state_dict(cfg, seed=int(z["seed"]), perturb_norm=True)
+    m = build(cfg, sd)
+    m.use_cuda_graph = graph
+    idx = t(z["idx"]).to(DEV)
+    # 1) no-cache forward (model.py:100-103)
+    torch.testing.assert_close(m(idx).cpu(), t(z["ref_full"]), **TIGHT)
+    # 2) cached prefill + teacher-forced decode steps, B = 2 in lock-step
+    max_seq = int(z["max_seq"])
+    pos = torch.arange(idx.shape[1], device=DEV)
+    torch.testing.assert_close(m(idx, max_seq, pos).cpu(), t(z["ref_prefill"]), **TIGHT)
+    for s, tok in enumerate(t(z["forced"])):
+        pos = pos[-1:] + 1
+        torch.testing.assert_close(m(tok.to(DEV), max_seq, pos).cpu(), t(z["ref_steps"][s]), **TIGHT)
+    # 3) cache contents: the reference's cache, one head per query group (reference tests/test_model.py:70-82)
+    k = torch.stack([kv[0] for kv in m.kv_caches]).cpu()
+    v = torch.stack([kv[1] for kv in m.kv_caches]).cpu()
+    torch.testing.assert_close(k, t(z["ref_k_compact"]), **TIGHT)
+    torch.testing.assert_close(v, t(z["ref_v_compact"]), **TIGHT)
+    # 4) greedy generate, incl. the sliding-window overflow (max_seq_length 12 < 30 tokens)
+    m.reset_cache()
+    prompt = t(z["prompt"]).to(DEV)
+    out = lp.generate(m, prompt, 30, 30, temperature=1.0, top_k=1)
+    assert out.dtype == prompt.dtype and torch.equal(out.cpu(), t(z["ref_gen"]))
+    m.reset_cache()
+    out = lp.generate(m, prompt, 30, 12, temperature=1.0, top_k=1)
+    assert torch.equal(out.cpu(), t(z["ref_gen_overflow"]))
+
+
+def test_kv_cache_consistency():
+    """reference tests/test_model.py:228-259 (max_seq_length = 25 case): cached == uncached arg-max for 20 steps."""
+    cfg = lp.Config(block_size=25, padded_vocab_size=5, n_layer=2, n_head=2, n_embd=8)
+    m = build(cfg, O.random_state_dict(cfg, seed=11))
+    idx = torch.randint(0, cfg.padded_vocab_size, (1, 5), device=DEV)
+    x_no, x_c, pos = idx, idx, torch.arange(0, 5, device=DEV)
+    for _ in range(20):
+        a = m(x_no, 25)[:, -1:].argmax().view(1, 1)
+        b = m(x_c, 25, pos)[:, -1:].argmax().view(1, 1)
+        assert torch.equal(a, b)
+        x_no = torch.cat((x_no, a), dim=1)
+        x_c = b
+        pos = pos[-1:] + 1
+
+
+def test_generate_reference_shape_and_topk():
+    """reference tests/test_generate.py:14-42: output = prompt ++ sampled tokens, all sampled from the top-k set."""
+    cfg = lp.Config(block_size=128, vocab_size=16, n_layer=1, n_head=4, n_embd=8)
+    sd = O.random_state_dict(cfg, seed=3)
+    m = build(cfg, sd)
+    prompt = torch.randint(10, size=(5,), device=DEV)
+    for max_seq_length in (10, 25):
+        m.reset_cache()
+        out = lp.generate(m, prompt, 25, max_seq_length=max_seq_length, top_k=4)
+        assert out.size(0) == 25 and torch.equal(out[:5], prompt)
+    # teacher-force the oracle with the sampled stream: every sampled token must be inside the oracle's top-4
+    m.reset_cache()
+    torch.manual_seed(0)
+    out = lp.generate(m, prompt, 25, top_k=4, temperature=0.8).cpu()
+    om = O.OracleGPT(cfg, sd)
+    pos = torch.arange(5)
+    lg = om(out[:5].view(1, -1), 25, pos)[0, -1]
+    for i in range(5, 25):
+        kth = torch.topk(lg, 4).values[-1]
+        assert lg[out[i]] >= kth - 1e-5
+        pos = pos[-1:] + 1
+        lg = om(out[i].view(1, 1), 25, pos)[0, -1]
+
+
+def test_generate_eos(golden_dir):
+    z, kw, cfg = load_tiny("llama_mha")
+    m = build(cfg, O.random_state_dict(cfg, seed=int(z["seed"]), perturb_norm=True))
+    prompt = t(z["prompt"]).to(DEV)
+    ref = t(z["ref_gen"])
+    eos = int(ref[12])
+    first = int((ref[5:] == eos).nonzero()[0]) + 5
+    out = lp.generate(m, prompt, 30, 30, top_k=1, eos_id=eos)
+    assert torch.equal(out.cpu(), ref[:first])  # cut before the EOS token, like idx[:input_pos] (base.py:156-157)
+
+
+def test_pythia70m_greedy_128_tokens_fp32(golden_dir):
+    """BASELINE config 1 on the GPU: pythia-70m random init fp32, greedy 16 -> 128, token-exact with the reference run;
+    logits at the probe steps within 2e-2 / cosine 0.999 (measured: ~1e-5)."""
+    z = np.load(f"{golden_dir}/pythia70m_greedy.npz")
+    cfg = lp.Config.from_name("pythia-70m")
+    m = build(cfg, O.random_state_dict(cfg, seed=int(z["seed"])))
+    prompt = t(z["prompt"]).to(DEV)
+    out = lp.generate(m, prompt, 128, 128, temperature=1.0, top_k=1)
+    ref = t(z["tokens"])
+    assert torch.equal(out.cpu(), ref), f"first mismatch at {int((out.cpu() != ref).nonzero()[0])}, min gap {z['gaps'].min()}"
+    # teacher-forced logits at the probe steps
+    m.reset_cache()
+    pos = torch.arange(16, device=DEV)
+    toks = ref.to(DEV)
+    got = {0: m(toks[:16].view(1, -1).long(), 128, pos)[0, -1].cpu()}
+    for i in range(16, 127):
+        pos = pos[-1:] + 1
+        got[i - 15] = m(toks[i].view(1, 1).long(), 128, pos)[0, -1].cpu()
+    for j, s in enumerate(z["probe_steps"].tolist()):
+        want = t(z["probe_logits"][j])
+        assert (got[s] - want).abs().max() < 2e-2 and cosine(got[s], want) > 0.999
+        torch.testing.assert_close(got[s], want, rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["neox", "falcon_mqa", "llama_gqa"])
+def test_bf16_weights_fp32_activations_token_exact(name):
+    """The token-exact mode for 16-bit checkpoints: bf16-stored weights, fp32 activations.  Oracle = the reference
+    arithmetic in fp32 on the same bf16-rounded weights.  64 greedy tokens identical, logits within 2e-2 / 0.999."""
+    _, kw, cfg = load_tiny(name)
+    cfg = lp.Config(**{**kw, "block_size": 96})
+    sd = {k: v.bfloat16() for k, v in O.random_state_dict(cfg, seed=21, perturb_norm=True).items()}
+    m = build(cfg, sd, dtype=torch.bfloat16)
+    m.kv_cache_dtype = torch.float32
+    om = O.OracleGPT(cfg, {k: v.float() for k, v in sd.items()})
+    prompt = torch.randint(0, cfg.padded_vocab_size, (16,), generator=torch.Generator().manual_seed(1)).to(torch.int32)
+    logits = []
+    want = O.generate(om, prompt, 80, 80, top_k=1, argmax_ties=True, logits_out=logits)
+    out = lp.generate(m, prompt.to(DEV), 80, 80, top_k=1)
+    assert torch.equal(out.cpu(), want)
+    m.reset_cache()
+    got = m._forward_impl(prompt.view(1, -1).to(DEV), 80, torch.arange(16, device=DEV), last_only=True, raw_logits=True)
+    got = got[0, -1].float().cpu()  # fp32 logits before the cast to the parameter dtype
+    assert (got - logits[0]).abs().max() < 2e-2 and cosine(got, logits[0]) > 0.999
+
+
+@pytest.mark.parametrize("name", ["neox", "llama_mha"])
+def test_bf16_faithful_mode_close_to_reference_bf16(name):
+    """precision='bf16' rounds where the reference's bf16-true run rounds; against the oracle evaluated in bf16 on CPU
+    the logits stay within the north-star tolerance for these shallow models (deep models: see DESIGN.md noise floor)."""
+    _, kw, cfg = load_tiny(name)
+    sd = {k: v.bfloat16() for k, v in O.random_state_dict(cfg, seed=22, perturb_norm=True).items()}
+    m = build(cfg, sd, dtype=torch.bfloat16, precision="bf16")
+    om = O.OracleGPT(cfg, sd, dtype=torch.bfloat16)
+    idx = torch.randint(0, cfg.padded_vocab_size, (1, 12), generator=torch.Generator().manual_seed(2))
+    want = om(idx).float()
+    got = m(idx.to(DEV)).float().cpu()
+    assert got.dtype == torch.float32 and (got - want).abs().max() < 2e-2 and cosine(got, want) > 0.999
+
+
+QCFG = dict(block_size=64, vocab_size=128, padding_multiple=64, n_layer=2, n_head=4, n_embd=128, n_query_groups=2,
+            rotary_percentage=1.0, parallel_residual=False, bias=False, _norm_class="RMSNorm", _mlp_class="LLaMAMLP",
+            intermediate_size=256)
+
+
+@pytest.mark.parametrize("tile", [128, -1])
+def test_gptq_int4_model_token_exact(tile):
+    """`quantization('gptq.int4')` model: state dict in the reference's layout, oracle = get_weight()+F.linear in fp32."""
+    cfg = lp.Config(**QCFG)
+    fsd = O.random_state_dict(cfg, seed=31)
+    with lp.quantization("gptq.int4", gptq_tile_cols=tile):
+        m = lp.GPT(cfg)
+    qsd = {}
+    for k, v in fsd.items():
+        if v.dim() == 2 and "wte" not in k:
+            packed, scales, zeros = O.gptq_rtn_quantize(v, tile)
+            base = k[: -len(".weight")]
+            qsd[base + ".quant_weight"], qsd[base + ".scales"], qsd[base + ".zeros"] = packed, scales, zeros
+        else:
+            qsd[k] = v
+    m.load_state_dict(qsd)
+    m = m.to(DEV).eval()
+    om = O.OracleGPT(cfg, qsd)
+    prompt = torch.randint(0, cfg.padded_vocab_size, (8,), generator=torch.Generator().manual_seed(3)).to(torch.int32)
+    logits = []
+    want = O.generate(om, prompt, 40, 40, top_k=1, argmax_ties=True, logits_out=logits)
+    out = lp.generate(m, prompt.to(DEV), 40, 40, top_k=1)
+    assert torch.equal(out.cpu(), want)
+    m.reset_cache()
+    got = m(prompt.view(1, -1).to(DEV), 40, torch.arange(8, device=DEV))[0, -1].cpu()
+    torch.testing.assert_close(got, logits[0], rtol=0, atol=1e-4)
+    # the state dict survives packing with the same logical content
+    back = m.state_dict()
+    for k in qsd:
+        assert torch.equal(back[k].cpu(), qsd[k]), k
+
+
+@pytest.mark.parametrize("mode", ["bnb.nf4", "bnb.int8"])
+def test_bnb_style_models(mode):
+    cfg = lp.Config(**QCFG)
+    fsd = O.random_state_dict(cfg, seed=32)
+    with lp.quantization(mode):
+        m = lp.GPT(cfg)
+    m.load_state_dict(fsd)
+    m = m.to(DEV).eval()
+    # oracle: dequantised weights through the fp32 reference arithmetic
+    dsd = {}
+    for k, v in fsd.items():
+        if v.dim() == 2 and "wte" not in k:
+            if mode == "bnb.nf4":
+                p, a = O.nf4_quantize(v)
+                dsd[k] = O.nf4_dequantize(p, a, v.shape)
+            else:
+                dsd[k] = O.int8_dequantize(*O.int8_quantize(v))
+        else:
+            dsd[k] = v
+    om = O.OracleGPT(cfg, dsd)
+    idx = torch.randint(0, cfg.padded_vocab_size, (1, 9), generator=torch.Generator().manual_seed(4))
+    torch.testing.assert_close(m(idx.to(DEV)).cpu(), om(idx), rtol=0, atol=1e-4)
+
+
+def test_real_width_two_layer_llama7b_bf16():
+    """Llama-2-7b widths (E 4096, I 11008, V 32000, hs 128), 2 layers, bf16 weights, fp32 activations: 64 greedy tokens
+    identical to the oracle (fp32 arithmetic on the bf16 weights) and logits within tolerance."""
+    cfg = lp.Config.from_name("Llama-2-7b-hf", n_layer=2, block_size=128)
+    sd = {k: v.bfloat16() for k, v in O.random_state_dict(cfg, seed=1234).items()}
+    m = build(cfg, sd, dtype=torch.bfloat16)
+    m.kv_cache_dtype = torch.float32
+    om = O.OracleGPT(cfg, {k: v.float() for k, v in sd.items()})
+    prompt = torch.randint(0, cfg.vocab_size, (16,), generator=torch.Generator().manual_seed(1)).to(torch.int32)
+    logits = []
+    want = O.generate(om, prompt, 80, 80, top_k=1, argmax_ties=True, logits_out=logits)
+    lg = torch.stack(logits)
+    top2 = torch.topk(lg, 2, dim=-1).values
+    min_gap = float((top2[:, 0] - top2[:, 1]).min())
+    out = lp.generate(m, prompt.to(DEV), 80, 80, top_k=1)
+    assert torch.equal(out.cpu(), want), f"min oracle top1-top2 gap {min_gap:.2e}"
+    m.reset_cache()
+    got = m._forward_impl(prompt.view(1, -1).to(DEV), 80, torch.arange(16, device=DEV), last_only=True, raw_logits=True)
+    got = got[0, -1].float().cpu()
+    assert (got - lg[0]).abs().max() < 2e-2 and cosine(got, lg[0]) > 0.999
