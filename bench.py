@@ -212,7 +212,7 @@ def run_workload(workload, steps, warmup, device, rank=0, world=1, with_e2e=True
             h_out.copy_(t, non_blocking=True)
             torch.cuda.current_stream(device).synchronize()
             h_idx[:, 0] = h_out.long()
-            h_pos += 1
+            h_pos.add_(1)
 
         for _ in range(warmup):
             e2e_step()

@@ -107,6 +107,13 @@ int lp_norm(int kind, const float* x, const float* weight, const float* bias, fl
 int lp_linear(const float* x, int M, const lp_weight* W, int epilogue, const float* residual, float* out,
               int round_bf16, void* stream);
 
+/* lp_norm fused into lp_linear as a prologue (each CTA normalises x while its first weight tiles are in flight):
+ * out = epilogue(norm(x) . W^T + bias).  Returns LP_ERR_UNSUPPORTED when the fusion is not available for this
+ * shape / format / mode (bf16-faithful rounding, M > 4, formats other than bf16 and int4): callers then issue
+ * lp_norm followed by lp_linear. */
+int lp_norm_linear(int norm_kind, const float* norm_w, const float* norm_b, float eps, const float* x, int M,
+                   const lp_weight* W, int epilogue, const float* residual, float* out, int round_bf16, void* stream);
+
 /* replaces the q/k regroup + apply_rope + torch.cat + cache index_copy_ of CausalSelfAttention.forward
  * (model.py:208-245, 330-336).  qkv [B*T, (H+2G)*hs] rows group-interleaved [q x q_per_kv, k, v] (model.py:210-214);
  * cos/sin fp32 [block_size, n_elem]; pos int32 [T] (shared by the batch, model.py:88-92).

@@ -41,6 +41,8 @@ PROTOTYPES = {
     "lp_embed": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "lp_norm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
     "lp_linear": (c_int, [c_void_p, c_int, ctypes.POINTER(LpWeight), c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "lp_norm_linear": (c_int, [c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, ctypes.POINTER(LpWeight), c_int, c_void_p,
+                               c_void_p, c_int, c_void_p]),
     "lp_rope_kv_append": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "lp_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),

@@ -8,6 +8,14 @@ namespace lp {
 int linear_fma(const float* x, int M, const lp_weight& W, int epi, const float* residual, float* out, int round_bf16, void* stream);
 int linear_mma(const float* x, int M, const lp_weight& W, int epi, const float* residual, float* out, int round_bf16, void* stream);
 int linear_mma_max_m();
+struct NormArgs {
+  const float* w;
+  const float* b;
+  float eps;
+  int kind;
+};
+int linear_mma_norm(const float* x, int M, const lp_weight& W, const NormArgs& nrm, int epi, const float* residual, float* out,
+                    int round_bf16, void* stream);
 static std::atomic<int> g_path{0};  // 0 auto, 1 force FMA, 2 force MMA
 }  // namespace lp
 
@@ -31,18 +39,9 @@ int lp_linear(const float* x, int M, const lp_weight* Wp, int epilogue, const fl
   const int out_ld = epilogue == LP_EPI_SWIGLU ? W.N / 2 : W.N;
 
   if (path != 1) {
-    const int step = lp::linear_mma_max_m();
-    int rc = LP_OK;
-    bool ok = true;
-    for (int m0 = 0; m0 < M && ok; m0 += step) {
-      const int mc = (M - m0) < step ? (M - m0) : step;
-      rc = lp::linear_mma(x + (size_t)m0 * W.K, mc, W, epilogue, residual ? residual + (size_t)m0 * W.N : nullptr,
-                          out + (size_t)m0 * out_ld, round_bf16, stream);
-      if (rc == LP_ERR_UNSUPPORTED && m0 == 0) ok = false;  // shape not covered: use the FMA family
-      else if (rc != LP_OK) return rc;
-    }
-    if (ok) return LP_OK;
-    if (path == 2) return LP_ERR_UNSUPPORTED;
+    // the MMA family takes the call when the whole activation block fits its column budget, else the FMA family does
+    const int rc = lp::linear_mma(x, M, W, epilogue, residual, out, round_bf16, stream);
+    if (rc != LP_ERR_UNSUPPORTED || path == 2) return rc;
   }
   for (int m0 = 0; m0 < M; m0 += LP_LINEAR_MAX_M) {
     const int mc = (M - m0) < LP_LINEAR_MAX_M ? (M - m0) : LP_LINEAR_MAX_M;
@@ -51,6 +50,21 @@ int lp_linear(const float* x, int M, const lp_weight* Wp, int epilogue, const fl
     if (rc != LP_OK) return rc;
   }
   return LP_OK;
+}
+
+
+int lp_norm_linear(int norm_kind, const float* norm_w, const float* norm_b, float eps, const float* x, int M, const lp_weight* Wp,
+                   int epilogue, const float* residual, float* out, int round_bf16, void* stream) {
+  if (!x || !Wp || !out || !norm_w || M <= 0) return LP_ERR_INVALID_ARG;
+  if (norm_kind != LP_NORM_LAYERNORM && norm_kind != LP_NORM_RMS) return LP_ERR_INVALID_ARG;
+  const lp_weight& W = *Wp;
+  if (!W.w || W.N <= 0 || W.K <= 0) return LP_ERR_INVALID_ARG;
+  if (epilogue < LP_EPI_NONE || epilogue > LP_EPI_RESIDUAL) return LP_ERR_INVALID_ARG;
+  if (epilogue == LP_EPI_RESIDUAL && !residual) return LP_ERR_INVALID_ARG;
+  if (epilogue == LP_EPI_SWIGLU && (W.N & 1)) return LP_ERR_INVALID_ARG;
+  if (round_bf16 || lp::g_path.load() == 1) return LP_ERR_UNSUPPORTED;  // bf16-faithful norm roundings live in lp_norm
+  lp::NormArgs nrm = {norm_w, norm_b, eps, norm_kind};
+  return lp::linear_mma_norm(x, M, W, nrm, epilogue, residual, out, round_bf16, stream);
 }
 
 }  // extern "C"

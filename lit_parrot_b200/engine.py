@@ -177,43 +177,44 @@ class Engine:
         scale = 1.0 / math.sqrt(hs)
         wte_dt = _KV_OF_DTYPE[self.wte.dtype]
         chk(lib.lp_embed(idx_ptr, idx64, idx_off, self.wte.data_ptr(), wte_dt, x, rows, E, r, stream), "lp_embed")
+        def norm_linear(src, nw, nb, W, epi, dst, scratch, what):
+            """norm fused into the GEMV prologue where the kernel supports it, else lp_norm + lp_linear."""
+            rc = lib.lp_norm_linear(self.norm_kind, _ptr(nw), _ptr(nb), cfg.norm_eps, src, rows, W.ref, epi, None, dst, r, stream)
+            if rc == -2:
+                chk(lib.lp_norm(self.norm_kind, src, _ptr(nw), _ptr(nb), cfg.norm_eps, scratch, rows, E, r, stream), "lp_norm")
+                rc = lib.lp_linear(scratch, rows, W.ref, epi, None, dst, r, stream)
+            chk(rc, what)
+
         for li, L in enumerate(self.layers):
             kc, vc = caches[li][0].data_ptr(), caches[li][1].data_ptr()
-            chk(lib.lp_norm(self.norm_kind, x, _ptr(L.n1_w), _ptr(L.n1_b), cfg.norm_eps, n1, rows, E, r, stream), "lp_norm")
-            chk(lib.lp_linear(n1, rows, L.qkv.ref, _lib.LP_EPI_NONE, None, qkv, r, stream), "lp_linear(qkv)")
+            norm_linear(x, L.n1_w, L.n1_b, L.qkv, _lib.LP_EPI_NONE, qkv, n1, "lp_linear(qkv)")
             chk(lib.lp_rope_kv_append(qkv, _ptr(self.cos), _ptr(self.sin), pos_ptr, q, kc, vc, kvd, B, T, H, G, hs,
                                       cfg.rope_n_elem, max_seq, r, stream), "lp_rope_kv_append")
             chk(lib.lp_attn_decode(q, kc, vc, kvd, pos_ptr, att, ws, ws_bytes, B, T, H, G, hs, max_seq, scale, r, stream),
                 "lp_attn_decode")
             if cfg.parallel_residual:
-                if cfg.shared_attention_norm:
-                    mlp_in = n1
-                else:
-                    chk(lib.lp_norm(self.norm_kind, x, _ptr(L.n2_w), _ptr(L.n2_b), cfg.norm_eps, n2, rows, E, r, stream),
-                        "lp_norm")
-                    mlp_in = n2
+                # x + attn(n1) + mlp(n2), n2 = n1 when the norm is shared (model.py:169-171); both GEMVs read the old x
+                n2w, n2b = (L.n1_w, L.n1_b) if cfg.shared_attention_norm else (L.n2_w, L.n2_b)
+                norm_linear(x, n2w, n2b, L.fc, self.act, u, n2, "lp_linear(fc)")
                 chk(lib.lp_linear(att, rows, L.proj.ref, _lib.LP_EPI_RESIDUAL, x, xmid, r, stream), "lp_linear(proj)")
-                chk(lib.lp_linear(mlp_in, rows, L.fc.ref, self.act, None, u, r, stream), "lp_linear(fc)")
                 chk(lib.lp_linear(u, rows, L.mlp_proj.ref, _lib.LP_EPI_RESIDUAL, xmid, x, r, stream), "lp_linear(mlp.proj)")
             else:
                 if cfg.shared_attention_norm:
                     raise NotImplementedError("No checkpoint amongst the ones we support uses this configuration"
                                               " (non-parallel residual and shared attention norm).")
                 chk(lib.lp_linear(att, rows, L.proj.ref, _lib.LP_EPI_RESIDUAL, x, x, r, stream), "lp_linear(proj)")
-                chk(lib.lp_norm(self.norm_kind, x, _ptr(L.n2_w), _ptr(L.n2_b), cfg.norm_eps, n2, rows, E, r, stream), "lp_norm")
-                chk(lib.lp_linear(n2, rows, L.fc.ref, self.act, None, u, r, stream), "lp_linear(fc)")
+                norm_linear(x, L.n2_w, L.n2_b, L.fc, self.act, u, n2, "lp_linear(fc)")
                 chk(lib.lp_linear(u, rows, L.mlp_proj.ref, _lib.LP_EPI_RESIDUAL, x, x, r, stream), "lp_linear(mlp.proj)")
         xf, logits = b["xf"].data_ptr(), b["logits"].data_ptr()
         if last_only and T > 1:
-            # only the last position of each sequence feeds the sampler (generate/base.py:136)
+            # only the last position of each sequence feeds the sampler (generate/base.py:136): gather those rows
             for bi in range(B):
-                off = ((bi + 1) * T - 1) * E * 4
-                chk(lib.lp_norm(self.norm_kind, x + off, _ptr(self.lnf_w), _ptr(self.lnf_b), cfg.norm_eps, xf + bi * E * 4, 1, E, r,
+                src = x + ((bi + 1) * T - 1) * E * 4
+                chk(lib.lp_norm(self.norm_kind, src, _ptr(self.lnf_w), _ptr(self.lnf_b), cfg.norm_eps, xf + bi * E * 4, 1, E, r,
                                 stream), "lp_norm")
             chk(lib.lp_linear(xf, B, self.lm_head.ref, _lib.LP_EPI_NONE, None, logits, r, stream), "lp_linear(lm_head)")
         else:
-            chk(lib.lp_norm(self.norm_kind, x, _ptr(self.lnf_w), _ptr(self.lnf_b), cfg.norm_eps, xf, rows, E, r, stream), "lp_norm")
-            chk(lib.lp_linear(xf, rows, self.lm_head.ref, _lib.LP_EPI_NONE, None, logits, r, stream), "lp_linear(lm_head)")
+            norm_linear(x, self.lnf_w, self.lnf_b, self.lm_head, _lib.LP_EPI_NONE, logits, xf, "lp_linear(lm_head)")
 
     # ------------------------------------------------------------------ public entry used by GPT.forward
     def _check_caches(self, caches, B: int) -> None:

@@ -288,12 +288,25 @@ def gptq_rtn_quantize(w: Tensor, tile_cols: int, bits: int = 4):
     return packed, scales, zeros
 
 
-def gptq_dequant(quant_weight: Tensor, scales: Tensor, zeros: Tensor, dtype=torch.float32, bits: int = 4) -> Tensor:
+def infer_tile_cols(in_f: int, n_tiles: int) -> int:
+    """The module stores `tile_cols` (gptq.py:209); a bare state dict only has n_tiles = ceil(in/tile_cols).  Exact when
+    divisible; for a ragged last tile pick the multiple of 32 that reproduces n_tiles (e.g. 4544 / 36 tiles -> 128)."""
+    if in_f % n_tiles == 0:
+        return in_f // n_tiles
+    for t in range(32, in_f + 32, 32):
+        if -(-in_f // t) == n_tiles:
+            return t
+    return -(-in_f // n_tiles)
+
+
+def gptq_dequant(quant_weight: Tensor, scales: Tensor, zeros: Tensor, dtype=torch.float32, bits: int = 4,
+                 tile_cols: Optional[int] = None) -> Tensor:
     """quantize/gptq.py:243-252: nibble -> float, then `-= zero`, `*= scale` evaluated in `dtype`
     (so in bf16 the dequantised weight is rounded to bf16 before the matmul)."""
     out_f, per = quant_weight.shape[0], 8 // bits
     in_f = quant_weight.shape[1] * per
-    tile_cols = -(-in_f // scales.shape[1])
+    if tile_cols is None:
+        tile_cols = infer_tile_cols(in_f, scales.shape[1])
     w = torch.empty((out_f, in_f), dtype=dtype)
     m = (1 << bits) - 1
     for nr in range(per):

@@ -99,6 +99,7 @@ def test_linear_gptq_int4(lib, path, group, M, N, K):
     assert int(rows[:, K // 2:].sum()) == 0
     x = f32(M, K, seed=6)
     g = K if group == -1 else group
+    assert O.infer_tile_cols(K, scales.shape[1]) == g
     wd = O.gptq_dequant(packed, scales, zeros)  # fp32 dequant, as the reference does for fp32 activations
     want = F.linear(x.cpu().double(), wd.double()).float().to(DEV)
     got = run_linear(lib, x, rows, _lib.LP_W_INT4, N, K, aux0=scales.to(DEV).contiguous(), aux1=zeros.to(DEV).contiguous(),
@@ -273,3 +274,35 @@ def test_sample_distribution(lib):
         counts += np.bincount(tok.cpu().numpy(), minlength=V)
     chi2 = float(((counts - n * p) ** 2 / (n * p)).sum())
     assert chi2 < 45.0, chi2  # 11 dof: P(chi2 > 45) ~ 5e-6
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("fmt", ["bf16", "int4"])
+@pytest.mark.parametrize("M,N,K", [(1, 64, 128), (2, 256, 512), (4, 96, 1024), (1, 4672, 4544)])
+def test_norm_linear_fused(lib, kind, fmt, M, N, K):
+    """lp_norm_linear (norm as the GEMV prologue) == lp_norm followed by lp_linear == torch restatement."""
+    x, nw, nb = f32(M, K, seed=1), 1 + 0.1 * f32(K, seed=2), 0.1 * f32(K, seed=3)
+    xn = (F.layer_norm(x, (K,), nw, nb, 1e-5) if kind == 0 else O.rms_norm(x, nw, 1e-5)).double()
+    p = lambda a: None if a is None else a.data_ptr()  # noqa: E731
+    if fmt == "bf16":
+        w = f32(N, K, seed=4, scale=0.05).bfloat16()
+        rec = LpWeight(w.data_ptr(), None, None, None, _lib.LP_W_BF16, N, K, 0)
+        want = F.linear(xn, w.double()).float()
+    else:
+        wf = torch.randn(N, K, generator=torch.Generator().manual_seed(5)) * 0.02
+        packed, scales, zeros = O.gptq_rtn_quantize(wf, 128)
+        src = torch.empty((K // 2, N), dtype=torch.uint8, device=DEV).t()
+        src.copy_(packed)
+        rows = torch.empty((N, lib.lp_int4_row_bytes(K)), dtype=torch.uint8, device=DEV)
+        _lib.check(lib.lp_repack_gptq_int4(src.data_ptr(), rows.data_ptr(), N, K, stream()))
+        sc, ze = scales.to(DEV).contiguous(), zeros.to(DEV).contiguous()
+        rec = LpWeight(rows.data_ptr(), sc.data_ptr(), ze.data_ptr(), None, _lib.LP_W_INT4, N, K, 128)
+        want = F.linear(xn, O.gptq_dequant(packed, scales, zeros, tile_cols=128).double().to(DEV)).float()
+    out = torch.full((M, N), float("nan"), device=DEV)
+    rc = lib.lp_norm_linear(kind, nw.data_ptr(), p(nb if kind == 0 else None), 1e-5, x.data_ptr(), M, ctypes.byref(rec), 0, None,
+                            out.data_ptr(), 0, stream())
+    _lib.check(rc, "lp_norm_linear")
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out, want, rtol=3e-5, atol=3e-5 * math.sqrt(K))
+    # the fusion must decline (not mis-compute) what it does not cover
+    assert lib.lp_norm_linear(kind, nw.data_ptr(), None, 1e-5, x.data_ptr(), M, ctypes.byref(rec), 0, None, out.data_ptr(), 1, stream()) == -2

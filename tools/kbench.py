@@ -1,0 +1,107 @@
+"""Kernel micro-benchmarks on a B200 (CUDA events, rotating operands larger than L2).  Not a bench.py value: a tuning aid.
+
+    python tools/kbench.py [linear] [attn]
+"""
+import ctypes
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lit_parrot_b200 import _lib  # noqa: E402
+from lit_parrot_b200._lib import LpWeight  # noqa: E402
+
+DEV = torch.device("cuda", 0)
+lib = _lib.init(0)
+PEAK = 6550.0
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def timeit(fn, iters=50, warm=5):
+    for i in range(warm):
+        fn(i)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(iters):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / iters  # us
+
+
+def bench_linear():
+    shapes = [("qkv7b", 12288, 4096), ("proj7b", 4096, 4096), ("fc7b(swiglu)", 22016, 4096), ("mlpproj7b", 4096, 11008),
+              ("lmhead7b", 32000, 4096), ("fc3b", 16384, 4096), ("falcon qkv", 4672, 4544), ("fc70b/tp8", 7168, 8192)]
+    print(f"{'shape':16s} {'fmt':5s} {'M':>2s} {'path':4s} {'us':>8s} {'GB/s':>8s} {'%peak':>6s}")
+    for name, N, K in shapes:
+        for fmt in ("bf16", "int4"):
+            nbuf = max(2, int(400e6 // (N * K * (2 if fmt == "bf16" else 0.5))) + 1)
+            nbuf = min(nbuf, 24)
+            recs, keep = [], []
+            for i in range(nbuf):
+                if fmt == "bf16":
+                    w = torch.randn(N, K, device=DEV, dtype=torch.bfloat16) * 0.02
+                    keep.append(w)
+                    recs.append(LpWeight(w.data_ptr(), None, None, None, _lib.LP_W_BF16, N, K, 0))
+                    nbytes = N * K * 2
+                else:
+                    rb = lib.lp_int4_row_bytes(K)
+                    w = torch.randint(0, 256, (N, rb), device=DEV, dtype=torch.uint8)
+                    ng = (K + 127) // 128
+                    sc = torch.rand(N, ng, device=DEV) * 0.01
+                    ze = torch.full((N, ng), 8.0, device=DEV)
+                    keep += [w, sc, ze]
+                    recs.append(LpWeight(w.data_ptr(), sc.data_ptr(), ze.data_ptr(), None, _lib.LP_W_INT4, N, K, 128))
+                    nbytes = N * rb + 2 * N * ng * 4
+            for M in (1, 2, 4):
+                x = torch.randn(M, K, device=DEV)
+                out = torch.empty(M, N, device=DEV)
+                for path, pname in ((1, "fma"), (2, "mma")):
+                    lib.lp_set_linear_path(path)
+                    rc = lib.lp_linear(x.data_ptr(), M, ctypes.byref(recs[0]), 0, None, out.data_ptr(), 0, stream())
+                    if rc != 0:
+                        print(f"{name:16s} {fmt:5s} {M:2d} {pname:4s} unsupported ({rc})")
+                        continue
+                    us = timeit(lambda i: lib.lp_linear(x.data_ptr(), M, ctypes.byref(recs[i % nbuf]), 0, None, out.data_ptr(), 0, stream()))
+                    print(f"{name:16s} {fmt:5s} {M:2d} {pname:4s} {us:8.2f} {nbytes / us / 1e3:8.0f} {100 * nbytes / us / 1e3 / PEAK:6.1f}")
+            lib.lp_set_linear_path(0)
+            del recs, keep
+            torch.cuda.empty_cache()
+    # plain streaming read reference: torch sum over a large bf16 buffer
+    big = torch.empty(1 << 30, device=DEV, dtype=torch.bfloat16).normal_()
+    us = timeit(lambda i: big.sum(), iters=10, warm=2)
+    print(f"torch.sum over 2 GiB: {us:.0f} us = {big.numel() * 2 / us / 1e3:.0f} GB/s (read-only streaming reference)")
+
+
+def bench_attn():
+    print(f"{'case':28s} {'kv':5s} {'us':>8s} {'GB/s':>8s}")
+    for name, B, H, G, hs, ctx in [("3b B=1 ctx2k", 1, 32, 32, 128, 2048), ("3b B=32 ctx2k", 32, 32, 32, 128, 2048),
+                                   ("70b B=1 ctx2k", 1, 64, 8, 128, 2048), ("falcon B=1 ctx2k", 1, 71, 1, 64, 2048),
+                                   ("7b B=1 ctx512", 1, 32, 32, 128, 512)]:
+        for kvdt in (torch.bfloat16,):
+            L = 4
+            kc = [torch.randn(B, G, ctx, hs, device=DEV).to(kvdt) for _ in range(L)]
+            vc = [torch.randn(B, G, ctx, hs, device=DEV).to(kvdt) for _ in range(L)]
+            q = torch.randn(B, H * hs, device=DEV)
+            out = torch.empty(B, H * hs, device=DEV)
+            pos = torch.tensor([ctx - 1], dtype=torch.int32, device=DEV)
+            ws = torch.empty(lib.lp_attn_workspace_bytes(B, 1, H, hs, ctx) + 16, dtype=torch.uint8, device=DEV)
+            fn = lambda i: lib.lp_attn_decode(q.data_ptr(), kc[i % L].data_ptr(), vc[i % L].data_ptr(), 1, pos.data_ptr(), out.data_ptr(),  # noqa: E731
+                                              ws.data_ptr(), ws.numel(), B, 1, H, G, hs, ctx, 1 / math.sqrt(hs), 0, stream())
+            us = timeit(fn, iters=30)
+            nbytes = 2 * B * G * ctx * hs * 2
+            print(f"{name:28s} {'bf16':5s} {us:8.2f} {nbytes / us / 1e3:8.0f}")
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["linear", "attn"]
+    if "linear" in what:
+        bench_linear()
+    if "attn" in what:
+        bench_attn()
