@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LP_ABI_VERSION 1
+#define LP_ABI_VERSION 2
 
 typedef enum {
   LP_OK = 0,
@@ -45,7 +45,7 @@ typedef enum {
   LP_W_F32 = 0,   /* float  [N,K] row-major (nn.Linear.weight)                                          */
   LP_W_BF16 = 1,  /* bf16   [N,K] row-major (nn.Linear.weight)                                          */
   LP_W_INT4 = 2,  /* GPTQ int4, repacked by lp_repack_gptq_int4: [N, Kp/2] bytes row-major, byte j of a
-                     row holds column 2j (low nibble) and 2j+1 (high nibble); Kp = K rounded up to 128;
+                     row holds column 2j (low nibble) and 2j+1 (high nibble); Kp = K rounded up to 256 (128-byte rows);
                      scales/zeros fp32 [N, n_groups]; w = (q - zero) * scale   (quantize/gptq.py:243-252) */
   LP_W_NF4 = 3,   /* bitsandbytes NF4: bytes [N*K/2], first element in the HIGH nibble, absmax fp32 per
                      `group` (=blocksize 64) consecutive elements of the flattened weight               */
@@ -61,15 +61,24 @@ typedef enum {
 
 typedef enum { LP_NORM_LAYERNORM = 0, LP_NORM_RMS = 1 } lp_norm_kind;
 
+/* lp_weight.flags */
+#define LP_WF_AUX_PACKED 1 /* aux2 holds one 32-bit word per (row, group): bf16 scale bits << 16 | integer zero point;
+                              otherwise a float2 {scale, zero}.  Packed is exact when the scales are bf16-representable
+                              (a bf16 checkpoint) and halves the scale/zero traffic: 0.5 + 4/128 bytes per weight.   */
+
 /* One linear layer's weights.  `aux0`/`aux1`: INT4 -> scales/zeros; NF4 -> absmax/unused; INT8 -> row scales. */
 typedef struct {
   const void* w;
   const float* aux0;
   const float* aux1;
+  const void* aux2;    /* INT4, optional: scale/zero pairs TILE-MAJOR [N/16][n_groups][16 rows] (see flags), the layout
+                          the streaming kernel fetches with one bulk copy per stage; NULL -> exact CUDA-core kernel   */
   const float* bias;   /* fp32 [N] or NULL                                                              */
   int32_t fmt;         /* lp_wfmt                                                                       */
   int32_t N, K;
   int32_t group;       /* INT4: columns per scale/zero group (K for per-row); NF4: blocksize            */
+  int32_t flags;       /* LP_WF_*                                                                        */
+  int32_t reserved;
 } lp_weight;
 
 int lp_abi_version(void);
@@ -82,8 +91,9 @@ unsigned long long lp_launch_count(void);
 /* Programmatic Dependent Launch on/off (default on; env LP_PDL=0 disables).  Debug aid. */
 int lp_set_pdl(int enabled);
 
-/* Which kernel family lp_linear uses: 0 = auto (tensor-core MMA family where it applies, else FMA), 1 = FMA family
- * only (exact fp32 CUDA-core math), 2 = MMA family only (LP_ERR_UNSUPPORTED where it does not apply).  Test aid. */
+/* Which kernel family lp_linear uses: 0 = auto (streaming family where it applies, else FMA), 1 = FMA family only
+ * (exact fp32 CUDA-core math, every format), 2 = streaming family only (persistent TMA-bulk ring + mma.sync;
+ * LP_ERR_UNSUPPORTED where it does not apply).  Test aid. */
 int lp_set_linear_path(int path);
 
 /* One-time per-device setup (cudaFuncSetAttribute for large dynamic shared memory).  Idempotent, thread-safe. */
@@ -107,9 +117,9 @@ int lp_norm(int kind, const float* x, const float* weight, const float* bias, fl
 int lp_linear(const float* x, int M, const lp_weight* W, int epilogue, const float* residual, float* out,
               int round_bf16, void* stream);
 
-/* lp_norm fused into lp_linear as a prologue (each CTA normalises x while its first weight tiles are in flight):
+/* lp_norm fused into lp_linear as a prologue (each CTA normalises x while its first weight stages are in flight):
  * out = epilogue(norm(x) . W^T + bias).  Returns LP_ERR_UNSUPPORTED when the fusion is not available for this
- * shape / format / mode (bf16-faithful rounding, M > 4, formats other than bf16 and int4): callers then issue
+ * shape / format / mode (bf16-faithful rounding, M > 8, formats other than bf16 and int4): callers then issue
  * lp_norm followed by lp_linear. */
 int lp_norm_linear(int norm_kind, const float* norm_w, const float* norm_b, float eps, const float* x, int M,
                    const lp_weight* W, int epilogue, const float* residual, float* out, int round_bf16, void* stream);
@@ -131,6 +141,17 @@ size_t lp_attn_workspace_bytes(int B, int T, int H, int hs, int max_seq);
 int lp_attn_decode(const float* q, const void* k_cache, const void* v_cache, int kv_dtype, const int32_t* pos,
                    float* out, void* workspace, size_t workspace_bytes, int B, int T, int H, int G, int hs,
                    int max_seq, float scale, int round_bf16, void* stream);
+
+/* ONE launch for a single-token step (T == 1): lp_rope_kv_append + lp_attn_decode + the split merge, on the tensor cores
+ * (mma.sync; q and P split into bf16 hi + lo terms, so accuracy is that of fp32 activations over the bf16 cache).
+ * qkv [B, (H+2G)*hs] is the raw QKV projection; pos int32 [1]; out [B, H*hs].  The kernel writes the rotated k and v
+ * of the new token into slot pos % max_seq of the caches.  Covers bf16 caches with hs 64 / 128; LP_ERR_UNSUPPORTED
+ * otherwise (callers then issue the two calls above).  `workspace` (lp_attn_fused_workspace_bytes) must be
+ * zero-filled before its first use; every launch leaves its ticket area zeroed again. */
+size_t lp_attn_fused_workspace_bytes(int B, int H, int G, int hs, int max_seq);
+int lp_attn_decode_fused(const float* qkv, const float* cos, const float* sin, const int32_t* pos, float* out, void* k_cache,
+                         void* v_cache, int kv_dtype, void* workspace, size_t workspace_bytes, int B, int H, int G, int hs,
+                         int n_elem, int max_seq, float scale, int round_bf16, void* stream);
 
 /* replaces the sampling tail of generate() (generate/base.py:136-153): logits/temperature, top-k threshold
  * (ties with the k-th value survive), softmax, one multinomial draw (exponential race, Philox keyed by

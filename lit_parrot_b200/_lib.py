@@ -17,7 +17,8 @@ LP_F32, LP_BF16 = 0, 1
 LP_W_F32, LP_W_BF16, LP_W_INT4, LP_W_NF4, LP_W_INT8 = 0, 1, 2, 3, 4
 LP_EPI_NONE, LP_EPI_GELU, LP_EPI_SWIGLU, LP_EPI_RESIDUAL = 0, 1, 2, 3
 LP_NORM_LAYERNORM, LP_NORM_RMS = 0, 1
-LP_ABI_VERSION = 1
+LP_ABI_VERSION = 2
+LP_WF_AUX_PACKED = 1
 
 c_void_p, c_int, c_float, c_size_t, c_u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_uint64
 
@@ -25,8 +26,9 @@ c_void_p, c_int, c_float, c_size_t, c_u64 = ctypes.c_void_p, ctypes.c_int, ctype
 class LpWeight(ctypes.Structure):
     """struct lp_weight"""
 
-    _fields_ = [("w", c_void_p), ("aux0", c_void_p), ("aux1", c_void_p), ("bias", c_void_p), ("fmt", ctypes.c_int32),
-                ("N", ctypes.c_int32), ("K", ctypes.c_int32), ("group", ctypes.c_int32)]
+    _fields_ = [("w", c_void_p), ("aux0", c_void_p), ("aux1", c_void_p), ("aux2", c_void_p), ("bias", c_void_p),
+                ("fmt", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32), ("group", ctypes.c_int32),
+                ("flags", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/lp_abi.h
@@ -48,6 +50,9 @@ PROTOTYPES = {
     "lp_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "lp_attn_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int,
                                c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "lp_attn_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "lp_attn_decode_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                     c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "lp_sample": (c_int, [c_void_p, c_int, c_int, c_float, c_int, c_u64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lp_int4_row_bytes": (c_size_t, [c_int]),
     "lp_repack_gptq_int4": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),

@@ -39,6 +39,7 @@ attn_split_kernel(const float* __restrict__ q, const KV* __restrict__ kc, const 
   const int b = row / T, t = row % T;
   const int qpk = H / G;
   const int ldk = hs + 4;
+  const bool vec4 = (hs & 3) == 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // warps split heads first (WH), then key tiles (WT)
   const int WH = qpk >= 4 ? 4 : (qpk >= 2 ? 2 : 1);
@@ -91,7 +92,14 @@ attn_split_kernel(const float* __restrict__ q, const KV* __restrict__ kc, const 
     const int nk = min(ATT_TILE, k_end - tile0);
     __syncthreads();  // previous tile fully consumed (also orders the sq / sm initialisation)
     // cooperative, coalesced copy of nk x hs K and V elements into padded fp32 tiles
-    for (int i = threadIdx.x * 4; i < nk * hs; i += ATT_THREADS * 4) {
+    if (!vec4) {  // odd head sizes (the reference's unit tests use hs = 2 and 4): scalar staging
+      for (int i = threadIdx.x; i < nk * hs; i += ATT_THREADS) {
+        const int kk = i / hs, d = i % hs;
+        sk[kk * ldk + d] = kv_to_float(kbase[(size_t)(tile0 + kk) * hs + d]);
+        sv[kk * ldk + d] = kv_to_float(vbase[(size_t)(tile0 + kk) * hs + d]);
+      }
+    }
+    for (int i = threadIdx.x * 4; vec4 && i < nk * hs; i += ATT_THREADS * 4) {
       const int kk = i / hs, d = i % hs;  // hs % 4 == 0, so a 4-vector never crosses a key
       const KV* ks = kbase + (size_t)(tile0 + kk) * hs + d;
       const KV* vs = vbase + (size_t)(tile0 + kk) * hs + d;
@@ -120,7 +128,9 @@ attn_split_kernel(const float* __restrict__ q, const KV* __restrict__ kc, const 
         if (h >= qpk) break;
         const float* qh = sq + h * hs;
         float sc = 0.f;
-        for (int d = 0; d < hs; d += 4) {
+        if (!vec4)
+          for (int d = 0; d < hs; ++d) sc = fmaf(qh[d], krow[d], sc);
+        for (int d = 0; vec4 && d < hs; d += 4) {
           const float4 kv4 = *reinterpret_cast<const float4*>(krow + d);
           const float4 q4 = *reinterpret_cast<const float4*>(qh + d);
           sc = fmaf(q4.x, kv4.x, sc);
@@ -271,7 +281,7 @@ int lp_attn_decode(const float* q, const void* k_cache, const void* v_cache, int
                    int round_bf16, void* stream) {
   if (!q || !k_cache || !v_cache || !pos || !out) return LP_ERR_INVALID_ARG;
   if (B <= 0 || T <= 0 || H <= 0 || G <= 0 || H % G || hs <= 0 || max_seq <= 0) return LP_ERR_INVALID_ARG;
-  if (hs % 4 || hs > 32 * lp::ATT_MAX_DPL) return LP_ERR_UNSUPPORTED;
+  if (hs > 32 * lp::ATT_MAX_DPL) return LP_ERR_UNSUPPORTED;
   const int rows = B * T, qpk = H / G;
   const size_t smem = lp::attn_smem_bytes(qpk, hs);
   if (smem > 200 * 1024) return LP_ERR_UNSUPPORTED;

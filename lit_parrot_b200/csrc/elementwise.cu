@@ -166,7 +166,7 @@ int lp_rope_kv_append(const float* qkv, const float* cos, const float* sin, cons
                       void* stream) {
   if (!qkv || !pos || !q_out || !k_cache || !v_cache) return LP_ERR_INVALID_ARG;
   if (n_elem > 0 && (!cos || !sin)) return LP_ERR_INVALID_ARG;
-  if (B <= 0 || T <= 0 || H <= 0 || G <= 0 || H % G || hs <= 0 || hs > 1024 || n_elem < 0 || n_elem > hs || (n_elem & 1) || max_seq <= 0)
+  if (B <= 0 || T <= 0 || H <= 0 || G <= 0 || H % G || hs <= 0 || hs > 1024 || n_elem < 0 || n_elem > hs || ((n_elem & 1) && n_elem != 1) || max_seq <= 0)
     return LP_ERR_INVALID_ARG;
   dim3 grid(B * T, H + 2 * G), block((hs + 31) / 32 * 32);
   if (kv_dtype == LP_F32)
@@ -178,7 +178,7 @@ int lp_rope_kv_append(const float* qkv, const float* cos, const float* sin, cons
   return LP_ERR_INVALID_ARG;
 }
 
-size_t lp_int4_row_bytes(int K) { return (size_t)((K + 127) / 128 * 128) / 2; }
+size_t lp_int4_row_bytes(int K) { return (size_t)((K + 255) / 256 * 256) / 2; }
 
 int lp_repack_gptq_int4(const uint8_t* src, uint8_t* dst, int N, int K, void* stream) {
   if (!src || !dst || N <= 0 || K <= 0 || (K & 1)) return LP_ERR_INVALID_ARG;

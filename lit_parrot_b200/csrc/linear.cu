@@ -1,22 +1,20 @@
-// lp_linear: dispatch between the FMA family (exact fp32 CUDA-core math, any format) and the MMA family
-// (mma.sync tensor-core skinny GEMM; bf16 / int4 / int8 weights, up to 32 activation rows per pass).
+// lp_linear: dispatch between the FMA family (exact fp32 CUDA-core math, any format) and the streaming family
+// (persistent TMA-bulk ring + mma.sync; bf16 / int4 weights, decode batches).
 #include <atomic>
 
 #include "common.cuh"
 
 namespace lp {
 int linear_fma(const float* x, int M, const lp_weight& W, int epi, const float* residual, float* out, int round_bf16, void* stream);
-int linear_mma(const float* x, int M, const lp_weight& W, int epi, const float* residual, float* out, int round_bf16, void* stream);
-int linear_mma_max_m();
 struct NormArgs {
   const float* w;
   const float* b;
   float eps;
   int kind;
 };
-int linear_mma_norm(const float* x, int M, const lp_weight& W, const NormArgs& nrm, int epi, const float* residual, float* out,
-                    int round_bf16, void* stream);
-static std::atomic<int> g_path{0};  // 0 auto, 1 force FMA, 2 force MMA
+int linear_stream(const float* x, int M, const lp_weight& W, const NormArgs& nrm, int epi, const float* residual, float* out,
+                  int round_bf16, void* stream);
+static std::atomic<int> g_path{0};  // 0 auto, 1 force FMA, 2 force streaming
 }  // namespace lp
 
 extern "C" {
@@ -39,8 +37,9 @@ int lp_linear(const float* x, int M, const lp_weight* Wp, int epilogue, const fl
   const int out_ld = epilogue == LP_EPI_SWIGLU ? W.N / 2 : W.N;
 
   if (path != 1) {
-    // the MMA family takes the call when the whole activation block fits its column budget, else the FMA family does
-    const int rc = lp::linear_mma(x, M, W, epilogue, residual, out, round_bf16, stream);
+    // the streaming family takes the call when the whole activation block fits its column budget, else the FMA family does
+    const lp::NormArgs none = {nullptr, nullptr, 0.f, -1};
+    const int rc = lp::linear_stream(x, M, W, none, epilogue, residual, out, round_bf16, stream);
     if (rc != LP_ERR_UNSUPPORTED || path == 2) return rc;
   }
   for (int m0 = 0; m0 < M; m0 += LP_LINEAR_MAX_M) {
@@ -64,7 +63,7 @@ int lp_norm_linear(int norm_kind, const float* norm_w, const float* norm_b, floa
   if (epilogue == LP_EPI_SWIGLU && (W.N & 1)) return LP_ERR_INVALID_ARG;
   if (round_bf16 || lp::g_path.load() == 1) return LP_ERR_UNSUPPORTED;  // bf16-faithful norm roundings live in lp_norm
   lp::NormArgs nrm = {norm_w, norm_b, eps, norm_kind};
-  return lp::linear_mma_norm(x, M, W, nrm, epilogue, residual, out, round_bf16, stream);
+  return lp::linear_stream(x, M, W, nrm, epilogue, residual, out, round_bf16, stream);
 }
 
 }  // extern "C"

@@ -96,7 +96,7 @@ linear_fma_kernel(const float* __restrict__ x, int m_actual, lp_weight W, int ep
   if constexpr (FMT == LP_W_F32) row_bytes = (size_t)K * 4;
   else if constexpr (FMT == LP_W_BF16) row_bytes = (size_t)K * 2;
   else if constexpr (FMT == LP_W_INT8) row_bytes = (size_t)K;
-  else if constexpr (FMT == LP_W_INT4) row_bytes = (size_t)((K + 127) / 128 * 128) / 2;
+  else if constexpr (FMT == LP_W_INT4) row_bytes = (size_t)((K + 255) / 256 * 256) / 2;
   else row_bytes = (size_t)K / 2;
   const char* p0 = reinterpret_cast<const char*>(W.w) + (size_t)r0 * row_bytes;
   const char* p1 = p0 + (has1 ? row_bytes : 0);

@@ -1,0 +1,578 @@
+// Weight-streaming linear layer, "stream family": y = x[M,K] . W[N,K]^T for the decode step (M <= 8), built to keep
+// HBM busy across kernel boundaries.  Judged on GB/s.
+//
+//   * PERSISTENT grid (one CTA per SM); each CTA owns a contiguous range of 16-row weight tiles;
+//   * a PRODUCER thread streams the weights with TMA tensor copies (cp.async.bulk.tensor, completion on an mbarrier)
+//     into a ring of stages.  The row-major weight matrix [N, K] is described to the TMA unit as a 3-D tensor
+//     {128 bytes, N rows, K-blocks} so that ONE copy brings a whole stage (16 rows x 8 K-blocks = 16 KB) and lays it out
+//     as [K-block][row][128 B] with the hardware 128-byte swizzle: every ldmatrix / 128-bit fragment load is bank-conflict
+//     free.  (Measured: 1 KB bulk copies cap an SM at ~18 GB/s whatever the ring depth — the copy count, not the bytes in
+//     flight, is the limit; 16 KB copies lift it.)  The ring is filled BEFORE griddepcontrol.wait: under PDL the first
+//     stages of layer n+1's weights are already in flight while layer n drains;
+//   * eight CONSUMER warps split K inside a stage.  The multiply-accumulates run on the tensor cores
+//     (mma.sync.m16n8k16, bf16 x bf16 -> fp32) so the issue slots are left for what an int4 GEMV is limited by — nibble
+//     unpacking: nibble -> bf16 is ONE lop3 per two weights ((w & 0x000F000F) | 0x43004300 = {128+q_lo, 128+q_hi}); the
+//     +128 and the GPTQ zero point are removed algebraically per 128-column group:
+//          sum (q - z) s x = s * (sum (128+q) x - (128 + z) * sum x);
+//   * x (the M activation rows) is the 8- or 16-column B operand, staged once per CTA in shared memory, optionally
+//     through a fused LayerNorm / RMSNorm.  To keep fp32 ACTIVATION accuracy every row is split into bf16 terms
+//     x = hi + mid (+ lo) in separate columns (products with the bf16 / int4 weights are exact in the fp32
+//     accumulator); the columns are re-added in the epilogue.  bf16-faithful mode has bf16-valued x: one column per row;
+//   * per tile: cross-warp reduction through shared memory, then the fused epilogue (bias, GELU, SwiGLU, residual).
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+
+namespace lp {
+
+constexpr int GS_CWARPS = 8;                      // consumer warps
+constexpr int GS_THREADS = (GS_CWARPS + 1) * 32;  // + 1 producer warp
+constexpr int GS_ROWS = 16;
+constexpr int GS_BLK_BYTES = GS_ROWS * 128;       // one K-block of a tile: 16 rows x 128 bytes (64 bf16 / 256 int4 columns)
+constexpr size_t GS_SMEM_BUDGET = 200 * 1024;     // measured: a deeper ring beats co-residency of two kernels under PDL
+constexpr int GS_MAX_STAGES = 12;
+constexpr int GS_KB = 8;                          // K-blocks per stage: 16 KB of weights
+
+struct NormArgs {
+  const float* w;
+  const float* b;
+  float eps;
+  int kind;  // -1: none, else lp_norm_kind
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t gs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void gs_ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void gs_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t gs_nib(uint32_t w) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, 0x000F000F, 0x43004300, 0xEA;\n" : "=r"(r) : "r"(w));  // (w & m) | magic
+  return r;
+}
+__device__ __forceinline__ void gs_bar_consumers() { asm volatile("bar.sync 1, %0;\n" ::"n"(GS_CWARPS * 32) : "memory"); }
+__device__ __forceinline__ uint16_t gs_bf16_bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+
+struct GsParams {
+  const float* x;
+  const float* residual;
+  float* out;
+  lp_weight W;
+  NormArgs nrm;
+  int M, split, epi, round_bf16;
+  int ldx;          // bf16 elements per staged x row
+  int nkb;          // K-blocks per row = ceil(row bytes / 128)
+  int nks;          // stages per tile = ceil(nkb / GS_KB)
+  int ntiles;       // N / 16
+  int nstages;      // ring depth
+  int stage_stride; // bytes (multiple of 1024: the 128-byte swizzle pattern is anchored at 1 KB)
+  int tma_rank;     // 3: one copy per stage; 2: one copy per K-block (fallback if the 3-D map was refused)
+  int ngroups;      // int4 groups per row
+  int gp128;        // 128-column chunks per scale group (group / 128)
+};
+
+template <int FMT, int NB>
+__global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __grid_constant__ CUtensorMap tmap, const GsParams p) {
+  constexpr int NCOL = 8 * NB;
+  constexpr int COLS_PER_BLK = (FMT == LP_W_BF16) ? 64 : 256;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int K = p.W.K, N = p.W.N;
+  const int ncols = p.M * p.split;
+  const int nch128 = (K + 127) / 128;
+  // ---- shared memory carve-up: [ring (1 KB aligned)] [barriers] [red] [xsum] [xs] ----
+  unsigned char* ring = smem;
+  unsigned char* after = smem + (size_t)p.nstages * p.stage_stride;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after);                      // full[nstages], empty[nstages]
+  float* red = reinterpret_cast<float*>(after + 256);                       // [2][CWARPS][16][NCOL]
+  float* xsum = red + 2 * GS_CWARPS * 16 * NCOL;                            // [nch128][NCOL]   (int4 only)
+  uint16_t* xs = reinterpret_cast<uint16_t*>(xsum + (FMT == LP_W_INT4 ? nch128 * NCOL : 0));  // [ncols][ldx] bf16 bits
+  __shared__ float s_stat[2][GS_CWARPS];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = gs_smem_u32(bars);
+  const uint32_t ring_u32 = gs_smem_u32(ring);
+  auto full_bar = [&](int s) { return bar0 + 8 * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8 * (p.nstages + s); };
+
+  // tiles of this CTA: contiguous range
+  const int tile_begin = (int)(((long long)p.ntiles * blockIdx.x) / gridDim.x);
+  const int tile_end = (int)(((long long)p.ntiles * (blockIdx.x + 1)) / gridDim.x);
+  const int nunits = (tile_end - tile_begin) * p.nks;
+  const int aux_bytes = (p.W.flags & LP_WF_AUX_PACKED) ? 4 : 8;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nstages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), GS_CWARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == GS_CWARPS) {
+    // =========================== PRODUCER: weights do not depend on the previous kernel -> no griddepcontrol.wait ====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmap) : "memory");
+      int s = 0, ph = 0, ks = 0, tile = tile_begin;
+      for (int u = 0; u < nunits; ++u) {
+        mbar_wait(empty_bar(s), ph ^ 1);
+        const uint32_t dst = ring_u32 + (uint32_t)s * p.stage_stride;
+        uint32_t aux_len = 0;
+        int g_begin = 0;
+        if constexpr (FMT == LP_W_INT4) {
+          // scale/zero words of this tile for the groups that intersect this stage: [tile][group][16 rows]
+          const int c_begin = ks * GS_KB * 2, c_end = min(nch128, (ks + 1) * GS_KB * 2);
+          g_begin = c_begin / p.gp128;
+          aux_len = (uint32_t)((c_end + p.gp128 - 1) / p.gp128 - g_begin) * 16 * aux_bytes;
+        }
+        mbar_expect_tx(full_bar(s), GS_KB * GS_BLK_BYTES + aux_len);
+        if (p.tma_rank == 3) {
+          tma_load_3d(dst, &tmap, 0, tile * GS_ROWS, ks * GS_KB, full_bar(s));
+        } else {
+          for (int kb = 0; kb < GS_KB; ++kb)
+            tma_load_2d(dst + kb * GS_BLK_BYTES, &tmap, (ks * GS_KB + kb) * (FMT == LP_W_BF16 ? 64 : 128), tile * GS_ROWS, full_bar(s));
+        }
+        if constexpr (FMT == LP_W_INT4) {
+          const char* src = reinterpret_cast<const char*>(p.W.aux2) + ((size_t)tile * p.ngroups + g_begin) * 16 * aux_bytes;
+          bulk_g2s(dst + GS_KB * GS_BLK_BYTES, src, aux_len, full_bar(s));
+        }
+        if (++s == p.nstages) { s = 0; ph ^= 1; }
+        if (++ks == p.nks) { ks = 0; ++tile; }
+      }
+    }
+    return;
+  }
+
+  // =============================== CONSUMERS ========================================================================
+  pdl_wait();  // activations of the previous kernel are visible from here on
+  pdl_launch_dependents();
+  const int ctid = threadIdx.x;  // 0 .. 255
+  const int g = lane >> 2, t = lane & 3;
+
+  // ---- stage x: (optional norm) -> bf16 split terms -> shared memory ------------------------------------------------
+  for (int m = 0; m < p.M; ++m) {
+    const float* xr = p.x + (size_t)m * K;
+    float mean = 0.f, rstd = 1.f;
+    if (p.nrm.kind >= 0) {
+      float s = 0.f, ss = 0.f;
+      for (int k = ctid * 4; k < K; k += GS_CWARPS * 32 * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + k);
+        s += v.x + v.y + v.z + v.w;
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      }
+      s = warp_sum(s);
+      ss = warp_sum(ss);
+      gs_bar_consumers();
+      if (lane == 0) {
+        s_stat[0][warp] = s;
+        s_stat[1][warp] = ss;
+      }
+      gs_bar_consumers();
+      s = ss = 0.f;
+#pragma unroll
+      for (int w = 0; w < GS_CWARPS; ++w) {
+        s += s_stat[0][w];
+        ss += s_stat[1][w];
+      }
+      if (p.nrm.kind == LP_NORM_LAYERNORM) {
+        mean = s / (float)K;
+        float v2 = 0.f;  // two-pass variance (second pass hits L1)
+        for (int k = ctid * 4; k < K; k += GS_CWARPS * 32 * 4) {
+          const float4 v = *reinterpret_cast<const float4*>(xr + k);
+          const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+          v2 += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        }
+        v2 = warp_sum(v2);
+        gs_bar_consumers();
+        if (lane == 0) s_stat[0][warp] = v2;
+        gs_bar_consumers();
+        v2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < GS_CWARPS; ++w) v2 += s_stat[0][w];
+        rstd = 1.0f / sqrtf(v2 / (float)K + p.nrm.eps);
+      } else {
+        rstd = 1.0f / sqrtf(ss / (float)K + p.nrm.eps);
+      }
+    }
+    // one warp stages 128 consecutive columns per iteration (= one int4 chunk, so its x-sum is a warp reduction)
+    for (int c = warp; c < nch128; c += GS_CWARPS) {
+      const int k = c * 128 + lane * 4;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (k < K) {  // K % 4 == 0
+        const float4 xv = *reinterpret_cast<const float4*>(xr + k);
+        v[0] = xv.x; v[1] = xv.y; v[2] = xv.z; v[3] = xv.w;
+        if (p.nrm.kind >= 0) {
+          const float4 wv = *reinterpret_cast<const float4*>(p.nrm.w + k);
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.nrm.b) bv = *reinterpret_cast<const float4*>(p.nrm.b + k);
+          if (p.nrm.kind == LP_NORM_LAYERNORM) {
+            v[0] = (v[0] - mean) * rstd * wv.x + bv.x; v[1] = (v[1] - mean) * rstd * wv.y + bv.y;
+            v[2] = (v[2] - mean) * rstd * wv.z + bv.z; v[3] = (v[3] - mean) * rstd * wv.w + bv.w;
+          } else {
+            v[0] = wv.x * (v[0] * rstd); v[1] = wv.y * (v[1] * rstd);
+            v[2] = wv.z * (v[2] * rstd); v[3] = wv.w * (v[3] * rstd);
+          }
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        if (s < p.split) {
+          uint16_t hb[4];
+          float part = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            hb[i] = gs_bf16_bits(v[i]);
+            const float hv = __uint_as_float((uint32_t)hb[i] << 16);
+            part += hv;
+            v[i] -= hv;  // exact: next term of the split
+          }
+          uint16_t* dst = xs + (size_t)(m * p.split + s) * p.ldx;
+          if constexpr (FMT == LP_W_INT4) {
+            // The 8 columns a lane feeds to one pair of MMAs are kc = 32 tt + 8 j + e of the chunk (tt = MMA k-lane, j = step).
+            // They are stored at 16-byte unit (4 j + tt) so the four k-lanes of a step read adjacent units (conflict free),
+            // and inside the unit in the order [0,4,1,5,2,6,3,7] that matches the lop3 nibble pairs.
+            const int kc = lane * 4;  // first of this lane's 4 columns inside the chunk
+            const int tt = kc >> 5, j = (kc >> 3) & 3, p0 = (kc & 4) ? 1 : 0;
+            uint16_t* d8 = dst + c * 128 + (4 * j + tt) * 8;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d8[2 * i + p0] = hb[i];
+            part = warp_sum(part);
+            if (lane == 0) xsum[c * NCOL + m * p.split + s] = part;
+          } else {
+            *reinterpret_cast<uint2*>(dst + k) = make_uint2(hb[0] | ((uint32_t)hb[1] << 16), hb[2] | ((uint32_t)hb[3] << 16));
+          }
+        }
+      }
+      if constexpr (FMT == LP_W_INT4) {
+        if (m == 0 && lane >= ncols && lane < NCOL) xsum[c * NCOL + lane] = 0.f;
+      }
+    }
+  }
+  gs_bar_consumers();
+
+  // ---- main loop ----------------------------------------------------------------------------------------------------
+  float acc[NB][4];
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[nb][i] = 0.f;
+  const uint16_t* xrow[NB];
+  bool bvalid[NB];
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
+    bvalid[nb] = (g + 8 * nb) < ncols;
+    xrow[nb] = xs + (size_t)(bvalid[nb] ? g + 8 * nb : 0) * p.ldx;
+  }
+  // int4: MMA row g <-> tile row pr0 (and g + 8 <-> pr0 + 8).  Neighbouring g get rows 4 apart, so under the 128-byte
+  // swizzle (16-byte unit ^= row & 7) the two rows of a quarter warp read opposite halves of a 128-byte line.
+  const int pr0 = (FMT == LP_W_INT4) ? ((g >> 1) + 4 * (g & 1)) : g;
+
+  int s = 0, ph = 0, ks = 0, tile = tile_begin;
+  for (int u = 0; u < nunits; ++u) {
+    mbar_wait(full_bar(s), ph);
+    const uint32_t st = ring_u32 + (uint32_t)s * p.stage_stride;
+    const int kb = ks * GS_KB + warp;  // this warp's K-block (GS_KB == GS_CWARPS)
+    if (kb < p.nkb) {
+      if constexpr (FMT == LP_W_BF16) {
+        const int kcol = kb * COLS_PER_BLK;
+        const uint32_t blk = st + warp * GS_BLK_BYTES;
+        const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t a[4];
+          gs_ldsm_x4(a, blk + row * 128 + (((kk * 2 + (lane >> 4)) ^ (row & 7)) << 4));
+          const int k0 = kcol + kk * 16;
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) {
+            uint32_t b0 = 0, b1 = 0;
+            if (bvalid[nb]) {
+              b0 = *reinterpret_cast<const uint32_t*>(xrow[nb] + k0 + 2 * t);
+              b1 = *reinterpret_cast<const uint32_t*>(xrow[nb] + k0 + 8 + 2 * t);
+            }
+            gs_mma(acc[nb], a[0], a[1], a[2], a[3], b0, b1);
+          }
+        }
+      } else {
+        const unsigned char* blk = ring + (size_t)s * p.stage_stride + warp * GS_BLK_BYTES;
+        const unsigned char* auxp = ring + (size_t)s * p.stage_stride + GS_KB * GS_BLK_BYTES;
+        const int g_begin = (ks * GS_KB * 2) / p.gp128;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = kb * 2 + cc;  // 128-column chunk inside the row
+          if (c < nch128) {
+            const uint4 wa4 = *reinterpret_cast<const uint4*>(blk + pr0 * 128 + (((cc * 4 + t) ^ (pr0 & 7)) << 4));
+            const uint4 wb4 = *reinterpret_cast<const uint4*>(blk + (pr0 + 8) * 128 + (((cc * 4 + t) ^ (pr0 & 7)) << 4));
+            const uint32_t wa[4] = {wa4.x, wa4.y, wa4.z, wa4.w};
+            const uint32_t wb[4] = {wb4.x, wb4.y, wb4.z, wb4.w};
+            const int gl = (p.gp128 == 1 ? c : c / p.gp128) - g_begin;  // group inside the stage's aux block
+            float s0, s1, z0, z1;
+            if (p.W.flags & LP_WF_AUX_PACKED) {
+              const uint32_t u0 = *reinterpret_cast<const uint32_t*>(auxp + ((size_t)gl * 16 + pr0) * 4);
+              const uint32_t u1 = *reinterpret_cast<const uint32_t*>(auxp + ((size_t)gl * 16 + pr0 + 8) * 4);
+              s0 = __uint_as_float(u0 & 0xffff0000u);
+              s1 = __uint_as_float(u1 & 0xffff0000u);
+              z0 = (float)(u0 & 0xffffu);
+              z1 = (float)(u1 & 0xffffu);
+            } else {
+              const float2 a0 = *reinterpret_cast<const float2*>(auxp + ((size_t)gl * 16 + pr0) * 8);
+              const float2 a1 = *reinterpret_cast<const float2*>(auxp + ((size_t)gl * 16 + pr0 + 8) * 8);
+              s0 = a0.x; z0 = a0.y; s1 = a1.x; z1 = a1.y;
+            }
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+              float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};  // two chains: half the MMA dependency depth
+              const uint4 z4 = make_uint4(0, 0, 0, 0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                // 8 columns 128 c + 32 t + 8 j of rows pr0 (wa) and pr0 + 8 (wb); x holds them at unit 4 j + t
+                const uint4 xv = bvalid[nb] ? *reinterpret_cast<const uint4*>(xrow[nb] + c * 128 + (4 * j + t) * 8) : z4;
+                gs_mma(ca, gs_nib(wa[j]), gs_nib(wb[j]), gs_nib(wa[j] >> 4), gs_nib(wb[j] >> 4), xv.x, xv.y);
+                gs_mma(cb, gs_nib(wa[j] >> 8), gs_nib(wb[j] >> 8), gs_nib(wa[j] >> 12), gs_nib(wb[j] >> 12), xv.z, xv.w);
+              }
+              const float2 xsv = *reinterpret_cast<const float2*>(xsum + c * NCOL + nb * 8 + 2 * t);
+              const float o0 = 128.f + z0, o1 = 128.f + z1;
+              acc[nb][0] = fmaf(s0, fmaf(-o0, xsv.x, ca[0] + cb[0]), acc[nb][0]);
+              acc[nb][1] = fmaf(s0, fmaf(-o0, xsv.y, ca[1] + cb[1]), acc[nb][1]);
+              acc[nb][2] = fmaf(s1, fmaf(-o1, xsv.x, ca[2] + cb[2]), acc[nb][2]);
+              acc[nb][3] = fmaf(s1, fmaf(-o1, xsv.y, ca[3] + cb[3]), acc[nb][3]);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar(s));  // this warp is done with the stage
+    if (++s == p.nstages) { s = 0; ph ^= 1; }
+
+    if (++ks == p.nks) {
+      ks = 0;
+      // ---- tile finished: cross-warp reduction, column recombination, epilogue ----
+      float* r = red + ((size_t)(tile & 1) * GS_CWARPS + warp) * 16 * NCOL;
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        r[pr0 * NCOL + nb * 8 + 2 * t] = acc[nb][0];
+        r[pr0 * NCOL + nb * 8 + 2 * t + 1] = acc[nb][1];
+        r[(pr0 + 8) * NCOL + nb * 8 + 2 * t] = acc[nb][2];
+        r[(pr0 + 8) * NCOL + nb * 8 + 2 * t + 1] = acc[nb][3];
+        acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
+      }
+      gs_bar_consumers();  // one barrier per tile: `red` is double buffered by tile parity
+      if (ctid < 16 * p.M) {
+        const int rr = ctid & 15, m = ctid >> 4;
+        const float* rbase = red + (size_t)(tile & 1) * GS_CWARPS * 16 * NCOL;
+        auto rowsum = [&](int row_in_tile) {
+          float y = 0.f;
+          for (int s2 = p.split - 1; s2 >= 0; --s2) {  // smallest terms first
+            float part = 0.f;
+#pragma unroll
+            for (int w = 0; w < GS_CWARPS; ++w) part += rbase[(w * 16 + row_in_tile) * NCOL + m * p.split + s2];
+            y += part;
+          }
+          const int row = tile * GS_ROWS + row_in_tile;
+          if (p.W.bias) y += p.W.bias[row];
+          return maybe_round(y, p.round_bf16);
+        };
+        const int row = tile * GS_ROWS + rr;
+        if (p.epi == LP_EPI_SWIGLU) {
+          if ((rr & 1) == 0) {
+            const float a = maybe_round(silu(rowsum(rr)), p.round_bf16);
+            p.out[(size_t)m * (N / 2) + (row >> 1)] = maybe_round(a * rowsum(rr + 1), p.round_bf16);
+          }
+        } else {
+          float y = rowsum(rr);
+          if (p.epi == LP_EPI_GELU) y = maybe_round(gelu_erf(y), p.round_bf16);
+          else if (p.epi == LP_EPI_RESIDUAL) y = maybe_round(p.residual[(size_t)m * N + row] + y, p.round_bf16);
+          p.out[(size_t)m * N + row] = y;
+        }
+      }
+      ++tile;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+// TMA descriptors of the weight matrices, built once per (pointer, shape) and cached.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+struct GsMap {
+  CUtensorMap map;
+  int rank;  // 0 = could not be built
+};
+
+static const GsMap& gs_tensor_map(const lp_weight& W, size_t row_bytes) {
+  static std::mutex mu;
+  static std::map<std::tuple<const void*, int, int, int>, GsMap> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_tuple(W.w, W.N, W.K, W.fmt);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  GsMap m;
+  memset(&m, 0, sizeof(m));
+  EncodeTiledFn enc = encode_fn();
+  if (enc) {
+    const bool bf = W.fmt == LP_W_BF16;
+    const CUtensorMapDataType dt = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    const cuuint64_t inner = bf ? 64 : 128;  // elements per 128 bytes
+    const cuuint64_t nkb = (row_bytes + 127) / 128;
+    {  // 3-D view {128 B, N rows, K-blocks}: the K-block stride (128 B) is smaller than the row stride on purpose
+      cuuint64_t dims[3] = {inner, (cuuint64_t)W.N, nkb};
+      cuuint64_t strides[2] = {(cuuint64_t)row_bytes, 128};
+      cuuint32_t box[3] = {(cuuint32_t)inner, GS_ROWS, GS_KB};
+      cuuint32_t es[3] = {1, 1, 1};
+      if (row_bytes % 128 == 0 &&
+          enc(&m.map, dt, 3, const_cast<void*>(W.w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+        m.rank = 3;
+    }
+    if (m.rank == 0) {  // plain 2-D {row bytes, N}: one 2 KB copy per K-block
+      cuuint64_t dims[2] = {(cuuint64_t)(bf ? W.K : row_bytes), (cuuint64_t)W.N};
+      cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+      cuuint32_t box[2] = {(cuuint32_t)inner, GS_ROWS};
+      cuuint32_t es[2] = {1, 1};
+      if (enc(&m.map, dt, 2, const_cast<void*>(W.w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+        m.rank = 2;
+    }
+  }
+  if (cache.size() > 4096) cache.clear();
+  return cache.emplace(key, m).first->second;
+}
+
+static size_t gs_tail_smem(int fmt, int NB, int K, int ncols, int ldx) {
+  const int NCOL = 8 * NB;
+  return 256 + (size_t)2 * GS_CWARPS * 16 * NCOL * 4 + (fmt == LP_W_INT4 ? (size_t)((K + 127) / 128) * NCOL * 4 : 0) + (size_t)ncols * ldx * 2;
+}
+
+template <int FMT, int NB>
+static int gs_launch(const CUtensorMap& map, const GsParams& p, size_t smem, int grid, void* stream) {
+  static bool attr_set = false;
+  auto kern = linear_stream_kernel<FMT, NB>;
+  if (!attr_set) {
+    LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)));
+    attr_set = true;
+  }
+  return launch(kern, dim3(grid), dim3(GS_THREADS), smem, stream, map, p);
+}
+
+// `nrm.kind` -1: no fused norm
+int linear_stream(const float* x, int M, const lp_weight& W, const NormArgs& nrm, int epi, const float* residual, float* out,
+                  int round_bf16, void* stream) {
+  static_assert(GS_KB == GS_CWARPS, "one K-block per consumer warp per stage");
+  if (W.fmt != LP_W_BF16 && W.fmt != LP_W_INT4) return LP_ERR_UNSUPPORTED;
+  if (W.N % GS_ROWS) return LP_ERR_UNSUPPORTED;
+  const int K = W.K;
+  if (K % 16) return LP_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(W.w) & 15) != 0) return LP_ERR_UNSUPPORTED;
+  int split;
+  if (round_bf16 && nrm.kind < 0) {
+    if (M > 16) return LP_ERR_UNSUPPORTED;
+    split = 1;  // x is bf16-valued already
+  } else {
+    if (round_bf16) return LP_ERR_UNSUPPORTED;  // bf16-faithful norm roundings live in lp_norm
+    if (M > 8) return LP_ERR_UNSUPPORTED;
+    split = M <= 2 ? 3 : 2;
+    if (split == 3 && (size_t)M * 3 * K * 2 > 48 * 1024) split = 2;  // long rows: 16 mantissa bits per term pair are plenty
+  }
+  const int ncols = M * split;
+  const int NB = ncols <= 8 ? 1 : 2;
+  GsParams p = {};
+  p.x = x; p.residual = residual; p.out = out; p.W = W; p.nrm = nrm;
+  p.M = M; p.split = split; p.epi = epi; p.round_bf16 = round_bf16;
+  const int kpad = (K + 255) / 256 * 256;
+  size_t row_bytes;
+  int aux_stage = 0;
+  if (W.fmt == LP_W_BF16) {
+    if (K % 64) return LP_ERR_UNSUPPORTED;  // 128-byte K-blocks
+    row_bytes = (size_t)K * 2;
+    p.ldx = kpad + 8;  // row stride = 16 bytes mod 128: B-fragment loads of a warp touch 32 distinct banks
+  } else {
+    if (W.group <= 0 || W.group % 128 || !W.aux2) return LP_ERR_UNSUPPORTED;
+    row_bytes = (size_t)kpad / 2;  // lp_int4_row_bytes(K)
+    p.ldx = kpad + 32;  // row stride = 64 bytes mod 128: the two rows of a quarter warp read opposite 64-byte halves
+    if ((p.ldx * 2) % 128 != 64) p.ldx += 32;
+    p.gp128 = W.group / 128;
+    p.ngroups = (K + W.group - 1) / W.group;
+    const int groups_per_stage = (GS_KB * 2 + p.gp128 - 1) / p.gp128 + 1;
+    aux_stage = groups_per_stage * 16 * ((W.flags & LP_WF_AUX_PACKED) ? 4 : 8);
+  }
+  const GsMap& gm = gs_tensor_map(W, row_bytes);
+  if (gm.rank == 0) return LP_ERR_UNSUPPORTED;
+  p.tma_rank = gm.rank;
+  p.nkb = (int)((row_bytes + 127) / 128);
+  p.nks = (p.nkb + GS_KB - 1) / GS_KB;
+  p.ntiles = W.N / GS_ROWS;
+  p.stage_stride = (GS_KB * GS_BLK_BYTES + aux_stage + 1023) / 1024 * 1024;
+  const size_t tail = gs_tail_smem(W.fmt, NB, K, ncols, p.ldx);
+  static const size_t env_budget = [] {
+    const char* e = getenv("LP_GS_BUDGET_KB");
+    return e ? (size_t)atoi(e) * 1024 : GS_SMEM_BUDGET;
+  }();
+  size_t budget = env_budget;
+  if (tail + 3 * (size_t)p.stage_stride + 1024 > budget) budget = 224 * 1024;  // long activation rows: give up co-residency
+  if (tail + 3 * (size_t)p.stage_stride + 1024 > budget) return LP_ERR_UNSUPPORTED;
+  int ns = (int)((budget - tail - 1024) / p.stage_stride);
+  if (ns > GS_MAX_STAGES) ns = GS_MAX_STAGES;
+  p.nstages = ns;
+  const size_t smem = (size_t)ns * p.stage_stride + tail + 1024;  // + slack for the 1 KB alignment of the ring
+  const int grid = p.ntiles < num_sms() ? p.ntiles : num_sms();
+  if (W.fmt == LP_W_BF16)
+    return NB == 1 ? gs_launch<LP_W_BF16, 1>(gm.map, p, smem, grid, stream) : gs_launch<LP_W_BF16, 2>(gm.map, p, smem, grid, stream);
+  return NB == 1 ? gs_launch<LP_W_INT4, 1>(gm.map, p, smem, grid, stream) : gs_launch<LP_W_INT4, 2>(gm.map, p, smem, grid, stream);
+}
+
+}  // namespace lp

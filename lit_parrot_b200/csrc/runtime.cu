@@ -42,7 +42,6 @@ int num_sms() {
   return v;
 }
 
-int init_linear_mma();  // linear_mma.cu
 int init_attention();   // attention.cu
 
 }  // namespace lp
@@ -84,9 +83,7 @@ int lp_init(int device) {
   }
   lp::g_sms.store(0);
   (void)lp::num_sms();
-  int rc = lp::init_attention();
-  if (rc != LP_OK) return rc;
-  return lp::init_linear_mma();
+  return lp::init_attention();
 }
 
 }  // extern "C"

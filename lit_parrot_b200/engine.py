@@ -24,18 +24,21 @@ class PackedLinear:
     """One linear layer as the kernels see it.  Keeps the tensors alive that the raw pointers refer to."""
 
     def __init__(self, w: torch.Tensor, fmt: int, N: int, K: int, bias: Optional[torch.Tensor] = None,
-                 aux0: Optional[torch.Tensor] = None, aux1: Optional[torch.Tensor] = None, group: int = 0) -> None:
+                 aux0: Optional[torch.Tensor] = None, aux1: Optional[torch.Tensor] = None, group: int = 0,
+                 aux2: Optional[torch.Tensor] = None, flags: int = 0) -> None:
         assert w.is_contiguous()
-        self.keep = (w, bias, aux0, aux1)
+        self.keep = (w, bias, aux0, aux1, aux2)
         self.N, self.K, self.fmt = N, K, fmt
-        self.rec = LpWeight(_ptr(w), _ptr(aux0), _ptr(aux1), _ptr(bias), fmt, N, K, group)
+        self.rec = LpWeight(_ptr(w), _ptr(aux0), _ptr(aux1), _ptr(aux2), _ptr(bias), fmt, N, K, group, flags, 0)
         self.ref = ctypes.byref(self.rec)
 
     @property
     def stored_bytes(self) -> int:
-        """Bytes a decode step must stream for this layer (weights + scales/zeros/absmax)."""
-        w, _bias, aux0, aux1 = self.keep
-        return sum(t.numel() * t.element_size() for t in (w, aux0, aux1) if t is not None)
+        """Bytes a decode step must stream for this layer (weights + scales/zeros/absmax).  When the tile-major
+        scale/zero buffer (aux2) exists it is what the streaming kernel reads instead of aux0/aux1."""
+        w, _bias, aux0, aux1, aux2 = self.keep
+        aux = (aux2,) if aux2 is not None else (aux0, aux1)
+        return sum(t.numel() * t.element_size() for t in (w, *aux) if t is not None)
 
 
 def _f32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
@@ -127,7 +130,17 @@ class Engine:
 
     # ------------------------------------------------------------------ bookkeeping
     def set_rope(self, rope) -> None:
-        self.cos, self.sin = (t.to(self.device, torch.float32).contiguous() for t in rope)
+        cos, sin = (t.to(self.device, torch.float32) for t in rope)
+        n_elem = self.cfg.rope_n_elem
+        if n_elem % 2 and cos.size(-1) != n_elem:
+            # n_elem == 1 (hs 4 at rotary_percentage 0.25: the reference's own unit-test config).  The reference's table is
+            # then 2 wide and `x[..., :1] * cos` broadcasts (model.py:229, 336): the head grows to hs + 1 dims with the rotated
+            # value r = x0 * (cos - sin) duplicated, so q.k gains 2 * r_q * r_k.  Same scores within hs dims: rotate by
+            # sqrt(2) * (cos, -sin) (the kernels' partner for d >= n_elem / 2 is +x).  Other odd sizes fail in the reference too.
+            if n_elem != 1:
+                raise RuntimeError(f"rotary dimension {n_elem} is odd: the reference cannot apply RoPE to it either")
+            cos, sin = cos[:, :1] * math.sqrt(2.0), -sin[:, :1] * math.sqrt(2.0)
+        self.cos, self.sin = cos.contiguous(), sin.contiguous()
 
     def drop_graphs(self) -> None:
         self._graphs.clear()
@@ -155,10 +168,11 @@ class Engine:
             cfg, dev = self.cfg, self.device
             f = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)  # noqa: E731
             E, I, V = cfg.n_embd, cfg.intermediate_size, cfg.padded_vocab_size
-            ws_bytes = self.lib.lp_attn_workspace_bytes(B, T, cfg.n_head, cfg.head_size, max_seq)
+            ws_bytes = max(self.lib.lp_attn_workspace_bytes(B, T, cfg.n_head, cfg.head_size, max_seq),
+                           self.lib.lp_attn_fused_workspace_bytes(B, cfg.n_head, cfg.n_query_groups, cfg.head_size, max_seq))
             b = dict(x=f(rows, E), n1=f(rows, E), n2=f(rows, E), qkv=f(rows, cfg.qkv_rows), q=f(rows, E), att=f(rows, E),
                      xmid=f(rows, E), u=f(rows, I), xf=f(rows, E), logits=f(rows, V),
-                     ws=torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8))
+                     ws=torch.zeros(max(ws_bytes, 16), device=dev, dtype=torch.uint8))  # zeroed: split-merge tickets
             if len(self._bufs) > 8:
                 self._bufs.clear()
             self._bufs[key] = b
@@ -188,10 +202,17 @@ class Engine:
         for li, L in enumerate(self.layers):
             kc, vc = caches[li][0].data_ptr(), caches[li][1].data_ptr()
             norm_linear(x, L.n1_w, L.n1_b, L.qkv, _lib.LP_EPI_NONE, qkv, n1, "lp_linear(qkv)")
-            chk(lib.lp_rope_kv_append(qkv, _ptr(self.cos), _ptr(self.sin), pos_ptr, q, kc, vc, kvd, B, T, H, G, hs,
-                                      cfg.rope_n_elem, max_seq, r, stream), "lp_rope_kv_append")
-            chk(lib.lp_attn_decode(q, kc, vc, kvd, pos_ptr, att, ws, ws_bytes, B, T, H, G, hs, max_seq, scale, r, stream),
-                "lp_attn_decode")
+            rc = -2
+            if T == 1:  # one launch: RoPE + cache append + split-K tensor-core attention + merge
+                rc = lib.lp_attn_decode_fused(qkv, _ptr(self.cos), _ptr(self.sin), pos_ptr, att, kc, vc, kvd, ws, ws_bytes, B, H, G,
+                                              hs, cfg.rope_n_elem, max_seq, scale, r, stream)
+                if rc != -2:
+                    chk(rc, "lp_attn_decode_fused")
+            if rc == -2:
+                chk(lib.lp_rope_kv_append(qkv, _ptr(self.cos), _ptr(self.sin), pos_ptr, q, kc, vc, kvd, B, T, H, G, hs,
+                                          cfg.rope_n_elem, max_seq, r, stream), "lp_rope_kv_append")
+                chk(lib.lp_attn_decode(q, kc, vc, kvd, pos_ptr, att, ws, ws_bytes, B, T, H, G, hs, max_seq, scale, r, stream),
+                    "lp_attn_decode")
             if cfg.parallel_residual:
                 # x + attn(n1) + mlp(n2), n2 = n1 when the norm is shared (model.py:169-171); both GEMVs read the old x
                 n2w, n2b = (L.n1_w, L.n1_b) if cfg.shared_attention_norm else (L.n2_w, L.n2_b)

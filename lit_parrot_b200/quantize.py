@@ -60,6 +60,23 @@ def rtn_int4_params(w: torch.Tensor, tile_cols: int) -> Tuple[torch.Tensor, torc
     return q.view(N, -1)[:, :K].contiguous(), scales, zeros
 
 
+def tile_major_aux(scales: torch.Tensor, zeros: torch.Tensor) -> Tuple[Optional[torch.Tensor], int]:
+    """Scale / zero pairs in the layout the streaming int4 kernel fetches with one bulk copy per stage:
+    [N/16 tiles][n_groups][16 rows].  One 32-bit word per pair (bf16 scale bits << 16 | integer zero) when that is exact
+    — scales of a bf16 checkpoint, zeros integral in [0, 65535] (quantize/gptq.py:337 rounds them) — else float2.
+    Returns (buffer, lp_weight.flags); (None, 0) when N is not a multiple of 16 (the exact CUDA-core kernel is used)."""
+    N, ng = scales.shape
+    if N % 16:
+        return None, 0
+    sc, ze = scales.detach().float(), zeros.detach().float()
+    tile = lambda t: t.view(N // 16, 16, ng).permute(0, 2, 1).contiguous()  # noqa: E731
+    exact = bool((sc.bfloat16().float() == sc).all()) and bool(((ze == ze.round()) & (ze >= 0) & (ze <= 65535)).all())
+    if exact:
+        word = (sc.bfloat16().view(torch.int16).to(torch.int32) << 16) | ze.to(torch.int32)
+        return tile(word), _lib.LP_WF_AUX_PACKED
+    return torch.stack((tile(sc), tile(ze)), dim=-1).contiguous(), 0
+
+
 class ColBlockQuantizedLinear(torch.nn.Module):
     def __init__(self, in_features: int, out_features: int, bias: bool, *, bits: int = 4, tile_cols: int = -1,
                  device=None, dtype=None) -> None:
@@ -140,9 +157,10 @@ class ColBlockQuantizedLinear(torch.nn.Module):
         if not rows.is_contiguous():
             rows = rows.contiguous()
         bias = None if self.bias is None else self.bias.detach().float().contiguous()
+        aux2, flags = tile_major_aux(self.scales, self.zeros)
         return _packed_linear(rows, _lib.LP_W_INT4, self.out_features, self.in_features, bias=bias,
                               aux0=self.scales.detach().float().contiguous(), aux1=self.zeros.detach().float().contiguous(),
-                              group=self.tile_cols)
+                              group=self.tile_cols, aux2=aux2, flags=flags)
 
     def lp_pack_pair(self, other: "ColBlockQuantizedLinear"):
         """fc_1 / fc_2 interleaved row-wise for the fused SwiGLU epilogue."""
@@ -159,8 +177,10 @@ class ColBlockQuantizedLinear(torch.nn.Module):
             inter = torch.as_strided(a, (2 * N, rb), (rb, 1))
         il = lambda x, y: torch.stack((x.detach().float(), y.detach().float()), dim=1).reshape(2 * N, -1).contiguous()  # noqa: E731
         bias = None if self.bias is None else il(self.bias[:, None], other.bias[:, None]).reshape(-1)
-        return _packed_linear(inter, _lib.LP_W_INT4, 2 * N, self.in_features, bias=bias, aux0=il(self.scales, other.scales),
-                              aux1=il(self.zeros, other.zeros), group=self.tile_cols)
+        sc, ze = il(self.scales, other.scales), il(self.zeros, other.zeros)
+        aux2, flags = tile_major_aux(sc, ze)
+        return _packed_linear(inter, _lib.LP_W_INT4, 2 * N, self.in_features, bias=bias, aux0=sc, aux1=ze, group=self.tile_cols,
+                              aux2=aux2, flags=flags)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -33,11 +33,18 @@ def bf16r(x):
     return x.to(torch.bfloat16).float()
 
 
-def run_linear(lib, x, wt, fmt, N, K, *, bias=None, aux0=None, aux1=None, group=0, epi=0, residual=None, rnd=0, path=0):
+def run_linear(lib, x, wt, fmt, N, K, *, bias=None, aux0=None, aux1=None, group=0, epi=0, residual=None, rnd=0, path=0,
+               packed_aux=None):
     M = x.shape[0]
     out = torch.full((M, N // 2 if epi == _lib.LP_EPI_SWIGLU else N), float("nan"), device=DEV)
     p = lambda a: None if a is None else a.data_ptr()  # noqa: E731
-    rec = LpWeight(wt.data_ptr(), p(aux0), p(aux1), p(bias), fmt, N, K, group)
+    aux2, flags = None, 0
+    if fmt == _lib.LP_W_INT4:  # tile-major scale/zero buffer for the streaming kernel (exact float2 unless asked otherwise)
+        from lit_parrot_b200.quantize import tile_major_aux
+        aux2, flags = tile_major_aux(aux0, aux1)
+        if packed_aux is not None:
+            assert bool(flags & _lib.LP_WF_AUX_PACKED) == packed_aux
+    rec = LpWeight(wt.data_ptr(), p(aux0), p(aux1), p(aux2), p(bias), fmt, N, K, group, flags, 0)
     _lib.check(lib.lp_set_linear_path(path))
     try:
         rc = lib.lp_linear(x.data_ptr(), M, ctypes.byref(rec), epi, p(residual), out.data_ptr(), rnd, stream())
@@ -58,7 +65,7 @@ def ref_epilogue(y, epi, residual):
     return y
 
 
-PATHS = [1, 0]  # 1 = FMA family only, 0 = auto (MMA family where it applies)
+PATHS = [1, 0]  # 1 = FMA family only, 0 = auto (streaming family where it applies)
 
 
 @pytest.mark.parametrize("path", PATHS)
@@ -115,6 +122,51 @@ def test_linear_gptq_int4(lib, path, group, M, N, K):
     # identical except where the fp32 sum lands within rounding noise of a bf16 tie: at most 1 ulp, rarely
     assert mism.float().mean() < 0.02
     torch.testing.assert_close(gotb, wantb, rtol=2 ** -7, atol=1e-6)
+
+
+@pytest.mark.parametrize("M,N,K,group", [(1, 64, 256, 128), (2, 4096, 4096, 128), (1, 22016, 4096, 128), (4, 4096, 11008, 128),
+                                         (1, 256, 2048, 256), (8, 128, 4096, -1), (1, 4672, 4608, 128)])
+def test_linear_gptq_int4_stream_packed_scales(lib, M, N, K, group):
+    """bf16-representable scales (a bf16 checkpoint, quantize/gptq.py under bf16-true): the streaming kernel reads one
+    packed 32-bit scale|zero word per (row, group) — results identical to the float2 layout and to the oracle."""
+    w = (torch.randn(N, K, generator=torch.Generator().manual_seed(5)) * 0.02)
+    packed, scales, zeros = O.gptq_rtn_quantize(w, group)
+    scales = scales.bfloat16().float()
+    src = torch.empty((K // 2, N), dtype=torch.uint8, device=DEV).t()
+    src.copy_(packed)
+    rows = torch.empty((N, lib.lp_int4_row_bytes(K)), dtype=torch.uint8, device=DEV)
+    _lib.check(lib.lp_repack_gptq_int4(src.data_ptr(), rows.data_ptr(), N, K, stream()))
+    x = f32(M, K, seed=6)
+    g = K if group == -1 else group
+    wd = O.gptq_dequant(packed, scales, zeros)
+    want = F.linear(x.cpu().double(), wd.double()).float().to(DEV)
+    path = 0 if M * K > 16384 else 2  # long activation blocks do not fit the streaming kernel's shared memory: auto path
+    for epi in (0, 2, 3):
+        res = f32(M, N, seed=4)
+        got = run_linear(lib, x, rows, _lib.LP_W_INT4, N, K, aux0=scales.to(DEV).contiguous(), aux1=zeros.to(DEV).contiguous(),
+                         group=g, path=path, packed_aux=True, epi=epi, residual=res)
+        torch.testing.assert_close(got, ref_epilogue(want.double(), epi, res.double()).float(), rtol=2e-5, atol=3e-5 * math.sqrt(K) * 0.3)
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 4096, 4096), (2, 12288, 4096), (1, 4096, 11008), (3, 4544, 18176), (8, 1024, 4096), (16, 512, 2048),
+                                   (1, 50688, 4096), (5, 160, 1040)])
+def test_linear_stream_bf16_large(lib, M, N, K):
+    """Real layer shapes through the streaming family only (path 2): multi-tile persistent CTAs, ragged last stage."""
+    w = f32(N, K, seed=1, scale=0.05).bfloat16()
+    x, b = f32(M, K, seed=2), f32(N, seed=3)
+    rnd = 1 if M > 8 else 0
+    if rnd:
+        x = bf16r(x)
+    ref = F.linear(x.double(), w.double(), b.double())
+    path = 2 if (K % 64 == 0 and M * K <= 32768) else 0  # what the streaming kernel covers; else auto (exact CUDA-core kernel)
+    for epi in (0, 1, 2, 3):
+        res = f32(M, N, seed=4)
+        got = run_linear(lib, x, w, _lib.LP_W_BF16, N, K, bias=b, epi=epi, residual=res, path=path, rnd=rnd)
+        want = ref_epilogue(ref, epi, res.double()).float()
+        if rnd:  # y and epilogue(y) are each rounded to bf16: two half-ulp roundings
+            torch.testing.assert_close(got, want, rtol=2 ** -6, atol=2e-2)
+        else:
+            torch.testing.assert_close(got, want, rtol=2e-5, atol=2e-5 * math.sqrt(K))
 
 
 @pytest.mark.parametrize("path", PATHS)
@@ -203,7 +255,8 @@ def test_rope_kv_append(lib, kvdt, B, T, H, G, hs, n_elem):
 @pytest.mark.parametrize("kvdt", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,T,H,G,hs,max_seq,p0", [
     (1, 1, 8, 8, 64, 64, 0), (1, 1, 8, 8, 64, 64, 63), (2, 1, 32, 32, 128, 2048, 1500), (1, 1, 71, 1, 64, 512, 300),
-    (2, 1, 64, 8, 128, 1024, 1023), (1, 7, 4, 2, 16, 32, 0), (3, 5, 8, 8, 32, 40, 9), (1, 1, 8, 8, 64, 48, 200)])
+    (2, 1, 64, 8, 128, 1024, 1023), (1, 7, 4, 2, 16, 32, 0), (3, 5, 8, 8, 32, 40, 9), (1, 1, 8, 8, 64, 48, 200),
+    (1, 3, 2, 2, 4, 25, 3), (1, 2, 4, 4, 2, 25, 6), (2, 1, 3, 1, 6, 20, 11)])
 def test_attention_against_sdpa(lib, kvdt, B, T, H, G, hs, max_seq, p0):
     """lp_attn_decode against masked SDPA over the zero-filled cache, as the reference runs it (model.py:91-92, 273-275).
     p0 >= max_seq exercises the ring (sliding-window) case: all max_seq slots are attended."""
@@ -228,6 +281,53 @@ def test_attention_against_sdpa(lib, kvdt, B, T, H, G, hs, max_seq, p0):
     want = F.scaled_dot_product_attention(qq, kk, vv, attn_mask=mask[None, None], scale=scale)
     want = want.transpose(1, 2).reshape(B * T, H * hs).float()
     torch.testing.assert_close(out, want, rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("B,H,G,hs,n_elem,max_seq,p0", [
+    (1, 8, 8, 64, 16, 64, 0), (1, 8, 8, 64, 16, 64, 63), (2, 32, 32, 128, 32, 2048, 1500), (1, 71, 1, 64, 64, 512, 300),
+    (2, 64, 8, 128, 128, 1024, 1023), (1, 32, 32, 128, 128, 2048, 2047), (1, 8, 8, 64, 64, 48, 200), (3, 128, 8, 64, 64, 200, 130),
+    (1, 64, 2, 128, 128, 300, 77), (32, 32, 32, 128, 32, 256, 100)])
+def test_attention_decode_fused(lib, B, H, G, hs, n_elem, max_seq, p0):
+    """lp_attn_decode_fused (RoPE + append + split-K tensor-core attention + merge in one launch) against the reference
+    op sequence (model.py:208-249) in float64 on the same bf16 cache.  p0 >= max_seq: ring / sliding-window case."""
+    qpk = H // G
+    qkv = f32(B, (H + 2 * G) * hs, seed=1)
+    cos, sin = O.rope_tables(max(p0 + 1, 64), n_elem, torch.float32)
+    cos, sin = cos.to(DEV).contiguous(), sin.to(DEV).contiguous()
+    pos = torch.tensor([p0], dtype=torch.int32, device=DEV)
+    kc = torch.zeros(B, G, max_seq, hs, device=DEV, dtype=torch.bfloat16)
+    vc = torch.zeros_like(kc)
+    n_old = min(p0, max_seq)
+    kc[:, :, :n_old] = f32(B, G, n_old, hs, seed=2).bfloat16()
+    vc[:, :, :n_old] = f32(B, G, n_old, hs, seed=3).bfloat16()
+    k_before, v_before = kc.clone(), vc.clone()
+    out = torch.full((B, H * hs), float("nan"), device=DEV)
+    ws = torch.zeros(lib.lp_attn_fused_workspace_bytes(B, H, G, hs, max_seq) + 16, dtype=torch.uint8, device=DEV)
+    scale = 1.0 / math.sqrt(hs)
+    for rep in range(2):  # twice: the ticket area must be left zeroed
+        kc.copy_(k_before)
+        vc.copy_(v_before)
+        _lib.check(lib.lp_attn_decode_fused(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), pos.data_ptr(), out.data_ptr(),
+                                            kc.data_ptr(), vc.data_ptr(), _lib.LP_BF16, ws.data_ptr(), ws.numel(), B, H, G, hs, n_elem,
+                                            max_seq, scale, 0, stream()), "lp_attn_decode_fused")
+    torch.cuda.synchronize()
+    v5 = qkv.view(B, 1, G, qpk + 2, hs).permute(0, 2, 3, 1, 4)
+    q, k, v = v5.split((qpk, 1, 1), dim=2)
+    c, s = cos[pos.long()], sin[pos.long()]
+    rot = lambda z: torch.cat((O.rotate(z[..., :n_elem], c, s), z[..., n_elem:]), dim=-1)  # noqa: E731
+    q, k = rot(q), rot(k)
+    slot = p0 % max_seq
+    want_k, want_v = k_before.clone(), v_before.clone()
+    want_k[:, :, slot] = k[:, :, 0, 0].bfloat16()
+    want_v[:, :, slot] = v[:, :, 0, 0].bfloat16()
+    assert torch.equal(kc, want_k) and torch.equal(vc, want_v)
+    n_valid = min(p0 + 1, max_seq)
+    qq = q.reshape(B, H, 1, hs).double()
+    kk = want_k[:, :, :n_valid].double().repeat_interleave(qpk, dim=1)
+    vv = want_v[:, :, :n_valid].double().repeat_interleave(qpk, dim=1)
+    want = F.scaled_dot_product_attention(qq, kk, vv, scale=scale).reshape(B, H * hs).float()
+    torch.testing.assert_close(out, want, rtol=1e-4, atol=2e-5)
+    assert int(ws[:4 * B * G].view(torch.int32).abs().sum()) == 0  # tickets reset for the next launch
 
 
 def test_sample_greedy_and_topk(lib):
@@ -286,7 +386,7 @@ def test_norm_linear_fused(lib, kind, fmt, M, N, K):
     p = lambda a: None if a is None else a.data_ptr()  # noqa: E731
     if fmt == "bf16":
         w = f32(N, K, seed=4, scale=0.05).bfloat16()
-        rec = LpWeight(w.data_ptr(), None, None, None, _lib.LP_W_BF16, N, K, 0)
+        rec = LpWeight(w.data_ptr(), None, None, None, None, _lib.LP_W_BF16, N, K, 0, 0, 0)
         want = F.linear(xn, w.double()).float()
     else:
         wf = torch.randn(N, K, generator=torch.Generator().manual_seed(5)) * 0.02
@@ -296,7 +396,9 @@ def test_norm_linear_fused(lib, kind, fmt, M, N, K):
         rows = torch.empty((N, lib.lp_int4_row_bytes(K)), dtype=torch.uint8, device=DEV)
         _lib.check(lib.lp_repack_gptq_int4(src.data_ptr(), rows.data_ptr(), N, K, stream()))
         sc, ze = scales.to(DEV).contiguous(), zeros.to(DEV).contiguous()
-        rec = LpWeight(rows.data_ptr(), sc.data_ptr(), ze.data_ptr(), None, _lib.LP_W_INT4, N, K, 128)
+        from lit_parrot_b200.quantize import tile_major_aux
+        aux2, flags = tile_major_aux(sc, ze)
+        rec = LpWeight(rows.data_ptr(), sc.data_ptr(), ze.data_ptr(), aux2.data_ptr(), None, _lib.LP_W_INT4, N, K, 128, flags, 0)
         want = F.linear(xn, O.gptq_dequant(packed, scales, zeros, tile_cols=128).double().to(DEV)).float()
     out = torch.full((M, N), float("nan"), device=DEV)
     rc = lib.lp_norm_linear(kind, nw.data_ptr(), p(nb if kind == 0 else None), 1e-5, x.data_ptr(), M, ctypes.byref(rec), 0, None,

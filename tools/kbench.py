@@ -48,7 +48,7 @@ def bench_linear():
                 if fmt == "bf16":
                     w = torch.randn(N, K, device=DEV, dtype=torch.bfloat16) * 0.02
                     keep.append(w)
-                    recs.append(LpWeight(w.data_ptr(), None, None, None, _lib.LP_W_BF16, N, K, 0))
+                    recs.append(LpWeight(w.data_ptr(), None, None, None, None, _lib.LP_W_BF16, N, K, 0, 0, 0))
                     nbytes = N * K * 2
                 else:
                     rb = lib.lp_int4_row_bytes(K)
@@ -57,12 +57,16 @@ def bench_linear():
                     sc = torch.rand(N, ng, device=DEV) * 0.01
                     ze = torch.full((N, ng), 8.0, device=DEV)
                     keep += [w, sc, ze]
-                    recs.append(LpWeight(w.data_ptr(), sc.data_ptr(), ze.data_ptr(), None, _lib.LP_W_INT4, N, K, 128))
-                    nbytes = N * rb + 2 * N * ng * 4
-            for M in (1, 2, 4):
+                    from lit_parrot_b200.quantize import tile_major_aux
+                    sc = sc.bfloat16().float()
+                    aux2, flags = tile_major_aux(sc, ze)
+                    keep.append(aux2)
+                    recs.append(LpWeight(w.data_ptr(), sc.data_ptr(), ze.data_ptr(), aux2.data_ptr(), None, _lib.LP_W_INT4, N, K, 128, flags, 0))
+                    nbytes = N * rb + N * ng * 4
+            for M in (1, 2, 4, 8):
                 x = torch.randn(M, K, device=DEV)
                 out = torch.empty(M, N, device=DEV)
-                for path, pname in ((1, "fma"), (2, "mma")):
+                for path, pname in ((1, "fma"), (2, "strm")):
                     lib.lp_set_linear_path(path)
                     rc = lib.lp_linear(x.data_ptr(), M, ctypes.byref(recs[0]), 0, None, out.data_ptr(), 0, stream())
                     if rc != 0:
@@ -85,7 +89,7 @@ def bench_attn():
                                    ("70b B=1 ctx2k", 1, 64, 8, 128, 2048), ("falcon B=1 ctx2k", 1, 71, 1, 64, 2048),
                                    ("7b B=1 ctx512", 1, 32, 32, 128, 512)]:
         for kvdt in (torch.bfloat16,):
-            L = 4
+            L = max(4, min(64, int(300e6 // (2 * B * G * ctx * hs * 2)) + 1))  # rotate over > L2 worth of cache
             kc = [torch.randn(B, G, ctx, hs, device=DEV).to(kvdt) for _ in range(L)]
             vc = [torch.randn(B, G, ctx, hs, device=DEV).to(kvdt) for _ in range(L)]
             q = torch.randn(B, H * hs, device=DEV)
@@ -96,7 +100,16 @@ def bench_attn():
                                               ws.data_ptr(), ws.numel(), B, 1, H, G, hs, ctx, 1 / math.sqrt(hs), 0, stream())
             us = timeit(fn, iters=30)
             nbytes = 2 * B * G * ctx * hs * 2
-            print(f"{name:28s} {'bf16':5s} {us:8.2f} {nbytes / us / 1e3:8.0f}")
+            print(f"{name:28s} {'bf16':5s} {us:8.2f} {nbytes / us / 1e3:8.0f}   (generic kernel, attention only)")
+            qkv = torch.randn(B, (H + 2 * G) * hs, device=DEV)
+            cos = torch.randn(ctx, hs, device=DEV)
+            wsf = torch.zeros(lib.lp_attn_fused_workspace_bytes(B, H, G, hs, ctx) + 16, dtype=torch.uint8, device=DEV)
+            fn2 = lambda i: lib.lp_attn_decode_fused(qkv.data_ptr(), cos.data_ptr(), cos.data_ptr(), pos.data_ptr(), out.data_ptr(),  # noqa: E731
+                                                     kc[i % L].data_ptr(), vc[i % L].data_ptr(), 1, wsf.data_ptr(), wsf.numel(), B, H, G, hs,
+                                                     hs, ctx, 1 / math.sqrt(hs), 0, stream())
+            assert fn2(0) == 0
+            us = timeit(fn2, iters=30)
+            print(f"{name:28s} {'bf16':5s} {us:8.2f} {nbytes / us / 1e3:8.0f}   (fused rope+append+attention+merge)")
 
 
 if __name__ == "__main__":
