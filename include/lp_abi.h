@@ -62,7 +62,7 @@ typedef enum {
 typedef enum { LP_NORM_LAYERNORM = 0, LP_NORM_RMS = 1 } lp_norm_kind;
 
 /* lp_weight.flags */
-#define LP_WF_AUX_PACKED 1 /* aux2 holds one 32-bit word per (row, group): bf16 scale bits << 16 | integer zero point;
+#define LP_WF_AUX_PACKED 1 /* aux2 holds one 32-bit word per (row, group): bf16 scale bits << 16 | bf16 zero-point bits;
                               otherwise a float2 {scale, zero}.  Packed is exact when the scales are bf16-representable
                               (a bf16 checkpoint) and halves the scale/zero traffic: 0.5 + 4/128 bytes per weight.   */
 
@@ -95,6 +95,10 @@ int lp_set_pdl(int enabled);
  * (exact fp32 CUDA-core math, every format), 2 = streaming family only (persistent TMA-bulk ring + mma.sync;
  * LP_ERR_UNSUPPORTED where it does not apply).  Test aid. */
 int lp_set_linear_path(int path);
+
+/* Debug aid: when `device_buf` (>= 8 * 148 uint64) is non-NULL every streaming-GEMV CTA records globaltimer stamps
+ * [start, after griddepcontrol.wait, x staged, first four stages consumed, end]; NULL switches it off. */
+int lp_debug_stream_trace(void* device_buf);
 
 /* One-time per-device setup (cudaFuncSetAttribute for large dynamic shared memory).  Idempotent, thread-safe. */
 int lp_init(int device);

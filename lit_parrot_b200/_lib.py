@@ -39,6 +39,7 @@ PROTOTYPES = {
     "lp_launch_count": (ctypes.c_ulonglong, []),
     "lp_set_pdl": (c_int, [c_int]),
     "lp_set_linear_path": (c_int, [c_int]),
+    "lp_debug_stream_trace": (c_int, [c_void_p]),
     "lp_init": (c_int, [c_int]),
     "lp_embed": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "lp_norm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -14,6 +14,7 @@ struct NormArgs {
 };
 int linear_stream(const float* x, int M, const lp_weight& W, const NormArgs& nrm, int epi, const float* residual, float* out,
                   int round_bf16, void* stream);
+void set_stream_trace(void* buf);
 static std::atomic<int> g_path{0};  // 0 auto, 1 force FMA, 2 force streaming
 }  // namespace lp
 
@@ -22,6 +23,11 @@ extern "C" {
 int lp_set_linear_path(int path) {
   if (path < 0 || path > 2) return LP_ERR_INVALID_ARG;
   lp::g_path.store(path);
+  return LP_OK;
+}
+
+int lp_debug_stream_trace(void* device_buf) {
+  lp::set_stream_trace(device_buf);
   return LP_OK;
 }
 

@@ -9,7 +9,7 @@
 //     free.  (Measured: 1 KB bulk copies cap an SM at ~18 GB/s whatever the ring depth — the copy count, not the bytes in
 //     flight, is the limit; 16 KB copies lift it.)  The ring is filled BEFORE griddepcontrol.wait: under PDL the first
 //     stages of layer n+1's weights are already in flight while layer n drains;
-//   * eight CONSUMER warps split K inside a stage.  The multiply-accumulates run on the tensor cores
+//   * sixteen CONSUMER warps split K inside a stage.  The multiply-accumulates run on the tensor cores
 //     (mma.sync.m16n8k16, bf16 x bf16 -> fp32) so the issue slots are left for what an int4 GEMV is limited by — nibble
 //     unpacking: nibble -> bf16 is ONE lop3 per two weights ((w & 0x000F000F) | 0x43004300 = {128+q_lo, 128+q_hi}); the
 //     +128 and the GPTQ zero point are removed algebraically per 128-column group:
@@ -30,7 +30,7 @@
 
 namespace lp {
 
-constexpr int GS_CWARPS = 8;                      // consumer warps
+constexpr int GS_CWARPS = 16;                     // consumer warps (two per K-block of a stage)
 constexpr int GS_THREADS = (GS_CWARPS + 1) * 32;  // + 1 producer warp
 constexpr int GS_ROWS = 16;
 constexpr int GS_BLK_BYTES = GS_ROWS * 128;       // one K-block of a tile: 16 rows x 128 bytes (64 bf16 / 256 int4 columns)
@@ -87,6 +87,10 @@ __device__ __forceinline__ void gs_mma(float (&c)[4], uint32_t a0, uint32_t a1, 
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void gs_imma(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ uint32_t gs_nib(uint32_t w) {
   uint32_t r;
   asm("lop3.b32 %0, %1, 0x000F000F, 0x43004300, 0xEA;\n" : "=r"(r) : "r"(w));  // (w & m) | magic
@@ -111,7 +115,169 @@ struct GsParams {
   int tma_rank;     // 3: one copy per stage; 2: one copy per K-block (fallback if the 3-D map was refused)
   int ngroups;      // int4 groups per row
   int gp128;        // 128-column chunks per scale group (group / 128)
+  unsigned long long* trace;  // debug: per-CTA phase timestamps (globaltimer ns), NULL in production
 };
+
+__device__ __forceinline__ unsigned long long gs_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// One activation row -> shared-memory B-operand columns (see the call site).  s_stat: [2][GS_CWARPS] floats.
+template <int FMT, bool CACHED>
+__device__ __forceinline__ void gs_stage_row(const GsParams& p, int m, int NCOL, int ncols, float* s_stat, uint16_t* xs, signed char* xs8,
+                                             float* xsum, float* colscale) {
+  constexpr int STRIDE = GS_CWARPS * 32 * 4;
+  constexpr int NI = CACHED ? 4 : 1;
+  const int K = p.W.K;
+  const int nch128 = (K + 127) / 128;
+  const int niter = (nch128 * 128 + STRIDE - 1) / STRIDE;  // covers the zero padding up to a whole 128-column chunk
+  const int ctid = threadIdx.x, warp = ctid >> 5, lane = ctid & 31;
+  const float* xr = p.x + (size_t)m * K;
+  const bool has_norm = p.nrm.kind >= 0;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 xc[NI], wc[NI], bc[NI];
+  auto ld = [&](const float* base, int i) { const int k = ctid * 4 + i * STRIDE; return (base && k < K) ? *reinterpret_cast<const float4*>(base + k) : zero4; };
+  if (CACHED) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      xc[i] = i < niter ? ld(xr, i) : zero4;
+      wc[i] = (has_norm && i < niter) ? ld(p.nrm.w, i) : zero4;
+      bc[i] = (has_norm && i < niter) ? ld(p.nrm.b, i) : zero4;
+    }
+  }
+#define GS_ITERS(i) _Pragma("unroll") for (int i = 0; i < (CACHED ? NI : niter); ++i) if (!CACHED || i < niter)
+  auto raw = [&](int i) { return CACHED ? xc[CACHED ? i : 0] : ld(xr, i); };
+  auto block_reduce = [&](float a, float b, bool is_max, float& ra, float& rb) {
+    a = is_max ? warp_max(a) : warp_sum(a);
+    b = warp_sum(b);
+    gs_bar_consumers();
+    if (lane == 0) {
+      s_stat[warp] = a;
+      s_stat[GS_CWARPS + warp] = b;
+    }
+    gs_bar_consumers();
+    ra = is_max ? 0.f : 0.f;
+    rb = 0.f;
+#pragma unroll
+    for (int w = 0; w < GS_CWARPS; ++w) {
+      ra = is_max ? fmaxf(ra, s_stat[w]) : ra + s_stat[w];
+      rb += s_stat[GS_CWARPS + w];
+    }
+  };
+  float mean = 0.f, rstd = 1.f;
+  if (has_norm) {
+    float sm = 0.f, ss = 0.f;
+    GS_ITERS(i) {
+      const float4 v = raw(i);
+      sm += v.x + v.y + v.z + v.w;
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    block_reduce(sm, ss, false, sm, ss);
+    if (p.nrm.kind == LP_NORM_LAYERNORM) {
+      mean = sm / (float)K;
+      float v2 = 0.f, dummy;  // two-pass variance
+      GS_ITERS(i) {
+        const int k = ctid * 4 + i * STRIDE;
+        if (k < K) {
+          const float4 v = raw(i);
+          const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+          v2 += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        }
+      }
+      block_reduce(v2, 0.f, false, v2, dummy);
+      rstd = 1.0f / sqrtf(v2 / (float)K + p.nrm.eps);
+    } else {
+      rstd = 1.0f / sqrtf(ss / (float)K + p.nrm.eps);
+    }
+  }
+  // normalised values of this thread's 4 columns of iteration i (zeros beyond K)
+  auto nv = [&](int i, float (&v)[4]) {
+    const float4 x4 = raw(i);
+    v[0] = x4.x; v[1] = x4.y; v[2] = x4.z; v[3] = x4.w;
+    if (has_norm) {
+      const float4 w4 = CACHED ? wc[CACHED ? i : 0] : ld(p.nrm.w, i);
+      const float4 b4 = CACHED ? bc[CACHED ? i : 0] : ld(p.nrm.b, i);
+      if (p.nrm.kind == LP_NORM_LAYERNORM) {
+        v[0] = (v[0] - mean) * rstd * w4.x + b4.x; v[1] = (v[1] - mean) * rstd * w4.y + b4.y;
+        v[2] = (v[2] - mean) * rstd * w4.z + b4.z; v[3] = (v[3] - mean) * rstd * w4.w + b4.w;
+      } else {
+        v[0] = w4.x * (v[0] * rstd); v[1] = w4.y * (v[1] * rstd);
+        v[2] = w4.z * (v[2] * rstd); v[3] = w4.w * (v[3] * rstd);
+      }
+      if (ctid * 4 + i * STRIDE >= K) v[0] = v[1] = v[2] = v[3] = 0.f;  // LayerNorm bias must not leak into the padding
+    }
+  };
+  if constexpr (FMT == LP_W_INT4) {
+    // int4 weights run on the INTEGER tensor cores (IMMA u8 x s8 -> s32).  The activation row becomes block fixed
+    // point: X_k = rint(x_k * 2^22 / max|x|), written as three balanced base-256 digits (int8) in three B columns.
+    // Integer dot products are exact; the digits' weights (max|x| / 2^22 * 256^i) are applied in the epilogue, so the
+    // result carries ~22 bits of the largest activation: fp32-activation accuracy.
+    float amax = 0.f, dummy;
+    GS_ITERS(i) {
+      float v[4];
+      nv(i, v);
+      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))));
+    }
+    block_reduce(amax, 0.f, true, amax, dummy);
+    const float inv = amax > 0.f ? 4194304.0f / amax : 0.f;
+    if (ctid < 3) colscale[m * 3 + ctid] = (amax / 4194304.0f) * (ctid == 0 ? 1.0f : (ctid == 1 ? 256.0f : 65536.0f));
+    GS_ITERS(i) {
+      const int c = warp + GS_CWARPS * i;  // 128-column chunk: columns 128 c + 4 lane = 4 ctid + STRIDE i
+      if (c < nch128) {
+        float v[4];
+        nv(i, v);
+        // The 8 columns a lane feeds to one IMMA are kc = 32 tt + 8 j + e of the chunk (tt = MMA k-lane, j = word).  They
+        // are stored at byte 32 tt + 8 j + (e >> 1) + 4 (e & 1): even nibbles (operand a0/a1) first, odd nibbles (a2/a3) after.
+        const int kc = lane * 4, tt = kc >> 5, j = (kc >> 3) & 3, e0 = kc & 7;
+        int sum[3] = {0, 0, 0};
+        signed char* d8 = xs8 + c * 128 + tt * 32 + j * 8;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          int X = __float2int_rn(v[q] * inv);
+          const int e = e0 + q, pos = (e >> 1) + 4 * (e & 1);
+#pragma unroll
+          for (int dgt = 0; dgt < 3; ++dgt) {
+            const int tdig = dgt < 2 ? (((X + 128) & 255) - 128) : X;
+            X = (X - tdig) >> 8;
+            sum[dgt] += tdig;
+            d8[(size_t)(m * 3 + dgt) * p.ldx + pos] = (signed char)tdig;
+          }
+        }
+#pragma unroll
+        for (int dgt = 0; dgt < 3; ++dgt) {
+          const float ps = warp_sum((float)sum[dgt]);
+          if (lane == 0) xsum[c * NCOL + m * 3 + dgt] = ps;
+        }
+        if (m == 0 && lane >= ncols && lane < NCOL) xsum[c * NCOL + lane] = 0.f;
+      }
+    }
+  } else {
+    GS_ITERS(i) {
+      const int k = ctid * 4 + i * STRIDE;
+      if (k < K) {
+        float v[4];
+        nv(i, v);
+#pragma unroll
+        for (int sp = 0; sp < 3; ++sp) {
+          if (sp < p.split) {
+            uint16_t hb[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              hb[q] = gs_bf16_bits(v[q]);
+              v[q] -= __uint_as_float((uint32_t)hb[q] << 16);  // exact: next term of the split
+            }
+            uint16_t* dst = xs + (size_t)(m * p.split + sp) * p.ldx;
+            *reinterpret_cast<uint2*>(dst + k) = make_uint2(hb[0] | ((uint32_t)hb[1] << 16), hb[2] | ((uint32_t)hb[3] << 16));
+          }
+        }
+      }
+    }
+    if (ctid < p.split) colscale[m * p.split + ctid] = 1.0f;
+  }
+#undef GS_ITERS
+}
 
 template <int FMT, int NB>
 __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __grid_constant__ CUtensorMap tmap, const GsParams p) {
@@ -125,10 +291,15 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
   unsigned char* ring = smem;
   unsigned char* after = smem + (size_t)p.nstages * p.stage_stride;
   uint64_t* bars = reinterpret_cast<uint64_t*>(after);                      // full[nstages], empty[nstages]
+  volatile int* done = reinterpret_cast<volatile int*>(after + 240);         // [2] last finalised local tile per parity
   float* red = reinterpret_cast<float*>(after + 256);                       // [2][CWARPS][16][NCOL]
-  float* xsum = red + 2 * GS_CWARPS * 16 * NCOL;                            // [nch128][NCOL]   (int4 only)
-  uint16_t* xs = reinterpret_cast<uint16_t*>(xsum + (FMT == LP_W_INT4 ? nch128 * NCOL : 0));  // [ncols][ldx] bf16 bits
+  float* colscale = red + 2 * GS_CWARPS * 16 * NCOL;                        // [NCOL] weight of each B column in the epilogue
+  float* xsum = colscale + NCOL;                                            // [nch128][NCOL]   (int4 only)
+  // bf16 weights: [ncols][ldx] bf16 bits;  int4 weights: [ncols][ldx] int8 digits (ldx in elements of either kind)
+  uint16_t* xs = reinterpret_cast<uint16_t*>(xsum + (FMT == LP_W_INT4 ? nch128 * NCOL : 0));
+  signed char* xs8 = reinterpret_cast<signed char*>(xs);
   __shared__ float s_stat[2][GS_CWARPS];
+  (void)xs8;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = gs_smem_u32(bars);
@@ -142,11 +313,13 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
   const int nunits = (tile_end - tile_begin) * p.nks;
   const int aux_bytes = (p.W.flags & LP_WF_AUX_PACKED) ? 4 : 8;
 
+  if (p.trace && threadIdx.x == 0) p.trace[blockIdx.x * 8 + 0] = gs_now();
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nstages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), GS_CWARPS);
     }
+    done[0] = done[1] = -1;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -188,109 +361,20 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
   // =============================== CONSUMERS ========================================================================
   pdl_wait();  // activations of the previous kernel are visible from here on
   pdl_launch_dependents();
-  const int ctid = threadIdx.x;  // 0 .. 255
+  if (p.trace && threadIdx.x == 0) p.trace[blockIdx.x * 8 + 1] = gs_now();
   const int g = lane >> 2, t = lane & 3;
 
-  // ---- stage x: (optional norm) -> bf16 split terms -> shared memory ------------------------------------------------
-  for (int m = 0; m < p.M; ++m) {
-    const float* xr = p.x + (size_t)m * K;
-    float mean = 0.f, rstd = 1.f;
-    if (p.nrm.kind >= 0) {
-      float s = 0.f, ss = 0.f;
-      for (int k = ctid * 4; k < K; k += GS_CWARPS * 32 * 4) {
-        const float4 v = *reinterpret_cast<const float4*>(xr + k);
-        s += v.x + v.y + v.z + v.w;
-        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-      }
-      s = warp_sum(s);
-      ss = warp_sum(ss);
-      gs_bar_consumers();
-      if (lane == 0) {
-        s_stat[0][warp] = s;
-        s_stat[1][warp] = ss;
-      }
-      gs_bar_consumers();
-      s = ss = 0.f;
-#pragma unroll
-      for (int w = 0; w < GS_CWARPS; ++w) {
-        s += s_stat[0][w];
-        ss += s_stat[1][w];
-      }
-      if (p.nrm.kind == LP_NORM_LAYERNORM) {
-        mean = s / (float)K;
-        float v2 = 0.f;  // two-pass variance (second pass hits L1)
-        for (int k = ctid * 4; k < K; k += GS_CWARPS * 32 * 4) {
-          const float4 v = *reinterpret_cast<const float4*>(xr + k);
-          const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
-          v2 += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-        }
-        v2 = warp_sum(v2);
-        gs_bar_consumers();
-        if (lane == 0) s_stat[0][warp] = v2;
-        gs_bar_consumers();
-        v2 = 0.f;
-#pragma unroll
-        for (int w = 0; w < GS_CWARPS; ++w) v2 += s_stat[0][w];
-        rstd = 1.0f / sqrtf(v2 / (float)K + p.nrm.eps);
-      } else {
-        rstd = 1.0f / sqrtf(ss / (float)K + p.nrm.eps);
-      }
-    }
-    // one warp stages 128 consecutive columns per iteration (= one int4 chunk, so its x-sum is a warp reduction)
-    for (int c = warp; c < nch128; c += GS_CWARPS) {
-      const int k = c * 128 + lane * 4;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (k < K) {  // K % 4 == 0
-        const float4 xv = *reinterpret_cast<const float4*>(xr + k);
-        v[0] = xv.x; v[1] = xv.y; v[2] = xv.z; v[3] = xv.w;
-        if (p.nrm.kind >= 0) {
-          const float4 wv = *reinterpret_cast<const float4*>(p.nrm.w + k);
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.nrm.b) bv = *reinterpret_cast<const float4*>(p.nrm.b + k);
-          if (p.nrm.kind == LP_NORM_LAYERNORM) {
-            v[0] = (v[0] - mean) * rstd * wv.x + bv.x; v[1] = (v[1] - mean) * rstd * wv.y + bv.y;
-            v[2] = (v[2] - mean) * rstd * wv.z + bv.z; v[3] = (v[3] - mean) * rstd * wv.w + bv.w;
-          } else {
-            v[0] = wv.x * (v[0] * rstd); v[1] = wv.y * (v[1] * rstd);
-            v[2] = wv.z * (v[2] * rstd); v[3] = wv.w * (v[3] * rstd);
-          }
-        }
-      }
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        if (s < p.split) {
-          uint16_t hb[4];
-          float part = 0.f;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            hb[i] = gs_bf16_bits(v[i]);
-            const float hv = __uint_as_float((uint32_t)hb[i] << 16);
-            part += hv;
-            v[i] -= hv;  // exact: next term of the split
-          }
-          uint16_t* dst = xs + (size_t)(m * p.split + s) * p.ldx;
-          if constexpr (FMT == LP_W_INT4) {
-            // The 8 columns a lane feeds to one pair of MMAs are kc = 32 tt + 8 j + e of the chunk (tt = MMA k-lane, j = step).
-            // They are stored at 16-byte unit (4 j + tt) so the four k-lanes of a step read adjacent units (conflict free),
-            // and inside the unit in the order [0,4,1,5,2,6,3,7] that matches the lop3 nibble pairs.
-            const int kc = lane * 4;  // first of this lane's 4 columns inside the chunk
-            const int tt = kc >> 5, j = (kc >> 3) & 3, p0 = (kc & 4) ? 1 : 0;
-            uint16_t* d8 = dst + c * 128 + (4 * j + tt) * 8;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) d8[2 * i + p0] = hb[i];
-            part = warp_sum(part);
-            if (lane == 0) xsum[c * NCOL + m * p.split + s] = part;
-          } else {
-            *reinterpret_cast<uint2*>(dst + k) = make_uint2(hb[0] | ((uint32_t)hb[1] << 16), hb[2] | ((uint32_t)hb[3] << 16));
-          }
-        }
-      }
-      if constexpr (FMT == LP_W_INT4) {
-        if (m == 0 && lane >= ncols && lane < NCOL) xsum[c * NCOL + lane] = 0.f;
-      }
-    }
+  // ---- stage x: (optional norm) -> B-operand columns in shared memory ----------------------------------------------
+  // Thread `ctid` owns columns 4 ctid + 2048 i (.. + 3) of every pass (statistics, max, conversion), so for rows of up to
+  // 8192 columns the activations (and norm parameters) are read from global memory ONCE and stay in registers; every
+  // later pass costs only a named barrier.
+  if ((nch128 * 128 + 2047) / 2048 <= 4) {
+    for (int m = 0; m < p.M; ++m) gs_stage_row<FMT, true>(p, m, NCOL, ncols, &s_stat[0][0], xs, xs8, xsum, colscale);
+  } else {
+    for (int m = 0; m < p.M; ++m) gs_stage_row<FMT, false>(p, m, NCOL, ncols, &s_stat[0][0], xs, xs8, xsum, colscale);
   }
   gs_bar_consumers();
+  if (p.trace && threadIdx.x == 0) p.trace[blockIdx.x * 8 + 2] = gs_now();
 
   // ---- main loop ----------------------------------------------------------------------------------------------------
   float acc[NB][4];
@@ -299,12 +383,15 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[nb][i] = 0.f;
   const uint16_t* xrow[NB];
+  const signed char* xrow8[NB];
   bool bvalid[NB];
 #pragma unroll
   for (int nb = 0; nb < NB; ++nb) {
     bvalid[nb] = (g + 8 * nb) < ncols;
     xrow[nb] = xs + (size_t)(bvalid[nb] ? g + 8 * nb : 0) * p.ldx;
+    xrow8[nb] = xs8 + (size_t)(bvalid[nb] ? g + 8 * nb : 0) * p.ldx;
   }
+  (void)xrow; (void)xrow8;
   // int4: MMA row g <-> tile row pr0 (and g + 8 <-> pr0 + 8).  Neighbouring g get rows 4 apart, so under the 128-byte
   // swizzle (16-byte unit ^= row & 7) the two rows of a quarter warp read opposite halves of a 128-byte line.
   const int pr0 = (FMT == LP_W_INT4) ? ((g >> 1) + 4 * (g & 1)) : g;
@@ -312,15 +399,18 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
   int s = 0, ph = 0, ks = 0, tile = tile_begin;
   for (int u = 0; u < nunits; ++u) {
     mbar_wait(full_bar(s), ph);
+    if (p.trace && threadIdx.x == 0 && u < 4) p.trace[blockIdx.x * 8 + 3 + u] = gs_now();
     const uint32_t st = ring_u32 + (uint32_t)s * p.stage_stride;
-    const int kb = ks * GS_KB + warp;  // this warp's K-block (GS_KB == GS_CWARPS)
+    const int kbl = warp >> 1, sub = warp & 1;  // K-block inside the stage; which half of it this warp owns
+    const int kb = ks * GS_KB + kbl;
     if (kb < p.nkb) {
       if constexpr (FMT == LP_W_BF16) {
         const int kcol = kb * COLS_PER_BLK;
-        const uint32_t blk = st + warp * GS_BLK_BYTES;
+        const uint32_t blk = st + kbl * GS_BLK_BYTES;
         const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
+        for (int kk2 = 0; kk2 < 2; ++kk2) {
+          const int kk = sub * 2 + kk2;
           uint32_t a[4];
           gs_ldsm_x4(a, blk + row * 128 + (((kk * 2 + (lane >> 4)) ^ (row & 7)) << 4));
           const int k0 = kcol + kk * 16;
@@ -335,11 +425,11 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
           }
         }
       } else {
-        const unsigned char* blk = ring + (size_t)s * p.stage_stride + warp * GS_BLK_BYTES;
+        const unsigned char* blk = ring + (size_t)s * p.stage_stride + kbl * GS_BLK_BYTES;
         const unsigned char* auxp = ring + (size_t)s * p.stage_stride + GS_KB * GS_BLK_BYTES;
-        const int g_begin = (ks * GS_KB * 2) / p.gp128;
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
+        const int g_begin = p.gp128 == 1 ? ks * GS_KB * 2 : (ks * GS_KB * 2) / p.gp128;
+        {
+          const int cc = sub;
           const int c = kb * 2 + cc;  // 128-column chunk inside the row
           if (c < nch128) {
             const uint4 wa4 = *reinterpret_cast<const uint4*>(blk + pr0 * 128 + (((cc * 4 + t) ^ (pr0 & 7)) << 4));
@@ -348,13 +438,13 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
             const uint32_t wb[4] = {wb4.x, wb4.y, wb4.z, wb4.w};
             const int gl = (p.gp128 == 1 ? c : c / p.gp128) - g_begin;  // group inside the stage's aux block
             float s0, s1, z0, z1;
-            if (p.W.flags & LP_WF_AUX_PACKED) {
+            if (p.W.flags & LP_WF_AUX_PACKED) {  // bf16 scale << 16 | bf16 zero
               const uint32_t u0 = *reinterpret_cast<const uint32_t*>(auxp + ((size_t)gl * 16 + pr0) * 4);
               const uint32_t u1 = *reinterpret_cast<const uint32_t*>(auxp + ((size_t)gl * 16 + pr0 + 8) * 4);
               s0 = __uint_as_float(u0 & 0xffff0000u);
               s1 = __uint_as_float(u1 & 0xffff0000u);
-              z0 = (float)(u0 & 0xffffu);
-              z1 = (float)(u1 & 0xffffu);
+              z0 = __uint_as_float(u0 << 16);
+              z1 = __uint_as_float(u1 << 16);
             } else {
               const float2 a0 = *reinterpret_cast<const float2*>(auxp + ((size_t)gl * 16 + pr0) * 8);
               const float2 a1 = *reinterpret_cast<const float2*>(auxp + ((size_t)gl * 16 + pr0 + 8) * 8);
@@ -362,21 +452,23 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
             }
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb) {
-              float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};  // two chains: half the MMA dependency depth
-              const uint4 z4 = make_uint4(0, 0, 0, 0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                // 8 columns 128 c + 32 t + 8 j of rows pr0 (wa) and pr0 + 8 (wb); x holds them at unit 4 j + t
-                const uint4 xv = bvalid[nb] ? *reinterpret_cast<const uint4*>(xrow[nb] + c * 128 + (4 * j + t) * 8) : z4;
-                gs_mma(ca, gs_nib(wa[j]), gs_nib(wb[j]), gs_nib(wa[j] >> 4), gs_nib(wb[j] >> 4), xv.x, xv.y);
-                gs_mma(cb, gs_nib(wa[j] >> 8), gs_nib(wb[j] >> 8), gs_nib(wa[j] >> 12), gs_nib(wb[j] >> 12), xv.z, xv.w);
+              int ca[4] = {0, 0, 0, 0}, cb[4] = {0, 0, 0, 0};
+              uint4 xv0 = make_uint4(0, 0, 0, 0), xv1 = xv0;
+              if (bvalid[nb]) {  // 32 digit bytes: this k-lane's 32 columns of the chunk, in operand order
+                xv0 = *reinterpret_cast<const uint4*>(xrow8[nb] + c * 128 + t * 32);
+                xv1 = *reinterpret_cast<const uint4*>(xrow8[nb] + c * 128 + t * 32 + 16);
               }
+              const uint32_t M4 = 0x0F0F0F0Fu;
+              gs_imma(ca, wa[0] & M4, wb[0] & M4, (wa[0] >> 4) & M4, (wb[0] >> 4) & M4, xv0.x, xv0.y);
+              gs_imma(cb, wa[1] & M4, wb[1] & M4, (wa[1] >> 4) & M4, (wb[1] >> 4) & M4, xv0.z, xv0.w);
+              gs_imma(ca, wa[2] & M4, wb[2] & M4, (wa[2] >> 4) & M4, (wb[2] >> 4) & M4, xv1.x, xv1.y);
+              gs_imma(cb, wa[3] & M4, wb[3] & M4, (wa[3] >> 4) & M4, (wb[3] >> 4) & M4, xv1.z, xv1.w);
               const float2 xsv = *reinterpret_cast<const float2*>(xsum + c * NCOL + nb * 8 + 2 * t);
-              const float o0 = 128.f + z0, o1 = 128.f + z1;
-              acc[nb][0] = fmaf(s0, fmaf(-o0, xsv.x, ca[0] + cb[0]), acc[nb][0]);
-              acc[nb][1] = fmaf(s0, fmaf(-o0, xsv.y, ca[1] + cb[1]), acc[nb][1]);
-              acc[nb][2] = fmaf(s1, fmaf(-o1, xsv.x, ca[2] + cb[2]), acc[nb][2]);
-              acc[nb][3] = fmaf(s1, fmaf(-o1, xsv.y, ca[3] + cb[3]), acc[nb][3]);
+              // sum (q - z) s x = s * (sum q X - z * sum X), all integers exact in fp32 (|.| < 2^24)
+              acc[nb][0] = fmaf(s0, fmaf(-z0, xsv.x, (float)(ca[0] + cb[0])), acc[nb][0]);
+              acc[nb][1] = fmaf(s0, fmaf(-z0, xsv.y, (float)(ca[1] + cb[1])), acc[nb][1]);
+              acc[nb][2] = fmaf(s1, fmaf(-z1, xsv.x, (float)(ca[2] + cb[2])), acc[nb][2]);
+              acc[nb][3] = fmaf(s1, fmaf(-z1, xsv.y, (float)(ca[3] + cb[3])), acc[nb][3]);
             }
           }
         }
@@ -389,7 +481,14 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
     if (++ks == p.nks) {
       ks = 0;
       // ---- tile finished: cross-warp reduction, column recombination, epilogue ----
-      float* r = red + ((size_t)(tile & 1) * GS_CWARPS + warp) * 16 * NCOL;
+      // Only ONE warp (rotating with the tile) waits for the others and finalises; everybody else drops its partial sums,
+      // arrives on the named barrier and moves on to the next tile.  `red` is double buffered by tile parity: before
+      // overwriting a buffer a warp checks that the tile that used it two tiles ago has been finalised (`done`).
+      const int lt = tile - tile_begin, par = lt & 1;
+      if (lt >= 2) {
+        while (done[par] < lt - 2) {}
+      }
+      float* r = red + ((size_t)par * GS_CWARPS + warp) * 16 * NCOL;
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) {
         r[pr0 * NCOL + nb * 8 + 2 * t] = acc[nb][0];
@@ -398,38 +497,60 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
         r[(pr0 + 8) * NCOL + nb * 8 + 2 * t + 1] = acc[nb][3];
         acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
       }
-      gs_bar_consumers();  // one barrier per tile: `red` is double buffered by tile parity
-      if (ctid < 16 * p.M) {
-        const int rr = ctid & 15, m = ctid >> 4;
-        const float* rbase = red + (size_t)(tile & 1) * GS_CWARPS * 16 * NCOL;
-        auto rowsum = [&](int row_in_tile) {
-          float y = 0.f;
-          for (int s2 = p.split - 1; s2 >= 0; --s2) {  // smallest terms first
-            float part = 0.f;
+      const int fin = lt % GS_CWARPS;        // first finalising warp of this tile (rotates)
+      const int nfin = p.M;                  // one finalising warp per activation row
+      const int fidx = (warp - fin + GS_CWARPS) % GS_CWARPS;
+      if (fidx >= nfin) {
+        asm volatile("bar.arrive %0, %1;\n" ::"r"(2 + par), "n"(GS_CWARPS * 32) : "memory");
+      } else {
+        asm volatile("bar.sync %0, %1;\n" ::"r"(2 + par), "n"(GS_CWARPS * 32) : "memory");
+        // lane = (row of the tile, half): each half adds the partial sums of 8 warps per B column, then one shuffle
+        const int m = fidx, rr = lane & 15, half = lane >> 4;
+        const float* rb = red + ((size_t)par * GS_CWARPS + half * (GS_CWARPS / 2)) * 16 * NCOL + rr * NCOL + m * p.split;
+        float cs[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-            for (int w = 0; w < GS_CWARPS; ++w) part += rbase[(w * 16 + row_in_tile) * NCOL + m * p.split + s2];
-            y += part;
+        for (int w = 0; w < GS_CWARPS / 2; ++w) {
+#pragma unroll
+          for (int s2 = 0; s2 < 3; ++s2)
+            if (s2 < p.split) cs[s2] += rb[(size_t)w * 16 * NCOL + s2];
+        }
+        float y = 0.f;
+#pragma unroll
+        for (int si = 0; si < 3; ++si) {  // smallest terms first (bf16 split: last term; int8 digits: digit 0)
+          if (si < p.split) {
+            const int s2 = (FMT == LP_W_INT4) ? si : p.split - 1 - si;
+            float c = 0.f;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) c = (q == s2) ? cs[q] : c;
+            c += __shfl_xor_sync(0xffffffffu, c, 16);
+            y = fmaf(c, colscale[m * p.split + s2], y);
           }
-          const int row = tile * GS_ROWS + row_in_tile;
-          if (p.W.bias) y += p.W.bias[row];
-          return maybe_round(y, p.round_bf16);
-        };
+        }
         const int row = tile * GS_ROWS + rr;
+        if (p.W.bias) y += p.W.bias[row];
+        y = maybe_round(y, p.round_bf16);
         if (p.epi == LP_EPI_SWIGLU) {
-          if ((rr & 1) == 0) {
-            const float a = maybe_round(silu(rowsum(rr)), p.round_bf16);
-            p.out[(size_t)m * (N / 2) + (row >> 1)] = maybe_round(a * rowsum(rr + 1), p.round_bf16);
+          const float other = __shfl_xor_sync(0xffffffffu, y, 1);  // fc_2 row of the pair
+          if (half == 0 && (rr & 1) == 0) {
+            const float a = maybe_round(silu(y), p.round_bf16);
+            p.out[(size_t)m * (N / 2) + (row >> 1)] = maybe_round(a * other, p.round_bf16);
           }
-        } else {
-          float y = rowsum(rr);
+        } else if (half == 0) {
           if (p.epi == LP_EPI_GELU) y = maybe_round(gelu_erf(y), p.round_bf16);
           else if (p.epi == LP_EPI_RESIDUAL) y = maybe_round(p.residual[(size_t)m * N + row] + y, p.round_bf16);
           p.out[(size_t)m * N + row] = y;
+        }
+        if (nfin > 1) asm volatile("bar.sync %0, %1;\n" ::"r"(4 + par), "r"(nfin * 32) : "memory");  // all finalisers have read `red`
+        __syncwarp();
+        if (fidx == 0 && lane == 0) {
+          __threadfence_block();
+          done[par] = lt;
         }
       }
       ++tile;
     }
   }
+  if (p.trace && threadIdx.x == 0) p.trace[blockIdx.x * 8 + 7] = gs_now();
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -493,9 +614,13 @@ static const GsMap& gs_tensor_map(const lp_weight& W, size_t row_bytes) {
   return cache.emplace(key, m).first->second;
 }
 
+static unsigned long long* g_trace = nullptr;
+void set_stream_trace(void* buf) { g_trace = reinterpret_cast<unsigned long long*>(buf); }
+
 static size_t gs_tail_smem(int fmt, int NB, int K, int ncols, int ldx) {
   const int NCOL = 8 * NB;
-  return 256 + (size_t)2 * GS_CWARPS * 16 * NCOL * 4 + (fmt == LP_W_INT4 ? (size_t)((K + 127) / 128) * NCOL * 4 : 0) + (size_t)ncols * ldx * 2;
+  return 256 + (size_t)2 * GS_CWARPS * 16 * NCOL * 4 + (size_t)NCOL * 4 + (fmt == LP_W_INT4 ? (size_t)((K + 127) / 128) * NCOL * 4 : 0) +
+         (size_t)ncols * ldx * (fmt == LP_W_INT4 ? 1 : 2);
 }
 
 template <int FMT, int NB>
@@ -512,14 +637,19 @@ static int gs_launch(const CUtensorMap& map, const GsParams& p, size_t smem, int
 // `nrm.kind` -1: no fused norm
 int linear_stream(const float* x, int M, const lp_weight& W, const NormArgs& nrm, int epi, const float* residual, float* out,
                   int round_bf16, void* stream) {
-  static_assert(GS_KB == GS_CWARPS, "one K-block per consumer warp per stage");
+  static_assert(2 * GS_KB == GS_CWARPS, "two consumer warps per K-block of a stage");
   if (W.fmt != LP_W_BF16 && W.fmt != LP_W_INT4) return LP_ERR_UNSUPPORTED;
   if (W.N % GS_ROWS) return LP_ERR_UNSUPPORTED;
   const int K = W.K;
   if (K % 16) return LP_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(W.w) & 15) != 0) return LP_ERR_UNSUPPORTED;
   int split;
-  if (round_bf16 && nrm.kind < 0) {
+  if (W.fmt == LP_W_INT4) {
+    // integer path: three int8 digits per activation row in every mode (a bf16-valued x is covered exactly as well)
+    if (round_bf16 && nrm.kind >= 0) return LP_ERR_UNSUPPORTED;  // bf16-faithful norm roundings live in lp_norm
+    if (M > 5) return LP_ERR_UNSUPPORTED;
+    split = 3;
+  } else if (round_bf16 && nrm.kind < 0) {
     if (M > 16) return LP_ERR_UNSUPPORTED;
     split = 1;  // x is bf16-valued already
   } else {
@@ -533,6 +663,7 @@ int linear_stream(const float* x, int M, const lp_weight& W, const NormArgs& nrm
   GsParams p = {};
   p.x = x; p.residual = residual; p.out = out; p.W = W; p.nrm = nrm;
   p.M = M; p.split = split; p.epi = epi; p.round_bf16 = round_bf16;
+  p.trace = g_trace;
   const int kpad = (K + 255) / 256 * 256;
   size_t row_bytes;
   int aux_stage = 0;
@@ -543,8 +674,7 @@ int linear_stream(const float* x, int M, const lp_weight& W, const NormArgs& nrm
   } else {
     if (W.group <= 0 || W.group % 128 || !W.aux2) return LP_ERR_UNSUPPORTED;
     row_bytes = (size_t)kpad / 2;  // lp_int4_row_bytes(K)
-    p.ldx = kpad + 32;  // row stride = 64 bytes mod 128: the two rows of a quarter warp read opposite 64-byte halves
-    if ((p.ldx * 2) % 128 != 64) p.ldx += 32;
+    p.ldx = kpad + 16;  // int8 digits; row stride = odd multiple of 16 bytes: neighbouring columns read opposite-parity units
     p.gp128 = W.group / 128;
     p.ngroups = (K + W.group - 1) / W.group;
     const int groups_per_stage = (GS_KB * 2 + p.gp128 - 1) / p.gp128 + 1;

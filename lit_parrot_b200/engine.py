@@ -191,7 +191,16 @@ class Engine:
         scale = 1.0 / math.sqrt(hs)
         wte_dt = _KV_OF_DTYPE[self.wte.dtype]
         chk(lib.lp_embed(idx_ptr, idx64, idx_off, self.wte.data_ptr(), wte_dt, x, rows, E, r, stream), "lp_embed")
+        trace = getattr(self, "trace", None)  # debug: (ncalls, 148 * 8) int64, one row of stamps per streaming GEMV
+        tcount = [0]
+
+        def mark():
+            if trace is not None:
+                lib.lp_debug_stream_trace(trace[tcount[0] % trace.size(0)].data_ptr())
+                tcount[0] += 1
+
         def norm_linear(src, nw, nb, W, epi, dst, scratch, what):
+            mark()
             """norm fused into the GEMV prologue where the kernel supports it, else lp_norm + lp_linear."""
             rc = lib.lp_norm_linear(self.norm_kind, _ptr(nw), _ptr(nb), cfg.norm_eps, src, rows, W.ref, epi, None, dst, r, stream)
             if rc == -2:
@@ -217,16 +226,22 @@ class Engine:
                 # x + attn(n1) + mlp(n2), n2 = n1 when the norm is shared (model.py:169-171); both GEMVs read the old x
                 n2w, n2b = (L.n1_w, L.n1_b) if cfg.shared_attention_norm else (L.n2_w, L.n2_b)
                 norm_linear(x, n2w, n2b, L.fc, self.act, u, n2, "lp_linear(fc)")
+                mark()
                 chk(lib.lp_linear(att, rows, L.proj.ref, _lib.LP_EPI_RESIDUAL, x, xmid, r, stream), "lp_linear(proj)")
+                mark()
                 chk(lib.lp_linear(u, rows, L.mlp_proj.ref, _lib.LP_EPI_RESIDUAL, xmid, x, r, stream), "lp_linear(mlp.proj)")
             else:
                 if cfg.shared_attention_norm:
                     raise NotImplementedError("No checkpoint amongst the ones we support uses this configuration"
                                               " (non-parallel residual and shared attention norm).")
+                mark()
                 chk(lib.lp_linear(att, rows, L.proj.ref, _lib.LP_EPI_RESIDUAL, x, x, r, stream), "lp_linear(proj)")
                 norm_linear(x, L.n2_w, L.n2_b, L.fc, self.act, u, n2, "lp_linear(fc)")
+                mark()
                 chk(lib.lp_linear(u, rows, L.mlp_proj.ref, _lib.LP_EPI_RESIDUAL, x, x, r, stream), "lp_linear(mlp.proj)")
         xf, logits = b["xf"].data_ptr(), b["logits"].data_ptr()
+        if trace is not None:
+            lib.lp_debug_stream_trace(None)
         if last_only and T > 1:
             # only the last position of each sequence feeds the sampler (generate/base.py:136): gather those rows
             for bi in range(B):

@@ -62,17 +62,17 @@ def rtn_int4_params(w: torch.Tensor, tile_cols: int) -> Tuple[torch.Tensor, torc
 
 def tile_major_aux(scales: torch.Tensor, zeros: torch.Tensor) -> Tuple[Optional[torch.Tensor], int]:
     """Scale / zero pairs in the layout the streaming int4 kernel fetches with one bulk copy per stage:
-    [N/16 tiles][n_groups][16 rows].  One 32-bit word per pair (bf16 scale bits << 16 | integer zero) when that is exact
-    — scales of a bf16 checkpoint, zeros integral in [0, 65535] (quantize/gptq.py:337 rounds them) — else float2.
+    [N/16 tiles][n_groups][16 rows].  One 32-bit word per pair (bf16 scale bits << 16 | bf16 zero bits) when that is exact
+    — scales of a bf16 checkpoint, zeros integral in [0, 255] (quantize/gptq.py:337 rounds them) — else float2.
     Returns (buffer, lp_weight.flags); (None, 0) when N is not a multiple of 16 (the exact CUDA-core kernel is used)."""
     N, ng = scales.shape
     if N % 16:
         return None, 0
     sc, ze = scales.detach().float(), zeros.detach().float()
     tile = lambda t: t.view(N // 16, 16, ng).permute(0, 2, 1).contiguous()  # noqa: E731
-    exact = bool((sc.bfloat16().float() == sc).all()) and bool(((ze == ze.round()) & (ze >= 0) & (ze <= 65535)).all())
+    exact = bool((sc.bfloat16().float() == sc).all()) and bool(((ze == ze.round()) & (ze >= 0) & (ze <= 255)).all())
     if exact:
-        word = (sc.bfloat16().view(torch.int16).to(torch.int32) << 16) | ze.to(torch.int32)
+        word = (sc.bfloat16().view(torch.int16).to(torch.int32) << 16) | (ze.bfloat16().view(torch.int16).to(torch.int32) & 0xFFFF)
         return tile(word), _lib.LP_WF_AUX_PACKED
     return torch.stack((tile(sc), tile(ze)), dim=-1).contiguous(), 0
 
