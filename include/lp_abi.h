@@ -128,6 +128,22 @@ int lp_linear(const float* x, int M, const lp_weight* W, int epilogue, const flo
 int lp_norm_linear(int norm_kind, const float* norm_w, const float* norm_b, float eps, const float* x, int M,
                    const lp_weight* W, int epilogue, const float* residual, float* out, int round_bf16, void* stream);
 
+/* ---- prefill (T > 1) projections on tcgen05 tensor cores ----------------------------------------------------------
+ * lp_split_bf16: x fp32 [rows, K] -> `nterms` bf16 arrays [nterms][rows, K] with x = t0 + t1 (+ t2) exactly (1 term in
+ * bf16-faithful mode), optionally through LayerNorm / RMSNorm first (norm_kind < 0: none).  These terms are the A operand
+ * of lp_gemm_bf16_tc, which multiplies each with the same weight tile: fp32-activation accuracy on bf16 tensor cores.
+ * lp_gemm_bf16_tc: out = epilogue(x . W^T + bias), W bf16 [N, K] row-major (nn.Linear.weight; other formats are first
+ * expanded with lp_dequant_bf16), TMA-fed tcgen05.mma with the accumulator in tensor memory.  The result is written as
+ * fp32 [M, Nout] (out_f32) and / or as `out_terms` bf16 split arrays [out_terms][M, Nout] (out_bf16) — the next GEMM's
+ * operand.  Nout = N (N / 2 for LP_EPI_SWIGLU).  Requires N % 128 == 0 and K % 8 == 0, else LP_ERR_UNSUPPORTED.
+ * replaces nn.Linear.forward on T > 1 tokens (model.py:111, 205, 252, 285-301). */
+int lp_split_bf16(const float* x, void* out_bf16, int rows, int K, int nterms, int norm_kind, const float* norm_w,
+                  const float* norm_b, float eps, int round_bf16, void* stream);
+int lp_gemm_bf16_tc(const void* x_terms, int nterms, int M, const void* w_bf16, int N, int K, const float* bias, int epilogue,
+                    const float* residual, float* out_f32, void* out_bf16, int out_terms, int round_bf16, void* stream);
+/* W in any lp_wfmt -> dense bf16 [N, K] (int4 / NF4 rounded to bf16 like the reference's bf16 dequantisation). */
+int lp_dequant_bf16(const lp_weight* W, void* out_bf16, void* stream);
+
 /* replaces the q/k regroup + apply_rope + torch.cat + cache index_copy_ of CausalSelfAttention.forward
  * (model.py:208-245, 330-336).  qkv [B*T, (H+2G)*hs] rows group-interleaved [q x q_per_kv, k, v] (model.py:210-214);
  * cos/sin fp32 [block_size, n_elem]; pos int32 [T] (shared by the batch, model.py:88-92).

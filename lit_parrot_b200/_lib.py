@@ -46,6 +46,10 @@ PROTOTYPES = {
     "lp_linear": (c_int, [c_void_p, c_int, ctypes.POINTER(LpWeight), c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "lp_norm_linear": (c_int, [c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, ctypes.POINTER(LpWeight), c_int, c_void_p,
                                c_void_p, c_int, c_void_p]),
+    "lp_split_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p]),
+    "lp_gemm_bf16_tc": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                c_int, c_void_p]),
+    "lp_dequant_bf16": (c_int, [ctypes.POINTER(LpWeight), c_void_p, c_void_p]),
     "lp_rope_kv_append": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "lp_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),

@@ -442,6 +442,7 @@ static int ad_launch(const AttnDecParams& p, int B, int head_tiles, void* stream
   const size_t smem = ad_smem_bytes<HS>();
   if (!attr_set) {
     LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   return launch(kern, dim3(B * p.G, p.n_splits, head_tiles), dim3(AD_THREADS), smem, stream, p);

@@ -1,0 +1,404 @@
+// Dense projections for prefill (and wide decode batches) on the 5th-generation tensor cores:
+//   C[M,N] = epilogue( X[M,K] . W[N,K]^T + bias ),  X and W bf16 K-major, fp32 accumulation in TENSOR MEMORY.
+//
+//   reference ops: every nn.Linear of GPT.forward applied to T > 1 tokens (model.py:111, 205, 252, 285-301).
+//
+// One CTA computes a 128 x BN output tile (BN = 256 or 128):
+//   warp 0   : TMA producer — cp.async.bulk.tensor.2d loads of a 128 x 64 X tile (per activation term, see below) and a
+//              BN x 64 W tile per stage into a 128-byte-swizzled ring, full/empty mbarriers;
+//   warp 1   : MMA issuer — one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M 128, N BN, K 16) from
+//              shared-memory descriptors, accumulating into TMEM (BN columns x 128 lanes of fp32); tcgen05.commit
+//              releases ring slots and finally signals the epilogue;
+//   warp 2   : allocates / frees the TMEM columns;
+//   warps 2-5: epilogue — tcgen05.ld (32 lanes x 32 columns per instruction), bias / GELU(erf) / SwiGLU / residual,
+//              then either fp32 rows or the bf16 hi/mid/lo split of the result (the next GEMM's operand).
+// fp32-ACTIVATION accuracy on bf16 tensor cores: the activation is passed as `nterms` bf16 arrays with
+// x = t0 + t1 (+ t2) exactly (lp_split_bf16); every term is multiplied with the same W tile (nterms MMAs per k-step), the
+// products are exact in the fp32 accumulator.  bf16-faithful mode uses one term.
+// Grid: (M tiles, N tiles) with the M tiles fastest, so the CTAs that share a W tile run together and W is streamed from
+// HBM once while the (small) activation tiles stay in L2.
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+
+namespace lp {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;       // 128 bytes of bf16: one swizzle span
+constexpr int TC_THREADS = 192; // 6 warps
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"
+      "%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+        "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// K-major, 128-byte swizzle: rows of 128 bytes, 8-row atoms 1024 bytes apart (SBO), descriptor version 1 (Blackwell)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
+struct TcParams {
+  const float* bias;      // [N] or NULL
+  const float* residual;  // [M, N] or NULL
+  float* out_f32;         // [M, Nout] or NULL
+  __nv_bfloat16* out_bf;  // [out_terms][M, Nout] bf16 split of the result, or NULL
+  int M, N, K, epi, round_bf16, nterms, out_terms;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p, int nstages) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int A_BYTES = TC_BM * TC_BK * 2;           // per term
+  constexpr int B_BYTES = BN * TC_BK * 2;
+  const int stage_bytes = p.nterms * A_BYTES + B_BYTES;
+  __shared__ __align__(8) uint64_t bars[2 * 8 + 1];  // full[], empty[], accumulator-ready
+  __shared__ uint32_t s_tmem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+  const int nk = (p.K + TC_BK - 1) / TC_BK;
+  const uint32_t bar0 = tc_smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8 * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8 * (8 + s); };
+  const uint32_t acc_bar = bar0 + 8 * 16;
+  const uint32_t ring = tc_smem_u32(smem);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstages; ++s) {
+      tc_mbar_init(full_bar(s), 1);
+      tc_mbar_init(empty_bar(s), 1);
+    }
+    tc_mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 2) {  // TMEM allocation: BN fp32 columns (power of two >= 32), by one warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tc_smem_u32(&s_tmem)), "r"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  pdl_wait();  // the activation terms are written by the preceding kernel
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int s = 0, ph = 0;
+      for (int kb = 0; kb < nk; ++kb) {
+        tc_mbar_wait(empty_bar(s), ph ^ 1);
+        const uint32_t dst = ring + (uint32_t)s * stage_bytes;
+        tc_mbar_expect_tx(full_bar(s), stage_bytes);
+        for (int t = 0; t < p.nterms; ++t)  // term t of X: rows [t*M + m0, +128) of the stacked [nterms*M, K] tensor
+          tc_tma_2d(dst + t * A_BYTES, &map_x, kb * TC_BK, t * p.M + m0, full_bar(s));
+        tc_tma_2d(dst + p.nterms * A_BYTES, &map_w, kb * TC_BK, n0, full_bar(s));
+        if (++s == nstages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int s = 0, ph = 0;
+      uint32_t accumulate = 0;
+      for (int kb = 0; kb < nk; ++kb) {
+        tc_mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t a0 = ring + (uint32_t)s * stage_bytes;
+        const uint32_t b0 = a0 + p.nterms * A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint64_t db = tc_smem_desc(b0 + k * 32);
+          for (int t = 0; t < p.nterms; ++t) {
+            tc_mma(tmem, tc_smem_desc(a0 + t * A_BYTES + k * 32), db, idesc, accumulate);
+            accumulate = 1;
+          }
+        }
+        tc_commit(empty_bar(s));  // the slot is free once these MMAs have read it
+        if (++s == nstages) { s = 0; ph ^= 1; }
+      }
+      tc_commit(acc_bar);  // accumulator complete
+    }
+  }
+  if (warp >= 2) {
+    // ===== epilogue: warp w may touch TMEM lanes [32 (w % 4), +32) =====
+    tc_mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    const bool swiglu = p.epi == LP_EPI_SWIGLU;
+    const int nout = swiglu ? p.N / 2 : p.N;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+      if (row < p.M) {
+        float y[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + c0 + j;
+          float t = __uint_as_float(v[j]);
+          if (p.bias && n < p.N) t += p.bias[n];
+          y[j] = maybe_round(t, p.round_bf16);
+        }
+        int ncols = 32, ocol = n0 + c0;
+        if (swiglu) {  // W rows interleaved: column 2i = fc_1 row i, 2i+1 = fc_2 row i (model.py:298-300)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = maybe_round(silu(y[2 * j]), p.round_bf16);
+            y[j] = maybe_round(a * y[2 * j + 1], p.round_bf16);
+          }
+          ncols = 16;
+          ocol = (n0 + c0) / 2;
+        } else if (p.epi == LP_EPI_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] = maybe_round(gelu_erf(y[j]), p.round_bf16);
+        } else if (p.epi == LP_EPI_RESIDUAL) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (ocol + j < nout) y[j] = maybe_round(p.residual[(size_t)row * nout + ocol + j] + y[j], p.round_bf16);
+        }
+        if (p.out_f32) {
+          float* dst = p.out_f32 + (size_t)row * nout + ocol;
+          if (ocol + ncols <= nout && (nout & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (j < ncols) *reinterpret_cast<float4*>(dst + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+          } else {
+            for (int j = 0; j < ncols; ++j)
+              if (ocol + j < nout) dst[j] = y[j];
+          }
+        }
+        if (p.out_bf) {
+          for (int t = 0; t < p.out_terms; ++t) {
+            __nv_bfloat16* dst = p.out_bf + ((size_t)t * p.M + row) * nout + ocol;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < ncols && ocol + j < nout) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(y[j]);
+                dst[j] = h;
+                y[j] -= __bfloat162float(h);
+              }
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(BN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// x fp32 [rows, K] (optionally through LayerNorm / RMSNorm) -> nterms bf16 arrays [nterms][rows, K] with x = sum of terms
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int rows, int K,
+                                                         int nterms, int norm_kind, const float* __restrict__ nw,
+                                                         const float* __restrict__ nb, float eps, int round_bf16) {
+  __shared__ float red[2][8];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int r = blockIdx.x;
+  const float* xr = x + (size_t)r * K;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float mean = 0.f, rstd = 1.f;
+  auto block_sum = [&](float v, int slot) {
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[slot][warp] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[slot][w];
+    return t;
+  };
+  if (norm_kind >= 0) {
+    float s = 0.f, ss = 0.f;
+    for (int k = threadIdx.x; k < K; k += 256) {
+      const float v = xr[k];
+      s += v;
+      ss += v * v;
+    }
+    s = block_sum(s, 0);
+    ss = block_sum(ss, 1);
+    if (norm_kind == LP_NORM_LAYERNORM) {
+      mean = s / (float)K;
+      float v2 = 0.f;
+      for (int k = threadIdx.x; k < K; k += 256) {
+        const float d = xr[k] - mean;
+        v2 += d * d;
+      }
+      v2 = block_sum(v2, 0);
+      rstd = 1.0f / sqrtf(v2 / (float)K + eps);
+    } else {
+      rstd = 1.0f / sqrtf(ss / (float)K + eps);
+    }
+  }
+  for (int k = threadIdx.x; k < K; k += 256) {
+    float v = xr[k];
+    if (norm_kind == LP_NORM_LAYERNORM) v = (v - mean) * rstd * nw[k] + (nb ? nb[k] : 0.f);
+    else if (norm_kind == LP_NORM_RMS) v = nw[k] * (v * rstd);
+    v = maybe_round(v, round_bf16);
+    for (int t = 0; t < nterms; ++t) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      out[((size_t)t * rows + r) * K + k] = h;
+      v -= __bfloat162float(h);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static TcEncodeFn tc_encode_fn() {
+  static TcEncodeFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<TcEncodeFn>(f);
+  }();
+  return fn;
+}
+
+// bf16 row-major [rows, K] -> 2-D map with a {64, box_rows} box, 128-byte swizzle; out-of-range rows / columns read as zero
+static bool tc_make_map(CUtensorMap* m, const void* ptr, int rows, int K, int box_rows) {
+  TcEncodeFn enc = tc_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static const CUtensorMap* tc_cached_map(const void* ptr, int rows, int K, int box_rows) {
+  static std::mutex mu;
+  static std::map<std::tuple<const void*, int, int, int>, CUtensorMap> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_tuple(ptr, rows, K, box_rows);
+  auto it = cache.find(key);
+  if (it != cache.end()) return &it->second;
+  CUtensorMap m;
+  if (!tc_make_map(&m, ptr, rows, K, box_rows)) return nullptr;
+  if (cache.size() > 8192) cache.clear();
+  return &cache.emplace(key, m).first->second;
+}
+
+template <int BN>
+static int tc_launch(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, void* stream) {
+  static bool attr_set = false;
+  auto kern = gemm_tc_kernel<BN>;
+  if (!attr_set) {
+    LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  const int stage_bytes = p.nterms * TC_BM * TC_BK * 2 + BN * TC_BK * 2;
+  int nstages = (212 * 1024) / stage_bytes;
+  if (nstages > 8) nstages = 8;
+  if (nstages < 2) return LP_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)nstages * stage_bytes + 1024;
+  dim3 grid((p.M + TC_BM - 1) / TC_BM, p.N / BN);
+  return launch(kern, grid, dim3(TC_THREADS), smem, stream, mx, mw, p, nstages);
+}
+
+}  // namespace lp
+
+extern "C" {
+
+int lp_split_bf16(const float* x, void* out_bf16, int rows, int K, int nterms, int norm_kind, const float* norm_w, const float* norm_b,
+                  float eps, int round_bf16, void* stream) {
+  if (!x || !out_bf16 || rows <= 0 || K <= 0 || nterms < 1 || nterms > 3) return LP_ERR_INVALID_ARG;
+  if (norm_kind >= 0 && !norm_w) return LP_ERR_INVALID_ARG;
+  return lp::launch(lp::split_bf16_kernel, dim3(rows), dim3(256), 0, stream, x, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, K, nterms,
+                    norm_kind, norm_w, norm_b, eps, round_bf16);
+}
+
+int lp_gemm_bf16_tc(const void* x_terms, int nterms, int M, const void* w_bf16, int N, int K, const float* bias, int epilogue,
+                    const float* residual, float* out_f32, void* out_bf16, int out_terms, int round_bf16, void* stream) {
+  if (!x_terms || !w_bf16 || M <= 0 || N <= 0 || K <= 0 || nterms < 1 || nterms > 3) return LP_ERR_INVALID_ARG;
+  if (!out_f32 && !out_bf16) return LP_ERR_INVALID_ARG;
+  if (out_bf16 && (out_terms < 1 || out_terms > 3)) return LP_ERR_INVALID_ARG;
+  if (epilogue < LP_EPI_NONE || epilogue > LP_EPI_RESIDUAL) return LP_ERR_INVALID_ARG;
+  if (epilogue == LP_EPI_RESIDUAL && !residual) return LP_ERR_INVALID_ARG;
+  if (K % 8 || N % 128) return LP_ERR_UNSUPPORTED;  // 16-byte global strides; whole 128-column tiles
+  if ((reinterpret_cast<uintptr_t>(x_terms) & 15) || (reinterpret_cast<uintptr_t>(w_bf16) & 15)) return LP_ERR_UNSUPPORTED;
+  const int BN = (N % 256 == 0 && nterms <= 2) ? 256 : 128;
+  const CUtensorMap* mx = lp::tc_cached_map(x_terms, nterms * M, K, lp::TC_BM);
+  const CUtensorMap* mw = lp::tc_cached_map(w_bf16, N, K, BN);
+  if (!mx || !mw) return LP_ERR_UNSUPPORTED;
+  lp::TcParams p;
+  p.bias = bias;
+  p.residual = residual;
+  p.out_f32 = out_f32;
+  p.out_bf = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.epi = epilogue;
+  p.round_bf16 = round_bf16;
+  p.nterms = nterms;
+  p.out_terms = out_terms;
+  return BN == 256 ? lp::tc_launch<256>(*mx, *mw, p, stream) : lp::tc_launch<128>(*mx, *mw, p, stream);
+}
+
+}  // extern "C"

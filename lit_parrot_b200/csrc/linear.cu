@@ -15,6 +15,7 @@ struct NormArgs {
 int linear_stream(const float* x, int M, const lp_weight& W, const NormArgs& nrm, int epi, const float* residual, float* out,
                   int round_bf16, void* stream);
 void set_stream_trace(void* buf);
+int dequant_bf16(const lp_weight& W, void* out, void* stream);
 static std::atomic<int> g_path{0};  // 0 auto, 1 force FMA, 2 force streaming
 }  // namespace lp
 
@@ -29,6 +30,11 @@ int lp_set_linear_path(int path) {
 int lp_debug_stream_trace(void* device_buf) {
   lp::set_stream_trace(device_buf);
   return LP_OK;
+}
+
+int lp_dequant_bf16(const lp_weight* W, void* out_bf16, void* stream) {
+  if (!W || !W->w || !out_bf16 || W->N <= 0 || W->K <= 0) return LP_ERR_INVALID_ARG;
+  return lp::dequant_bf16(*W, out_bf16, stream);
 }
 
 int lp_linear(const float* x, int M, const lp_weight* Wp, int epilogue, const float* residual, float* out, int round_bf16,

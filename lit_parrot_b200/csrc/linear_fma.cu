@@ -204,6 +204,53 @@ linear_fma_kernel(const float* __restrict__ x, int m_actual, lp_weight W, int ep
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// W (any stored format) -> dense bf16 [N, K] row-major, for the tensor-core prefill GEMM.  One thread per 16-byte chunk.
+// int4 / NF4 are dequantised exactly like the reference does for bf16 activations: (q - zero) * scale, resp.
+// code * absmax, rounded to bf16 (quantize/gptq.py:243-252).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(256) dequant_bf16_kernel(lp_weight W, __nv_bfloat16* __restrict__ out) {
+  constexpr int EL = FmtTraits<FMT>::ELEMS;
+  __shared__ float s_nf4[16];
+  if (threadIdx.x < 16) s_nf4[threadIdx.x] = c_nf4_code[threadIdx.x];
+  __syncthreads();
+  const int K = W.K, nchunks = K / EL;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)W.N * nchunks) return;
+  const int row = (int)(idx / nchunks), c = (int)(idx % nchunks);
+  size_t row_bytes;
+  if constexpr (FMT == LP_W_F32) row_bytes = (size_t)K * 4;
+  else if constexpr (FMT == LP_W_BF16) row_bytes = (size_t)K * 2;
+  else if constexpr (FMT == LP_W_INT8) row_bytes = (size_t)K;
+  else if constexpr (FMT == LP_W_INT4) row_bytes = (size_t)((K + 255) / 256 * 256) / 2;
+  else row_bytes = (size_t)K / 2;
+  const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(W.w) + (size_t)row * row_bytes + (size_t)c * 16);
+  float w[EL];
+  decode_chunk<FMT>(v, w, W, row, c * EL, 0, s_nf4);
+  const float rs = (FMT == LP_W_INT8) ? W.aux0[row] : 1.0f;
+  __nv_bfloat16* dst = out + (size_t)row * K + (size_t)c * EL;
+#pragma unroll
+  for (int i = 0; i < EL; ++i) dst[i] = __float2bfloat16_rn(w[i] * rs);
+}
+
+int dequant_bf16(const lp_weight& W, void* out, void* stream) {
+  const int K = W.K;
+  auto go = [&](auto kern, int el) {
+    if (K % el) return (int)LP_ERR_UNSUPPORTED;
+    const long long n = (long long)W.N * (K / el);
+    return launch(kern, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, W, reinterpret_cast<__nv_bfloat16*>(out));
+  };
+  switch (W.fmt) {
+    case LP_W_F32: return go(dequant_bf16_kernel<LP_W_F32>, 4);
+    case LP_W_BF16: return go(dequant_bf16_kernel<LP_W_BF16>, 8);
+    case LP_W_INT8: return W.aux0 ? go(dequant_bf16_kernel<LP_W_INT8>, 16) : (int)LP_ERR_INVALID_ARG;
+    case LP_W_INT4: return (W.aux0 && W.aux1 && W.group > 0 && W.group % 32 == 0) ? go(dequant_bf16_kernel<LP_W_INT4>, 32) : (int)LP_ERR_UNSUPPORTED;
+    case LP_W_NF4: return (W.aux0 && W.group > 0 && W.group % 32 == 0) ? go(dequant_bf16_kernel<LP_W_NF4>, 32) : (int)LP_ERR_UNSUPPORTED;
+    default: return LP_ERR_INVALID_ARG;
+  }
+}
+
 template <int FMT>
 static int launch_fma(const float* x, int M, const lp_weight& W, int epi, const float* residual, float* out, int round_bf16,
                       void* stream) {

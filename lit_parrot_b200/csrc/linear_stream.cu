@@ -30,7 +30,10 @@
 
 namespace lp {
 
-constexpr int GS_CWARPS = 16;                     // consumer warps (two per K-block of a stage)
+#ifndef GS_CWARPS_DEF
+#define GS_CWARPS_DEF 16
+#endif
+constexpr int GS_CWARPS = GS_CWARPS_DEF;          // consumer warps: 16 (two per K-block of a stage) or 8 (one per K-block)
 constexpr int GS_THREADS = (GS_CWARPS + 1) * 32;  // + 1 producer warp
 constexpr int GS_ROWS = 16;
 constexpr int GS_BLK_BYTES = GS_ROWS * 128;       // one K-block of a tile: 16 rows x 128 bytes (64 bf16 / 256 int4 columns)
@@ -401,7 +404,9 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
     mbar_wait(full_bar(s), ph);
     if (p.trace && threadIdx.x == 0 && u < 4) p.trace[blockIdx.x * 8 + 3 + u] = gs_now();
     const uint32_t st = ring_u32 + (uint32_t)s * p.stage_stride;
-    const int kbl = warp >> 1, sub = warp & 1;  // K-block inside the stage; which half of it this warp owns
+    constexpr int NSUB = 2 * GS_KB / GS_CWARPS;  // halves of a K-block per warp: 1 (16 warps) or 2 (8 warps)
+    const int kbl = NSUB == 1 ? warp >> 1 : warp;  // K-block inside the stage
+    const int sub0 = NSUB == 1 ? (warp & 1) : 0;
     const int kb = ks * GS_KB + kbl;
     if (kb < p.nkb) {
       if constexpr (FMT == LP_W_BF16) {
@@ -409,8 +414,8 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
         const uint32_t blk = st + kbl * GS_BLK_BYTES;
         const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
-        for (int kk2 = 0; kk2 < 2; ++kk2) {
-          const int kk = sub * 2 + kk2;
+        for (int kk2 = 0; kk2 < 2 * NSUB; ++kk2) {
+          const int kk = sub0 * 2 + kk2;
           uint32_t a[4];
           gs_ldsm_x4(a, blk + row * 128 + (((kk * 2 + (lane >> 4)) ^ (row & 7)) << 4));
           const int k0 = kcol + kk * 16;
@@ -428,8 +433,9 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
         const unsigned char* blk = ring + (size_t)s * p.stage_stride + kbl * GS_BLK_BYTES;
         const unsigned char* auxp = ring + (size_t)s * p.stage_stride + GS_KB * GS_BLK_BYTES;
         const int g_begin = p.gp128 == 1 ? ks * GS_KB * 2 : (ks * GS_KB * 2) / p.gp128;
-        {
-          const int cc = sub;
+#pragma unroll
+        for (int cs = 0; cs < NSUB; ++cs) {
+          const int cc = sub0 + cs;
           const int c = kb * 2 + cc;  // 128-column chunk inside the row
           if (c < nch128) {
             const uint4 wa4 = *reinterpret_cast<const uint4*>(blk + pr0 * 128 + (((cc * 4 + t) ^ (pr0 & 7)) << 4));
@@ -498,14 +504,19 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
         acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
       }
       const int fin = lt % GS_CWARPS;        // first finalising warp of this tile (rotates)
-      const int nfin = p.M;                  // one finalising warp per activation row
+      const int nfin = p.M < GS_CWARPS ? p.M : GS_CWARPS;  // one finalising warp per activation row (or several rows each)
       const int fidx = (warp - fin + GS_CWARPS) % GS_CWARPS;
       if (fidx >= nfin) {
-        asm volatile("bar.arrive %0, %1;\n" ::"r"(2 + par), "n"(GS_CWARPS * 32) : "memory");
+        // barrier ids are immediates on purpose: a register id makes ptxas reserve all 16 named barriers of the SM for
+        // one CTA, which forbids two of these kernels to be co-resident (PDL overlap)
+        if (par == 0) asm volatile("bar.arrive 2, %0;\n" ::"n"(GS_CWARPS * 32) : "memory");
+        else asm volatile("bar.arrive 3, %0;\n" ::"n"(GS_CWARPS * 32) : "memory");
       } else {
-        asm volatile("bar.sync %0, %1;\n" ::"r"(2 + par), "n"(GS_CWARPS * 32) : "memory");
+        if (par == 0) asm volatile("bar.sync 2, %0;\n" ::"n"(GS_CWARPS * 32) : "memory");
+        else asm volatile("bar.sync 3, %0;\n" ::"n"(GS_CWARPS * 32) : "memory");
         // lane = (row of the tile, half): each half adds the partial sums of 8 warps per B column, then one shuffle
-        const int m = fidx, rr = lane & 15, half = lane >> 4;
+        const int rr = lane & 15, half = lane >> 4;
+        for (int m = fidx; m < p.M; m += nfin) {
         const float* rb = red + ((size_t)par * GS_CWARPS + half * (GS_CWARPS / 2)) * 16 * NCOL + rr * NCOL + m * p.split;
         float cs[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -540,7 +551,11 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
           else if (p.epi == LP_EPI_RESIDUAL) y = maybe_round(p.residual[(size_t)m * N + row] + y, p.round_bf16);
           p.out[(size_t)m * N + row] = y;
         }
-        if (nfin > 1) asm volatile("bar.sync %0, %1;\n" ::"r"(4 + par), "r"(nfin * 32) : "memory");  // all finalisers have read `red`
+        }
+        if (nfin > 1) {  // all finalisers have read `red`
+          if (par == 0) asm volatile("bar.sync 4, %0;\n" ::"r"(nfin * 32) : "memory");
+          else asm volatile("bar.sync 5, %0;\n" ::"r"(nfin * 32) : "memory");
+        }
         __syncwarp();
         if (fidx == 0 && lane == 0) {
           __threadfence_block();
@@ -629,6 +644,9 @@ static int gs_launch(const CUtensorMap& map, const GsParams& p, size_t smem, int
   auto kern = linear_stream_kernel<FMT, NB>;
   if (!attr_set) {
     LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)));
+    // keep the SM's L1/shared split at maximum shared memory: otherwise the carve-out is sized for ONE CTA of this kernel
+    // and the next kernel's CTAs (PDL) cannot become resident before this one drains
+    LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   return launch(kern, dim3(grid), dim3(GS_THREADS), smem, stream, map, p);
@@ -637,7 +655,7 @@ static int gs_launch(const CUtensorMap& map, const GsParams& p, size_t smem, int
 // `nrm.kind` -1: no fused norm
 int linear_stream(const float* x, int M, const lp_weight& W, const NormArgs& nrm, int epi, const float* residual, float* out,
                   int round_bf16, void* stream) {
-  static_assert(2 * GS_KB == GS_CWARPS, "two consumer warps per K-block of a stage");
+  static_assert(2 * GS_KB == GS_CWARPS || GS_KB == GS_CWARPS, "one or two consumer warps per K-block of a stage");
   if (W.fmt != LP_W_BF16 && W.fmt != LP_W_INT4) return LP_ERR_UNSUPPORTED;
   if (W.N % GS_ROWS) return LP_ERR_UNSUPPORTED;
   const int K = W.K;

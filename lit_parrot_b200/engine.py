@@ -161,6 +161,30 @@ class Engine:
             n += L.qkv.stored_bytes + L.proj.stored_bytes + L.fc.stored_bytes + L.mlp_proj.stored_bytes
         return n
 
+    # ------------------------------------------------------------------ prefill on the tcgen05 GEMM
+    def tc_eligible(self, rows: int) -> bool:
+        """T > 1 goes through lp_gemm_bf16_tc when every linear is bf16 (fp32-activation accuracy via bf16 term splitting) or,
+        in bf16-faithful mode, quantised (weights expanded to bf16 like the reference's bf16 dequantisation)."""
+        if rows < 9 or getattr(self, "disable_tc", False):
+            return False
+        mats = [self.lm_head] + [m for L in self.layers for m in (L.qkv, L.proj, L.fc, L.mlp_proj)]
+        if any(m.N % 128 or m.K % 8 for m in mats if m is not self.lm_head):
+            return False
+        if all(m.fmt == _lib.LP_W_BF16 for m in mats):
+            return True
+        return self.round == 1 and all(m.fmt in (_lib.LP_W_BF16, _lib.LP_W_INT4, _lib.LP_W_NF4, _lib.LP_W_INT8) for m in mats)
+
+    def _bf16_weight(self, W: "PackedLinear", stream: int) -> int:
+        """Device pointer of W as dense bf16 [N, K]; quantised formats are expanded into a scratch buffer (stream ordered)."""
+        if W.fmt == _lib.LP_W_BF16:
+            return W.rec.w
+        need = W.N * W.K
+        if getattr(self, "_wscratch", None) is None or self._wscratch.numel() < need:
+            biggest = max(m.N * m.K for L in self.layers for m in (L.qkv, L.proj, L.fc, L.mlp_proj))
+            self._wscratch = torch.empty(max(need, biggest), dtype=torch.bfloat16, device=self.device)
+        _lib.check(self.lib.lp_dequant_bf16(W.ref, self._wscratch.data_ptr(), stream), "lp_dequant_bf16")
+        return self._wscratch.data_ptr()
+
     def buffers(self, rows: int, B: int, T: int, max_seq: int) -> Dict[str, torch.Tensor]:
         key = (rows, max_seq)
         b = self._bufs.get(key)
@@ -173,6 +197,10 @@ class Engine:
             b = dict(x=f(rows, E), n1=f(rows, E), n2=f(rows, E), qkv=f(rows, cfg.qkv_rows), q=f(rows, E), att=f(rows, E),
                      xmid=f(rows, E), u=f(rows, I), xf=f(rows, E), logits=f(rows, V),
                      ws=torch.zeros(max(ws_bytes, 16), device=dev, dtype=torch.uint8))  # zeroed: split-merge tickets
+            if self.tc_eligible(rows):
+                # bf16 split terms of the GEMM operands: [3][rows, width]
+                bf = lambda w: torch.empty((3, rows, w), device=dev, dtype=torch.bfloat16)  # noqa: E731
+                b.update(t_n=bf(E), t_att=bf(E), t_u=bf(I))
             if len(self._bufs) > 8:
                 self._bufs.clear()
             self._bufs[key] = b
@@ -252,6 +280,66 @@ class Engine:
         else:
             norm_linear(x, self.lnf_w, self.lnf_b, self.lm_head, _lib.LP_EPI_NONE, logits, xf, "lp_linear(lm_head)")
 
+    def _run_tc(self, b: Dict[str, torch.Tensor], idx_ptr: int, idx64: int, pos_ptr: int, caches, B: int, T: int, stream: int,
+                last_only: bool = False) -> None:
+        """T > 1: the same op sequence as `_run`, with every projection on the tcgen05 GEMM (lp_gemm_bf16_tc)."""
+        lib, cfg, r, chk = self.lib, self.cfg, self.round, _lib.check
+        rows = B * T
+        E, H, G, hs, I = cfg.n_embd, cfg.n_head, cfg.n_query_groups, cfg.head_size, cfg.intermediate_size
+        max_seq = caches[0][0].size(2)
+        kvd = _KV_OF_DTYPE[caches[0][0].dtype]
+        x, qkv, q, att, xmid, u = (b[k].data_ptr() for k in ("x", "qkv", "q", "att", "xmid", "u"))
+        t_n, t_att, t_u = b["t_n"].data_ptr(), b["t_att"].data_ptr(), b["t_u"].data_ptr()
+        ws, ws_bytes = b["ws"].data_ptr(), b["ws"].numel()
+        scale = 1.0 / math.sqrt(hs)
+        nt = 1 if r else (3 if rows <= 256 else 2)  # bf16 terms per activation
+        nk = self.norm_kind
+        chk(lib.lp_embed(idx_ptr, idx64, None, self.wte.data_ptr(), _KV_OF_DTYPE[self.wte.dtype], x, rows, E, r, stream), "lp_embed")
+
+        def gemm(terms, W, epi, res, out_f32, out_bf=None):
+            chk(lib.lp_gemm_bf16_tc(terms, nt, rows, self._bf16_weight(W, stream), W.N, W.K, W.rec.bias, epi, res, out_f32, out_bf,
+                                    nt, r, stream), "lp_gemm_bf16_tc")
+
+        def norm_split(src, nw, nb, dst):
+            chk(lib.lp_split_bf16(src, dst, rows, E, nt, nk, _ptr(nw), _ptr(nb), cfg.norm_eps, r, stream), "lp_split_bf16")
+
+        for li, L in enumerate(self.layers):
+            kc, vc = caches[li][0].data_ptr(), caches[li][1].data_ptr()
+            norm_split(x, L.n1_w, L.n1_b, t_n)
+            gemm(t_n, L.qkv, _lib.LP_EPI_NONE, None, qkv)
+            chk(lib.lp_rope_kv_append(qkv, _ptr(self.cos), _ptr(self.sin), pos_ptr, q, kc, vc, kvd, B, T, H, G, hs, cfg.rope_n_elem,
+                                      max_seq, r, stream), "lp_rope_kv_append")
+            chk(lib.lp_attn_decode(q, kc, vc, kvd, pos_ptr, att, ws, ws_bytes, B, T, H, G, hs, max_seq, scale, r, stream),
+                "lp_attn_decode")
+            chk(lib.lp_split_bf16(att, t_att, rows, E, nt, -1, None, None, 0.0, 0, stream), "lp_split_bf16")
+            if cfg.parallel_residual:
+                if not cfg.shared_attention_norm:
+                    norm_split(x, L.n2_w, L.n2_b, t_n)  # shared norm: t_n already holds norm_1(x)
+                gemm(t_n, L.fc, self.act, None, None, t_u)
+                gemm(t_att, L.proj, _lib.LP_EPI_RESIDUAL, x, xmid)
+                gemm(t_u, L.mlp_proj, _lib.LP_EPI_RESIDUAL, xmid, x)
+            else:
+                if cfg.shared_attention_norm:
+                    raise NotImplementedError("No checkpoint amongst the ones we support uses this configuration"
+                                              " (non-parallel residual and shared attention norm).")
+                gemm(t_att, L.proj, _lib.LP_EPI_RESIDUAL, x, x)
+                norm_split(x, L.n2_w, L.n2_b, t_n)
+                gemm(t_n, L.fc, self.act, None, None, t_u)
+                gemm(t_u, L.mlp_proj, _lib.LP_EPI_RESIDUAL, x, x)
+        xf, logits = b["xf"].data_ptr(), b["logits"].data_ptr()
+        if last_only:
+            # only the last position of each sequence feeds the sampler (generate/base.py:136)
+            for bi in range(B):
+                src = x + ((bi + 1) * T - 1) * E * 4
+                chk(lib.lp_norm(nk, src, _ptr(self.lnf_w), _ptr(self.lnf_b), cfg.norm_eps, xf + bi * E * 4, 1, E, r, stream), "lp_norm")
+            chk(lib.lp_linear(xf, B, self.lm_head.ref, _lib.LP_EPI_NONE, None, logits, r, stream), "lp_linear(lm_head)")
+        elif self.lm_head.N % 128 == 0:
+            norm_split(x, self.lnf_w, self.lnf_b, t_n)
+            gemm(t_n, self.lm_head, _lib.LP_EPI_NONE, None, logits)
+        else:
+            chk(lib.lp_norm(nk, x, _ptr(self.lnf_w), _ptr(self.lnf_b), cfg.norm_eps, xf, rows, E, r, stream), "lp_norm")
+            chk(lib.lp_linear(xf, rows, self.lm_head.ref, _lib.LP_EPI_NONE, None, logits, r, stream), "lp_linear(lm_head)")
+
     # ------------------------------------------------------------------ public entry used by GPT.forward
     def _check_caches(self, caches, B: int) -> None:
         k = caches[0][0]
@@ -279,7 +367,10 @@ class Engine:
         idx = idx.contiguous()
         pos32 = pos.to(device=self.device, dtype=torch.int32).contiguous()
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        self._run(b, idx.data_ptr(), int(idx.dtype == torch.int64), None, pos32.data_ptr(), caches, B, T, stream, last_only)
+        if self.tc_eligible(B * T):
+            self._run_tc(b, idx.data_ptr(), int(idx.dtype == torch.int64), pos32.data_ptr(), caches, B, T, stream, last_only)
+        else:
+            self._run(b, idx.data_ptr(), int(idx.dtype == torch.int64), None, pos32.data_ptr(), caches, B, T, stream, last_only)
         out = b["logits"][:B].view(B, 1, V) if (last_only and T > 1) else b["logits"].view(B, T, V)
         return out if raw_logits else out.to(self.param_dtype, copy=True)
 

@@ -408,3 +408,72 @@ def test_norm_linear_fused(lib, kind, fmt, M, N, K):
     torch.testing.assert_close(out, want, rtol=3e-5, atol=3e-5 * math.sqrt(K))
     # the fusion must decline (not mis-compute) what it does not cover
     assert lib.lp_norm_linear(kind, nw.data_ptr(), None, 1e-5, x.data_ptr(), M, ctypes.byref(rec), 0, None, out.data_ptr(), 1, stream()) == -2
+
+
+@pytest.mark.parametrize("nterms", [1, 2, 3])
+@pytest.mark.parametrize("M,N,K", [(16, 128, 64), (128, 256, 512), (200, 384, 4096), (333, 4608, 4544), (2048, 512, 1024), (9, 1280, 8192)])
+def test_gemm_bf16_tc(lib, nterms, M, N, K):
+    """lp_split_bf16 + lp_gemm_bf16_tc (TMA + tcgen05.mma, accumulator in tensor memory) against float64 F.linear.
+    nterms = 1: bf16 activations (the reference's bf16-true matmul inputs); 2 / 3: fp32-activation accuracy."""
+    x = f32(M, K, seed=1)
+    w = f32(N, K, seed=2, scale=0.05).bfloat16()
+    bias = f32(N, seed=3)
+    res = f32(M, N, seed=4)
+    terms = torch.empty(nterms, M, K, dtype=torch.bfloat16, device=DEV)
+    _lib.check(lib.lp_split_bf16(x.data_ptr(), terms.data_ptr(), M, K, nterms, -1, None, None, 0.0, 0, stream()), "lp_split_bf16")
+    xe = terms.double().sum(0)  # what the tensor cores see
+    if nterms == 3:
+        assert torch.equal(xe.float(), x)  # three bf16 terms carry all 24 bits
+    ref = F.linear(xe, w.double(), bias.double())
+    tol = dict(rtol=2e-5, atol=2e-5 * math.sqrt(K))
+    for epi in (0, 1, 2, 3):
+        nout = N // 2 if epi == 2 else N
+        out = torch.full((M, nout), float("nan"), device=DEV)
+        out_t = torch.zeros(2, M, nout, dtype=torch.bfloat16, device=DEV)
+        _lib.check(lib.lp_gemm_bf16_tc(terms.data_ptr(), nterms, M, w.data_ptr(), N, K, bias.data_ptr(), epi, res.data_ptr(),
+                                       out.data_ptr(), out_t.data_ptr(), 2, 0, stream()), "lp_gemm_bf16_tc")
+        torch.cuda.synchronize()
+        want = ref_epilogue(ref, epi, res.double()).float()
+        if epi == 2:  # silu(a) * b multiplies the absolute error of a by |b| (up to ~10 here)
+            torch.testing.assert_close(out, want, rtol=5e-4, atol=2e-4 * math.sqrt(K))
+        else:
+            torch.testing.assert_close(out, want, **tol)
+        # the bf16 split of the result (operand of the next GEMM): hi + lo reproduces it to 16 bits
+        torch.testing.assert_close(out_t.float().sum(0), out, rtol=2 ** -15, atol=1e-30)
+    # fused norm in the splitter
+    nw, nb = 1 + 0.1 * f32(K, seed=5), 0.1 * f32(K, seed=6)
+    for kind in (0, 1):
+        _lib.check(lib.lp_split_bf16(x.data_ptr(), terms.data_ptr(), M, K, nterms, kind, nw.data_ptr(), nb.data_ptr() if kind == 0 else None,
+                                     1e-5, 0, stream()), "lp_split_bf16")
+        want = F.layer_norm(x, (K,), nw, nb, 1e-5) if kind == 0 else O.rms_norm(x, nw, 1e-5)
+        torch.testing.assert_close(terms.float().sum(0), want, rtol=2 ** (-8 * nterms + 1), atol=1e-5)
+
+
+@pytest.mark.parametrize("fmt", ["int4", "nf4", "int8"])
+def test_dequant_bf16(lib, fmt):
+    N, K = 96, 512
+    w = torch.randn(N, K, generator=torch.Generator().manual_seed(8)) * 0.02
+    out = torch.empty(N, K, dtype=torch.bfloat16, device=DEV)
+    p = lambda a: a.data_ptr()  # noqa: E731
+    if fmt == "int4":
+        packed, scales, zeros = O.gptq_rtn_quantize(w, 128)
+        src = torch.empty((K // 2, N), dtype=torch.uint8, device=DEV).t()
+        src.copy_(packed)
+        rows = torch.empty((N, lib.lp_int4_row_bytes(K)), dtype=torch.uint8, device=DEV)
+        _lib.check(lib.lp_repack_gptq_int4(src.data_ptr(), rows.data_ptr(), N, K, stream()))
+        sc, ze = scales.to(DEV).contiguous(), zeros.to(DEV).contiguous()
+        rec = LpWeight(p(rows), p(sc), p(ze), None, None, _lib.LP_W_INT4, N, K, 128, 0, 0)
+        want = O.gptq_dequant(packed, scales, zeros).bfloat16()
+    elif fmt == "nf4":
+        packed, absmax = O.nf4_quantize(w)
+        pk, am = packed.to(DEV), absmax.to(DEV)
+        rec = LpWeight(p(pk), p(am), None, None, None, _lib.LP_W_NF4, N, K, 64, 0, 0)
+        want = O.nf4_dequantize(packed, absmax, w.shape).bfloat16()
+    else:
+        cb, scb = O.int8_quantize(w)
+        cbd, sc = cb.to(DEV), (scb / 127.0).to(DEV)
+        rec = LpWeight(p(cbd), p(sc), None, None, None, _lib.LP_W_INT8, N, K, 0, 0, 0)
+        want = O.int8_dequantize(cb, scb).bfloat16()
+    _lib.check(lib.lp_dequant_bf16(ctypes.byref(rec), out.data_ptr(), stream()), "lp_dequant_bf16")
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out.float().cpu(), want.float(), rtol=2 ** -7, atol=1e-8)
