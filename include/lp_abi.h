@@ -173,6 +173,13 @@ int lp_attn_decode_fused(const float* qkv, const float* cos, const float* sin, c
                          void* v_cache, int kv_dtype, void* workspace, size_t workspace_bytes, int B, int H, int G, int hs,
                          int n_elem, int max_seq, float scale, int round_bf16, void* stream);
 
+/* Causal attention of T > 1 consecutive query positions (pos[0] .. pos[0] + T - 1, already appended to the cache by
+ * lp_rope_kv_append) against the bf16 KV cache, FlashAttention-2 style on the tensor cores (model.py:247, 256-275 with the
+ * mask rows of model.py:91-92).  q, out fp32 [B*T, H*hs].  hs 64 / 128, bf16 cache, pos[0] + T <= max_seq (the caller
+ * guarantees the positions are consecutive and do not wrap); LP_ERR_UNSUPPORTED otherwise -> lp_attn_decode. */
+int lp_attn_prefill(const float* q, const void* k_cache, const void* v_cache, int kv_dtype, const int32_t* pos, float* out, int B,
+                    int T, int H, int G, int hs, int max_seq, float scale, int round_bf16, void* stream);
+
 /* replaces the sampling tail of generate() (generate/base.py:136-153): logits/temperature, top-k threshold
  * (ties with the k-th value survive), softmax, one multinomial draw (exponential race, Philox keyed by
  * (seed, *step)).  top_k == 1 is lowest-index arg-max.  logits fp32 [rows, V] -> token_out int32 [rows].

@@ -506,3 +506,222 @@ int lp_attn_decode_fused(const float* qkv, const float* cos, const float* sin, c
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// Prefill attention (T > 1 query rows against the bf16 KV cache, causal): FlashAttention-2 style on mma.sync.
+//
+//   reference: scaled_dot_product_attention with the lower-triangular mask rows of `input_pos` (model.py:91-92, 256-275).
+//
+// grid (ceil(T / 64), H, B), 128 threads: a CTA owns 64 consecutive query positions of one head, each warp 16 of them.
+// K/V tiles (64 keys) of the head's KV group stream through a cp.async ring exactly as in the decode kernel; tiles entirely
+// above the causal diagonal are never loaded.  q (already rotated, fp32) is split into bf16 hi + lo, P likewise, unless
+// `exact` is 0 (bf16-faithful mode: q is bf16-valued and P is rounded to bf16 like the reference's bf16 SDPA).
+// Query row t sits at position pos0 + t and attends keys [0, pos0 + t]; requires pos0 + T <= max_seq (no ring wrap).
+// =====================================================================================================================
+namespace lp {
+
+template <int HS>
+__global__ void __launch_bounds__(AD_THREADS)
+attn_prefill_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kc, const __nv_bfloat16* __restrict__ vc,
+                    const int* __restrict__ pos, float* __restrict__ out, int T, int H, int G, int max_seq, float scale_log2, int exact,
+                    int round_bf16) {
+  constexpr int CH = HS / 8;
+  constexpr int STAGE_BYTES = AD_TILE * HS * 2;
+  constexpr int NT = AD_TILE / 8;  // score n-tiles per warp: every warp sees the whole 64-key tile
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g8 = lane >> 2, t4 = lane & 3;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int g = h / (H / G);
+  const uint32_t sKV_u32 = smem_u32(smem);
+
+  pdl_wait();
+  pdl_launch_dependents();
+  const int pos0 = pos[0];
+  const int q_first = qt * 64;                       // first query row (time index) of the CTA
+  const int q_last = min(T, q_first + 64) - 1;
+  const int k_end = pos0 + q_last + 1;               // keys [0, k_end) are visible to at least one row
+  const int ntiles = (k_end + AD_TILE - 1) / AD_TILE;
+  const __nv_bfloat16* kbase = kc + ((size_t)b * G + g) * max_seq * HS;
+  const __nv_bfloat16* vbase = vc + ((size_t)b * G + g) * max_seq * HS;
+
+  auto issue_tile = [&](int t) {
+    if (t < ntiles) {
+      const int tile0 = t * AD_TILE;
+      const uint32_t sk = sKV_u32 + (t % AD_STAGES) * 2 * STAGE_BYTES, sv = sk + STAGE_BYTES;
+#pragma unroll
+      for (int i = tid; i < AD_TILE * CH; i += AD_THREADS) {
+        const int row = i / CH, c = i % CH;
+        const int key = tile0 + row;
+        const bool valid = key < k_end;
+        const size_t off = (size_t)(valid ? key : 0) * HS + c * 8;
+        const uint32_t d = (row * CH + (c ^ (row & 7))) * 16;
+        cp_async16(sk + d, kbase + off, valid ? 16 : 0);
+        cp_async16(sv + d, vbase + off, valid ? 16 : 0);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < AD_STAGES - 1; ++s) issue_tile(s);
+
+  // ---- this warp's 16 query rows as A fragments (hi / lo), straight from global memory ----
+  const int r0 = q_first + warp * 16 + g8, r1 = r0 + 8;  // time indices of the two rows this lane holds
+  uint32_t qh[HS / 16][4], ql[HS / 16][4];
+  {
+    const float* q0 = q + ((size_t)b * T + min(r0, T - 1)) * H * HS + (size_t)h * HS;
+    const float* q1 = q + ((size_t)b * T + min(r1, T - 1)) * H * HS + (size_t)h * HS;
+#pragma unroll
+    for (int ks = 0; ks < HS / 16; ++ks) {
+      const float2 a = *reinterpret_cast<const float2*>(q0 + ks * 16 + 2 * t4);
+      const float2 c = *reinterpret_cast<const float2*>(q1 + ks * 16 + 2 * t4);
+      const float2 a8 = *reinterpret_cast<const float2*>(q0 + ks * 16 + 8 + 2 * t4);
+      const float2 c8 = *reinterpret_cast<const float2*>(q1 + ks * 16 + 8 + 2 * t4);
+      split2(a.x * scale_log2, a.y * scale_log2, qh[ks][0], ql[ks][0]);
+      split2(c.x * scale_log2, c.y * scale_log2, qh[ks][1], ql[ks][1]);
+      split2(a8.x * scale_log2, a8.y * scale_log2, qh[ks][2], ql[ks][2]);
+      split2(c8.x * scale_log2, c8.y * scale_log2, qh[ks][3], ql[ks][3]);
+    }
+  }
+  const int lim0 = pos0 + r0, lim1 = pos0 + r1;  // last visible key of each row
+
+  float O[HS / 8][4];
+  float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int dn = 0; dn < HS / 8; ++dn) O[dn][0] = O[dn][1] = O[dn][2] = O[dn][3] = 0.f;
+
+  for (int t = 0; t < ntiles; ++t) {
+    cp_async_wait<AD_STAGES - 2>();
+    __syncthreads();
+    issue_tile(t + AD_STAGES - 1);
+    const int tile0 = t * AD_TILE;
+    const uint32_t sk = sKV_u32 + (t % AD_STAGES) * 2 * STAGE_BYTES, sv = sk + STAGE_BYTES;
+    if (tile0 > pos0 + q_first + warp * 16 + 15) continue;  // whole tile above this warp's diagonal (warp-uniform)
+
+    float S[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) S[nt][0] = S[nt][1] = S[nt][2] = S[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < HS / 16; ks += 2) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        uint32_t kb[4];
+        const int row = nt * 8 + (lane & 7), c = 2 * ks + (lane >> 3);
+        ldsm_x4(kb, sk + (row * CH + (c ^ (row & 7))) * 16);
+        mma16816(S[nt], qh[ks], kb[0], kb[1]);
+        mma16816(S[nt], qh[ks + 1], kb[2], kb[3]);
+        if (exact) {
+          mma16816(S[nt], ql[ks], kb[0], kb[1]);
+          mma16816(S[nt], ql[ks + 1], kb[2], kb[3]);
+        }
+      }
+    }
+    float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int key = tile0 + nt * 8 + 2 * t4;
+      if (key > lim0) S[nt][0] = -CUDART_INF_F;
+      if (key + 1 > lim0) S[nt][1] = -CUDART_INF_F;
+      if (key > lim1) S[nt][2] = -CUDART_INF_F;
+      if (key + 1 > lim1) S[nt][3] = -CUDART_INF_F;
+      mx0 = fmaxf(mx0, fmaxf(S[nt][0], S[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(S[nt][2], S[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float base0 = (mn0 == -CUDART_INF_F) ? 0.f : mn0, base1 = (mn1 == -CUDART_INF_F) ? 0.f : mn1;
+    const float corr0 = exp2f(m0 - base0), corr1 = exp2f(m1 - base1);
+    m0 = mn0;
+    m1 = mn1;
+    uint32_t ph[NT][2], pl[NT][2];
+    float ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      float p0 = exp2f(S[nt][0] - base0), p1 = exp2f(S[nt][1] - base0);
+      float p2 = exp2f(S[nt][2] - base1), p3 = exp2f(S[nt][3] - base1);
+      split2(p0, p1, ph[nt][0], pl[nt][0]);
+      split2(p2, p3, ph[nt][1], pl[nt][1]);
+      if (!exact) {  // the row sum uses the probabilities that are actually multiplied with V
+        const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&ph[nt][0]);
+        const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&ph[nt][1]);
+        p0 = __bfloat162float(h0.x); p1 = __bfloat162float(h0.y);
+        p2 = __bfloat162float(h1.x); p3 = __bfloat162float(h1.y);
+      }
+      ls0 += p0 + p1;
+      ls1 += p2 + p3;
+    }
+    l0 = l0 * corr0 + ls0;
+    l1 = l1 * corr1 + ls1;
+#pragma unroll
+    for (int dn = 0; dn < HS / 8; ++dn) {
+      O[dn][0] *= corr0;
+      O[dn][1] *= corr0;
+      O[dn][2] *= corr1;
+      O[dn][3] *= corr1;
+    }
+#pragma unroll
+    for (int kk = 0; kk < AD_TILE / 16; ++kk) {
+      const uint32_t ah[4] = {ph[2 * kk][0], ph[2 * kk][1], ph[2 * kk + 1][0], ph[2 * kk + 1][1]};
+      const uint32_t al[4] = {pl[2 * kk][0], pl[2 * kk][1], pl[2 * kk + 1][0], pl[2 * kk + 1][1]};
+#pragma unroll
+      for (int dn = 0; dn < HS / 8; dn += 2) {
+        uint32_t vb[4];
+        const int row = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, c = dn + (lane >> 4);
+        ldsm_x4_trans(vb, sv + (row * CH + (c ^ (row & 7))) * 16);
+        mma16816(O[dn], ah, vb[0], vb[1]);
+        mma16816(O[dn + 1], ah, vb[2], vb[3]);
+        if (exact) {
+          mma16816(O[dn], al, vb[0], vb[1]);
+          mma16816(O[dn + 1], al, vb[2], vb[3]);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  if (r0 < T) {
+    float* o = out + ((size_t)b * T + r0) * H * HS + (size_t)h * HS;
+#pragma unroll
+    for (int dn = 0; dn < HS / 8; ++dn)
+      *reinterpret_cast<float2*>(o + dn * 8 + 2 * t4) = make_float2(maybe_round(O[dn][0] * i0, round_bf16), maybe_round(O[dn][1] * i0, round_bf16));
+  }
+  if (r1 < T) {
+    float* o = out + ((size_t)b * T + r1) * H * HS + (size_t)h * HS;
+#pragma unroll
+    for (int dn = 0; dn < HS / 8; ++dn)
+      *reinterpret_cast<float2*>(o + dn * 8 + 2 * t4) = make_float2(maybe_round(O[dn][2] * i1, round_bf16), maybe_round(O[dn][3] * i1, round_bf16));
+  }
+}
+
+template <int HS>
+static int ap_launch(const float* q, const void* kc, const void* vc, const int* pos, float* out, int B, int T, int H, int G, int max_seq,
+                     float scale, int exact, int round_bf16, void* stream) {
+  static bool attr_set = false;
+  auto kern = attn_prefill_kernel<HS>;
+  const size_t smem = (size_t)AD_STAGES * 2 * AD_TILE * HS * 2;
+  if (!attr_set) {
+    LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  return launch(kern, dim3((T + 63) / 64, H, B), dim3(AD_THREADS), smem, stream, q, reinterpret_cast<const __nv_bfloat16*>(kc),
+                reinterpret_cast<const __nv_bfloat16*>(vc), pos, out, T, H, G, max_seq, scale * 1.4426950408889634f, exact, round_bf16);
+}
+
+}  // namespace lp
+
+extern "C" int lp_attn_prefill(const float* q, const void* k_cache, const void* v_cache, int kv_dtype, const int32_t* pos, float* out, int B,
+                               int T, int H, int G, int hs, int max_seq, float scale, int round_bf16, void* stream) {
+  if (!q || !k_cache || !v_cache || !pos || !out) return LP_ERR_INVALID_ARG;
+  if (B <= 0 || T <= 0 || H <= 0 || G <= 0 || H % G || max_seq <= 0) return LP_ERR_INVALID_ARG;
+  if (kv_dtype != LP_BF16 || (hs != 64 && hs != 128) || T > max_seq) return LP_ERR_UNSUPPORTED;
+  const int exact = round_bf16 ? 0 : 1;
+  if (hs == 128) return lp::ap_launch<128>(q, k_cache, v_cache, pos, out, B, T, H, G, max_seq, scale, exact, round_bf16, stream);
+  return lp::ap_launch<64>(q, k_cache, v_cache, pos, out, B, T, H, G, max_seq, scale, exact, round_bf16, stream);
+}

@@ -127,6 +127,7 @@ class Engine:
         self._bufs: Dict[int, Dict[str, torch.Tensor]] = {}
         self._graphs: Dict[Tuple, Tuple] = {}
         self._scratch: Optional[Tuple] = None
+        self._consecutive = False
 
     # ------------------------------------------------------------------ bookkeeping
     def set_rope(self, rope) -> None:
@@ -248,8 +249,7 @@ class Engine:
             if rc == -2:
                 chk(lib.lp_rope_kv_append(qkv, _ptr(self.cos), _ptr(self.sin), pos_ptr, q, kc, vc, kvd, B, T, H, G, hs,
                                           cfg.rope_n_elem, max_seq, r, stream), "lp_rope_kv_append")
-                chk(lib.lp_attn_decode(q, kc, vc, kvd, pos_ptr, att, ws, ws_bytes, B, T, H, G, hs, max_seq, scale, r, stream),
-                    "lp_attn_decode")
+                self._attention_rows(q, kc, vc, kvd, pos_ptr, att, ws, ws_bytes, B, T, max_seq, scale, stream)
             if cfg.parallel_residual:
                 # x + attn(n1) + mlp(n2), n2 = n1 when the norm is shared (model.py:169-171); both GEMVs read the old x
                 n2w, n2b = (L.n1_w, L.n1_b) if cfg.shared_attention_norm else (L.n2_w, L.n2_b)
@@ -280,6 +280,20 @@ class Engine:
         else:
             norm_linear(x, self.lnf_w, self.lnf_b, self.lm_head, _lib.LP_EPI_NONE, logits, xf, "lp_linear(lm_head)")
 
+    def _attention_rows(self, q, kc, vc, kvd, pos_ptr, att, ws, ws_bytes, B, T, max_seq, scale, stream) -> None:
+        """Attention of T query rows against the cache: the tensor-core causal kernel when the positions are consecutive
+        and do not wrap (`self._consecutive`, set by forward()), else the generic exact kernel."""
+        lib, cfg, r = self.lib, self.cfg, self.round
+        rc = -2
+        if T > 1 and self._consecutive:
+            rc = lib.lp_attn_prefill(q, kc, vc, kvd, pos_ptr, att, B, T, cfg.n_head, cfg.n_query_groups, cfg.head_size, max_seq, scale, r,
+                                     stream)
+            if rc != -2:
+                _lib.check(rc, "lp_attn_prefill")
+        if rc == -2:
+            _lib.check(lib.lp_attn_decode(q, kc, vc, kvd, pos_ptr, att, ws, ws_bytes, B, T, cfg.n_head, cfg.n_query_groups,
+                                          cfg.head_size, max_seq, scale, r, stream), "lp_attn_decode")
+
     def _run_tc(self, b: Dict[str, torch.Tensor], idx_ptr: int, idx64: int, pos_ptr: int, caches, B: int, T: int, stream: int,
                 last_only: bool = False) -> None:
         """T > 1: the same op sequence as `_run`, with every projection on the tcgen05 GEMM (lp_gemm_bf16_tc)."""
@@ -309,8 +323,7 @@ class Engine:
             gemm(t_n, L.qkv, _lib.LP_EPI_NONE, None, qkv)
             chk(lib.lp_rope_kv_append(qkv, _ptr(self.cos), _ptr(self.sin), pos_ptr, q, kc, vc, kvd, B, T, H, G, hs, cfg.rope_n_elem,
                                       max_seq, r, stream), "lp_rope_kv_append")
-            chk(lib.lp_attn_decode(q, kc, vc, kvd, pos_ptr, att, ws, ws_bytes, B, T, H, G, hs, max_seq, scale, r, stream),
-                "lp_attn_decode")
+            self._attention_rows(q, kc, vc, kvd, pos_ptr, att, ws, ws_bytes, B, T, max_seq, scale, stream)
             chk(lib.lp_split_bf16(att, t_att, rows, E, nt, -1, None, None, 0.0, 0, stream), "lp_split_bf16")
             if cfg.parallel_residual:
                 if not cfg.shared_attention_norm:
@@ -367,6 +380,10 @@ class Engine:
         idx = idx.contiguous()
         pos32 = pos.to(device=self.device, dtype=torch.int32).contiguous()
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._consecutive = False
+        if T > 1:  # one host read per prefill: are the positions p, p+1, ... without wrapping the cache?
+            ph = pos32.cpu()
+            self._consecutive = bool((ph[1:] - ph[:-1] == 1).all()) and int(ph[-1]) < max_seq
         if self.tc_eligible(B * T):
             self._run_tc(b, idx.data_ptr(), int(idx.dtype == torch.int64), pos32.data_ptr(), caches, B, T, stream, last_only)
         else:

@@ -477,3 +477,34 @@ def test_dequant_bf16(lib, fmt):
     _lib.check(lib.lp_dequant_bf16(ctypes.byref(rec), out.data_ptr(), stream()), "lp_dequant_bf16")
     torch.cuda.synchronize()
     torch.testing.assert_close(out.float().cpu(), want.float(), rtol=2 ** -7, atol=1e-8)
+
+
+@pytest.mark.parametrize("rnd", [0, 1])
+@pytest.mark.parametrize("B,T,H,G,hs,max_seq,p0", [(1, 16, 8, 8, 64, 64, 0), (2, 100, 32, 32, 128, 256, 0), (1, 300, 71, 1, 64, 512, 0),
+                                                   (1, 130, 64, 8, 128, 1024, 500), (2, 65, 8, 2, 64, 200, 7), (1, 2048, 4, 4, 128, 2048, 0)])
+def test_attention_prefill(lib, rnd, B, T, H, G, hs, max_seq, p0):
+    """lp_attn_prefill (causal FlashAttention-2 style tensor-core kernel over the bf16 cache) against masked SDPA in float64."""
+    qpk = H // G
+    q = f32(B * T, H * hs, seed=1)
+    if rnd:
+        q = bf16r(q)
+    pos = torch.arange(p0, p0 + T, dtype=torch.int32, device=DEV)
+    kc = torch.zeros(B, G, max_seq, hs, device=DEV, dtype=torch.bfloat16)
+    vc = torch.zeros_like(kc)
+    n_valid = p0 + T
+    kc[:, :, :n_valid] = f32(B, G, n_valid, hs, seed=2).bfloat16()
+    vc[:, :, :n_valid] = f32(B, G, n_valid, hs, seed=3).bfloat16()
+    out = torch.full((B * T, H * hs), float("nan"), device=DEV)
+    scale = 1.0 / math.sqrt(hs)
+    _lib.check(lib.lp_attn_prefill(q.data_ptr(), kc.data_ptr(), vc.data_ptr(), _lib.LP_BF16, pos.data_ptr(), out.data_ptr(), B, T, H, G, hs,
+                                   max_seq, scale, rnd, stream()), "lp_attn_prefill")
+    torch.cuda.synchronize()
+    qq = q.view(B, T, H, hs).transpose(1, 2).double()
+    kk = kc[:, :, :n_valid].double().repeat_interleave(qpk, dim=1)
+    vv = vc[:, :, :n_valid].double().repeat_interleave(qpk, dim=1)
+    mask = torch.arange(n_valid, device=DEV)[None, :] <= pos.long()[:, None]
+    want = F.scaled_dot_product_attention(qq, kk, vv, attn_mask=mask[None, None], scale=scale).transpose(1, 2).reshape(B * T, H * hs).float()
+    if rnd:  # P and the output are rounded to bf16, as in the reference's bf16 SDPA
+        torch.testing.assert_close(out, want, rtol=2 ** -6, atol=2e-2)
+    else:
+        torch.testing.assert_close(out, want, rtol=1e-4, atol=2e-5)
