@@ -237,6 +237,53 @@ def run_workload(workload, steps, warmup, device, rank=0, world=1, with_e2e=True
     return res
 
 
+def run_prefill(preset, T, device, reps=3):
+    """BASELINE configs[3]: prompt prefill through the public API (bf16-faithful mode: one bf16 term per activation, the
+    reference's bf16-true arithmetic), tensor-core roofline.  FLOPs = 2 T sum(out*in) (lm_head on the last row only, as
+    generate() consumes it) + causal attention L * 4 H hs T (T + 1) / 2."""
+    import torch
+
+    import lit_parrot_b200 as lp
+
+    cfg = lp.Config.from_name(preset)
+    torch.manual_seed(1234)
+    with torch.device(device):
+        prev = torch.get_default_dtype()
+        torch.set_default_dtype(torch.bfloat16)
+        try:
+            model = lp.GPT(cfg)
+        finally:
+            torch.set_default_dtype(prev)
+    model.apply(model._init_weights)
+    model.eval().set_precision("bf16")
+    max_seq = cfg.block_size
+    idx = torch.randint(0, cfg.vocab_size, (1, T), generator=torch.Generator().manual_seed(1)).to(device)
+    pos = torch.arange(T, device=device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    times = []
+    for i in range(reps + 1):
+        model.reset_cache()
+        model.kv_caches = model.build_kv_caches(idx, max_seq)
+        torch.cuda.synchronize(device)
+        e0.record()
+        model._forward_impl(idx, max_seq, pos, last_only=True, raw_logits=True)
+        e1.record()
+        torch.cuda.synchronize(device)
+        if i:
+            times.append(e0.elapsed_time(e1))
+    ms = min(times)
+    eng = model._get_engine(device)
+    lin = sum(m.N * m.K for L in eng.layers for m in (L.qkv, L.proj, L.fc, L.mlp_proj))
+    flops = 2.0 * T * lin + 2.0 * cfg.padded_vocab_size * cfg.n_embd + cfg.n_layer * 4.0 * cfg.n_head * cfg.head_size * T * (T + 1) / 2
+    pk = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else {}
+    peak = float(pk.get("bf16_tflops_sustained", 1400.0))
+    tf = flops / ms / 1e9
+    del model
+    torch.cuda.empty_cache()
+    return {"workload": f"{preset} bf16 prefill T={T} (block_size {cfg.block_size}), batch 1", "ms": ms, "prefill_tok_s": T / ms * 1e3,
+            "tflops": tf, "tensor_frac_of_sustained_peak": tf / peak, "flops": flops}
+
+
 def time_dominant_kernel(eng, cfg, B, device, iters=64):
     import torch
 
@@ -365,6 +412,10 @@ def main():
                     extras.append(run_workload(w, args.steps, args.warmup, device, with_e2e=False))
                 except Exception as e:  # an extra must never cost the headline line
                     extras.append({"workload": w, "error": repr(e)[:200]})
+        try:
+            extras.append(run_prefill("falcon-7b", 1792, device))  # 1792 + 256 decode tokens = block_size 2048
+        except Exception as e:
+            extras.append({"workload": "falcon-7b prefill", "error": repr(e)[:200]})
     if rank == 0:
         peak, peak_src = peaks()
         k = res["kernel"]
@@ -377,7 +428,8 @@ def main():
                                              "bytes": res["bytes_per_step"], "launches": res["launches_per_step"]}})
         if extras:
             line["also"] = [{kk: e[kk] for kk in e if kk in ("workload", "tok_s", "ms_per_step", "step_gbs", "launches_per_step",
-                                                              "bytes_per_step", "kernel", "error")} for e in extras]
+                                                              "bytes_per_step", "kernel", "error", "ms", "prefill_tok_s", "tflops",
+                                                              "tensor_frac_of_sustained_peak")} for e in extras]
             for e in line["also"]:
                 if "step_gbs" in e:
                     e["step_frac"] = e["step_gbs"] / peak

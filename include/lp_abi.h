@@ -135,7 +135,7 @@ int lp_norm_linear(int norm_kind, const float* norm_w, const float* norm_b, floa
  * lp_gemm_bf16_tc: out = epilogue(x . W^T + bias), W bf16 [N, K] row-major (nn.Linear.weight; other formats are first
  * expanded with lp_dequant_bf16), TMA-fed tcgen05.mma with the accumulator in tensor memory.  The result is written as
  * fp32 [M, Nout] (out_f32) and / or as `out_terms` bf16 split arrays [out_terms][M, Nout] (out_bf16) — the next GEMM's
- * operand.  Nout = N (N / 2 for LP_EPI_SWIGLU).  Requires N % 128 == 0 and K % 8 == 0, else LP_ERR_UNSUPPORTED.
+ * operand.  Nout = N (N / 2 for LP_EPI_SWIGLU).  Requires N % 8 == 0 and K % 8 == 0, else LP_ERR_UNSUPPORTED.
  * replaces nn.Linear.forward on T > 1 tokens (model.py:111, 205, 252, 285-301). */
 int lp_split_bf16(const float* x, void* out_bf16, int rows, int K, int nterms, int norm_kind, const float* norm_w,
                   const float* norm_b, float eps, int round_bf16, void* stream);

@@ -216,8 +216,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             for (int j = 0; j < 32; j += 4)
               if (j < ncols) *reinterpret_cast<float4*>(dst + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
           } else {
-            for (int j = 0; j < ncols; ++j)
-              if (ocol + j < nout) dst[j] = y[j];
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols && ocol + j < nout) dst[j] = y[j];
           }
         }
         if (p.out_bf) {
@@ -357,7 +358,7 @@ static int tc_launch(const CUtensorMap& mx, const CUtensorMap& mw, const TcParam
   if (nstages > 8) nstages = 8;
   if (nstages < 2) return LP_ERR_UNSUPPORTED;
   const size_t smem = (size_t)nstages * stage_bytes + 1024;
-  dim3 grid((p.M + TC_BM - 1) / TC_BM, p.N / BN);
+  dim3 grid((p.M + TC_BM - 1) / TC_BM, (p.N + BN - 1) / BN);
   return launch(kern, grid, dim3(TC_THREADS), smem, stream, mx, mw, p, nstages);
 }
 
@@ -380,9 +381,9 @@ int lp_gemm_bf16_tc(const void* x_terms, int nterms, int M, const void* w_bf16, 
   if (out_bf16 && (out_terms < 1 || out_terms > 3)) return LP_ERR_INVALID_ARG;
   if (epilogue < LP_EPI_NONE || epilogue > LP_EPI_RESIDUAL) return LP_ERR_INVALID_ARG;
   if (epilogue == LP_EPI_RESIDUAL && !residual) return LP_ERR_INVALID_ARG;
-  if (K % 8 || N % 128) return LP_ERR_UNSUPPORTED;  // 16-byte global strides; whole 128-column tiles
+  if (K % 8 || N % 8) return LP_ERR_UNSUPPORTED;  // 16-byte global strides (ragged N / K tiles are zero-filled by TMA)
   if ((reinterpret_cast<uintptr_t>(x_terms) & 15) || (reinterpret_cast<uintptr_t>(w_bf16) & 15)) return LP_ERR_UNSUPPORTED;
-  const int BN = (N % 256 == 0 && nterms <= 2) ? 256 : 128;
+  const int BN = (N % 256 == 0 && nterms <= 2) ? 256 : 128;  // a ragged last tile wastes less at 128
   const CUtensorMap* mx = lp::tc_cached_map(x_terms, nterms * M, K, lp::TC_BM);
   const CUtensorMap* mw = lp::tc_cached_map(w_bf16, N, K, BN);
   if (!mx || !mw) return LP_ERR_UNSUPPORTED;

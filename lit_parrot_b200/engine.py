@@ -169,7 +169,7 @@ class Engine:
         if rows < 9 or getattr(self, "disable_tc", False):
             return False
         mats = [self.lm_head] + [m for L in self.layers for m in (L.qkv, L.proj, L.fc, L.mlp_proj)]
-        if any(m.N % 128 or m.K % 8 for m in mats if m is not self.lm_head):
+        if any(m.N % 8 or m.K % 8 for m in mats):
             return False
         if all(m.fmt == _lib.LP_W_BF16 for m in mats):
             return True
@@ -346,7 +346,7 @@ class Engine:
                 src = x + ((bi + 1) * T - 1) * E * 4
                 chk(lib.lp_norm(nk, src, _ptr(self.lnf_w), _ptr(self.lnf_b), cfg.norm_eps, xf + bi * E * 4, 1, E, r, stream), "lp_norm")
             chk(lib.lp_linear(xf, B, self.lm_head.ref, _lib.LP_EPI_NONE, None, logits, r, stream), "lp_linear(lm_head)")
-        elif self.lm_head.N % 128 == 0:
+        elif True:
             norm_split(x, self.lnf_w, self.lnf_b, t_n)
             gemm(t_n, self.lm_head, _lib.LP_EPI_NONE, None, logits)
         else:

@@ -411,7 +411,8 @@ def test_norm_linear_fused(lib, kind, fmt, M, N, K):
 
 
 @pytest.mark.parametrize("nterms", [1, 2, 3])
-@pytest.mark.parametrize("M,N,K", [(16, 128, 64), (128, 256, 512), (200, 384, 4096), (333, 4608, 4544), (2048, 512, 1024), (9, 1280, 8192)])
+@pytest.mark.parametrize("M,N,K", [(16, 128, 64), (128, 256, 512), (200, 384, 4096), (333, 4608, 4544), (2048, 512, 1024), (9, 1280, 8192),
+                                   (150, 4544, 1024), (70, 200, 136)])
 def test_gemm_bf16_tc(lib, nterms, M, N, K):
     """lp_split_bf16 + lp_gemm_bf16_tc (TMA + tcgen05.mma, accumulator in tensor memory) against float64 F.linear.
     nterms = 1: bf16 activations (the reference's bf16-true matmul inputs); 2 / 3: fp32-activation accuracy."""

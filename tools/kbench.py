@@ -112,9 +112,34 @@ def bench_attn():
             print(f"{name:28s} {'bf16':5s} {us:8.2f} {nbytes / us / 1e3:8.0f}   (fused rope+append+attention+merge)")
 
 
+def bench_gemm():
+    """lp_gemm_bf16_tc alone (prefill projections): TFLOP/s against the measured cuBLAS bf16 peak."""
+    import json
+    pk = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+    peak = pk.get("bf16_tflops", 1672.9)
+    print(f"{'shape (M,N,K)':28s} {'terms':>5s} {'us':>9s} {'TFLOP/s':>8s} {'%burst':>7s}   torch.matmul us / TF")
+    for M, N, K in [(2048, 4608, 4544), (2048, 18176, 4544), (2048, 4544, 18176), (2048, 12288, 4096), (2048, 22016, 4096), (2048, 4096, 11008),
+                    (4096, 8192, 8192), (32, 16384, 4096)]:
+        x = torch.randn(M, K, device=DEV)
+        w = [torch.randn(N, K, device=DEV, dtype=torch.bfloat16) * 0.02 for _ in range(3)]
+        out = torch.empty(M, N, device=DEV)
+        for nt in (1, 2):
+            terms = torch.empty(nt, M, K, dtype=torch.bfloat16, device=DEV)
+            _lib.check(lib.lp_split_bf16(x.data_ptr(), terms.data_ptr(), M, K, nt, -1, None, None, 0.0, 0, stream()))
+            fn = lambda i: lib.lp_gemm_bf16_tc(terms.data_ptr(), nt, M, w[i % 3].data_ptr(), N, K, None, 0, None, out.data_ptr(), None, 0, 0, stream())  # noqa: E731
+            assert fn(0) == 0
+            us = timeit(fn, iters=20, warm=3)
+            tf = 2.0 * M * N * K / us / 1e6
+            xb = x.bfloat16()
+            ust = timeit(lambda i: torch.matmul(xb, w[i % 3].t()), iters=20, warm=3)
+            print(f"{str((M, N, K)):28s} {nt:5d} {us:9.1f} {tf:8.1f} {100 * tf / peak:7.1f}   {ust:8.1f} / {2.0 * M * N * K / ust / 1e6:6.1f}")
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["linear", "attn"]
     if "linear" in what:
         bench_linear()
+    if "gemm" in what:
+        bench_gemm()
     if "attn" in what:
         bench_attn()
