@@ -37,6 +37,8 @@ WORKLOADS = {
     "llama2-7b-bf16-b1": ("Llama-2-7b-hf", None, 0, 1, 2048),
     "falcon-7b-bf16-b1": ("falcon-7b", None, 0, 1, 2048),
     "pythia-70m-bf16-b1": ("pythia-70m", None, 0, 1, 2048),
+    # tensor parallel over all launched ranks (BASELINE configs[4]); at 1 GPU it is the unsharded 70B model (137 GB of 180)
+    "llama2-70b-bf16-b1-tp": ("Llama-2-70b-hf", None, 0, 1, 2048),
 }
 DEFAULT = "stablelm-3b-bf16-b1"
 EXTRAS = ["llama2-7b-int4g128-b1", "stablelm-3b-bf16-b32"]
@@ -125,11 +127,44 @@ def build_model(workload: str, device):
     return q.eval(), cfg, B, ctx
 
 
+def build_tp_model(preset, device, rank, world):
+    """Llama-2-70b (or any GQA preset) sharded over `world` GPUs: every rank materialises ITS shard of the same random
+    model (per-tensor seeds, so all ranks agree on the global weights without ever holding them all)."""
+    import torch
+    import torch.distributed as dist
+
+    import lit_parrot_b200 as lp
+    from lit_parrot_b200.tp import TPContext
+
+    cfg = lp.Config.from_name(preset).with_tp(world, rank)
+    with torch.device(device):
+        prev = torch.get_default_dtype()
+        torch.set_default_dtype(torch.bfloat16)
+        try:
+            model = lp.GPT(cfg)
+        finally:
+            torch.set_default_dtype(prev)
+    gen = torch.Generator(device=device)
+    for i, (name, p) in enumerate(model.named_parameters()):
+        if p.dim() == 2:
+            gen.manual_seed(1234 + i)  # same seed per tensor on every rank; shards differ only through their rank offset
+            gen.manual_seed(1234 + i * 64 + (rank if (".attn." in name or ".mlp." in name) else 0))
+            p.data.normal_(0.0, 0.02, generator=gen)
+        elif name.endswith("weight"):
+            p.data.fill_(1.0)
+        else:
+            p.data.zero_()
+    model.eval()
+    if world > 1:
+        model.tp_context = TPContext(dist.group.WORLD, device, max_rows=8, n_embd=cfg.n_embd)
+    return model, cfg
+
+
 def algorithmic_bytes_per_step(eng, cfg, B, kv_len_avg, kv_elem_bytes):
     """weights of every linear at stored width (+scales/zeros/absmax) + one embedding row per sequence
     + compact KV read B*2*L*G*hs*bytes*(pos+1) + KV write."""
     w = eng.weight_bytes_per_token() + (B - 1) * cfg.n_embd * eng.wte.element_size()
-    kv_row = 2 * cfg.n_layer * cfg.n_query_groups * cfg.head_size * kv_elem_bytes
+    kv_row = 2 * cfg.n_layer * cfg.n_query_groups_local * cfg.head_size * kv_elem_bytes
     return w, B * kv_row * kv_len_avg + B * kv_row
 
 
@@ -140,7 +175,12 @@ def run_workload(workload, steps, warmup, device, rank=0, world=1, with_e2e=True
     import lit_parrot_b200 as lp
     from lit_parrot_b200 import _lib
 
-    model, cfg, B, ctx = build_model(workload, device)
+    tp = workload.endswith("-tp")
+    if tp:
+        preset, _q, _t, B, ctx = WORKLOADS[workload]
+        model, cfg = build_tp_model(preset, device, rank, world)
+    else:
+        model, cfg, B, ctx = build_model(workload, device)
     lib = _lib.init(device.index)
     V = cfg.padded_vocab_size
     start = ctx - steps - warmup - 1
@@ -189,7 +229,8 @@ def run_workload(workload, steps, warmup, device, rank=0, world=1, with_e2e=True
         ms = float(tms)
     kv_b = model.kv_caches[0][0].element_size()
     wbytes, kvbytes = algorithmic_bytes_per_step(eng, cfg, B, start + warmup + steps / 2 + 1, kv_b)
-    res = {"workload": workload, "ms_per_step": ms / steps, "tok_s": world * B * steps / (ms / 1e3),
+    replicas = 1 if tp else world  # tensor parallel: ONE model over all ranks (strong scaling); else independent replicas
+    res = {"workload": workload, "ms_per_step": ms / steps, "tok_s": replicas * B * steps / (ms / 1e3),
            "launches_per_step": int(launches_per_step), "bytes_per_step": {"weights": int(wbytes), "kv": int(kvbytes)},
            "step_gbs": (wbytes + kvbytes) / (ms / steps) / 1e6, "clocks": clk.summary(), "B": B, "ctx": ctx}
 
@@ -226,7 +267,7 @@ def run_workload(workload, steps, warmup, device, rank=0, world=1, with_e2e=True
             tdt = torch.tensor([dt], device=device)
             dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
             dt = float(tdt)
-        res["e2e"] = {"value": world * B * steps / dt, "unit": "tok/s", "h2d_bytes_per_step": int(B * 8 + 8),
+        res["e2e"] = {"value": replicas * B * steps / dt, "unit": "tok/s", "h2d_bytes_per_step": int(B * 8 + 8),
                       "d2h_bytes_per_step": int(B * 4)}
 
     # ---- dominant kernel alone: lp_linear on the MLP up-projection, rotating over the layers' weights (>> L2) ------
@@ -322,6 +363,11 @@ def cpu_oracle_decode(workload, max_steps, warmup, budget_s=75.0):
 
     preset, quant, tile, B, ctx = WORKLOADS[workload]
     cfg = lp.Config.from_name(preset)
+    full_layers = cfg.n_layer
+    if cfg.n_layer * cfg.n_embd * cfg.n_embd * 12 * 4 > 100e9:
+        # Llama-2-70b in fp32 does not fit the host (276 GB): time a 4-layer slice of it and scale the per-token time by
+        # n_layer / 4 (lm_head + embedding are counted once); stated in `sample`
+        cfg = lp.Config.from_name(preset, n_layer=4)
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     t_build = time.perf_counter()
@@ -355,9 +401,18 @@ def cpu_oracle_decode(workload, max_steps, warmup, budget_s=75.0):
             tok = m(tok, 64, pos)[:, -1].argmax(-1, keepdim=True)
             n += 1
         dt = time.perf_counter() - t0
+        if cfg.n_layer != full_layers and n:
+            t_head, h0 = 0.0, time.perf_counter()  # lm_head share: time it alone on the same shapes
+            for _ in range(3):
+                torch.nn.functional.linear(torch.randn(B, cfg.n_embd), m.sd["lm_head.weight"])
+            t_head = (time.perf_counter() - h0) / 3
+            per_layer = max(dt / n - t_head, 0.0) / cfg.n_layer
+            dt = n * (t_head + per_layer * full_layers)
     desc = (f"{preset} fp32 weights on CPU ({'int4 g128 dequant+F.linear per call, ' if quant else ''}oracle port of the reference, "
             f"torch {torch.__version__}), batch {B}, 16-token prefill then {n} greedy decode steps at context 17-{17 + n} "
-            f"(not 2k: bounded sample), {threads} threads; weight build {t_build:.0f}s not timed")
+            f"(not 2k: bounded sample), {threads} threads; weight build {t_build:.0f}s not timed"
+            + (f"; {cfg.n_layer}-layer slice timed and scaled to {full_layers} layers (fp32 70B does not fit host RAM)"
+               if cfg.n_layer != full_layers else ""))
     return B * n / dt, n, threads, desc
 
 
@@ -367,22 +422,31 @@ def main():
     ap.add_argument("--steps", type=int, default=128)
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help=f"default: {DEFAULT} at 1 GPU; llama2-70b-bf16-b1-tp (tensor parallel over all ranks) at N > 1")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload is None:
+        # N = 1: BASELINE configs[1].  N > 1: configs[4], the one configuration of the path that shards —
+        # Llama-2-70b tensor parallel over the N ranks, strong scaling (the same single sequence on more GPUs).
+        args.workload = DEFAULT if world == 1 else "llama2-70b-bf16-b1-tp"
+    is_tp = args.workload.endswith("-tp")
     preset, quant, tile, B, ctx = WORKLOADS[args.workload]
     base = {"metric": "decode_tokens_per_second", "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong" if is_tp else "weak", "vs_baseline": None,
             "dtype": "bf16" if quant is None else f"bf16 activations-in-fp32 / {quant} weights", "data": "synthetic",
             "config": {"workload": f"{preset} {'bf16' if quant is None else quant} decode, batch {B}, context {ctx} "
                                    f"(positions {ctx - args.steps - args.warmup - 1}..{ctx - 1})",
                        "weights": "random init N(0,0.02) (_init_weights), seed 1234", "kv_cache": "synthetic N(0,1) prefix, bf16, compact (B,G,ctx,hs)",
                        "l2": "inputs larger than L2 (weights streamed per step >> 126 MB)",
-                       "parallelism": "1 GPU" if args.gpus == 1 else f"{args.gpus} independent replicas (no collective)"}}
+                       "parallelism": ("1 GPU" if world == 1 else
+                                       (f"tensor parallel tp={world}: weights sharded by query group / MLP column, one-shot NVLink all-reduce "
+                                        "fused with the residual add (2 exchanges per layer)" if is_tp else
+                                        f"{world} independent replicas (no collective)"))}}
 
     if args.impl == "reference":
         if rank != 0:

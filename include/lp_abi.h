@@ -180,6 +180,16 @@ int lp_attn_decode_fused(const float* qkv, const float* cos, const float* sin, c
 int lp_attn_prefill(const float* q, const void* k_cache, const void* v_cache, int kv_dtype, const int32_t* pos, float* out, int B,
                     int T, int H, int G, int hs, int max_seq, float scale, int round_bf16, void* stream);
 
+/* Tensor-parallel exchange fused with the residual add: out[n] = residual[n] + sum over ranks of partial_r[n], n fp32.
+ * `buf_ptrs_dev` / `pad_ptrs_dev`: device arrays of `tp` peer-mapped addresses (symmetric buffer and signal pad of every
+ * rank, e.g. torch.distributed._symmetric_memory: buffer_ptrs_dev / signal_pad_ptrs_dev).  This rank's partial must
+ * already be at its symmetric buffer + buf_offset_bytes (the producing GEMV writes it there); callers alternate between
+ * two slots (buf_offset_bytes, pad_base) so that a slot is not rewritten while a slower peer reads it.  `state`: two
+ * zero-initialised uint32 per slot (epoch, ticket), owned by this library afterwards.  No reference counterpart: the
+ * reference's multi-GPU path is FSDP (generate/base.py:187-205); the oracle is the single-device model. */
+int lp_tp_allreduce_residual(const void* buf_ptrs_dev, const void* pad_ptrs_dev, int rank, int tp, size_t buf_offset_bytes,
+                             int pad_base, void* state, int n, const float* residual, float* out, int round_bf16, void* stream);
+
 /* replaces the sampling tail of generate() (generate/base.py:136-153): logits/temperature, top-k threshold
  * (ties with the k-th value survive), softmax, one multinomial draw (exponential race, Philox keyed by
  * (seed, *step)).  top_k == 1 is lowest-index arg-max.  logits fp32 [rows, V] -> token_out int32 [rows].

@@ -71,6 +71,46 @@ class Config:
         """Output rows of the fused QKV projection (model.py:186)."""
         return (self.n_head + 2 * self.n_query_groups) * self.head_size
 
+    # ---- tensor-parallel view (SURVEY §8e; not part of the reference's Config: plain attributes, not dataclass fields) ----
+    @property
+    def tp_size(self) -> int:
+        return getattr(self, "_tp_size", 1)
+
+    @property
+    def tp_rank(self) -> int:
+        return getattr(self, "_tp_rank", 0)
+
+    def with_tp(self, tp_size: int, tp_rank: int) -> "Config":
+        """A copy of this config whose `*_local` quantities describe rank `tp_rank`'s shard: query groups (with their q
+        heads) and MLP columns are split evenly; everything else is replicated."""
+        import copy
+
+        if tp_size < 1 or not 0 <= tp_rank < tp_size:
+            raise ValueError(f"bad tensor-parallel coordinates {tp_rank}/{tp_size}")
+        if self.n_query_groups % tp_size or self.intermediate_size % tp_size:
+            raise ValueError(f"n_query_groups={self.n_query_groups} and intermediate_size={self.intermediate_size} must be "
+                             f"divisible by the tensor-parallel size {tp_size} (query groups are the sharding unit)")
+        c = copy.copy(self)
+        object.__setattr__(c, "_tp_size", tp_size)
+        object.__setattr__(c, "_tp_rank", tp_rank)
+        return c
+
+    @property
+    def n_head_local(self) -> int:
+        return self.n_head // self.tp_size
+
+    @property
+    def n_query_groups_local(self) -> int:
+        return self.n_query_groups // self.tp_size
+
+    @property
+    def intermediate_size_local(self) -> int:
+        return self.intermediate_size // self.tp_size
+
+    @property
+    def qkv_rows_local(self) -> int:
+        return self.qkv_rows // self.tp_size
+
     @classmethod
     def from_name(cls, name: str, **kwargs: Any) -> "Config":
         conf = dict(name_to_config[name])

@@ -95,6 +95,9 @@ class Engine:
         self.use_graph = bool(model.use_cuda_graph)
         self.round = 1 if model.precision == "bf16" else 0
         self.cfg = cfg = model.config
+        self.tp = model.tp_context if cfg.tp_size > 1 else None
+        if cfg.tp_size > 1 and self.tp is None:
+            raise RuntimeError("config.tp_size > 1: set model.tp_context = lit_parrot_b200.tp.TPContext(...) before the first forward")
         self.lib = _lib.init(device.index if device.index is not None else torch.cuda.current_device())
         self.param_dtype = model.transformer.wte.weight.dtype
         if self.param_dtype not in _FMT_OF_DTYPE:
@@ -150,7 +153,7 @@ class Engine:
         key = (B, T)
         if self._scratch is None or self._scratch[0] != key:
             cfg = self.cfg
-            store = torch.empty((cfg.n_layer, 2, B, cfg.n_query_groups, T, cfg.head_size), device=self.device,
+            store = torch.empty((cfg.n_layer, 2, B, cfg.n_query_groups_local, T, cfg.head_size), device=self.device,
                                 dtype=self.param_dtype)
             self._scratch = (key, [(store[l, 0], store[l, 1]) for l in range(cfg.n_layer)])
         return self._scratch[1]
@@ -166,7 +169,7 @@ class Engine:
     def tc_eligible(self, rows: int) -> bool:
         """T > 1 goes through lp_gemm_bf16_tc when every linear is bf16 (fp32-activation accuracy via bf16 term splitting) or,
         in bf16-faithful mode, quantised (weights expanded to bf16 like the reference's bf16 dequantisation)."""
-        if rows < 9 or getattr(self, "disable_tc", False):
+        if rows < 9 or getattr(self, "disable_tc", False) or self.tp is not None:
             return False
         mats = [self.lm_head] + [m for L in self.layers for m in (L.qkv, L.proj, L.fc, L.mlp_proj)]
         if any(m.N % 8 or m.K % 8 for m in mats):
@@ -192,16 +195,17 @@ class Engine:
         if b is None:
             cfg, dev = self.cfg, self.device
             f = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)  # noqa: E731
-            E, I, V = cfg.n_embd, cfg.intermediate_size, cfg.padded_vocab_size
-            ws_bytes = max(self.lib.lp_attn_workspace_bytes(B, T, cfg.n_head, cfg.head_size, max_seq),
-                           self.lib.lp_attn_fused_workspace_bytes(B, cfg.n_head, cfg.n_query_groups, cfg.head_size, max_seq))
-            b = dict(x=f(rows, E), n1=f(rows, E), n2=f(rows, E), qkv=f(rows, cfg.qkv_rows), q=f(rows, E), att=f(rows, E),
-                     xmid=f(rows, E), u=f(rows, I), xf=f(rows, E), logits=f(rows, V),
+            E, I, V = cfg.n_embd, cfg.intermediate_size_local, cfg.padded_vocab_size
+            Hl, Gl = cfg.n_head_local, cfg.n_query_groups_local
+            ws_bytes = max(self.lib.lp_attn_workspace_bytes(B, T, Hl, cfg.head_size, max_seq),
+                           self.lib.lp_attn_fused_workspace_bytes(B, Hl, Gl, cfg.head_size, max_seq))
+            b = dict(x=f(rows, E), n1=f(rows, E), n2=f(rows, E), qkv=f(rows, cfg.qkv_rows_local), q=f(rows, Hl * cfg.head_size),
+                     att=f(rows, Hl * cfg.head_size), xmid=f(rows, E), u=f(rows, I), xf=f(rows, E), logits=f(rows, V),
                      ws=torch.zeros(max(ws_bytes, 16), device=dev, dtype=torch.uint8))  # zeroed: split-merge tickets
             if self.tc_eligible(rows):
                 # bf16 split terms of the GEMM operands: [3][rows, width]
                 bf = lambda w: torch.empty((3, rows, w), device=dev, dtype=torch.bfloat16)  # noqa: E731
-                b.update(t_n=bf(E), t_att=bf(E), t_u=bf(I))
+                b.update(t_n=bf(E), t_att=bf(Hl * cfg.head_size), t_u=bf(I))
             if len(self._bufs) > 8:
                 self._bufs.clear()
             self._bufs[key] = b
@@ -212,10 +216,27 @@ class Engine:
              caches, B: int, T: int, stream: int, last_only: bool = False) -> None:
         lib, cfg, r, chk = self.lib, self.cfg, self.round, _lib.check
         rows = B * T
-        E, H, G, hs = cfg.n_embd, cfg.n_head, cfg.n_query_groups, cfg.head_size
+        E, H, G, hs = cfg.n_embd, cfg.n_head_local, cfg.n_query_groups_local, cfg.head_size
         max_seq = caches[0][0].size(2)
         kvd = _KV_OF_DTYPE[caches[0][0].dtype]
         x, n1, n2, qkv, q, att, xmid, u = (b[k].data_ptr() for k in ("x", "n1", "n2", "qkv", "q", "att", "xmid", "u"))
+        tp = self.tp
+        if tp is not None:
+            if rows * E > tp.slot_floats:
+                raise RuntimeError(f"tensor-parallel exchange buffer holds {tp.slot_floats // E} rows; got {rows}")
+            tp.begin_forward()
+
+        def row_parallel(src, W, res, dst, what):
+            """dst = res + src . W^T.  Tensor parallel: W is a column shard, so the product is a partial sum: it goes to this
+            rank's slot of the symmetric buffer and lp_tp_allreduce_residual adds all ranks' partials and the residual."""
+            mark()
+            if tp is None:
+                chk(lib.lp_linear(src, rows, W.ref, _lib.LP_EPI_RESIDUAL, res, dst, r, stream), what)
+                return
+            slot, part = tp.next_slot()
+            chk(lib.lp_linear(src, rows, W.ref, _lib.LP_EPI_NONE, None, part, 0, stream), what)
+            chk(lib.lp_tp_allreduce_residual(tp.buf_ptrs, tp.pad_ptrs, tp.rank, tp.size, slot * tp.slot_floats * 4, slot * tp.size,
+                                             tp.state[slot].data_ptr(), rows * E, res, dst, r, stream), "lp_tp_allreduce_residual")
         ws, ws_bytes = b["ws"].data_ptr(), b["ws"].numel()
         scale = 1.0 / math.sqrt(hs)
         wte_dt = _KV_OF_DTYPE[self.wte.dtype]
@@ -254,20 +275,20 @@ class Engine:
                 # x + attn(n1) + mlp(n2), n2 = n1 when the norm is shared (model.py:169-171); both GEMVs read the old x
                 n2w, n2b = (L.n1_w, L.n1_b) if cfg.shared_attention_norm else (L.n2_w, L.n2_b)
                 norm_linear(x, n2w, n2b, L.fc, self.act, u, n2, "lp_linear(fc)")
-                mark()
-                chk(lib.lp_linear(att, rows, L.proj.ref, _lib.LP_EPI_RESIDUAL, x, xmid, r, stream), "lp_linear(proj)")
-                mark()
-                chk(lib.lp_linear(u, rows, L.mlp_proj.ref, _lib.LP_EPI_RESIDUAL, xmid, x, r, stream), "lp_linear(mlp.proj)")
+                row_parallel(att, L.proj, x, xmid, "lp_linear(proj)")
+                row_parallel(u, L.mlp_proj, xmid, x, "lp_linear(mlp.proj)")
             else:
                 if cfg.shared_attention_norm:
                     raise NotImplementedError("No checkpoint amongst the ones we support uses this configuration"
                                               " (non-parallel residual and shared attention norm).")
-                mark()
-                chk(lib.lp_linear(att, rows, L.proj.ref, _lib.LP_EPI_RESIDUAL, x, x, r, stream), "lp_linear(proj)")
+                row_parallel(att, L.proj, x, x, "lp_linear(proj)")
                 norm_linear(x, L.n2_w, L.n2_b, L.fc, self.act, u, n2, "lp_linear(fc)")
-                mark()
-                chk(lib.lp_linear(u, rows, L.mlp_proj.ref, _lib.LP_EPI_RESIDUAL, x, x, r, stream), "lp_linear(mlp.proj)")
+                row_parallel(u, L.mlp_proj, x, x, "lp_linear(mlp.proj)")
         xf, logits = b["xf"].data_ptr(), b["logits"].data_ptr()
+        if tp is not None and tp.count % 2:  # keep the slot sequence of a (replayed) forward even: see TPContext
+            slot, part = tp.next_slot()
+            chk(lib.lp_tp_allreduce_residual(tp.buf_ptrs, tp.pad_ptrs, tp.rank, tp.size, slot * tp.slot_floats * 4, slot * tp.size,
+                                             tp.state[slot].data_ptr(), 4, None, b["xmid"].data_ptr(), 0, stream), "lp_tp_allreduce_residual")
         if trace is not None:
             lib.lp_debug_stream_trace(None)
         if last_only and T > 1:
@@ -286,12 +307,12 @@ class Engine:
         lib, cfg, r = self.lib, self.cfg, self.round
         rc = -2
         if T > 1 and self._consecutive:
-            rc = lib.lp_attn_prefill(q, kc, vc, kvd, pos_ptr, att, B, T, cfg.n_head, cfg.n_query_groups, cfg.head_size, max_seq, scale, r,
-                                     stream)
+            rc = lib.lp_attn_prefill(q, kc, vc, kvd, pos_ptr, att, B, T, cfg.n_head_local, cfg.n_query_groups_local, cfg.head_size,
+                                     max_seq, scale, r, stream)
             if rc != -2:
                 _lib.check(rc, "lp_attn_prefill")
         if rc == -2:
-            _lib.check(lib.lp_attn_decode(q, kc, vc, kvd, pos_ptr, att, ws, ws_bytes, B, T, cfg.n_head, cfg.n_query_groups,
+            _lib.check(lib.lp_attn_decode(q, kc, vc, kvd, pos_ptr, att, ws, ws_bytes, B, T, cfg.n_head_local, cfg.n_query_groups_local,
                                           cfg.head_size, max_seq, scale, r, stream), "lp_attn_decode")
 
     def _run_tc(self, b: Dict[str, torch.Tensor], idx_ptr: int, idx64: int, pos_ptr: int, caches, B: int, T: int, stream: int,
@@ -357,8 +378,8 @@ class Engine:
     def _check_caches(self, caches, B: int) -> None:
         k = caches[0][0]
         cfg = self.cfg
-        if k.dim() != 4 or k.size(0) != B or k.size(1) != cfg.n_query_groups or k.size(3) != cfg.head_size:
-            raise RuntimeError(f"kv cache shape {tuple(k.shape)} does not match (B={B}, G={cfg.n_query_groups}, max_seq, "
+        if k.dim() != 4 or k.size(0) != B or k.size(1) != cfg.n_query_groups_local or k.size(3) != cfg.head_size:
+            raise RuntimeError(f"kv cache shape {tuple(k.shape)} does not match (B={B}, G={cfg.n_query_groups_local}, max_seq, "
                                f"hs={cfg.head_size}); call model.reset_cache() when the batch size changes")
         if k.dtype not in _KV_OF_DTYPE or not k.is_contiguous():
             raise RuntimeError("kv cache must be a contiguous float32 / bfloat16 tensor")

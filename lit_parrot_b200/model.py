@@ -50,8 +50,9 @@ class CausalSelfAttention(nn.Module):
     def __init__(self, config: Config) -> None:
         super().__init__()
         # `nn.Linear` is looked up at call time so that the `quantization()` plug-in switch applies (utils.py)
-        self.attn = nn.Linear(config.n_embd, config.qkv_rows, bias=config.bias)
-        self.proj = nn.Linear(config.n_embd, config.n_embd, bias=config.bias)
+        # tensor parallel (config.with_tp): this rank's query groups / their heads only; tp_size == 1 is the reference layout
+        self.attn = nn.Linear(config.n_embd, config.qkv_rows_local, bias=config.bias)
+        self.proj = nn.Linear(config.n_head_local * config.head_size, config.n_embd, bias=config.bias)
         self.config = config
 
     def forward(self, *a, **k):  # pragma: no cover
@@ -61,8 +62,8 @@ class CausalSelfAttention(nn.Module):
 class GptNeoxMLP(nn.Module):
     def __init__(self, config: Config) -> None:
         super().__init__()
-        self.fc = nn.Linear(config.n_embd, config.intermediate_size, bias=config.bias)
-        self.proj = nn.Linear(config.intermediate_size, config.n_embd, bias=config.bias)
+        self.fc = nn.Linear(config.n_embd, config.intermediate_size_local, bias=config.bias)
+        self.proj = nn.Linear(config.intermediate_size_local, config.n_embd, bias=config.bias)
 
     def forward(self, *a, **k):  # pragma: no cover
         raise NotImplementedError(_DRIVEN)
@@ -71,9 +72,9 @@ class GptNeoxMLP(nn.Module):
 class LLaMAMLP(nn.Module):
     def __init__(self, config: Config) -> None:
         super().__init__()
-        self.fc_1 = nn.Linear(config.n_embd, config.intermediate_size, bias=config.bias)
-        self.fc_2 = nn.Linear(config.n_embd, config.intermediate_size, bias=config.bias)
-        self.proj = nn.Linear(config.intermediate_size, config.n_embd, bias=config.bias)
+        self.fc_1 = nn.Linear(config.n_embd, config.intermediate_size_local, bias=config.bias)
+        self.fc_2 = nn.Linear(config.n_embd, config.intermediate_size_local, bias=config.bias)
+        self.proj = nn.Linear(config.intermediate_size_local, config.n_embd, bias=config.bias)
 
     def forward(self, *a, **k):  # pragma: no cover
         raise NotImplementedError(_DRIVEN)
@@ -126,6 +127,7 @@ class GPT(nn.Module):
         self.precision = "fp32"          # "fp32": fp32 activations; "bf16": round where the reference's bf16-true rounds
         self.kv_cache_dtype: Optional[torch.dtype] = None  # default: parameter dtype (reference: model.py:236)
         self.use_cuda_graph = True
+        self.tp_context = None           # lit_parrot_b200.tp.TPContext when config.tp_size > 1
         self._engine = None
 
     # ------------------------------------------------------------------ reference-compatible helpers
@@ -197,7 +199,7 @@ class GPT(nn.Module):
         """Zero-filled caches, one (k, v) pair per layer, COMPACT layout (B, n_query_groups, max_seq, hs)."""
         cfg = self.config
         B = idx.size(0)
-        shape = (cfg.n_layer, 2, B, cfg.n_query_groups, max_seq_length, cfg.head_size)
+        shape = (cfg.n_layer, 2, B, cfg.n_query_groups_local, max_seq_length, cfg.head_size)
         store = torch.zeros(shape, device=idx.device, dtype=self._kv_dtype())
         return [(store[l, 0], store[l, 1]) for l in range(cfg.n_layer)]
 

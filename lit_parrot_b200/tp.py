@@ -1,0 +1,75 @@
+"""Tensor parallelism for the decode hot path (BASELINE configs[4]: Llama-2-70b over 2/4/8 B200).
+
+The reference has no tensor parallelism (its multi-GPU inference is FSDP, generate/base.py:187-205, which re-gathers
+every layer's weights for every token); this module is the B200-native replacement: one process per GPU,
+``torch.distributed`` (NCCL) for bootstrap, weights sharded by query group / MLP column, and ONE exchange per
+sub-block — a one-shot all-reduce over NVLink peer memory fused with the residual add (``lp_tp_allreduce_residual``),
+fed straight from the projection GEMV's output buffer.  No NCCL call on the per-token path.
+
+    cfg  = Config.from_name("Llama-2-70b-hf").with_tp(world, rank)
+    model = GPT(cfg); model.load_state_dict(shard_state_dict(full_sd, cfg)); model.cuda()
+    model.tp_context = TPContext(dist.group.WORLD, device, max_rows=..., n_embd=cfg.n_embd)
+"""
+from typing import Dict
+
+import torch
+
+from lit_parrot_b200.config import Config
+
+
+def shard_state_dict(sd: Dict[str, torch.Tensor], cfg: Config) -> Dict[str, torch.Tensor]:
+    """Rank ``cfg.tp_rank``'s shard of a full (reference-layout) state dict.
+
+    * ``attn.attn`` rows are group-major ``[q x q_per_kv, k, v] x hs`` per query group (model.py:210-214): a rank takes the
+      contiguous rows of its groups; ``attn.proj`` takes the matching input columns (heads are group-major after the
+      transpose at model.py:249);
+    * ``mlp.fc / fc_1 / fc_2`` rows and ``mlp.proj`` columns are split evenly;
+    * biases of the row-parallel outputs (``attn.proj``, ``mlp.proj``) live on rank 0 only (they are added once, after the
+      exchange); everything else (norms, ``wte``, ``lm_head``) is replicated.
+    """
+    tp, r = cfg.tp_size, cfg.tp_rank
+    if tp == 1:
+        return dict(sd)
+    out = {}
+    for k, v in sd.items():
+        if ".attn.attn." in k or ".mlp.fc" in k:  # column-parallel: split output rows (weight dim 0, bias dim 0)
+            out[k] = v.chunk(tp, dim=0)[r].contiguous()
+        elif k.endswith(".attn.proj.weight") or k.endswith(".mlp.proj.weight"):  # row-parallel: split input columns
+            out[k] = v.chunk(tp, dim=1)[r].contiguous()
+        elif k.endswith(".attn.proj.bias") or k.endswith(".mlp.proj.bias"):
+            out[k] = v if r == 0 else torch.zeros_like(v)
+        else:
+            out[k] = v
+    return out
+
+
+class TPContext:
+    """Symmetric (peer-mapped) exchange buffers of one tensor-parallel group + the slot bookkeeping of the exchanges."""
+
+    def __init__(self, group, device: torch.device, max_rows: int, n_embd: int) -> None:
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.group = group
+        self.rank, self.size = dist.get_rank(group), dist.get_world_size(group)
+        self.slot_floats = max_rows * n_embd
+        self.buf = symm.empty(2 * self.slot_floats, dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.buf, group)
+        if self.hdl.signal_pad_size < 2 * self.size * 4:
+            raise RuntimeError("symmetric-memory signal pad too small")
+        self.buf_ptrs = self.hdl.buffer_ptrs_dev      # device arrays of `size` peer-mapped addresses
+        self.pad_ptrs = self.hdl.signal_pad_ptrs_dev
+        self.state = torch.zeros(2, 2, dtype=torch.int32, device=device)  # per slot: epoch, CTA ticket
+        self.slot = 0
+        self.count = 0
+        dist.barrier(group)
+
+    def begin_forward(self) -> None:
+        self.slot, self.count = 0, 0
+
+    def next_slot(self):
+        """(slot index, device pointer of this rank's slot) for the next exchange; slots alternate."""
+        s = self.slot
+        self.slot ^= 1
+        self.count += 1
+        return s, self.buf.data_ptr() + s * self.slot_floats * 4

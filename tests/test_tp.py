@@ -1,0 +1,138 @@
+"""Tensor parallelism: host-side sharding logic on CPU (gloo, world size 2) and the CUDA exchange path on >= 2 GPUs."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn.functional as F
+
+import lit_parrot_b200 as lp
+from lit_parrot_b200.tp import shard_state_dict
+from oracle import lit_oracle as O
+
+CFG = dict(block_size=64, vocab_size=512, padding_multiple=64, n_layer=2, n_head=8, n_embd=512, n_query_groups=4,
+           rotary_percentage=1.0, parallel_residual=False, bias=False, _norm_class="RMSNorm", _mlp_class="LLaMAMLP",
+           intermediate_size=1024)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _cpu_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cfg = lp.Config(**CFG)
+        sd = O.random_state_dict(cfg, seed=5)
+        lcfg = cfg.with_tp(world, rank)
+        ssd = shard_state_dict(sd, lcfg)
+        hs, qpk = cfg.head_size, cfg.q_per_kv
+        x = torch.randn(3, cfg.n_embd, generator=torch.Generator().manual_seed(1))
+        pre = "transformer.h.0."
+        # column-parallel QKV: this rank's rows are exactly its query groups (group-major [q x qpk, k, v] x hs)
+        full = F.linear(x, sd[pre + "attn.attn.weight"]).view(3, cfg.n_query_groups, qpk + 2, hs)
+        mine = F.linear(x, ssd[pre + "attn.attn.weight"]).view(3, lcfg.n_query_groups_local, qpk + 2, hs)
+        g0 = rank * lcfg.n_query_groups_local
+        assert torch.equal(mine, full[:, g0:g0 + lcfg.n_query_groups_local])
+        # row-parallel attn.proj on this rank's heads (head-major attention output), summed over ranks
+        att_full = torch.randn(3, cfg.n_embd, generator=torch.Generator().manual_seed(2))
+        hl = lcfg.n_head_local * hs
+        part = F.linear(att_full[:, rank * hl:(rank + 1) * hl], ssd[pre + "attn.proj.weight"])
+        dist.all_reduce(part)
+        torch.testing.assert_close(part, F.linear(att_full, sd[pre + "attn.proj.weight"]), rtol=1e-5, atol=1e-5)
+        # MLP: fc_1 / fc_2 rows, proj columns
+        il = lcfg.intermediate_size_local
+        u_full = F.silu(F.linear(x, sd[pre + "mlp.fc_1.weight"])) * F.linear(x, sd[pre + "mlp.fc_2.weight"])
+        u_mine = F.silu(F.linear(x, ssd[pre + "mlp.fc_1.weight"])) * F.linear(x, ssd[pre + "mlp.fc_2.weight"])
+        assert torch.equal(u_mine, u_full[:, rank * il:(rank + 1) * il])
+        part = F.linear(u_mine, ssd[pre + "mlp.proj.weight"])
+        dist.all_reduce(part)
+        torch.testing.assert_close(part, F.linear(u_full, sd[pre + "mlp.proj.weight"]), rtol=1e-5, atol=1e-5)
+        # replicated tensors and the module tree of the sharded model
+        assert torch.equal(ssd["lm_head.weight"], sd["lm_head.weight"]) and torch.equal(ssd[pre + "norm_1.weight"], sd[pre + "norm_1.weight"])
+        m = lp.GPT(lcfg)
+        m.load_state_dict(ssd)  # shapes of the local module tree match the shard
+        assert m.transformer.h[0].attn.attn.weight.shape == (cfg.qkv_rows // world, cfg.n_embd)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_tp_sharding_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == {0: "ok", 1: "ok"}, res
+
+
+def test_tp_config_errors():
+    cfg = lp.Config.from_name("falcon-7b")
+    with pytest.raises(ValueError):
+        cfg.with_tp(2, 0)  # one query group (MQA) cannot be split
+    c = lp.Config.from_name("Llama-2-70b-hf").with_tp(8, 3)
+    assert (c.n_head_local, c.n_query_groups_local, c.intermediate_size_local, c.qkv_rows_local) == (8, 1, 3584, 1280)
+    assert lp.Config.from_name("Llama-2-70b-hf").tp_size == 1
+
+
+def _gpu_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from lit_parrot_b200.tp import TPContext
+
+        cfg = lp.Config(**CFG)
+        sd = {k: v.bfloat16() for k, v in O.random_state_dict(cfg, seed=7).items()}
+        prompt = torch.randint(0, cfg.vocab_size, (8,), generator=torch.Generator().manual_seed(1)).to(torch.int32)
+        lcfg = cfg.with_tp(world, rank)
+        m = lp.GPT(lcfg)
+        m.load_state_dict(shard_state_dict(sd, lcfg))
+        m = m.to(device=dev, dtype=torch.bfloat16).eval()
+        m.kv_cache_dtype = torch.float32
+        m.tp_context = TPContext(dist.group.WORLD, dev, max_rows=16, n_embd=cfg.n_embd)
+        out = lp.generate(m, prompt.to(dev), 48, 48, temperature=1.0, top_k=1).cpu()
+        m.reset_cache()
+        lg = m._forward_impl(prompt.view(1, -1).long().to(dev), 48, torch.arange(8, device=dev), raw_logits=True).float().cpu()
+        if rank == 0:
+            om = O.OracleGPT(cfg, {k: v.float() for k, v in sd.items()})
+            want = O.generate(om, prompt, 48, 48, top_k=1, argmax_ties=True)
+            ref = om(prompt.view(1, -1).long(), 48, torch.arange(8))
+            assert torch.equal(out, want), (out, want)
+            torch.testing.assert_close(lg, ref, rtol=0, atol=2e-4)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_tp2_matches_single_device_oracle():
+    """Llama-style GQA model sharded over 2 GPUs (one-shot NVLink all-reduce fused with the residual add) == the
+    single-device oracle: 40 greedy tokens identical, prefill logits within 2e-4."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == {0: "ok", 1: "ok"}, res
