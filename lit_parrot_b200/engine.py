@@ -216,6 +216,9 @@ class Engine:
              caches, B: int, T: int, stream: int, last_only: bool = False) -> None:
         lib, cfg, r, chk = self.lib, self.cfg, self.round, _lib.check
         rows = B * T
+        if idx_off is None and self.tc_eligible(rows):
+            # wide decode batches (B >= 9) and prefill: projections on the tcgen05 GEMM, weights still streamed once
+            return self._run_tc(b, idx_ptr, idx64, pos_ptr, caches, B, T, stream, last_only)
         E, H, G, hs = cfg.n_embd, cfg.n_head_local, cfg.n_query_groups_local, cfg.head_size
         max_seq = caches[0][0].size(2)
         kvd = _KV_OF_DTYPE[caches[0][0].dtype]
@@ -342,9 +345,16 @@ class Engine:
             kc, vc = caches[li][0].data_ptr(), caches[li][1].data_ptr()
             norm_split(x, L.n1_w, L.n1_b, t_n)
             gemm(t_n, L.qkv, _lib.LP_EPI_NONE, None, qkv)
-            chk(lib.lp_rope_kv_append(qkv, _ptr(self.cos), _ptr(self.sin), pos_ptr, q, kc, vc, kvd, B, T, H, G, hs, cfg.rope_n_elem,
-                                      max_seq, r, stream), "lp_rope_kv_append")
-            self._attention_rows(q, kc, vc, kvd, pos_ptr, att, ws, ws_bytes, B, T, max_seq, scale, stream)
+            rc = -2
+            if T == 1:
+                rc = lib.lp_attn_decode_fused(qkv, _ptr(self.cos), _ptr(self.sin), pos_ptr, att, kc, vc, kvd, ws, ws_bytes, B, H, G, hs,
+                                              cfg.rope_n_elem, max_seq, scale, r, stream)
+                if rc != -2:
+                    chk(rc, "lp_attn_decode_fused")
+            if rc == -2:
+                chk(lib.lp_rope_kv_append(qkv, _ptr(self.cos), _ptr(self.sin), pos_ptr, q, kc, vc, kvd, B, T, H, G, hs, cfg.rope_n_elem,
+                                          max_seq, r, stream), "lp_rope_kv_append")
+                self._attention_rows(q, kc, vc, kvd, pos_ptr, att, ws, ws_bytes, B, T, max_seq, scale, stream)
             chk(lib.lp_split_bf16(att, t_att, rows, E, nt, -1, None, None, 0.0, 0, stream), "lp_split_bf16")
             if cfg.parallel_residual:
                 if not cfg.shared_attention_norm:
@@ -361,7 +371,7 @@ class Engine:
                 gemm(t_n, L.fc, self.act, None, None, t_u)
                 gemm(t_u, L.mlp_proj, _lib.LP_EPI_RESIDUAL, x, x)
         xf, logits = b["xf"].data_ptr(), b["logits"].data_ptr()
-        if last_only:
+        if last_only and T > 1:
             # only the last position of each sequence feeds the sampler (generate/base.py:136)
             for bi in range(B):
                 src = x + ((bi + 1) * T - 1) * E * 4
@@ -405,10 +415,7 @@ class Engine:
         if T > 1:  # one host read per prefill: are the positions p, p+1, ... without wrapping the cache?
             ph = pos32.cpu()
             self._consecutive = bool((ph[1:] - ph[:-1] == 1).all()) and int(ph[-1]) < max_seq
-        if self.tc_eligible(B * T):
-            self._run_tc(b, idx.data_ptr(), int(idx.dtype == torch.int64), pos32.data_ptr(), caches, B, T, stream, last_only)
-        else:
-            self._run(b, idx.data_ptr(), int(idx.dtype == torch.int64), None, pos32.data_ptr(), caches, B, T, stream, last_only)
+        self._run(b, idx.data_ptr(), int(idx.dtype == torch.int64), None, pos32.data_ptr(), caches, B, T, stream, last_only)
         out = b["logits"][:B].view(B, 1, V) if (last_only and T > 1) else b["logits"].view(B, T, V)
         return out if raw_logits else out.to(self.param_dtype, copy=True)
 

@@ -244,3 +244,28 @@ def test_real_width_two_layer_llama7b_bf16():
     got = m._forward_impl(prompt.view(1, -1).to(DEV), 80, torch.arange(16, device=DEV), last_only=True, raw_logits=True)
     got = got[0, -1].float().cpu()
     assert (got - lg[0]).abs().max() < 2e-2 and cosine(got, lg[0]) > 0.999
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_wide_batch_decode_on_tensor_core_gemm(precision):
+    """Lock-step batch of 16 sequences (model.py:66): prefill and every decode step run their projections on the tcgen05
+    GEMM (rows >= 9), attention on the fused decode kernel; logits against the oracle on the same bf16 weights."""
+    cfg = lp.Config(**{**QCFG, "n_embd": 256, "intermediate_size": 512, "n_head": 4, "n_query_groups": 2})
+    sd = {k: v.bfloat16() for k, v in O.random_state_dict(cfg, seed=41).items()}
+    m = build(cfg, sd, dtype=torch.bfloat16, precision=precision)
+    m.kv_cache_dtype = torch.float32 if precision == "fp32" else torch.bfloat16
+    om = O.OracleGPT(cfg, {k: v.float() for k, v in sd.items()})
+    B, T0 = 16, 5
+    idx = torch.randint(0, cfg.padded_vocab_size, (B, T0), generator=torch.Generator().manual_seed(5))
+    pos = torch.arange(T0)
+    want = om(idx, 32, pos)
+    got = m._forward_impl(idx.to(DEV), 32, pos.to(DEV), raw_logits=True).float().cpu()
+    tol = dict(rtol=0, atol=1e-4) if precision == "fp32" else dict(rtol=0, atol=6e-2)
+    torch.testing.assert_close(got, want, **tol)
+    for _ in range(4):
+        tok = want[:, -1].argmax(-1, keepdim=True)
+        pos = pos[-1:] + 1
+        want = om(tok, 32, pos)
+        got = m._forward_impl(tok.to(DEV), 32, pos.to(DEV), raw_logits=True).float().cpu()
+        torch.testing.assert_close(got, want, **tol)
+        assert cosine(got, want) > 0.999

@@ -1,2 +1,7 @@
-timeout 600 python -m pytest tests/test_tp.py -m gpu -q --timeout 500 > gpurun_out/r27_tests.log 2>&1; tail -25 gpurun_out/r27_tests.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 32 --warmup 4 --no-cpu-baseline > gpurun_out/r27_bench_tp2.log 2>&1; tail -3 gpurun_out/r27_bench_tp2.log | cut -c1-1800
+timeout 900 python -m pytest tests -m gpu -q --maxfail=10 --timeout 300 > gpurun_out/r29_tests.log 2>&1; tail -8 gpurun_out/r29_tests.log
+python bench.py --steps 64 --warmup 8 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/r29_bench.log; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r29_bench.log').read())
+print('3b-b1 tok/s', round(d['value'],1), 'ms', round(d['ms_per_step'],3), 'frac', round(d['roofline']['whole_step']['frac'],3), 'launches', d['roofline']['whole_step']['launches'], 'kernel', d['roofline']['kernel'])
+for e in d.get('also',[]): print({k:(round(v,3) if isinstance(v,float) else v) for k,v in e.items() if k not in ('bytes_per_step','kernel')})
+PY
