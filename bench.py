@@ -431,9 +431,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload is None:
-        # N = 1: BASELINE configs[1].  N > 1: configs[4], the one configuration of the path that shards —
-        # Llama-2-70b tensor parallel over the N ranks, strong scaling (the same single sequence on more GPUs).
-        args.workload = DEFAULT if world == 1 else "llama2-70b-bf16-b1-tp"
+        # BASELINE configs[1] at every N: a 3B model does not shard, so N > 1 runs N independent replicas (weak scaling, no
+        # collective) and the line stays comparable across N.  The configuration of the path that DOES shard — configs[4],
+        # Llama-2-70b tensor parallel over the N ranks, strong scaling — is measured in the same run and reported under "tp".
+        args.workload = DEFAULT
     is_tp = args.workload.endswith("-tp")
     preset, quant, tile, B, ctx = WORKLOADS[args.workload]
     base = {"metric": "decode_tokens_per_second", "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -469,6 +470,13 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     res = run_workload(args.workload, args.steps, args.warmup, device, rank, world)
     extras = []
+    tp_res = None
+    if not args.no_extras and not is_tp:
+        try:  # Llama-2-70b bf16, batch 1, 2k context over all `world` ranks (world == 1: the unsharded model, 137 GB of HBM)
+            tp_res = run_workload("llama2-70b-bf16-b1-tp", min(args.steps, 32), min(args.warmup, 4), device, rank, world, with_e2e=False,
+                                  with_kernel=False)
+        except Exception as e:
+            tp_res = {"workload": "llama2-70b-bf16-b1-tp", "error": repr(e)[:200]}
     if not args.no_extras and world == 1:
         for w in EXTRAS:
             if w != args.workload:
@@ -490,6 +498,13 @@ def main():
                               "peak_source": peak_src,
                               "whole_step": {"achieved": res["step_gbs"], "frac": res["step_gbs"] / peak,
                                              "bytes": res["bytes_per_step"], "launches": res["launches_per_step"]}})
+        if tp_res is not None:
+            line["tp"] = {"workload": f"Llama-2-70b-hf bf16 decode, batch 1, context 2048, tensor parallel over {world} GPU(s)",
+                          "scaling": "strong", "n_gpus": world,
+                          **{kk: tp_res[kk] for kk in ("tok_s", "ms_per_step", "launches_per_step", "bytes_per_step", "step_gbs", "error")
+                             if kk in tp_res}}
+            if "step_gbs" in tp_res:
+                line["tp"]["per_gpu_hbm_frac"] = tp_res["step_gbs"] / peak
         if extras:
             line["also"] = [{kk: e[kk] for kk in e if kk in ("workload", "tok_s", "ms_per_step", "step_gbs", "launches_per_step",
                                                               "bytes_per_step", "kernel", "error", "ms", "prefill_tok_s", "tflops",

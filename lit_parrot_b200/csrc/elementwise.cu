@@ -90,11 +90,12 @@ __global__ void rope_kv_kernel(const float* __restrict__ qkv, const float* __res
   const int row = blockIdx.x;  // b*T + t
   const int b = row / T, t = row % T;
   const int qpk = H / G;
-  const int slot_in_row = blockIdx.y;  // 0 .. H+2G-1, in qkv row order
-  const int g = slot_in_row / (qpk + 2), j = slot_in_row % (qpk + 2);
-  const int d = threadIdx.x;
-  if (d >= hs) return;
   const int p = pos[t];
+  // one CTA per token row; its threads walk the (head slot, dim) pairs of the row
+  for (int e = threadIdx.x; e < (H + 2 * G) * hs; e += blockDim.x) {
+  const int slot_in_row = e / hs;  // 0 .. H+2G-1, in qkv row order
+  const int d = e % hs;
+  const int g = slot_in_row / (qpk + 2), j = slot_in_row % (qpk + 2);
   const float* src = qkv + (size_t)row * (H + 2 * G) * hs + (size_t)slot_in_row * hs;
   float v = src[d];
   if (j <= qpk && d < n_elem) {  // q heads and the k head are rotated, v is not
@@ -111,6 +112,7 @@ __global__ void rope_kv_kernel(const float* __restrict__ qkv, const float* __res
     KV* dst = (j == qpk ? kc : vc) + (((size_t)b * G + g) * max_seq + slot) * hs + d;
     if constexpr (sizeof(KV) == 2) *dst = __float2bfloat16_rn(v);
     else *dst = v;
+  }
   }
 }
 
@@ -168,7 +170,7 @@ int lp_rope_kv_append(const float* qkv, const float* cos, const float* sin, cons
   if (n_elem > 0 && (!cos || !sin)) return LP_ERR_INVALID_ARG;
   if (B <= 0 || T <= 0 || H <= 0 || G <= 0 || H % G || hs <= 0 || hs > 1024 || n_elem < 0 || n_elem > hs || ((n_elem & 1) && n_elem != 1) || max_seq <= 0)
     return LP_ERR_INVALID_ARG;
-  dim3 grid(B * T, H + 2 * G), block((hs + 31) / 32 * 32);
+  dim3 grid(B * T), block(256);
   if (kv_dtype == LP_F32)
     return lp::launch(lp::rope_kv_kernel<float>, grid, block, 0, stream, qkv, cos, sin, pos, q_out, (float*)k_cache, (float*)v_cache,
                       T, H, G, hs, n_elem, max_seq, round_bf16);

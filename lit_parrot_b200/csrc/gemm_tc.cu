@@ -3,7 +3,8 @@
 //
 //   reference ops: every nn.Linear of GPT.forward applied to T > 1 tokens (model.py:111, 205, 252, 285-301).
 //
-// One CTA computes a 128 x BN output tile (BN = 256 or 128):
+// PERSISTENT CTAs (one per SM) walk the 128 x BN output tiles (BN = 256 or 128), M tiles fastest; the accumulator is
+// double buffered in TMEM (2 x BN of the 512 columns), so the epilogue of tile i overlaps the MMAs of tile i + 1:
 //   warp 0   : TMA producer — cp.async.bulk.tensor.2d loads of a 128 x 64 X tile (per activation term, see below) and a
 //              BN x 64 W tile per stage into a 128-byte-swizzled ring, full/empty mbarriers;
 //   warp 1   : MMA issuer — one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M 128, N BN, K 16) from
@@ -99,16 +100,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   const int A_BYTES = TC_BM * TC_BK * 2;           // per term
   constexpr int B_BYTES = BN * TC_BK * 2;
   const int stage_bytes = p.nterms * A_BYTES + B_BYTES;
-  __shared__ __align__(8) uint64_t bars[2 * 8 + 1];  // full[], empty[], accumulator-ready
+  __shared__ __align__(8) uint64_t bars[2 * 12 + 4];  // full[12], empty[12], accumulator full[2], accumulator empty[2]
   __shared__ uint32_t s_tmem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
   const int nk = (p.K + TC_BK - 1) / TC_BK;
+  const int tiles_m = (p.M + TC_BM - 1) / TC_BM, tiles_n = (p.N + BN - 1) / BN;
+  const int ntiles = tiles_m * tiles_n;
   const uint32_t bar0 = tc_smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8 * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8 * (8 + s); };
-  const uint32_t acc_bar = bar0 + 8 * 16;
+  auto empty_bar = [&](int s) { return bar0 + 8 * (12 + s); };
+  auto acc_full = [&](int a) { return bar0 + 8 * (24 + a); };
+  auto acc_empty = [&](int a) { return bar0 + 8 * (26 + a); };
   const uint32_t ring = tc_smem_u32(smem);
 
   if (threadIdx.x == 0) {
@@ -116,11 +119,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       tc_mbar_init(full_bar(s), 1);
       tc_mbar_init(empty_bar(s), 1);
     }
-    tc_mbar_init(acc_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      tc_mbar_init(acc_full(a), 1);
+      tc_mbar_init(acc_empty(a), 4);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (warp == 2) {  // TMEM allocation: BN fp32 columns (power of two >= 32), by one warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tc_smem_u32(&s_tmem)), "r"(BN) : "memory");
+  if (warp == 2) {  // TMEM allocation: two accumulators of BN fp32 columns (power of two >= 32), by one warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tc_smem_u32(&s_tmem)), "r"(2 * BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   tc_fence_before();
@@ -135,14 +141,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     // ===== TMA producer =====
     if (lane == 0) {
       int s = 0, ph = 0;
-      for (int kb = 0; kb < nk; ++kb) {
-        tc_mbar_wait(empty_bar(s), ph ^ 1);
-        const uint32_t dst = ring + (uint32_t)s * stage_bytes;
-        tc_mbar_expect_tx(full_bar(s), stage_bytes);
-        for (int t = 0; t < p.nterms; ++t)  // term t of X: rows [t*M + m0, +128) of the stacked [nterms*M, K] tensor
-          tc_tma_2d(dst + t * A_BYTES, &map_x, kb * TC_BK, t * p.M + m0, full_bar(s));
-        tc_tma_2d(dst + p.nterms * A_BYTES, &map_w, kb * TC_BK, n0, full_bar(s));
-        if (++s == nstages) { s = 0; ph ^= 1; }
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = (tile % tiles_m) * TC_BM, n0 = (tile / tiles_m) * BN;
+        for (int kb = 0; kb < nk; ++kb) {
+          tc_mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t dst = ring + (uint32_t)s * stage_bytes;
+          tc_mbar_expect_tx(full_bar(s), stage_bytes);
+          for (int t = 0; t < p.nterms; ++t)  // term t of X: rows [t*M + m0, +128) of the stacked [nterms*M, K] tensor
+            tc_tma_2d(dst + t * A_BYTES, &map_x, kb * TC_BK, t * p.M + m0, full_bar(s));
+          tc_tma_2d(dst + p.nterms * A_BYTES, &map_w, kb * TC_BK, n0, full_bar(s));
+          if (++s == nstages) { s = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -150,39 +159,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     if (lane == 0) {
       // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      int s = 0, ph = 0;
-      uint32_t accumulate = 0;
-      for (int kb = 0; kb < nk; ++kb) {
-        tc_mbar_wait(full_bar(s), ph);
+      int s = 0, ph = 0, it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int a = it & 1;  // TMEM accumulator of this tile
+        tc_mbar_wait(acc_empty(a), ((it >> 1) & 1) ^ 1);  // the epilogue has drained it (first use: passes immediately)
         tc_fence_after();
-        const uint32_t a0 = ring + (uint32_t)s * stage_bytes;
-        const uint32_t b0 = a0 + p.nterms * A_BYTES;
+        const uint32_t tacc = tmem + a * BN;
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < nk; ++kb) {
+          tc_mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t a0 = ring + (uint32_t)s * stage_bytes;
+          const uint32_t b0 = a0 + p.nterms * A_BYTES;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint64_t db = tc_smem_desc(b0 + k * 32);
-          for (int t = 0; t < p.nterms; ++t) {
-            tc_mma(tmem, tc_smem_desc(a0 + t * A_BYTES + k * 32), db, idesc, accumulate);
-            accumulate = 1;
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t db = tc_smem_desc(b0 + k * 32);
+            for (int t = 0; t < p.nterms; ++t) {
+              tc_mma(tacc, tc_smem_desc(a0 + t * A_BYTES + k * 32), db, idesc, accumulate);
+              accumulate = 1;
+            }
           }
+          tc_commit(empty_bar(s));  // the slot is free once these MMAs have read it
+          if (++s == nstages) { s = 0; ph ^= 1; }
         }
-        tc_commit(empty_bar(s));  // the slot is free once these MMAs have read it
-        if (++s == nstages) { s = 0; ph ^= 1; }
+        tc_commit(acc_full(a));  // accumulator complete
       }
-      tc_commit(acc_bar);  // accumulator complete
     }
   }
   if (warp >= 2) {
     // ===== epilogue: warp w may touch TMEM lanes [32 (w % 4), +32) =====
-    tc_mbar_wait(acc_bar, 0);
-    tc_fence_after();
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
     const bool swiglu = p.epi == LP_EPI_SWIGLU;
     const int nout = swiglu ? p.N / 2 : p.N;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int a = it & 1;
+    const int m0 = (tile % tiles_m) * TC_BM, n0 = (tile / tiles_m) * BN;
+    const int row = m0 + q * 32 + lane;
+    tc_mbar_wait(acc_full(a), (it >> 1) & 1);
+    tc_fence_after();
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
-      tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+      tc_ld32(tmem + a * BN + ((uint32_t)(q * 32) << 16) + c0, v);
       if (row < p.M) {
         float y[32];
 #pragma unroll
@@ -222,26 +241,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           }
         }
         if (p.out_bf) {
+          const bool vec = ocol + ncols <= nout && (nout & 7) == 0;  // 16-byte stores of 8 bf16
           for (int t = 0; t < p.out_terms; ++t) {
             __nv_bfloat16* dst = p.out_bf + ((size_t)t * p.M + row) * nout + ocol;
+            uint32_t pk[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < ncols && ocol + j < nout) {
-                const __nv_bfloat16 h = __float2bfloat16_rn(y[j]);
-                dst[j] = h;
-                y[j] -= __bfloat162float(h);
-              }
+            for (int j = 0; j < 32; j += 2) {
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(y[j]), h1 = __float2bfloat16_rn(y[j + 1]);
+              y[j] -= __bfloat162float(h0);
+              y[j + 1] -= __bfloat162float(h1);
+              pk[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            }
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8)
+                if (j < ncols) *reinterpret_cast<uint4*>(dst + j) = make_uint4(pk[j / 2], pk[j / 2 + 1], pk[j / 2 + 2], pk[j / 2 + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols && ocol + j < nout)
+                  dst[j] = __ushort_as_bfloat16((unsigned short)((j & 1) ? (pk[j / 2] >> 16) : (pk[j / 2] & 0xffffu)));
             }
           }
         }
       }
     }
     tc_fence_before();
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(acc_empty(a)) : "memory");  // TMEM buffer may be reused
+    }
   }
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(2 * BN) : "memory");
   }
 }
 
@@ -355,11 +388,12 @@ static int tc_launch(const CUtensorMap& mx, const CUtensorMap& mw, const TcParam
   }
   const int stage_bytes = p.nterms * TC_BM * TC_BK * 2 + BN * TC_BK * 2;
   int nstages = (212 * 1024) / stage_bytes;
-  if (nstages > 8) nstages = 8;
+  if (nstages > 12) nstages = 12;
   if (nstages < 2) return LP_ERR_UNSUPPORTED;
   const size_t smem = (size_t)nstages * stage_bytes + 1024;
-  dim3 grid((p.M + TC_BM - 1) / TC_BM, (p.N + BN - 1) / BN);
-  return launch(kern, grid, dim3(TC_THREADS), smem, stream, mx, mw, p, nstages);
+  const int ntiles = ((p.M + TC_BM - 1) / TC_BM) * ((p.N + BN - 1) / BN);
+  const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  return launch(kern, dim3(grid), dim3(TC_THREADS), smem, stream, mx, mw, p, nstages);
 }
 
 }  // namespace lp
@@ -383,7 +417,17 @@ int lp_gemm_bf16_tc(const void* x_terms, int nterms, int M, const void* w_bf16, 
   if (epilogue == LP_EPI_RESIDUAL && !residual) return LP_ERR_INVALID_ARG;
   if (K % 8 || N % 8) return LP_ERR_UNSUPPORTED;  // 16-byte global strides (ragged N / K tiles are zero-filled by TMA)
   if ((reinterpret_cast<uintptr_t>(x_terms) & 15) || (reinterpret_cast<uintptr_t>(w_bf16) & 15)) return LP_ERR_UNSUPPORTED;
-  const int BN = (N % 256 == 0 && nterms <= 2) ? 256 : 128;  // a ragged last tile wastes less at 128
+  // Tile width: 256 halves the activation re-reads (prefill); decode batches (one M tile) are weight-streaming bound and
+  // need ~one tile per SM, so the width shrinks until the grid fills the chip.  Ragged last tiles are zero-filled by TMA.
+  const int tiles_m = (M + lp::TC_BM - 1) / lp::TC_BM;
+  int BN = 32;
+  for (int bn : {256, 128, 64}) {
+    if (bn == 256 && nterms > 2) continue;  // shared-memory budget of a stage
+    if ((long long)tiles_m * ((N + bn - 1) / bn) >= (long long)lp::num_sms() * 4 / 5) {
+      BN = bn;
+      break;
+    }
+  }
   const CUtensorMap* mx = lp::tc_cached_map(x_terms, nterms * M, K, lp::TC_BM);
   const CUtensorMap* mw = lp::tc_cached_map(w_bf16, N, K, BN);
   if (!mx || !mw) return LP_ERR_UNSUPPORTED;
@@ -399,7 +443,12 @@ int lp_gemm_bf16_tc(const void* x_terms, int nterms, int M, const void* w_bf16, 
   p.round_bf16 = round_bf16;
   p.nterms = nterms;
   p.out_terms = out_terms;
-  return BN == 256 ? lp::tc_launch<256>(*mx, *mw, p, stream) : lp::tc_launch<128>(*mx, *mw, p, stream);
+  switch (BN) {
+    case 256: return lp::tc_launch<256>(*mx, *mw, p, stream);
+    case 128: return lp::tc_launch<128>(*mx, *mw, p, stream);
+    case 64: return lp::tc_launch<64>(*mx, *mw, p, stream);
+    default: return lp::tc_launch<32>(*mx, *mw, p, stream);
+  }
 }
 
 }  // extern "C"

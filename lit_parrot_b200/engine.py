@@ -330,7 +330,7 @@ class Engine:
         t_n, t_att, t_u = b["t_n"].data_ptr(), b["t_att"].data_ptr(), b["t_u"].data_ptr()
         ws, ws_bytes = b["ws"].data_ptr(), b["ws"].numel()
         scale = 1.0 / math.sqrt(hs)
-        nt = 1 if r else (3 if rows <= 256 else 2)  # bf16 terms per activation
+        nt = 1 if r else (3 if rows <= 16 else 2)  # bf16 terms per activation (3 terms = all 24 bits; 2 = 16 bits, error 2^-17)
         nk = self.norm_kind
         chk(lib.lp_embed(idx_ptr, idx64, None, self.wte.data_ptr(), _KV_OF_DTYPE[self.wte.dtype], x, rows, E, r, stream), "lp_embed")
 
