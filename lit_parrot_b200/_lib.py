@@ -10,7 +10,7 @@ import threading
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblitparrot_b200.so")
+LIB_PATH = os.environ.get("LP_LIB_PATH") or os.path.join(_HERE, "liblitparrot_b200.so")  # LP_LIB_PATH: A/B builds
 
 # enums of lp_abi.h
 LP_F32, LP_BF16 = 0, 1

@@ -119,9 +119,6 @@ struct GsParams {
   int ngroups;      // int4 groups per row
   int gp128;        // 128-column chunks per scale group (group / 128)
   unsigned long long* trace;  // debug: per-CTA phase timestamps (globaltimer ns), NULL in production
-  float* sk_ws;     // stream-K: [grid][16][16] partial sums of a tile that straddles two CTAs' ranges
-  int* sk_flags;    // stream-K: [grid] "partial written" flags, zero between launches
-  int streamk;      // 1: stage-granular split (balanced, cross-CTA partial sums); 0: tile-granular split
 };
 
 __device__ __forceinline__ unsigned long long gs_now() {
@@ -313,15 +310,12 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
   auto full_bar = [&](int s) { return bar0 + 8 * s; };
   auto empty_bar = [&](int s) { return bar0 + 8 * (p.nstages + s); };
 
-  // STREAM-K work split: the (tile, stage) units are dealt out evenly, so a CTA's contiguous range may begin and / or end
-  // in the middle of a tile.  Every CTA streams the same number of bytes (+-1 stage); see the tile flush below.
-  // (p.streamk == 0: ranges are rounded to whole tiles — no cross-CTA traffic, up to one tile of imbalance.)
-  const long long total_units = p.streamk ? (long long)p.ntiles * p.nks : (long long)p.ntiles;
-  const int unit_scale = p.streamk ? 1 : p.nks;
-  const int u0 = (int)((total_units * blockIdx.x) / gridDim.x) * unit_scale;
-  const int u1 = (int)((total_units * (blockIdx.x + 1)) / gridDim.x) * unit_scale;
-  const int nunits = u1 - u0;
-  const int tile_begin = u0 / p.nks, ks_begin = u0 % p.nks;
+  // Tiles of this CTA: contiguous range of WHOLE tiles.  A stage-granular (stream-K) split with cross-CTA partial sums was
+  // tried (git history: "stream-K (opt-in)"): perfectly balanced, but 2.03 vs 1.74 ms per stablelm-3b step and 2.70 vs 2.13 ms
+  // per 7B-int4 step on B200 — a CTA that starts late then also delays its neighbour's tile — so it was dropped.
+  const int tile_begin = (int)(((long long)p.ntiles * blockIdx.x) / gridDim.x);
+  const int tile_end = (int)(((long long)p.ntiles * (blockIdx.x + 1)) / gridDim.x);
+  const int nunits = (tile_end - tile_begin) * p.nks;
   const int aux_bytes = (p.W.flags & LP_WF_AUX_PACKED) ? 4 : 8;
 
   if (p.trace && threadIdx.x == 0) p.trace[blockIdx.x * 8 + 0] = gs_now();
@@ -339,7 +333,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
     // =========================== PRODUCER: weights do not depend on the previous kernel -> no griddepcontrol.wait ====
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmap) : "memory");
-      int s = 0, ph = 0, ks = ks_begin, tile = tile_begin;
+      int s = 0, ph = 0, ks = 0, tile = tile_begin;
       for (int u = 0; u < nunits; ++u) {
         mbar_wait(empty_bar(s), ph ^ 1);
         const uint32_t dst = ring_u32 + (uint32_t)s * p.stage_stride;
@@ -407,7 +401,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
   // swizzle (16-byte unit ^= row & 7) the two rows of a quarter warp read opposite halves of a 128-byte line.
   const int pr0 = (FMT == LP_W_INT4) ? ((g >> 1) + 4 * (g & 1)) : g;
 
-  int s = 0, ph = 0, ks = ks_begin, tile = tile_begin, lt = 0;
+  int s = 0, ph = 0, ks = 0, tile = tile_begin;
   for (int u = 0; u < nunits; ++u) {
     mbar_wait(full_bar(s), ph);
     if (p.trace && threadIdx.x == 0 && u < 4) p.trace[blockIdx.x * 8 + 3 + u] = gs_now();
@@ -492,19 +486,13 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
     if (lane == 0) mbar_arrive(empty_bar(s));  // this warp is done with the stage
     if (++s == p.nstages) { s = 0; ph ^= 1; }
 
-    ++ks;
-    if (ks == p.nks || u == nunits - 1) {
-      // ---- tile finished (or this CTA's range ends inside it): cross-warp reduction, column recombination, epilogue ----
-      // A tile that straddles CTA ranges is FINALISED by the CTA that owns its first stage — that CTA reaches the tile at
-      // the very end of its own range — while the CTAs that own the later stages meet it at the START of their ranges and
-      // only CONTRIBUTE: they drop their partial sums into a global slot and raise a flag long before the finaliser looks.
-      // Partial sums are added in CTA order: deterministic.
-      const bool owns_first = (long long)tile * p.nks >= u0;
-      const bool complete = owns_first && ks == p.nks;
+    if (++ks == p.nks) {
+      ks = 0;
+      // ---- tile finished: cross-warp reduction, column recombination, epilogue ----
       // Only ONE warp (rotating with the tile) waits for the others and finalises; everybody else drops its partial sums,
       // arrives on the named barrier and moves on to the next tile.  `red` is double buffered by tile parity: before
       // overwriting a buffer a warp checks that the tile that used it two tiles ago has been finalised (`done`).
-      const int par = lt & 1;
+      const int lt = tile - tile_begin, par = lt & 1;
       if (lt >= 2) {
         while (done[par] < lt - 2) {}
       }
@@ -548,21 +536,9 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
 #pragma unroll
             for (int q = 0; q < 3; ++q) c = (q == s2) ? cs[q] : c;
             c += __shfl_xor_sync(0xffffffffu, c, 16);
-            if (!owns_first) {  // contributor: hand the partial sum to the finaliser
-              if (half == 0) p.sk_ws[((size_t)blockIdx.x * 16 + rr) * 16 + m * p.split + s2] = c;
-            } else if (!complete) {  // finaliser: add the later CTAs' parts of this tile, in CTA order
-              for (int j = blockIdx.x + 1; j < (int)gridDim.x && (total_units * j) / gridDim.x * unit_scale < (long long)(tile + 1) * p.nks; ++j) {
-                int f;
-                do {
-                  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(f) : "l"(p.sk_flags + j) : "memory");
-                } while (f == 0);
-                c += __ldcg(p.sk_ws + ((size_t)j * 16 + rr) * 16 + m * p.split + s2);
-              }
-            }
             y = fmaf(c, colscale[m * p.split + s2], y);
           }
         }
-        if (!owns_first) continue;  // contributors stop here
         const int row = tile * GS_ROWS + rr;
         if (p.W.bias) y += p.W.bias[row];
         y = maybe_round(y, p.round_bf16);
@@ -578,28 +554,17 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
           p.out[(size_t)m * N + row] = y;
         }
         }
-        if (nfin > 1) {  // all finalisers have read `red` (and written / read the stream-K slots)
+        if (nfin > 1) {  // all finalisers have read `red`
           if (par == 0) asm volatile("bar.sync 4, %0;\n" ::"r"(nfin * 32) : "memory");
           else asm volatile("bar.sync 5, %0;\n" ::"r"(nfin * 32) : "memory");
         }
         __syncwarp();
         if (fidx == 0 && lane == 0) {
-          if (!owns_first) {  // publish the contribution
-            __threadfence();
-            asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p.sk_flags + blockIdx.x), "r"(1) : "memory");
-          } else if (!complete) {  // consumed: re-arm the contributors' flags for the next launch
-            for (int j = blockIdx.x + 1; j < (int)gridDim.x && (total_units * j) / gridDim.x * unit_scale < (long long)(tile + 1) * p.nks; ++j)
-              p.sk_flags[j] = 0;
-          }
           __threadfence_block();
           done[par] = lt;
         }
       }
-      ++lt;
-      if (ks == p.nks) {
-        ks = 0;
-        ++tile;
-      }
+      ++tile;
     }
   }
   if (p.trace && threadIdx.x == 0) p.trace[blockIdx.x * 8 + 7] = gs_now();
@@ -666,17 +631,6 @@ static const GsMap& gs_tensor_map(const lp_weight& W, size_t row_bytes) {
   return cache.emplace(key, m).first->second;
 }
 
-static float* g_sk_ws = nullptr;  // stream-K exchange slots, allocated once by init_linear_stream() (lp_init)
-static int* g_sk_flags = nullptr;
-int init_linear_stream() {
-  if (g_sk_ws) return LP_OK;
-  const int n = num_sms() > 256 ? num_sms() : 256;
-  LP_CUDA_TRY(cudaMalloc(&g_sk_ws, (size_t)n * 16 * 16 * sizeof(float)));
-  LP_CUDA_TRY(cudaMalloc(&g_sk_flags, (size_t)n * sizeof(int)));
-  LP_CUDA_TRY(cudaMemset(g_sk_flags, 0, (size_t)n * sizeof(int)));
-  return LP_OK;
-}
-
 static unsigned long long* g_trace = nullptr;
 void set_stream_trace(void* buf) { g_trace = reinterpret_cast<unsigned long long*>(buf); }
 
@@ -730,9 +684,6 @@ int linear_stream(const float* x, int M, const lp_weight& W, const NormArgs& nrm
   p.x = x; p.residual = residual; p.out = out; p.W = W; p.nrm = nrm;
   p.M = M; p.split = split; p.epi = epi; p.round_bf16 = round_bf16;
   p.trace = g_trace;
-  p.sk_ws = g_sk_ws;
-  p.sk_flags = g_sk_flags;
-  if (!g_sk_ws) return LP_ERR_UNSUPPORTED;  // lp_init was not called
   const int kpad = (K + 255) / 256 * 256;
   size_t row_bytes;
   int aux_stage = 0;
@@ -768,12 +719,7 @@ int linear_stream(const float* x, int M, const lp_weight& W, const NormArgs& nrm
   if (ns > GS_MAX_STAGES) ns = GS_MAX_STAGES;
   p.nstages = ns;
   const size_t smem = (size_t)ns * p.stage_stride + tail + 1024;  // + slack for the 1 KB alignment of the ring
-  // Measured on B200 (7B int4 / 3B bf16 decode steps): the balanced stage-granular split is SLOWER end to end (2.03 vs
-  // 1.74 ms, 2.70 vs 2.13 ms) — a CTA that starts late now delays its neighbour's finalisation — so it is opt-in.
-  static const int env_streamk = [] { const char* e = getenv("LP_GS_STREAMK"); return e ? atoi(e) : 0; }();
-  p.streamk = env_streamk;
-  const long long total_units = p.streamk ? (long long)p.ntiles * p.nks : (long long)p.ntiles;
-  const int grid = total_units < num_sms() ? (int)total_units : num_sms();
+  const int grid = p.ntiles < num_sms() ? p.ntiles : num_sms();
   if (W.fmt == LP_W_BF16)
     return NB == 1 ? gs_launch<LP_W_BF16, 1>(gm.map, p, smem, grid, stream) : gs_launch<LP_W_BF16, 2>(gm.map, p, smem, grid, stream);
   return NB == 1 ? gs_launch<LP_W_INT4, 1>(gm.map, p, smem, grid, stream) : gs_launch<LP_W_INT4, 2>(gm.map, p, smem, grid, stream);

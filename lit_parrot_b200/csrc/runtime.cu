@@ -43,7 +43,6 @@ int num_sms() {
 }
 
 int init_attention();   // attention.cu
-int init_linear_stream();  // linear_stream.cu
 
 }  // namespace lp
 
@@ -84,9 +83,7 @@ int lp_init(int device) {
   }
   lp::g_sms.store(0);
   (void)lp::num_sms();
-  int rc = lp::init_attention();
-  if (rc != LP_OK) return rc;
-  return lp::init_linear_stream();
+  return lp::init_attention();
 }
 
 }  // extern "C"
