@@ -128,11 +128,11 @@ __device__ __forceinline__ unsigned long long gs_now() {
 }
 
 // One activation row -> shared-memory B-operand columns (see the call site).  s_stat: [2][GS_CWARPS] floats.
-template <int FMT, bool CACHED>
+template <int FMT, bool CACHED, int NIC = 4>
 __device__ __forceinline__ void gs_stage_row(const GsParams& p, int m, int NCOL, int ncols, float* s_stat, uint16_t* xs, signed char* xs8,
                                              float* xsum, float* colscale) {
   constexpr int STRIDE = GS_CWARPS * 32 * 4;
-  constexpr int NI = CACHED ? 4 : 1;
+  constexpr int NI = CACHED ? NIC : 1;
   const int K = p.W.K;
   const int nch128 = (K + 127) / 128;
   const int niter = (nch128 * 128 + STRIDE - 1) / STRIDE;  // covers the zero padding up to a whole 128-column chunk
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
   // later pass costs only a named barrier.
   if ((nch128 * 128 + 2047) / 2048 <= 4) {
     for (int m = 0; m < p.M; ++m) gs_stage_row<FMT, true>(p, m, NCOL, ncols, &s_stat[0][0], xs, xs8, xsum, colscale);
-  } else {
+  } else {  // (a 6-deep register cache for 11008-column rows was tried: it spills and slows the main loop)
     for (int m = 0; m < p.M; ++m) gs_stage_row<FMT, false>(p, m, NCOL, ncols, &s_stat[0][0], xs, xs8, xsum, colscale);
   }
   gs_bar_consumers();

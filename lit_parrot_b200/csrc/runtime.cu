@@ -43,6 +43,7 @@ int num_sms() {
 }
 
 int init_attention();   // attention.cu
+int init_sample();      // sample.cu
 
 }  // namespace lp
 
@@ -83,7 +84,9 @@ int lp_init(int device) {
   }
   lp::g_sms.store(0);
   (void)lp::num_sms();
-  return lp::init_attention();
+  int rc = lp::init_attention();
+  if (rc != LP_OK) return rc;
+  return lp::init_sample();
 }
 
 }  // extern "C"

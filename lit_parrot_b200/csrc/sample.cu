@@ -125,12 +125,84 @@ sample_kernel(const float* __restrict__ logits, int V, float temperature, int to
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Greedy fast path (top_k == 1, the reference's "greedy"): the arg-max of a 50k-65k vocabulary is spread over
+// GREEDY_CTAS CTAs per row; partial (value, index) pairs go to a small global scratch and the last CTA of the row (atomic
+// ticket, self-resetting) reduces them and performs the same device-side bookkeeping as sample_kernel.  Lowest index
+// wins ties, exactly like the single-CTA kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int GREEDY_CTAS = 32;
+constexpr int GREEDY_THREADS = 256;
+constexpr int GREEDY_MAX_ROWS = 256;
+static Best* g_greedy_part = nullptr;   // [GREEDY_MAX_ROWS][GREEDY_CTAS]
+static unsigned int* g_greedy_ticket = nullptr;  // [GREEDY_MAX_ROWS]
+
+int init_sample() {
+  if (g_greedy_part) return LP_OK;
+  LP_CUDA_TRY(cudaMalloc(&g_greedy_part, sizeof(Best) * GREEDY_MAX_ROWS * GREEDY_CTAS));
+  LP_CUDA_TRY(cudaMalloc(&g_greedy_ticket, sizeof(unsigned int) * GREEDY_MAX_ROWS));
+  LP_CUDA_TRY(cudaMemset(g_greedy_ticket, 0, sizeof(unsigned int) * GREEDY_MAX_ROWS));
+  return LP_OK;
+}
+
+__global__ void __launch_bounds__(GREEDY_THREADS)
+greedy_kernel(const float* __restrict__ logits, int V, float temperature, int* __restrict__ step, int* __restrict__ token_out,
+              int* __restrict__ seq_buf, int* __restrict__ pos_inout, Best* __restrict__ part, unsigned int* __restrict__ ticket) {
+  __shared__ Best s_best[GREEDY_THREADS / 32];
+  __shared__ int s_last;
+  pdl_wait();
+  pdl_launch_dependents();
+  const int row = blockIdx.y, tid = threadIdx.x;
+  const float* lg = logits + (size_t)row * V;
+  Best best = {-CUDART_INF_F, 0x7fffffff};
+  for (int i = blockIdx.x * GREEDY_THREADS + tid; i < V; i += GREEDY_CTAS * GREEDY_THREADS) best = better(best, Best{lg[i] / temperature, i});
+  auto block_best = [&](Best b) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b = better(b, Best{__shfl_xor_sync(0xffffffffu, b.v, o), __shfl_xor_sync(0xffffffffu, b.i, o)});
+    __syncthreads();
+    if ((tid & 31) == 0) s_best[tid >> 5] = b;
+    __syncthreads();
+    b = tid < GREEDY_THREADS / 32 ? s_best[tid] : Best{-CUDART_INF_F, 0x7fffffff};
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b = better(b, Best{__shfl_xor_sync(0xffffffffu, b.v, o), __shfl_xor_sync(0xffffffffu, b.i, o)});
+    return b;
+  };
+  best = block_best(best);
+  if (tid == 0) {
+    part[row * GREEDY_CTAS + blockIdx.x] = best;
+    __threadfence();
+    s_last = (atomicAdd(ticket + row, 1u) == GREEDY_CTAS - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  Best b = {-CUDART_INF_F, 0x7fffffff};
+  if (tid < GREEDY_CTAS) {
+    const volatile Best* pp = part + row * GREEDY_CTAS + tid;
+    b = Best{pp->v, pp->i};
+  }
+  b = block_best(b);
+  if (tid == 0) {
+    ticket[row] = 0;
+    token_out[row] = b.i;
+    if (row == 0 && pos_inout) {
+      const int p = *pos_inout;
+      if (seq_buf) seq_buf[p + 1] = b.i;
+      *pos_inout = p + 1;
+    }
+    if (step && gridDim.y == 1) *step = *step + 1;
+  }
+}
+
 }  // namespace lp
 
 extern "C" int lp_sample(const float* logits, int rows, int V, float temperature, int top_k, uint64_t seed, int32_t* step,
                          int32_t* token_out, int32_t* seq_buf, int32_t* pos_inout, void* stream) {
   if (!logits || !token_out || rows <= 0 || V <= 0 || !(temperature > 0.f) || top_k < 0) return LP_ERR_INVALID_ARG;
   if (seq_buf && (rows != 1 || !pos_inout)) return LP_ERR_INVALID_ARG;  // pos_inout alone (any rows): just advance
+  if (top_k == 1 && rows <= lp::GREEDY_MAX_ROWS && lp::g_greedy_part)
+    return lp::launch(lp::greedy_kernel, dim3(lp::GREEDY_CTAS, rows), dim3(lp::GREEDY_THREADS), 0, stream, logits, V, temperature, step,
+                      token_out, seq_buf, pos_inout, lp::g_greedy_part, lp::g_greedy_ticket);
   return lp::launch(lp::sample_kernel, dim3(rows), dim3(lp::SAMPLE_THREADS), 0, stream, logits, V, temperature, top_k, seed, step,
                     token_out, seq_buf, pos_inout);
 }
