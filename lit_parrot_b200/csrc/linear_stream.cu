@@ -312,7 +312,9 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
 
   // Tiles of this CTA: contiguous range of WHOLE tiles.  A stage-granular (stream-K) split with cross-CTA partial sums was
   // tried (git history: "stream-K (opt-in)"): perfectly balanced, but 2.03 vs 1.74 ms per stablelm-3b step and 2.70 vs 2.13 ms
-  // per 7B-int4 step on B200 — a CTA that starts late then also delays its neighbour's tile — so it was dropped.
+  // per 7B-int4 step on B200 — a CTA that starts late then also delays its neighbour's tile — so it was dropped.  A
+  // dynamic tile scheduler (static tiles for the ring depth, atomic claims afterwards) was tried too: no gain (1.78 vs 1.74
+  // ms), because for the small layers the whole per-CTA work fits inside the prefetch ring, i.e. is static anyway.
   const int tile_begin = (int)(((long long)p.ntiles * blockIdx.x) / gridDim.x);
   const int tile_end = (int)(((long long)p.ntiles * (blockIdx.x + 1)) / gridDim.x);
   const int nunits = (tile_end - tile_begin) * p.nks;
