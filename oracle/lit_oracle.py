@@ -7,7 +7,7 @@ legs may import this module, and only as the checker / CPU baseline.  The produc
 (``lit_parrot_b200``) never does.
 
 Pinning: the reference is Python, so this restatement is pinned against the *unmodified* reference
-imported from ``/root/reference`` in the build container (``oracle/check_against_reference.py``) and
+imported from ``/root/reference`` in the build container (``oracle/make_golden.py`` asserts oracle == reference) and
 against the golden vectors that run produced (``tests/golden/*.npz``, made by ``oracle/make_golden.py``).
 The bitsandbytes NF4/int8 arithmetic is NOT in the reference tree (third-party ``bitsandbytes>=0.40.0``,
 unpinned, requirements.txt:5): for those two functions the header below each says "parity unpinned".
