@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LP_ABI_VERSION 2
+#define LP_ABI_VERSION 3
 
 typedef enum {
   LP_OK = 0,
@@ -179,6 +179,70 @@ int lp_attn_decode_fused(const float* qkv, const float* cos, const float* sin, c
  * guarantees the positions are consecutive and do not wrap); LP_ERR_UNSUPPORTED otherwise -> lp_attn_decode. */
 int lp_attn_prefill(const float* q, const void* k_cache, const void* v_cache, int kv_dtype, const int32_t* pos, float* out, int B,
                     int T, int H, int G, int hs, int max_seq, float scale, int round_bf16, void* stream);
+
+/* ---- the whole single-token decode step (batch 1) as ONE persistent kernel ------------------------------------------
+ * replaces GPT.forward for T == 1 (model.py:63-111 -> Block.forward 158-180 -> CausalSelfAttention.forward 194-254 -> MLP
+ * 284-301): the caller describes the step once as an ordered table of ops — LINEAR (lp_norm_linear semantics, M = 1) and
+ * ATTENTION (lp_attn_decode_fused semantics) — and lp_decode_step then runs it with two launches (embedding-row prologue +
+ * step kernel).  Inside the step kernel one TMA ring per SM streams the weights and the old K/V rows of ALL ops back to back
+ * (they do not depend on the activations), so HBM stays busy while the consumers wait on the grid-wide arrival counter of an
+ * op they depend on (csrc/decode_step.cu).
+ *   dep: index of the latest earlier op whose output this op's input (x / qkv / attention partials) is — the op waits until
+ *        every CTA has finished op `dep` (and therefore all ops before it); -1 = inputs of the step only.
+ *   residual: must be covered by `dep`, be a step input, or be the output of an earlier LINEAR op with the same N (the same
+ *        CTA then wrote the rows it reads); checked by lp_decode_step_plan.
+ * Covers fp32-activation mode, bf16 / GPTQ-int4 (tile-major aux2) weights, multi-head attention (H == G), bf16 KV cache,
+ * hs 64 / 128; LP_ERR_UNSUPPORTED otherwise (callers then issue the per-op calls above). */
+typedef enum { LP_STEP_LINEAR = 0, LP_STEP_ATTENTION = 1 } lp_step_kind;
+
+typedef struct {
+  int32_t kind;            /* lp_step_kind */
+  int32_t dep;
+  /* LINEAR: out = epilogue(norm(x) . W^T + bias [, residual]); x_is_attention: x is the output of the preceding ATTENTION
+   * op (its split partials are merged while the row is staged) */
+  const lp_weight* W;
+  const float* x;
+  int32_t x_is_attention;
+  int32_t norm_kind;       /* lp_norm_kind, or -1: none */
+  const float* norm_w;
+  const float* norm_b;
+  float eps;
+  int32_t epilogue;        /* lp_epilogue */
+  const float* residual;
+  float* out;
+  /* ATTENTION: qkv [ (H+2G)*hs ] raw projection of this token, caches [G, max_seq, hs] bf16 */
+  const float* qkv;
+  void* k_cache;
+  void* v_cache;
+} lp_step_op;
+
+typedef struct {
+  const int32_t* pos;        /* [1] device-side position of the token being decoded                               */
+  const void* idx;           /* token ids (int32 / int64); the step embeds idx[idx_offset ? *idx_offset : 0]      */
+  const int32_t* idx_offset;
+  const void* wte;           /* embedding table [V, E] in wte_dtype (lp_dtype)                                    */
+  float* x0;                 /* [E] residual stream: written by the prologue, input of the first op               */
+  const float* cos;          /* RoPE tables fp32 [block_size, n_elem]                                             */
+  const float* sin;
+  void* workspace;           /* lp_decode_step_workspace_bytes(H, hs)                                             */
+  size_t workspace_bytes;
+  int32_t idx_is_int64, wte_dtype, E, H, G, hs, n_elem, max_seq, kv_dtype;
+  float scale;               /* softmax scale, 1/sqrt(hs)                                                         */
+} lp_step_geom;
+
+typedef struct { uint64_t opaque[32]; } lp_step_handle;  /* filled by lp_decode_step_plan; plain data, copyable */
+
+size_t lp_decode_step_plan_bytes(int n_ops);
+size_t lp_decode_step_workspace_bytes(int H, int hs);
+/* Load time (synchronous copy, not capturable): validates the table, builds the TMA descriptors and writes the device-side
+ * op table into plan_dev (128-byte aligned, lp_decode_step_plan_bytes(n_ops)). */
+int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* geom, void* plan_dev, size_t plan_bytes,
+                        lp_step_handle* handle);
+/* One decode step: 2 launches, graph-capturable, no allocation, no synchronisation. */
+int lp_decode_step(const lp_step_handle* handle, void* stream);
+/* Debug aid: device_buf (>= n_ops * 148 * 8 uint64) receives per-(op, CTA) globaltimer stamps [start, dependency met,
+ * activations staged, end, x loaded, normalised, max|x| known, -]; NULL switches it off. */
+int lp_debug_step_trace(void* device_buf);
 
 /* Tensor-parallel exchange fused with the residual add: out[n] = residual[n] + sum over ranks of partial_r[n], n fp32.
  * `buf_ptrs_dev` / `pad_ptrs_dev`: device arrays of `tp` peer-mapped addresses (symmetric buffer and signal pad of every

@@ -17,8 +17,9 @@ LP_F32, LP_BF16 = 0, 1
 LP_W_F32, LP_W_BF16, LP_W_INT4, LP_W_NF4, LP_W_INT8 = 0, 1, 2, 3, 4
 LP_EPI_NONE, LP_EPI_GELU, LP_EPI_SWIGLU, LP_EPI_RESIDUAL = 0, 1, 2, 3
 LP_NORM_LAYERNORM, LP_NORM_RMS = 0, 1
-LP_ABI_VERSION = 2
+LP_ABI_VERSION = 3
 LP_WF_AUX_PACKED = 1
+LP_STEP_LINEAR, LP_STEP_ATTENTION = 0, 1
 
 c_void_p, c_int, c_float, c_size_t, c_u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_uint64
 
@@ -29,6 +30,31 @@ class LpWeight(ctypes.Structure):
     _fields_ = [("w", c_void_p), ("aux0", c_void_p), ("aux1", c_void_p), ("aux2", c_void_p), ("bias", c_void_p),
                 ("fmt", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32), ("group", ctypes.c_int32),
                 ("flags", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class LpStepOp(ctypes.Structure):
+    """struct lp_step_op: one entry of the decode-step op table"""
+
+    _fields_ = [("kind", ctypes.c_int32), ("dep", ctypes.c_int32), ("W", ctypes.POINTER(LpWeight)), ("x", c_void_p),
+                ("x_is_attention", ctypes.c_int32), ("norm_kind", ctypes.c_int32), ("norm_w", c_void_p), ("norm_b", c_void_p),
+                ("eps", c_float), ("epilogue", ctypes.c_int32), ("residual", c_void_p), ("out", c_void_p),
+                ("qkv", c_void_p), ("k_cache", c_void_p), ("v_cache", c_void_p)]
+
+
+class LpStepGeom(ctypes.Structure):
+    """struct lp_step_geom"""
+
+    _fields_ = [("pos", c_void_p), ("idx", c_void_p), ("idx_offset", c_void_p), ("wte", c_void_p), ("x0", c_void_p),
+                ("cos", c_void_p), ("sin", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+                ("idx_is_int64", ctypes.c_int32), ("wte_dtype", ctypes.c_int32), ("E", ctypes.c_int32), ("H", ctypes.c_int32),
+                ("G", ctypes.c_int32), ("hs", ctypes.c_int32), ("n_elem", ctypes.c_int32), ("max_seq", ctypes.c_int32),
+                ("kv_dtype", ctypes.c_int32), ("scale", c_float)]
+
+
+class LpStepHandle(ctypes.Structure):
+    """struct lp_step_handle (opaque)"""
+
+    _fields_ = [("opaque", ctypes.c_uint64 * 32)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/lp_abi.h
@@ -60,6 +86,12 @@ PROTOTYPES = {
                                      c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "lp_attn_prefill": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_float, c_int, c_void_p]),
+    "lp_decode_step_plan_bytes": (c_size_t, [c_int]),
+    "lp_decode_step_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "lp_decode_step_plan": (c_int, [ctypes.POINTER(LpStepOp), c_int, ctypes.POINTER(LpStepGeom), c_void_p, c_size_t,
+                                    ctypes.POINTER(LpStepHandle)]),
+    "lp_decode_step": (c_int, [ctypes.POINTER(LpStepHandle), c_void_p]),
+    "lp_debug_step_trace": (c_int, [c_void_p]),
     "lp_tp_allreduce_residual": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                          c_void_p]),
     "lp_sample": (c_int, [c_void_p, c_int, c_int, c_float, c_int, c_u64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -1,0 +1,1206 @@
+// The whole single-token decode step (batch 1) as ONE persistent kernel: every linear layer of every block, the attention
+// of every block and the lm_head, behind a single TMA ring that never stops streaming.
+//
+//   reference: GPT.forward (model.py:63-111) -> Block.forward (158-180) -> CausalSelfAttention.forward (194-254, apply_rope
+//   330-336, cache index_copy_ 236-245, scaled_dot_product_attention 256-275) -> MLP (284-301), for T == 1.
+//
+// Why: with one launch per op a replayed int4 Llama-2-7b layer spends 21 us streaming weights and 45 us on what surrounds a
+// launch (activation staging, ramp-up / drain of the ring, tile skew, attention start-up; profiles/r1_results.md).  Weights
+// and old K/V rows do not depend on the activations, so here
+//   * one PRODUCER thread per CTA walks a static op table (device memory: TMA descriptor + shapes per op) and keeps a ring of
+//     16 KB stages full: `cp.async.bulk.tensor.3d` weight stages (linear_stream.cu layout), 16 KB `cp.async.bulk` K / V tiles
+//     for attention.  It only ever waits for a free ring slot: while the consumers sit at a grid-wide dependency the ring
+//     fills with the NEXT ops' bytes, HBM stays busy across op boundaries;
+//   * sixteen CONSUMER warps execute the ops in order.  An op that reads another op's output waits for that op's arrival
+//     counter (one `red.release.gpu` per CTA, polled with `ld.acquire.gpu`), re-stages its activation row (fused LayerNorm /
+//     RMSNorm, bf16 term split or int8 digit split as in linear_stream.cu) and drains the ring: mma.sync bf16 / IMMA int4;
+//   * attention (MHA): head h is split over P = #CTAs / H CTAs along the sequence; RoPE(q, k_new), the cache append (global
+//     + patch of the landed tile), q.K^T, online softmax and P.V run on the CUDA cores straight from the ring stages; the
+//     (m, l, o) partials of the P splits are merged by the attention-projection's activation staging — no extra pass.
+// The op table is built once per (model, cache) by lp_decode_step_plan; a step is lp_decode_step: a tiny prologue kernel
+// (embedding row, counter reset) + this kernel.  Judged on whole-step GB/s against the HBM roofline.
+#include <math_constants.h>
+
+#include <cstring>
+#include <vector>
+
+#include "stream_common.cuh"
+
+namespace lp {
+
+constexpr int DS_MAXP = 4;           // max sequence splits per head
+constexpr int DS_CTHREADS = GS_CWARPS * 32;
+constexpr int DS_EWARPS = 2;                                   // epilogue warps (tile parity 0 / 1)
+constexpr int DS_THREADS = (GS_CWARPS + 1 + DS_EWARPS) * 32;   // consumers + producer warp + epilogue warps
+constexpr int DS_TILE_BAR_THREADS = DS_CTHREADS + 32;          // named barriers 2 / 3: the consumers arrive, one epilogue warp waits
+constexpr int DS_OPEND_THREADS = DS_CTHREADS + DS_EWARPS * 32; // named barrier 4: end of an op
+constexpr int DS_KIND_LINEAR = 0;
+constexpr int DS_RED_FLOATS = 2 * GS_CWARPS * 16 * 4;  // [2 parities][warps][16 rows][4 B-columns]
+
+struct alignas(128) DsOp {
+  CUtensorMap map;  // linear: weight matrix {128 B, N rows, K-blocks}
+  const float* x;
+  const float* residual;
+  float* out;
+  const float* bias;
+  const float* nw;
+  const float* nb;
+  const void* aux2;
+  const float* qkv;       // attention
+  __nv_bfloat16* kc;
+  __nv_bfloat16* vc;
+  float eps;
+  int kind, dep, signal;
+  int norm_kind, epi, fmt, N, K, split, ldx, nkb, nks, ntiles, ngroups, gp128, aux_bytes, x_attn;
+};
+
+struct DsParams {
+  const DsOp* ops;
+  unsigned* counters;  // [nops], zeroed by the prologue kernel of every step
+  const int* pos;
+  const float* cosT;
+  const float* sinT;
+  float* part;         // attention partials [H][P][hs + 4]
+  unsigned long long* trace;
+  float scale_log2;
+  int nops, H, n_elem, max_seq, P;
+  int nstages, stage_stride, xsum_floats;
+};
+
+__device__ __forceinline__ unsigned ds_ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ds_ld_relaxed(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ds_red_release(unsigned* p) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ float4 ds_ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+// `bytes` (multiple of 16) of constants into L2: issued by the producer thread well ahead of the consumers' need
+__device__ __forceinline__ void ds_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p), "r"(bytes) : "memory");
+}
+
+struct DsRing {
+  uint32_t bar0, ring_u32;
+  unsigned char* ring;
+  int nstages, stage_stride;
+  int s, ph;
+  __device__ __forceinline__ uint32_t full() const { return bar0 + 8 * s; }
+  __device__ __forceinline__ uint32_t empty() const { return bar0 + 8 * (nstages + s); }
+  __device__ __forceinline__ void advance() {
+    if (++s == nstages) { s = 0; ph ^= 1; }
+  }
+};
+
+// Attention geometry of this step (depends on the device-side position).
+template <int HS>
+struct DsAttnGeo {
+  static constexpr int TPK = HS / 16;             // threads per key in q.K^T (16 dims each)
+  static constexpr int AT = DS_CTHREADS / TPK;    // keys per 16 KB tile
+  static constexpr int DCH = HS / 8;              // 16-byte chunks per row
+  static constexpr int NSL = DS_CTHREADS / DCH;   // key slices in P.V (2 keys of a tile each)
+  static constexpr int LDM = HS + 4;              // partial record: o[HS], m, l, pad
+  int pos, kv_len, slot, nblk, bpp, slot_blk;
+  __device__ __forceinline__ void init(const DsParams& p) {
+    pos = p.pos[0];
+    kv_len = min(pos + 1, p.max_seq);
+    slot = pos % p.max_seq;
+    nblk = (kv_len + AT - 1) / AT;
+    bpp = (nblk + p.P - 1) / p.P;
+    slot_blk = slot / AT;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ shared-memory access
+// The hot loops address shared memory through 32-bit shared-space addresses (generic pointers cost an address
+// conversion per access).
+__device__ __forceinline__ uint4 ds_lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 ds_lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t ds_lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 ds_lds128f(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 ds_lds64f(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void ds_sts64f(uint32_t a, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1,%2};\n" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ void ds_sts64(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1,%2};\n" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void ds_sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
+// Loop invariants that ptxas would otherwise rematerialise from %tid / kernel parameters in every iteration of the stage
+// loop (measured: ~40 of 133 instructions per warp-stage): an opaque move keeps them in their register.
+__device__ __forceinline__ uint32_t ds_pin(uint32_t v) {
+  asm volatile("mov.b32 %0, %1;\n" : "=r"(v) : "r"(v));
+  return v;
+}
+__device__ __forceinline__ int ds_pin(int v) { return (int)ds_pin((uint32_t)v); }
+
+// ------------------------------------------------------------------------------------------------ activation staging
+// One activation row -> shared-memory B-operand columns.  Thread `ctid` owns the 8 consecutive columns 8 ctid + 4096 i of
+// every pass, so the row is read from L2 once (activations are produced by other SMs inside this kernel: __ldcg) and kept
+// in registers through the norm statistics, max|x| and the conversion; every term / digit row is written with one 8- or
+// 16-byte store per 8 columns.  NI = 2 (K <= 8192; norm parameters cached as well) or 4 (K <= 16384).
+//   bf16 weights: x = hi + mid (+ lo) as bf16 rows [split][ldx];
+//   int4 weights: block fixed point X = rint(x * 2^22 / max|x|) as three balanced base-256 int8 digit rows, bytes of an 8-column
+//   group in IMMA operand order (even columns, then odd columns), plus the per-128-column digit sums (zero-point term).
+template <int NI, class LoadX, class WaitDep>
+__device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDep wait_dep, float* s_stat, uint32_t xs_u32, float* xsum,
+                                             float* colscale, unsigned long long* tr) {
+  constexpr int STRIDE = DS_CTHREADS * 8;
+  constexpr bool WCACHE = NI <= 2;
+  const int K = o.K, fmt = o.fmt, split = o.split, ldx = o.ldx, norm_kind = o.norm_kind;
+  const float* nw = o.nw;
+  const float* nb = o.nb;
+  const int kpad = (K + 127) / 128 * 128;
+  const int ctid = threadIdx.x, warp = ctid >> 5, lane = ctid & 31;
+  const bool has_norm = norm_kind >= 0, has_bias = has_norm && norm_kind == LP_NORM_LAYERNORM;
+  float x[NI][8];
+  float wq[WCACHE ? NI : 1][8], bq[WCACHE ? NI : 1][8];
+  auto ld8 = [&](const float* base, int k, float (&d)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(base + k), b = *reinterpret_cast<const float4*>(base + k + 4);
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+  };
+  // norm parameters are constants: fetch them BEFORE waiting for the producer op, so that they are neither part of the burst of
+  // activation loads all CTAs issue at the same moment nor on the critical path behind the dependency
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int k = ctid * 8 + i * STRIDE;
+    if (WCACHE && has_norm && k < K) {
+      ld8(nw, k, wq[WCACHE ? i : 0]);
+      if (has_bias) ld8(nb, k, bq[WCACHE ? i : 0]);
+    }
+  }
+  wait_dep();
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int k = ctid * 8 + i * STRIDE;
+    if (k < K) {
+      const float4 a = load_x(k), b = load_x(k + 4);
+      x[i][0] = a.x; x[i][1] = a.y; x[i][2] = a.z; x[i][3] = a.w; x[i][4] = b.x; x[i][5] = b.y; x[i][6] = b.z; x[i][7] = b.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) x[i][q] = 0.f;
+    }
+  }
+  if (tr && ctid == 0) {
+    float acc0 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) acc0 += x[i][0] + (WCACHE && has_norm ? wq[WCACHE ? i : 0][0] : 0.f);
+    if (acc0 != 12345.678f) tr[4] = gs_now();  // the loads have returned
+  }
+  int sbuf = 0;
+  // block-wide (sum or max of a, sum of b); one barrier per reduction: the statistics buffer is double buffered
+  auto block_reduce = [&](float a, float b, bool is_max, float& ra, float& rb) {
+    a = is_max ? warp_max(a) : warp_sum(a);
+    b = warp_sum(b);
+    float* st = s_stat + sbuf * 2 * GS_CWARPS;
+    sbuf ^= 1;
+    if (lane == 0) {
+      st[warp] = a;
+      st[GS_CWARPS + warp] = b;
+    }
+    gs_bar_consumers();
+    const float4* s4 = reinterpret_cast<const float4*>(st);
+    ra = 0.f;
+    rb = 0.f;
+#pragma unroll
+    for (int w = 0; w < GS_CWARPS / 4; ++w) {
+      const float4 va = s4[w], vb = s4[GS_CWARPS / 4 + w];
+      ra = is_max ? fmaxf(fmaxf(ra, fmaxf(va.x, va.y)), fmaxf(va.z, va.w)) : ra + ((va.x + va.y) + (va.z + va.w));
+      rb += (vb.x + vb.y) + (vb.z + vb.w);
+    }
+  };
+  float amax_pre = -1.f;  // max|x| when it came for free with the norm statistics
+  if (has_norm && !has_bias && fmt == LP_W_INT4 && WCACHE) {
+    // RMSNorm feeding an int4 layer: x_n = w x rstd, so max|x_n| = rstd max|w x|: ONE reduction gives both statistics
+    float ss = 0.f, mw = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        ss = fmaf(x[i][q], x[i][q], ss);
+        mw = fmaxf(mw, fabsf(wq[WCACHE ? i : 0][q] * x[i][q]));
+      }
+    block_reduce(mw, ss, true, mw, ss);
+    const float rstd = 1.0f / sqrtf(ss / (float)K + o.eps);
+    float am = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        x[i][q] = wq[WCACHE ? i : 0][q] * (x[i][q] * rstd);
+        am = fmaxf(am, fabsf(x[i][q]));
+      }
+    // every thread needs the SAME max: take the bound rstd * max|w x| rounded up a little instead of a second reduction
+    // (the products above are rounded differently than w * x alone, by at most 2 ulp)
+    amax_pre = mw * rstd * 1.000001f;
+    (void)am;
+  } else if (has_norm) {
+    float sm = 0.f, ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        sm += x[i][q];
+        ss = fmaf(x[i][q], x[i][q], ss);
+      }
+    block_reduce(sm, ss, false, sm, ss);
+    float mean = 0.f, rstd;
+    if (has_bias) {
+      mean = sm / (float)K;
+      float v2 = 0.f, dummy;  // two-pass variance
+#pragma unroll
+      for (int i = 0; i < NI; ++i)
+        if (ctid * 8 + i * STRIDE < K) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float d = x[i][q] - mean;
+            v2 = fmaf(d, d, v2);
+          }
+        }
+      block_reduce(v2, 0.f, false, v2, dummy);
+      rstd = 1.0f / sqrtf(v2 / (float)K + o.eps);
+    } else {
+      rstd = 1.0f / sqrtf(ss / (float)K + o.eps);
+    }
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int k = ctid * 8 + i * STRIDE;
+      if (k < K) {
+        float wl[8], bl[8];
+        if (!WCACHE) {
+          ld8(nw, k, wl);
+          if (has_bias) ld8(nb, k, bl);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float wv = WCACHE ? wq[WCACHE ? i : 0][q] : wl[q];
+          if (has_bias) x[i][q] = (x[i][q] - mean) * rstd * wv + (WCACHE ? bq[WCACHE ? i : 0][q] : bl[q]);
+          else x[i][q] = wv * (x[i][q] * rstd);
+        }
+      }
+    }
+  }
+  if (tr && ctid == 0) tr[5] = gs_now();  // normalised
+  if (fmt == LP_W_INT4) {
+    float amax = amax_pre, dummy;
+    if (amax_pre < 0.f) {
+      amax = 0.f;
+#pragma unroll
+      for (int i = 0; i < NI; ++i)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) amax = fmaxf(amax, fabsf(x[i][q]));
+      block_reduce(amax, 0.f, true, amax, dummy);
+    }
+    if (tr && ctid == 0) tr[6] = gs_now();  // max|x| known
+    const float inv = amax > 0.f ? 4194304.0f / amax : 0.f;
+    if (ctid < 3) colscale[ctid] = (amax / 4194304.0f) * (ctid == 0 ? 1.0f : (ctid == 1 ? 256.0f : 65536.0f));
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int k = ctid * 8 + i * STRIDE;
+      if (k < kpad) {  // half-warp uniform (a 128-column chunk = 16 threads): the zero padding of the last chunk is written too
+        int dg[3][8], sum[3] = {0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          // X = d0 + 256 d1 + 65536 d2 with balanced digits d0, d1 in [-128, 127]
+          const int X = __float2int_rn(x[i][q] * inv);
+          const int t1 = (X + 128) >> 8;
+          const int d0 = X - (t1 << 8);
+          const int d2 = (t1 + 128) >> 8;
+          const int d1 = t1 - (d2 << 8);
+          dg[0][q] = d0; dg[1][q] = d1; dg[2][q] = d2;
+          sum[0] += d0; sum[1] += d1; sum[2] += d2;
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          // bytes of the 8-column group in operand order: columns 0,2,4,6 (IMMA a0/a1 side), then 1,3,5,7 (a2/a3 side)
+          const uint32_t lo = __byte_perm(__byte_perm(dg[d][0], dg[d][2], 0x0040), __byte_perm(dg[d][4], dg[d][6], 0x0040), 0x5410);
+          const uint32_t hi = __byte_perm(__byte_perm(dg[d][1], dg[d][3], 0x0040), __byte_perm(dg[d][5], dg[d][7], 0x0040), 0x5410);
+          ds_sts64(xs_u32 + (uint32_t)(d * ldx + k), lo, hi);
+          float ps = (float)sum[d];
+#pragma unroll
+          for (int off = 8; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
+          if ((lane & 15) == 0) xsum[(k >> 7) * 4 + d] = ps;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int k = ctid * 8 + i * STRIDE;
+      if (k < K) {
+#pragma unroll
+        for (int sp = 0; sp < 3; ++sp) {
+          if (sp < split) {
+            uint32_t w2[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t h0 = gs_bf16_bits(x[i][2 * q]), h1 = gs_bf16_bits(x[i][2 * q + 1]);
+              x[i][2 * q] -= __uint_as_float(h0 << 16);  // exact: next term of the split
+              x[i][2 * q + 1] -= __uint_as_float(h1 << 16);
+              w2[q] = h0 | (h1 << 16);
+            }
+            ds_sts128(xs_u32 + (uint32_t)(sp * ldx + k) * 2, w2[0], w2[1], w2[2], w2[3]);
+          }
+        }
+      }
+    }
+    if (ctid < split) colscale[ctid] = 1.0f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ one linear op (consumers)
+// Main loop of one linear op, specialised per weight format.  Per 16 KB stage a warp handles half a K-block of the 16-row
+// tile: bf16: 2 x (ldmatrix.x4 + mma.sync.m16n8k16) against the bf16 term columns; int4: 4 x IMMA m16n8k32 u8 x s8 against the
+// int8 digit columns, then the per-group scale / zero point.  Everything that does not change from stage to stage (lane
+// offsets inside a stage, the position of the warp's K-slice) lives in registers; per stage: wait, loads, math, arrive.
+template <int FMT, bool PACKED>
+__device__ __forceinline__ void ds_linear_main(const DsOp& o, DsRing& rg, uint32_t red_u32, const float* colscale, uint32_t xsum_u32,
+                                               uint32_t xs_u32, volatile int* done, int tile_begin, int tile_end, int& gt) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int nks = o.nks, split = o.split, ldx = o.ldx, gp128 = o.gp128;
+  const int kbl = warp >> 1, sub0 = warp & 1;
+  const int bcol = g < split ? g : split - 1;  // B columns >= split only feed accumulator columns nobody reads
+  const int nunits = (tile_end - tile_begin) * nks;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  (void)colscale;
+
+  // lane-constant byte offsets inside a stage, and the K position of this warp's slice in the first stage of a tile
+  uint32_t woff0, woff1, xpos0, xstep;
+  int slice0, nslices;  // this warp's slice index in stage 0 and the number of slices per row (bounds check of the last stage)
+  const int pr0 = (g >> 1) + 4 * (g & 1);  // int4: MMA row g <-> tile row pr0 (bank-conflict-free under the 128-byte swizzle)
+  if (FMT == LP_W_BF16) {
+    const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
+    woff0 = kbl * GS_BLK_BYTES + row * 128 + ((((sub0 * 2 + 0) * 2 + (lane >> 4)) ^ (row & 7)) << 4);
+    woff1 = kbl * GS_BLK_BYTES + row * 128 + ((((sub0 * 2 + 1) * 2 + (lane >> 4)) ^ (row & 7)) << 4);
+    xpos0 = xs_u32 + (uint32_t)(bcol * ldx + kbl * 64 + sub0 * 32 + 2 * t) * 2;
+    xstep = GS_KB * 64 * 2;
+    slice0 = kbl;
+    nslices = o.nkb;
+  } else {
+    woff0 = kbl * GS_BLK_BYTES + pr0 * 128 + (((sub0 * 4 + t) ^ (pr0 & 7)) << 4);
+    woff1 = woff0 + 8 * 128;
+    xpos0 = xs_u32 + (uint32_t)(bcol * ldx + (kbl * 2 + sub0) * 128 + t * 32);
+    xstep = GS_KB * 2 * 128;
+    slice0 = kbl * 2 + sub0;
+    nslices = (o.K + 127) / 128;
+  }
+  const int slice_step = FMT == LP_W_BF16 ? GS_KB : GS_KB * 2;
+  constexpr int AUXB = PACKED ? 4 : 8;
+  const uint32_t xsum0 = ds_pin(xsum_u32 + (uint32_t)((kbl * 2 + sub0) * 4 + 2 * (t & 1)) * 4);
+  const uint32_t aux0 = ds_pin((uint32_t)(GS_KB * GS_BLK_BYTES + (slice0 * 16 + pr0) * AUXB));  // group 128: scale slot of this slice
+  const uint32_t auxr = ds_pin((uint32_t)(GS_KB * GS_BLK_BYTES + pr0 * AUXB));
+  woff0 = ds_pin(woff0);
+  woff1 = ds_pin(woff1);
+  xpos0 = ds_pin(xpos0);
+  slice0 = ds_pin(slice0);
+  const bool lane0 = ds_pin(lane) == 0;
+  const uint32_t ring_u32 = ds_pin(rg.ring_u32), bar0 = ds_pin(rg.bar0);
+  const int nstages = ds_pin(rg.nstages), stage_stride = ds_pin(rg.stage_stride);
+  int rs = rg.s, rph = rg.ph;
+  uint32_t xpos = xpos0, xsp = xsum0;
+  int slice = slice0;
+
+  int ks = 0, tile = tile_begin;
+  for (int u = 0; u < nunits; ++u) {
+    mbar_wait(bar0 + 8 * rs, rph);
+    const uint32_t st = ring_u32 + (uint32_t)(rs * stage_stride);
+    if (slice < nslices) {
+      if (FMT == LP_W_BF16) {
+        uint32_t a[4], c[4];
+        gs_ldsm_x4(a, st + woff0);
+        gs_ldsm_x4(c, st + woff1);
+        const uint32_t b0 = ds_lds32(xpos), b1 = ds_lds32(xpos + 16), b2 = ds_lds32(xpos + 32), b3 = ds_lds32(xpos + 48);
+        gs_mma(acc, a[0], a[1], a[2], a[3], b0, b1);
+        gs_mma(acc, c[0], c[1], c[2], c[3], b2, b3);
+      } else {
+        const uint4 wa = ds_lds128(st + woff0), wb = ds_lds128(st + woff1);
+        const uint4 xv0 = ds_lds128(xpos), xv1 = ds_lds128(xpos + 16);
+        const float2 xsv = ds_lds64f(xsp);
+        // scale / zero of this row pair for the slice's group (aux block behind the weights of the stage)
+        const uint32_t ap = st + (gp128 == 1 ? aux0 : auxr + (uint32_t)(slice / gp128 - (ks * GS_KB * 2) / gp128) * 16 * AUXB);
+        float s0, s1, z0, z1;
+        if (PACKED) {  // bf16 scale << 16 | bf16 zero
+          const uint32_t u0 = ds_lds32(ap), u1 = ds_lds32(ap + 8 * AUXB);
+          s0 = __uint_as_float(u0 & 0xffff0000u);
+          s1 = __uint_as_float(u1 & 0xffff0000u);
+          z0 = __uint_as_float(u0 << 16);
+          z1 = __uint_as_float(u1 << 16);
+        } else {
+          const float2 a0 = ds_lds64f(ap), a1 = ds_lds64f(ap + 8 * AUXB);
+          s0 = a0.x; z0 = a0.y; s1 = a1.x; z1 = a1.y;
+        }
+        // low nibbles (even columns) and high nibbles (odd columns, left in place: 16 q) go through separate IMMAs, so the
+        // unpack is one LOP3 per operand register; 16 q d sums are exact multiples of 16 and rescaled in fp32.
+        int cl[4] = {0, 0, 0, 0}, ch[4] = {0, 0, 0, 0};
+        const uint32_t ML = 0x0F0F0F0Fu, MH = 0xF0F0F0F0u;
+        gs_imma(cl, wa.x & ML, wb.x & ML, wa.y & ML, wb.y & ML, xv0.x, xv0.z);
+        gs_imma(ch, wa.x & MH, wb.x & MH, wa.y & MH, wb.y & MH, xv0.y, xv0.w);
+        gs_imma(cl, wa.z & ML, wb.z & ML, wa.w & ML, wb.w & ML, xv1.x, xv1.z);
+        gs_imma(ch, wa.z & MH, wb.z & MH, wa.w & MH, wb.w & MH, xv1.y, xv1.w);
+        // sum (q - z) s x = s * (sum q X - z * sum X), all integers exact in fp32 (|.| < 2^24)
+        acc[0] = fmaf(s0, fmaf((float)ch[0], 0.0625f, fmaf(-z0, xsv.x, (float)cl[0])), acc[0]);
+        acc[1] = fmaf(s0, fmaf((float)ch[1], 0.0625f, fmaf(-z0, xsv.y, (float)cl[1])), acc[1]);
+        acc[2] = fmaf(s1, fmaf((float)ch[2], 0.0625f, fmaf(-z1, xsv.x, (float)cl[2])), acc[2]);
+        acc[3] = fmaf(s1, fmaf((float)ch[3], 0.0625f, fmaf(-z1, xsv.y, (float)cl[3])), acc[3]);
+      }
+    }
+    __syncwarp();
+    if (lane0) mbar_arrive(bar0 + 8 * (nstages + rs));
+    if (++rs == nstages) { rs = 0; rph ^= 1; }
+    xpos += xstep;
+    xsp += GS_KB * 2 * 4 * 4;
+    slice += slice_step;
+
+    if (++ks == nks) {
+      ks = 0;
+      xpos = xpos0;
+      xsp = xsum0;
+      slice = slice0;
+      // tile finished: every warp drops its partial sums (columns 0..3) and moves on; the epilogue warp of this parity
+      // finalises.  `gt` numbers the tiles of this CTA across ALL ops: parity = gt & 1, and a `red` buffer may be rewritten once
+      // the previous tile of the same parity has been finalised (done[par] counts finalised tiles).
+      const int par = gt & 1;
+      while (done[par] < (gt >> 1)) {}
+      if (t < 2) {
+        const int prow = FMT == LP_W_INT4 ? pr0 : g;  // tile row held by accumulator row g
+        const uint32_t r = red_u32 + (uint32_t)(((par * GS_CWARPS + warp) * 16 + prow) * 4 + 2 * t) * 4;
+        ds_sts64f(r, acc[0], acc[1]);
+        ds_sts64f(r + 8 * 4 * 4, acc[2], acc[3]);
+      }
+      acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+      // barrier ids are immediates on purpose (a register id makes ptxas reserve all 16 named barriers)
+      if (par == 0) asm volatile("bar.arrive 2, %0;\n" ::"n"(DS_TILE_BAR_THREADS) : "memory");
+      else asm volatile("bar.arrive 3, %0;\n" ::"n"(DS_TILE_BAR_THREADS) : "memory");
+      ++gt;
+      ++tile;
+    }
+  }
+  rg.s = rs;
+  rg.ph = rph;
+}
+
+template <int HS, class WaitDep>
+__device__ __forceinline__ void ds_linear(const DsParams& p, const DsOp& o, const DsAttnGeo<HS>& geo, DsRing& rg, uint32_t red_u32,
+                                          float* colscale, float* xsum, uint32_t xs_u32, volatile int* done, float* s_stat,
+                                          unsigned long long* tr, int& gt, WaitDep wait_dep) {
+  const int ntiles = o.ntiles;
+  const int tile_begin = (int)(((long long)ntiles * blockIdx.x) / gridDim.x);
+  const int tile_end = (int)(((long long)ntiles * (blockIdx.x + 1)) / gridDim.x);
+  if (tile_end == tile_begin) {  // CTA-uniform: nothing to compute, but later ops rely on the (cumulative) dependency
+    wait_dep();
+    return;
+  }
+  // ---- stage x ----
+  const bool small = o.K <= 2 * DS_CTHREADS * 8;
+  if (o.x_attn) {
+    // x = attention output: merge the P sequence-split partials (m, l, o[hs]) of every head on the fly
+    const int nvalid = (geo.nblk + geo.bpp - 1) / geo.bpp;  // splits with at least one key block
+    const float* part = p.part;
+    const int P = p.P;
+    auto load_attn = [&](int k) -> float4 {
+      constexpr int LDM = DsAttnGeo<HS>::LDM;
+      const int h = k / HS, d = k % HS;
+      const float* base = part + (size_t)h * P * LDM;
+      float m[DS_MAXP], l[DS_MAXP];
+      float4 ov[DS_MAXP];
+#pragma unroll
+      for (int q = 0; q < DS_MAXP; ++q) {
+        if (q < nvalid) {
+          const float2 ml = __ldcg(reinterpret_cast<const float2*>(base + q * LDM + HS));
+          m[q] = ml.x;
+          l[q] = ml.y;
+          ov[q] = ds_ldcg4(base + q * LDM + d);
+        } else {
+          m[q] = -CUDART_INF_F;
+          l[q] = 0.f;
+          ov[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      float mx = m[0];
+#pragma unroll
+      for (int q = 1; q < DS_MAXP; ++q) mx = fmaxf(mx, m[q]);
+      float L = 0.f;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < DS_MAXP; ++q) {  // split order: deterministic
+        const float c = exp2f(m[q] - mx);
+        L = fmaf(l[q], c, L);
+        acc.x = fmaf(ov[q].x, c, acc.x); acc.y = fmaf(ov[q].y, c, acc.y);
+        acc.z = fmaf(ov[q].z, c, acc.z); acc.w = fmaf(ov[q].w, c, acc.w);
+      }
+      const float inv = 1.0f / L;
+      return make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    };
+    ds_stage_row<2>(o, load_attn, wait_dep, s_stat, xs_u32, xsum, colscale, tr);  // H * hs <= 8192 (checked by lp_decode_step_plan)
+  } else {
+    const float* xg = o.x;
+    auto load_plain = [&](int k) -> float4 { return ds_ldcg4(xg + k); };
+    if (small) ds_stage_row<2>(o, load_plain, wait_dep, s_stat, xs_u32, xsum, colscale, tr);
+    else ds_stage_row<4>(o, load_plain, wait_dep, s_stat, xs_u32, xsum, colscale, tr);
+  }
+  gs_bar_consumers();
+  if (tr && threadIdx.x == 0) tr[2] = gs_now();
+  const uint32_t xsum_u32 = gs_smem_u32(xsum);
+  if (o.fmt == LP_W_BF16) ds_linear_main<LP_W_BF16, false>(o, rg, red_u32, colscale, xsum_u32, xs_u32, done, tile_begin, tile_end, gt);
+  else if (o.aux_bytes == 4) ds_linear_main<LP_W_INT4, true>(o, rg, red_u32, colscale, xsum_u32, xs_u32, done, tile_begin, tile_end, gt);
+  else ds_linear_main<LP_W_INT4, false>(o, rg, red_u32, colscale, xsum_u32, xs_u32, done, tile_begin, tile_end, gt);
+}
+
+// Epilogue warp `e` finalises the tiles of parity e: cross-warp reduction of the 16 partial sums, digit / term recombination,
+// bias, activation, residual, store.  The consumers never stop for this: they drop their partials and stream on.
+__device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint32_t red_u32, const float* colscale, volatile int* done) {
+  const int lane = threadIdx.x & 31;
+  const int rr = lane & 15, half = lane >> 4;
+  int gt = 0;
+  for (int op = 0; op < p.nops; ++op) {
+    const DsOp& o = p.ops[op];
+    if (o.kind == DS_KIND_LINEAR) {
+      const int ntiles = o.ntiles, fmt = o.fmt, split = o.split, epi = o.epi;
+      const float* bias = o.bias;
+      const float* residual = o.residual;
+      float* out = o.out;
+      const int tile_begin = (int)(((long long)ntiles * blockIdx.x) / gridDim.x);
+      const int tile_end = (int)(((long long)ntiles * (blockIdx.x + 1)) / gridDim.x);
+      for (int tile = tile_begin; tile < tile_end; ++tile, ++gt) {
+        if ((gt & 1) != e) continue;
+        if (e == 0) asm volatile("bar.sync 2, %0;\n" ::"n"(DS_TILE_BAR_THREADS) : "memory");
+        else asm volatile("bar.sync 3, %0;\n" ::"n"(DS_TILE_BAR_THREADS) : "memory");
+        // lane = (row of the tile, half): each half adds the partial sums of 8 warps, then one shuffle
+        const uint32_t rb = red_u32 + (uint32_t)(((e * GS_CWARPS + half * (GS_CWARPS / 2)) * 16 + rr) * 4) * 4;
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < GS_CWARPS / 2; ++w) {
+          const float4 v = ds_lds128f(rb + (uint32_t)w * 16 * 4 * 4);
+          c0 += v.x;
+          c1 += v.y;
+          c2 += v.z;
+        }
+        c0 += __shfl_xor_sync(0xffffffffu, c0, 16);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, 16);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, 16);
+        __syncwarp();
+        if (lane == 0) done[e] = (gt >> 1) + 1;  // the partial sums are in registers: the buffer may be rewritten
+        float y;
+        if (fmt == LP_W_INT4) {  // digit 0 (smallest) first
+          y = c0 * colscale[0];
+          y = fmaf(c1, colscale[1], y);
+          y = fmaf(c2, colscale[2], y);
+        } else {  // last (smallest) bf16 term first
+          y = split == 3 ? c2 : 0.f;
+          y += c1;
+          y += c0;
+        }
+        const int row = tile * GS_ROWS + rr;
+        if (bias) y += bias[row];
+        if (epi == LP_EPI_SWIGLU) {
+          const float other = __shfl_xor_sync(0xffffffffu, y, 1);  // fc_2 row of the pair
+          if (half == 0 && (rr & 1) == 0) out[row >> 1] = silu(y) * other;
+        } else if (half == 0) {
+          if (epi == LP_EPI_GELU) y = gelu_erf(y);
+          else if (epi == LP_EPI_RESIDUAL) y = __ldcg(residual + row) + y;
+          out[row] = y;
+        }
+      }
+    }
+    // end of the op: this warp's rows are written (the consumers signal the op after this barrier).  bar.sync, not arrive:
+    // an epilogue warp must not run ahead into the next op's barrier phase.
+    asm volatile("bar.sync 4, %0;\n" ::"n"(DS_OPEND_THREADS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ attention op (consumers)
+// Head h, sequence split sp of this CTA: flash-decoding with WARP-private state.  Of every 16 KB key tile (AT keys) warp w owns
+// keys w*KPW .. w*KPW+KPW-1: it computes their scores (TPK lanes per key, 16 dims each), keeps its own running (m, l, o[hs]) —
+// o spread over the lanes, hs/32 dims each — and never synchronises with the other warps inside the block loop: a warp only
+// waits for the ring stage it needs and releases it when done, exactly like the linear ops.  The 16 warp states are merged once
+// per (head, split) through shared memory.  The new token's k / v row (RoPE'd here, appended to the cache by the CTA that owns
+// its block) is read from shared memory instead of the landed tile.
+template <int HS>
+__device__ __forceinline__ void ds_attention(const DsParams& p, const DsOp& o, const DsAttnGeo<HS>& geo, DsRing& rg, unsigned char* scratch,
+                                             unsigned long long* tr) {
+  using G = DsAttnGeo<HS>;
+  constexpr int TPK = G::TPK, AT = G::AT, LDM = G::LDM;
+  constexpr int KPW = 32 / TPK;   // keys per warp per tile
+  constexpr int DPL = HS / 32;    // output dims per lane
+  constexpr int LDW = HS + 4;     // warp record: o[HS], m, l
+  float* sQ = reinterpret_cast<float*>(scratch);                              // [HS] rotated q * scale * log2(e)
+  __nv_bfloat16* sNew = reinterpret_cast<__nv_bfloat16*>(sQ + HS);            // [2][HS] rotated new k, new v
+  float* sW = reinterpret_cast<float*>(sNew + 2 * HS);                        // [warps][LDW]
+  float* sZero = sW + GS_CWARPS * LDW;                                        // 16 zero bytes
+  const uint32_t sNew_u32 = gs_smem_u32(sNew);
+  const int ctid = threadIdx.x, warp = ctid >> 5, lane = ctid & 31;
+  const int kq = lane / TPK, dc = lane % TPK;
+  const int npairs = p.H * p.P;
+  const int half = p.n_elem >> 1;
+  for (int j = blockIdx.x; j < npairs; j += gridDim.x) {
+    const int h = j / p.P, sp = j % p.P;
+    const int b0 = sp * geo.bpp, b1 = min(geo.nblk, b0 + geo.bpp);
+    if (b0 >= b1) continue;  // CTA-uniform; the producer applies the same rule
+    const bool patch = geo.slot_blk >= b0 && geo.slot_blk < b1;
+    // ---- q (and, in the CTA that owns the new token's block, k_new / v_new): RoPE, scale; cache append ----
+    {
+      const float* src0 = o.qkv + (size_t)h * 3 * HS;  // MHA: rows [q | k | v] of group h (model.py:210-214)
+      const int nrows = patch ? 3 : 1;
+      for (int i = ctid; i < nrows * HS; i += DS_CTHREADS) {
+        const int r = i / HS, d = i % HS;
+        const float* src = src0 + r * HS;
+        float v = __ldcg(src + d);
+        if (r <= 1 && d < p.n_elem) {
+          const float partner = (d < half) ? -__ldcg(src + d + half) : __ldcg(src + d - half);
+          const float c = p.cosT[(size_t)geo.pos * p.n_elem + d], s = p.sinT[(size_t)geo.pos * p.n_elem + d];
+          v = __fadd_rn(__fmul_rn(v, c), __fmul_rn(partner, s));  // same op order as apply_rope (model.py:330-336)
+        }
+        if (i < 4) sZero[i] = 0.f;
+        if (r == 0) {
+          sQ[d] = v * p.scale_log2;
+        } else {
+          const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+          sNew[(r - 1) * HS + d] = hb;
+          (r == 1 ? o.kc : o.vc)[((size_t)h * p.max_seq + geo.slot) * HS + d] = hb;
+        }
+      }
+    }
+    gs_bar_consumers();
+    if (tr && ctid == 0) tr[4] = gs_now();  // q staged
+    float q[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      q[i] = sQ[dc * 8 + i];
+      q[8 + i] = sQ[(dc + TPK) * 8 + i];
+    }
+    float m_run = -CUDART_INF_F, l_lane = 0.f, ov[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) ov[i] = 0.f;
+    // loop invariants, pinned (see ds_pin): ring geometry, this lane's byte offsets inside a K / V tile
+    const uint32_t ring_u32 = ds_pin(rg.ring_u32), bar0 = ds_pin(rg.bar0);
+    const int nstages = ds_pin(rg.nstages), stage_stride = ds_pin(rg.stage_stride);
+    const uint32_t koff = ds_pin((uint32_t)((warp * KPW + kq) * HS * 2 + dc * 16));  // this lane's key row, first 8-dim chunk
+    const uint32_t voff = ds_pin((uint32_t)(warp * KPW * HS * 2 + lane * (DPL * 2)));  // first key row of the warp, this lane's dims
+    const uint32_t knew = ds_pin(sNew_u32 + dc * 16), vnew = ds_pin(sNew_u32 + HS * 2 + lane * (DPL * 2));
+    const uint32_t vzero = ds_pin(gs_smem_u32(sZero));
+    const bool lane0 = ds_pin(lane) == 0;
+    const bool dc0 = ds_pin(dc) == 0;
+    int rs = rg.s, rph = rg.ph;
+
+    for (int blk = b0; blk < b1; ++blk) {
+      const int key0 = blk * AT + warp * KPW;  // first key of this warp in the tile
+      const int nvalid = geo.kv_len - key0;    // keys key0 .. key0 + nvalid - 1 exist
+      const int pslot = (patch && blk == geo.slot_blk) ? geo.slot - key0 : -1;  // index of the new token among the warp's keys
+      // ---- K tile: scores of this warp's keys ----
+      mbar_wait(bar0 + 8 * rs, rph);
+      if (tr && ctid == 0 && blk == b0) tr[5] = gs_now();  // first K tile present
+      float sc;
+      {
+        const uint32_t rowa = kq == pslot ? knew : ring_u32 + (uint32_t)(rs * stage_stride) + koff;
+        const uint4 ka = ds_lds128(rowa), kb = ds_lds128(rowa + TPK * 16);
+        // four independent chains
+        float s0 = q[0] * bf16lo(ka.x), s1 = q[2] * bf16lo(ka.y), s2 = q[4] * bf16lo(ka.z), s3 = q[6] * bf16lo(ka.w);
+        s0 = fmaf(q[1], bf16hi(ka.x), s0); s1 = fmaf(q[3], bf16hi(ka.y), s1);
+        s2 = fmaf(q[5], bf16hi(ka.z), s2); s3 = fmaf(q[7], bf16hi(ka.w), s3);
+        s0 = fmaf(q[8], bf16lo(kb.x), s0); s1 = fmaf(q[10], bf16lo(kb.y), s1);
+        s2 = fmaf(q[12], bf16lo(kb.z), s2); s3 = fmaf(q[14], bf16lo(kb.w), s3);
+        s0 = fmaf(q[9], bf16hi(kb.x), s0); s1 = fmaf(q[11], bf16hi(kb.y), s1);
+        s2 = fmaf(q[13], bf16hi(kb.z), s2); s3 = fmaf(q[15], bf16hi(kb.w), s3);
+        sc = (s0 + s1) + (s2 + s3);
+      }
+      __syncwarp();
+      if (lane0) mbar_arrive(bar0 + 8 * (nstages + rs));
+      if (++rs == nstages) { rs = 0; rph ^= 1; }
+#pragma unroll
+      for (int off = 1; off < TPK; off <<= 1) sc += __shfl_xor_sync(0xffffffffu, sc, off);
+      if (kq >= nvalid) sc = -CUDART_INF_F;  // rows past the end of the sequence hold stale bytes
+      float mx = sc;
+#pragma unroll
+      for (int off = TPK; off < 32; off <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      // ---- V tile: online softmax of the warp's keys, P.V ----
+      mbar_wait(bar0 + 8 * rs, rph);
+      if (mx > -CUDART_INF_F) {  // warp-uniform: at least one valid key
+        const uint32_t tv = ring_u32 + (uint32_t)(rs * stage_stride) + voff;
+        const float m_new = fmaxf(m_run, mx);
+        const float corr = exp2f(m_run - m_new);  // 0 for the first tile (m_run = -inf, m_new finite)
+        const float pk = exp2f(sc - m_new);       // 0 for keys past the end
+        m_run = m_new;
+        l_lane = fmaf(l_lane, corr, dc0 ? pk : 0.f);
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) ov[i] *= corr;
+#pragma unroll
+        for (int kk = 0; kk < KPW; ++kk) {
+          const float pkk = __shfl_sync(0xffffffffu, pk, kk * TPK);
+          // keys past the end read a zero row (their stage bytes are stale: keep NaN bit patterns out of 0 * v)
+          const uint32_t rowa = kk == pslot ? vnew : (kk < nvalid ? tv + kk * HS * 2 : vzero);
+          if (DPL == 4) {
+            const uint2 vv = ds_lds64(rowa);
+            ov[0] = fmaf(pkk, bf16lo(vv.x), ov[0]);
+            ov[1] = fmaf(pkk, bf16hi(vv.x), ov[1]);
+            ov[DPL - 2] = fmaf(pkk, bf16lo(vv.y), ov[DPL - 2]);
+            ov[DPL - 1] = fmaf(pkk, bf16hi(vv.y), ov[DPL - 1]);
+          } else {
+            const uint32_t vv = ds_lds32(rowa);
+            ov[0] = fmaf(pkk, bf16lo(vv), ov[0]);
+            ov[1] = fmaf(pkk, bf16hi(vv), ov[1]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane0) mbar_arrive(bar0 + 8 * (nstages + rs));
+      if (++rs == nstages) { rs = 0; rph ^= 1; }
+    }
+    rg.s = rs;
+    rg.ph = rph;
+    // ---- merge the 16 warp states, write this split's partial ----
+    if (tr && ctid == 0) tr[6] = gs_now();  // block loop done (warp 0)
+    {
+      const float lw = warp_sum(l_lane);
+      float* rec = sW + warp * LDW;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) rec[lane * DPL + i] = ov[i];
+      if (lane == 0) {
+        rec[HS] = m_run;
+        rec[HS + 1] = lw;
+      }
+    }
+    gs_bar_consumers();
+    {
+      // 4 lanes per output dim (HS 128: all 512 threads; HS 64: the first 256), each folds 4 of the 16 warp records
+      const int d = ctid >> 2, qd = ctid & 3;
+      if (d < HS) {
+        float mx = -CUDART_INF_F;
+#pragma unroll
+        for (int w = 0; w < GS_CWARPS; ++w) mx = fmaxf(mx, sW[w * LDW + HS]);
+        float acc = 0.f, L = 0.f;
+#pragma unroll
+        for (int w4 = 0; w4 < GS_CWARPS / 4; ++w4) {  // fixed order: deterministic
+          const int w = qd * (GS_CWARPS / 4) + w4;
+          const float c = exp2f(sW[w * LDW + HS] - mx);  // 0 for warps that saw no valid key
+          acc = fmaf(sW[w * LDW + d], c, acc);
+          L = fmaf(sW[w * LDW + HS + 1], c, L);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        L += __shfl_xor_sync(0xffffffffu, L, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        L += __shfl_xor_sync(0xffffffffu, L, 2);
+        if (qd == 0) {
+          float* dst = p.part + ((size_t)h * p.P + sp) * LDM;
+          dst[d] = acc;
+          if (d == 0) {
+            dst[HS] = mx;
+            dst[HS + 1] = L;
+          }
+        }
+      }
+    }
+    gs_bar_consumers();  // scratch is reused by the next pair / the next op's staging
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <int HS>
+__global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* ring = smem;
+  unsigned char* after = smem + (size_t)p.nstages * p.stage_stride;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after);                    // full[nstages], empty[nstages] (<= 15 stages)
+  volatile int* done = reinterpret_cast<volatile int*>(after + 240);
+  float* red = reinterpret_cast<float*>(after + 256);
+  float* colscale = red + DS_RED_FLOATS;
+  float* xsum = colscale + 8;
+  unsigned char* xs = reinterpret_cast<unsigned char*>(xsum + p.xsum_floats);  // activation columns; attention scratch
+  __shared__ __align__(16) float s_stat[4 * GS_CWARPS];
+  const uint32_t red_u32 = gs_smem_u32(red), xs_u32 = gs_smem_u32(xs);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  DsRing rg;
+  rg.bar0 = gs_smem_u32(bars);
+  rg.ring_u32 = gs_smem_u32(ring);
+  rg.ring = ring;
+  rg.nstages = p.nstages;
+  rg.stage_stride = p.stage_stride;
+  rg.s = 0;
+  rg.ph = 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nstages; ++s) {
+      mbar_init(rg.bar0 + 8 * s, 1);
+      mbar_init(rg.bar0 + 8 * (p.nstages + s), GS_CWARPS);
+    }
+    done[0] = done[1] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp > GS_CWARPS) {
+    pdl_wait();
+    ds_epilogue_warp(p, warp - GS_CWARPS - 1, red_u32, colscale, done);
+    return;
+  }
+  if (warp == GS_CWARPS) {
+    // =========================== PRODUCER: walks the op table, waits only for free ring slots =========================
+    if (lane != 0) return;
+    bool have_geo = false;
+    DsAttnGeo<HS> geo;
+    for (int op = 0; op < p.nops; ++op) {
+      const DsOp& o = p.ops[op];
+      if (o.kind == DS_KIND_LINEAR) {
+        const int ntiles = o.ntiles, nks = o.nks, fmt = o.fmt, gp128 = o.gp128, aux_bytes = o.aux_bytes, ngroups = o.ngroups;
+        const int nch128 = (o.K + 127) / 128;
+        const int tile_begin = (int)(((long long)ntiles * blockIdx.x) / gridDim.x);
+        const int tile_end = (int)(((long long)ntiles * (blockIdx.x + 1)) / gridDim.x);
+        const char* aux2 = reinterpret_cast<const char*>(o.aux2);
+        // the norm parameters of this op are read once per step (HBM misses of ~2 us on the consumers' critical path
+        // otherwise): one CTA pulls them into L2 now — the producer runs a ring depth ahead of the consumers
+        if (o.norm_kind >= 0 && (int)blockIdx.x == op % (int)gridDim.x) {
+          ds_prefetch_l2(o.nw, (uint32_t)o.K * 4);
+          if (o.nb) ds_prefetch_l2(o.nb, (uint32_t)o.K * 4);
+        }
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
+          for (int ks = 0; ks < nks; ++ks) {
+            mbar_wait(rg.empty(), rg.ph ^ 1);
+            const uint32_t dst = rg.ring_u32 + (uint32_t)rg.s * rg.stage_stride;
+            uint32_t aux_len = 0;
+            int g_begin = 0;
+            if (fmt == LP_W_INT4) {
+              const int c_begin = ks * GS_KB * 2, c_end = min(nch128, (ks + 1) * GS_KB * 2);
+              g_begin = c_begin / gp128;
+              aux_len = (uint32_t)((c_end + gp128 - 1) / gp128 - g_begin) * 16 * aux_bytes;
+            }
+            mbar_expect_tx(rg.full(), GS_KB * GS_BLK_BYTES + aux_len);
+            tma_load_3d(dst, &o.map, 0, tile * GS_ROWS, ks * GS_KB, rg.full());
+            if (fmt == LP_W_INT4)
+              bulk_g2s(dst + GS_KB * GS_BLK_BYTES, aux2 + ((size_t)tile * ngroups + g_begin) * 16 * aux_bytes, aux_len, rg.full());
+            rg.advance();
+          }
+        }
+      } else {
+        if (!have_geo) {
+          pdl_wait();  // the position is written by the previous step's sampler
+          geo.init(p);
+          have_geo = true;
+        }
+        constexpr int AT = DsAttnGeo<HS>::AT;
+        const int npairs = p.H * p.P;
+        for (int j = blockIdx.x; j < npairs; j += gridDim.x) {
+          const int h = j / p.P, sp = j % p.P;
+          const int b0 = sp * geo.bpp, b1 = min(geo.nblk, b0 + geo.bpp);
+          for (int blk = b0; blk < b1; ++blk) {
+            const int rows = min(AT, p.max_seq - blk * AT);
+            const uint32_t bytes = (uint32_t)rows * HS * 2;
+            const size_t off = ((size_t)h * p.max_seq + (size_t)blk * AT) * HS;
+            mbar_wait(rg.empty(), rg.ph ^ 1);
+            mbar_expect_tx(rg.full(), bytes);
+            bulk_g2s(rg.ring_u32 + (uint32_t)rg.s * rg.stage_stride, o.kc + off, bytes, rg.full());
+            rg.advance();
+            mbar_wait(rg.empty(), rg.ph ^ 1);
+            mbar_expect_tx(rg.full(), bytes);
+            bulk_g2s(rg.ring_u32 + (uint32_t)rg.s * rg.stage_stride, o.vc + off, bytes, rg.full());
+            rg.advance();
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // =============================== CONSUMERS ==========================================================================
+  pdl_wait();  // embedding row, zeroed counters, position
+  pdl_launch_dependents();
+  DsAttnGeo<HS> geo;
+  geo.init(p);
+  int waited = -1, gt = 0;
+  for (int op = 0; op < p.nops; ++op) {
+    const DsOp& o = p.ops[op];
+    unsigned long long* tr = p.trace ? p.trace + ((size_t)op * gridDim.x + blockIdx.x) * 8 : nullptr;
+    if (tr && threadIdx.x == 0) tr[0] = gs_now();
+    const int dep = o.dep;
+    // barriers are cumulative: a CTA arrives for op d only after all of its earlier ops
+    auto wait_dep = [&]() {
+      if (dep > waited) {
+        if (threadIdx.x == 0) {  // cheap relaxed polls, one acquire at the end
+          while (ds_ld_relaxed(p.counters + dep) < gridDim.x) {}
+          (void)ds_ld_acquire(p.counters + dep);
+        }
+        gs_bar_consumers();
+        waited = dep;
+      }
+      if (tr && threadIdx.x == 0) tr[1] = gs_now();
+    };
+    if (o.kind == DS_KIND_LINEAR) {
+      ds_linear<HS>(p, o, geo, rg, red_u32, colscale, xsum, xs_u32, done, s_stat, tr, gt, wait_dep);
+    } else {
+      wait_dep();
+      ds_attention<HS>(p, o, geo, rg, xs, tr);
+    }
+    asm volatile("bar.sync 4, %0;\n" ::"n"(DS_OPEND_THREADS) : "memory");  // the epilogue warps have written this op's rows
+    if (threadIdx.x == 0) {
+      // release at gpu scope: covers the rows written by the other warps of this CTA (ordered before by the barrier above)
+      if (o.signal) ds_red_release(p.counters + op);
+      if (tr) tr[3] = gs_now();
+    }
+  }
+}
+
+// Prologue of a step: x = wte[token] (model.py:99), arrival counters = 0.
+__global__ void decode_step_prep_kernel(const void* __restrict__ idx, int idx64, const int* __restrict__ idx_offset,
+                                        const void* __restrict__ wte, int wte_dtype, float* __restrict__ x, int E,
+                                        unsigned* __restrict__ counters, int nops) {
+  pdl_launch_dependents();  // the step kernel prefetches weights while the previous step's sampler is still running
+  pdl_wait();
+  const int at = idx_offset ? idx_offset[0] : 0;
+  const long long tok = idx64 ? reinterpret_cast<const long long*>(idx)[at] : (long long)reinterpret_cast<const int*>(idx)[at];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x)
+    x[e] = wte_dtype == LP_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(wte)[(size_t)tok * E + e])
+                                : reinterpret_cast<const float*>(wte)[(size_t)tok * E + e];
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < nops; i += blockDim.x) counters[i] = 0u;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct DsHostPlan {  // lp_step_handle, opaque to the caller
+  uint32_t magic;
+  int nops, nstages, stage_stride, xsum_floats, hs, H, P, n_elem, max_seq, E, wte_dtype, idx64, grid;
+  float scale_log2;
+  size_t smem;
+  const DsOp* ops_dev;
+  unsigned* counters;
+  const int* pos;
+  const float* cosT;
+  const float* sinT;
+  float* part;
+  const void* idx;
+  const int* idx_offset;
+  const void* wte;
+  float* x0;
+};
+static_assert(sizeof(DsHostPlan) <= sizeof(lp_step_handle), "lp_step_handle too small");
+constexpr uint32_t DS_MAGIC = 0x4c504453u;
+
+static unsigned long long* g_ds_trace = nullptr;
+
+template <int HS>
+static int ds_launch(const DsParams& p, const DsHostPlan& h, void* stream) {
+  static bool attr_set = false;
+  auto kern = decode_step_kernel<HS>;
+  if (!attr_set) {
+    LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)));
+    attr_set = true;
+  }
+  return launch(kern, dim3(h.grid), dim3(DS_THREADS), h.smem, stream, p);
+}
+
+}  // namespace lp
+
+extern "C" {
+
+size_t lp_decode_step_plan_bytes(int n_ops) { return n_ops > 0 ? (size_t)n_ops * sizeof(lp::DsOp) + (size_t)n_ops * 4 + 256 : 0; }
+
+size_t lp_decode_step_workspace_bytes(int H, int hs) { return (size_t)H * lp::DS_MAXP * (hs + 4) * 4; }
+
+int lp_debug_step_trace(void* device_buf) {
+  lp::g_ds_trace = reinterpret_cast<unsigned long long*>(device_buf);
+  return LP_OK;
+}
+
+int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm, void* plan_dev, size_t plan_bytes,
+                        lp_step_handle* handle) {
+  using namespace lp;
+  if (!ops || n_ops <= 0 || !gm || !plan_dev || !handle) return LP_ERR_INVALID_ARG;
+  if (plan_bytes < lp_decode_step_plan_bytes(n_ops) || (reinterpret_cast<uintptr_t>(plan_dev) & 127)) return LP_ERR_WORKSPACE;
+  if (!gm->pos || !gm->idx || !gm->wte || !gm->x0 || !gm->workspace || gm->E <= 0) return LP_ERR_INVALID_ARG;
+  if (gm->hs != 64 && gm->hs != 128) return LP_ERR_UNSUPPORTED;
+  if (gm->H <= 0 || gm->H != gm->G) return LP_ERR_UNSUPPORTED;  // multi-head attention only (one q head per KV group)
+  if (gm->kv_dtype != LP_BF16 || gm->max_seq <= 0 || gm->n_elem < 0 || gm->n_elem > gm->hs || (gm->n_elem & 1)) return LP_ERR_UNSUPPORTED;
+  if (gm->n_elem > 0 && (!gm->cos || !gm->sin)) return LP_ERR_INVALID_ARG;
+  if (gm->workspace_bytes < lp_decode_step_workspace_bytes(gm->H, gm->hs)) return LP_ERR_WORKSPACE;
+  const int grid = num_sms();
+  if (gm->H > grid) return LP_ERR_UNSUPPORTED;
+
+  std::vector<DsOp> dev(n_ops);
+  int stage_stride = GS_KB * GS_BLK_BYTES, xsum_floats = 0;
+  // attention scratch inside the activation area: q, new k/v, scores, slice sums (ds_attention)
+  size_t xs_bytes = (size_t)gm->hs * 4 + 2 * gm->hs * 2 + (size_t)GS_CWARPS * (gm->hs + 4) * 4 + 16;
+  for (int i = 0; i < n_ops; ++i) {
+    const lp_step_op& s = ops[i];
+    DsOp& d = dev[i];
+    memset(&d, 0, sizeof(d));
+    d.kind = s.kind;
+    d.dep = s.dep;
+    d.signal = 0;
+    if (s.dep >= i || s.dep < -1) return LP_ERR_INVALID_ARG;
+    if (s.dep >= 0) dev[s.dep].signal = 1;
+    if (s.kind == LP_STEP_ATTENTION) {
+      if (!s.qkv || !s.k_cache || !s.v_cache) return LP_ERR_INVALID_ARG;
+      if ((reinterpret_cast<uintptr_t>(s.k_cache) | reinterpret_cast<uintptr_t>(s.v_cache) | reinterpret_cast<uintptr_t>(s.qkv)) & 15)
+        return LP_ERR_UNSUPPORTED;
+      d.qkv = s.qkv;
+      d.kc = reinterpret_cast<__nv_bfloat16*>(s.k_cache);
+      d.vc = reinterpret_cast<__nv_bfloat16*>(s.v_cache);
+      continue;
+    }
+    if (s.kind != LP_STEP_LINEAR || !s.W || !s.out) return LP_ERR_INVALID_ARG;
+    const lp_weight& W = *s.W;
+    if (!W.w || W.N <= 0 || W.K <= 0) return LP_ERR_INVALID_ARG;
+    if (W.fmt != LP_W_BF16 && W.fmt != LP_W_INT4) return LP_ERR_UNSUPPORTED;
+    if (W.N % GS_ROWS || W.K % 16 || W.K > 4 * DS_CTHREADS * 8 || (reinterpret_cast<uintptr_t>(W.w) & 15)) return LP_ERR_UNSUPPORTED;
+    if (s.epilogue < LP_EPI_NONE || s.epilogue > LP_EPI_RESIDUAL) return LP_ERR_INVALID_ARG;
+    if (s.epilogue == LP_EPI_RESIDUAL && !s.residual) return LP_ERR_INVALID_ARG;
+    if (s.x_is_attention ? (W.K != gm->H * gm->hs) : !s.x) return LP_ERR_INVALID_ARG;
+    if (s.x_is_attention && W.K > 2 * DS_CTHREADS * 8) return LP_ERR_UNSUPPORTED;
+    if (s.norm_kind >= 0 && (s.norm_kind > LP_NORM_RMS || !s.norm_w)) return LP_ERR_INVALID_ARG;
+    const int K = W.K, kpad = (K + 255) / 256 * 256;
+    size_t row_bytes;
+    int aux_stage = 0;
+    d.fmt = W.fmt;
+    if (W.fmt == LP_W_BF16) {
+      if (K % 64) return LP_ERR_UNSUPPORTED;
+      row_bytes = (size_t)K * 2;
+      d.split = ((size_t)3 * K * 2 > 48 * 1024) ? 2 : 3;  // long rows: 16 mantissa bits per term pair are plenty
+      d.ldx = kpad + 8;
+      d.gp128 = 1;
+      xs_bytes = std::max(xs_bytes, (size_t)d.split * d.ldx * 2);
+    } else {
+      if (W.group <= 0 || W.group % 128 || !W.aux2) return LP_ERR_UNSUPPORTED;
+      row_bytes = (size_t)kpad / 2;
+      d.split = 3;
+      d.ldx = kpad + 16;
+      d.gp128 = W.group / 128;
+      d.ngroups = (K + W.group - 1) / W.group;
+      d.aux_bytes = (W.flags & LP_WF_AUX_PACKED) ? 4 : 8;
+      // groups that can intersect one stage (16 chunks of 128 columns); group 128: exactly 16, no straddling
+      const int groups_per_stage = d.gp128 == 1 ? GS_KB * 2 : (GS_KB * 2 + d.gp128 - 1) / d.gp128 + 1;
+      aux_stage = groups_per_stage * 16 * d.aux_bytes;
+      xs_bytes = std::max(xs_bytes, (size_t)3 * d.ldx);
+      xsum_floats = std::max(xsum_floats, (K + 127) / 128 * 8);
+    }
+    if (s.epilogue == LP_EPI_RESIDUAL) {
+      // who wrote the residual?  covered by `dep`, a step input, or the same CTA (equal N -> equal tile ranges)
+      for (int r = i - 1; r >= 0; --r) {
+        if (ops[r].kind == LP_STEP_LINEAR && ops[r].out == s.residual) {
+          const bool same_rows = ops[r].epilogue != LP_EPI_SWIGLU && ops[r].W->N == W.N;
+          if (r > s.dep && !same_rows) return LP_ERR_INVALID_ARG;
+          break;
+        }
+      }
+    }
+    const GsMap& gmap = gs_tensor_map(W, row_bytes);
+    if (gmap.rank != 3) return LP_ERR_UNSUPPORTED;
+    d.map = gmap.map;
+    d.x = s.x;
+    d.residual = s.residual;
+    d.out = s.out;
+    d.bias = W.bias;
+    d.nw = s.norm_kind >= 0 ? s.norm_w : nullptr;
+    d.nb = s.norm_kind >= 0 ? s.norm_b : nullptr;
+    d.aux2 = W.aux2;
+    d.eps = s.eps;
+    d.norm_kind = s.norm_kind >= 0 ? s.norm_kind : -1;
+    d.epi = s.epilogue;
+    d.N = W.N;
+    d.K = K;
+    d.nkb = (int)((row_bytes + 127) / 128);
+    d.nks = (d.nkb + GS_KB - 1) / GS_KB;
+    d.ntiles = W.N / GS_ROWS;
+    d.x_attn = s.x_is_attention ? 1 : 0;
+    stage_stride = std::max(stage_stride, (GS_KB * GS_BLK_BYTES + aux_stage + 1023) / 1024 * 1024);
+  }
+  xs_bytes = (xs_bytes + 15) / 16 * 16;
+  const size_t tail = 256 + (size_t)DS_RED_FLOATS * 4 + 32 + (size_t)xsum_floats * 4 + xs_bytes;
+  const size_t budget = 226 * 1024;  // 227 KB per CTA minus the 1 KB static block
+  if (tail + 3 * (size_t)stage_stride + 1024 > budget) return LP_ERR_UNSUPPORTED;
+  int ns = (int)((budget - tail - 1024) / stage_stride);
+  if (ns > 14) ns = 14;
+
+  DsHostPlan h;
+  memset(&h, 0, sizeof(h));
+  h.magic = DS_MAGIC;
+  h.nops = n_ops;
+  h.nstages = ns;
+  h.stage_stride = stage_stride;
+  h.xsum_floats = xsum_floats;
+  h.hs = gm->hs;
+  h.H = gm->H;
+  h.P = std::max(1, std::min(DS_MAXP, grid / gm->H));
+  h.n_elem = gm->n_elem;
+  h.max_seq = gm->max_seq;
+  h.E = gm->E;
+  h.wte_dtype = gm->wte_dtype;
+  h.idx64 = gm->idx_is_int64;
+  h.grid = grid;
+  h.scale_log2 = gm->scale * 1.4426950408889634f;
+  h.smem = (size_t)ns * stage_stride + tail + 1024;
+  h.ops_dev = reinterpret_cast<const DsOp*>(plan_dev);
+  h.counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(plan_dev) + (size_t)n_ops * sizeof(DsOp));
+  h.pos = gm->pos;
+  h.cosT = gm->cos;
+  h.sinT = gm->sin;
+  h.part = reinterpret_cast<float*>(gm->workspace);
+  h.idx = gm->idx;
+  h.idx_offset = gm->idx_offset;
+  h.wte = gm->wte;
+  h.x0 = gm->x0;
+  // load-time copy of the op table (synchronous: the staging vector dies at return)
+  LP_CUDA_TRY(cudaMemcpy(plan_dev, dev.data(), (size_t)n_ops * sizeof(DsOp), cudaMemcpyHostToDevice));
+  memset(handle, 0, sizeof(*handle));
+  memcpy(handle, &h, sizeof(h));
+  return LP_OK;
+}
+
+int lp_decode_step(const lp_step_handle* handle, void* stream) {
+  using namespace lp;
+  if (!handle) return LP_ERR_INVALID_ARG;
+  DsHostPlan h;
+  memcpy(&h, handle, sizeof(h));
+  if (h.magic != DS_MAGIC) return LP_ERR_INVALID_ARG;
+  int rc = launch(decode_step_prep_kernel, dim3((h.E + 1023) / 1024), dim3(256), 0, stream, h.idx, h.idx64, h.idx_offset, h.wte, h.wte_dtype,
+                  h.x0, h.E, h.counters, h.nops);
+  if (rc != LP_OK) return rc;
+  DsParams p;
+  p.ops = h.ops_dev;
+  p.counters = h.counters;
+  p.pos = h.pos;
+  p.cosT = h.cosT;
+  p.sinT = h.sinT;
+  p.part = h.part;
+  p.trace = g_ds_trace;
+  p.scale_log2 = h.scale_log2;
+  p.nops = h.nops;
+  p.H = h.H;
+  p.n_elem = h.n_elem;
+  p.max_seq = h.max_seq;
+  p.P = h.P;
+  p.nstages = h.nstages;
+  p.stage_stride = h.stage_stride;
+  p.xsum_floats = h.xsum_floats;
+  return h.hs == 128 ? ds_launch<128>(p, h, stream) : ds_launch<64>(p, h, stream);
+}
+
+}  // extern "C"

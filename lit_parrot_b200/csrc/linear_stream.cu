@@ -19,88 +19,14 @@
 //     x = hi + mid (+ lo) in separate columns (products with the bf16 / int4 weights are exact in the fp32
 //     accumulator); the columns are re-added in the epilogue.  bf16-faithful mode has bf16-valued x: one column per row;
 //   * per tile: cross-warp reduction through shared memory, then the fused epilogue (bias, GELU, SwiGLU, residual).
-#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
-
 #include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
 
-#include "common.cuh"
+#include "stream_common.cuh"
 
 namespace lp {
-
-#ifndef GS_CWARPS_DEF
-#define GS_CWARPS_DEF 16
-#endif
-constexpr int GS_CWARPS = GS_CWARPS_DEF;          // consumer warps: 16 (two per K-block of a stage) or 8 (one per K-block)
-constexpr int GS_THREADS = (GS_CWARPS + 1) * 32;  // + 1 producer warp
-constexpr int GS_ROWS = 16;
-constexpr int GS_BLK_BYTES = GS_ROWS * 128;       // one K-block of a tile: 16 rows x 128 bytes (64 bf16 / 256 int4 columns)
-constexpr size_t GS_SMEM_BUDGET = 200 * 1024;     // measured: a deeper ring beats co-residency of two kernels under PDL
-constexpr int GS_MAX_STAGES = 12;
-constexpr int GS_KB = 8;                          // K-blocks per stage: 16 KB of weights
-
-struct NormArgs {
-  const float* w;
-  const float* b;
-  float eps;
-  int kind;  // -1: none, else lp_norm_kind
-};
-
-// ------------------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t gs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(dst),
-               "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
-               "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void gs_ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void gs_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void gs_imma(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t gs_nib(uint32_t w) {
-  uint32_t r;
-  asm("lop3.b32 %0, %1, 0x000F000F, 0x43004300, 0xEA;\n" : "=r"(r) : "r"(w));  // (w & m) | magic
-  return r;
-}
-__device__ __forceinline__ void gs_bar_consumers() { asm volatile("bar.sync 1, %0;\n" ::"n"(GS_CWARPS * 32) : "memory"); }
-__device__ __forceinline__ uint16_t gs_bf16_bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
 
 struct GsParams {
   const float* x;
@@ -120,12 +46,6 @@ struct GsParams {
   int gp128;        // 128-column chunks per scale group (group / 128)
   unsigned long long* trace;  // debug: per-CTA phase timestamps (globaltimer ns), NULL in production
 };
-
-__device__ __forceinline__ unsigned long long gs_now() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
 
 // One activation row -> shared-memory B-operand columns (see the call site).  s_stat: [2][GS_CWARPS] floats.
 template <int FMT, bool CACHED, int NIC = 4>
@@ -589,12 +509,7 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-struct GsMap {
-  CUtensorMap map;
-  int rank;  // 0 = could not be built
-};
-
-static const GsMap& gs_tensor_map(const lp_weight& W, size_t row_bytes) {
+const GsMap& gs_tensor_map(const lp_weight& W, size_t row_bytes) {
   static std::mutex mu;
   static std::map<std::tuple<const void*, int, int, int>, GsMap> cache;
   std::lock_guard<std::mutex> lock(mu);

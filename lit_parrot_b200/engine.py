@@ -5,6 +5,7 @@ capture only; every arithmetic operation on the path is a kernel of liblitparrot
 """
 import ctypes
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -131,6 +132,9 @@ class Engine:
         self._graphs: Dict[Tuple, Tuple] = {}
         self._scratch: Optional[Tuple] = None
         self._consecutive = False
+        # batch-1 decode: the whole step as one persistent kernel (lp_decode_step) where the library covers the model
+        self.use_step_kernel = os.environ.get("LP_DECODE_STEP", "1") != "0" and bool(getattr(model, "use_step_kernel", True))
+        self._steps: Dict[Tuple, Optional[Tuple]] = {}
 
     # ------------------------------------------------------------------ bookkeeping
     def set_rope(self, rope) -> None:
@@ -148,6 +152,79 @@ class Engine:
 
     def drop_graphs(self) -> None:
         self._graphs.clear()
+        self._steps.clear()
+
+    # ------------------------------------------------------------------ batch-1 decode step as one persistent kernel
+    def _step_plan(self, b: Dict[str, torch.Tensor], idx_ptr: int, idx64: int, idx_off: Optional[int], pos_ptr: int, caches):
+        """Op table of one decode step (same op order as `_run`) -> lp_decode_step_plan.  Returns the handle, or None when the
+        library does not cover this model (GQA / MQA, fp32 cache, NF4 / int8 / fp32 weights, ...): the per-op path runs then."""
+        cfg, lib = self.cfg, self.lib
+        max_seq = caches[0][0].size(2)
+        key = (idx_ptr, idx64, idx_off, pos_ptr, caches[0][0].data_ptr(), max_seq, b["x"].data_ptr())
+        if key in self._steps:
+            ent = self._steps[key]
+            return None if ent is None else ent[0]
+        if len(self._steps) > 16:
+            self._steps.clear()
+        E, H, G, hs = cfg.n_embd, cfg.n_head_local, cfg.n_query_groups_local, cfg.head_size
+        x, qkv, xmid, u, logits = (b[k].data_ptr() for k in ("x", "qkv", "xmid", "u", "logits"))
+        ops: List[_lib.LpStepOp] = []
+
+        def linear(W, src, norm, epi, res, dst, dep, from_attn=False):
+            op = _lib.LpStepOp()
+            op.kind, op.dep, op.W = _lib.LP_STEP_LINEAR, dep, ctypes.pointer(W.rec)
+            op.x, op.x_is_attention = (None if from_attn else src), int(from_attn)
+            op.norm_kind = -1
+            if norm is not None:
+                op.norm_kind, op.norm_w, op.norm_b, op.eps = self.norm_kind, _ptr(norm[0]), _ptr(norm[1]), cfg.norm_eps
+            op.epilogue, op.residual, op.out = epi, res, dst
+            ops.append(op)
+            return len(ops) - 1
+
+        def attention(li, dep):
+            op = _lib.LpStepOp()
+            op.kind, op.dep, op.norm_kind = _lib.LP_STEP_ATTENTION, dep, -1
+            op.qkv, op.k_cache, op.v_cache = qkv, caches[li][0].data_ptr(), caches[li][1].data_ptr()
+            ops.append(op)
+            return len(ops) - 1
+
+        last = -1
+        for li, L in enumerate(self.layers):
+            i_qkv = linear(L.qkv, x, (L.n1_w, L.n1_b), _lib.LP_EPI_NONE, None, qkv, last)
+            if cfg.parallel_residual:
+                n2 = (L.n1_w, L.n1_b) if cfg.shared_attention_norm else (L.n2_w, L.n2_b)
+                i_fc = linear(L.fc, x, n2, self.act, None, u, last)   # reads the old x: streams right behind the QKV weights
+                i_att = attention(li, i_qkv)
+                linear(L.proj, None, None, _lib.LP_EPI_RESIDUAL, x, xmid, i_att, from_attn=True)
+                last = linear(L.mlp_proj, u, None, _lib.LP_EPI_RESIDUAL, xmid, x, i_fc)
+            else:
+                if cfg.shared_attention_norm:
+                    return self._steps.setdefault(key, None)
+                i_att = attention(li, i_qkv)
+                i_proj = linear(L.proj, None, None, _lib.LP_EPI_RESIDUAL, x, x, i_att, from_attn=True)
+                i_fc = linear(L.fc, x, (L.n2_w, L.n2_b), self.act, None, u, i_proj)
+                last = linear(L.mlp_proj, u, None, _lib.LP_EPI_RESIDUAL, x, x, i_fc)
+        linear(self.lm_head, x, (self.lnf_w, self.lnf_b), _lib.LP_EPI_NONE, None, logits, last)
+
+        n = len(ops)
+        arr = (_lib.LpStepOp * n)(*ops)
+        plan = torch.zeros(lib.lp_decode_step_plan_bytes(n), dtype=torch.uint8, device=self.device)
+        ws = torch.zeros(max(lib.lp_decode_step_workspace_bytes(H, hs), 16), dtype=torch.uint8, device=self.device)
+        gm = _lib.LpStepGeom()
+        gm.pos, gm.idx, gm.idx_offset, gm.wte, gm.x0 = pos_ptr, idx_ptr, idx_off, self.wte.data_ptr(), x
+        gm.cos, gm.sin = _ptr(self.cos), _ptr(self.sin)
+        gm.workspace, gm.workspace_bytes = ws.data_ptr(), ws.numel()
+        gm.idx_is_int64, gm.wte_dtype = idx64, _KV_OF_DTYPE[self.wte.dtype]
+        gm.E, gm.H, gm.G, gm.hs, gm.n_elem, gm.max_seq = E, H, G, hs, cfg.rope_n_elem, max_seq
+        gm.kv_dtype, gm.scale = _KV_OF_DTYPE[caches[0][0].dtype], 1.0 / math.sqrt(hs)
+        handle = _lib.LpStepHandle()
+        rc = lib.lp_decode_step_plan(arr, n, ctypes.byref(gm), plan.data_ptr(), plan.numel(), ctypes.byref(handle))
+        if rc == -2:
+            self._steps[key] = None
+            return None
+        _lib.check(rc, "lp_decode_step_plan")
+        self._steps[key] = (handle, plan, ws, arr, n)
+        return handle
 
     def scratch_cache(self, B: int, T: int):
         key = (B, T)
@@ -219,6 +296,12 @@ class Engine:
         if idx_off is None and self.tc_eligible(rows):
             # wide decode batches (B >= 9) and prefill: projections on the tcgen05 GEMM, weights still streamed once
             return self._run_tc(b, idx_ptr, idx64, pos_ptr, caches, B, T, stream, last_only)
+        if (rows == 1 and self.use_step_kernel and r == 0 and self.tp is None and getattr(self, "trace", None) is None
+                and self.cos is not None and caches[0][0].dtype == torch.bfloat16):
+            handle = self._step_plan(b, idx_ptr, idx64, idx_off, pos_ptr, caches)
+            if handle is not None:
+                chk(lib.lp_decode_step(ctypes.byref(handle), stream), "lp_decode_step")
+                return
         E, H, G, hs = cfg.n_embd, cfg.n_head_local, cfg.n_query_groups_local, cfg.head_size
         max_seq = caches[0][0].size(2)
         kvd = _KV_OF_DTYPE[caches[0][0].dtype]

@@ -80,8 +80,11 @@ def mlp(cfg, x: Tensor, sd: Dict[str, Tensor], prefix: str) -> Tensor:
 # attention with the reference's cache semantics
 # ----------------------------------------------------------------------------------------------
 def attention(cfg, x: Tensor, sd: Dict[str, Tensor], prefix: str, cos: Tensor, sin: Tensor, max_seq_length: int,
-              mask: Optional[Tensor], input_pos: Optional[Tensor], kv: Optional[Tuple[Tensor, Tensor]]):
-    """CausalSelfAttention.forward, model.py:194-254."""
+              mask: Optional[Tensor], input_pos: Optional[Tensor], kv: Optional[Tuple[Tensor, Tensor]],
+              kv_round: Optional[torch.dtype] = None):
+    """CausalSelfAttention.forward, model.py:194-254.  `kv_round`: storage precision of the cache when it is narrower than
+    the activations (bf16 cache under fp32 activations): the new k / v are rounded to it before they enter the cache — the
+    rounding the reference's own bf16 cache applies (model.py:236-245 with bf16 tensors)."""
     B, T, C = x.shape
     H, G, hs = cfg.n_head, cfg.n_query_groups, cfg.n_embd // cfg.n_head
     qpk = H // G
@@ -98,6 +101,8 @@ def attention(cfg, x: Tensor, sd: Dict[str, Tensor], prefix: str, cos: Tensor, s
     q = torch.cat((rotate(q[..., :n_elem], cos, sin), q[..., n_elem:]), dim=-1)  # model.py:225-232
     k = torch.cat((rotate(k[..., :n_elem], cos, sin), k[..., n_elem:]), dim=-1)
     if kv is not None:  # model.py:234-245
+        if kv_round is not None:
+            k, v = k.to(kv_round).to(q.dtype), v.to(kv_round).to(q.dtype)
         ck, cv = kv
         ck, cv = ck.to(dtype=k.dtype), cv.to(dtype=v.dtype)
         if input_pos[-1] >= max_seq_length:  # sliding window by physical roll, model.py:238-242
@@ -113,11 +118,11 @@ def attention(cfg, x: Tensor, sd: Dict[str, Tensor], prefix: str, cos: Tensor, s
     return linear(y, sd, prefix + ".proj"), kv
 
 
-def block(cfg, x, sd, i, cos, sin, max_seq_length, mask, input_pos, kv):
+def block(cfg, x, sd, i, cos, sin, max_seq_length, mask, input_pos, kv, kv_round=None):
     """Block.forward, model.py:158-180."""
     p = f"transformer.h.{i}"
     n1 = norm(cfg, x, sd, p + ".norm_1")
-    h, kv = attention(cfg, n1, sd, p + ".attn", cos, sin, max_seq_length, mask, input_pos, kv)
+    h, kv = attention(cfg, n1, sd, p + ".attn", cos, sin, max_seq_length, mask, input_pos, kv, kv_round)
     if cfg.parallel_residual:
         n2 = n1 if cfg.shared_attention_norm else norm(cfg, x, sd, p + ".norm_2")
         x = x + h + mlp(cfg, n2, sd, p + ".mlp")  # (x + h) + mlp, model.py:171
@@ -133,8 +138,10 @@ class OracleGPT:
     """Holds the lazily built rope/mask/kv caches exactly like the reference module (model.py:37-39,
     79-85, 105) so it can be driven call-for-call like ``GPT.forward``."""
 
-    def __init__(self, cfg, state_dict: Dict[str, Tensor], dtype: Optional[torch.dtype] = None) -> None:
+    def __init__(self, cfg, state_dict: Dict[str, Tensor], dtype: Optional[torch.dtype] = None,
+                 kv_round: Optional[torch.dtype] = None) -> None:
         self.config = cfg
+        self.kv_round = kv_round
         self.dtype = dtype or state_dict["transformer.wte.weight"].dtype
         self.sd = {k: (v.to(self.dtype) if v.is_floating_point() and not k.endswith("quant_weight") else v)
                    for k, v in state_dict.items()}
@@ -180,7 +187,7 @@ class OracleGPT:
                 self.kv = [(torch.zeros(k_shape, dtype=self.dtype), torch.zeros(v_shape, dtype=self.dtype))
                            for _ in range(cfg.n_layer)]
             for i in range(cfg.n_layer):
-                x, self.kv[i] = block(cfg, x, self.sd, i, cos, sin, max_seq_length, mask, input_pos, self.kv[i])
+                x, self.kv[i] = block(cfg, x, self.sd, i, cos, sin, max_seq_length, mask, input_pos, self.kv[i], self.kv_round)
         x = norm(cfg, x, self.sd, "transformer.ln_f")
         return linear(x, self.sd, "lm_head")  # all T positions, model.py:111
 
