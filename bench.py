@@ -44,6 +44,18 @@ DEFAULT = "stablelm-3b-bf16-b1"
 EXTRAS = ["llama2-7b-int4g128-b1", "stablelm-3b-bf16-b32"]
 
 
+def ncu_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of the same workload
+    (profiles/step_kernel_ncu.json, written by tools/ncu_step_summary.py), or None."""
+    path = os.path.join(REPO, "profiles", "step_kernel_ncu.json")
+    try:
+        with open(path) as f:
+            ent = json.load(f).get(workload)
+        return None if ent is None else int(ent["dram_bytes_read"] + ent["dram_bytes_write"])
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -272,7 +284,11 @@ def run_workload(workload, steps, warmup, device, rank=0, world=1, with_e2e=True
 
     # ---- dominant kernel alone: lp_linear on the MLP up-projection, rotating over the layers' weights (>> L2) ------
     if with_kernel:
-        res["kernel"] = time_dominant_kernel(eng, cfg, B, device)
+        eng = model._get_engine(device)
+        if B == 1 and any(v is not None for v in eng._steps.values()):
+            res["kernel"] = time_step_kernel(eng, model, cfg, device, kv_b)
+        else:
+            res["kernel"] = time_dominant_kernel(eng, cfg, B, device)
     del model
     torch.cuda.empty_cache()
     return res
@@ -323,6 +339,33 @@ def run_prefill(preset, T, device, reps=3):
     torch.cuda.empty_cache()
     return {"workload": f"{preset} bf16 prefill T={T} (block_size {cfg.block_size}), batch 1", "ms": ms, "prefill_tok_s": T / ms * 1e3,
             "tflops": tf, "tensor_frac_of_sustained_peak": tf / peak, "flops": flops}
+
+
+def time_step_kernel(eng, model, cfg, device, kv_elem_bytes, iters=64):
+    """Batch-1 decode: the dominant kernel is the persistent step kernel (lp_decode_step = prologue + decode_step_kernel, one
+    launch pair per token).  Timed alone with CUDA events on the launching stream, position fixed at the last one reached by the
+    timed loop (the same KV slot is rewritten), algorithmic bytes = all weights + the KV rows read + written."""
+    import torch
+
+    st = eng._gen
+    b = eng.buffers(1, 1, 1, model.kv_caches[0][0].size(2))
+    stream = torch.cuda.current_stream(device).cuda_stream
+    pos = int(st["pos"][0])
+    run = lambda: eng._run(b, st["seq"].data_ptr(), 0, st["pos"].data_ptr(), st["pos"].data_ptr(), model.kv_caches, 1, 1, stream)  # noqa: E731
+    for _ in range(4):
+        run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(device)
+    e0.record()
+    for _ in range(iters):
+        run()
+    e1.record()
+    torch.cuda.synchronize(device)
+    us = e0.elapsed_time(e1) * 1e3 / iters
+    wbytes, kvbytes = algorithmic_bytes_per_step(eng, cfg, 1, pos + 1, kv_elem_bytes)
+    nbytes = wbytes + kvbytes
+    return {"name": f"lp_decode_step (decode_step_kernel<{cfg.head_size}>, {cfg.n_layer} layers + lm_head, kv length {pos + 1})",
+            "us": us, "bytes": int(nbytes), "gbs": nbytes / us / 1e3}
 
 
 def time_dominant_kernel(eng, cfg, B, device, iters=64):
@@ -494,7 +537,8 @@ def main():
         line = dict(base, value=res["tok_s"], ms_per_step=res["ms_per_step"], e2e=res["e2e"],
                     gpu_launches=res["launches_per_step"] * args.steps, clocks=res["clocks"],
                     roofline={"bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s", "frac": k["gbs"] / peak,
-                              "traffic": None, "kernel": f"{k['name']} N={k['N']} K={k['K']}: {k['bytes']} B in {k['us']:.2f} us",
+                              "traffic": ncu_traffic(args.workload) if k["name"].startswith("lp_decode_step") else None,
+                              "kernel": f"{k['name']}{' N=%d K=%d' % (k['N'], k['K']) if 'N' in k else ''}: {k['bytes']} B in {k['us']:.2f} us",
                               "peak_source": peak_src,
                               "whole_step": {"achieved": res["step_gbs"], "frac": res["step_gbs"] / peak,
                                              "bytes": res["bytes_per_step"], "launches": res["launches_per_step"]}})

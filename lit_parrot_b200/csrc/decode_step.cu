@@ -170,8 +170,9 @@ __device__ __forceinline__ int ds_pin(int v) { return (int)ds_pin((uint32_t)v); 
 // in registers through the norm statistics, max|x| and the conversion; every term / digit row is written with one 8- or
 // 16-byte store per 8 columns.  NI = 2 (K <= 8192; norm parameters cached as well) or 4 (K <= 16384).
 //   bf16 weights: x = hi + mid (+ lo) as bf16 rows [split][ldx];
-//   int4 weights: block fixed point X = rint(x * 2^22 / max|x|) as three balanced base-256 int8 digit rows, bytes of an 8-column
-//   group in IMMA operand order (even columns, then odd columns), plus the per-128-column digit sums (zero-point term).
+//   int4 weights: block fixed point X = rint(x * 2^22 / max|x|) as three balanced base-256 int8 digit rows, bytes of a 16-column
+//   pair of groups in IMMA operand order (even columns of both groups, then odd columns), plus the per-128-column digit sums
+//   (zero-point term).
 template <int NI, class LoadX, class WaitDep>
 __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDep wait_dep, float* s_stat, uint32_t xs_u32, float* xsum,
                                              float* colscale, unsigned long long* tr) {
@@ -191,15 +192,21 @@ __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDe
   };
   // norm parameters are constants: fetch them BEFORE waiting for the producer op, so that they are neither part of the burst of
   // activation loads all CTAs issue at the same moment nor on the critical path behind the dependency
+  // (warp 0 polls the dependency counter: its own parameter loads come after the wait, so that the polling loads do not queue
+  // behind them; by then the producer's L2 prefetch has brought the lines in)
+  auto load_norm = [&]() {
 #pragma unroll
-  for (int i = 0; i < NI; ++i) {
-    const int k = ctid * 8 + i * STRIDE;
-    if (WCACHE && has_norm && k < K) {
-      ld8(nw, k, wq[WCACHE ? i : 0]);
-      if (has_bias) ld8(nb, k, bq[WCACHE ? i : 0]);
+    for (int i = 0; i < NI; ++i) {
+      const int k = ctid * 8 + i * STRIDE;
+      if (WCACHE && has_norm && k < K) {
+        ld8(nw, k, wq[WCACHE ? i : 0]);
+        if (has_bias) ld8(nb, k, bq[WCACHE ? i : 0]);
+      }
     }
-  }
+  };
+  if (warp != 0) load_norm();
   wait_dep();
+  if (warp == 0) load_norm();
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
     const int k = ctid * 8 + i * STRIDE;
@@ -345,7 +352,11 @@ __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDe
           // bytes of the 8-column group in operand order: columns 0,2,4,6 (IMMA a0/a1 side), then 1,3,5,7 (a2/a3 side)
           const uint32_t lo = __byte_perm(__byte_perm(dg[d][0], dg[d][2], 0x0040), __byte_perm(dg[d][4], dg[d][6], 0x0040), 0x5410);
           const uint32_t hi = __byte_perm(__byte_perm(dg[d][1], dg[d][3], 0x0040), __byte_perm(dg[d][5], dg[d][7], 0x0040), 0x5410);
-          ds_sts64(xs_u32 + (uint32_t)(d * ldx + k), lo, hi);
+          // 16-column pair of groups (A, B) -> [A.even | B.even | A.odd | B.odd]: the B operands of the low-nibble and the
+          // high-nibble IMMA are then adjacent registers of one 128-bit load
+          const uint32_t a16 = xs_u32 + (uint32_t)(d * ldx + (k & ~15) + ((k & 8) >> 1));
+          asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(a16), "r"(lo) : "memory");
+          asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(a16 + 8), "r"(hi) : "memory");
           float ps = (float)sum[d];
 #pragma unroll
           for (int off = 8; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
@@ -464,10 +475,10 @@ __device__ __forceinline__ void ds_linear_main(const DsOp& o, DsRing& rg, uint32
         // unpack is one LOP3 per operand register; 16 q d sums are exact multiples of 16 and rescaled in fp32.
         int cl[4] = {0, 0, 0, 0}, ch[4] = {0, 0, 0, 0};
         const uint32_t ML = 0x0F0F0F0Fu, MH = 0xF0F0F0F0u;
-        gs_imma(cl, wa.x & ML, wb.x & ML, wa.y & ML, wb.y & ML, xv0.x, xv0.z);
-        gs_imma(ch, wa.x & MH, wb.x & MH, wa.y & MH, wb.y & MH, xv0.y, xv0.w);
-        gs_imma(cl, wa.z & ML, wb.z & ML, wa.w & ML, wb.w & ML, xv1.x, xv1.z);
-        gs_imma(ch, wa.z & MH, wb.z & MH, wa.w & MH, wb.w & MH, xv1.y, xv1.w);
+        gs_imma(cl, wa.x & ML, wb.x & ML, wa.y & ML, wb.y & ML, xv0.x, xv0.y);
+        gs_imma(ch, wa.x & MH, wb.x & MH, wa.y & MH, wb.y & MH, xv0.z, xv0.w);
+        gs_imma(cl, wa.z & ML, wb.z & ML, wa.w & ML, wb.w & ML, xv1.x, xv1.y);
+        gs_imma(ch, wa.z & MH, wb.z & MH, wa.w & MH, wb.w & MH, xv1.z, xv1.w);
         // sum (q - z) s x = s * (sum q X - z * sum X), all integers exact in fp32 (|.| < 2^24)
         acc[0] = fmaf(s0, fmaf((float)ch[0], 0.0625f, fmaf(-z0, xsv.x, (float)cl[0])), acc[0]);
         acc[1] = fmaf(s0, fmaf((float)ch[1], 0.0625f, fmaf(-z0, xsv.y, (float)cl[1])), acc[1]);
