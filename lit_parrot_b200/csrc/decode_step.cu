@@ -52,6 +52,7 @@ struct alignas(128) DsOp {
   float eps;
   int kind, dep, signal;
   int norm_kind, epi, fmt, N, K, split, ldx, nkb, nks, ntiles, ngroups, gp128, aux_bytes, x_attn;
+  int streamk;  // in-place residual op: stages (not tiles) are split evenly over the CTAs, partial tiles are added atomically
 };
 
 struct DsParams {
@@ -98,6 +99,21 @@ struct DsRing {
     if (++s == nstages) { s = 0; ph ^= 1; }
   }
 };
+
+// Stages [sb, se) of a linear op that belong to this CTA, in (tile, K-stage) order.  Whole 16-row tiles normally; for in-place
+// residual ops (N = n_embd: 256 tiles for 148 CTAs would mean 1 or 2 tiles each) the STAGES are split evenly — a tile that
+// straddles two CTAs is finished by both with `x += partial` as an atomic add, nobody waits for anybody.
+__device__ __forceinline__ void ds_stage_range(const DsOp& o, int& sb, int& se) {
+  const long long G = gridDim.x, c = blockIdx.x;
+  if (o.streamk) {
+    const long long T = (long long)o.ntiles * o.nks;
+    sb = (int)(T * c / G);
+    se = (int)(T * (c + 1) / G);
+  } else {
+    sb = (int)((long long)o.ntiles * c / G) * o.nks;
+    se = (int)((long long)o.ntiles * (c + 1) / G) * o.nks;
+  }
+}
 
 // Attention geometry of this step (depends on the device-side position).
 template <int HS>
@@ -396,13 +412,13 @@ __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDe
 // offsets inside a stage, the position of the warp's K-slice) lives in registers; per stage: wait, loads, math, arrive.
 template <int FMT, bool PACKED>
 __device__ __forceinline__ void ds_linear_main(const DsOp& o, DsRing& rg, uint32_t red_u32, const float* colscale, uint32_t xsum_u32,
-                                               uint32_t xs_u32, volatile int* done, int tile_begin, int tile_end, int& gt) {
+                                               uint32_t xs_u32, volatile int* done, int sb, int se, int& gt) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int nks = o.nks, split = o.split, ldx = o.ldx, gp128 = o.gp128;
   const int kbl = warp >> 1, sub0 = warp & 1;
   const int bcol = g < split ? g : split - 1;  // B columns >= split only feed accumulator columns nobody reads
-  const int nunits = (tile_end - tile_begin) * nks;
+  const int nunits = se - sb;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   (void)colscale;
 
@@ -439,10 +455,10 @@ __device__ __forceinline__ void ds_linear_main(const DsOp& o, DsRing& rg, uint32
   const uint32_t ring_u32 = ds_pin(rg.ring_u32), bar0 = ds_pin(rg.bar0);
   const int nstages = ds_pin(rg.nstages), stage_stride = ds_pin(rg.stage_stride);
   int rs = rg.s, rph = rg.ph;
-  uint32_t xpos = xpos0, xsp = xsum0;
-  int slice = slice0;
+  int ks = sb % nks;  // the first tile may start in the middle (stream-K ops)
+  uint32_t xpos = xpos0 + (uint32_t)ks * xstep, xsp = xsum0 + (uint32_t)ks * (GS_KB * 2 * 4 * 4);
+  int slice = slice0 + ks * slice_step;
 
-  int ks = 0, tile = tile_begin;
   for (int u = 0; u < nunits; ++u) {
     mbar_wait(bar0 + 8 * rs, rph);
     const uint32_t st = ring_u32 + (uint32_t)(rs * stage_stride);
@@ -493,7 +509,7 @@ __device__ __forceinline__ void ds_linear_main(const DsOp& o, DsRing& rg, uint32
     xsp += GS_KB * 2 * 4 * 4;
     slice += slice_step;
 
-    if (++ks == nks) {
+    if (++ks == nks || u == nunits - 1) {  // end of the tile, or of this CTA's part of it
       ks = 0;
       xpos = xpos0;
       xsp = xsum0;
@@ -514,7 +530,6 @@ __device__ __forceinline__ void ds_linear_main(const DsOp& o, DsRing& rg, uint32
       if (par == 0) asm volatile("bar.arrive 2, %0;\n" ::"n"(DS_TILE_BAR_THREADS) : "memory");
       else asm volatile("bar.arrive 3, %0;\n" ::"n"(DS_TILE_BAR_THREADS) : "memory");
       ++gt;
-      ++tile;
     }
   }
   rg.s = rs;
@@ -525,10 +540,9 @@ template <int HS, class WaitDep>
 __device__ __forceinline__ void ds_linear(const DsParams& p, const DsOp& o, const DsAttnGeo<HS>& geo, DsRing& rg, uint32_t red_u32,
                                           float* colscale, float* xsum, uint32_t xs_u32, volatile int* done, float* s_stat,
                                           unsigned long long* tr, int& gt, WaitDep wait_dep) {
-  const int ntiles = o.ntiles;
-  const int tile_begin = (int)(((long long)ntiles * blockIdx.x) / gridDim.x);
-  const int tile_end = (int)(((long long)ntiles * (blockIdx.x + 1)) / gridDim.x);
-  if (tile_end == tile_begin) {  // CTA-uniform: nothing to compute, but later ops rely on the (cumulative) dependency
+  int sb, se;
+  ds_stage_range(o, sb, se);
+  if (se == sb) {  // CTA-uniform: nothing to compute, but later ops rely on the (cumulative) dependency
     wait_dep();
     return;
   }
@@ -583,9 +597,9 @@ __device__ __forceinline__ void ds_linear(const DsParams& p, const DsOp& o, cons
   gs_bar_consumers();
   if (tr && threadIdx.x == 0) tr[2] = gs_now();
   const uint32_t xsum_u32 = gs_smem_u32(xsum);
-  if (o.fmt == LP_W_BF16) ds_linear_main<LP_W_BF16, false>(o, rg, red_u32, colscale, xsum_u32, xs_u32, done, tile_begin, tile_end, gt);
-  else if (o.aux_bytes == 4) ds_linear_main<LP_W_INT4, true>(o, rg, red_u32, colscale, xsum_u32, xs_u32, done, tile_begin, tile_end, gt);
-  else ds_linear_main<LP_W_INT4, false>(o, rg, red_u32, colscale, xsum_u32, xs_u32, done, tile_begin, tile_end, gt);
+  if (o.fmt == LP_W_BF16) ds_linear_main<LP_W_BF16, false>(o, rg, red_u32, colscale, xsum_u32, xs_u32, done, sb, se, gt);
+  else if (o.aux_bytes == 4) ds_linear_main<LP_W_INT4, true>(o, rg, red_u32, colscale, xsum_u32, xs_u32, done, sb, se, gt);
+  else ds_linear_main<LP_W_INT4, false>(o, rg, red_u32, colscale, xsum_u32, xs_u32, done, sb, se, gt);
 }
 
 // Epilogue warp `e` finalises the tiles of parity e: cross-warp reduction of the 16 partial sums, digit / term recombination,
@@ -597,13 +611,16 @@ __device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint3
   for (int op = 0; op < p.nops; ++op) {
     const DsOp& o = p.ops[op];
     if (o.kind == DS_KIND_LINEAR) {
-      const int ntiles = o.ntiles, fmt = o.fmt, split = o.split, epi = o.epi;
+      const int nks = o.nks, fmt = o.fmt, split = o.split, epi = o.epi, streamk = o.streamk;
       const float* bias = o.bias;
       const float* residual = o.residual;
       float* out = o.out;
-      const int tile_begin = (int)(((long long)ntiles * blockIdx.x) / gridDim.x);
-      const int tile_end = (int)(((long long)ntiles * (blockIdx.x + 1)) / gridDim.x);
-      for (int tile = tile_begin; tile < tile_end; ++tile, ++gt) {
+      int sb, se;
+      ds_stage_range(o, sb, se);
+      for (int s0 = sb; s0 < se; ++gt) {
+        const int tile = s0 / nks;
+        const bool first = s0 == tile * nks;  // this CTA's part of the tile starts at K = 0: it adds the bias
+        s0 = min(se, (tile + 1) * nks);
         if ((gt & 1) != e) continue;
         if (e == 0) asm volatile("bar.sync 2, %0;\n" ::"n"(DS_TILE_BAR_THREADS) : "memory");
         else asm volatile("bar.sync 3, %0;\n" ::"n"(DS_TILE_BAR_THREADS) : "memory");
@@ -633,8 +650,10 @@ __device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint3
           y += c0;
         }
         const int row = tile * GS_ROWS + rr;
-        if (bias) y += bias[row];
-        if (epi == LP_EPI_SWIGLU) {
+        if (bias && first) y += bias[row];
+        if (streamk) {
+          if (half == 0) atomicAdd(out + row, y);  // x += (partial) W . u, in place
+        } else if (epi == LP_EPI_SWIGLU) {
           const float other = __shfl_xor_sync(0xffffffffu, y, 1);  // fc_2 row of the pair
           if (half == 0 && (rr & 1) == 0) out[row >> 1] = silu(y) * other;
         } else if (half == 0) {
@@ -883,10 +902,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
     for (int op = 0; op < p.nops; ++op) {
       const DsOp& o = p.ops[op];
       if (o.kind == DS_KIND_LINEAR) {
-        const int ntiles = o.ntiles, nks = o.nks, fmt = o.fmt, gp128 = o.gp128, aux_bytes = o.aux_bytes, ngroups = o.ngroups;
+        const int nks = o.nks, fmt = o.fmt, gp128 = o.gp128, aux_bytes = o.aux_bytes, ngroups = o.ngroups;
         const int nch128 = (o.K + 127) / 128;
-        const int tile_begin = (int)(((long long)ntiles * blockIdx.x) / gridDim.x);
-        const int tile_end = (int)(((long long)ntiles * (blockIdx.x + 1)) / gridDim.x);
+        int sb, se;
+        ds_stage_range(o, sb, se);
         const char* aux2 = reinterpret_cast<const char*>(o.aux2);
         // the norm parameters of this op are read once per step (HBM misses of ~2 us on the consumers' critical path
         // otherwise): one CTA pulls them into L2 now — the producer runs a ring depth ahead of the consumers
@@ -894,22 +913,25 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
           ds_prefetch_l2(o.nw, (uint32_t)o.K * 4);
           if (o.nb) ds_prefetch_l2(o.nb, (uint32_t)o.K * 4);
         }
-        for (int tile = tile_begin; tile < tile_end; ++tile) {
-          for (int ks = 0; ks < nks; ++ks) {
-            mbar_wait(rg.empty(), rg.ph ^ 1);
-            const uint32_t dst = rg.ring_u32 + (uint32_t)rg.s * rg.stage_stride;
-            uint32_t aux_len = 0;
-            int g_begin = 0;
-            if (fmt == LP_W_INT4) {
-              const int c_begin = ks * GS_KB * 2, c_end = min(nch128, (ks + 1) * GS_KB * 2);
-              g_begin = c_begin / gp128;
-              aux_len = (uint32_t)((c_end + gp128 - 1) / gp128 - g_begin) * 16 * aux_bytes;
-            }
-            mbar_expect_tx(rg.full(), GS_KB * GS_BLK_BYTES + aux_len);
-            tma_load_3d(dst, &o.map, 0, tile * GS_ROWS, ks * GS_KB, rg.full());
-            if (fmt == LP_W_INT4)
-              bulk_g2s(dst + GS_KB * GS_BLK_BYTES, aux2 + ((size_t)tile * ngroups + g_begin) * 16 * aux_bytes, aux_len, rg.full());
-            rg.advance();
+        int tile = sb / nks, ks = sb % nks;
+        for (int s0 = sb; s0 < se; ++s0) {
+          mbar_wait(rg.empty(), rg.ph ^ 1);
+          const uint32_t dst = rg.ring_u32 + (uint32_t)rg.s * rg.stage_stride;
+          uint32_t aux_len = 0;
+          int g_begin = 0;
+          if (fmt == LP_W_INT4) {
+            const int c_begin = ks * GS_KB * 2, c_end = min(nch128, (ks + 1) * GS_KB * 2);
+            g_begin = c_begin / gp128;
+            aux_len = (uint32_t)((c_end + gp128 - 1) / gp128 - g_begin) * 16 * aux_bytes;
+          }
+          mbar_expect_tx(rg.full(), GS_KB * GS_BLK_BYTES + aux_len);
+          tma_load_3d(dst, &o.map, 0, tile * GS_ROWS, ks * GS_KB, rg.full());
+          if (fmt == LP_W_INT4)
+            bulk_g2s(dst + GS_KB * GS_BLK_BYTES, aux2 + ((size_t)tile * ngroups + g_begin) * 16 * aux_bytes, aux_len, rg.full());
+          rg.advance();
+          if (++ks == nks) {
+            ks = 0;
+            ++tile;
           }
         }
       } else {
@@ -1116,8 +1138,10 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
       // who wrote the residual?  covered by `dep`, a step input, or the same CTA (equal N -> equal tile ranges)
       for (int r = i - 1; r >= 0; --r) {
         if (ops[r].kind == LP_STEP_LINEAR && ops[r].out == s.residual) {
-          const bool same_rows = ops[r].epilogue != LP_EPI_SWIGLU && ops[r].W->N == W.N;
-          if (r > s.dep && !same_rows) return LP_ERR_INVALID_ARG;
+          const bool inplace = s.residual == s.out, r_inplace = ops[r].epilogue == LP_EPI_RESIDUAL && ops[r].residual == ops[r].out;
+          const bool same_rows = !inplace && ops[r].epilogue != LP_EPI_SWIGLU && ops[r].W->N == W.N;
+          // two in-place residual ops may overlap: both accumulate atomically
+          if (r > s.dep && !same_rows && !(inplace && r_inplace)) return LP_ERR_INVALID_ARG;
           break;
         }
       }
@@ -1141,6 +1165,8 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
     d.nks = (d.nkb + GS_KB - 1) / GS_KB;
     d.ntiles = W.N / GS_ROWS;
     d.x_attn = s.x_is_attention ? 1 : 0;
+    // in-place residual (x += W . u): evenly split stages, atomic accumulation (see ds_stage_range)
+    d.streamk = (s.epilogue == LP_EPI_RESIDUAL && s.residual == s.out) ? 1 : 0;
     stage_stride = std::max(stage_stride, (GS_KB * GS_BLK_BYTES + aux_stage + 1023) / 1024 * 1024);
   }
   xs_bytes = (xs_bytes + 15) / 16 * 16;

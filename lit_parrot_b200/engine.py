@@ -195,8 +195,9 @@ class Engine:
                 n2 = (L.n1_w, L.n1_b) if cfg.shared_attention_norm else (L.n2_w, L.n2_b)
                 i_fc = linear(L.fc, x, n2, self.act, None, u, last)   # reads the old x: streams right behind the QKV weights
                 i_att = attention(li, i_qkv)
-                linear(L.proj, None, None, _lib.LP_EPI_RESIDUAL, x, xmid, i_att, from_attn=True)
-                last = linear(L.mlp_proj, u, None, _lib.LP_EPI_RESIDUAL, xmid, x, i_fc)
+                # x += attn.proj(att); x += mlp.proj(u): both in place (atomic accumulation, stage-granular split), no barrier
+                linear(L.proj, None, None, _lib.LP_EPI_RESIDUAL, x, x, i_att, from_attn=True)
+                last = linear(L.mlp_proj, u, None, _lib.LP_EPI_RESIDUAL, x, x, i_fc)
             else:
                 if cfg.shared_attention_norm:
                     return self._steps.setdefault(key, None)
