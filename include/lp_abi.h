@@ -193,8 +193,8 @@ int lp_attn_prefill(const float* q, const void* k_cache, const void* v_cache, in
  *        CTA then wrote the rows it reads); checked by lp_decode_step_plan.  residual == out (x += W . u in place) is the
  *        preferred form: such ops are split over the CTAs at 16 KB-stage granularity and accumulate with atomic adds, so two
  *        of them may overlap (parallel-residual blocks); the summation order of their partial sums is not fixed.
- * Covers fp32-activation mode, bf16 / GPTQ-int4 (tile-major aux2) weights, multi-head attention (H == G), bf16 KV cache,
- * hs 64 / 128; LP_ERR_UNSUPPORTED otherwise (callers then issue the per-op calls above). */
+ * Covers fp32-activation mode, bf16 / GPTQ-int4 (tile-major aux2) weights, MHA / GQA / MQA with H <= #SMs, bf16 KV cache,
+ * hs 64 / 128, batch 1; LP_ERR_UNSUPPORTED otherwise (callers then issue the per-op calls above). */
 typedef enum { LP_STEP_LINEAR = 0, LP_STEP_ATTENTION = 1 } lp_step_kind;
 
 typedef struct {

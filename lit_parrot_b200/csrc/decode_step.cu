@@ -14,7 +14,8 @@
 //   * sixteen CONSUMER warps execute the ops in order.  An op that reads another op's output waits for that op's arrival
 //     counter (one `red.release.gpu` per CTA, polled with `ld.acquire.gpu`), re-stages its activation row (fused LayerNorm /
 //     RMSNorm, bf16 term split or int8 digit split as in linear_stream.cu) and drains the ring: mma.sync bf16 / IMMA int4;
-//   * attention (MHA): head h is split over P = #CTAs / H CTAs along the sequence; RoPE(q, k_new), the cache append (global
+//   * attention (MHA / GQA / MQA): q head h is split over P = min(4, #CTAs / H) CTAs along the sequence (the heads of a group
+//     stream the same K / V tiles: L2 hits); RoPE(q, k_new), the cache append (global
 //     + patch of the landed tile), q.K^T, online softmax and P.V run on the CUDA cores straight from the ring stages; the
 //     (m, l, o) partials of the P splits are merged by the attention-projection's activation staging — no extra pass.
 // The op table is built once per (model, cache) by lp_decode_step_plan; a step is lp_decode_step: a tiny prologue kernel
@@ -64,7 +65,7 @@ struct DsParams {
   float* part;         // attention partials [H][P][hs + 4]
   unsigned long long* trace;
   float scale_log2;
-  int nops, H, n_elem, max_seq, P;
+  int nops, H, G, n_elem, max_seq, P;
   int nstages, stage_stride, xsum_floats;
 };
 
@@ -184,7 +185,7 @@ __device__ __forceinline__ int ds_pin(int v) { return (int)ds_pin((uint32_t)v); 
 // One activation row -> shared-memory B-operand columns.  Thread `ctid` owns the 8 consecutive columns 8 ctid + 4096 i of
 // every pass, so the row is read from L2 once (activations are produced by other SMs inside this kernel: __ldcg) and kept
 // in registers through the norm statistics, max|x| and the conversion; every term / digit row is written with one 8- or
-// 16-byte store per 8 columns.  NI = 2 (K <= 8192; norm parameters cached as well) or 4 (K <= 16384).
+// 16-byte store per 8 columns.  NI = 2 (K <= 8192; norm parameters cached as well), 4 (K <= 16384) or 6 (K <= 24576).
 //   bf16 weights: x = hi + mid (+ lo) as bf16 rows [split][ldx];
 //   int4 weights: block fixed point X = rint(x * 2^22 / max|x|) as three balanced base-256 int8 digit rows, bytes of a 16-column
 //   pair of groups in IMMA operand order (even columns of both groups, then odd columns), plus the per-128-column digit sums
@@ -592,7 +593,8 @@ __device__ __forceinline__ void ds_linear(const DsParams& p, const DsOp& o, cons
     const float* xg = o.x;
     auto load_plain = [&](int k) -> float4 { return ds_ldcg4(xg + k); };
     if (small) ds_stage_row<2>(o, load_plain, wait_dep, s_stat, xs_u32, xsum, colscale, tr);
-    else ds_stage_row<4>(o, load_plain, wait_dep, s_stat, xs_u32, xsum, colscale, tr);
+    else if (o.K <= 4 * DS_CTHREADS * 8) ds_stage_row<4>(o, load_plain, wait_dep, s_stat, xs_u32, xsum, colscale, tr);
+    else ds_stage_row<6>(o, load_plain, wait_dep, s_stat, xs_u32, xsum, colscale, tr);  // e.g. falcon-7b mlp.proj, K = 18176
   }
   gs_bar_consumers();
   if (tr && threadIdx.x == 0) tr[2] = gs_now();
@@ -695,16 +697,18 @@ __device__ __forceinline__ void ds_attention(const DsParams& p, const DsOp& o, c
   const int half = p.n_elem >> 1;
   for (int j = blockIdx.x; j < npairs; j += gridDim.x) {
     const int h = j / p.P, sp = j % p.P;
+    const int qpk = p.H / p.G, g = h / qpk;  // KV group of this q head: its K / V tiles are shared by qpk heads (CTAs)
     const int b0 = sp * geo.bpp, b1 = min(geo.nblk, b0 + geo.bpp);
     if (b0 >= b1) continue;  // CTA-uniform; the producer applies the same rule
     const bool patch = geo.slot_blk >= b0 && geo.slot_blk < b1;
     // ---- q (and, in the CTA that owns the new token's block, k_new / v_new): RoPE, scale; cache append ----
     {
-      const float* src0 = o.qkv + (size_t)h * 3 * HS;  // MHA: rows [q | k | v] of group h (model.py:210-214)
+      // rows of group g in the raw projection: [q x qpk | k | v] (model.py:210-214); MHA qpk = 1, MQA one group
+      const float* grp = o.qkv + (size_t)g * (qpk + 2) * HS;
       const int nrows = patch ? 3 : 1;
       for (int i = ctid; i < nrows * HS; i += DS_CTHREADS) {
         const int r = i / HS, d = i % HS;
-        const float* src = src0 + r * HS;
+        const float* src = grp + (size_t)(r == 0 ? h - g * qpk : qpk + r - 1) * HS;
         float v = __ldcg(src + d);
         if (r <= 1 && d < p.n_elem) {
           const float partner = (d < half) ? -__ldcg(src + d + half) : __ldcg(src + d - half);
@@ -717,7 +721,8 @@ __device__ __forceinline__ void ds_attention(const DsParams& p, const DsOp& o, c
         } else {
           const __nv_bfloat16 hb = __float2bfloat16_rn(v);
           sNew[(r - 1) * HS + d] = hb;
-          (r == 1 ? o.kc : o.vc)[((size_t)h * p.max_seq + geo.slot) * HS + d] = hb;
+          // the first q head of the group appends to the cache; the others only need the row in shared memory
+          if (h == g * qpk) (r == 1 ? o.kc : o.vc)[((size_t)g * p.max_seq + geo.slot) * HS + d] = hb;
         }
       }
     }
@@ -948,7 +953,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
           for (int blk = b0; blk < b1; ++blk) {
             const int rows = min(AT, p.max_seq - blk * AT);
             const uint32_t bytes = (uint32_t)rows * HS * 2;
-            const size_t off = ((size_t)h * p.max_seq + (size_t)blk * AT) * HS;
+            const size_t off = ((size_t)(h / (p.H / p.G)) * p.max_seq + (size_t)blk * AT) * HS;
             mbar_wait(rg.empty(), rg.ph ^ 1);
             mbar_expect_tx(rg.full(), bytes);
             bulk_g2s(rg.ring_u32 + (uint32_t)rg.s * rg.stage_stride, o.kc + off, bytes, rg.full());
@@ -1020,7 +1025,7 @@ __global__ void decode_step_prep_kernel(const void* __restrict__ idx, int idx64,
 // ------------------------------------------------------------------------------------------------ host side
 struct DsHostPlan {  // lp_step_handle, opaque to the caller
   uint32_t magic;
-  int nops, nstages, stage_stride, xsum_floats, hs, H, P, n_elem, max_seq, E, wte_dtype, idx64, grid;
+  int nops, nstages, stage_stride, xsum_floats, hs, H, G, P, n_elem, max_seq, E, wte_dtype, idx64, grid;
   float scale_log2;
   size_t smem;
   const DsOp* ops_dev;
@@ -1070,7 +1075,7 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
   if (plan_bytes < lp_decode_step_plan_bytes(n_ops) || (reinterpret_cast<uintptr_t>(plan_dev) & 127)) return LP_ERR_WORKSPACE;
   if (!gm->pos || !gm->idx || !gm->wte || !gm->x0 || !gm->workspace || gm->E <= 0) return LP_ERR_INVALID_ARG;
   if (gm->hs != 64 && gm->hs != 128) return LP_ERR_UNSUPPORTED;
-  if (gm->H <= 0 || gm->H != gm->G) return LP_ERR_UNSUPPORTED;  // multi-head attention only (one q head per KV group)
+  if (gm->H <= 0 || gm->G <= 0 || gm->H % gm->G) return LP_ERR_INVALID_ARG;
   if (gm->kv_dtype != LP_BF16 || gm->max_seq <= 0 || gm->n_elem < 0 || gm->n_elem > gm->hs || (gm->n_elem & 1)) return LP_ERR_UNSUPPORTED;
   if (gm->n_elem > 0 && (!gm->cos || !gm->sin)) return LP_ERR_INVALID_ARG;
   if (gm->workspace_bytes < lp_decode_step_workspace_bytes(gm->H, gm->hs)) return LP_ERR_WORKSPACE;
@@ -1103,7 +1108,7 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
     const lp_weight& W = *s.W;
     if (!W.w || W.N <= 0 || W.K <= 0) return LP_ERR_INVALID_ARG;
     if (W.fmt != LP_W_BF16 && W.fmt != LP_W_INT4) return LP_ERR_UNSUPPORTED;
-    if (W.N % GS_ROWS || W.K % 16 || W.K > 4 * DS_CTHREADS * 8 || (reinterpret_cast<uintptr_t>(W.w) & 15)) return LP_ERR_UNSUPPORTED;
+    if (W.N % GS_ROWS || W.K % 16 || W.K > 6 * DS_CTHREADS * 8 || (reinterpret_cast<uintptr_t>(W.w) & 15)) return LP_ERR_UNSUPPORTED;
     if (s.epilogue < LP_EPI_NONE || s.epilogue > LP_EPI_RESIDUAL) return LP_ERR_INVALID_ARG;
     if (s.epilogue == LP_EPI_RESIDUAL && !s.residual) return LP_ERR_INVALID_ARG;
     if (s.x_is_attention ? (W.K != gm->H * gm->hs) : !s.x) return LP_ERR_INVALID_ARG;
@@ -1185,6 +1190,7 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
   h.xsum_floats = xsum_floats;
   h.hs = gm->hs;
   h.H = gm->H;
+  h.G = gm->G;
   h.P = std::max(1, std::min(DS_MAXP, grid / gm->H));
   h.n_elem = gm->n_elem;
   h.max_seq = gm->max_seq;
@@ -1231,6 +1237,7 @@ int lp_decode_step(const lp_step_handle* handle, void* stream) {
   p.scale_log2 = h.scale_log2;
   p.nops = h.nops;
   p.H = h.H;
+  p.G = h.G;
   p.n_elem = h.n_elem;
   p.max_seq = h.max_seq;
   p.P = h.P;

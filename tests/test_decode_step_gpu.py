@@ -17,6 +17,9 @@ LLAMA = dict(block_size=256, vocab_size=320, padding_multiple=64, n_layer=3, n_h
 NEOX = dict(block_size=256, vocab_size=320, padding_multiple=64, n_layer=3, n_head=4, n_embd=256, rotary_percentage=0.25,
             parallel_residual=True, bias=True, _norm_class="LayerNorm", _mlp_class="GptNeoxMLP")
 NEOX_SHARED = dict(NEOX, shared_attention_norm=True, n_head=2)
+LLAMA_GQA = dict(LLAMA, n_head=4, n_query_groups=2)                                    # hs 64, two q heads per KV group
+LLAMA_GQA128 = dict(LLAMA, n_embd=512, n_head=4, n_query_groups=2, intermediate_size=768)  # hs 128
+FALCON_MQA = dict(NEOX, n_head=4, n_query_groups=1, rotary_percentage=1.0, shared_attention_norm=True, bias=False)  # falcon-7b style
 
 
 def bf16_model(kw, seed):
@@ -72,7 +75,8 @@ def teacher_forced(m, om, cfg, prompt_len, steps, max_seq, seed=5):
     return worst
 
 
-@pytest.mark.parametrize("kw,seed", [(LLAMA, 51), (NEOX, 52), (NEOX_SHARED, 53)], ids=["llama_hs128", "neox_hs64", "neox_shared_hs128"])
+@pytest.mark.parametrize("kw,seed", [(LLAMA, 51), (NEOX, 52), (NEOX_SHARED, 53), (LLAMA_GQA, 58), (LLAMA_GQA128, 59), (FALCON_MQA, 60)],
+                         ids=["llama_hs128", "neox_hs64", "neox_shared_hs128", "llama_gqa_hs64", "llama_gqa_hs128", "falcon_mqa_hs64"])
 def test_step_kernel_logits_bf16(kw, seed):
     """Teacher-forced decode from position 60 to 150: key tiles fill up, a second (third) tile and sequence split appear."""
     cfg, m, om = bf16_model(kw, seed)
@@ -86,11 +90,12 @@ def test_step_kernel_logits_int4():
     assert step_kernel_used(m)
 
 
-@pytest.mark.parametrize("which", ["bf16", "int4"])
+@pytest.mark.parametrize("which", ["bf16", "int4", "gqa", "mqa"])
 def test_step_kernel_greedy_tokens_and_sliding_window(which):
     """generate(): 100 greedy tokens identical to the oracle, then the overflow case (max_seq_length 80 < 140 tokens: the ring
     slot replaces the reference's roll, model.py:238-242)."""
-    cfg, m, om = bf16_model(LLAMA, 55) if which == "bf16" else int4_model(LLAMA, 56)
+    cfg, m, om = {"bf16": lambda: bf16_model(LLAMA, 55), "int4": lambda: int4_model(LLAMA, 56),
+                  "gqa": lambda: bf16_model(LLAMA_GQA, 61), "mqa": lambda: bf16_model(FALCON_MQA, 62)}[which]()
     prompt = torch.randint(0, cfg.padded_vocab_size, (12,), generator=torch.Generator().manual_seed(7)).to(torch.int32)
     want = O.generate(om, prompt, 112, 112, top_k=1, argmax_ties=True)
     out = lp.generate(m, prompt.to(DEV), 112, 112, top_k=1)
