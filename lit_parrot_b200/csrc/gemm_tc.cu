@@ -54,6 +54,10 @@ __device__ __forceinline__ void tc_tma_2d(uint32_t dst, const CUtensorMap* map, 
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
                "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void tc_tma_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -83,6 +87,22 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
+}
+
+// The same descriptor as {lo, hi} words: only the 14-bit start-address field (bytes >> 4) changes from MMA to MMA, so the issuing
+// thread adds to `lo` instead of rebuilding 64-bit values (it is the bottleneck for the narrow decode-batch MMAs).
+constexpr uint32_t TC_DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t tc_desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFF) | (1u << 16); }
+__device__ __forceinline__ void tc_mma_lo(uint32_t tmem_c, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+      "}\n" ::"r"(tmem_c), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(TC_DESC_HI) : "memory");
 }
 
 struct TcParams {
@@ -278,6 +298,213 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Decode batches (9 <= M <= 64 rows): "swap-AB".  The WEIGHTS are the 128-row A operand (M_mma = 128 weight rows per tile),
+// the batch is the N dimension of the MMA (NB = M rounded up to 16), so a stage is KB x (16 KB of weights + NB x 128 B per
+// activation term) — weight-streaming bound, like the GEMV — instead of 16 KB of zero-padded activations per 4 KB of weights.
+// Both operands are fetched through 3-D tensor maps {128 B, rows, K-blocks} (as in linear_stream.cu) with KB = 4 (2) K-blocks per
+// copy: 512 (256) contiguous bytes per weight row.  With one 128-byte segment per row per copy (2-D box) HBM delivered 1.5 TB/s.  TMEM holds
+// C^T: lane = weight row n, column = batch row m; the epilogue thread of lane n walks the batch rows, so for a fixed m the
+// warp stores 32 consecutive n: coalesced.  In-place residual projections (N = n_embd: only N / 128 tiles) are additionally
+// split along K over `ksplit` CTAs and accumulate with atomic adds (x += partial).
+// ---------------------------------------------------------------------------------------------------------------------
+struct TcSwapParams {
+  const float* bias;
+  const float* residual;
+  float* out_f32;
+  __nv_bfloat16* out_bf;
+  int M, N, K, epi, round_bf16, nterms, out_terms, NB, ksplit, KB;
+  int fuse;  // M % 16 == 0: the terms are one stacked B operand (N_mma = nterms * NB), their columns are added in the epilogue
+};
+constexpr int TC_SWAP_ACC = 256;  // TMEM columns per accumulator (nterms * NB <= 192), two accumulators
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcSwapParams p, int nstages) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  constexpr int A_BYTES = TC_BM * TC_BK * 2;  // weight slab: 128 rows x 64 k
+  const int XB = p.NB * TC_BK * 2;            // activation slab of one term: NB rows x 64 k
+  const int KB = p.KB;                        // K-blocks (slabs) per stage
+  const int stage_bytes = KB * (A_BYTES + p.nterms * XB);
+  __shared__ __align__(8) uint64_t bars[2 * 12 + 4];
+  __shared__ uint32_t s_tmem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk = (p.K / TC_BK + KB - 1) / KB;  // stages along K (K % 64 == 0; slabs past the end are zero-filled by TMA)
+  const int tiles_n = (p.N + TC_BM - 1) / TC_BM;
+  const int nunits = tiles_n * p.ksplit;
+  const uint32_t bar0 = tc_smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8 * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8 * (12 + s); };
+  auto acc_full = [&](int a) { return bar0 + 8 * (24 + a); };
+  auto acc_empty = [&](int a) { return bar0 + 8 * (26 + a); };
+  const uint32_t ring = tc_smem_u32(smem);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstages; ++s) {
+      tc_mbar_init(full_bar(s), 1);
+      tc_mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      tc_mbar_init(acc_full(a), 1);
+      tc_mbar_init(acc_empty(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tc_smem_u32(&s_tmem)), "r"(2 * TC_SWAP_ACC) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  if (warp == 0) {
+    // ===== TMA producer: the weights do not depend on the preceding kernel, the activation terms do =====
+    if (lane == 0) {
+      int s = 0, ph = 0;
+      bool waited = false;
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+        const int n0 = (u / p.ksplit) * TC_BM, ks = u % p.ksplit;
+        const int kb0 = (int)((long long)nk * ks / p.ksplit), kb1 = (int)((long long)nk * (ks + 1) / p.ksplit);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          tc_mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t dst = ring + (uint32_t)s * stage_bytes;
+          tc_mbar_expect_tx(full_bar(s), stage_bytes);
+          tc_tma_3d(dst, &map_w, 0, n0, kb * KB, full_bar(s));
+          if (!waited) {
+            pdl_wait();
+            waited = true;
+          }
+          if (p.fuse) {  // all terms in one copy: rows [0, nterms*M) of the stacked [nterms*M, K] tensor, slabs [kk][nterms*NB rows]
+            tc_tma_3d(dst + KB * A_BYTES, &map_x, 0, 0, kb * KB, full_bar(s));
+          } else {
+            for (int t = 0; t < p.nterms; ++t)  // term t: rows [t*M, t*M + NB), slabs [t][kk][NB rows]
+              tc_tma_3d(dst + KB * A_BYTES + t * KB * XB, &map_x, 0, t * p.M, kb * KB, full_bar(s));
+          }
+          if (++s == nstages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: D[128 weight rows, NB batch rows] += W_slab . X_term_slab^T =====
+    if (lane == 0) {
+      const int nmma = p.fuse ? p.nterms * p.NB : p.NB;  // N of one MMA
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nmma >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const int nb_ops = p.fuse ? 1 : p.nterms;                         // B operands per k-step
+      const uint32_t bslab = (uint32_t)(p.fuse ? p.nterms * XB : XB) >> 4;  // distance of consecutive K slabs of one B operand
+      const uint32_t bterm = (uint32_t)(KB * XB) >> 4;                  // distance of the terms (unfused layout)
+      int s = 0, ph = 0, it = 0;
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++it) {
+        const int ks = u % p.ksplit;
+        const int kb0 = (int)((long long)nk * ks / p.ksplit), kb1 = (int)((long long)nk * (ks + 1) / p.ksplit);
+        const int a = it & 1;
+        tc_mbar_wait(acc_empty(a), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem + a * TC_SWAP_ACC;
+        uint32_t accumulate = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          tc_mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t st = ring + (uint32_t)s * stage_bytes;
+          uint32_t a_lo = tc_desc_lo(st);
+          uint32_t b_lo = tc_desc_lo(st + KB * A_BYTES);
+          for (int kk = 0; kk < KB; ++kk) {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {  // 32 bytes (16 bf16) per MMA along K: +2 in the address field
+              uint32_t bt = b_lo + 2 * k;
+              for (int t = 0; t < nb_ops; ++t) {
+                tc_mma_lo(tacc + (p.fuse ? 0 : t * p.NB), a_lo + 2 * k, bt, idesc, accumulate);
+                bt += bterm;
+              }
+              accumulate = 1;
+            }
+            a_lo += A_BYTES >> 4;
+            b_lo += bslab;
+          }
+          tc_commit(empty_bar(s));
+          if (++s == nstages) { s = 0; ph ^= 1; }
+        }
+        tc_commit(acc_full(a));
+      }
+    }
+  }
+  if (warp >= 2) {
+    // ===== epilogue: warp w owns TMEM lanes [32 (w % 4), +32) = weight rows; columns = batch rows =====
+    pdl_wait();  // residual / bias of earlier kernels
+    pdl_launch_dependents();
+    const int q = warp & 3;
+    const bool swiglu = p.epi == LP_EPI_SWIGLU;
+    const int nout = swiglu ? p.N / 2 : p.N;
+    const bool atomic = p.ksplit > 1;
+    int it = 0;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++it) {
+      const int a = it & 1;
+      const int n = (u / p.ksplit) * TC_BM + q * 32 + lane;  // weight row = output column
+      const bool first = (u % p.ksplit) == 0;
+      tc_mbar_wait(acc_full(a), (it >> 1) & 1);
+      tc_fence_after();
+      const float bias = (p.bias && n < p.N && first) ? p.bias[n] : 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.NB; c0 += 32) {
+        // the accumulator holds one column block per activation term (term t of batch row m: column t*NB + m): add them
+        uint32_t v[32];
+        float acc[32];
+        tc_ld32(tmem + a * TC_SWAP_ACC + ((uint32_t)(q * 32) << 16) + c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+        for (int t = 1; t < p.nterms; ++t) {
+          tc_ld32(tmem + a * TC_SWAP_ACC + ((uint32_t)(q * 32) << 16) + t * p.NB + c0, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int m = c0 + j;  // batch row (warp-uniform)
+          if (m < p.M) {
+            float y = maybe_round(acc[j] + bias, p.round_bf16);
+            int oc = n;
+            bool store = n < p.N;
+            if (swiglu) {  // W rows interleaved: row 2i = fc_1 row i, 2i+1 = fc_2 row i (model.py:298-300): neighbouring lanes
+              const float other = __shfl_xor_sync(0xffffffffu, y, 1);
+              y = maybe_round(maybe_round(silu(y), p.round_bf16) * other, p.round_bf16);
+              oc = n >> 1;
+              store = store && (n & 1) == 0;
+            } else if (p.epi == LP_EPI_GELU) {
+              y = maybe_round(gelu_erf(y), p.round_bf16);
+            } else if (p.epi == LP_EPI_RESIDUAL && !atomic && store) {
+              y = maybe_round(p.residual[(size_t)m * nout + oc] + y, p.round_bf16);
+            }
+            if (store) {
+              if (atomic) {
+                atomicAdd(p.out_f32 + (size_t)m * nout + oc, y);  // in place: x += partial
+              } else {
+                if (p.out_f32) p.out_f32[(size_t)m * nout + oc] = y;
+                if (p.out_bf) {
+                  for (int t = 0; t < p.out_terms; ++t) {
+                    const __nv_bfloat16 hb = __float2bfloat16_rn(y);
+                    p.out_bf[((size_t)t * p.M + m) * nout + oc] = hb;
+                    y -= __bfloat162float(hb);
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(acc_empty(a)) : "memory");
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(2 * TC_SWAP_ACC) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // x fp32 [rows, K] (optionally through LayerNorm / RMSNorm) -> nterms bf16 arrays [nterms][rows, K] with x = sum of terms
 // ---------------------------------------------------------------------------------------------------------------------
@@ -378,6 +605,29 @@ static const CUtensorMap* tc_cached_map(const void* ptr, int rows, int K, int bo
   return &cache.emplace(key, m).first->second;
 }
 
+// bf16 row-major [rows, K] (K % 64 == 0) as a 3-D tensor {64 elements = 128 B, rows, K / 64 blocks}: one copy brings `kb` slabs
+// of box_rows x 128 B, laid out [slab][row][128 B] under the 128-byte swizzle, from kb * 128 contiguous bytes of every row
+static const CUtensorMap* tc_cached_map3(const void* ptr, int rows, int K, int box_rows, int kb) {
+  static std::mutex mu;
+  static std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_tuple(ptr, rows, K, box_rows, kb);
+  auto it = cache.find(key);
+  if (it != cache.end()) return &it->second;
+  TcEncodeFn enc = tc_encode_fn();
+  if (!enc) return nullptr;
+  CUtensorMap m;
+  cuuint64_t dims[3] = {TC_BK, (cuuint64_t)rows, (cuuint64_t)(K / TC_BK)};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, 128};
+  cuuint32_t box[3] = {TC_BK, (cuuint32_t)box_rows, (cuuint32_t)kb};
+  cuuint32_t es[3] = {1, 1, 1};
+  if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return nullptr;
+  if (cache.size() > 8192) cache.clear();
+  return &cache.emplace(key, m).first->second;
+}
+
 template <int BN>
 static int tc_launch(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, void* stream) {
   static bool attr_set = false;
@@ -393,6 +643,23 @@ static int tc_launch(const CUtensorMap& mx, const CUtensorMap& mw, const TcParam
   const size_t smem = (size_t)nstages * stage_bytes + 1024;
   const int ntiles = ((p.M + TC_BM - 1) / TC_BM) * ((p.N + BN - 1) / BN);
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  return launch(kern, dim3(grid), dim3(TC_THREADS), smem, stream, mx, mw, p, nstages);
+}
+
+static int tc_launch_swap(const CUtensorMap& mx, const CUtensorMap& mw, const TcSwapParams& p, void* stream) {
+  static bool attr_set = false;
+  auto kern = gemm_tc_swap_kernel;
+  if (!attr_set) {
+    LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  const int stage_bytes = p.KB * (TC_BM * TC_BK * 2 + p.nterms * p.NB * TC_BK * 2);
+  int nstages = (212 * 1024) / stage_bytes;
+  if (nstages > 12) nstages = 12;
+  if (nstages < 2) return LP_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)nstages * stage_bytes + 1024;
+  const int nunits = ((p.N + TC_BM - 1) / TC_BM) * p.ksplit;
+  const int grid = nunits < num_sms() ? nunits : num_sms();
   return launch(kern, dim3(grid), dim3(TC_THREADS), smem, stream, mx, mw, p, nstages);
 }
 
@@ -417,6 +684,39 @@ int lp_gemm_bf16_tc(const void* x_terms, int nterms, int M, const void* w_bf16, 
   if (epilogue == LP_EPI_RESIDUAL && !residual) return LP_ERR_INVALID_ARG;
   if (K % 8 || N % 8) return LP_ERR_UNSUPPORTED;  // 16-byte global strides (ragged N / K tiles are zero-filled by TMA)
   if ((reinterpret_cast<uintptr_t>(x_terms) & 15) || (reinterpret_cast<uintptr_t>(w_bf16) & 15)) return LP_ERR_UNSUPPORTED;
+  if (M <= 64 && K % lp::TC_BK == 0) {
+    // decode batches: swap-AB (weights = 128-row A operand, batch = N of the MMA), see gemm_tc_swap_kernel
+    lp::TcSwapParams q;
+    q.bias = bias;
+    q.residual = residual;
+    q.out_f32 = out_f32;
+    q.out_bf = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+    q.M = M;
+    q.N = N;
+    q.K = K;
+    q.epi = epilogue;
+    q.round_bf16 = round_bf16;
+    q.nterms = nterms;
+    q.out_terms = out_terms;
+    q.NB = (M + 15) / 16 * 16;
+    q.fuse = (M % 16 == 0) ? 1 : 0;
+    // K-blocks per copy: 4 (512 contiguous bytes per weight row) if two stages fit, else 2
+    q.KB = 2 * 4 * (lp::TC_BM * lp::TC_BK * 2 + nterms * q.NB * lp::TC_BK * 2) <= 212 * 1024 ? 4 : 2;
+    q.ksplit = 1;
+    const int tiles_n = (N + lp::TC_BM - 1) / lp::TC_BM, nk = (K / lp::TC_BK + q.KB - 1) / q.KB;
+    if (epilogue == LP_EPI_RESIDUAL && residual == out_f32 && !out_bf16 && !round_bf16 && tiles_n < lp::num_sms()) {
+      // x += W . u in place: split K so that every SM streams weights; partial sums are added atomically
+      int ks = (lp::num_sms() + tiles_n - 1) / tiles_n;
+      while (ks > 1 && nk / ks < 2) --ks;
+      q.ksplit = ks > 8 ? 8 : ks;
+    }
+    const CUtensorMap* mx = lp::tc_cached_map3(x_terms, nterms * M, K, q.fuse ? nterms * q.NB : q.NB, q.KB);
+    const CUtensorMap* mw = lp::tc_cached_map3(w_bf16, N, K, lp::TC_BM, q.KB);
+    if (mx && mw) {
+      const int rc = lp::tc_launch_swap(*mx, *mw, q, stream);
+      if (rc != LP_ERR_UNSUPPORTED) return rc;
+    }
+  }
   // Tile width: 256 halves the activation re-reads (prefill); decode batches (one M tile) are weight-streaming bound and
   // need ~one tile per SM, so the width shrinks until the grid fills the chip.  Ragged last tiles are zero-filled by TMA.
   const int tiles_m = (M + lp::TC_BM - 1) / lp::TC_BM;

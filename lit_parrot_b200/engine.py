@@ -444,8 +444,12 @@ class Engine:
                 if not cfg.shared_attention_norm:
                     norm_split(x, L.n2_w, L.n2_b, t_n)  # shared norm: t_n already holds norm_1(x)
                 gemm(t_n, L.fc, self.act, None, None, t_u)
-                gemm(t_att, L.proj, _lib.LP_EPI_RESIDUAL, x, xmid)
-                gemm(t_u, L.mlp_proj, _lib.LP_EPI_RESIDUAL, xmid, x)
+                if r == 0:  # x += attn.proj(att); x += mlp.proj(u), in place (decode batches: split-K with atomic accumulation)
+                    gemm(t_att, L.proj, _lib.LP_EPI_RESIDUAL, x, x)
+                    gemm(t_u, L.mlp_proj, _lib.LP_EPI_RESIDUAL, x, x)
+                else:  # bf16-faithful: the reference rounds (x + h) before adding the MLP branch (model.py:171)
+                    gemm(t_att, L.proj, _lib.LP_EPI_RESIDUAL, x, xmid)
+                    gemm(t_u, L.mlp_proj, _lib.LP_EPI_RESIDUAL, xmid, x)
             else:
                 if cfg.shared_attention_norm:
                     raise NotImplementedError("No checkpoint amongst the ones we support uses this configuration"

@@ -412,7 +412,7 @@ def test_norm_linear_fused(lib, kind, fmt, M, N, K):
 
 @pytest.mark.parametrize("nterms", [1, 2, 3])
 @pytest.mark.parametrize("M,N,K", [(16, 128, 64), (128, 256, 512), (200, 384, 4096), (333, 4608, 4544), (2048, 512, 1024), (9, 1280, 8192),
-                                   (150, 4544, 1024), (70, 200, 136)])
+                                   (150, 4544, 1024), (70, 200, 136), (32, 4096, 4096), (33, 4672, 4544), (64, 200, 136), (48, 16384, 512)])
 def test_gemm_bf16_tc(lib, nterms, M, N, K):
     """lp_split_bf16 + lp_gemm_bf16_tc (TMA + tcgen05.mma, accumulator in tensor memory) against float64 F.linear.
     nterms = 1: bf16 activations (the reference's bf16-true matmul inputs); 2 / 3: fp32-activation accuracy."""
@@ -448,6 +448,24 @@ def test_gemm_bf16_tc(lib, nterms, M, N, K):
                                      1e-5, 0, stream()), "lp_split_bf16")
         want = F.layer_norm(x, (K,), nw, nb, 1e-5) if kind == 0 else O.rms_norm(x, nw, 1e-5)
         torch.testing.assert_close(terms.float().sum(0), want, rtol=2 ** (-8 * nterms + 1), atol=1e-5)
+
+
+@pytest.mark.parametrize("M,N,K", [(32, 4096, 4096), (9, 512, 16384), (64, 4544, 18176), (17, 256, 192)])
+def test_gemm_bf16_tc_inplace_residual_split_k(lib, M, N, K):
+    """Decode batches (M <= 64): swap-AB kernel; x += u . W^T + b in place is split along K over several CTAs that
+    accumulate atomically (the summation order of the <= 8 partial sums is not fixed: tolerance, not bit-equality)."""
+    u = f32(M, K, seed=11)
+    w = f32(N, K, seed=12, scale=0.05).bfloat16()
+    bias = f32(N, seed=13)
+    x0 = f32(M, N, seed=14)
+    terms = torch.empty(2, M, K, dtype=torch.bfloat16, device=DEV)
+    _lib.check(lib.lp_split_bf16(u.data_ptr(), terms.data_ptr(), M, K, 2, -1, None, None, 0.0, 0, stream()), "lp_split_bf16")
+    want = (x0.double() + F.linear(terms.double().sum(0), w.double(), bias.double())).float()
+    x = x0.clone()
+    _lib.check(lib.lp_gemm_bf16_tc(terms.data_ptr(), 2, M, w.data_ptr(), N, K, bias.data_ptr(), 3, x.data_ptr(), x.data_ptr(), None, 0, 0,
+                                   stream()), "lp_gemm_bf16_tc")
+    torch.cuda.synchronize()
+    torch.testing.assert_close(x, want, rtol=2e-5, atol=2e-5 * math.sqrt(K))
 
 
 @pytest.mark.parametrize("fmt", ["int4", "nf4", "int8"])
