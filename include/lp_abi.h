@@ -174,9 +174,12 @@ int lp_attn_decode_fused(const float* qkv, const float* cos, const float* sin, c
                          int n_elem, int max_seq, float scale, int round_bf16, void* stream);
 
 /* Causal attention of T > 1 consecutive query positions (pos[0] .. pos[0] + T - 1, already appended to the cache by
- * lp_rope_kv_append) against the bf16 KV cache, FlashAttention-2 style on the tensor cores (model.py:247, 256-275 with the
- * mask rows of model.py:91-92).  q, out fp32 [B*T, H*hs].  hs 64 / 128, bf16 cache, pos[0] + T <= max_seq (the caller
+ * lp_rope_kv_append) against the bf16 KV cache (model.py:247, 256-275 with the mask rows of model.py:91-92).  T >= 1024: tcgen05
+ * kernel (csrc/attention_tc.cu: S = Q.K^T and O += P.V as tcgen05.mma with the accumulators in tensor memory, K / V tiles by TMA
+ * straight from the cache, V as an MN-major operand); shorter prompts: FlashAttention-2 style mma.sync kernel.  q, out fp32 [B*T, H*hs].  hs 64 / 128, bf16 cache, pos[0] + T <= max_seq (the caller
  * guarantees the positions are consecutive and do not wrap); LP_ERR_UNSUPPORTED otherwise -> lp_attn_decode. */
+/* Which kernel lp_attn_prefill uses: 0 = auto, 1 = mma.sync kernel only, 2 = tcgen05 kernel only.  Test aid. */
+int lp_set_attn_prefill_path(int path);
 int lp_attn_prefill(const float* q, const void* k_cache, const void* v_cache, int kv_dtype, const int32_t* pos, float* out, int B,
                     int T, int H, int G, int hs, int max_seq, float scale, int round_bf16, void* stream);
 

@@ -84,6 +84,7 @@ PROTOTYPES = {
     "lp_attn_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "lp_attn_decode_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                      c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "lp_set_attn_prefill_path": (c_int, [c_int]),
     "lp_attn_prefill": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_float, c_int, c_void_p]),
     "lp_decode_step_plan_bytes": (c_size_t, [c_int]),

@@ -716,11 +716,27 @@ static int ap_launch(const float* q, const void* kc, const void* vc, const int* 
 
 }  // namespace lp
 
+namespace lp {
+int attn_prefill_tc(const float* q, const void* k_cache, const void* v_cache, const int32_t* pos, float* out, int B, int T, int H, int G,
+                    int hs, int max_seq, float scale, int round_bf16, void* stream);  // attention_tc.cu
+static int g_prefill_path = 0;  // 0 auto (tcgen05 for T >= 1024, measured break-even), 1 mma.sync kernel only, 2 tcgen05 kernel only
+}  // namespace lp
+
+extern "C" int lp_set_attn_prefill_path(int path) {
+  if (path < 0 || path > 2) return LP_ERR_INVALID_ARG;
+  lp::g_prefill_path = path;
+  return LP_OK;
+}
+
 extern "C" int lp_attn_prefill(const float* q, const void* k_cache, const void* v_cache, int kv_dtype, const int32_t* pos, float* out, int B,
                                int T, int H, int G, int hs, int max_seq, float scale, int round_bf16, void* stream) {
   if (!q || !k_cache || !v_cache || !pos || !out) return LP_ERR_INVALID_ARG;
   if (B <= 0 || T <= 0 || H <= 0 || G <= 0 || H % G || max_seq <= 0) return LP_ERR_INVALID_ARG;
   if (kv_dtype != LP_BF16 || (hs != 64 && hs != 128) || T > max_seq) return LP_ERR_UNSUPPORTED;
+  if (lp::g_prefill_path == 2 || (lp::g_prefill_path == 0 && T >= 1024)) {
+    const int rc = lp::attn_prefill_tc(q, k_cache, v_cache, pos, out, B, T, H, G, hs, max_seq, scale, round_bf16, stream);
+    if (rc != LP_ERR_UNSUPPORTED || lp::g_prefill_path == 2) return rc;
+  }
   const int exact = round_bf16 ? 0 : 1;
   if (hs == 128) return lp::ap_launch<128>(q, k_cache, v_cache, pos, out, B, T, H, G, max_seq, scale, exact, round_bf16, stream);
   return lp::ap_launch<64>(q, k_cache, v_cache, pos, out, B, T, H, G, max_seq, scale, exact, round_bf16, stream);

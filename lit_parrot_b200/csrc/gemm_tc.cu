@@ -368,7 +368,11 @@ gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
         const int n0 = (u / p.ksplit) * TC_BM, ks = u % p.ksplit;
         const int kb0 = (int)((long long)nk * ks / p.ksplit), kb1 = (int)((long long)nk * (ks + 1) / p.ksplit);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        // every CTA needs the same activation slabs: start the K loop at a CTA-dependent offset (and wrap) so that the CTAs read
+        // different slabs at any one time instead of the same few L2 lines
+        const int nkb = kb1 - kb0, rot = (int)((blockIdx.x * 5u) % (unsigned)nkb);
+        for (int i = 0; i < nkb; ++i) {
+          const int kb = kb0 + (i + rot) % nkb;
           tc_mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t dst = ring + (uint32_t)s * stage_bytes;
           tc_mbar_expect_tx(full_bar(s), stage_bytes);
@@ -592,7 +596,7 @@ static bool tc_make_map(CUtensorMap* m, const void* ptr, int rows, int K, int bo
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static const CUtensorMap* tc_cached_map(const void* ptr, int rows, int K, int box_rows) {
+const CUtensorMap* tc_cached_map(const void* ptr, int rows, int K, int box_rows) {  // also used by attention_tc.cu
   static std::mutex mu;
   static std::map<std::tuple<const void*, int, int, int>, CUtensorMap> cache;
   std::lock_guard<std::mutex> lock(mu);

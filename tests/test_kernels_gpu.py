@@ -498,11 +498,15 @@ def test_dequant_bf16(lib, fmt):
     torch.testing.assert_close(out.float().cpu(), want.float(), rtol=2 ** -7, atol=1e-8)
 
 
+@pytest.mark.parametrize("path", [1, 2], ids=["mma_sync", "tcgen05"])
 @pytest.mark.parametrize("rnd", [0, 1])
 @pytest.mark.parametrize("B,T,H,G,hs,max_seq,p0", [(1, 16, 8, 8, 64, 64, 0), (2, 100, 32, 32, 128, 256, 0), (1, 300, 71, 1, 64, 512, 0),
-                                                   (1, 130, 64, 8, 128, 1024, 500), (2, 65, 8, 2, 64, 200, 7), (1, 2048, 4, 4, 128, 2048, 0)])
-def test_attention_prefill(lib, rnd, B, T, H, G, hs, max_seq, p0):
-    """lp_attn_prefill (causal FlashAttention-2 style tensor-core kernel over the bf16 cache) against masked SDPA in float64."""
+                                                   (1, 130, 64, 8, 128, 1024, 500), (2, 65, 8, 2, 64, 200, 7), (1, 2048, 4, 4, 128, 2048, 0),
+                                                   (1, 128, 2, 2, 128, 128, 0), (1, 129, 3, 1, 64, 640, 511)])
+def test_attention_prefill(lib, rnd, B, T, H, G, hs, max_seq, p0, path):
+    """lp_attn_prefill over the bf16 cache — both kernels: FlashAttention-2 style mma.sync, and tcgen05.mma with the S / O
+    accumulators in tensor memory (csrc/attention_tc.cu) — against masked SDPA in float64."""
+    lib.lp_set_attn_prefill_path(path)
     qpk = H // G
     q = f32(B * T, H * hs, seed=1)
     if rnd:
@@ -515,9 +519,12 @@ def test_attention_prefill(lib, rnd, B, T, H, G, hs, max_seq, p0):
     vc[:, :, :n_valid] = f32(B, G, n_valid, hs, seed=3).bfloat16()
     out = torch.full((B * T, H * hs), float("nan"), device=DEV)
     scale = 1.0 / math.sqrt(hs)
-    _lib.check(lib.lp_attn_prefill(q.data_ptr(), kc.data_ptr(), vc.data_ptr(), _lib.LP_BF16, pos.data_ptr(), out.data_ptr(), B, T, H, G, hs,
-                                   max_seq, scale, rnd, stream()), "lp_attn_prefill")
-    torch.cuda.synchronize()
+    try:
+        _lib.check(lib.lp_attn_prefill(q.data_ptr(), kc.data_ptr(), vc.data_ptr(), _lib.LP_BF16, pos.data_ptr(), out.data_ptr(), B, T, H, G, hs,
+                                       max_seq, scale, rnd, stream()), "lp_attn_prefill")
+        torch.cuda.synchronize()
+    finally:
+        lib.lp_set_attn_prefill_path(0)
     qq = q.view(B, T, H, hs).transpose(1, 2).double()
     kk = kc[:, :, :n_valid].double().repeat_interleave(qpk, dim=1)
     vv = vc[:, :, :n_valid].double().repeat_interleave(qpk, dim=1)
