@@ -3,15 +3,16 @@
 //   reference: scaled_dot_product_attention over the KV cache for T > 1 consecutive positions (model.py:247, 256-275 with the
 //   mask rows of model.py:91-92); q is already rotated, k / v are already in the cache (lp_rope_kv_append).
 //
-// One CTA = 128 query rows of one head (grid: query tiles x heads x batch), 5 warps:
-//   warp 4 (one thread): TMA producer AND MMA issuer.  K / V tiles of 64 keys come straight from the bf16 cache
+// One CTA = 128 query rows of one head (grid: query tiles x heads x batch), 9 warps:
+//   warp 8 (one thread): TMA producer AND MMA issuer.  K / V tiles of 64 keys come straight from the bf16 cache
 //            [B, G, max_seq, hs] through 2-D tensor maps (box 64 keys x 64 dims = 128-byte rows, hardware 128-byte swizzle, two
 //            stages).  S = Q . K^T : A = Q (K-major), B = K tile (K-major), D = S[128 x 64] fp32 in TMEM.  O += P . V : A = P
 //            (K-major, written by the softmax warps), B = V tile used AS LOADED — keys are the rows, i.e. an MN-major operand
 //            (instruction-descriptor bit 16, leading-dimension byte offset = distance of the two 64-dim slabs), D = O[128 x hs];
-//   warps 0-3 (128 threads, thread r = query row r = TMEM lane r): convert q (fp32, pre-scaled by softmax scale x log2 e) to the
-//            swizzled bf16 operand, then per key tile: tcgen05.ld the row of S, causal mask, online softmax with exp2, rescale
-//            of O in TMEM (tcgen05.ld / st) only when some row maximum of the warp moved, P -> shared memory, signal.
+//   warps 0-7 (query row r = TMEM lane r is shared by warps w and w + 4: keys 0-31 / 32-63 of a tile, dims 0..hs/2 / hs/2..hs of
+//            O): convert q (fp32, pre-scaled by softmax scale x log2 e) to the swizzled bf16 operand, then per key tile:
+//            tcgen05.ld half a row of S, causal mask, row maximum exchanged through shared memory, exp2, rescale of O in TMEM
+//            (tcgen05.ld / st) only when some row maximum of the warp moved, P -> shared memory, signal.
 // fp32-ACTIVATION accuracy: q and P are split into bf16 hi + lo terms (two MMAs each into the same accumulator); products with
 // the bf16 K / V are exact in fp32.  bf16-faithful mode uses one term.
 // S is double buffered in TMEM: the scores of key block j+1 are computed while the softmax warps work on block j, and P.V of
@@ -27,7 +28,9 @@ const CUtensorMap* tc_cached_map(const void* ptr, int rows, int K, int box_rows)
 
 constexpr int AT_BM = 128;      // query rows per CTA
 constexpr int AT_BN = 64;       // keys per tile
-constexpr int AT_THREADS = 160;
+constexpr int AT_SM_WARPS = 8;                       // softmax warps: two per TMEM lane quarter, 32 of the 64 key columns each
+constexpr int AT_SM_THREADS = AT_SM_WARPS * 32;
+constexpr int AT_THREADS = AT_SM_THREADS + 32;      // + the TMA / MMA control warp
 
 __device__ __forceinline__ uint32_t at_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void at_mbar_init(uint32_t bar, uint32_t count) {
@@ -124,6 +127,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
   unsigned char* sP = sV + 2 * KV_TILE;                       // [nterms][128][128 B]
   __shared__ __align__(8) uint64_t bars[9];                   // kv_full[2], kv_empty[2], s_full[2], p_ready, pv_done, q_ready
   __shared__ uint32_t s_tmem;
+  __shared__ float s_mx[2][2][AT_BM];   // [tile parity][column half][row]: partial row maxima
+  __shared__ float s_l[AT_BM];          // row sums of the upper column half (final normalisation)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = blockIdx.x * AT_BM, h = blockIdx.y, b = blockIdx.z;
@@ -138,9 +143,9 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
     }
     at_mbar_init(s_full0, 1);
     at_mbar_init(s_full0 + 8, 1);
-    at_mbar_init(p_ready, AT_BM);
+    at_mbar_init(p_ready, AT_SM_THREADS);
     at_mbar_init(pv_done, 1);
-    at_mbar_init(q_ready, AT_BM);
+    at_mbar_init(q_ready, AT_SM_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
@@ -159,7 +164,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
   const int ntiles = (p0 + t0 + rows - 1) / AT_BN + 1;        // key tiles up to the diagonal of the last valid row
   const int kv_row0 = (b * p.G + g) * p.max_seq;              // first cache row of this (batch, group)
 
-  if (warp == 4) {
+  if (warp == AT_SM_WARPS) {
     if (lane == 0) {
       // ======================= TMA producer + MMA issuer =======================
       const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_BN >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
@@ -220,13 +225,16 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
       }
     }
   } else {
-    // ======================= softmax warps: thread r = query row r = TMEM lane r =======================
-    const int r = threadIdx.x;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    // ---- q -> bf16 terms in the swizzled K-major operand layout (coalesced: one warp reads one row at a time) ----
+    // ======================= softmax warps: row r = TMEM lane r, column half `ch` =======================
+    const int wq = warp & 3, ch = warp >> 2;
+    const int r = wq * 32 + lane;
+    constexpr int HC = AT_BN / 2;   // key columns of a tile per thread
+    constexpr int HO = HS / 2;      // O columns per thread
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    // ---- q -> bf16 terms in the swizzled K-major operand layout (coalesced: a warp reads whole rows) ----
     {
       constexpr int LPR = HS / 4;  // lanes per row (float4 each)
-      for (int rr = warp * 32 + lane / LPR; rr < warp * 32 + 32; rr += 32 / LPR) {
+      for (int rr = warp * 16 + lane / LPR; rr < warp * 16 + 16; rr += 32 / LPR) {
         const int d = (lane % LPR) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (rr < rows) v = *reinterpret_cast<const float4*>(p.q + ((size_t)(b * p.T + t0 + rr) * p.H + h) * HS + d);
@@ -254,54 +262,55 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
     for (int j = 0; j < ntiles; ++j) {
       at_mbar_wait(s_full0 + 8 * (j & 1), (j >> 1) & 1);
       at_fence_after();
-      float sc[AT_BN];
+      float sc[HC];
       {
         uint32_t v[32];
-        at_ld32(tmem + lane_base + TM_S + (j & 1) * AT_BN, v);
+        at_ld32(tmem + lane_base + TM_S + (j & 1) * AT_BN + ch * HC, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sc[i] = __uint_as_float(v[i]);
-        at_ld32(tmem + lane_base + TM_S + (j & 1) * AT_BN + 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sc[32 + i] = __uint_as_float(v[i]);
+        for (int i = 0; i < HC; ++i) sc[i] = __uint_as_float(v[i]);
       }
-      const int key0 = j * AT_BN;
-      if (key0 + AT_BN - 1 > p0 + t0 + warp * 32) {  // the tile touches the diagonal for some row of this warp
+      const int key0 = j * AT_BN + ch * HC;
+      if (key0 + HC - 1 > p0 + t0 + wq * 32) {  // these columns touch the diagonal for some row of this warp
 #pragma unroll
-        for (int i = 0; i < AT_BN; ++i)
+        for (int i = 0; i < HC; ++i)
           if (key0 + i > qpos) sc[i] = -CUDART_INF_F;
       }
       float mx = sc[0];
 #pragma unroll
-      for (int i = 1; i < AT_BN; ++i) mx = fmaxf(mx, sc[i]);
+      for (int i = 1; i < HC; ++i) mx = fmaxf(mx, sc[i]);
+      // row maximum over both column halves (the partner warp has the same rows): shared memory, double buffered by tile
+      s_mx[j & 1][ch][r] = mx;
+      asm volatile("bar.sync 1, %0;\n" ::"n"(AT_SM_THREADS) : "memory");
+      mx = fmaxf(mx, s_mx[j & 1][ch ^ 1][r]);
       const float m_new = fmaxf(m_run, mx);             // finite from tile 0 on (key 0 is visible to every row)
       const float base = m_new == -CUDART_INF_F ? 0.f : m_new;
       const float corr = exp2f(m_run - base);           // 0 for the first tile
       float ls = 0.f;
 #pragma unroll
-      for (int i = 0; i < AT_BN; ++i) {
+      for (int i = 0; i < HC; ++i) {
         sc[i] = exp2f(sc[i] - base);
         ls += sc[i];
       }
-      l_run = fmaf(l_run, corr, ls);
+      l_run = fmaf(l_run, corr, ls);  // partial row sum of this column half; the halves are added at the end
       m_run = m_new;
       if (j > 0) {
         at_mbar_wait(pv_done, (j - 1) & 1);  // P.V of the previous block is complete: O is stable, the P buffer is free
         at_fence_after();
-        if (__any_sync(0xffffffffu, corr != 1.0f)) {  // some row maximum of this warp moved: rescale O in tensor memory
+        if (__any_sync(0xffffffffu, corr != 1.0f)) {  // some row maximum of this warp moved: rescale this warp's half of O
 #pragma unroll 1
-          for (int c0 = 0; c0 < HS; c0 += 32) {
+          for (int c0 = 0; c0 < HO; c0 += 32) {
             uint32_t v[32];
-            at_ld32(tmem + lane_base + TM_O + c0, v);
+            at_ld32(tmem + lane_base + TM_O + ch * HO + c0, v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * corr);
-            at_st32(tmem + lane_base + TM_O + c0, v);
+            at_st32(tmem + lane_base + TM_O + ch * HO + c0, v);
           }
         }
       }
-      // ---- P -> bf16 terms, swizzled K-major rows of 64 keys ----
+      // ---- P -> bf16 terms, swizzled K-major rows of 64 keys (this thread: chunks ch*4 .. ch*4+3) ----
       for (int t = 0; t < nterms; ++t) {
 #pragma unroll
-        for (int c = 0; c < AT_BN / 8; ++c) {
+        for (int c = 0; c < HC / 8; ++c) {
           uint32_t w[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -310,22 +319,27 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
             sc[8 * c + 2 * i + 1] -= __bfloat162float(h1);
             w[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
           }
-          *reinterpret_cast<uint4*>(sP + t * Q_SLAB + r * 128 + ((c ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          const int cc = ch * (HC / 8) + c;
+          *reinterpret_cast<uint4*>(sP + t * Q_SLAB + r * 128 + ((cc ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
       at_fence_async_smem();
       at_fence_before();
       at_mbar_arrive(p_ready);
     }
-    // ---- O / l -> out ----
+    // ---- O / l -> out (this thread: its half of the columns; l = sum of both halves) ----
+    if (ch == 1) s_l[r] = l_run;
+    asm volatile("bar.sync 1, %0;\n" ::"n"(AT_SM_THREADS) : "memory");
+    if (ch == 0) s_l[r] += l_run;
+    asm volatile("bar.sync 1, %0;\n" ::"n"(AT_SM_THREADS) : "memory");
     at_mbar_wait(pv_done, (ntiles - 1) & 1);
     at_fence_after();
-    const float inv = 1.0f / l_run;
-    float* dst = p.out + ((size_t)(b * p.T + t0 + r) * p.H + h) * HS;
+    const float inv = 1.0f / s_l[r];
+    float* dst = p.out + ((size_t)(b * p.T + t0 + r) * p.H + h) * HS + ch * HO;
 #pragma unroll 1
-    for (int c0 = 0; c0 < HS; c0 += 32) {
+    for (int c0 = 0; c0 < HO; c0 += 32) {
       uint32_t v[32];
-      at_ld32(tmem + lane_base + TM_O + c0, v);
+      at_ld32(tmem + lane_base + TM_O + ch * HO + c0, v);
       if (r < rows) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
