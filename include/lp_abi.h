@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LP_ABI_VERSION 3
+#define LP_ABI_VERSION 4
 
 typedef enum {
   LP_OK = 0,
@@ -185,8 +185,8 @@ int lp_attn_prefill(const float* q, const void* k_cache, const void* v_cache, in
 
 /* ---- the whole single-token decode step (batch 1) as ONE persistent kernel ------------------------------------------
  * replaces GPT.forward for T == 1 (model.py:63-111 -> Block.forward 158-180 -> CausalSelfAttention.forward 194-254 -> MLP
- * 284-301): the caller describes the step once as an ordered table of ops — LINEAR (lp_norm_linear semantics, M = 1) and
- * ATTENTION (lp_attn_decode_fused semantics) — and lp_decode_step then runs it with two launches (embedding-row prologue +
+ * 284-301): the caller describes the step once as an ordered table of ops — LINEAR (lp_norm_linear semantics, M = 1),
+ * ATTENTION (lp_attn_decode_fused semantics) and, under tensor parallelism, EXCHANGE (lp_tp_allreduce_residual semantics) — and lp_decode_step then runs it with two launches (embedding-row prologue +
  * step kernel).  Inside the step kernel one TMA ring per SM streams the weights and the old K/V rows of ALL ops back to back
  * (they do not depend on the activations), so HBM stays busy while the consumers wait on the grid-wide arrival counter of an
  * op they depend on (csrc/decode_step.cu).
@@ -198,7 +198,7 @@ int lp_attn_prefill(const float* q, const void* k_cache, const void* v_cache, in
  *        of them may overlap (parallel-residual blocks); the summation order of their partial sums is not fixed.
  * Covers fp32-activation mode, bf16 / GPTQ-int4 (tile-major aux2) weights, MHA / GQA / MQA with H <= #SMs, bf16 KV cache,
  * hs 64 / 128, batch 1; LP_ERR_UNSUPPORTED otherwise (callers then issue the per-op calls above). */
-typedef enum { LP_STEP_LINEAR = 0, LP_STEP_ATTENTION = 1 } lp_step_kind;
+typedef enum { LP_STEP_LINEAR = 0, LP_STEP_ATTENTION = 1, LP_STEP_EXCHANGE = 2 } lp_step_kind;
 
 typedef struct {
   int32_t kind;            /* lp_step_kind */
@@ -219,6 +219,15 @@ typedef struct {
   const float* qkv;
   void* k_cache;
   void* v_cache;
+  /* EXCHANGE (tensor parallelism): out = residual + sum over the tp ranks of the [E] partial found at tp_buf_offset of every
+   * rank's symmetric buffer — lp_tp_allreduce_residual inside the step kernel, same arguments and the same `state` (so per-op
+   * and in-kernel exchanges may alternate).  The preceding row-parallel LINEAR op (epilogue NONE) writes this rank's partial to
+   * its own buffer + tp_buf_offset; `dep` is that op.  At most two slots (state pointers), used alternately. */
+  const void* tp_buf_ptrs;
+  const void* tp_pad_ptrs;
+  void* tp_state;
+  uint64_t tp_buf_offset;
+  int32_t tp_pad_base, tp_rank, tp_size, reserved;
 } lp_step_op;
 
 typedef struct {

@@ -17,9 +17,9 @@ LP_F32, LP_BF16 = 0, 1
 LP_W_F32, LP_W_BF16, LP_W_INT4, LP_W_NF4, LP_W_INT8 = 0, 1, 2, 3, 4
 LP_EPI_NONE, LP_EPI_GELU, LP_EPI_SWIGLU, LP_EPI_RESIDUAL = 0, 1, 2, 3
 LP_NORM_LAYERNORM, LP_NORM_RMS = 0, 1
-LP_ABI_VERSION = 3
+LP_ABI_VERSION = 4
 LP_WF_AUX_PACKED = 1
-LP_STEP_LINEAR, LP_STEP_ATTENTION = 0, 1
+LP_STEP_LINEAR, LP_STEP_ATTENTION, LP_STEP_EXCHANGE = 0, 1, 2
 
 c_void_p, c_int, c_float, c_size_t, c_u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_uint64
 
@@ -38,7 +38,9 @@ class LpStepOp(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("dep", ctypes.c_int32), ("W", ctypes.POINTER(LpWeight)), ("x", c_void_p),
                 ("x_is_attention", ctypes.c_int32), ("norm_kind", ctypes.c_int32), ("norm_w", c_void_p), ("norm_b", c_void_p),
                 ("eps", c_float), ("epilogue", ctypes.c_int32), ("residual", c_void_p), ("out", c_void_p),
-                ("qkv", c_void_p), ("k_cache", c_void_p), ("v_cache", c_void_p)]
+                ("qkv", c_void_p), ("k_cache", c_void_p), ("v_cache", c_void_p),
+                ("tp_buf_ptrs", c_void_p), ("tp_pad_ptrs", c_void_p), ("tp_state", c_void_p), ("tp_buf_offset", ctypes.c_uint64),
+                ("tp_pad_base", ctypes.c_int32), ("tp_rank", ctypes.c_int32), ("tp_size", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class LpStepGeom(ctypes.Structure):

@@ -35,7 +35,8 @@ constexpr int DS_EWARPS = 2;                                   // epilogue warps
 constexpr int DS_THREADS = (GS_CWARPS + 1 + DS_EWARPS) * 32;   // consumers + producer warp + epilogue warps
 constexpr int DS_TILE_BAR_THREADS = DS_CTHREADS + 32;          // named barriers 2 / 3: the consumers arrive, one epilogue warp waits
 constexpr int DS_OPEND_THREADS = DS_CTHREADS + DS_EWARPS * 32; // named barrier 4: end of an op
-constexpr int DS_KIND_LINEAR = 0;
+constexpr int DS_KIND_LINEAR = 0, DS_KIND_EXCHANGE = 2;
+constexpr int DS_MAX_TP = 8;
 constexpr int DS_RED_FLOATS = 2 * GS_CWARPS * 16 * 4;  // [2 parities][warps][16 rows][4 B-columns]
 
 struct alignas(128) DsOp {
@@ -54,6 +55,12 @@ struct alignas(128) DsOp {
   int kind, dep, signal;
   int norm_kind, epi, fmt, N, K, split, ldx, nkb, nks, ntiles, ngroups, gp128, aux_bytes, x_attn;
   int streamk;  // in-place residual op: stages (not tiles) are split evenly over the CTAs, partial tiles are added atomically
+  // tensor-parallel exchange (kind 2): out = residual + sum over ranks of the partial at buf_off of every rank's symmetric buffer
+  const unsigned long long* tp_bufs;  // [tp] peer-mapped buffer addresses
+  const unsigned long long* tp_pads;  // [tp] peer-mapped signal pads
+  unsigned int* tp_state;             // [2] of the slot: epoch (shared with lp_tp_allreduce_residual), unused
+  unsigned long long tp_buf_off;
+  int tp_pad_base, tp_rank, tp_size, tp_use, tp_uses;  // tp_use: index of this exchange among the tp_uses of its slot per step
 };
 
 struct DsParams {
@@ -67,6 +74,8 @@ struct DsParams {
   float scale_log2;
   int nops, H, G, n_elem, max_seq, P;
   int nstages, stage_stride, xsum_floats;
+  unsigned int* tp_state0;  // epoch counters of the (up to two) tensor-parallel exchange slots, or NULL
+  unsigned int* tp_state1;
 };
 
 __device__ __forceinline__ unsigned ds_ld_acquire(const unsigned* p) {
@@ -860,6 +869,52 @@ __device__ __forceinline__ void ds_attention(const DsParams& p, const DsOp& o, c
 }
 
 
+// ------------------------------------------------------------------------------------------------ tensor-parallel exchange op
+// One-shot all-reduce over NVLink peer memory inside the step kernel (the protocol of tp_allreduce.cu): the preceding linear op
+// wrote this rank's partial into its slot of the symmetric buffer; CTA 0 publishes the slot's next epoch to every peer, every
+// CTA waits until all peers have published it, then reduces ITS slice of the row (n / #CTAs floats) over all ranks in rank order
+// — bit-identical on every rank — adds the residual and stores it locally.  The epoch counter is the one the per-op kernel uses,
+// so prefill (per-op path) and decode (this kernel) can alternate; it is advanced once per step by the last exchange of a slot.
+__device__ __forceinline__ void ds_exchange(const DsOp& o, unsigned int epoch0) {
+  const int tid = threadIdx.x, tp = o.tp_size;
+  const unsigned int epoch = epoch0 + (unsigned)o.tp_use + 1u;
+  if (tid < tp) {
+    if (blockIdx.x == 0) {  // publish to peer `tid` (and to ourselves): this rank's partial is complete (dependency wait above)
+      __threadfence_system();
+      unsigned int* flag = reinterpret_cast<unsigned int*>(o.tp_pads[tid]) + o.tp_pad_base + o.tp_rank;
+      asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(flag), "r"(epoch) : "memory");
+    }
+    const unsigned int* mine = reinterpret_cast<const unsigned int*>(o.tp_pads[o.tp_rank]) + o.tp_pad_base + tid;
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(mine) : "memory");
+    } while ((int)(v - epoch) < 0);
+  }
+  gs_bar_consumers();
+  const int n4 = o.N / 4;
+  const int i0 = (int)((long long)n4 * blockIdx.x / gridDim.x), i1 = (int)((long long)n4 * (blockIdx.x + 1) / gridDim.x);
+  for (int i = i0 + tid; i < i1; i += DS_CTHREADS) {
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < DS_MAX_TP; ++r) {
+      if (r < tp) {
+        const float4* src = reinterpret_cast<const float4*>(o.tp_bufs[r] + o.tp_buf_off) + i;
+        float4 v;
+        asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src));
+        if (r == 0) sum = v;
+        else { sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w; }
+      }
+    }
+    if (o.residual) {
+      const float4 rv = ds_ldcg4(o.residual + 4 * i);
+      sum.x += rv.x; sum.y += rv.y; sum.z += rv.z; sum.w += rv.w;
+    }
+    *reinterpret_cast<float4*>(o.out + 4 * i) = sum;
+  }
+  // the last exchange of this slot in the step advances the shared epoch counter (every CTA read it at kernel start)
+  if (blockIdx.x == 0 && tid == 0 && o.tp_use == o.tp_uses - 1) o.tp_state[0] = epoch0 + (unsigned)o.tp_uses;
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int HS>
 __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsParams p) {
@@ -939,7 +994,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
             ++tile;
           }
         }
-      } else {
+      } else if (o.kind != DS_KIND_EXCHANGE) {
         if (!have_geo) {
           pdl_wait();  // the position is written by the previous step's sampler
           geo.init(p);
@@ -974,6 +1029,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
   pdl_launch_dependents();
   DsAttnGeo<HS> geo;
   geo.init(p);
+  // tensor parallel: epoch counters of the two exchange slots as of the start of this step
+  unsigned int tp_epoch[2] = {0u, 0u};
+  if (p.tp_state0) tp_epoch[0] = *reinterpret_cast<volatile unsigned int*>(p.tp_state0);
+  if (p.tp_state1) tp_epoch[1] = *reinterpret_cast<volatile unsigned int*>(p.tp_state1);
   int waited = -1, gt = 0;
   for (int op = 0; op < p.nops; ++op) {
     const DsOp& o = p.ops[op];
@@ -994,6 +1053,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
     };
     if (o.kind == DS_KIND_LINEAR) {
       ds_linear<HS>(p, o, geo, rg, red_u32, colscale, xsum, xs_u32, done, s_stat, tr, gt, wait_dep);
+    } else if (o.kind == DS_KIND_EXCHANGE) {
+      wait_dep();
+      ds_exchange(o, o.tp_state == p.tp_state1 ? tp_epoch[1] : tp_epoch[0]);
     } else {
       wait_dep();
       ds_attention<HS>(p, o, geo, rg, xs, tr);
@@ -1038,6 +1100,8 @@ struct DsHostPlan {  // lp_step_handle, opaque to the caller
   const int* idx_offset;
   const void* wte;
   float* x0;
+  unsigned int* tp_state0;
+  unsigned int* tp_state1;
 };
 static_assert(sizeof(DsHostPlan) <= sizeof(lp_step_handle), "lp_step_handle too small");
 constexpr uint32_t DS_MAGIC = 0x4c504453u;
@@ -1083,6 +1147,8 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
   if (gm->H > grid) return LP_ERR_UNSUPPORTED;
 
   std::vector<DsOp> dev(n_ops);
+  unsigned int* tp_state[2] = {nullptr, nullptr};
+  int tp_uses[2] = {0, 0};
   int stage_stride = GS_KB * GS_BLK_BYTES, xsum_floats = 0;
   // attention scratch inside the activation area: q, new k/v, scores, slice sums (ds_attention)
   size_t xs_bytes = (size_t)gm->hs * 4 + 2 * gm->hs * 2 + (size_t)GS_CWARPS * (gm->hs + 4) * 4 + 16;
@@ -1095,6 +1161,33 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
     d.signal = 0;
     if (s.dep >= i || s.dep < -1) return LP_ERR_INVALID_ARG;
     if (s.dep >= 0) dev[s.dep].signal = 1;
+    if (s.kind == LP_STEP_EXCHANGE) {
+      if (!s.tp_buf_ptrs || !s.tp_pad_ptrs || !s.tp_state || !s.out || s.tp_size < 1 || s.tp_size > DS_MAX_TP || s.tp_rank < 0 ||
+          s.tp_rank >= s.tp_size || s.dep < 0)
+        return LP_ERR_INVALID_ARG;
+      if (gm->E % 4 || s.tp_buf_offset % 16) return LP_ERR_UNSUPPORTED;
+      d.kind = DS_KIND_EXCHANGE;
+      d.tp_bufs = reinterpret_cast<const unsigned long long*>(s.tp_buf_ptrs);
+      d.tp_pads = reinterpret_cast<const unsigned long long*>(s.tp_pad_ptrs);
+      d.tp_state = reinterpret_cast<unsigned int*>(s.tp_state);
+      d.tp_buf_off = s.tp_buf_offset;
+      d.tp_pad_base = s.tp_pad_base;
+      d.tp_rank = s.tp_rank;
+      d.tp_size = s.tp_size;
+      d.residual = s.residual;
+      d.out = s.out;
+      d.N = gm->E;
+      if (!tp_state[0] || tp_state[0] == d.tp_state) {
+        tp_state[0] = d.tp_state;
+        d.tp_use = tp_uses[0]++;
+      } else if (!tp_state[1] || tp_state[1] == d.tp_state) {
+        tp_state[1] = d.tp_state;
+        d.tp_use = tp_uses[1]++;
+      } else {
+        return LP_ERR_UNSUPPORTED;  // two alternating slots
+      }
+      continue;
+    }
     if (s.kind == LP_STEP_ATTENTION) {
       if (!s.qkv || !s.k_cache || !s.v_cache) return LP_ERR_INVALID_ARG;
       if ((reinterpret_cast<uintptr_t>(s.k_cache) | reinterpret_cast<uintptr_t>(s.v_cache) | reinterpret_cast<uintptr_t>(s.qkv)) & 15)
@@ -1174,6 +1267,8 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
     d.streamk = (s.epilogue == LP_EPI_RESIDUAL && s.residual == s.out) ? 1 : 0;
     stage_stride = std::max(stage_stride, (GS_KB * GS_BLK_BYTES + aux_stage + 1023) / 1024 * 1024);
   }
+  for (int i = 0; i < n_ops; ++i)
+    if (dev[i].kind == DS_KIND_EXCHANGE) dev[i].tp_uses = tp_uses[dev[i].tp_state == tp_state[1] ? 1 : 0];
   xs_bytes = (xs_bytes + 15) / 16 * 16;
   const size_t tail = 256 + (size_t)DS_RED_FLOATS * 4 + 32 + (size_t)xsum_floats * 4 + xs_bytes;
   const size_t budget = 226 * 1024;  // 227 KB per CTA minus the 1 KB static block
@@ -1210,6 +1305,8 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
   h.idx_offset = gm->idx_offset;
   h.wte = gm->wte;
   h.x0 = gm->x0;
+  h.tp_state0 = tp_state[0];
+  h.tp_state1 = tp_state[1];
   // load-time copy of the op table (synchronous: the staging vector dies at return)
   LP_CUDA_TRY(cudaMemcpy(plan_dev, dev.data(), (size_t)n_ops * sizeof(DsOp), cudaMemcpyHostToDevice));
   memset(handle, 0, sizeof(*handle));
@@ -1244,6 +1341,8 @@ int lp_decode_step(const lp_step_handle* handle, void* stream) {
   p.nstages = h.nstages;
   p.stage_stride = h.stage_stride;
   p.xsum_floats = h.xsum_floats;
+  p.tp_state0 = h.tp_state0;
+  p.tp_state1 = h.tp_state1;
   return h.hs == 128 ? ds_launch<128>(p, h, stream) : ds_launch<64>(p, h, stream);
 }
 

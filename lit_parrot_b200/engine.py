@@ -188,6 +188,27 @@ class Engine:
             ops.append(op)
             return len(ops) - 1
 
+        tp = self.tp
+        n_exch = [0]
+
+        def row_parallel(W, src, dep, from_attn=False):
+            """x += src . W^T.  Single GPU: in place (stage-granular split, atomic accumulation).  Tensor parallel: W is a column
+            shard, the product a partial sum: it goes to this rank's slot of the symmetric buffer and an EXCHANGE op adds all
+            ranks' partials and the residual (the one-shot NVLink all-reduce of lp_tp_allreduce_residual, inside the kernel)."""
+            if tp is None:
+                return linear(W, src, None, _lib.LP_EPI_RESIDUAL, x, x, dep, from_attn=from_attn)
+            slot = n_exch[0] % 2
+            n_exch[0] += 1
+            part = tp.buf.data_ptr() + slot * tp.slot_floats * 4
+            i_part = linear(W, src, None, _lib.LP_EPI_NONE, None, part, dep, from_attn=from_attn)
+            op = _lib.LpStepOp()
+            op.kind, op.dep, op.norm_kind = _lib.LP_STEP_EXCHANGE, i_part, -1
+            op.tp_buf_ptrs, op.tp_pad_ptrs, op.tp_state = tp.buf_ptrs, tp.pad_ptrs, tp.state[slot].data_ptr()
+            op.tp_buf_offset, op.tp_pad_base, op.tp_rank, op.tp_size = slot * tp.slot_floats * 4, slot * tp.size, tp.rank, tp.size
+            op.residual, op.out = x, x
+            ops.append(op)
+            return len(ops) - 1
+
         last = -1
         for li, L in enumerate(self.layers):
             i_qkv = linear(L.qkv, x, (L.n1_w, L.n1_b), _lib.LP_EPI_NONE, None, qkv, last)
@@ -196,15 +217,15 @@ class Engine:
                 i_fc = linear(L.fc, x, n2, self.act, None, u, last)   # reads the old x: streams right behind the QKV weights
                 i_att = attention(li, i_qkv)
                 # x += attn.proj(att); x += mlp.proj(u): both in place (atomic accumulation, stage-granular split), no barrier
-                linear(L.proj, None, None, _lib.LP_EPI_RESIDUAL, x, x, i_att, from_attn=True)
-                last = linear(L.mlp_proj, u, None, _lib.LP_EPI_RESIDUAL, x, x, i_fc)
+                i_proj = row_parallel(L.proj, None, i_att, from_attn=True)
+                last = row_parallel(L.mlp_proj, u, i_fc if tp is None else max(i_fc, i_proj))
             else:
                 if cfg.shared_attention_norm:
                     return self._steps.setdefault(key, None)
                 i_att = attention(li, i_qkv)
-                i_proj = linear(L.proj, None, None, _lib.LP_EPI_RESIDUAL, x, x, i_att, from_attn=True)
+                i_proj = row_parallel(L.proj, None, i_att, from_attn=True)
                 i_fc = linear(L.fc, x, (L.n2_w, L.n2_b), self.act, None, u, i_proj)
-                last = linear(L.mlp_proj, u, None, _lib.LP_EPI_RESIDUAL, x, x, i_fc)
+                last = row_parallel(L.mlp_proj, u, i_fc)
         linear(self.lm_head, x, (self.lnf_w, self.lnf_b), _lib.LP_EPI_NONE, None, logits, last)
 
         n = len(ops)
@@ -297,7 +318,7 @@ class Engine:
         if idx_off is None and self.tc_eligible(rows):
             # wide decode batches (B >= 9) and prefill: projections on the tcgen05 GEMM, weights still streamed once
             return self._run_tc(b, idx_ptr, idx64, pos_ptr, caches, B, T, stream, last_only)
-        if (rows == 1 and self.use_step_kernel and r == 0 and self.tp is None and getattr(self, "trace", None) is None
+        if (rows == 1 and self.use_step_kernel and r == 0 and getattr(self, "trace", None) is None
                 and self.cos is not None and caches[0][0].dtype == torch.bfloat16):
             handle = self._step_plan(b, idx_ptr, idx64, idx_off, pos_ptr, caches)
             if handle is not None:

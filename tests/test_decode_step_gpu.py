@@ -166,3 +166,72 @@ def test_real_width_llama7b_two_layers_step_kernel():
         assert (a - ref).abs().max() < 2e-2 and cosine(a, ref) > 0.999
         torch.testing.assert_close(a, b, rtol=0, atol=1e-4)
     assert not step_kernel_used(m2)
+
+
+def test_step_kernel_exchange_op_self():
+    """The tensor-parallel EXCHANGE op of the step kernel on ONE GPU (tp = 1: the 'peer' buffers are this GPU's own): a hand-built
+    op table  part0 = W0.x | x += part0 | part1 = W1.x | x += part1 | logits = Wl.x , run twice (the slot epochs advance and are
+    shared with lp_tp_allreduce_residual, which is run in between)."""
+    import ctypes
+
+    from lit_parrot_b200 import _lib
+
+    lib = _lib.init(0)
+    E, V = 512, 64
+    g = torch.Generator().manual_seed(77)
+    W = [(torch.randn(E, E, generator=g) * 0.05).bfloat16().to(DEV) for _ in range(2)]
+    Wl = (torch.randn(V, E, generator=g) * 0.05).bfloat16().to(DEV)
+    wte = torch.randn(4, E, generator=g).to(DEV)
+    idx = torch.tensor([2], dtype=torch.int32, device=DEV)
+    pos = torch.zeros(1, dtype=torch.int32, device=DEV)
+    x = torch.zeros(E, device=DEV)
+    logits = torch.zeros(V, device=DEV)
+    buf = torch.zeros(2 * E, device=DEV)                       # two exchange slots
+    pad = torch.zeros(64, dtype=torch.int32, device=DEV)      # signal pad: slot s -> flags [s * tp, (s + 1) * tp)
+    state = torch.zeros(2, 2, dtype=torch.int32, device=DEV)
+    bufs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device=DEV)
+    pads = torch.tensor([pad.data_ptr()], dtype=torch.int64, device=DEV)
+    recs = [_lib.LpWeight(w.data_ptr(), None, None, None, None, _lib.LP_W_BF16, w.shape[0], E, 0, 0, 0) for w in (*W, Wl)]
+    ops = (_lib.LpStepOp * 5)()
+
+    def lin(i, rec, out, dep):
+        ops[i].kind, ops[i].dep, ops[i].W, ops[i].x, ops[i].norm_kind = _lib.LP_STEP_LINEAR, dep, ctypes.pointer(rec), x.data_ptr(), -1
+        ops[i].epilogue, ops[i].out = _lib.LP_EPI_NONE, out
+
+    def exch(i, slot, dep):
+        ops[i].kind, ops[i].dep, ops[i].norm_kind = _lib.LP_STEP_EXCHANGE, dep, -1
+        ops[i].tp_buf_ptrs, ops[i].tp_pad_ptrs, ops[i].tp_state = bufs.data_ptr(), pads.data_ptr(), state[slot].data_ptr()
+        ops[i].tp_buf_offset, ops[i].tp_pad_base, ops[i].tp_rank, ops[i].tp_size = slot * E * 4, slot * 1, 0, 1
+        ops[i].residual, ops[i].out = x.data_ptr(), x.data_ptr()
+
+    lin(0, recs[0], buf.data_ptr(), -1)
+    exch(1, 0, 0)
+    lin(2, recs[1], buf.data_ptr() + E * 4, 1)
+    exch(3, 1, 2)
+    lin(4, recs[2], logits.data_ptr(), 3)
+    ws = torch.zeros(lib.lp_decode_step_workspace_bytes(1, 64), dtype=torch.uint8, device=DEV)
+    gm = _lib.LpStepGeom()
+    gm.pos, gm.idx, gm.idx_offset, gm.wte, gm.x0 = pos.data_ptr(), idx.data_ptr(), None, wte.data_ptr(), x.data_ptr()
+    gm.cos = gm.sin = None
+    gm.workspace, gm.workspace_bytes = ws.data_ptr(), ws.numel()
+    gm.idx_is_int64, gm.wte_dtype, gm.E, gm.H, gm.G, gm.hs, gm.n_elem, gm.max_seq, gm.kv_dtype, gm.scale = 0, _lib.LP_F32, E, 1, 1, 64, 0, 64, _lib.LP_BF16, 1.0
+    plan = torch.zeros(lib.lp_decode_step_plan_bytes(5), dtype=torch.uint8, device=DEV)
+    handle = _lib.LpStepHandle()
+    _lib.check(lib.lp_decode_step_plan(ops, 5, ctypes.byref(gm), plan.data_ptr(), plan.numel(), ctypes.byref(handle)), "plan")
+    x0 = wte[2].double()
+    x1 = x0 + W[0].double() @ x0
+    x2 = x1 + W[1].double() @ x1
+    want = (Wl.double() @ x2).float()
+    stream = torch.cuda.current_stream().cuda_stream
+    for rep in range(3):
+        _lib.check(lib.lp_decode_step(ctypes.byref(handle), stream), "lp_decode_step")
+        torch.cuda.synchronize()
+        torch.testing.assert_close(logits, want, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(x, x2.float(), rtol=1e-4, atol=1e-4)
+        # a per-op exchange on slot 0 in between (the prefill path): same epoch counter
+        tmp = torch.zeros(E, device=DEV)
+        _lib.check(lib.lp_tp_allreduce_residual(bufs.data_ptr(), pads.data_ptr(), 0, 1, 0, 0, state[0].data_ptr(), E, None, tmp.data_ptr(), 0,
+                                                stream), "lp_tp_allreduce_residual")
+        torch.cuda.synchronize()
+        torch.testing.assert_close(tmp, buf[:E])
+    assert state[0, 0].item() == 6 and state[1, 0].item() == 3  # slot 0: 3 in-kernel + 3 per-op exchanges; slot 1: 3
