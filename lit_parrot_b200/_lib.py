@@ -74,6 +74,7 @@ PROTOTYPES = {
     "lp_linear": (c_int, [c_void_p, c_int, ctypes.POINTER(LpWeight), c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "lp_norm_linear": (c_int, [c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, ctypes.POINTER(LpWeight), c_int, c_void_p,
                                c_void_p, c_int, c_void_p]),
+    "lp_set_gemm_pair": (c_int, [c_int]),
     "lp_split_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p]),
     "lp_gemm_bf16_tc": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                 c_int, c_void_p]),

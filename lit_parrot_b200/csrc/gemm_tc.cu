@@ -20,6 +20,8 @@
 // HBM once while the (small) activation tiles stay in L2.
 #include <cuda.h>
 
+#include <atomic>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -53,6 +55,20 @@ __device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tc_tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
                "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+// multicast: the box lands at the same shared-memory offset of every CTA in `mask`, and completes on the mbarrier at the same
+// offset in each of them
+__device__ __forceinline__ void tc_tma_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;\n" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 __device__ __forceinline__ void tc_tma_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(dst),
@@ -113,7 +129,84 @@ struct TcParams {
   int M, N, K, epi, round_bf16, nterms, out_terms;
 };
 
+// Epilogue of one 128 x BN accumulator tile held in TMEM at `tacc`: warp quarter q owns lanes [32 q, +32) = rows m0 + 32 q + lane.
 template <int BN>
+__device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tacc, int m0, int n0, int q, int lane, bool swiglu, int nout) {
+  const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t v[32];
+    tc_ld32(tacc + ((uint32_t)(q * 32) << 16) + c0, v);
+    if (row < p.M) {
+      float y[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int n = n0 + c0 + j;
+        float t = __uint_as_float(v[j]);
+        if (p.bias && n < p.N) t += p.bias[n];
+        y[j] = maybe_round(t, p.round_bf16);
+      }
+      int ncols = 32, ocol = n0 + c0;
+      if (swiglu) {  // W rows interleaved: column 2i = fc_1 row i, 2i+1 = fc_2 row i (model.py:298-300)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = maybe_round(silu(y[2 * j]), p.round_bf16);
+          y[j] = maybe_round(a * y[2 * j + 1], p.round_bf16);
+        }
+        ncols = 16;
+        ocol = (n0 + c0) / 2;
+      } else if (p.epi == LP_EPI_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = maybe_round(gelu_erf(y[j]), p.round_bf16);
+      } else if (p.epi == LP_EPI_RESIDUAL) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (ocol + j < nout) y[j] = maybe_round(p.residual[(size_t)row * nout + ocol + j] + y[j], p.round_bf16);
+      }
+      if (p.out_f32) {
+        float* dst = p.out_f32 + (size_t)row * nout + ocol;
+        if (ocol + ncols <= nout && (nout & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (j < ncols) *reinterpret_cast<float4*>(dst + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncols && ocol + j < nout) dst[j] = y[j];
+        }
+      }
+      if (p.out_bf) {
+        const bool vec = ocol + ncols <= nout && (nout & 7) == 0;  // 16-byte stores of 8 bf16
+        for (int t = 0; t < p.out_terms; ++t) {
+          __nv_bfloat16* dst = p.out_bf + ((size_t)t * p.M + row) * nout + ocol;
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(y[j]), h1 = __float2bfloat16_rn(y[j + 1]);
+            y[j] -= __bfloat162float(h0);
+            y[j + 1] -= __bfloat162float(h1);
+            pk[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          }
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              if (j < ncols) *reinterpret_cast<uint4*>(dst + j) = make_uint4(pk[j / 2], pk[j / 2 + 1], pk[j / 2 + 2], pk[j / 2 + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols && ocol + j < nout)
+                dst[j] = __ushort_as_bfloat16((unsigned short)((j & 1) ? (pk[j / 2] >> 16) : (pk[j / 2] & 0xffffu)));
+          }
+        }
+      }
+    }
+  }
+}
+
+// CL = 2: the CTAs of a 2-CTA cluster work on neighbouring M tiles of the SAME N tile (tiles_m even) in lock step and share the W
+// tile: each loads one half of its rows and multicasts it to both, which cuts the L2 -> SM traffic the kernel is bound by from
+// (nterms * 16 + BN / 8) KB to (nterms * 16 + BN / 16) KB per k-block.  A ring slot is free once BOTH CTAs' MMAs have read it.
+template <int BN, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p, int nstages) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -137,7 +230,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < nstages; ++s) {
       tc_mbar_init(full_bar(s), 1);
-      tc_mbar_init(empty_bar(s), 1);
+      tc_mbar_init(empty_bar(s), CL);  // CL = 2: this CTA's and the partner's MMAs have both read the slot
     }
     for (int a = 0; a < 2; ++a) {
       tc_mbar_init(acc_full(a), 1);
@@ -153,6 +246,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
+  uint32_t cta_rank = 0;
+  if (CL == 2) {
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(cta_rank));
+    tc_cluster_sync();  // the partner's barriers are initialised before anything is multicast to them
+  }
 
   pdl_wait();  // the activation terms are written by the preceding kernel
   pdl_launch_dependents();
@@ -169,7 +267,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           tc_mbar_expect_tx(full_bar(s), stage_bytes);
           for (int t = 0; t < p.nterms; ++t)  // term t of X: rows [t*M + m0, +128) of the stacked [nterms*M, K] tensor
             tc_tma_2d(dst + t * A_BYTES, &map_x, kb * TC_BK, t * p.M + m0, full_bar(s));
-          tc_tma_2d(dst + p.nterms * A_BYTES, &map_w, kb * TC_BK, n0, full_bar(s));
+          if (CL == 1)
+            tc_tma_2d(dst + p.nterms * A_BYTES, &map_w, kb * TC_BK, n0, full_bar(s));
+          else  // this CTA's half of the W tile's rows, to both CTAs (map_w has a BN / 2 row box)
+            tc_tma_2d_mc(dst + p.nterms * A_BYTES + cta_rank * (B_BYTES / 2), &map_w, kb * TC_BK, n0 + (int)cta_rank * (BN / 2), full_bar(s),
+                         (uint16_t)3);
           if (++s == nstages) { s = 0; ph ^= 1; }
         }
       }
@@ -199,7 +301,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
               accumulate = 1;
             }
           }
-          tc_commit(empty_bar(s));  // the slot is free once these MMAs have read it
+          if (CL == 1) tc_commit(empty_bar(s));  // the slot is free once these MMAs have read it
+          else tc_commit_mc(empty_bar(s), (uint16_t)3);  // ... in both CTAs: the partner multicasts into this slot too
           if (++s == nstages) { s = 0; ph ^= 1; }
         }
         tc_commit(acc_full(a));  // accumulator complete
@@ -215,86 +318,178 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int a = it & 1;
     const int m0 = (tile % tiles_m) * TC_BM, n0 = (tile / tiles_m) * BN;
-    const int row = m0 + q * 32 + lane;
     tc_mbar_wait(acc_full(a), (it >> 1) & 1);
     tc_fence_after();
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tc_ld32(tmem + a * BN + ((uint32_t)(q * 32) << 16) + c0, v);
-      if (row < p.M) {
-        float y[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c0 + j;
-          float t = __uint_as_float(v[j]);
-          if (p.bias && n < p.N) t += p.bias[n];
-          y[j] = maybe_round(t, p.round_bf16);
-        }
-        int ncols = 32, ocol = n0 + c0;
-        if (swiglu) {  // W rows interleaved: column 2i = fc_1 row i, 2i+1 = fc_2 row i (model.py:298-300)
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a = maybe_round(silu(y[2 * j]), p.round_bf16);
-            y[j] = maybe_round(a * y[2 * j + 1], p.round_bf16);
-          }
-          ncols = 16;
-          ocol = (n0 + c0) / 2;
-        } else if (p.epi == LP_EPI_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = maybe_round(gelu_erf(y[j]), p.round_bf16);
-        } else if (p.epi == LP_EPI_RESIDUAL) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (ocol + j < nout) y[j] = maybe_round(p.residual[(size_t)row * nout + ocol + j] + y[j], p.round_bf16);
-        }
-        if (p.out_f32) {
-          float* dst = p.out_f32 + (size_t)row * nout + ocol;
-          if (ocol + ncols <= nout && (nout & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (j < ncols) *reinterpret_cast<float4*>(dst + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols && ocol + j < nout) dst[j] = y[j];
-          }
-        }
-        if (p.out_bf) {
-          const bool vec = ocol + ncols <= nout && (nout & 7) == 0;  // 16-byte stores of 8 bf16
-          for (int t = 0; t < p.out_terms; ++t) {
-            __nv_bfloat16* dst = p.out_bf + ((size_t)t * p.M + row) * nout + ocol;
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const __nv_bfloat16 h0 = __float2bfloat16_rn(y[j]), h1 = __float2bfloat16_rn(y[j + 1]);
-              y[j] -= __bfloat162float(h0);
-              y[j + 1] -= __bfloat162float(h1);
-              pk[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            }
-            if (vec) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8)
-                if (j < ncols) *reinterpret_cast<uint4*>(dst + j) = make_uint4(pk[j / 2], pk[j / 2 + 1], pk[j / 2 + 2], pk[j / 2 + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols && ocol + j < nout)
-                  dst[j] = __ushort_as_bfloat16((unsigned short)((j & 1) ? (pk[j / 2] >> 16) : (pk[j / 2] & 0xffffu)));
-            }
-          }
-        }
-      }
-    }
+    tc_epilogue_tile<BN>(p, tmem + a * BN, m0, n0, q, lane, swiglu, nout);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(acc_empty(a)) : "memory");  // TMEM buffer may be reused
     }
   }
   __syncthreads();
+  if (CL == 2) tc_cluster_sync();  // no CTA leaves while the partner may still multicast into it / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(2 * BN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA PAIRS (cta_group::2): one 256 x 256 output tile per 2-CTA cluster.  With one CTA per tile the SS-mode MMA is bound by
+// shared-memory bandwidth (per k-block the TMA writes and the MMA reads nterms * 16 + 32 KB each: ~190 B/clk of 128); as a
+// pair each SM holds its own 128 rows of X and HALF of the W tile (128 of its 256 rows) and the tensor cores of both SMs see
+// both halves, so per SM the traffic drops to nterms * 16 + 16 KB per k-block at the same MMA time.
+//   both CTAs : TMA producer (own X rows, own half of W) — every load completes on the LEADER's `full` barrier;
+//   leader    : issues tcgen05.mma.cta_group::2 (M 256, N 256, K 16) from its own descriptors (same offsets in both CTAs);
+//               tcgen05.commit multicast frees the ring slot / publishes the accumulator in BOTH CTAs;
+//   both CTAs : epilogue of their 128 accumulator rows; the `accumulator drained` arrivals go to the leader's barrier.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tc_mapa(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void tc_tma_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(leader_bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma2(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {  // arrives on the barrier at this offset in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p, int nstages) {
+  constexpr int BN = 256;                        // N of the pair's tile; each CTA stages BN / 2 rows of W
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int A_BYTES = TC_BM * TC_BK * 2;         // per term: this CTA's 128 rows of X
+  constexpr int B_BYTES = (BN / 2) * TC_BK * 2;  // this CTA's half of the W tile
+  const int stage_bytes = p.nterms * A_BYTES + B_BYTES;
+  __shared__ __align__(8) uint64_t bars[2 * 12 + 4];
+  __shared__ uint32_t s_tmem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
+  const bool leader = rank == 0;
+  const int nk = (p.K + TC_BK - 1) / TC_BK;
+  const int tiles_m = (p.M + 2 * TC_BM - 1) / (2 * TC_BM), tiles_n = (p.N + BN - 1) / BN;
+  const int ntiles = tiles_m * tiles_n;
+  const int cluster = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const uint32_t bar0 = tc_smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8 * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8 * (12 + s); };
+  auto acc_full = [&](int a) { return bar0 + 8 * (24 + a); };
+  auto acc_empty = [&](int a) { return bar0 + 8 * (26 + a); };
+  const uint32_t ring = tc_smem_u32(smem);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstages; ++s) {
+      tc_mbar_init(full_bar(s), 1);   // leader: its own arrive.expect_tx; the bytes of both CTAs' loads complete on it
+      tc_mbar_init(empty_bar(s), 1);  // one multicast commit of the leader
+    }
+    for (int a = 0; a < 2; ++a) {
+      tc_mbar_init(acc_full(a), 1);   // one multicast commit of the leader
+      tc_mbar_init(acc_empty(a), 8);  // leader: one arrival per epilogue warp of BOTH CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  tc_cluster_sync();  // both CTAs' barriers exist
+  if (warp == 2) {    // TMEM of both SMs: two accumulators of BN fp32 columns; one warp of each CTA takes part
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tc_smem_u32(&s_tmem)), "r"(2 * BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (lane == 0) {
+      int s = 0, ph = 0;
+      for (int tile = cluster; tile < ntiles; tile += nclusters) {
+        const int m0 = (tile % tiles_m) * 2 * TC_BM + (int)rank * TC_BM, n0 = (tile / tiles_m) * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < nk; ++kb) {
+          tc_mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t dst = ring + (uint32_t)s * stage_bytes;
+          const uint32_t lfull = tc_mapa(full_bar(s), 0);  // the leader's barrier
+          if (leader) tc_mbar_expect_tx(full_bar(s), 2 * stage_bytes);
+          for (int t = 0; t < p.nterms; ++t)
+            tc_tma_2d_pair(dst + t * A_BYTES, &map_x, kb * TC_BK, t * p.M + m0, lfull);
+          tc_tma_2d_pair(dst + p.nterms * A_BYTES, &map_w, kb * TC_BK, n0, lfull);
+          if (++s == nstages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ===== MMA issuer (leader only) =====
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+      int s = 0, ph = 0, it = 0;
+      for (int tile = cluster; tile < ntiles; tile += nclusters, ++it) {
+        const int a = it & 1;
+        tc_mbar_wait(acc_empty(a), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem + a * BN;
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < nk; ++kb) {
+          tc_mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t a0 = ring + (uint32_t)s * stage_bytes;
+          const uint32_t b0 = a0 + p.nterms * A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t db = tc_smem_desc(b0 + k * 32);
+            for (int t = 0; t < p.nterms; ++t) {
+              tc_mma2(tacc, tc_smem_desc(a0 + t * A_BYTES + k * 32), db, idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          tc_commit2(empty_bar(s));
+          if (++s == nstages) { s = 0; ph ^= 1; }
+        }
+        tc_commit2(acc_full(a));
+      }
+    }
+  }
+  if (warp >= 2) {
+    // ===== epilogue (both CTAs): this CTA's 128 rows x 256 columns =====
+    const int q = warp & 3;
+    const bool swiglu = p.epi == LP_EPI_SWIGLU;
+    const int nout = swiglu ? p.N / 2 : p.N;
+    int it = 0;
+    for (int tile = cluster; tile < ntiles; tile += nclusters, ++it) {
+      const int a = it & 1;
+      const int m0 = (tile % tiles_m) * 2 * TC_BM + (int)rank * TC_BM, n0 = (tile / tiles_m) * BN;
+      tc_mbar_wait(acc_full(a), (it >> 1) & 1);
+      tc_fence_after();
+      tc_epilogue_tile<BN>(p, tmem + a * BN, m0, n0, q, lane, swiglu, nout);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {  // the accumulator may be reused: tell the leader
+        const uint32_t lb = tc_mapa(acc_empty(a), 0);
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(lb) : "memory");
+      }
+    }
+  }
+  __syncthreads();
+  tc_cluster_sync();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(2 * BN) : "memory");
   }
 }
 
@@ -632,10 +827,10 @@ static const CUtensorMap* tc_cached_map3(const void* ptr, int rows, int K, int b
   return &cache.emplace(key, m).first->second;
 }
 
-template <int BN>
+template <int BN, int CL>
 static int tc_launch(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, void* stream) {
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN>;
+  auto kern = gemm_tc_kernel<BN, CL>;
   if (!attr_set) {
     LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
@@ -646,8 +841,65 @@ static int tc_launch(const CUtensorMap& mx, const CUtensorMap& mw, const TcParam
   if (nstages < 2) return LP_ERR_UNSUPPORTED;
   const size_t smem = (size_t)nstages * stage_bytes + 1024;
   const int ntiles = ((p.M + TC_BM - 1) / TC_BM) * ((p.N + BN - 1) / BN);
-  const int grid = ntiles < num_sms() ? ntiles : num_sms();
-  return launch(kern, dim3(grid), dim3(TC_THREADS), smem, stream, mx, mw, p, nstages);
+  int grid = ntiles < num_sms() ? ntiles : num_sms();
+  if (CL == 1) return launch(kern, dim3(grid), dim3(TC_THREADS), smem, stream, mx, mw, p, nstages);
+  // 2-CTA clusters: even grid; tiles_m is even, so CTAs 2i and 2i+1 always get tiles t, t+1 of one N tile and the same number
+  // of them (the pair runs in lock step)
+  grid &= ~1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  LP_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, mx, mw, p, nstages));
+  count_launch();
+  return LP_OK;
+}
+
+static std::atomic<int> g_gemm_pair{[] {
+  const char* e = getenv("LP_GEMM_PAIR");
+  return e ? atoi(e) : 0;
+}()};
+
+static int tc_launch_pair(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, void* stream) {
+  static bool attr_set = false;
+  auto kern = gemm_tc_pair_kernel;
+  if (!attr_set) {
+    LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  const int stage_bytes = p.nterms * TC_BM * TC_BK * 2 + 128 * TC_BK * 2;
+  int nstages = (212 * 1024) / stage_bytes;
+  if (nstages > 12) nstages = 12;
+  const size_t smem = (size_t)nstages * stage_bytes + 1024;
+  const int ntiles = ((p.M + 2 * TC_BM - 1) / (2 * TC_BM)) * ((p.N + 255) / 256);
+  int grid = 2 * ntiles < num_sms() ? 2 * ntiles : (num_sms() & ~1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  LP_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, mx, mw, p, nstages));
+  count_launch();
+  return LP_OK;
 }
 
 static int tc_launch_swap(const CUtensorMap& mx, const CUtensorMap& mw, const TcSwapParams& p, void* stream) {
@@ -670,6 +922,11 @@ static int tc_launch_swap(const CUtensorMap& mx, const CUtensorMap& mw, const Tc
 }  // namespace lp
 
 extern "C" {
+
+int lp_set_gemm_pair(int enabled) {
+  lp::g_gemm_pair.store(enabled ? 1 : 0);
+  return LP_OK;
+}
 
 int lp_split_bf16(const float* x, void* out_bf16, int rows, int K, int nterms, int norm_kind, const float* norm_w, const float* norm_b,
                   float eps, int round_bf16, void* stream) {
@@ -733,7 +990,26 @@ int lp_gemm_bf16_tc(const void* x_terms, int nterms, int M, const void* w_bf16, 
     }
   }
   const CUtensorMap* mx = lp::tc_cached_map(x_terms, nterms * M, K, lp::TC_BM);
-  const CUtensorMap* mw = lp::tc_cached_map(w_bf16, N, K, BN);
+  // W-tile multicast over CTA pairs: prefill-sized problems whose M tiles pair up inside one N tile
+  static const bool cl_env = [] {
+    const char* e = getenv("LP_GEMM_CLUSTER");
+    return !(e && e[0] == '0');
+  }();
+  // CTA pairs are opt-in (lp_set_gemm_pair / LP_GEMM_PAIR=1): parity-tested, but measured no faster than single CTAs yet
+  if (lp::g_gemm_pair.load() && BN == 256 && (long long)((M + 255) / 256) * ((N + 255) / 256) * 2 >= lp::num_sms()) {
+    // prefill-sized: CTA pairs (cta_group::2), 256 x 256 tiles
+    const CUtensorMap* mx2 = lp::tc_cached_map(x_terms, nterms * M, K, lp::TC_BM);
+    const CUtensorMap* mw2 = lp::tc_cached_map(w_bf16, N, K, 128);
+    if (mx2 && mw2) {
+      lp::TcParams q;
+      q.bias = bias; q.residual = residual; q.out_f32 = out_f32; q.out_bf = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+      q.M = M; q.N = N; q.K = K; q.epi = epilogue; q.round_bf16 = round_bf16; q.nterms = nterms; q.out_terms = out_terms;
+      return lp::tc_launch_pair(*mx2, *mw2, q, stream);
+    }
+  }
+  const int tiles_n = (N + BN - 1) / BN;
+  const bool pair = cl_env && BN >= 128 && tiles_m % 2 == 0 && (long long)tiles_m * tiles_n >= 2LL * lp::num_sms();
+  const CUtensorMap* mw = lp::tc_cached_map(w_bf16, N, K, pair ? BN / 2 : BN);
   if (!mx || !mw) return LP_ERR_UNSUPPORTED;
   lp::TcParams p;
   p.bias = bias;
@@ -747,11 +1023,12 @@ int lp_gemm_bf16_tc(const void* x_terms, int nterms, int M, const void* w_bf16, 
   p.round_bf16 = round_bf16;
   p.nterms = nterms;
   p.out_terms = out_terms;
+  if (pair) return BN == 256 ? lp::tc_launch<256, 2>(*mx, *mw, p, stream) : lp::tc_launch<128, 2>(*mx, *mw, p, stream);
   switch (BN) {
-    case 256: return lp::tc_launch<256>(*mx, *mw, p, stream);
-    case 128: return lp::tc_launch<128>(*mx, *mw, p, stream);
-    case 64: return lp::tc_launch<64>(*mx, *mw, p, stream);
-    default: return lp::tc_launch<32>(*mx, *mw, p, stream);
+    case 256: return lp::tc_launch<256, 1>(*mx, *mw, p, stream);
+    case 128: return lp::tc_launch<128, 1>(*mx, *mw, p, stream);
+    case 64: return lp::tc_launch<64, 1>(*mx, *mw, p, stream);
+    default: return lp::tc_launch<32, 1>(*mx, *mw, p, stream);
   }
 }
 

@@ -412,10 +412,12 @@ def test_norm_linear_fused(lib, kind, fmt, M, N, K):
 
 @pytest.mark.parametrize("nterms", [1, 2, 3])
 @pytest.mark.parametrize("M,N,K", [(16, 128, 64), (128, 256, 512), (200, 384, 4096), (333, 4608, 4544), (2048, 512, 1024), (9, 1280, 8192),
-                                   (150, 4544, 1024), (70, 200, 136), (32, 4096, 4096), (33, 4672, 4544), (64, 200, 136), (48, 16384, 512)])
+                                   (150, 4544, 1024), (70, 200, 136), (32, 4096, 4096), (33, 4672, 4544), (64, 200, 136), (48, 16384, 512),
+                                   (1024, 4864, 256), (777, 6400, 320), (512, 9736, 128)])  # the last three: CTA-pair (cta_group::2) kernel
 def test_gemm_bf16_tc(lib, nterms, M, N, K):
     """lp_split_bf16 + lp_gemm_bf16_tc (TMA + tcgen05.mma, accumulator in tensor memory) against float64 F.linear.
     nterms = 1: bf16 activations (the reference's bf16-true matmul inputs); 2 / 3: fp32-activation accuracy."""
+    lib.lp_set_gemm_pair(1 if (M, N, K) in ((1024, 4864, 256), (777, 6400, 320), (512, 9736, 128)) else 0)
     x = f32(M, K, seed=1)
     w = f32(N, K, seed=2, scale=0.05).bfloat16()
     bias = f32(N, seed=3)
@@ -441,6 +443,7 @@ def test_gemm_bf16_tc(lib, nterms, M, N, K):
             torch.testing.assert_close(out, want, **tol)
         # the bf16 split of the result (operand of the next GEMM): hi + lo reproduces it to 16 bits
         torch.testing.assert_close(out_t.float().sum(0), out, rtol=2 ** -15, atol=1e-30)
+    lib.lp_set_gemm_pair(0)
     # fused norm in the splitter
     nw, nb = 1 + 0.1 * f32(K, seed=5), 0.1 * f32(K, seed=6)
     for kind in (0, 1):
