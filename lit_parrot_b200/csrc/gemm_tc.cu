@@ -707,50 +707,87 @@ gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 // ---------------------------------------------------------------------------------------------------------------------
 // x fp32 [rows, K] (optionally through LayerNorm / RMSNorm) -> nterms bf16 arrays [nterms][rows, K] with x = sum of terms
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int rows, int K,
-                                                         int nterms, int norm_kind, const float* __restrict__ nw,
-                                                         const float* __restrict__ nb, float eps, int round_bf16) {
-  __shared__ float red[2][8];
+// One block of 512 threads per row; the row is read ONCE (float4 per thread and pass, up to 8 passes = 16384 columns, kept in
+// registers through the statistics and the split; longer rows are re-read).  Decode batches call this with a handful of rows, so
+// the kernel is latency-bound: one pass and two block reductions instead of three passes.
+constexpr int SPL_THREADS = 512;
+constexpr int SPL_CACHE = 8;
+__global__ void __launch_bounds__(SPL_THREADS) split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int rows, int K,
+                                                                 int nterms, int norm_kind, const float* __restrict__ nw,
+                                                                 const float* __restrict__ nb, float eps, int round_bf16) {
+  __shared__ float red[2][SPL_THREADS / 32];
   pdl_wait();
   pdl_launch_dependents();
   const int r = blockIdx.x;
   const float* xr = x + (size_t)r * K;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float mean = 0.f, rstd = 1.f;
-  auto block_sum = [&](float v, int slot) {
-    v = warp_sum(v);
-    __syncthreads();
-    if (lane == 0) red[slot][warp] = v;
-    __syncthreads();
-    float t = 0.f;
+  const bool vec = (K & 3) == 0 && K <= SPL_CACHE * SPL_THREADS * 4;  // register-cached path
+  float4 xc[SPL_CACHE];
+  if (vec) {
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[slot][w];
-    return t;
+    for (int i = 0; i < SPL_CACHE; ++i) {
+      const int k = (i * SPL_THREADS + threadIdx.x) * 4;
+      xc[i] = k < K ? *reinterpret_cast<const float4*>(xr + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  auto block_sum2 = [&](float& a, float& b) {  // both sums with one pair of barriers
+    a = warp_sum(a);
+    b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) {
+      red[0][warp] = a;
+      red[1][warp] = b;
+    }
+    __syncthreads();
+    a = 0.f;
+    b = 0.f;
+#pragma unroll
+    for (int w = 0; w < SPL_THREADS / 32; ++w) {
+      a += red[0][w];
+      b += red[1][w];
+    }
   };
+  float mean = 0.f, rstd = 1.f;
   if (norm_kind >= 0) {
     float s = 0.f, ss = 0.f;
-    for (int k = threadIdx.x; k < K; k += 256) {
-      const float v = xr[k];
-      s += v;
-      ss += v * v;
+    if (vec) {
+#pragma unroll
+      for (int i = 0; i < SPL_CACHE; ++i) {
+        s += (xc[i].x + xc[i].y) + (xc[i].z + xc[i].w);
+        ss += xc[i].x * xc[i].x + xc[i].y * xc[i].y + xc[i].z * xc[i].z + xc[i].w * xc[i].w;
+      }
+    } else {
+      for (int k = threadIdx.x; k < K; k += SPL_THREADS) {
+        const float v = xr[k];
+        s += v;
+        ss += v * v;
+      }
     }
-    s = block_sum(s, 0);
-    ss = block_sum(ss, 1);
+    block_sum2(s, ss);
     if (norm_kind == LP_NORM_LAYERNORM) {
       mean = s / (float)K;
-      float v2 = 0.f;
-      for (int k = threadIdx.x; k < K; k += 256) {
-        const float d = xr[k] - mean;
-        v2 += d * d;
+      float v2 = 0.f, dummy = 0.f;  // two-pass variance
+      if (vec) {
+#pragma unroll
+        for (int i = 0; i < SPL_CACHE; ++i) {
+          if ((i * SPL_THREADS + threadIdx.x) * 4 < K) {
+            const float d0 = xc[i].x - mean, d1 = xc[i].y - mean, d2 = xc[i].z - mean, d3 = xc[i].w - mean;
+            v2 += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+          }
+        }
+      } else {
+        for (int k = threadIdx.x; k < K; k += SPL_THREADS) {
+          const float d = xr[k] - mean;
+          v2 += d * d;
+        }
       }
-      v2 = block_sum(v2, 0);
+      block_sum2(v2, dummy);
       rstd = 1.0f / sqrtf(v2 / (float)K + eps);
     } else {
       rstd = 1.0f / sqrtf(ss / (float)K + eps);
     }
   }
-  for (int k = threadIdx.x; k < K; k += 256) {
-    float v = xr[k];
+  auto emit = [&](int k, float v) {
     if (norm_kind == LP_NORM_LAYERNORM) v = (v - mean) * rstd * nw[k] + (nb ? nb[k] : 0.f);
     else if (norm_kind == LP_NORM_RMS) v = nw[k] * (v * rstd);
     v = maybe_round(v, round_bf16);
@@ -759,6 +796,43 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
       out[((size_t)t * rows + r) * K + k] = h;
       v -= __bfloat162float(h);
     }
+  };
+  if (vec) {
+#pragma unroll
+    for (int i = 0; i < SPL_CACHE; ++i) {
+      const int k = (i * SPL_THREADS + threadIdx.x) * 4;
+      if (k < K) {
+        float v[4] = {xc[i].x, xc[i].y, xc[i].z, xc[i].w};
+        float w4[4] = {1.f, 1.f, 1.f, 1.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (norm_kind >= 0) {
+          const float4 t = *reinterpret_cast<const float4*>(nw + k);
+          w4[0] = t.x; w4[1] = t.y; w4[2] = t.z; w4[3] = t.w;
+          if (norm_kind == LP_NORM_LAYERNORM && nb) {
+            const float4 u = *reinterpret_cast<const float4*>(nb + k);
+            b4[0] = u.x; b4[1] = u.y; b4[2] = u.z; b4[3] = u.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (norm_kind == LP_NORM_LAYERNORM) v[j] = (v[j] - mean) * rstd * w4[j] + b4[j];
+          else if (norm_kind == LP_NORM_RMS) v[j] = w4[j] * (v[j] * rstd);
+          v[j] = maybe_round(v[j], round_bf16);
+        }
+        for (int t = 0; t < nterms; ++t) {  // 8-byte stores of 4 bf16
+          uint32_t pk[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+            v[2 * j] -= __bfloat162float(h0);
+            v[2 * j + 1] -= __bfloat162float(h1);
+            pk[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          }
+          *reinterpret_cast<uint2*>(out + ((size_t)t * rows + r) * K + k) = make_uint2(pk[0], pk[1]);
+        }
+      }
+    }
+  } else {
+    for (int k = threadIdx.x; k < K; k += SPL_THREADS) emit(k, xr[k]);
   }
 }
 
@@ -838,6 +912,11 @@ static int tc_launch(const CUtensorMap& mx, const CUtensorMap& mw, const TcParam
   const int stage_bytes = p.nterms * TC_BM * TC_BK * 2 + BN * TC_BK * 2;
   int nstages = (212 * 1024) / stage_bytes;
   if (nstages > 12) nstages = 12;
+  static const int cap = [] {  // tuning aid: LP_GEMM_STAGES caps the ring depth
+    const char* e = getenv("LP_GEMM_STAGES");
+    return e ? atoi(e) : 0;
+  }();
+  if (cap > 1 && nstages > cap) nstages = cap;
   if (nstages < 2) return LP_ERR_UNSUPPORTED;
   const size_t smem = (size_t)nstages * stage_bytes + 1024;
   const int ntiles = ((p.M + TC_BM - 1) / TC_BM) * ((p.N + BN - 1) / BN);
@@ -932,7 +1011,7 @@ int lp_split_bf16(const float* x, void* out_bf16, int rows, int K, int nterms, i
                   float eps, int round_bf16, void* stream) {
   if (!x || !out_bf16 || rows <= 0 || K <= 0 || nterms < 1 || nterms > 3) return LP_ERR_INVALID_ARG;
   if (norm_kind >= 0 && !norm_w) return LP_ERR_INVALID_ARG;
-  return lp::launch(lp::split_bf16_kernel, dim3(rows), dim3(256), 0, stream, x, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, K, nterms,
+  return lp::launch(lp::split_bf16_kernel, dim3(rows), dim3(lp::SPL_THREADS), 0, stream, x, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, K, nterms,
                     norm_kind, norm_w, norm_b, eps, round_bf16);
 }
 
