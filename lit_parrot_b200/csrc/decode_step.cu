@@ -22,6 +22,7 @@
 // (embedding row, counter reset) + this kernel.  Judged on whole-step GB/s against the HBM roofline.
 #include <math_constants.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -74,6 +75,8 @@ struct DsParams {
   float scale_log2;
   int nops, H, G, n_elem, max_seq, P;
   int nstages, stage_stride, xsum_floats;
+  int i4pair;  // int4 ops use the paired main loop (even stage count)
+  int l2_ahead;  // weight stages the producer keeps prefetched into L2 beyond the shared-memory ring
   unsigned int* tp_state0;  // epoch counters of the (up to two) tensor-parallel exchange slots, or NULL
   unsigned int* tp_state1;
 };
@@ -96,6 +99,11 @@ __device__ __forceinline__ float4 ds_ldcg4(const float* p) { return __ldcg(reint
 // `bytes` (multiple of 16) of constants into L2: issued by the producer thread well ahead of the consumers' need
 __device__ __forceinline__ void ds_prefetch_l2(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// one weight stage (same tensor map and box as the TMA load) into L2 only
+__device__ __forceinline__ void ds_prefetch_stage_l2(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];\n" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 struct DsRing {
@@ -546,6 +554,127 @@ __device__ __forceinline__ void ds_linear_main(const DsOp& o, DsRing& rg, uint32
   rg.ph = rph;
 }
 
+// int4 main loop, "paired" form (ring with an even number of stages): the stage loop of ds_linear_main costs ~60 SASS
+// instructions per warp and stage around ~55 of arithmetic (mbarrier wait / arrive, ring and K bookkeeping, bounds and tile
+// checks), and at int4 width the issue slots are what paces the stream.  Here a warp visits only every other stage — warps
+// with (warp & 1) == h own the ring slots of parity h — and works on a whole K-block (both 128-column groups, 2 KB) there, so
+// the fixed part is paid once per 2 KB.  A slot is released by its 8 warps with an arrival count of 2 each (the barrier keeps
+// its count of GS_CWARPS: attention and the bf16 loops share the ring).  Slot parity is fixed per warp because the stage
+// count is even, so every warp sees every phase of the barriers it waits on.
+__device__ __forceinline__ void mbar_arrive2(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], 2;\n" ::"r"(bar) : "memory");
+}
+
+template <bool PACKED>
+__device__ __forceinline__ void ds_linear_main_i4pair(const DsOp& o, DsRing& rg, uint32_t red_u32, uint32_t xsum_u32, uint32_t xs_u32,
+                                                      volatile int* done, int sb, int se, int& gt, bool nomath) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int nks = o.nks, split = o.split, ldx = o.ldx, gp128 = o.gp128;
+  const int kbl = warp >> 1, h = warp & 1;
+  const int bcol = g < split ? g : split - 1;
+  const int nunits = se - sb;
+  const int nslices = (o.K + 127) / 128;
+  const int pr0 = (g >> 1) + 4 * (g & 1);
+  constexpr int AUXB = PACKED ? 4 : 8;
+  constexpr uint32_t XSTEP = GS_KB * 2 * 128, XSUMSTEP = GS_KB * 2 * 4 * 4;
+  // lane-constant offsets of the FIRST group of the warp's K-block; the second group is + 128 B (x digits), + 16 B (digit
+  // sums), ^ 64 B (weights: chunk (4 + t) ^ (row & 7) under the 128-byte swizzle), + 16 AUXB (scales)
+  const uint32_t woff = ds_pin((uint32_t)(kbl * GS_BLK_BYTES + pr0 * 128 + ((t ^ (pr0 & 7)) << 4)));
+  const uint32_t xpos0 = ds_pin(xs_u32 + (uint32_t)(bcol * ldx + kbl * 256 + t * 32));
+  const uint32_t xsum0 = ds_pin(xsum_u32 + (uint32_t)(kbl * 8 + 2 * (t & 1)) * 4);
+  const uint32_t aux0 = ds_pin((uint32_t)(GS_KB * GS_BLK_BYTES + (kbl * 32 + pr0) * AUXB));
+  const uint32_t auxr = ds_pin((uint32_t)(GS_KB * GS_BLK_BYTES + pr0 * AUXB));
+  const int slice0 = ds_pin(kbl * 2);
+  const bool lane0 = ds_pin(lane) == 0;
+  const uint32_t ring_u32 = ds_pin(rg.ring_u32), bar0 = ds_pin(rg.bar0);
+  const int nstages = ds_pin(rg.nstages), stage_stride = ds_pin(rg.stage_stride);
+  // ring position of this warp's first unit (local unit h)
+  int rs = rg.s + h, rph = rg.ph;
+  if (rs >= nstages) { rs -= nstages; rph ^= 1; }
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+
+  auto group = [&](uint32_t st, const uint4& wa, const uint4& wb, const uint4& xv0, const uint4& xv1, const float2& xsv, int slice,
+                   int ks, uint32_t aux_first) {
+    const uint32_t ap = st + (gp128 == 1 ? aux_first : auxr + (uint32_t)(slice / gp128 - (ks * GS_KB * 2) / gp128) * 16 * AUXB);
+    float s0, s1, z0, z1;
+    if (PACKED) {
+      const uint32_t u0 = ds_lds32(ap), u1 = ds_lds32(ap + 8 * AUXB);
+      s0 = __uint_as_float(u0 & 0xffff0000u);
+      s1 = __uint_as_float(u1 & 0xffff0000u);
+      z0 = __uint_as_float(u0 << 16);
+      z1 = __uint_as_float(u1 << 16);
+    } else {
+      const float2 a0 = ds_lds64f(ap), a1 = ds_lds64f(ap + 8 * AUXB);
+      s0 = a0.x; z0 = a0.y; s1 = a1.x; z1 = a1.y;
+    }
+    int cl[4] = {0, 0, 0, 0}, ch[4] = {0, 0, 0, 0};
+    const uint32_t ML = 0x0F0F0F0Fu, MH = 0xF0F0F0F0u;
+    gs_imma(cl, wa.x & ML, wb.x & ML, wa.y & ML, wb.y & ML, xv0.x, xv0.y);
+    gs_imma(ch, wa.x & MH, wb.x & MH, wa.y & MH, wb.y & MH, xv0.z, xv0.w);
+    gs_imma(cl, wa.z & ML, wb.z & ML, wa.w & ML, wb.w & ML, xv1.x, xv1.y);
+    gs_imma(ch, wa.z & MH, wb.z & MH, wa.w & MH, wb.w & MH, xv1.z, xv1.w);
+    acc[0] = fmaf(s0, fmaf((float)ch[0], 0.0625f, fmaf(-z0, xsv.x, (float)cl[0])), acc[0]);
+    acc[1] = fmaf(s0, fmaf((float)ch[1], 0.0625f, fmaf(-z0, xsv.y, (float)cl[1])), acc[1]);
+    acc[2] = fmaf(s1, fmaf((float)ch[2], 0.0625f, fmaf(-z1, xsv.x, (float)cl[2])), acc[2]);
+    acc[3] = fmaf(s1, fmaf((float)ch[3], 0.0625f, fmaf(-z1, xsv.y, (float)cl[3])), acc[3]);
+  };
+
+  int ub = 0, ks0 = sb % nks;  // first local unit of the current tile, its K-stage
+  while (ub < nunits) {
+    const int ue = min(nunits, ub + nks - ks0);
+    int m = ub + ((ub ^ h) & 1);
+    int ks = ks0 + (m - ub);
+    uint32_t xpos = xpos0 + (uint32_t)ks * XSTEP, xsp = xsum0 + (uint32_t)ks * XSUMSTEP;
+    int slice = slice0 + ks * (GS_KB * 2);
+    for (; m < ue; m += 2) {
+      mbar_wait(bar0 + 8 * rs, rph);
+      const uint32_t st = ring_u32 + (uint32_t)(rs * stage_stride);
+      if (nomath) {
+      } else if (slice + 1 < nslices) {
+        const uint4 wa0 = ds_lds128(st + woff), wb0 = ds_lds128(st + woff + 8 * 128);
+        const uint4 wa1 = ds_lds128(st + (woff ^ 64u)), wb1 = ds_lds128(st + (woff ^ 64u) + 8 * 128);
+        const uint4 xa0 = ds_lds128(xpos), xa1 = ds_lds128(xpos + 16);
+        const uint4 xb0 = ds_lds128(xpos + 128), xb1 = ds_lds128(xpos + 144);
+        const float2 xs0 = ds_lds64f(xsp), xs1 = ds_lds64f(xsp + 16);
+        group(st, wa0, wb0, xa0, xa1, xs0, slice, ks, aux0);
+        group(st, wa1, wb1, xb0, xb1, xs1, slice + 1, ks, aux0 + 16 * AUXB);
+      } else if (slice < nslices) {
+        const uint4 wa0 = ds_lds128(st + woff), wb0 = ds_lds128(st + woff + 8 * 128);
+        const uint4 xa0 = ds_lds128(xpos), xa1 = ds_lds128(xpos + 16);
+        const float2 xs0 = ds_lds64f(xsp);
+        group(st, wa0, wb0, xa0, xa1, xs0, slice, ks, aux0);
+      }
+      __syncwarp();
+      if (lane0) mbar_arrive2(bar0 + 8 * (nstages + rs));
+      rs += 2;
+      if (rs >= nstages) { rs -= nstages; rph ^= 1; }
+      ks += 2;
+      xpos += 2 * XSTEP;
+      xsp += 2 * XSUMSTEP;
+      slice += 2 * GS_KB * 2;
+    }
+    // end of the tile (or of this CTA's part of it): as in ds_linear_main
+    const int par = gt & 1;
+    while (done[par] < (gt >> 1)) {}
+    if (t < 2) {
+      const uint32_t r = red_u32 + (uint32_t)(((par * GS_CWARPS + warp) * 16 + pr0) * 4 + 2 * t) * 4;
+      ds_sts64f(r, acc[0], acc[1]);
+      ds_sts64f(r + 8 * 4 * 4, acc[2], acc[3]);
+    }
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+    if (par == 0) asm volatile("bar.arrive 2, %0;\n" ::"n"(DS_TILE_BAR_THREADS) : "memory");
+    else asm volatile("bar.arrive 3, %0;\n" ::"n"(DS_TILE_BAR_THREADS) : "memory");
+    ++gt;
+    ub = ue;
+    ks0 = 0;
+  }
+  // common ring position after the op
+  const int adv = rg.s + nunits;
+  rg.ph ^= (adv / nstages) & 1;
+  rg.s = adv % nstages;
+}
+
 template <int HS, class WaitDep>
 __device__ __forceinline__ void ds_linear(const DsParams& p, const DsOp& o, const DsAttnGeo<HS>& geo, DsRing& rg, uint32_t red_u32,
                                           float* colscale, float* xsum, uint32_t xs_u32, volatile int* done, float* s_stat,
@@ -609,6 +738,8 @@ __device__ __forceinline__ void ds_linear(const DsParams& p, const DsOp& o, cons
   if (tr && threadIdx.x == 0) tr[2] = gs_now();
   const uint32_t xsum_u32 = gs_smem_u32(xsum);
   if (o.fmt == LP_W_BF16) ds_linear_main<LP_W_BF16, false>(o, rg, red_u32, colscale, xsum_u32, xs_u32, done, sb, se, gt);
+  else if (p.i4pair && o.aux_bytes == 4) ds_linear_main_i4pair<true>(o, rg, red_u32, xsum_u32, xs_u32, done, sb, se, gt, p.i4pair == 2);
+  else if (p.i4pair) ds_linear_main_i4pair<false>(o, rg, red_u32, xsum_u32, xs_u32, done, sb, se, gt, p.i4pair == 2);
   else if (o.aux_bytes == 4) ds_linear_main<LP_W_INT4, true>(o, rg, red_u32, colscale, xsum_u32, xs_u32, done, sb, se, gt);
   else ds_linear_main<LP_W_INT4, false>(o, rg, red_u32, colscale, xsum_u32, xs_u32, done, sb, se, gt);
 }
@@ -959,6 +1090,35 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
     if (lane != 0) return;
     bool have_geo = false;
     DsAttnGeo<HS> geo;
+    // L2 prefetch cursor: while the consumers sit at a grid dependency the ring is full and this thread is blocked, so HBM
+    // would idle; the cursor runs `l2_ahead` weight stages ahead of the TMA cursor (one step per issued stage), so those
+    // stages keep arriving in L2 during the stall and the ring then refills at L2 speed.
+    int pf_op = -1, pf_s = 0, pf_e = 0;
+    auto pf_step = [&]() {
+      while (pf_op < p.nops) {
+        if (pf_s < pf_e) {
+          const DsOp& q = p.ops[pf_op];
+          const int tile = pf_s / q.nks, ks = pf_s - tile * q.nks;
+          ds_prefetch_stage_l2(&q.map, 0, tile * GS_ROWS, ks * GS_KB);
+          if (q.fmt == LP_W_INT4) {
+            const int nch = (q.K + 127) / 128;
+            const int c_begin = ks * GS_KB * 2, c_end = min(nch, (ks + 1) * GS_KB * 2);
+            const int g_begin = c_begin / q.gp128;
+            const uint32_t len = (uint32_t)((c_end + q.gp128 - 1) / q.gp128 - g_begin) * 16 * q.aux_bytes;
+            ds_prefetch_l2(reinterpret_cast<const char*>(q.aux2) + ((size_t)tile * q.ngroups + g_begin) * 16 * q.aux_bytes, len);
+          }
+          ++pf_s;
+          return;
+        }
+        do ++pf_op; while (pf_op < p.nops && p.ops[pf_op].kind != DS_KIND_LINEAR);
+        if (pf_op < p.nops) ds_stage_range(p.ops[pf_op], pf_s, pf_e);
+      }
+    };
+    const bool pf_on = p.l2_ahead > 0;
+    if (pf_on) {
+      // put the cursor l2_ahead stages ahead of the TMA cursor
+      for (int i = 0; i < p.l2_ahead; ++i) pf_step();
+    }
     for (int op = 0; op < p.nops; ++op) {
       const DsOp& o = p.ops[op];
       if (o.kind == DS_KIND_LINEAR) {
@@ -989,6 +1149,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
           if (fmt == LP_W_INT4)
             bulk_g2s(dst + GS_KB * GS_BLK_BYTES, aux2 + ((size_t)tile * ngroups + g_begin) * 16 * aux_bytes, aux_len, rg.full());
           rg.advance();
+          if (pf_on) pf_step();
           if (++ks == nks) {
             ks = 0;
             ++tile;
@@ -1087,7 +1248,7 @@ __global__ void decode_step_prep_kernel(const void* __restrict__ idx, int idx64,
 // ------------------------------------------------------------------------------------------------ host side
 struct DsHostPlan {  // lp_step_handle, opaque to the caller
   uint32_t magic;
-  int nops, nstages, stage_stride, xsum_floats, hs, H, G, P, n_elem, max_seq, E, wte_dtype, idx64, grid;
+  int nops, nstages, stage_stride, xsum_floats, hs, H, G, P, n_elem, max_seq, E, wte_dtype, idx64, grid, i4pair, l2_ahead;
   float scale_log2;
   size_t smem;
   const DsOp* ops_dev;
@@ -1275,12 +1436,24 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
   if (tail + 3 * (size_t)stage_stride + 1024 > budget) return LP_ERR_UNSUPPORTED;
   int ns = (int)((budget - tail - 1024) / stage_stride);
   if (ns > 14) ns = 14;
+  // paired int4 main loop (ds_linear_main_i4pair) needs an even stage count; LP_DS_I4PAIR=0 keeps the one-group-per-warp loop
+  bool any_int4 = false;
+  for (int i = 0; i < n_ops; ++i) any_int4 |= dev[i].kind == DS_KIND_LINEAR && dev[i].fmt == LP_W_INT4;
+  const char* pair_env = getenv("LP_DS_I4PAIR");
+  const bool i4pair = any_int4 && !(pair_env && pair_env[0] == '0') && ns >= 5;
+  if (i4pair) ns &= ~1;
 
   DsHostPlan h;
   memset(&h, 0, sizeof(h));
   h.magic = DS_MAGIC;
   h.nops = n_ops;
   h.nstages = ns;
+  {
+    const char* e = getenv("LP_DS_L2AHEAD");
+    h.l2_ahead = e ? atoi(e) : 0;
+    if (h.l2_ahead < 0) h.l2_ahead = 0;
+  }
+  h.i4pair = i4pair ? (pair_env && pair_env[0] == '2' ? 2 : 1) : 0;  // 2: timing experiment, arithmetic skipped
   h.stage_stride = stage_stride;
   h.xsum_floats = xsum_floats;
   h.hs = gm->hs;
@@ -1341,6 +1514,8 @@ int lp_decode_step(const lp_step_handle* handle, void* stream) {
   p.nstages = h.nstages;
   p.stage_stride = h.stage_stride;
   p.xsum_floats = h.xsum_floats;
+  p.i4pair = h.i4pair;
+  p.l2_ahead = h.l2_ahead;
   p.tp_state0 = h.tp_state0;
   p.tp_state1 = h.tp_state1;
   return h.hs == 128 ? ds_launch<128>(p, h, stream) : ds_launch<64>(p, h, stream);

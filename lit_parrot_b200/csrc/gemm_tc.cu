@@ -127,6 +127,7 @@ struct TcParams {
   float* out_f32;         // [M, Nout] or NULL
   __nv_bfloat16* out_bf;  // [out_terms][M, Nout] bf16 split of the result, or NULL
   int M, N, K, epi, round_bf16, nterms, out_terms;
+  int debug;  // tuning aid (LP_GEMM_DEBUG): bit 0 = skip the epilogue arithmetic and stores (timing experiments only)
 };
 
 // Epilogue of one 128 x BN accumulator tile held in TMEM at `tacc`: warp quarter q owns lanes [32 q, +32) = rows m0 + 32 q + lane.
@@ -320,7 +321,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const int m0 = (tile % tiles_m) * TC_BM, n0 = (tile / tiles_m) * BN;
     tc_mbar_wait(acc_full(a), (it >> 1) & 1);
     tc_fence_after();
-    tc_epilogue_tile<BN>(p, tmem + a * BN, m0, n0, q, lane, swiglu, nout);
+    if (!(p.debug & 1)) tc_epilogue_tile<BN>(p, tmem + a * BN, m0, n0, q, lane, swiglu, nout);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(acc_empty(a)) : "memory");  // TMEM buffer may be reused
@@ -1102,6 +1103,13 @@ int lp_gemm_bf16_tc(const void* x_terms, int nterms, int M, const void* w_bf16, 
   p.round_bf16 = round_bf16;
   p.nterms = nterms;
   p.out_terms = out_terms;
+  {
+    static const int dbg = [] {
+      const char* e = getenv("LP_GEMM_DEBUG");
+      return e ? atoi(e) : 0;
+    }();
+    p.debug = dbg;
+  }
   if (pair) return BN == 256 ? lp::tc_launch<256, 2>(*mx, *mw, p, stream) : lp::tc_launch<128, 2>(*mx, *mw, p, stream);
   switch (BN) {
     case 256: return lp::tc_launch<256, 1>(*mx, *mw, p, stream);

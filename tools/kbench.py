@@ -118,8 +118,11 @@ def bench_gemm():
     pk = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
     peak = pk.get("bf16_tflops", 1672.9)
     print(f"{'shape (M,N,K)':28s} {'terms':>5s} {'us':>9s} {'TFLOP/s':>8s} {'%burst':>7s}   torch.matmul us / TF")
-    for M, N, K in [(2048, 4608, 4544), (2048, 18176, 4544), (2048, 4544, 18176), (2048, 12288, 4096), (2048, 22016, 4096), (2048, 4096, 11008),
-                    (4096, 8192, 8192), (32, 16384, 4096)]:
+    shapes = [(2048, 4608, 4544), (2048, 18176, 4544), (2048, 4544, 18176), (2048, 12288, 4096), (2048, 22016, 4096), (2048, 4096, 11008),
+              (4096, 8192, 8192), (32, 16384, 4096)]
+    if os.environ.get("KBENCH_GEMM_SHAPES"):  # e.g. "2048x18176x4544,2048x12288x4096"
+        shapes = [tuple(int(v) for v in s.split("x")) for s in os.environ["KBENCH_GEMM_SHAPES"].split(",")]
+    for M, N, K in shapes:
         x = torch.randn(M, K, device=DEV)
         w = [torch.randn(N, K, device=DEV, dtype=torch.bfloat16) * 0.02 for _ in range(3)]
         out = torch.empty(M, N, device=DEV)
