@@ -8,5 +8,7 @@ from lit_parrot_b200.config import Config, name_to_config  # noqa: F401
 from lit_parrot_b200.model import GPT  # noqa: F401
 from lit_parrot_b200.generate import generate, sample  # noqa: F401
 from lit_parrot_b200.utils import quantization  # noqa: F401
+from lit_parrot_b200.checkpoint import check_valid_checkpoint_dir, lazy_load, load_checkpoint, save_checkpoint  # noqa: F401
 
-__all__ = ["GPT", "Config", "generate", "sample", "quantization", "name_to_config"]
+__all__ = ["GPT", "Config", "generate", "sample", "quantization", "name_to_config", "lazy_load", "check_valid_checkpoint_dir",
+           "load_checkpoint", "save_checkpoint"]

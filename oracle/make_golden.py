@@ -266,6 +266,64 @@ def gptq_cases():
     print(f"[golden] gptq plug-in: {len(keys)} state-dict keys recorded")
 
 
+@torch.no_grad()
+def checkpoint_cases():
+    """Checkpoint directories as the reference's own tools leave them: `lit_config.json` =
+    json.dump(config.__dict__) (scripts/convert_hf_checkpoint.py:193-194), `lit_model.pth` = the GPT state dict,
+    `lit_model_gptq.4bit.pth` = state dict of the model built under quantization("gptq.int4") (quantize/gptq.py:595-596).
+    Read back with the reference's lazy_load + load_state_dict (generate/base.py:219-221); the logits of that reloaded
+    reference model are the expected outputs stored next to the files."""
+    import json
+    from pathlib import Path
+
+    from lit_gpt.utils import lazy_load, quantization
+
+    kw = TINY["llama_mha"]
+    cfg, model, sd = build_reference(kw, seed=4321)
+    d = Path(OUT) / "ckpt_tiny_llama"
+    d.mkdir(exist_ok=True)
+    with open(d / "lit_config.json", "w") as fp:
+        json.dump(cfg.__dict__, fp)
+    torch.save(model.state_dict(), d / "lit_model.pth")
+
+    # int4 file: every Linear (lm_head included, utils.py:72-74: per-row groups) round-to-nearest quantised
+    with quantization("gptq.int4"):
+        qmodel = lit_gpt.GPT(cfg)
+    qsd = {}
+    for k, v in sd.items():
+        if k.endswith(".weight") and v.dim() == 2 and "wte" not in k:
+            packed, scales, zeros = oracle.gptq_rtn_quantize(v.float(), -1)
+            base = k[: -len("weight")]
+            qsd[base + "quant_weight"], qsd[base + "scales"], qsd[base + "zeros"] = packed, scales, zeros
+        else:
+            qsd[k] = v
+    res = qmodel.load_state_dict(qsd, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    assert qmodel.lm_head.quant_weight.stride() == (1, cfg.padded_vocab_size)
+    torch.save(qmodel.state_dict(), d / "lit_model_gptq.4bit.pth")
+
+    g = torch.Generator().manual_seed(11)
+    idx = torch.randint(0, cfg.vocab_size, (2, 9), generator=g)
+    out = {}
+    for tag, fname, quant in (("fp32", "lit_model.pth", None), ("int4", "lit_model_gptq.4bit.pth", "gptq.int4")):
+        with quantization(quant):
+            m = lit_gpt.GPT(cfg)
+        with lazy_load(d / fname) as ckpt:
+            m.load_state_dict(ckpt.get("model", ckpt), strict=quant is None)
+        m.eval()
+        out[tag] = m(idx).float().numpy()
+        digest = sd_digest({k: (v.contiguous() if torch.is_tensor(v) else v) for k, v in m.state_dict().items()})
+        out[tag + "_digest"] = np.array(digest)
+    # the oracle on the same files (plain torch.load)
+    o32 = oracle.OracleGPT(oracle_cfg(kw), torch.load(d / "lit_model.pth"))(idx)
+    o4 = oracle.OracleGPT(oracle_cfg(kw), torch.load(d / "lit_model_gptq.4bit.pth"))(idx)
+    check("ckpt/int4/oracle", o4, torch.from_numpy(out["int4"]), 1e-5)
+    check("ckpt/fp32/oracle", o32, torch.from_numpy(out["fp32"]), 1e-5)
+    np.savez_compressed(os.path.join(OUT, "ckpt_tiny_llama_expected.npz"), idx=idx.numpy(), logits_fp32=out["fp32"],
+                        logits_int4=out["int4"], digest_fp32=out["fp32_digest"], digest_int4=out["int4_digest"])
+    print(f"[golden] checkpoint dir {d.name}: fp32 + gptq.int4 files written, reference reload logits stored")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -273,4 +331,5 @@ if __name__ == "__main__":
     tiny_cases()
     gptq_cases()
     pythia70m()
+    checkpoint_cases()
     print("[golden] all fixtures written to", OUT)
