@@ -260,6 +260,9 @@ int lp_decode_step(const lp_step_handle* handle, void* stream);
 /* Debug aid: device_buf (>= n_ops * 148 * 8 uint64) receives per-(op, CTA) globaltimer stamps [start, dependency met,
  * activations staged, end, x loaded, normalised, max|x| known, -]; NULL switches it off. */
 int lp_debug_step_trace(void* device_buf);
+/* Debug aid (env LP_GEMM_DEBUG=2 at load): {SM cycles, ns, k-blocks, 0} of the main loops of CTA 0's MMA issuer in the last
+ * lp_gemm_bf16_tc launch (synchronises the device). */
+int lp_debug_gemm_stats(long long* out4);
 
 /* Tensor-parallel exchange fused with the residual add: out[n] = residual[n] + sum over ranks of partial_r[n], n fp32.
  * `buf_ptrs_dev` / `pad_ptrs_dev`: device arrays of `tp` peer-mapped addresses (symmetric buffer and signal pad of every

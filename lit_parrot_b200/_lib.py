@@ -96,6 +96,7 @@ PROTOTYPES = {
                                     ctypes.POINTER(LpStepHandle)]),
     "lp_decode_step": (c_int, [ctypes.POINTER(LpStepHandle), c_void_p]),
     "lp_debug_step_trace": (c_int, [c_void_p]),
+    "lp_debug_gemm_stats": (c_int, [c_void_p]),
     "lp_tp_allreduce_residual": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                          c_void_p]),
     "lp_sample": (c_int, [c_void_p, c_int, c_int, c_float, c_int, c_u64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

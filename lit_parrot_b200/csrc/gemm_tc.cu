@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <atomic>
+#include <type_traits>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -52,6 +53,21 @@ __device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE:\n"
       "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+// Wait used by the FOUR epilogue warps for `accumulator full`: they wait for a whole tile's main loop (tens of thousands of
+// cycles); 128 threads re-issuing try_wait back to back compete with the TMA writes and the MMA's operand reads for shared
+// memory, so they sleep between polls (LP_GEMM_DEBUG bit 2 restores the hot spin for A/B measurements).
+__device__ __forceinline__ void tc_mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "nanosleep.u32 %2;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity), "r"(ns) : "memory");
+}
 __device__ __forceinline__ void tc_tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
                "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
@@ -62,6 +78,9 @@ __device__ __forceinline__ void tc_tma_2d_mc(uint32_t dst, const CUtensorMap* ma
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;\n" ::"r"(dst),
       "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_prefetch_2d(const CUtensorMap* map, int c0, int c1) {  // one box into L2 only
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];\n" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar), "h"(mask) : "memory");
@@ -121,12 +140,16 @@ __device__ __forceinline__ void tc_mma_lo(uint32_t tmem_c, uint32_t a_lo, uint32
       "}\n" ::"r"(tmem_c), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(TC_DESC_HI) : "memory");
 }
 
+// tuning aid (LP_GEMM_DEBUG bit 1): the MMA issuer of CTA 0 records {SM cycles, ns, k-blocks} of its main loops
+__device__ long long g_tc_debug[4];
+
 struct TcParams {
   const float* bias;      // [N] or NULL
   const float* residual;  // [M, N] or NULL
   float* out_f32;         // [M, Nout] or NULL
   __nv_bfloat16* out_bf;  // [out_terms][M, Nout] bf16 split of the result, or NULL
   int M, N, K, epi, round_bf16, nterms, out_terms;
+  int l2_ahead;  // k-blocks the producer prefetches into L2 ahead of its TMA loads (first-touch W tiles come from HBM)
   int debug;  // tuning aid (LP_GEMM_DEBUG): bit 0 = skip the epilogue arithmetic and stores (timing experiments only)
 };
 
@@ -263,6 +286,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int m0 = (tile % tiles_m) * TC_BM, n0 = (tile / tiles_m) * BN;
         for (int kb = 0; kb < nk; ++kb) {
+          if (p.l2_ahead > 0) {  // the operands of k-block kb + l2_ahead (possibly of this CTA's next tile) -> L2
+            int pk = kb + p.l2_ahead, ptile = tile;
+            while (pk >= nk) { pk -= nk; ptile += gridDim.x; }
+            if (ptile < ntiles) {
+              const int pm0 = (ptile % tiles_m) * TC_BM, pn0 = (ptile / tiles_m) * BN;
+              if (CL == 1) tc_prefetch_2d(&map_w, pk * TC_BK, pn0);
+              else tc_prefetch_2d(&map_w, pk * TC_BK, pn0 + (int)cta_rank * (BN / 2));
+              for (int t = 0; t < p.nterms; ++t) tc_prefetch_2d(&map_x, pk * TC_BK, t * p.M + pm0);
+            }
+          }
           tc_mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t dst = ring + (uint32_t)s * stage_bytes;
           tc_mbar_expect_tx(full_bar(s), stage_bytes);
@@ -283,30 +316,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int s = 0, ph = 0, it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int a = it & 1;  // TMEM accumulator of this tile
-        tc_mbar_wait(acc_empty(a), ((it >> 1) & 1) ^ 1);  // the epilogue has drained it (first use: passes immediately)
-        tc_fence_after();
-        const uint32_t tacc = tmem + a * BN;
-        uint32_t accumulate = 0;
-        for (int kb = 0; kb < nk; ++kb) {
-          tc_mbar_wait(full_bar(s), ph);
+      long long dbg_c0 = 0, dbg_t0 = 0, dbg_kb = 0;
+      if (p.debug & 2) {
+        dbg_c0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(dbg_t0));
+      }
+      // The issuing thread is the pace maker: with the term count a run-time value and 64-bit descriptors rebuilt per MMA the
+      // loop below cost ~175 cycles per k-step + ~58 per MMA (measured: 936 cycles per k-block of four 128-cycle MMAs, whatever
+      // the ring depth, cluster mode or epilogue did).  Hence: term count as a template constant, k-steps and terms fully
+      // unrolled, and only the 14-bit start-address field of the descriptors advanced, in 32-bit arithmetic.
+      const uint32_t stage_lo = (uint32_t)stage_bytes >> 4;
+      const uint32_t ring_lo = tc_desc_lo(ring);
+      auto issue_tiles = [&](auto nt_tag) {
+        constexpr int NT = decltype(nt_tag)::value;
+        const uint32_t b_off = (uint32_t)(NT * TC_BM * TC_BK * 2) >> 4;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+          const int a = it & 1;  // TMEM accumulator of this tile
+          tc_mbar_wait(acc_empty(a), ((it >> 1) & 1) ^ 1);  // the epilogue has drained it (first use: passes immediately)
           tc_fence_after();
-          const uint32_t a0 = ring + (uint32_t)s * stage_bytes;
-          const uint32_t b0 = a0 + p.nterms * A_BYTES;
+          const uint32_t tacc = tmem + a * BN;
+          for (int kb = 0; kb < nk; ++kb) {
+            tc_mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t a_lo = ring_lo + (uint32_t)s * stage_lo;
+            const uint32_t b_lo = a_lo + b_off;
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint64_t db = tc_smem_desc(b0 + k * 32);
-            for (int t = 0; t < p.nterms; ++t) {
-              tc_mma(tacc, tc_smem_desc(a0 + t * A_BYTES + k * 32), db, idesc, accumulate);
-              accumulate = 1;
+            for (int k = 0; k < TC_BK / 16; ++k) {
+#pragma unroll
+              for (int t = 0; t < NT; ++t)
+                tc_mma_lo(tacc, a_lo + (uint32_t)(t * (TC_BM * TC_BK * 2 >> 4) + k * 2), b_lo + (uint32_t)(k * 2), idesc,
+                          (k | t) ? 1u : (uint32_t)(kb != 0));
             }
+            if (CL == 1) tc_commit(empty_bar(s));  // the slot is free once these MMAs have read it
+            else tc_commit_mc(empty_bar(s), (uint16_t)3);  // ... in both CTAs: the partner multicasts into this slot too
+            if (++s == nstages) { s = 0; ph ^= 1; }
           }
-          if (CL == 1) tc_commit(empty_bar(s));  // the slot is free once these MMAs have read it
-          else tc_commit_mc(empty_bar(s), (uint16_t)3);  // ... in both CTAs: the partner multicasts into this slot too
-          if (++s == nstages) { s = 0; ph ^= 1; }
+          tc_commit(acc_full(a));  // accumulator complete
+          dbg_kb += nk;
         }
-        tc_commit(acc_full(a));  // accumulator complete
+      };
+      if (p.nterms == 1) issue_tiles(std::integral_constant<int, 1>{});
+      else if (p.nterms == 2) issue_tiles(std::integral_constant<int, 2>{});
+      else issue_tiles(std::integral_constant<int, 3>{});
+      if ((p.debug & 2) && blockIdx.x == 0) {
+        tc_mbar_wait(acc_full((it - 1) & 1), ((it - 1) >> 1) & 1);  // the last MMAs have completed
+        long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t1));
+        g_tc_debug[0] = clock64() - dbg_c0;
+        g_tc_debug[1] = t1 - dbg_t0;
+        g_tc_debug[2] = dbg_kb;
       }
     }
   }
@@ -319,7 +377,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int a = it & 1;
     const int m0 = (tile % tiles_m) * TC_BM, n0 = (tile / tiles_m) * BN;
-    tc_mbar_wait(acc_full(a), (it >> 1) & 1);
+    if (p.debug & 4) tc_mbar_wait(acc_full(a), (it >> 1) & 1);
+    else tc_mbar_wait_sleep(acc_full(a), (it >> 1) & 1, 256);
     tc_fence_after();
     if (!(p.debug & 1)) tc_epilogue_tile<BN>(p, tmem + a * BN, m0, n0, q, lane, swiglu, nout);
     tc_fence_before();
@@ -1003,6 +1062,10 @@ static int tc_launch_swap(const CUtensorMap& mx, const CUtensorMap& mw, const Tc
 
 extern "C" {
 
+int lp_debug_gemm_stats(long long* out4) {  // {cycles, ns, k-blocks, -} of the last LP_GEMM_DEBUG=2 launch (CTA 0)
+  return cudaMemcpyFromSymbol(out4, lp::g_tc_debug, 4 * sizeof(long long)) == cudaSuccess ? LP_OK : LP_ERR_CUDA;
+}
+
 int lp_set_gemm_pair(int enabled) {
   lp::g_gemm_pair.store(enabled ? 1 : 0);
   return LP_OK;
@@ -1084,6 +1147,7 @@ int lp_gemm_bf16_tc(const void* x_terms, int nterms, int M, const void* w_bf16, 
       lp::TcParams q;
       q.bias = bias; q.residual = residual; q.out_f32 = out_f32; q.out_bf = reinterpret_cast<__nv_bfloat16*>(out_bf16);
       q.M = M; q.N = N; q.K = K; q.epi = epilogue; q.round_bf16 = round_bf16; q.nterms = nterms; q.out_terms = out_terms;
+      q.debug = 0; q.l2_ahead = 0;
       return lp::tc_launch_pair(*mx2, *mw2, q, stream);
     }
   }
@@ -1109,6 +1173,11 @@ int lp_gemm_bf16_tc(const void* x_terms, int nterms, int M, const void* w_bf16, 
       return e ? atoi(e) : 0;
     }();
     p.debug = dbg;
+    static const int ahead = [] {
+      const char* e = getenv("LP_GEMM_L2AHEAD");
+      return e ? atoi(e) : 0;
+    }();
+    p.l2_ahead = ahead;
   }
   if (pair) return BN == 256 ? lp::tc_launch<256, 2>(*mx, *mw, p, stream) : lp::tc_launch<128, 2>(*mx, *mw, p, stream);
   switch (BN) {

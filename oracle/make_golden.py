@@ -278,7 +278,8 @@ def checkpoint_cases():
 
     from lit_gpt.utils import lazy_load, quantization
 
-    kw = TINY["llama_mha"]
+    # intermediate_size 192: the int4 kernels need in_features % 32 == 0 (true of every preset; 176 is not)
+    kw = dict(TINY["llama_mha"], intermediate_size=192)
     cfg, model, sd = build_reference(kw, seed=4321)
     d = Path(OUT) / "ckpt_tiny_llama"
     d.mkdir(exist_ok=True)
@@ -327,6 +328,9 @@ def checkpoint_cases():
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if "--only-checkpoint" in sys.argv:
+        checkpoint_cases()
+        sys.exit(0)
     preset_table()
     tiny_cases()
     gptq_cases()

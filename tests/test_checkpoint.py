@@ -46,7 +46,7 @@ def test_lazy_load_yields_the_saved_tensors():
 
 def test_config_from_lit_config_json():
     cfg = ck.load_config(CKPT)
-    assert (cfg.n_layer, cfg.n_head, cfg.n_embd, cfg.intermediate_size) == (2, 4, 64, 176)
+    assert (cfg.n_layer, cfg.n_head, cfg.n_embd, cfg.intermediate_size) == (2, 4, 64, 192)
     assert cfg._norm_class == "RMSNorm" and cfg._mlp_class == "LLaMAMLP" and cfg.padded_vocab_size == 96
 
 

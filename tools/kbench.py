@@ -135,7 +135,15 @@ def bench_gemm():
             tf = 2.0 * M * N * K / us / 1e6
             xb = x.bfloat16()
             ust = timeit(lambda i: torch.matmul(xb, w[i % 3].t()), iters=20, warm=3)
-            print(f"{str((M, N, K)):28s} {nt:5d} {us:9.1f} {tf:8.1f} {100 * tf / peak:7.1f}   {ust:8.1f} / {2.0 * M * N * K / ust / 1e6:6.1f}")
+            dbg = ""
+            if int(os.environ.get("LP_GEMM_DEBUG", "0")) & 2:
+                import ctypes
+                st = (ctypes.c_longlong * 4)()
+                fn(0)
+                lib.lp_debug_gemm_stats(ctypes.cast(st, ctypes.c_void_p))
+                if st[2]:
+                    dbg = f"   CTA0 main loops: {st[0] / st[2]:.0f} cycles/k-block, SM clock {st[0] / max(st[1], 1):.3f} GHz"
+            print(f"{str((M, N, K)):28s} {nt:5d} {us:9.1f} {tf:8.1f} {100 * tf / peak:7.1f}   {ust:8.1f} / {2.0 * M * N * K / ust / 1e6:6.1f}{dbg}")
 
 
 if __name__ == "__main__":

@@ -107,6 +107,15 @@ __global__ void __launch_bounds__(128, 1) k(long long* out, const __grid_constan
   if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512) : "memory");
 }
 
+__global__ void fill_random(unsigned short* p, size_t n, unsigned seed) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    unsigned h = (unsigned)i * 2654435761u + seed;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    // bf16 in roughly N(0, 1)-like range: random sign and mantissa, exponent 120..127
+    p[i] = (unsigned short)((h & 0x807fu) | ((120u + ((h >> 16) & 7u)) << 7));
+  }
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -121,8 +130,15 @@ int main(int argc, char** argv) {
   unsigned short *x, *w;
   cudaMalloc(&x, (size_t)M * K * 2);
   cudaMalloc(&w, (size_t)N * K * 2);
-  cudaMemset(x, 0, (size_t)M * K * 2);
-  cudaMemset(w, 0, (size_t)N * K * 2);
+  const bool rnd = argc > 4 && atoi(argv[4]) != 0;  // operand VALUES matter: tensor-core power depends on the data
+  if (rnd) {
+    fill_random<<<1024, 256>>>(x, (size_t)M * K, 1u);
+    fill_random<<<1024, 256>>>(w, (size_t)N * K, 2u);
+  } else {
+    cudaMemset(x, 0, (size_t)M * K * 2);
+    cudaMemset(w, 0, (size_t)N * K * 2);
+  }
+  printf("operands: %s\n", rnd ? "random bf16" : "zeros");
   long long* d;
   cudaMalloc(&d, 16 * 148);
   auto make = [&](void* p, int rows, int box_rows) {
@@ -145,7 +161,7 @@ int main(int argc, char** argv) {
                         {"loads + MMA, N 128, 4 stages", 128, 4, 1},       {"loads + MMA, N 128, 6 stages", 128, 6, 1}};
   for (const Case& c : cases) {
     const CUtensorMap mw = make(w, N, c.rows_w > 0 ? c.rows_w : 128);
-    for (int rep = 0; rep < 2; ++rep) k<<<148, 128, smem>>>(d, mx, mw, M, N, K, c.depth, c.rows_w, tpc, c.mma);
+    for (int rep = 0; rep < (argc > 5 ? atoi(argv[5]) : 2); ++rep) k<<<148, 128, smem>>>(d, mx, mw, M, N, K, c.depth, c.rows_w, tpc, c.mma);
     cudaDeviceSynchronize();
     long long h[2 * 148];
     cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
