@@ -369,30 +369,45 @@ def time_step_kernel(eng, model, cfg, device, kv_elem_bytes, iters=64):
 
 
 def time_dominant_kernel(eng, cfg, B, device, iters=64):
+    """Batches > 1: the MLP up-projection alone, rotating over all layers' weights (>> L2), through the kernel the step itself
+    uses for this batch size: the streaming GEMV (lp_linear) up to 8 rows, the swap-AB tcgen05 GEMM (lp_gemm_bf16_tc on the bf16
+    terms of the activations) from 9 rows on."""
     import torch
 
     from lit_parrot_b200 import _lib
 
     lib = eng.lib
     x = torch.randn(B, cfg.n_embd, device=device)
-    out = torch.empty(B, cfg.intermediate_size * (1 if eng.act != _lib.LP_EPI_SWIGLU else 1), device=device)
+    out = torch.empty(B, cfg.intermediate_size, device=device)
     stream = torch.cuda.current_stream(device).cuda_stream
     layers = eng.layers
+    if B <= 8:
+        name = "lp_linear(mlp.fc)"
+
+        def run(L):
+            _lib.check(lib.lp_linear(x.data_ptr(), B, L.fc.ref, eng.act, None, out.data_ptr(), eng.round, stream))
+    else:
+        nt = 1 if eng.round else (3 if B <= 16 else 2)  # as Engine._run_tc
+        name = f"lp_gemm_bf16_tc(mlp.fc, swap-AB, {nt} bf16 terms)"
+        terms = torch.empty(nt, B, cfg.n_embd, dtype=torch.bfloat16, device=device)
+        _lib.check(lib.lp_split_bf16(x.data_ptr(), terms.data_ptr(), B, cfg.n_embd, nt, -1, None, None, 0.0, eng.round, stream))
+
+        def run(L):
+            W = L.fc
+            _lib.check(lib.lp_gemm_bf16_tc(terms.data_ptr(), nt, B, eng._bf16_weight(W, stream), W.N, W.K, W.rec.bias, eng.act, None,
+                                           out.data_ptr(), None, 0, eng.round, stream))
     for i in range(8):
-        L = layers[i % len(layers)]
-        _lib.check(lib.lp_linear(x.data_ptr(), B, L.fc.ref, eng.act, None, out.data_ptr(), eng.round, stream))
+        run(layers[i % len(layers)])
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(device)
     e0.record()
     for i in range(iters):
-        L = layers[i % len(layers)]
-        _lib.check(lib.lp_linear(x.data_ptr(), B, L.fc.ref, eng.act, None, out.data_ptr(), eng.round, stream))
+        run(layers[i % len(layers)])
     e1.record()
     torch.cuda.synchronize(device)
     us = e0.elapsed_time(e1) * 1e3 / iters
     nbytes = layers[0].fc.stored_bytes
-    return {"name": "lp_linear(mlp.fc)", "N": layers[0].fc.N, "K": layers[0].fc.K, "us": us, "bytes": int(nbytes),
-            "gbs": nbytes / us / 1e3}
+    return {"name": name, "N": layers[0].fc.N, "K": layers[0].fc.K, "us": us, "bytes": int(nbytes), "gbs": nbytes / us / 1e3}
 
 
 # ------------------------------------------------------------------------------------------------------------------

