@@ -75,8 +75,10 @@ struct DsParams {
   float scale_log2;
   int nops, H, G, n_elem, max_seq, P;
   int nstages, stage_stride, xsum_floats;
-  int i4pair;  // int4 ops use the paired main loop (even stage count)
-  int l2_ahead;  // weight stages the producer keeps prefetched into L2 beyond the shared-memory ring
+  int i4pair;  // int4 ops use the paired main loop (even stage count); 2: arithmetic skipped (timing experiment)
+  int skip_dep;  // timing experiments only (LP_DS_SKIPDEP bit mask): skip the dependency wait of 1: attention, 2: attention
+                 // projection, 4: MLP down-projection, 8: the ops that read the residual stream — results are WRONG
+  int l2_ahead;  // weight stages the producer may prefetch into L2 beyond its TMA cursor while it is blocked on a full ring
   unsigned int* tp_state0;  // epoch counters of the (up to two) tensor-parallel exchange slots, or NULL
   unsigned int* tp_state1;
 };
@@ -1090,35 +1092,49 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
     if (lane != 0) return;
     bool have_geo = false;
     DsAttnGeo<HS> geo;
-    // L2 prefetch cursor: while the consumers sit at a grid dependency the ring is full and this thread is blocked, so HBM
-    // would idle; the cursor runs `l2_ahead` weight stages ahead of the TMA cursor (one step per issued stage), so those
-    // stages keep arriving in L2 during the stall and the ring then refills at L2 speed.
+    // L2 look-ahead, used ONLY while this thread is blocked on a full ring.  The producer is always a ring depth ahead of the
+    // consumers, so whenever they stop consuming (activation staging, dependency waits, attention start-up, epilogue tails:
+    // ~6 us around every op) the ring is already full, this thread cannot issue, and HBM idles for the whole pause whatever the
+    // ring depth.  While blocked it therefore walks a second cursor over the coming weight stages (same op order, linear ops
+    // only) and prefetches them into L2 (`cp.async.bulk.prefetch.tensor`), at most `l2_ahead` stages beyond the TMA cursor: HBM
+    // keeps working during the pause, and the ring then refills from L2.  (Prefetching at a fixed distance all the time — the
+    // first version of this knob — only adds requests while HBM is saturated and was slower.)
     int pf_op = -1, pf_s = 0, pf_e = 0;
-    auto pf_step = [&]() {
+    int n_issued = 0, n_pf = 0;  // linear stages handed to TMA / passed by the prefetch cursor (n_pf >= n_issued)
+    auto pf_step = [&](bool fetch) {
       while (pf_op < p.nops) {
         if (pf_s < pf_e) {
-          const DsOp& q = p.ops[pf_op];
-          const int tile = pf_s / q.nks, ks = pf_s - tile * q.nks;
-          ds_prefetch_stage_l2(&q.map, 0, tile * GS_ROWS, ks * GS_KB);
-          if (q.fmt == LP_W_INT4) {
-            const int nch = (q.K + 127) / 128;
-            const int c_begin = ks * GS_KB * 2, c_end = min(nch, (ks + 1) * GS_KB * 2);
-            const int g_begin = c_begin / q.gp128;
-            const uint32_t len = (uint32_t)((c_end + q.gp128 - 1) / q.gp128 - g_begin) * 16 * q.aux_bytes;
-            ds_prefetch_l2(reinterpret_cast<const char*>(q.aux2) + ((size_t)tile * q.ngroups + g_begin) * 16 * q.aux_bytes, len);
+          if (fetch) {
+            const DsOp& q = p.ops[pf_op];
+            const int tile = pf_s / q.nks, ks = pf_s - tile * q.nks;
+            ds_prefetch_stage_l2(&q.map, 0, tile * GS_ROWS, ks * GS_KB);
+            if (q.fmt == LP_W_INT4) {
+              const int nch = (q.K + 127) / 128;
+              const int c_begin = ks * GS_KB * 2, c_end = min(nch, (ks + 1) * GS_KB * 2);
+              const int g_begin = c_begin / q.gp128;
+              const uint32_t len = (uint32_t)((c_end + q.gp128 - 1) / q.gp128 - g_begin) * 16 * q.aux_bytes;
+              ds_prefetch_l2(reinterpret_cast<const char*>(q.aux2) + ((size_t)tile * q.ngroups + g_begin) * 16 * q.aux_bytes, len);
+            }
           }
           ++pf_s;
+          ++n_pf;
           return;
         }
         do ++pf_op; while (pf_op < p.nops && p.ops[pf_op].kind != DS_KIND_LINEAR);
         if (pf_op < p.nops) ds_stage_range(p.ops[pf_op], pf_s, pf_e);
       }
     };
-    const bool pf_on = p.l2_ahead > 0;
-    if (pf_on) {
-      // put the cursor l2_ahead stages ahead of the TMA cursor
-      for (int i = 0; i < p.l2_ahead; ++i) pf_step();
-    }
+    const int l2_ahead = p.l2_ahead;
+    auto wait_empty = [&]() {
+      const uint32_t bar = rg.empty(), par = (uint32_t)(rg.ph ^ 1);
+      if (l2_ahead > 0) {
+        while (!mbar_test(bar, par)) {
+          if (n_pf - n_issued < l2_ahead && pf_op < p.nops) pf_step(true);
+        }
+      } else {
+        mbar_wait(bar, par);
+      }
+    };
     for (int op = 0; op < p.nops; ++op) {
       const DsOp& o = p.ops[op];
       if (o.kind == DS_KIND_LINEAR) {
@@ -1135,7 +1151,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
         }
         int tile = sb / nks, ks = sb % nks;
         for (int s0 = sb; s0 < se; ++s0) {
-          mbar_wait(rg.empty(), rg.ph ^ 1);
+          wait_empty();
+          if (l2_ahead > 0) {
+            if (n_pf == n_issued) pf_step(false);  // the cursor never falls behind the TMA cursor
+            ++n_issued;
+          }
           const uint32_t dst = rg.ring_u32 + (uint32_t)rg.s * rg.stage_stride;
           uint32_t aux_len = 0;
           int g_begin = 0;
@@ -1149,7 +1169,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
           if (fmt == LP_W_INT4)
             bulk_g2s(dst + GS_KB * GS_BLK_BYTES, aux2 + ((size_t)tile * ngroups + g_begin) * 16 * aux_bytes, aux_len, rg.full());
           rg.advance();
-          if (pf_on) pf_step();
           if (++ks == nks) {
             ks = 0;
             ++tile;
@@ -1170,11 +1189,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
             const int rows = min(AT, p.max_seq - blk * AT);
             const uint32_t bytes = (uint32_t)rows * HS * 2;
             const size_t off = ((size_t)(h / (p.H / p.G)) * p.max_seq + (size_t)blk * AT) * HS;
-            mbar_wait(rg.empty(), rg.ph ^ 1);
+            wait_empty();
             mbar_expect_tx(rg.full(), bytes);
             bulk_g2s(rg.ring_u32 + (uint32_t)rg.s * rg.stage_stride, o.kc + off, bytes, rg.full());
             rg.advance();
-            mbar_wait(rg.empty(), rg.ph ^ 1);
+            wait_empty();
             mbar_expect_tx(rg.full(), bytes);
             bulk_g2s(rg.ring_u32 + (uint32_t)rg.s * rg.stage_stride, o.vc + off, bytes, rg.full());
             rg.advance();
@@ -1201,8 +1220,13 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
     if (tr && threadIdx.x == 0) tr[0] = gs_now();
     const int dep = o.dep;
     // barriers are cumulative: a CTA arrives for op d only after all of its earlier ops
+    int skip = 0;
+    if (p.skip_dep) {
+      const int cls = o.kind != DS_KIND_LINEAR ? 1 : (o.x_attn ? 2 : (o.streamk ? 4 : 8));
+      skip = p.skip_dep & cls;
+    }
     auto wait_dep = [&]() {
-      if (dep > waited) {
+      if (dep > waited && !skip) {
         if (threadIdx.x == 0) {  // cheap relaxed polls, one acquire at the end
           while (ds_ld_relaxed(p.counters + dep) < gridDim.x) {}
           (void)ds_ld_acquire(p.counters + dep);
@@ -1248,7 +1272,7 @@ __global__ void decode_step_prep_kernel(const void* __restrict__ idx, int idx64,
 // ------------------------------------------------------------------------------------------------ host side
 struct DsHostPlan {  // lp_step_handle, opaque to the caller
   uint32_t magic;
-  int nops, nstages, stage_stride, xsum_floats, hs, H, G, P, n_elem, max_seq, E, wte_dtype, idx64, grid, i4pair, l2_ahead;
+  int nops, nstages, stage_stride, xsum_floats, hs, H, G, P, n_elem, max_seq, E, wte_dtype, idx64, grid, i4pair, l2_ahead, skip_dep;
   float scale_log2;
   size_t smem;
   const DsOp* ops_dev;
@@ -1436,7 +1460,13 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
   if (tail + 3 * (size_t)stage_stride + 1024 > budget) return LP_ERR_UNSUPPORTED;
   int ns = (int)((budget - tail - 1024) / stage_stride);
   if (ns > 14) ns = 14;
+  if (const char* cap = getenv("LP_DS_STAGES")) {  // tuning aid: cap the ring depth
+    const int c = atoi(cap);
+    if (c >= 3 && c < ns) ns = c;
+  }
   // paired int4 main loop (ds_linear_main_i4pair) needs an even stage count; LP_DS_I4PAIR=0 keeps the one-group-per-warp loop
+  // (the same transformation of the bf16 loop was measured too: 1591 -> 1586 us on stablelm-3b, 3226 -> 3192 us on falcon-7b —
+  // not worth a second summation order next to the per-op path, so bf16 keeps one loop)
   bool any_int4 = false;
   for (int i = 0; i < n_ops; ++i) any_int4 |= dev[i].kind == DS_KIND_LINEAR && dev[i].fmt == LP_W_INT4;
   const char* pair_env = getenv("LP_DS_I4PAIR");
@@ -1452,6 +1482,8 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
     const char* e = getenv("LP_DS_L2AHEAD");
     h.l2_ahead = e ? atoi(e) : 0;
     if (h.l2_ahead < 0) h.l2_ahead = 0;
+    const char* sd = getenv("LP_DS_SKIPDEP");
+    h.skip_dep = sd ? atoi(sd) : 0;
   }
   h.i4pair = i4pair ? (pair_env && pair_env[0] == '2' ? 2 : 1) : 0;  // 2: timing experiment, arithmetic skipped
   h.stage_stride = stage_stride;
@@ -1516,6 +1548,7 @@ int lp_decode_step(const lp_step_handle* handle, void* stream) {
   p.xsum_floats = h.xsum_floats;
   p.i4pair = h.i4pair;
   p.l2_ahead = h.l2_ahead;
+  p.skip_dep = h.skip_dep;
   p.tp_state0 = h.tp_state0;
   p.tp_state1 = h.tp_state1;
   return h.hs == 128 ? ds_launch<128>(p, h, stream) : ds_launch<64>(p, h, stream);

@@ -1125,6 +1125,13 @@ int lp_gemm_bf16_tc(const void* x_terms, int nterms, int M, const void* w_bf16, 
     q.fuse = (M % 16 == 0) ? 1 : 0;
     // K-blocks per copy: 4 (512 contiguous bytes per weight row) if two stages fit, else 2
     q.KB = 2 * 4 * (lp::TC_BM * lp::TC_BK * 2 + nterms * q.NB * lp::TC_BK * 2) <= 212 * 1024 ? 4 : 2;
+    {
+      static const int kb_env = [] {  // tuning aid: LP_SWAP_KB = 1 | 2 | 4 forces the K-blocks per stage
+        const char* e = getenv("LP_SWAP_KB");
+        return e ? atoi(e) : 0;
+      }();
+      if (kb_env == 1 || kb_env == 2 || kb_env == 4) q.KB = kb_env;
+    }
     q.ksplit = 1;
     const int tiles_n = (N + lp::TC_BM - 1) / lp::TC_BM, nk = (K / lp::TC_BK + q.KB - 1) / q.KB;
     if (epilogue == LP_EPI_RESIDUAL && residual == out_f32 && !out_bf16 && !round_bf16 && tiles_n < lp::num_sms()) {

@@ -26,7 +26,7 @@ def timeit(fn, iters=40, warm=5):
 
 
 print(f"{'M,N,K':24s} {'terms':>5s} {'epi':>4s} {'us':>8s} {'GB/s':>7s}  torch.matmul us")
-for M in (16, 32, 64):
+for M in [int(v) for v in os.environ.get("KBENCH_M", "16,32,64").split(",")]:
     for N, K, epi in [(12288, 4096, 0), (16384, 4096, 1), (4096, 4096, 3), (4096, 16384, 3), (50688, 4096, 0)]:
         nt = 2
         x = torch.randn(M, K, device=DEV)

@@ -10,6 +10,8 @@ hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
 hdr = rows[hi]
 kn, mv, idc, gs, bs = (hdr.index(k) for k in ("Kernel Name", "Metric Value", "ID", "Grid Size", "Block Size"))
 ours = [r for r in rows[hi + 1:] if len(r) > mv and "lp::" in r[kn]]
+if not ours:  # list taken with `--kernel-name-base demangled -k regex:lp::`: already filtered, names come without the namespace
+    ours = [r for r in rows[hi + 1:] if len(r) > mv]
 with open(out + "_lp_launches.csv", "w", newline="") as f:
     w = csv.writer(f)
     w.writerow(["ID", "Kernel", "Grid", "Block", "gpu__time_duration.sum [ns]"])
