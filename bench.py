@@ -41,7 +41,7 @@ WORKLOADS = {
     "llama2-70b-bf16-b1-tp": ("Llama-2-70b-hf", None, 0, 1, 2048),
 }
 DEFAULT = "stablelm-3b-bf16-b1"
-EXTRAS = ["llama2-7b-int4g128-b1", "falcon-7b-bf16-b1", "stablelm-3b-bf16-b32"]
+EXTRAS = ["llama2-7b-int4g128-b1", "llama2-7b-nf4-b1", "falcon-7b-bf16-b1", "stablelm-3b-bf16-b32"]  # BASELINE configs[1..3]
 
 
 def ncu_traffic(workload):
