@@ -55,6 +55,8 @@ struct alignas(128) DsOp {
   float eps;
   int kind, dep, signal;
   int norm_kind, epi, fmt, N, K, split, ldx, nkb, nks, ntiles, ngroups, gp128, aux_bytes, x_attn;
+  int save_x, reuse_x;  // LayerNorm ops reading the same row back to back (parallel residual: QKV then FC): the first keeps the raw
+                        // row and its statistics in shared memory, the second stages from there (no L2 round trip, no reductions)
   int streamk;  // in-place residual op: stages (not tiles) are split evenly over the CTAs, partial tiles are added atomically
   // tensor-parallel exchange (kind 2): out = residual + sum over ranks of the partial at buf_off of every rank's symmetric buffer
   const unsigned long long* tp_bufs;  // [tp] peer-mapped buffer addresses
@@ -75,6 +77,7 @@ struct DsParams {
   float scale_log2;
   int nops, H, G, n_elem, max_seq, P;
   int nstages, stage_stride, xsum_floats;
+  int xs_bytes;  // size of the activation-column area; the raw-row buffer of save_x / reuse_x ops follows it
   int i4pair;  // int4 ops use the paired main loop (even stage count); 2: arithmetic skipped (timing experiment)
   int skip_dep;  // timing experiments only (LP_DS_SKIPDEP bit mask): skip the dependency wait of 1: attention, 2: attention
                  // projection, 4: MLP down-projection, 8: the ops that read the residual stream — results are WRONG
@@ -209,9 +212,12 @@ __device__ __forceinline__ int ds_pin(int v) { return (int)ds_pin((uint32_t)v); 
 //   int4 weights: block fixed point X = rint(x * 2^22 / max|x|) as three balanced base-256 int8 digit rows, bytes of a 16-column
 //   pair of groups in IMMA operand order (even columns of both groups, then odd columns), plus the per-128-column digit sums
 //   (zero-point term).
+// `xmode` 1: LayerNorm op that also leaves the raw row in `xraw` and (mean, rstd) in `xstat` for the next op; 2: the op that
+// stages from there — same arithmetic on the same values, so the result is bit-identical to staging from global memory.
 template <int NI, class LoadX, class WaitDep>
 __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDep wait_dep, float* s_stat, uint32_t xs_u32, float* xsum,
-                                             float* colscale, unsigned long long* tr) {
+                                             float* colscale, unsigned long long* tr, int xmode = 0, float* xraw = nullptr,
+                                             float* xstat = nullptr) {
   constexpr int STRIDE = DS_CTHREADS * 8;
   constexpr bool WCACHE = NI <= 2;
   const int K = o.K, fmt = o.fmt, split = o.split, ldx = o.ldx, norm_kind = o.norm_kind;
@@ -247,7 +253,18 @@ __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDe
   for (int i = 0; i < NI; ++i) {
     const int k = ctid * 8 + i * STRIDE;
     if (k < K) {
-      const float4 a = load_x(k), b = load_x(k + 4);
+      float4 a, b;
+      if (xmode == 2) {
+        a = *reinterpret_cast<const float4*>(xraw + k);
+        b = *reinterpret_cast<const float4*>(xraw + k + 4);
+      } else {
+        a = load_x(k);
+        b = load_x(k + 4);
+        if (xmode == 1) {
+          *reinterpret_cast<float4*>(xraw + k) = a;
+          *reinterpret_cast<float4*>(xraw + k + 4) = b;
+        }
+      }
       x[i][0] = a.x; x[i][1] = a.y; x[i][2] = a.z; x[i][3] = a.w; x[i][4] = b.x; x[i][5] = b.y; x[i][6] = b.z; x[i][7] = b.w;
     } else {
 #pragma unroll
@@ -316,8 +333,12 @@ __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDe
         sm += x[i][q];
         ss = fmaf(x[i][q], x[i][q], ss);
       }
-    block_reduce(sm, ss, false, sm, ss);
     float mean = 0.f, rstd;
+    if (xmode == 2) {
+      mean = xstat[0];
+      rstd = xstat[1];
+    } else {
+    block_reduce(sm, ss, false, sm, ss);
     if (has_bias) {
       mean = sm / (float)K;
       float v2 = 0.f, dummy;  // two-pass variance
@@ -334,6 +355,11 @@ __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDe
       rstd = 1.0f / sqrtf(v2 / (float)K + o.eps);
     } else {
       rstd = 1.0f / sqrtf(ss / (float)K + o.eps);
+    }
+    if (xmode == 1 && ctid == 0) {
+      xstat[0] = mean;
+      xstat[1] = rstd;
+    }
     }
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
@@ -680,13 +706,16 @@ __device__ __forceinline__ void ds_linear_main_i4pair(const DsOp& o, DsRing& rg,
 template <int HS, class WaitDep>
 __device__ __forceinline__ void ds_linear(const DsParams& p, const DsOp& o, const DsAttnGeo<HS>& geo, DsRing& rg, uint32_t red_u32,
                                           float* colscale, float* xsum, uint32_t xs_u32, volatile int* done, float* s_stat,
-                                          unsigned long long* tr, int& gt, WaitDep wait_dep) {
+                                          unsigned long long* tr, int& gt, WaitDep wait_dep, float* xraw, float* xstat, bool& have_xraw) {
   int sb, se;
   ds_stage_range(o, sb, se);
   if (se == sb) {  // CTA-uniform: nothing to compute, but later ops rely on the (cumulative) dependency
     wait_dep();
+    have_xraw = false;  // this CTA did not stage the row: a following reuse_x op stages from global memory
     return;
   }
+  const int xmode = (o.reuse_x && have_xraw) ? 2 : (o.save_x ? 1 : 0);
+  have_xraw = xmode == 1;
   // ---- stage x ----
   const bool small = o.K <= 2 * DS_CTHREADS * 8;
   if (o.x_attn) {
@@ -732,7 +761,7 @@ __device__ __forceinline__ void ds_linear(const DsParams& p, const DsOp& o, cons
   } else {
     const float* xg = o.x;
     auto load_plain = [&](int k) -> float4 { return ds_ldcg4(xg + k); };
-    if (small) ds_stage_row<2>(o, load_plain, wait_dep, s_stat, xs_u32, xsum, colscale, tr);
+    if (small) ds_stage_row<2>(o, load_plain, wait_dep, s_stat, xs_u32, xsum, colscale, tr, xmode, xraw, xstat);
     else if (o.K <= 4 * DS_CTHREADS * 8) ds_stage_row<4>(o, load_plain, wait_dep, s_stat, xs_u32, xsum, colscale, tr);
     else ds_stage_row<6>(o, load_plain, wait_dep, s_stat, xs_u32, xsum, colscale, tr);  // e.g. falcon-7b mlp.proj, K = 18176
   }
@@ -1061,6 +1090,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
   float* xsum = colscale + 8;
   unsigned char* xs = reinterpret_cast<unsigned char*>(xsum + p.xsum_floats);  // activation columns; attention scratch
   __shared__ __align__(16) float s_stat[4 * GS_CWARPS];
+  __shared__ float s_xstat[2];
+  __shared__ __align__(128) unsigned char s_ops[2 * sizeof(DsOp)];  // this op's and the next op's record (consumers)
+  float* xraw = reinterpret_cast<float*>(xs + p.xs_bytes);  // raw activation row kept for a reuse_x op (may be empty)
   const uint32_t red_u32 = gs_smem_u32(red), xs_u32 = gs_smem_u32(xs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1214,11 +1246,32 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
   if (p.tp_state0) tp_epoch[0] = *reinterpret_cast<volatile unsigned int*>(p.tp_state0);
   if (p.tp_state1) tp_epoch[1] = *reinterpret_cast<volatile unsigned int*>(p.tp_state1);
   int waited = -1, gt = 0;
+  bool have_xraw = false;  // the previous op left the raw activation row + statistics in shared memory (save_x)
+  // Op records are read from SHARED memory: every op used to start with an L2 round trip (~0.7 us under streaming load) for its
+  // own 384-byte record before it could even look at its dependency.  24 lanes of warp 1 copy the NEXT op's record with cp.async
+  // while the current op runs; the op-end barrier publishes it.  (The producer and the epilogue warps keep reading the table
+  // in global memory: they run ahead of / beside the critical path, and the TMA descriptor must stay in global memory.)
+  const uint32_t s_ops_u32 = gs_smem_u32(s_ops);
+  auto fetch_op = [&](int op) {
+    if (warp == 1 && lane < (int)(sizeof(DsOp) / 16)) {
+      const char* src = reinterpret_cast<const char*>(p.ops + op) + lane * 16;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s_ops_u32 + (uint32_t)((op & 1) * sizeof(DsOp) + lane * 16)), "l"(src) : "memory");
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+  };
+  auto fetch_wait = [&]() {
+    if (warp == 1) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  };
+  fetch_op(0);
+  fetch_wait();
+  gs_bar_consumers();
   for (int op = 0; op < p.nops; ++op) {
-    const DsOp& o = p.ops[op];
+    const DsOp& o = reinterpret_cast<const DsOp*>(s_ops)[op & 1];
+    if (op + 1 < p.nops) fetch_op(op + 1);
     unsigned long long* tr = p.trace ? p.trace + ((size_t)op * gridDim.x + blockIdx.x) * 8 : nullptr;
     if (tr && threadIdx.x == 0) tr[0] = gs_now();
     const int dep = o.dep;
+    const int signal = o.signal;  // read now: after the op-end barrier warp 1 may already overwrite this record with op + 2
     // barriers are cumulative: a CTA arrives for op d only after all of its earlier ops
     int skip = 0;
     if (p.skip_dep) {
@@ -1237,7 +1290,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
       if (tr && threadIdx.x == 0) tr[1] = gs_now();
     };
     if (o.kind == DS_KIND_LINEAR) {
-      ds_linear<HS>(p, o, geo, rg, red_u32, colscale, xsum, xs_u32, done, s_stat, tr, gt, wait_dep);
+      ds_linear<HS>(p, o, geo, rg, red_u32, colscale, xsum, xs_u32, done, s_stat, tr, gt, wait_dep, xraw, s_xstat, have_xraw);
     } else if (o.kind == DS_KIND_EXCHANGE) {
       wait_dep();
       ds_exchange(o, o.tp_state == p.tp_state1 ? tp_epoch[1] : tp_epoch[0]);
@@ -1245,10 +1298,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
       wait_dep();
       ds_attention<HS>(p, o, geo, rg, xs, tr);
     }
+    fetch_wait();  // the next op's record has landed (issued at the start of this op)
     asm volatile("bar.sync 4, %0;\n" ::"n"(DS_OPEND_THREADS) : "memory");  // the epilogue warps have written this op's rows
     if (threadIdx.x == 0) {
       // release at gpu scope: covers the rows written by the other warps of this CTA (ordered before by the barrier above)
-      if (o.signal) ds_red_release(p.counters + op);
+      if (signal) ds_red_release(p.counters + op);
       if (tr) tr[3] = gs_now();
     }
   }
@@ -1272,7 +1326,7 @@ __global__ void decode_step_prep_kernel(const void* __restrict__ idx, int idx64,
 // ------------------------------------------------------------------------------------------------ host side
 struct DsHostPlan {  // lp_step_handle, opaque to the caller
   uint32_t magic;
-  int nops, nstages, stage_stride, xsum_floats, hs, H, G, P, n_elem, max_seq, E, wte_dtype, idx64, grid, i4pair, l2_ahead, skip_dep;
+  int nops, nstages, stage_stride, xsum_floats, hs, H, G, P, n_elem, max_seq, E, wte_dtype, idx64, grid, i4pair, l2_ahead, skip_dep, xs_bytes;
   float scale_log2;
   size_t smem;
   const DsOp* ops_dev;
@@ -1298,7 +1352,7 @@ static int ds_launch(const DsParams& p, const DsHostPlan& h, void* stream) {
   static bool attr_set = false;
   auto kern = decode_step_kernel<HS>;
   if (!attr_set) {
-    LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)));
+    LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024)));
     attr_set = true;
   }
   return launch(kern, dim3(h.grid), dim3(DS_THREADS), h.smem, stream, p);
@@ -1455,8 +1509,25 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
   for (int i = 0; i < n_ops; ++i)
     if (dev[i].kind == DS_KIND_EXCHANGE) dev[i].tp_uses = tp_uses[dev[i].tp_state == tp_state[1] ? 1 : 0];
   xs_bytes = (xs_bytes + 15) / 16 * 16;
-  const size_t tail = 256 + (size_t)DS_RED_FLOATS * 4 + 32 + (size_t)xsum_floats * 4 + xs_bytes;
-  const size_t budget = 226 * 1024;  // 227 KB per CTA minus the 1 KB static block
+  // back-to-back LayerNorm ops on the same row (parallel residual: QKV, then FC on norm_2 of the same x): the second stages from
+  // the raw row + statistics the first leaves in shared memory (LP_DS_REUSEX=0 disables)
+  size_t xraw_bytes = 0;
+  {
+    const char* e = getenv("LP_DS_REUSEX");
+    const bool on = !(e && e[0] == '0');
+    for (int i = 1; on && i < n_ops; ++i) {
+      DsOp &a = dev[i - 1], &b = dev[i];
+      if (a.kind != DS_KIND_LINEAR || b.kind != DS_KIND_LINEAR) continue;
+      if (a.norm_kind != LP_NORM_LAYERNORM || b.norm_kind != LP_NORM_LAYERNORM || a.x_attn || b.x_attn) continue;
+      if (a.x != b.x || a.K != b.K || a.eps != b.eps || a.out == a.x || a.K > 2 * DS_CTHREADS * 8 || a.reuse_x) continue;
+      if (ops[i].dep != ops[i - 1].dep) continue;
+      a.save_x = 1;
+      b.reuse_x = 1;
+      xraw_bytes = std::max(xraw_bytes, (size_t)a.K * 4);
+    }
+  }
+  const size_t tail = 256 + (size_t)DS_RED_FLOATS * 4 + 32 + (size_t)xsum_floats * 4 + xs_bytes + xraw_bytes;
+  const size_t budget = 225 * 1024;  // 227 KB per CTA minus the static block (statistics, op records: < 2 KB)
   if (tail + 3 * (size_t)stage_stride + 1024 > budget) return LP_ERR_UNSUPPORTED;
   int ns = (int)((budget - tail - 1024) / stage_stride);
   if (ns > 14) ns = 14;
@@ -1488,6 +1559,7 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
   h.i4pair = i4pair ? (pair_env && pair_env[0] == '2' ? 2 : 1) : 0;  // 2: timing experiment, arithmetic skipped
   h.stage_stride = stage_stride;
   h.xsum_floats = xsum_floats;
+  h.xs_bytes = (int)xs_bytes;
   h.hs = gm->hs;
   h.H = gm->H;
   h.G = gm->G;
@@ -1549,6 +1621,7 @@ int lp_decode_step(const lp_step_handle* handle, void* stream) {
   p.i4pair = h.i4pair;
   p.l2_ahead = h.l2_ahead;
   p.skip_dep = h.skip_dep;
+  p.xs_bytes = h.xs_bytes;
   p.tp_state0 = h.tp_state0;
   p.tp_state1 = h.tp_state1;
   return h.hs == 128 ? ds_launch<128>(p, h, stream) : ds_launch<64>(p, h, stream);
