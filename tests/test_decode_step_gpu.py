@@ -92,6 +92,15 @@ def test_step_kernel_logits_int4():
     assert step_kernel_used(m)
 
 
+@pytest.mark.parametrize("kw,seed", [(NEOX, 61), (NEOX_SHARED, 62)], ids=["neox", "neox_shared_norm"])
+def test_step_kernel_logits_int4_layernorm_parallel_residual(kw, seed):
+    """GPTQ-int4 weights behind LayerNorm in a parallel-residual block: QKV and FC stage the same row back to back (the second
+    from the raw row + statistics the first leaves in shared memory), through the int8-digit activation path."""
+    cfg, m, om = int4_model(kw, seed)
+    teacher_forced(m, om, cfg, prompt_len=40, steps=40, max_seq=256)
+    assert step_kernel_used(m)
+
+
 @pytest.mark.parametrize("which", ["bf16", "int4", "gqa", "mqa"])
 def test_step_kernel_greedy_tokens_and_sliding_window(which):
     """generate(): 100 greedy tokens identical to the oracle, then the overflow case (max_seq_length 80 < 140 tokens: the ring
