@@ -688,6 +688,18 @@ gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           const uint32_t st = ring + (uint32_t)s * stage_bytes;
           uint32_t a_lo = tc_desc_lo(st);
           uint32_t b_lo = tc_desc_lo(st + KB * A_BYTES);
+          if (p.fuse && KB == 4) {
+            // the common decode-batch case, fully unrolled: with run-time loop bounds the 16 MMAs of a stage cost ~95 cycles of
+            // issue work each (they execute in 48), and with only two 96 KB stages that time is not hidden behind the loads
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k)
+                tc_mma_lo(tacc, a_lo + (uint32_t)(kk * (A_BYTES >> 4) + 2 * k), b_lo + (uint32_t)kk * bslab + (uint32_t)(2 * k), idesc,
+                          (kk | k) ? 1u : accumulate);
+            }
+            accumulate = 1;
+          } else
           for (int kk = 0; kk < KB; ++kk) {
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {  // 32 bytes (16 bf16) per MMA along K: +2 in the address field

@@ -16,7 +16,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 __global__ void __launch_bounds__(64, 1) k(const __grid_constant__ CUtensorMap map, const unsigned char* w, int N, int K, int mode, int depth,
-                                           uint32_t stage_bytes) {
+                                           uint32_t stage_bytes, int rows) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bars[16];
   if (threadIdx.x == 0) {
@@ -25,9 +25,9 @@ __global__ void __launch_bounds__(64, 1) k(const __grid_constant__ CUtensorMap m
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
-  const int kb_per_stage = (int)(stage_bytes / 2048);       // K-blocks of 128 B x 16 rows
+  const int kb_per_stage = (int)(stage_bytes / (128 * rows));  // K-blocks of 128 B x `rows` rows
   const int nks = (K * 2 / 128) / kb_per_stage;              // stages per 16-row tile
-  const long long ntiles = N / 16, total = ntiles * nks;
+  const long long ntiles = N / rows, total = ntiles * nks;
   const long long s0 = total * blockIdx.x / gridDim.x, s1 = total * (blockIdx.x + 1) / gridDim.x;  // contiguous ranges, like the step kernel
   int uses[16] = {0};
   int s = 0;
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(64, 1) k(const __grid_constant__ CUtensorMap m
     } else {
       const int tile = (int)(u / nks), ks = (int)(u % nks);
       asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(dst),
-                   "l"(&map), "r"(0), "r"(tile * 16), "r"(ks * kb_per_stage), "r"(bar) : "memory");
+                   "l"(&map), "r"(0), "r"(tile * rows), "r"(ks * kb_per_stage), "r"(bar) : "memory");
     }
     ++uses[s];
     if (++s == depth) s = 0;
@@ -62,24 +62,29 @@ int main(int argc, char** argv) {
   unsigned char* w;
   cudaMalloc(&w, (size_t)N * K * 2);
   cudaMemset(w, 1, (size_t)N * K * 2);
-  const int smem = 160 * 1024 + 1024;
+  const int smem = 200 * 1024 + 1024;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  struct Case { const char* name; int mode, depth; uint32_t stage; int l2; };
+  struct Case { const char* name; int mode, depth; uint32_t stage; int l2; int rows = 16; int ctas = 148; };
   const Case cases[] = {{"3-D tensor box, 16 rows x 1 KB runs, 16 KB x 10", 0, 10, 16384, 1}, {"contiguous 16 KB x 10", 1, 10, 16384, 1},
                         {"3-D tensor box, 16 rows x 2 KB runs, 32 KB x 5", 2, 5, 32768, 1}, {"contiguous 32 KB x 5", 1, 5, 32768, 1},
                         {"3-D tensor box 16 KB x 10, no L2 promotion", 0, 10, 16384, 0},
                         {"3-D tensor box 16 KB x 8", 0, 8, 16384, 1}, {"3-D tensor box 16 KB x 7", 0, 7, 16384, 1},
                         {"3-D tensor box 16 KB x 6", 0, 6, 16384, 1}, {"3-D tensor box 16 KB x 5", 0, 5, 16384, 1},
-                        {"3-D tensor box 16 KB x 4", 0, 4, 16384, 1}, {"3-D tensor box 16 KB x 3", 0, 3, 16384, 1}};
+                        {"3-D tensor box 16 KB x 4", 0, 4, 16384, 1}, {"3-D tensor box 16 KB x 3", 0, 3, 16384, 1},
+                        // the swap-AB GEMM's weight stages: 128 rows x 512 B runs
+                        {"128 rows x 512 B (64 KB) x 2, 148 CTAs", 0, 2, 65536, 1, 128, 148}, {"128 rows x 512 B (64 KB) x 2, 96 CTAs", 0, 2, 65536, 1, 128, 96},
+                        {"128 rows x 512 B (64 KB) x 3, 96 CTAs", 0, 3, 65536, 1, 128, 96}, {"128 rows x 256 B (32 KB) x 4, 96 CTAs", 0, 4, 32768, 1, 128, 96},
+                        {"128 rows x 256 B (32 KB) x 6, 96 CTAs", 0, 6, 32768, 1, 128, 96}, {"64 rows x 1 KB (64 KB) x 2, 96 CTAs", 0, 2, 65536, 1, 64, 96},
+                        {"contiguous 64 KB x 2, 96 CTAs", 1, 2, 65536, 1, 128, 96}, {"contiguous 64 KB x 3, 148 CTAs", 1, 3, 65536, 1, 128, 148}};
   printf("matrix %d x %d bf16 = %.0f MB, 148 CTAs\n", N, K, (double)N * K * 2e-6);
   for (const Case& c : cases) {
     CUtensorMap m;
     cuuint64_t dims[3] = {64, (cuuint64_t)N, (cuuint64_t)(K / 64)};
     cuuint64_t strides[2] = {(cuuint64_t)K * 2, 128};
-    cuuint32_t box[3] = {64, 16, c.stage / 2048};
+    cuuint32_t box[3] = {64, (cuuint32_t)c.rows, c.stage / (128 * c.rows)};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      c.l2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -87,7 +92,7 @@ int main(int argc, char** argv) {
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
       cudaEventRecord(e0);
-      k<<<148, 64, smem>>>(m, w, N, K, c.mode, c.depth, c.stage);
+      k<<<c.ctas, 64, smem>>>(m, w, N, K, c.mode, c.depth, c.stage, c.rows);
       cudaEventRecord(e1);
       cudaEventSynchronize(e1);
       float ms;
