@@ -79,6 +79,7 @@ struct DsParams {
   int nstages, stage_stride, xsum_floats;
   int xs_bytes;  // size of the activation-column area; the raw-row buffer of save_x / reuse_x ops follows it
   int i4pair;  // int4 ops use the paired main loop (even stage count); 2: arithmetic skipped (timing experiment)
+  int oprec;     // consumers read op records from the shared-memory double buffer (LP_DS_OPREC=1)
   int skip_dep;  // timing experiments only (LP_DS_SKIPDEP bit mask): skip the dependency wait of 1: attention, 2: attention
                  // projection, 4: MLP down-projection, 8: the ops that read the residual stream — results are WRONG
   int l2_ahead;  // weight stages the producer may prefetch into L2 beyond its TMA cursor while it is blocked on a full ring
@@ -1247,7 +1248,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
   if (p.tp_state1) tp_epoch[1] = *reinterpret_cast<volatile unsigned int*>(p.tp_state1);
   int waited = -1, gt = 0;
   bool have_xraw = false;  // the previous op left the raw activation row + statistics in shared memory (save_x)
-  // Op records are read from SHARED memory: every op used to start with an L2 round trip (~0.7 us under streaming load) for its
+  // LP_DS_OPREC=1 (off by default): op records are read from SHARED memory: every op otherwise starts with an L2 round trip (~0.7 us under streaming load) for its
   // own 384-byte record before it could even look at its dependency.  24 lanes of warp 1 copy the NEXT op's record with cp.async
   // while the current op runs; the op-end barrier publishes it.  (The producer and the epilogue warps keep reading the table
   // in global memory: they run ahead of / beside the critical path, and the TMA descriptor must stay in global memory.)
@@ -1262,12 +1263,15 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
   auto fetch_wait = [&]() {
     if (warp == 1) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   };
-  fetch_op(0);
-  fetch_wait();
-  gs_bar_consumers();
+  const bool oprec = p.oprec != 0;  // CTA-uniform
+  if (oprec) {
+    fetch_op(0);
+    fetch_wait();
+    gs_bar_consumers();
+  }
   for (int op = 0; op < p.nops; ++op) {
-    const DsOp& o = reinterpret_cast<const DsOp*>(s_ops)[op & 1];
-    if (op + 1 < p.nops) fetch_op(op + 1);
+    const DsOp& o = oprec ? reinterpret_cast<const DsOp*>(s_ops)[op & 1] : p.ops[op];
+    if (oprec && op + 1 < p.nops) fetch_op(op + 1);
     unsigned long long* tr = p.trace ? p.trace + ((size_t)op * gridDim.x + blockIdx.x) * 8 : nullptr;
     if (tr && threadIdx.x == 0) tr[0] = gs_now();
     const int dep = o.dep;
@@ -1298,7 +1302,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
       wait_dep();
       ds_attention<HS>(p, o, geo, rg, xs, tr);
     }
-    fetch_wait();  // the next op's record has landed (issued at the start of this op)
+    if (oprec) fetch_wait();  // the next op's record has landed (issued at the start of this op)
     asm volatile("bar.sync 4, %0;\n" ::"n"(DS_OPEND_THREADS) : "memory");  // the epilogue warps have written this op's rows
     if (threadIdx.x == 0) {
       // release at gpu scope: covers the rows written by the other warps of this CTA (ordered before by the barrier above)
@@ -1326,7 +1330,7 @@ __global__ void decode_step_prep_kernel(const void* __restrict__ idx, int idx64,
 // ------------------------------------------------------------------------------------------------ host side
 struct DsHostPlan {  // lp_step_handle, opaque to the caller
   uint32_t magic;
-  int nops, nstages, stage_stride, xsum_floats, hs, H, G, P, n_elem, max_seq, E, wte_dtype, idx64, grid, i4pair, l2_ahead, skip_dep, xs_bytes;
+  int nops, nstages, stage_stride, xsum_floats, hs, H, G, P, n_elem, max_seq, E, wte_dtype, idx64, grid, i4pair, l2_ahead, skip_dep, xs_bytes, oprec;
   float scale_log2;
   size_t smem;
   const DsOp* ops_dev;
@@ -1535,13 +1539,13 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
     const int c = atoi(cap);
     if (c >= 3 && c < ns) ns = c;
   }
-  // paired int4 main loop (ds_linear_main_i4pair) needs an even stage count; LP_DS_I4PAIR=0 keeps the one-group-per-warp loop
+  // paired int4 main loop (ds_linear_main_i4pair) needs an even stage count; without LP_DS_I4PAIR=1 the one-group-per-warp loop runs
   // (the same transformation of the bf16 loop was measured too: 1591 -> 1586 us on stablelm-3b, 3226 -> 3192 us on falcon-7b —
   // not worth a second summation order next to the per-op path, so bf16 keeps one loop)
   bool any_int4 = false;
   for (int i = 0; i < n_ops; ++i) any_int4 |= dev[i].kind == DS_KIND_LINEAR && dev[i].fmt == LP_W_INT4;
-  const char* pair_env = getenv("LP_DS_I4PAIR");
-  const bool i4pair = any_int4 && !(pair_env && pair_env[0] == '0') && ns >= 5;
+  const char* pair_env = getenv("LP_DS_I4PAIR");  // opt-in: "1" paired loop, "2" paired loop without arithmetic
+  const bool i4pair = any_int4 && pair_env && pair_env[0] != '0' && ns >= 5;
   if (i4pair) ns &= ~1;
 
   DsHostPlan h;
@@ -1555,6 +1559,8 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
     if (h.l2_ahead < 0) h.l2_ahead = 0;
     const char* sd = getenv("LP_DS_SKIPDEP");
     h.skip_dep = sd ? atoi(sd) : 0;
+    const char* orc = getenv("LP_DS_OPREC");
+    h.oprec = (orc && orc[0] == '1') ? 1 : 0;
   }
   h.i4pair = i4pair ? (pair_env && pair_env[0] == '2' ? 2 : 1) : 0;  // 2: timing experiment, arithmetic skipped
   h.stage_stride = stage_stride;
@@ -1622,6 +1628,7 @@ int lp_decode_step(const lp_step_handle* handle, void* stream) {
   p.l2_ahead = h.l2_ahead;
   p.skip_dep = h.skip_dep;
   p.xs_bytes = h.xs_bytes;
+  p.oprec = h.oprec;
   p.tp_state0 = h.tp_state0;
   p.tp_state1 = h.tp_state1;
   return h.hs == 128 ? ds_launch<128>(p, h, stream) : ds_launch<64>(p, h, stream);
