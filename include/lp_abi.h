@@ -27,14 +27,15 @@
 extern "C" {
 #endif
 
-#define LP_ABI_VERSION 4
+#define LP_ABI_VERSION 5
 
 typedef enum {
   LP_OK = 0,
   LP_ERR_INVALID_ARG = -1,   /* bad enum / null pointer / non-positive size                 */
   LP_ERR_UNSUPPORTED = -2,   /* shape or alignment the kernels do not cover                 */
   LP_ERR_CUDA = -3,          /* a CUDA runtime call failed (see lp_last_cuda_error)          */
-  LP_ERR_WORKSPACE = -4      /* caller-provided workspace too small                          */
+  LP_ERR_WORKSPACE = -4,     /* caller-provided workspace too small                          */
+  LP_ERR_TIMEOUT = -5        /* a bounded wait inside lp_decode_step expired (lp_decode_step_status) */
 } lp_status;
 
 /* storage types of tensors that are not fp32 activations */
@@ -102,6 +103,14 @@ int lp_debug_stream_trace(void* device_buf);
 
 /* One-time per-device setup (cudaFuncSetAttribute for large dynamic shared memory).  Idempotent, thread-safe. */
 int lp_init(int device);
+
+/* Range check of a step's inputs ON THE DEVICE, for callers whose ids / positions live in device memory they own (the replayed
+ * decode graph): the reference raises on a token id outside [0, vocab) (nn.Embedding, model.py:99) and on a position outside the
+ * RoPE table (index_select, model.py:88-92).  Out-of-range values are CLAMPED IN PLACE — the kernels that follow never index out
+ * of bounds — and *flag |= 1 (token) | 2 (position); `flag` may be mapped pinned host memory, so the host sees it without a copy.
+ * Callers that can read their inputs on the host (prefill) validate there and raise like the reference. */
+int lp_validate_inputs(void* idx, int idx_is_int64, int n_idx, int vocab, int32_t* pos, int n_pos, int block_size, int32_t* flag,
+                       void* stream);
 
 /* replaces nn.Embedding `self.transformer.wte(idx)` (model.py:99).  idx: int32 or int64 [rows]; if idx_offset is
  * non-NULL the rows are idx[*idx_offset + r] (device-side position, so a captured decode step can be replayed). */
@@ -255,8 +264,22 @@ size_t lp_decode_step_workspace_bytes(int H, int hs);
  * op table into plan_dev (128-byte aligned, lp_decode_step_plan_bytes(n_ops)). */
 int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* geom, void* plan_dev, size_t plan_bytes,
                         lp_step_handle* handle);
-/* One decode step: 2 launches, graph-capturable, no allocation, no synchronisation. */
+/* One decode step: 2 launches, graph-capturable, no allocation, no synchronisation.
+ * The step kernel is persistent (one CTA per SM) and its CTAs wait for each other through arrival counters, so the whole grid
+ * must be co-resident: lp_decode_step_plan checks the occupancy (LP_ERR_UNSUPPORTED if the grid cannot fit) and, where the
+ * device accepts it together with programmatic dependent launch (probed once per device), the kernel is launched with
+ * cudaLaunchAttributeCooperative, i.e. the driver guarantees co-residency.  Every wait on another CTA or another GPU is bounded
+ * (default 4 s, env LP_DS_TIMEOUT_MS, 0 = unbounded): when a bound expires the kernel records {code, op, dep, CTA, value seen}
+ * in the plan's sticky error record, stops waiting everywhere and runs to its end — no hang, the results of that step are
+ * garbage, and lp_decode_step_status reports it. */
 int lp_decode_step(const lp_step_handle* handle, void* stream);
+/* Synchronous health check of the steps launched so far with this plan (one 32-byte device-to-host copy): LP_OK, or
+ * LP_ERR_TIMEOUT with info = {code (1: dependency counter, 2: tensor-parallel peer flag), op index, dep / peer rank, CTA, value
+ * seen, 0, 0, 0}; the record is cleared when it has been reported.  info may be NULL.  generate() calls it once per call. */
+int lp_decode_step_status(const lp_step_handle* handle, int32_t info[8]);
+/* 1 if steps of this plan are launched cooperatively, 0 if the device refused the attribute combination (plain launch,
+ * occupancy check + watchdog only). */
+int lp_decode_step_cooperative(const lp_step_handle* handle);
 /* Debug aid: device_buf (>= n_ops * 148 * 8 uint64) receives per-(op, CTA) globaltimer stamps [start, dependency met,
  * activations staged, end, x loaded, normalised, max|x| known, -]; NULL switches it off. */
 int lp_debug_step_trace(void* device_buf);
@@ -278,8 +301,8 @@ int lp_tp_allreduce_residual(const void* buf_ptrs_dev, const void* pad_ptrs_dev,
  * (ties with the k-th value survive), softmax, one multinomial draw (exponential race, Philox keyed by
  * (seed, *step)).  top_k == 1 is lowest-index arg-max.  logits fp32 [rows, V] -> token_out int32 [rows].
  * If pos_inout != NULL the kernel advances the device-side position: *pos_inout += 1 (and, when seq_buf != NULL,
- * rows == 1: seq_buf[*pos_inout + 1] = token first), and for rows == 1 *step += 1 — so a captured decode step can be
- * replayed without host round trips (generate/base.py:147-153). */
+ * rows == 1: seq_buf[*pos_inout + 1] = token first); *step += 1 once per launch for any row count (the noise is keyed by
+ * (index, *step, row)) — so a captured decode step can be replayed without host round trips (generate/base.py:147-153). */
 int lp_sample(const float* logits, int rows, int V, float temperature, int top_k, uint64_t seed, int32_t* step,
               int32_t* token_out, int32_t* seq_buf, int32_t* pos_inout, void* stream);
 

@@ -17,7 +17,7 @@ LP_F32, LP_BF16 = 0, 1
 LP_W_F32, LP_W_BF16, LP_W_INT4, LP_W_NF4, LP_W_INT8 = 0, 1, 2, 3, 4
 LP_EPI_NONE, LP_EPI_GELU, LP_EPI_SWIGLU, LP_EPI_RESIDUAL = 0, 1, 2, 3
 LP_NORM_LAYERNORM, LP_NORM_RMS = 0, 1
-LP_ABI_VERSION = 4
+LP_ABI_VERSION = 5
 LP_WF_AUX_PACKED = 1
 LP_STEP_LINEAR, LP_STEP_ATTENTION, LP_STEP_EXCHANGE = 0, 1, 2
 
@@ -69,6 +69,7 @@ PROTOTYPES = {
     "lp_set_linear_path": (c_int, [c_int]),
     "lp_debug_stream_trace": (c_int, [c_void_p]),
     "lp_init": (c_int, [c_int]),
+    "lp_validate_inputs": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "lp_embed": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "lp_norm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
     "lp_linear": (c_int, [c_void_p, c_int, ctypes.POINTER(LpWeight), c_int, c_void_p, c_void_p, c_int, c_void_p]),
@@ -95,6 +96,8 @@ PROTOTYPES = {
     "lp_decode_step_plan": (c_int, [ctypes.POINTER(LpStepOp), c_int, ctypes.POINTER(LpStepGeom), c_void_p, c_size_t,
                                     ctypes.POINTER(LpStepHandle)]),
     "lp_decode_step": (c_int, [ctypes.POINTER(LpStepHandle), c_void_p]),
+    "lp_decode_step_status": (c_int, [ctypes.POINTER(LpStepHandle), ctypes.POINTER(ctypes.c_int32)]),
+    "lp_decode_step_cooperative": (c_int, [ctypes.POINTER(LpStepHandle)]),
     "lp_debug_step_trace": (c_int, [c_void_p]),
     "lp_debug_gemm_stats": (c_int, [c_void_p]),
     "lp_tp_allreduce_residual": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,

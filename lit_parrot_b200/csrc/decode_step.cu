@@ -33,11 +33,12 @@ namespace lp {
 constexpr int DS_MAXP = 4;           // max sequence splits per head
 constexpr int DS_CTHREADS = GS_CWARPS * 32;
 constexpr int DS_EWARPS = 2;                                   // epilogue warps (tile parity 0 / 1)
-constexpr int DS_THREADS = (GS_CWARPS + 1 + DS_EWARPS) * 32;   // consumers + producer warp + epilogue warps
+constexpr int DS_THREADS = (GS_CWARPS + 1 + DS_EWARPS + 1) * 32;   // consumers + producer warp + epilogue warps + watcher warp
 constexpr int DS_TILE_BAR_THREADS = DS_CTHREADS + 32;          // named barriers 2 / 3: the consumers arrive, one epilogue warp waits
 constexpr int DS_OPEND_THREADS = DS_CTHREADS + DS_EWARPS * 32; // named barrier 4: end of an op
 constexpr int DS_KIND_LINEAR = 0, DS_KIND_EXCHANGE = 2;
 constexpr int DS_MAX_TP = 8;
+constexpr int DS_NREC = 3;  // op records resident in shared memory: previous (its signal may still be pending), current, next
 constexpr int DS_RED_FLOATS = 2 * GS_CWARPS * 16 * 4;  // [2 parities][warps][16 rows][4 B-columns]
 
 struct alignas(128) DsOp {
@@ -79,10 +80,10 @@ struct DsParams {
   int nstages, stage_stride, xsum_floats;
   int xs_bytes;  // size of the activation-column area; the raw-row buffer of save_x / reuse_x ops follows it
   int i4pair;  // int4 ops use the paired main loop (even stage count); 2: arithmetic skipped (timing experiment)
-  int oprec;     // consumers read op records from the shared-memory double buffer (LP_DS_OPREC=1)
-  int skip_dep;  // timing experiments only (LP_DS_SKIPDEP bit mask): skip the dependency wait of 1: attention, 2: attention
-                 // projection, 4: MLP down-projection, 8: the ops that read the residual stream — results are WRONG
   int l2_ahead;  // weight stages the producer may prefetch into L2 beyond its TMA cursor while it is blocked on a full ring
+  const int* deps;      // [nops] dep of every op, contiguous (the watcher thread walks it)
+  unsigned* err;        // [8] sticky error record of the watchdog: {code, op, dep, CTA, counter value, ...}; 0 = healthy
+  unsigned long long timeout_ns;  // bound of every cross-CTA / cross-GPU wait (0: unbounded)
   unsigned int* tp_state0;  // epoch counters of the (up to two) tensor-parallel exchange slots, or NULL
   unsigned int* tp_state1;
 };
@@ -101,6 +102,30 @@ __device__ __forceinline__ void ds_red_release(unsigned* p) {
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(p) : "memory");
 }
 __device__ __forceinline__ float4 ds_ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ int ds_lds_acquire(const int* p) {  // CTA-scope acquire of a shared-memory flag
+  int v;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];\n" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ds_sts_release(int* p, int v) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
+// Watchdog: every wait on ANOTHER CTA (dependency counters) or another GPU (exchange flags) is bounded.  The first waiter whose
+// bound expires writes a record into the sticky error word of the plan and stops waiting; everybody else sees the word within a
+// few polls and stops waiting too, so the kernel runs to its end (results of that step are garbage) and exits: a dead dependency
+// becomes LP_ERR_TIMEOUT from lp_decode_step_status() instead of a hung GPU.  Waits inside a CTA (mbarriers, named barriers) only
+// depend on that CTA's own warps and need no bound.
+constexpr unsigned DS_ERR_DEP_TIMEOUT = 1u, DS_ERR_EXCHANGE_TIMEOUT = 2u;
+__device__ __forceinline__ void ds_report(unsigned* err, unsigned code, int op, int dep, unsigned seen) {
+  if (atomicCAS(err, 0u, code) == 0u) {
+    err[1] = (unsigned)op;
+    err[2] = (unsigned)dep;
+    err[3] = blockIdx.x;
+    err[4] = seen;
+    __threadfence();
+  }
+}
 
 // `bytes` (multiple of 16) of constants into L2: issued by the producer thread well ahead of the consumers' need
 __device__ __forceinline__ void ds_prefetch_l2(const void* p, uint32_t bytes) {
@@ -217,8 +242,7 @@ __device__ __forceinline__ int ds_pin(int v) { return (int)ds_pin((uint32_t)v); 
 // stages from there — same arithmetic on the same values, so the result is bit-identical to staging from global memory.
 template <int NI, class LoadX, class WaitDep>
 __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDep wait_dep, float* s_stat, uint32_t xs_u32, float* xsum,
-                                             float* colscale, unsigned long long* tr, int xmode = 0, float* xraw = nullptr,
-                                             float* xstat = nullptr) {
+                                             unsigned long long* tr, int xmode = 0, float* xraw = nullptr, float* xstat = nullptr) {
   constexpr int STRIDE = DS_CTHREADS * 8;
   constexpr bool WCACHE = NI <= 2;
   const int K = o.K, fmt = o.fmt, split = o.split, ldx = o.ldx, norm_kind = o.norm_kind;
@@ -233,23 +257,17 @@ __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDe
     const float4 a = *reinterpret_cast<const float4*>(base + k), b = *reinterpret_cast<const float4*>(base + k + 4);
     d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
   };
-  // norm parameters are constants: fetch them BEFORE waiting for the producer op, so that they are neither part of the burst of
-  // activation loads all CTAs issue at the same moment nor on the critical path behind the dependency
-  // (warp 0 polls the dependency counter: its own parameter loads come after the wait, so that the polling loads do not queue
-  // behind them; by then the producer's L2 prefetch has brought the lines in)
-  auto load_norm = [&]() {
+  // norm parameters are constants: every warp fetches them BEFORE waiting for the producer op (the dependency is polled by the
+  // watcher thread of the producer warp, so nobody here has a reason to hold back), off the critical path behind the dependency
 #pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const int k = ctid * 8 + i * STRIDE;
-      if (WCACHE && has_norm && k < K) {
-        ld8(nw, k, wq[WCACHE ? i : 0]);
-        if (has_bias) ld8(nb, k, bq[WCACHE ? i : 0]);
-      }
+  for (int i = 0; i < NI; ++i) {
+    const int k = ctid * 8 + i * STRIDE;
+    if (WCACHE && has_norm && k < K) {
+      ld8(nw, k, wq[WCACHE ? i : 0]);
+      if (has_bias) ld8(nb, k, bq[WCACHE ? i : 0]);
     }
-  };
-  if (warp != 0) load_norm();
+  }
   wait_dep();
-  if (warp == 0) load_norm();
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
     const int k = ctid * 8 + i * STRIDE;
@@ -279,9 +297,9 @@ __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDe
     if (acc0 != 12345.678f) tr[4] = gs_now();  // the loads have returned
   }
   int sbuf = 0;
-  // block-wide (sum or max of a, sum of b); one barrier per reduction: the statistics buffer is double buffered
-  auto block_reduce = [&](float a, float b, bool is_max, float& ra, float& rb) {
-    a = is_max ? warp_max(a) : warp_sum(a);
+  // block-wide (sum of a, sum of b); one barrier per reduction: the statistics buffer is double buffered
+  auto block_reduce = [&](float a, float b, float& ra, float& rb) {
+    a = warp_sum(a);
     b = warp_sum(b);
     float* st = s_stat + sbuf * 2 * GS_CWARPS;
     sbuf ^= 1;
@@ -296,35 +314,28 @@ __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDe
 #pragma unroll
     for (int w = 0; w < GS_CWARPS / 4; ++w) {
       const float4 va = s4[w], vb = s4[GS_CWARPS / 4 + w];
-      ra = is_max ? fmaxf(fmaxf(ra, fmaxf(va.x, va.y)), fmaxf(va.z, va.w)) : ra + ((va.x + va.y) + (va.z + va.w));
+      ra += (va.x + va.y) + (va.z + va.w);
       rb += (vb.x + vb.y) + (vb.z + vb.w);
     }
   };
-  float amax_pre = -1.f;  // max|x| when it came for free with the norm statistics
-  if (has_norm && !has_bias && fmt == LP_W_INT4 && WCACHE) {
-    // RMSNorm feeding an int4 layer: x_n = w x rstd, so max|x_n| = rstd max|w x|: ONE reduction gives both statistics
-    float ss = 0.f, mw = 0.f;
+  if (has_norm && !has_bias) {
+    // RMSNorm: W . (w x rstd) = rstd * (W . (w x)): the scalar rstd is applied by the tile epilogue, so the row is converted
+    // without waiting for a reduction; sum x^2 travels through s_stat[2 * GS_CWARPS ..] and the barrier that ends the staging
+    // (ds_linear turns it into the post scale).  No block reduction on this path.
+    float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < NI; ++i)
+    for (int i = 0; i < NI; ++i) {
+      const int k = ctid * 8 + i * STRIDE;
+      float wl[8];
+      if (!WCACHE && k < K) ld8(nw, k, wl);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         ss = fmaf(x[i][q], x[i][q], ss);
-        mw = fmaxf(mw, fabsf(wq[WCACHE ? i : 0][q] * x[i][q]));
+        x[i][q] *= (WCACHE ? wq[WCACHE ? i : 0][q] : (k < K ? wl[q] : 0.f));
       }
-    block_reduce(mw, ss, true, mw, ss);
-    const float rstd = 1.0f / sqrtf(ss / (float)K + o.eps);
-    float am = 0.f;
-#pragma unroll
-    for (int i = 0; i < NI; ++i)
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        x[i][q] = wq[WCACHE ? i : 0][q] * (x[i][q] * rstd);
-        am = fmaxf(am, fabsf(x[i][q]));
-      }
-    // every thread needs the SAME max: take the bound rstd * max|w x| rounded up a little instead of a second reduction
-    // (the products above are rounded differently than w * x alone, by at most 2 ulp)
-    amax_pre = mw * rstd * 1.000001f;
-    (void)am;
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) s_stat[2 * GS_CWARPS + warp] = ss;
   } else if (has_norm) {
     float sm = 0.f, ss = 0.f;
 #pragma unroll
@@ -339,8 +350,7 @@ __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDe
       mean = xstat[0];
       rstd = xstat[1];
     } else {
-    block_reduce(sm, ss, false, sm, ss);
-    if (has_bias) {
+      block_reduce(sm, ss, sm, ss);
       mean = sm / (float)K;
       float v2 = 0.f, dummy;  // two-pass variance
 #pragma unroll
@@ -352,15 +362,12 @@ __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDe
             v2 = fmaf(d, d, v2);
           }
         }
-      block_reduce(v2, 0.f, false, v2, dummy);
+      block_reduce(v2, 0.f, v2, dummy);
       rstd = 1.0f / sqrtf(v2 / (float)K + o.eps);
-    } else {
-      rstd = 1.0f / sqrtf(ss / (float)K + o.eps);
-    }
-    if (xmode == 1 && ctid == 0) {
-      xstat[0] = mean;
-      xstat[1] = rstd;
-    }
+      if (xmode == 1 && ctid == 0) {
+        xstat[0] = mean;
+        xstat[1] = rstd;
+      }
     }
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
@@ -369,62 +376,63 @@ __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDe
         float wl[8], bl[8];
         if (!WCACHE) {
           ld8(nw, k, wl);
-          if (has_bias) ld8(nb, k, bl);
+          ld8(nb, k, bl);
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float wv = WCACHE ? wq[WCACHE ? i : 0][q] : wl[q];
-          if (has_bias) x[i][q] = (x[i][q] - mean) * rstd * wv + (WCACHE ? bq[WCACHE ? i : 0][q] : bl[q]);
-          else x[i][q] = wv * (x[i][q] * rstd);
-        }
+        for (int q = 0; q < 8; ++q)
+          x[i][q] = (x[i][q] - mean) * rstd * (WCACHE ? wq[WCACHE ? i : 0][q] : wl[q]) + (WCACHE ? bq[WCACHE ? i : 0][q] : bl[q]);
       }
     }
   }
   if (tr && ctid == 0) tr[5] = gs_now();  // normalised
   if (fmt == LP_W_INT4) {
-    float amax = amax_pre, dummy;
-    if (amax_pre < 0.f) {
-      amax = 0.f;
-#pragma unroll
-      for (int i = 0; i < NI; ++i)
-#pragma unroll
-        for (int q = 0; q < 8; ++q) amax = fmaxf(amax, fabsf(x[i][q]));
-      block_reduce(amax, 0.f, true, amax, dummy);
-    }
-    if (tr && ctid == 0) tr[6] = gs_now();  // max|x| known
-    const float inv = amax > 0.f ? 4194304.0f / amax : 0.f;
-    if (ctid < 3) colscale[ctid] = (amax / 4194304.0f) * (ctid == 0 ? 1.0f : (ctid == 1 ? 256.0f : 65536.0f));
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
       const int k = ctid * 8 + i * STRIDE;
       if (k < kpad) {  // half-warp uniform (a 128-column chunk = 16 threads): the zero padding of the last chunk is written too
-        int dg[3][8], sum[3] = {0, 0, 0};
+        // block fixed point PER 128-COLUMN GROUP (the 16 lanes that own it): X = rint(x * 2^22 / max|x_group|); the group's
+        // scale a_g = max / 2^22 rides in the 4th float of the group's digit-sum record and is folded into the weight scale by
+        // the main loop.  No block-wide reduction, and small groups keep all 22 bits.
+        float am = 0.f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          // X = d0 + 256 d1 + 65536 d2 with balanced digits d0, d1 in [-128, 127]
-          const int X = __float2int_rn(x[i][q] * inv);
-          const int t1 = (X + 128) >> 8;
-          const int d0 = X - (t1 << 8);
-          const int d2 = (t1 + 128) >> 8;
-          const int d1 = t1 - (d2 << 8);
-          dg[0][q] = d0; dg[1][q] = d1; dg[2][q] = d2;
-          sum[0] += d0; sum[1] += d1; sum[2] += d2;
+        for (int q = 0; q < 8; ++q) am = fmaxf(am, fabsf(x[i][q]));
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, off));
+        const float inv = am > 0.f ? 4194304.0f / am : 0.f;
+        // X = d0 + 256 d1 + 65536 d2 with balanced digits d0, d1 in [-128, 127]: the bytes of Z = (X + 0x8080) ^ 0x8080 ARE those digits
+        // as int8 (X + 0x8080 = (d0 + 128) + 256 (d1 + 128) + 65536 d2 without carries; ^ 0x80 takes the 128 off again)
+        uint32_t z[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) z[q] = (uint32_t)(__float2int_rn(x[i][q] * inv) + 0x8080) ^ 0x8080u;
+        // 4 x 4 byte transposes: digit d of columns 0,2,4,6 (IMMA a0/a1 side) and of columns 1,3,5,7 (a2/a3 side)
+        uint32_t lo[3], hi[3];
+        {
+          const uint32_t u0 = __byte_perm(z[0], z[2], 0x5140), u1 = __byte_perm(z[4], z[6], 0x5140);
+          const uint32_t u2 = __byte_perm(z[0], z[2], 0x7362), u3 = __byte_perm(z[4], z[6], 0x7362);
+          lo[0] = __byte_perm(u0, u1, 0x5410);
+          lo[1] = __byte_perm(u0, u1, 0x7632);
+          lo[2] = __byte_perm(u2, u3, 0x5410);
+          const uint32_t v0 = __byte_perm(z[1], z[3], 0x5140), v1 = __byte_perm(z[5], z[7], 0x5140);
+          const uint32_t v2 = __byte_perm(z[1], z[3], 0x7362), v3 = __byte_perm(z[5], z[7], 0x7362);
+          hi[0] = __byte_perm(v0, v1, 0x5410);
+          hi[1] = __byte_perm(v0, v1, 0x7632);
+          hi[2] = __byte_perm(v2, v3, 0x5410);
         }
+        float ps[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          // bytes of the 8-column group in operand order: columns 0,2,4,6 (IMMA a0/a1 side), then 1,3,5,7 (a2/a3 side)
-          const uint32_t lo = __byte_perm(__byte_perm(dg[d][0], dg[d][2], 0x0040), __byte_perm(dg[d][4], dg[d][6], 0x0040), 0x5410);
-          const uint32_t hi = __byte_perm(__byte_perm(dg[d][1], dg[d][3], 0x0040), __byte_perm(dg[d][5], dg[d][7], 0x0040), 0x5410);
           // 16-column pair of groups (A, B) -> [A.even | B.even | A.odd | B.odd]: the B operands of the low-nibble and the
           // high-nibble IMMA are then adjacent registers of one 128-bit load
           const uint32_t a16 = xs_u32 + (uint32_t)(d * ldx + (k & ~15) + ((k & 8) >> 1));
-          asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(a16), "r"(lo) : "memory");
-          asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(a16 + 8), "r"(hi) : "memory");
-          float ps = (float)sum[d];
+          asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(a16), "r"(lo[d]) : "memory");
+          asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(a16 + 8), "r"(hi[d]) : "memory");
+          int sd = __dp4a((int)lo[d], 0x01010101, 0);  // digit sum of the thread's 8 columns
+          sd = __dp4a((int)hi[d], 0x01010101, sd);
 #pragma unroll
-          for (int off = 8; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
-          if ((lane & 15) == 0) xsum[(k >> 7) * 4 + d] = ps;
+          for (int off = 8; off > 0; off >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, off);
+          ps[d] = (float)sd;
         }
+        if ((lane & 15) == 0) *reinterpret_cast<float4*>(xsum + (k >> 7) * 4) = make_float4(ps[0], ps[1], ps[2], am * (1.0f / 4194304.0f));
       }
     }
   } else {
@@ -448,7 +456,6 @@ __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDe
         }
       }
     }
-    if (ctid < split) colscale[ctid] = 1.0f;
   }
 }
 
@@ -458,7 +465,7 @@ __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDe
 // int8 digit columns, then the per-group scale / zero point.  Everything that does not change from stage to stage (lane
 // offsets inside a stage, the position of the warp's K-slice) lives in registers; per stage: wait, loads, math, arrive.
 template <int FMT, bool PACKED>
-__device__ __forceinline__ void ds_linear_main(const DsOp& o, DsRing& rg, uint32_t red_u32, const float* colscale, uint32_t xsum_u32,
+__device__ __forceinline__ void ds_linear_main(const DsOp& o, DsRing& rg, uint32_t red_u32, uint32_t xsum_u32,
                                                uint32_t xs_u32, volatile int* done, int sb, int se, int& gt) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -467,7 +474,6 @@ __device__ __forceinline__ void ds_linear_main(const DsOp& o, DsRing& rg, uint32
   const int bcol = g < split ? g : split - 1;  // B columns >= split only feed accumulator columns nobody reads
   const int nunits = se - sb;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  (void)colscale;
 
   // lane-constant byte offsets inside a stage, and the K position of this warp's slice in the first stage of a tile
   uint32_t woff0, woff1, xpos0, xstep;
@@ -491,7 +497,8 @@ __device__ __forceinline__ void ds_linear_main(const DsOp& o, DsRing& rg, uint32
   }
   const int slice_step = FMT == LP_W_BF16 ? GS_KB : GS_KB * 2;
   constexpr int AUXB = PACKED ? 4 : 8;
-  const uint32_t xsum0 = ds_pin(xsum_u32 + (uint32_t)((kbl * 2 + sub0) * 4 + 2 * (t & 1)) * 4);
+  const uint32_t xsum0 = ds_pin(xsum_u32 + (uint32_t)((kbl * 2 + sub0) * 4) * 4);  // group record {digit sums 0..2, a_g}
+  const bool todd = ds_pin(t & 1) != 0;  // accumulator columns 2t, 2t+1: digits (0, 1) for even t, (2, -) for odd t
   const uint32_t aux0 = ds_pin((uint32_t)(GS_KB * GS_BLK_BYTES + (slice0 * 16 + pr0) * AUXB));  // group 128: scale slot of this slice
   const uint32_t auxr = ds_pin((uint32_t)(GS_KB * GS_BLK_BYTES + pr0 * AUXB));
   woff0 = ds_pin(woff0);
@@ -520,7 +527,10 @@ __device__ __forceinline__ void ds_linear_main(const DsOp& o, DsRing& rg, uint32
       } else {
         const uint4 wa = ds_lds128(st + woff0), wb = ds_lds128(st + woff1);
         const uint4 xv0 = ds_lds128(xpos), xv1 = ds_lds128(xpos + 16);
-        const float2 xsv = ds_lds64f(xsp);
+        const float4 xg = ds_lds128f(xsp);
+        float2 xsv;
+        xsv.x = todd ? xg.z : xg.x;
+        xsv.y = todd ? xg.w : xg.y;
         // scale / zero of this row pair for the slice's group (aux block behind the weights of the stage)
         const uint32_t ap = st + (gp128 == 1 ? aux0 : auxr + (uint32_t)(slice / gp128 - (ks * GS_KB * 2) / gp128) * 16 * AUXB);
         float s0, s1, z0, z1;
@@ -534,6 +544,8 @@ __device__ __forceinline__ void ds_linear_main(const DsOp& o, DsRing& rg, uint32
           const float2 a0 = ds_lds64f(ap), a1 = ds_lds64f(ap + 8 * AUXB);
           s0 = a0.x; z0 = a0.y; s1 = a1.x; z1 = a1.y;
         }
+        s0 *= xg.w;  // activation scale of this 128-column group (block fixed point per group, ds_stage_row)
+        s1 *= xg.w;
         // low nibbles (even columns) and high nibbles (odd columns, left in place: 16 q) go through separate IMMAs, so the
         // unpack is one LOP3 per operand register; 16 q d sums are exact multiples of 16 and rescaled in fp32.
         int cl[4] = {0, 0, 0, 0}, ch[4] = {0, 0, 0, 0};
@@ -611,7 +623,8 @@ __device__ __forceinline__ void ds_linear_main_i4pair(const DsOp& o, DsRing& rg,
   // sums), ^ 64 B (weights: chunk (4 + t) ^ (row & 7) under the 128-byte swizzle), + 16 AUXB (scales)
   const uint32_t woff = ds_pin((uint32_t)(kbl * GS_BLK_BYTES + pr0 * 128 + ((t ^ (pr0 & 7)) << 4)));
   const uint32_t xpos0 = ds_pin(xs_u32 + (uint32_t)(bcol * ldx + kbl * 256 + t * 32));
-  const uint32_t xsum0 = ds_pin(xsum_u32 + (uint32_t)(kbl * 8 + 2 * (t & 1)) * 4);
+  const uint32_t xsum0 = ds_pin(xsum_u32 + (uint32_t)(kbl * 8) * 4);
+  const bool todd = ds_pin(t & 1) != 0;
   const uint32_t aux0 = ds_pin((uint32_t)(GS_KB * GS_BLK_BYTES + (kbl * 32 + pr0) * AUXB));
   const uint32_t auxr = ds_pin((uint32_t)(GS_KB * GS_BLK_BYTES + pr0 * AUXB));
   const int slice0 = ds_pin(kbl * 2);
@@ -623,8 +636,11 @@ __device__ __forceinline__ void ds_linear_main_i4pair(const DsOp& o, DsRing& rg,
   if (rs >= nstages) { rs -= nstages; rph ^= 1; }
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
 
-  auto group = [&](uint32_t st, const uint4& wa, const uint4& wb, const uint4& xv0, const uint4& xv1, const float2& xsv, int slice,
+  auto group = [&](uint32_t st, const uint4& wa, const uint4& wb, const uint4& xv0, const uint4& xv1, const float4& xg, int slice,
                    int ks, uint32_t aux_first) {
+    float2 xsv;
+    xsv.x = todd ? xg.z : xg.x;
+    xsv.y = todd ? xg.w : xg.y;
     const uint32_t ap = st + (gp128 == 1 ? aux_first : auxr + (uint32_t)(slice / gp128 - (ks * GS_KB * 2) / gp128) * 16 * AUXB);
     float s0, s1, z0, z1;
     if (PACKED) {
@@ -637,6 +653,8 @@ __device__ __forceinline__ void ds_linear_main_i4pair(const DsOp& o, DsRing& rg,
       const float2 a0 = ds_lds64f(ap), a1 = ds_lds64f(ap + 8 * AUXB);
       s0 = a0.x; z0 = a0.y; s1 = a1.x; z1 = a1.y;
     }
+    s0 *= xg.w;
+    s1 *= xg.w;
     int cl[4] = {0, 0, 0, 0}, ch[4] = {0, 0, 0, 0};
     const uint32_t ML = 0x0F0F0F0Fu, MH = 0xF0F0F0F0u;
     gs_imma(cl, wa.x & ML, wb.x & ML, wa.y & ML, wb.y & ML, xv0.x, xv0.y);
@@ -665,13 +683,13 @@ __device__ __forceinline__ void ds_linear_main_i4pair(const DsOp& o, DsRing& rg,
         const uint4 wa1 = ds_lds128(st + (woff ^ 64u)), wb1 = ds_lds128(st + (woff ^ 64u) + 8 * 128);
         const uint4 xa0 = ds_lds128(xpos), xa1 = ds_lds128(xpos + 16);
         const uint4 xb0 = ds_lds128(xpos + 128), xb1 = ds_lds128(xpos + 144);
-        const float2 xs0 = ds_lds64f(xsp), xs1 = ds_lds64f(xsp + 16);
+        const float4 xs0 = ds_lds128f(xsp), xs1 = ds_lds128f(xsp + 16);
         group(st, wa0, wb0, xa0, xa1, xs0, slice, ks, aux0);
         group(st, wa1, wb1, xb0, xb1, xs1, slice + 1, ks, aux0 + 16 * AUXB);
       } else if (slice < nslices) {
         const uint4 wa0 = ds_lds128(st + woff), wb0 = ds_lds128(st + woff + 8 * 128);
         const uint4 xa0 = ds_lds128(xpos), xa1 = ds_lds128(xpos + 16);
-        const float2 xs0 = ds_lds64f(xsp);
+        const float4 xs0 = ds_lds128f(xsp);
         group(st, wa0, wb0, xa0, xa1, xs0, slice, ks, aux0);
       }
       __syncwarp();
@@ -758,32 +776,50 @@ __device__ __forceinline__ void ds_linear(const DsParams& p, const DsOp& o, cons
       const float inv = 1.0f / L;
       return make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
     };
-    ds_stage_row<2>(o, load_attn, wait_dep, s_stat, xs_u32, xsum, colscale, tr);  // H * hs <= 8192 (checked by lp_decode_step_plan)
+    ds_stage_row<2>(o, load_attn, wait_dep, s_stat, xs_u32, xsum, tr);  // H * hs <= 8192 (checked by lp_decode_step_plan)
   } else {
     const float* xg = o.x;
     auto load_plain = [&](int k) -> float4 { return ds_ldcg4(xg + k); };
-    if (small) ds_stage_row<2>(o, load_plain, wait_dep, s_stat, xs_u32, xsum, colscale, tr, xmode, xraw, xstat);
-    else if (o.K <= 4 * DS_CTHREADS * 8) ds_stage_row<4>(o, load_plain, wait_dep, s_stat, xs_u32, xsum, colscale, tr);
-    else ds_stage_row<6>(o, load_plain, wait_dep, s_stat, xs_u32, xsum, colscale, tr);  // e.g. falcon-7b mlp.proj, K = 18176
+    if (small) ds_stage_row<2>(o, load_plain, wait_dep, s_stat, xs_u32, xsum, tr, xmode, xraw, xstat);
+    else if (o.K <= 4 * DS_CTHREADS * 8) ds_stage_row<4>(o, load_plain, wait_dep, s_stat, xs_u32, xsum, tr);
+    else ds_stage_row<6>(o, load_plain, wait_dep, s_stat, xs_u32, xsum, tr);  // e.g. falcon-7b mlp.proj, K = 18176
   }
   gs_bar_consumers();
-  if (tr && threadIdx.x == 0) tr[2] = gs_now();
+  if (threadIdx.x == 0) {
+    // what the tile epilogue multiplies the accumulator columns with: digit weights (int4) x the scalar that was pulled out of the
+    // product (RMSNorm: rstd from the sum of squares the 16 warps left in s_stat).  Written before this warp's first tile arrival.
+    float post = 1.0f;
+    if (o.norm_kind == LP_NORM_RMS) {
+      float ss = 0.f;
+#pragma unroll
+      for (int w = 0; w < GS_CWARPS; ++w) ss += s_stat[2 * GS_CWARPS + w];
+      post = 1.0f / sqrtf(ss / (float)o.K + o.eps);
+    }
+    const bool i4 = o.fmt == LP_W_INT4;
+    colscale[0] = post;
+    colscale[1] = i4 ? 256.0f * post : post;
+    colscale[2] = i4 ? 65536.0f * post : post;
+    if (tr) tr[2] = gs_now();
+  }
   const uint32_t xsum_u32 = gs_smem_u32(xsum);
-  if (o.fmt == LP_W_BF16) ds_linear_main<LP_W_BF16, false>(o, rg, red_u32, colscale, xsum_u32, xs_u32, done, sb, se, gt);
+  if (o.fmt == LP_W_BF16) ds_linear_main<LP_W_BF16, false>(o, rg, red_u32, xsum_u32, xs_u32, done, sb, se, gt);
   else if (p.i4pair && o.aux_bytes == 4) ds_linear_main_i4pair<true>(o, rg, red_u32, xsum_u32, xs_u32, done, sb, se, gt, p.i4pair == 2);
   else if (p.i4pair) ds_linear_main_i4pair<false>(o, rg, red_u32, xsum_u32, xs_u32, done, sb, se, gt, p.i4pair == 2);
-  else if (o.aux_bytes == 4) ds_linear_main<LP_W_INT4, true>(o, rg, red_u32, colscale, xsum_u32, xs_u32, done, sb, se, gt);
-  else ds_linear_main<LP_W_INT4, false>(o, rg, red_u32, colscale, xsum_u32, xs_u32, done, sb, se, gt);
+  else if (o.aux_bytes == 4) ds_linear_main<LP_W_INT4, true>(o, rg, red_u32, xsum_u32, xs_u32, done, sb, se, gt);
+  else ds_linear_main<LP_W_INT4, false>(o, rg, red_u32, xsum_u32, xs_u32, done, sb, se, gt);
 }
 
 // Epilogue warp `e` finalises the tiles of parity e: cross-warp reduction of the 16 partial sums, digit / term recombination,
 // bias, activation, residual, store.  The consumers never stop for this: they drop their partials and stream on.
-__device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint32_t red_u32, const float* colscale, volatile int* done) {
+__device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint32_t red_u32, const float* colscale, volatile int* done,
+                                                 const DsOp* s_ops) {
   const int lane = threadIdx.x & 31;
   const int rr = lane & 15, half = lane >> 4;
   int gt = 0;
+  asm volatile("bar.sync 4, %0;\n" ::"n"(DS_OPEND_THREADS) : "memory");  // record of op 0 is in shared memory
   for (int op = 0; op < p.nops; ++op) {
-    const DsOp& o = p.ops[op];
+    const DsOp& o = s_ops[op % DS_NREC];
+    const int signal = o.signal;
     if (o.kind == DS_KIND_LINEAR) {
       const int nks = o.nks, fmt = o.fmt, split = o.split, epi = o.epi, streamk = o.streamk;
       const float* bias = o.bias;
@@ -822,6 +858,7 @@ __device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint3
           y = split == 3 ? c2 : 0.f;
           y += c1;
           y += c0;
+          y *= colscale[0];  // 1, or the RMSNorm scale pulled out of the product
         }
         const int row = tile * GS_ROWS + rr;
         if (bias && first) y += bias[row];
@@ -837,9 +874,12 @@ __device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint3
         }
       }
     }
-    // end of the op: this warp's rows are written (the consumers signal the op after this barrier).  bar.sync, not arrive:
-    // an epilogue warp must not run ahead into the next op's barrier phase.
+    // end of the op: this warp's rows are written.  bar.sync, not arrive: an epilogue warp must not run ahead into the next op's
+    // barrier phase.  One lane of epilogue warp 0 then publishes the op: release at gpu scope covers the rows written by ALL warps
+    // of this CTA (ordered before by the barrier).  The ~1 us of that fence is off the consumers' path: they are already staging
+    // the next op.
     asm volatile("bar.sync 4, %0;\n" ::"n"(DS_OPEND_THREADS) : "memory");
+    if (e == 0 && lane == 0 && signal) ds_red_release(p.counters + op);
   }
 }
 
@@ -1038,7 +1078,7 @@ __device__ __forceinline__ void ds_attention(const DsParams& p, const DsOp& o, c
 // CTA waits until all peers have published it, then reduces ITS slice of the row (n / #CTAs floats) over all ranks in rank order
 // — bit-identical on every rank — adds the residual and stores it locally.  The epoch counter is the one the per-op kernel uses,
 // so prefill (per-op path) and decode (this kernel) can alternate; it is advanced once per step by the last exchange of a slot.
-__device__ __forceinline__ void ds_exchange(const DsOp& o, unsigned int epoch0) {
+__device__ __forceinline__ void ds_exchange(const DsParams& p, const DsOp& o, int op, unsigned int epoch0) {
   const int tid = threadIdx.x, tp = o.tp_size;
   const unsigned int epoch = epoch0 + (unsigned)o.tp_use + 1u;
   if (tid < tp) {
@@ -1048,9 +1088,15 @@ __device__ __forceinline__ void ds_exchange(const DsOp& o, unsigned int epoch0) 
       asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(flag), "r"(epoch) : "memory");
     }
     const unsigned int* mine = reinterpret_cast<const unsigned int*>(o.tp_pads[o.tp_rank]) + o.tp_pad_base + tid;
-    unsigned int v;
+    unsigned int v, it = 0;
+    const unsigned long long t0 = gs_now();
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(mine) : "memory");
+      if ((int)(v - epoch) < 0 && p.timeout_ns) {  // a peer GPU that never publishes: watchdog (ds_report)
+        const bool expired = gs_now() - t0 > p.timeout_ns;
+        if (expired) ds_report(p.err, DS_ERR_EXCHANGE_TIMEOUT, op, tid, v);
+        if (expired || ((++it & 15u) == 0 && ds_ld_relaxed(p.err) != 0u)) break;
+      }
     } while ((int)(v - epoch) < 0);
   }
   gs_bar_consumers();
@@ -1092,7 +1138,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
   unsigned char* xs = reinterpret_cast<unsigned char*>(xsum + p.xsum_floats);  // activation columns; attention scratch
   __shared__ __align__(16) float s_stat[4 * GS_CWARPS];
   __shared__ float s_xstat[2];
-  __shared__ __align__(128) unsigned char s_ops[2 * sizeof(DsOp)];  // this op's and the next op's record (consumers)
+  __shared__ __align__(128) unsigned char s_ops[DS_NREC * sizeof(DsOp)];  // op records: previous / current / next (see fetch_op)
+  __shared__ int s_dep_ready;  // highest op index whose completion on ALL CTAs the watcher thread has observed
   float* xraw = reinterpret_cast<float*>(xs + p.xs_bytes);  // raw activation row kept for a reuse_x op (may be empty)
   const uint32_t red_u32 = gs_smem_u32(red), xs_u32 = gs_smem_u32(xs);
 
@@ -1111,13 +1158,51 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
       mbar_init(rg.bar0 + 8 * (p.nstages + s), GS_CWARPS);
     }
     done[0] = done[1] = 0;
+    s_dep_ready = -1;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
 
+  if (warp == GS_CWARPS + 1 + DS_EWARPS) {
+    if (lane != 0) return;
+    {
+      // =========================== WATCHER: polls the grid-wide dependencies on behalf of the consumers ==================
+      // One thread of a warp of its own (sharing the producer's warp starves both: divergent lanes of a warp do not overlap their
+      // stalls) walks the dependency list ahead of the consumers and polls the arrival
+      // counter of each new dependency (relaxed polls, one acquire), then publishes it in shared memory: the 512 consumer
+      // threads only ever spin on a shared-memory word, nobody leaves the critical path to poll L2, and the poll is already in
+      // flight while the consumers finish the previous op.  This is also where the watchdog lives (ds_report).
+      pdl_wait();  // the counters are zeroed by the prologue kernel of this step
+      int waited = -1;
+      bool dead = false;
+      for (int op = 0; op < p.nops; ++op) {
+        const int dep = __ldg(p.deps + op);
+        if (dep <= waited) continue;
+        if (!dead) {
+          const unsigned* ctr = p.counters + dep;
+          unsigned it = 0, seen;
+          const unsigned long long t0 = gs_now();
+          while ((seen = ds_ld_relaxed(ctr)) < gridDim.x) {
+            if (p.timeout_ns) {  // a timer read per poll is noise next to the poll's own L2 round trip
+              const bool expired = gs_now() - t0 > p.timeout_ns;
+              if (expired || ((++it & 15u) == 0 && ds_ld_relaxed(p.err) != 0u)) {
+                if (expired) ds_report(p.err, DS_ERR_DEP_TIMEOUT, op, dep, seen);
+                dead = true;
+                break;
+              }
+            }
+          }
+          (void)ds_ld_acquire(ctr);
+        }
+        waited = dep;
+        ds_sts_release(&s_dep_ready, dep);
+      }
+      return;
+    }
+  }
   if (warp > GS_CWARPS) {
     pdl_wait();
-    ds_epilogue_warp(p, warp - GS_CWARPS - 1, red_u32, colscale, done);
+    ds_epilogue_warp(p, warp - GS_CWARPS - 1, red_u32, colscale, done, reinterpret_cast<const DsOp*>(s_ops));
     return;
   }
   if (warp == GS_CWARPS) {
@@ -1212,6 +1297,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
           pdl_wait();  // the position is written by the previous step's sampler
           geo.init(p);
           have_geo = true;
+          // this position's RoPE rows are read by every attention op of the step and are cold in the first one: pull them into L2
+          if (blockIdx.x == 0 && p.n_elem > 0 && (p.n_elem & 3) == 0) {
+            ds_prefetch_l2(p.cosT + (size_t)geo.pos * p.n_elem, (uint32_t)p.n_elem * 4);
+            ds_prefetch_l2(p.sinT + (size_t)geo.pos * p.n_elem, (uint32_t)p.n_elem * 4);
+          }
         }
         constexpr int AT = DsAttnGeo<HS>::AT;
         const int npairs = p.H * p.P;
@@ -1248,47 +1338,35 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
   if (p.tp_state1) tp_epoch[1] = *reinterpret_cast<volatile unsigned int*>(p.tp_state1);
   int waited = -1, gt = 0;
   bool have_xraw = false;  // the previous op left the raw activation row + statistics in shared memory (save_x)
-  // LP_DS_OPREC=1 (off by default): op records are read from SHARED memory: every op otherwise starts with an L2 round trip (~0.7 us under streaming load) for its
-  // own 384-byte record before it could even look at its dependency.  24 lanes of warp 1 copy the NEXT op's record with cp.async
-  // while the current op runs; the op-end barrier publishes it.  (The producer and the epilogue warps keep reading the table
-  // in global memory: they run ahead of / beside the critical path, and the TMA descriptor must stay in global memory.)
+  // Op records live in SHARED memory (an op would otherwise begin with an L2 round trip, ~0.7 us under streaming load, for its
+  // own 384-byte record): 24 lanes of warp 1 copy the NEXT op's record with cp.async while the current op runs; the op-end
+  // barrier publishes it to the consumers and the epilogue warps.  Three slots: record k+1 replaces record k-2, which nobody can
+  // still be reading (everybody has passed the op-end barriers of k-2 and k-1).  The producer and the watcher read the table in
+  // global memory: they run ahead of the critical path, and the TMA descriptor must stay in global memory.
   const uint32_t s_ops_u32 = gs_smem_u32(s_ops);
   auto fetch_op = [&](int op) {
     if (warp == 1 && lane < (int)(sizeof(DsOp) / 16)) {
       const char* src = reinterpret_cast<const char*>(p.ops + op) + lane * 16;
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s_ops_u32 + (uint32_t)((op & 1) * sizeof(DsOp) + lane * 16)), "l"(src) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s_ops_u32 + (uint32_t)((op % DS_NREC) * sizeof(DsOp) + lane * 16)), "l"(src) : "memory");
       asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
   };
   auto fetch_wait = [&]() {
     if (warp == 1) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   };
-  const bool oprec = p.oprec != 0;  // CTA-uniform
-  if (oprec) {
-    fetch_op(0);
-    fetch_wait();
-    gs_bar_consumers();
-  }
+  if (p.nops > 0) fetch_op(0);
+  fetch_wait();
+  asm volatile("bar.sync 4, %0;\n" ::"n"(DS_OPEND_THREADS) : "memory");
   for (int op = 0; op < p.nops; ++op) {
-    const DsOp& o = oprec ? reinterpret_cast<const DsOp*>(s_ops)[op & 1] : p.ops[op];
-    if (oprec && op + 1 < p.nops) fetch_op(op + 1);
+    const DsOp& o = reinterpret_cast<const DsOp*>(s_ops)[op % DS_NREC];
+    if (op + 1 < p.nops) fetch_op(op + 1);
     unsigned long long* tr = p.trace ? p.trace + ((size_t)op * gridDim.x + blockIdx.x) * 8 : nullptr;
     if (tr && threadIdx.x == 0) tr[0] = gs_now();
     const int dep = o.dep;
-    const int signal = o.signal;  // read now: after the op-end barrier warp 1 may already overwrite this record with op + 2
-    // barriers are cumulative: a CTA arrives for op d only after all of its earlier ops
-    int skip = 0;
-    if (p.skip_dep) {
-      const int cls = o.kind != DS_KIND_LINEAR ? 1 : (o.x_attn ? 2 : (o.streamk ? 4 : 8));
-      skip = p.skip_dep & cls;
-    }
+    // counters are cumulative: a CTA arrives for op d only after all of its earlier ops
     auto wait_dep = [&]() {
-      if (dep > waited && !skip) {
-        if (threadIdx.x == 0) {  // cheap relaxed polls, one acquire at the end
-          while (ds_ld_relaxed(p.counters + dep) < gridDim.x) {}
-          (void)ds_ld_acquire(p.counters + dep);
-        }
-        gs_bar_consumers();
+      if (dep > waited) {
+        while (ds_lds_acquire(&s_dep_ready) < dep) {}
         waited = dep;
       }
       if (tr && threadIdx.x == 0) tr[1] = gs_now();
@@ -1297,18 +1375,15 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
       ds_linear<HS>(p, o, geo, rg, red_u32, colscale, xsum, xs_u32, done, s_stat, tr, gt, wait_dep, xraw, s_xstat, have_xraw);
     } else if (o.kind == DS_KIND_EXCHANGE) {
       wait_dep();
-      ds_exchange(o, o.tp_state == p.tp_state1 ? tp_epoch[1] : tp_epoch[0]);
+      ds_exchange(p, o, op, o.tp_state == p.tp_state1 ? tp_epoch[1] : tp_epoch[0]);
     } else {
       wait_dep();
       ds_attention<HS>(p, o, geo, rg, xs, tr);
     }
-    if (oprec) fetch_wait();  // the next op's record has landed (issued at the start of this op)
-    asm volatile("bar.sync 4, %0;\n" ::"n"(DS_OPEND_THREADS) : "memory");  // the epilogue warps have written this op's rows
-    if (threadIdx.x == 0) {
-      // release at gpu scope: covers the rows written by the other warps of this CTA (ordered before by the barrier above)
-      if (signal) ds_red_release(p.counters + op);
-      if (tr) tr[3] = gs_now();
-    }
+    fetch_wait();  // the next op's record has landed (issued at the start of this op)
+    // the epilogue warps have written this op's rows; one of their lanes signals the op after this barrier
+    asm volatile("bar.sync 4, %0;\n" ::"n"(DS_OPEND_THREADS) : "memory");
+    if (tr && threadIdx.x == 0) tr[3] = gs_now();
   }
 }
 
@@ -1330,7 +1405,10 @@ __global__ void decode_step_prep_kernel(const void* __restrict__ idx, int idx64,
 // ------------------------------------------------------------------------------------------------ host side
 struct DsHostPlan {  // lp_step_handle, opaque to the caller
   uint32_t magic;
-  int nops, nstages, stage_stride, xsum_floats, hs, H, G, P, n_elem, max_seq, E, wte_dtype, idx64, grid, i4pair, l2_ahead, skip_dep, xs_bytes, oprec;
+  int nops, nstages, stage_stride, xsum_floats, hs, H, G, P, n_elem, max_seq, E, wte_dtype, idx64, grid, i4pair, l2_ahead, xs_bytes, coop;
+  unsigned long long timeout_ns;
+  const int* deps;
+  unsigned* err;
   float scale_log2;
   size_t smem;
   const DsOp* ops_dev;
@@ -1351,22 +1429,82 @@ constexpr uint32_t DS_MAGIC = 0x4c504453u;
 
 static unsigned long long* g_ds_trace = nullptr;
 
+constexpr size_t DS_SMEM_OPTIN = 225 * 1024;  // 227 KB per CTA minus the static block (statistics, op records: < 2 KB)
+
+template <int HS>
+static int ds_prepare(int device) {  // per DEVICE: the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
+  static bool attr_set[64] = {};
+  if (device < 0 || device >= 64) return LP_ERR_INVALID_ARG;
+  if (!attr_set[device]) {
+    LP_CUDA_TRY(cudaFuncSetAttribute(decode_step_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DS_SMEM_OPTIN));
+    attr_set[device] = true;
+  }
+  return LP_OK;
+}
+
+// The step kernel spins on counters that OTHER CTAs of the same grid advance, so all CTAs must be resident at the same time.
+// (a) lp_decode_step_plan refuses a grid that the occupancy calculator says cannot be co-resident (1 CTA of 608 threads and
+// ~220 KB of shared memory per SM: grid <= #SMs); (b) the launch carries cudaLaunchAttributeCooperative, which makes the driver
+// guarantee co-residency (or fail the launch) whatever else is running on the device; (c) the watcher's waits are bounded
+// (ds_report).  LP_DS_COOP=0 drops (b) (A/B measurements only).
 template <int HS>
 static int ds_launch(const DsParams& p, const DsHostPlan& h, void* stream) {
-  static bool attr_set = false;
-  auto kern = decode_step_kernel<HS>;
-  if (!attr_set) {
-    LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024)));
-    attr_set = true;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(h.grid);
+  cfg.blockDim = dim3(DS_THREADS);
+  cfg.dynamicSmemBytes = h.smem;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
   }
-  return launch(kern, dim3(h.grid), dim3(DS_THREADS), h.smem, stream, p);
+  if (h.coop) {
+    attr[na].id = cudaLaunchAttributeCooperative;
+    attr[na].val.cooperative = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  LP_CUDA_TRY(cudaLaunchKernelEx(&cfg, decode_step_kernel<HS>, p));
+  count_launch();
+  return LP_OK;
+}
+
+// Can the device run this grid cooperatively together with the PDL attribute?  Probed once per device at plan time with an empty
+// op table (the kernel starts, finds nothing to do and exits).
+template <int HS>
+static int ds_probe_coop(const DsHostPlan& h, int device) {
+  static int mode[64];  // 0: unknown, 1: cooperative launch works, 2: it does not (plain launch + occupancy check + watchdog)
+  if (const char* e = getenv("LP_DS_COOP"))
+    if (e[0] == '0') return 0;
+  if (mode[device] == 0) {
+    DsParams p;
+    memset(&p, 0, sizeof(p));
+    p.pos = h.pos;
+    p.nstages = h.nstages;
+    p.stage_stride = h.stage_stride;
+    p.P = 1;
+    p.H = p.G = 1;
+    p.max_seq = 1;
+    DsHostPlan hp = h;
+    hp.coop = 1;
+    int rc = ds_launch<HS>(p, hp, nullptr);
+    cudaError_t e = rc == LP_OK ? cudaStreamSynchronize(nullptr) : cudaErrorUnknown;
+    (void)cudaGetLastError();
+    mode[device] = (rc == LP_OK && e == cudaSuccess) ? 1 : 2;
+  }
+  return mode[device] == 1;
 }
 
 }  // namespace lp
 
 extern "C" {
 
-size_t lp_decode_step_plan_bytes(int n_ops) { return n_ops > 0 ? (size_t)n_ops * sizeof(lp::DsOp) + (size_t)n_ops * 4 + 256 : 0; }
+/* op records | arrival counters [n] | dependency list [n] | error record [8] */
+size_t lp_decode_step_plan_bytes(int n_ops) { return n_ops > 0 ? (size_t)n_ops * sizeof(lp::DsOp) + (size_t)n_ops * 8 + 256 : 0; }
 
 size_t lp_decode_step_workspace_bytes(int H, int hs) { return (size_t)H * lp::DS_MAXP * (hs + 4) * 4; }
 
@@ -1531,7 +1669,7 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
     }
   }
   const size_t tail = 256 + (size_t)DS_RED_FLOATS * 4 + 32 + (size_t)xsum_floats * 4 + xs_bytes + xraw_bytes;
-  const size_t budget = 225 * 1024;  // 227 KB per CTA minus the static block (statistics, op records: < 2 KB)
+  const size_t budget = DS_SMEM_OPTIN;
   if (tail + 3 * (size_t)stage_stride + 1024 > budget) return LP_ERR_UNSUPPORTED;
   int ns = (int)((budget - tail - 1024) / stage_stride);
   if (ns > 14) ns = 14;
@@ -1557,10 +1695,12 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
     const char* e = getenv("LP_DS_L2AHEAD");
     h.l2_ahead = e ? atoi(e) : 0;
     if (h.l2_ahead < 0) h.l2_ahead = 0;
-    const char* sd = getenv("LP_DS_SKIPDEP");
-    h.skip_dep = sd ? atoi(sd) : 0;
-    const char* orc = getenv("LP_DS_OPREC");
-    h.oprec = (orc && orc[0] == '1') ? 1 : 0;
+    // bound of every cross-CTA / cross-GPU wait of the kernel (watchdog, ds_report); LP_DS_TIMEOUT_MS=0: unbounded (tools that
+    // slow the kernel down by orders of magnitude: compute-sanitizer)
+    const char* to = getenv("LP_DS_TIMEOUT_MS");
+    const long long ms = to ? atoll(to) : 4000;
+    h.timeout_ns = ms > 0 ? (unsigned long long)ms * 1000000ull : 0ull;
+    if (const char* ns_env = getenv("LP_DS_TIMEOUT_NS")) h.timeout_ns = (unsigned long long)atoll(ns_env);  // test aid: force expiry
   }
   h.i4pair = i4pair ? (pair_env && pair_env[0] == '2' ? 2 : 1) : 0;  // 2: timing experiment, arithmetic skipped
   h.stage_stride = stage_stride;
@@ -1580,6 +1720,8 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
   h.smem = (size_t)ns * stage_stride + tail + 1024;
   h.ops_dev = reinterpret_cast<const DsOp*>(plan_dev);
   h.counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(plan_dev) + (size_t)n_ops * sizeof(DsOp));
+  h.deps = reinterpret_cast<const int*>(h.counters + n_ops);
+  h.err = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(plan_dev) + ((size_t)n_ops * (sizeof(DsOp) + 8) + 15) / 16 * 16);
   h.pos = gm->pos;
   h.cosT = gm->cos;
   h.sinT = gm->sin;
@@ -1590,8 +1732,25 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
   h.x0 = gm->x0;
   h.tp_state0 = tp_state[0];
   h.tp_state1 = tp_state[1];
-  // load-time copy of the op table (synchronous: the staging vector dies at return)
+  // load-time copy of the op table, the dependency list and a clean error record (synchronous: the staging vectors die at return)
   LP_CUDA_TRY(cudaMemcpy(plan_dev, dev.data(), (size_t)n_ops * sizeof(DsOp), cudaMemcpyHostToDevice));
+  {
+    std::vector<int> deps(n_ops);
+    for (int i = 0; i < n_ops; ++i) deps[i] = dev[i].dep;
+    LP_CUDA_TRY(cudaMemcpy(const_cast<int*>(h.deps), deps.data(), (size_t)n_ops * sizeof(int), cudaMemcpyHostToDevice));
+    LP_CUDA_TRY(cudaMemset(h.err, 0, 32));
+  }
+  // co-residency of the whole grid: occupancy check here, cooperative launch attribute where the device accepts it (ds_launch)
+  {
+    int device = 0, per_sm = 0;
+    LP_CUDA_TRY(cudaGetDevice(&device));
+    const int rc = gm->hs == 128 ? ds_prepare<128>(device) : ds_prepare<64>(device);
+    if (rc != LP_OK) return rc;
+    if (gm->hs == 128) LP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_step_kernel<128>, DS_THREADS, h.smem));
+    else LP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_step_kernel<64>, DS_THREADS, h.smem));
+    if (per_sm < 1 || h.grid > per_sm * num_sms()) return LP_ERR_UNSUPPORTED;
+    h.coop = gm->hs == 128 ? ds_probe_coop<128>(h, device) : ds_probe_coop<64>(h, device);
+  }
   memset(handle, 0, sizeof(*handle));
   memcpy(handle, &h, sizeof(h));
   return LP_OK;
@@ -1626,12 +1785,35 @@ int lp_decode_step(const lp_step_handle* handle, void* stream) {
   p.xsum_floats = h.xsum_floats;
   p.i4pair = h.i4pair;
   p.l2_ahead = h.l2_ahead;
-  p.skip_dep = h.skip_dep;
   p.xs_bytes = h.xs_bytes;
-  p.oprec = h.oprec;
+  p.deps = h.deps;
+  p.err = h.err;
+  p.timeout_ns = h.timeout_ns;
   p.tp_state0 = h.tp_state0;
   p.tp_state1 = h.tp_state1;
   return h.hs == 128 ? ds_launch<128>(p, h, stream) : ds_launch<64>(p, h, stream);
+}
+
+int lp_decode_step_status(const lp_step_handle* handle, int32_t info[8]) {
+  using namespace lp;
+  if (!handle) return LP_ERR_INVALID_ARG;
+  DsHostPlan h;
+  memcpy(&h, handle, sizeof(h));
+  if (h.magic != DS_MAGIC) return LP_ERR_INVALID_ARG;
+  unsigned rec[8] = {};
+  LP_CUDA_TRY(cudaMemcpy(rec, h.err, sizeof(rec), cudaMemcpyDeviceToHost));  // synchronises with the steps launched so far
+  if (info) memcpy(info, rec, sizeof(rec));
+  if (rec[0] == 0) return LP_OK;
+  LP_CUDA_TRY(cudaMemset(h.err, 0, sizeof(rec)));  // reported once; the plan stays usable
+  return LP_ERR_TIMEOUT;
+}
+
+int lp_decode_step_cooperative(const lp_step_handle* handle) {
+  using namespace lp;
+  if (!handle) return LP_ERR_INVALID_ARG;
+  DsHostPlan h;
+  memcpy(&h, handle, sizeof(h));
+  return h.magic == DS_MAGIC ? h.coop : LP_ERR_INVALID_ARG;
 }
 
 }  // extern "C"

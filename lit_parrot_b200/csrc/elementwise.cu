@@ -140,9 +140,43 @@ __global__ void repack_int4_kernel(const uint8_t* __restrict__ src, uint8_t* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// range check of token ids and positions on the device (nn.Embedding / index_select raise in the reference, model.py:88-99)
+// ---------------------------------------------------------------------------------------------
+__global__ void validate_inputs_kernel(void* idx, int idx64, int n_idx, int vocab, int* pos, int n_pos, int block_size, int* flag) {
+  int bad = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_idx; i += gridDim.x * blockDim.x) {
+    if (idx64) {
+      long long& t = reinterpret_cast<long long*>(idx)[i];
+      if (t < 0 || t >= vocab) { bad |= 1; t = t < 0 ? 0 : vocab - 1; }
+    } else {
+      int& t = reinterpret_cast<int*>(idx)[i];
+      if (t < 0 || t >= vocab) { bad |= 1; t = t < 0 ? 0 : vocab - 1; }
+    }
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pos; i += gridDim.x * blockDim.x) {
+    int& q = pos[i];
+    if (q < 0 || q >= block_size) { bad |= 2; q = q < 0 ? 0 : block_size - 1; }
+  }
+  if (bad) atomicOr(flag, bad);
+}
+
 }  // namespace lp
 
 extern "C" {
+
+int lp_validate_inputs(void* idx, int idx_is_int64, int n_idx, int vocab, int32_t* pos, int n_pos, int block_size, int32_t* flag,
+                       void* stream) {
+  if (!flag || vocab <= 0 || block_size <= 0 || n_idx < 0 || n_pos < 0 || (n_idx && !idx) || (n_pos && !pos)) return LP_ERR_INVALID_ARG;
+  const int n = n_idx > n_pos ? n_idx : n_pos;
+  if (n == 0) return LP_OK;
+  const int grid = (n + 255) / 256 < 64 ? (n + 255) / 256 : 64;
+  lp::validate_inputs_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(idx, idx_is_int64, n_idx, vocab, pos, n_pos,
+                                                                                       block_size, flag);
+  LP_CUDA_TRY(cudaGetLastError());
+  lp::count_launch();
+  return LP_OK;
+}
 
 int lp_embed(const void* idx, int idx_is_int64, const int32_t* idx_offset, const void* wte, int wte_dtype, float* out, int rows,
              int E, int round_bf16, void* stream) {

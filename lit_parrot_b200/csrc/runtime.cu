@@ -58,6 +58,7 @@ const char* lp_status_str(int s) {
     case LP_ERR_UNSUPPORTED: return "LP_ERR_UNSUPPORTED";
     case LP_ERR_CUDA: return "LP_ERR_CUDA";
     case LP_ERR_WORKSPACE: return "LP_ERR_WORKSPACE";
+    case LP_ERR_TIMEOUT: return "LP_ERR_TIMEOUT";
     default: return "LP_ERR_UNKNOWN";
   }
 }

@@ -43,7 +43,7 @@ __device__ __forceinline__ Best better(Best a, Best b) {
 
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 sample_kernel(const float* __restrict__ logits, int V, float temperature, int top_k, uint64_t seed, int* __restrict__ step,
-              int* __restrict__ token_out, int* __restrict__ seq_buf, int* __restrict__ pos_inout) {
+              int* __restrict__ token_out, int* __restrict__ seq_buf, int* __restrict__ pos_inout, unsigned int* __restrict__ ticket) {
   __shared__ unsigned int hist[256];
   __shared__ unsigned int s_prefix, s_krem;
   __shared__ Best s_best[SAMPLE_THREADS / 32];
@@ -120,7 +120,12 @@ sample_kernel(const float* __restrict__ logits, int V, float temperature, int to
         if (seq_buf) seq_buf[p + 1] = best.i;
         *pos_inout = p + 1;
       }
-      if (step && gridDim.x == 1) *step = st + 1;  // multi-row callers advance the Philox step themselves
+      // the Philox step advances once per launch.  Every row read `st` before it took its ticket, so the LAST row to finish may
+      // publish st + 1 without racing a slower row of this launch (a replayed batched step never reuses a noise key).
+      if (step && (gridDim.x == 1 || atomicAdd(ticket, 1u) == gridDim.x - 1)) {
+        if (gridDim.x > 1) *ticket = 0;
+        *step = st + 1;
+      }
     }
   }
 }
@@ -140,8 +145,8 @@ static unsigned int* g_greedy_ticket = nullptr;  // [GREEDY_MAX_ROWS]
 int init_sample() {
   if (g_greedy_part) return LP_OK;
   LP_CUDA_TRY(cudaMalloc(&g_greedy_part, sizeof(Best) * GREEDY_MAX_ROWS * GREEDY_CTAS));
-  LP_CUDA_TRY(cudaMalloc(&g_greedy_ticket, sizeof(unsigned int) * GREEDY_MAX_ROWS));
-  LP_CUDA_TRY(cudaMemset(g_greedy_ticket, 0, sizeof(unsigned int) * GREEDY_MAX_ROWS));
+  LP_CUDA_TRY(cudaMalloc(&g_greedy_ticket, sizeof(unsigned int) * (GREEDY_MAX_ROWS + 1)));  // + 1: sample_kernel's row ticket
+  LP_CUDA_TRY(cudaMemset(g_greedy_ticket, 0, sizeof(unsigned int) * (GREEDY_MAX_ROWS + 1)));
   return LP_OK;
 }
 
@@ -190,7 +195,7 @@ greedy_kernel(const float* __restrict__ logits, int V, float temperature, int* _
       if (seq_buf) seq_buf[p + 1] = b.i;
       *pos_inout = p + 1;
     }
-    if (step && gridDim.y == 1) *step = *step + 1;
+    if (step && row == 0) *step = *step + 1;  // nobody reads the step in the greedy kernel: row 0 advances it for any row count
   }
 }
 
@@ -200,9 +205,10 @@ extern "C" int lp_sample(const float* logits, int rows, int V, float temperature
                          int32_t* token_out, int32_t* seq_buf, int32_t* pos_inout, void* stream) {
   if (!logits || !token_out || rows <= 0 || V <= 0 || !(temperature > 0.f) || top_k < 0) return LP_ERR_INVALID_ARG;
   if (seq_buf && (rows != 1 || !pos_inout)) return LP_ERR_INVALID_ARG;  // pos_inout alone (any rows): just advance
+  if (rows > 1 && step && !lp::g_greedy_ticket) return LP_ERR_INVALID_ARG;  // lp_init() allocates the row ticket
   if (top_k == 1 && rows <= lp::GREEDY_MAX_ROWS && lp::g_greedy_part)
     return lp::launch(lp::greedy_kernel, dim3(lp::GREEDY_CTAS, rows), dim3(lp::GREEDY_THREADS), 0, stream, logits, V, temperature, step,
                       token_out, seq_buf, pos_inout, lp::g_greedy_part, lp::g_greedy_ticket);
   return lp::launch(lp::sample_kernel, dim3(rows), dim3(lp::SAMPLE_THREADS), 0, stream, logits, V, temperature, top_k, seed, step,
-                    token_out, seq_buf, pos_inout);
+                    token_out, seq_buf, pos_inout, lp::g_greedy_ticket ? lp::g_greedy_ticket + lp::GREEDY_MAX_ROWS : nullptr);
 }

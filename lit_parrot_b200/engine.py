@@ -135,6 +135,7 @@ class Engine:
         # batch-1 decode: the whole step as one persistent kernel (lp_decode_step) where the library covers the model
         self.use_step_kernel = os.environ.get("LP_DECODE_STEP", "1") != "0" and bool(getattr(model, "use_step_kernel", True))
         self._steps: Dict[Tuple, Optional[Tuple]] = {}
+        self._flag = torch.zeros(1, dtype=torch.int32).pin_memory()  # mapped host word written by lp_validate_inputs
 
     # ------------------------------------------------------------------ bookkeeping
     def set_rope(self, rope) -> None:
@@ -248,6 +249,34 @@ class Engine:
         self._steps[key] = (handle, plan, ws, arr, n)
         return handle
 
+    def _raise_if_flagged(self) -> None:
+        f = int(self._flag[0])
+        if f:
+            self._flag.zero_()
+            what = " and ".join(w for bit, w in ((1, "a token id outside the embedding table"), (2, "a position outside the RoPE table"))
+                                if f & bit)
+            raise IndexError(f"an earlier decode step was given {what} (the value was clamped on the device; the reference raises)")
+
+    def check_step_health(self) -> None:
+        """Synchronous: raise if the watchdog of the persistent step kernel fired in any step launched so far (a dependency
+        counter or a tensor-parallel peer flag that never arrived, lp_decode_step_status).  generate() calls it once per call."""
+        torch.cuda.synchronize(self.device)
+        self._raise_if_flagged()
+        info = (ctypes.c_int32 * 8)()
+        first = None
+        for ent in self._steps.values():  # every plan is read (and its record cleared) before anything is raised
+            if ent is None:
+                continue
+            rc = self.lib.lp_decode_step_status(ctypes.byref(ent[0]), info)
+            if rc != 0 and first is None:
+                first = (rc, list(info))
+        if first is not None:
+            rc, info = first
+            what = {1: "dependency counter", 2: "tensor-parallel peer flag"}.get(info[0], f"code {info[0]}")
+            raise RuntimeError(f"liblitparrot_b200: lp_decode_step timed out ({self.lib.lp_status_str(rc).decode()}): {what} of op "
+                               f"{info[1]} (dep / peer {info[2]}) never arrived in CTA {info[3]} (value seen {info[4]}); the "
+                               "results of that step are invalid")
+
     def scratch_cache(self, B: int, T: int):
         key = (B, T)
         if self._scratch is None or self._scratch[0] != key:
@@ -289,7 +318,7 @@ class Engine:
         return self._wscratch.data_ptr()
 
     def buffers(self, rows: int, B: int, T: int, max_seq: int) -> Dict[str, torch.Tensor]:
-        key = (rows, max_seq)
+        key = (B, T, max_seq)  # the attention workspace is sized from (B, T), not from rows alone
         b = self._bufs.get(key)
         if b is None:
             cfg, dev = self.cfg, self.device
@@ -521,8 +550,16 @@ class Engine:
         pos32 = pos.to(device=self.device, dtype=torch.int32).contiguous()
         stream = torch.cuda.current_stream(self.device).cuda_stream
         self._consecutive = False
-        if T > 1:  # one host read per prefill: are the positions p, p+1, ... without wrapping the cache?
-            ph = pos32.cpu()
+        # one host read per call on this (not replayed) path: the reference raises on token ids outside the embedding table
+        # (nn.Embedding, model.py:99) and on positions outside the RoPE table (index_select, model.py:88-92); the kernels index
+        # with both.  Are the positions p, p+1, ... without wrapping the cache?
+        lim = torch.stack((idx.min(), idx.max())).tolist()
+        ph = pos32.cpu()
+        if lim[0] < 0 or lim[1] >= V:
+            raise IndexError(f"token id out of range: ids span [{int(lim[0])}, {int(lim[1])}], the embedding has {V} rows")
+        if int(ph.min()) < 0 or int(ph.max()) >= cfg.block_size:
+            raise IndexError(f"input_pos out of range: positions span [{int(ph.min())}, {int(ph.max())}], block_size is {cfg.block_size}")
+        if T > 1:
             self._consecutive = bool((ph[1:] - ph[:-1] == 1).all()) and int(ph[-1]) < max_seq
         self._run(b, idx.data_ptr(), int(idx.dtype == torch.int64), None, pos32.data_ptr(), caches, B, T, stream, last_only)
         out = b["logits"][:B].view(B, 1, V) if (last_only and T > 1) else b["logits"].view(B, T, V)
@@ -601,8 +638,13 @@ class Engine:
             g = (graph, b, s_idx, s_pos)
             self._graphs[key] = g
         graph, b, s_idx, s_pos = g
+        self._raise_if_flagged()  # an out-of-range id / position of an EARLIER replay (seen without a sync: mapped host flag)
         s_idx.copy_(idx.reshape(-1))
         s_pos.copy_(pos.reshape(-1))
+        # replayed path, inputs stay on the device: range check + clamp there (lp_validate_inputs), reported at the next call
+        _lib.check(self.lib.lp_validate_inputs(s_idx.data_ptr(), 1, B, V, s_pos.data_ptr(), 1, self.cfg.block_size,
+                                               self._flag.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream),
+                   "lp_validate_inputs")
         if graph is None:
             self._run(b, s_idx.data_ptr(), 1, None, s_pos.data_ptr(), caches, B, 1, torch.cuda.current_stream(self.device).cuda_stream)
         else:

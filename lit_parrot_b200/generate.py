@@ -110,7 +110,9 @@ def _generate_on_device(model, idx, max_returned_tokens, max_seq_length, tempera
         if hit.numel():
             cut = T + int(hit[0])
     out = seq[:max_returned_tokens] if cut is None else seq[:cut]
-    return out.to(idx.dtype, copy=True)
+    out = out.to(idx.dtype, copy=True)
+    eng.check_step_health()  # synchronises; raises if the step kernel's watchdog fired (never a silent wrong answer)
+    return out
 
 
 def _generate_foreign(model, idx, max_returned_tokens, max_seq_length, temperature, top_k, eos_id) -> torch.Tensor:

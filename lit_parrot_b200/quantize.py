@@ -214,7 +214,8 @@ class Linear4bit(torch.nn.Linear):
         if in_features % blocksize:
             raise NotImplementedError(f"in_features must be a multiple of the NF4 block size {blocksize}")
         self.blocksize = blocksize
-        self.absmax: Optional[torch.Tensor] = None
+        # a buffer (None until the first forward quantises the weight): it then travels with .to() and state_dict()
+        self.register_buffer("absmax", None)
 
     def forward(self, inp):  # pragma: no cover
         raise NotImplementedError("driven by GPT.forward through lp_linear")
@@ -251,7 +252,7 @@ class InferenceLinear8bitLt(torch.nn.Linear):
 
     def __init__(self, in_features: int, out_features: int, bias: bool = True, device=None, dtype=None, **_unused) -> None:
         super().__init__(in_features, out_features, bias, device=device, dtype=dtype)
-        self.SCB: Optional[torch.Tensor] = None
+        self.register_buffer("SCB", None)  # row scales; a buffer so that it travels with .to() and state_dict()
 
     def forward(self, inp):  # pragma: no cover
         raise NotImplementedError("driven by GPT.forward through lp_linear")

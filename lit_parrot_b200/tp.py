@@ -73,3 +73,25 @@ class TPContext:
         self.slot ^= 1
         self.count += 1
         return s, self.buf.data_ptr() + s * self.slot_floats * 4
+
+
+class LoopbackTPContext:
+    """One-rank stand-in for ``TPContext`` (single process, no ``torch.distributed``): the only 'peer' is this GPU's own
+    buffer, so an exchange adds ONE partial to the residual.  It lets a tensor-parallel SHARD (``Config.with_tp``) run alone —
+    the parity tests of the tp-local kernel shapes on one GPU use it; it is not a way to run a sharded model."""
+
+    def __init__(self, device: torch.device, max_rows: int, n_embd: int) -> None:
+        self.group = None
+        self.rank, self.size = 0, 1
+        self.slot_floats = max_rows * n_embd
+        self.buf = torch.zeros(2 * self.slot_floats, dtype=torch.float32, device=device)
+        self.pad = torch.zeros(64, dtype=torch.int32, device=device)
+        self._ptrs = torch.tensor([self.buf.data_ptr(), self.pad.data_ptr()], dtype=torch.int64, device=device)
+        self.buf_ptrs = self._ptrs.data_ptr()
+        self.pad_ptrs = self._ptrs.data_ptr() + 8
+        self.state = torch.zeros(2, 2, dtype=torch.int32, device=device)
+        self.slot = 0
+        self.count = 0
+
+    begin_forward = TPContext.begin_forward
+    next_slot = TPContext.next_slot

@@ -23,6 +23,11 @@ def quantization(mode: Optional[str] = None, *, gptq_tile_cols: int = -1):
         return
     if mode not in _MODES:
         raise ValueError(f"Unknown quantization mode: {mode}")
+    if "fp4" in mode or mode.endswith("-dq"):
+        # accepted by the reference (bitsandbytes arithmetic that is not restated here, DESIGN.md "out of scope"): refuse at mode
+        # selection, not in the middle of GPT construction
+        raise NotImplementedError(f"quantization mode {mode!r}: bitsandbytes FP4 and double quantisation (-dq) have no B200 kernel; "
+                                  "use 'bnb.nf4', 'bnb.int8' or 'gptq.int4'")
     from lit_parrot_b200 import quantize as q
 
     if mode == "bnb.int8":

@@ -175,7 +175,9 @@ def test_real_width_llama7b_two_layers_step_kernel():
         b = m2._forward_impl(want[i].view(1, 1).to(DEV), 348, p, raw_logits=True)[0, -1].float().cpu()
         ref = logits[i - 299]
         assert (a - ref).abs().max() < 2e-2 and cosine(a, ref) > 0.999
-        torch.testing.assert_close(a, b, rtol=0, atol=1e-4)
+        # two summation orders of the same fp32 arithmetic (the step kernel applies the RMSNorm scale after the product, the
+        # per-op path before it): observed 1.8e-4 on logits of magnitude ~1; both are 100x inside the north-star tolerance above
+        torch.testing.assert_close(a, b, rtol=0, atol=4e-4)
     assert not step_kernel_used(m2)
 
 
@@ -246,3 +248,49 @@ def test_step_kernel_exchange_op_self():
         torch.cuda.synchronize()
         torch.testing.assert_close(tmp, buf[:E])
     assert state[0, 0].item() == 6 and state[1, 0].item() == 3  # slot 0: 3 in-kernel + 3 per-op exchanges; slot 1: 3
+
+
+def test_step_kernel_watchdog_reports_instead_of_hanging(monkeypatch):
+    """A bound of 50 ns on the cross-CTA waits expires in every real step: the kernel must still run to its end (no hang), the
+    sticky error record must say which dependency was seen late, and the host must get LP_ERR_TIMEOUT -> RuntimeError; with the
+    default bound the same model then decodes correctly again."""
+    import ctypes
+
+    monkeypatch.setenv("LP_DS_TIMEOUT_NS", "50")
+    cfg, m, om = bf16_model(LLAMA, 63)
+    toks = torch.randint(0, cfg.padded_vocab_size, (24,), generator=torch.Generator().manual_seed(3))
+    m._forward_impl(toks[:16].view(1, -1).to(DEV), 64, torch.arange(16, device=DEV), raw_logits=True)
+    for i in range(16, 20):
+        m._forward_impl(toks[i].view(1, 1).to(DEV), 64, torch.tensor([i], device=DEV), raw_logits=True)
+    torch.cuda.synchronize()
+    assert step_kernel_used(m)
+    eng = m._engine
+    with pytest.raises(RuntimeError, match="timed out"):
+        eng.check_step_health()
+    eng.check_step_health()  # reported once, record cleared
+    ent = next(v for v in eng._steps.values() if v is not None)
+    assert eng.lib.lp_decode_step_cooperative(ctypes.byref(ent[0])) in (0, 1)
+    monkeypatch.delenv("LP_DS_TIMEOUT_NS")
+    cfg, m, om = bf16_model(LLAMA, 63)
+    teacher_forced(m, om, cfg, prompt_len=20, steps=12, max_seq=64)
+    m._engine.check_step_health()
+
+
+def test_out_of_range_inputs_raise_like_the_reference():
+    """Token ids outside the embedding table and positions outside the RoPE table: IndexError on the host-validated paths; on the
+    replayed decode graph the device clamps (no out-of-bounds access) and the next call / the health check raises."""
+    cfg, m, _ = bf16_model(LLAMA, 64)
+    V, bs = cfg.padded_vocab_size, cfg.block_size
+    good = torch.randint(0, V, (1, 8)).to(DEV)
+    with pytest.raises(IndexError):
+        m(torch.full((1, 8), V, device=DEV), 64, torch.arange(8, device=DEV))
+    with pytest.raises(IndexError):
+        m(good, 64, torch.arange(bs - 4, bs + 4, device=DEV))
+    m(good, 64, torch.arange(8, device=DEV))
+    m(good[:, :1], 64, torch.tensor([8], device=DEV))            # replayed path, valid
+    m(torch.full((1, 1), -3, device=DEV), 64, torch.tensor([9], device=DEV))   # clamped on the device, flagged
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError, match="token id"):
+        m(good[:, :1], 64, torch.tensor([10], device=DEV))
+    m(good[:, :1], 64, torch.tensor([10], device=DEV))
+    m._engine.check_step_health()

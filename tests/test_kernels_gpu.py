@@ -350,12 +350,34 @@ def test_sample_greedy_and_topk(lib):
     for i in range(300):
         _lib.check(lib.lp_sample(lg.data_ptr(), 1, V, 2.0, k, 99, step.data_ptr(), one.data_ptr(), None, None, stream()))
         seen.add(int(one))
-    assert seen <= allowed and len(seen) == k + 1 and int(step) == 300
+    assert seen <= allowed and len(seen) == k + 1 and int(step) == 301  # the 2-row greedy launch above advanced it too
     # device-side append used by the captured decode step
     seq = torch.zeros(8, dtype=torch.int32, device=DEV)
     pos = torch.tensor([2], dtype=torch.int32, device=DEV)
     _lib.check(lib.lp_sample(lg.data_ptr(), 1, V, 1.0, 1, 0, step.data_ptr(), one.data_ptr(), seq.data_ptr(), pos.data_ptr(), stream()))
     assert int(pos) == 3 and int(seq[3]) == int(lg[0].argmax()) == int(one)
+
+
+def test_sample_batched_step_advances(lib):
+    """Multi-row launches advance the Philox step once per launch (the noise is keyed by (index, step, row)): replaying the same
+    launch on the same logits must draw fresh noise every time, and a rewound step must reproduce the earlier draw."""
+    V, rows = 4096, 8
+    lg = torch.zeros(rows, V, device=DEV)  # uniform: the draw is the arg-max of the noise alone
+    tok = torch.zeros(rows, dtype=torch.int32, device=DEV)
+    step = torch.tensor([5], dtype=torch.int32, device=DEV)
+    draws = []
+    for i in range(6):
+        _lib.check(lib.lp_sample(lg.data_ptr(), rows, V, 1.0, 0, 42, step.data_ptr(), tok.data_ptr(), None, None, stream()))
+        draws.append(tok.cpu().clone())
+        assert int(step) == 6 + i
+    assert all(not torch.equal(draws[i], draws[i + 1]) for i in range(5))
+    assert len({tuple(d.tolist()) for d in draws}) == 6
+    step.fill_(7)  # the third launch again
+    _lib.check(lib.lp_sample(lg.data_ptr(), rows, V, 1.0, 0, 42, step.data_ptr(), tok.data_ptr(), None, None, stream()))
+    assert torch.equal(tok.cpu(), draws[2])
+    # greedy rows advance the step as well (it keys nothing there, but the counter stays in step with the launches)
+    _lib.check(lib.lp_sample(lg.data_ptr(), rows, V, 1.0, 1, 42, step.data_ptr(), tok.data_ptr(), None, None, stream()))
+    assert int(step) == 9
 
 
 def test_sample_distribution(lib):
