@@ -128,7 +128,9 @@ def build_model(workload: str, device):
     for name, mod in qmods.items():
         src = dmods[name]
         if hasattr(mod, "quantize_rtn_"):
-            mod.quantize_rtn_(src.weight.data.float())
+            # GPTQ: scales live in the model dtype like the reference's buffers under bf16-true (quantize/gptq.py:223-226); the
+            # weights are quantised against the rounded scales.  0.5 + 4/128 bytes per weight.
+            mod.quantize_rtn_(src.weight.data.float(), **({"scale_dtype": torch.bfloat16} if quant == "gptq.int4" else {}))
             src.weight.data = torch.empty(0, device=device)
         elif isinstance(mod, (torch.nn.Linear, torch.nn.Embedding)) or type(mod).__name__ in ("RMSNorm", "LayerNorm"):
             for pn, p in mod.named_parameters(recurse=False):
@@ -159,7 +161,7 @@ def build_tp_model(preset, device, rank, world):
     gen = torch.Generator(device=device)
     for i, (name, p) in enumerate(model.named_parameters()):
         if p.dim() == 2:
-            gen.manual_seed(1234 + i)  # same seed per tensor on every rank; shards differ only through their rank offset
+            # one seed per tensor: replicated tensors agree on every rank, sharded ones differ through the rank offset
             gen.manual_seed(1234 + i * 64 + (rank if (".attn." in name or ".mlp." in name) else 0))
             p.data.normal_(0.0, 0.02, generator=gen)
         elif name.endswith("weight"):
@@ -239,12 +241,23 @@ def run_workload(workload, steps, warmup, device, rank=0, world=1, with_e2e=True
         tms = torch.tensor([ms], device=device)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms)
+    eng.check_step_health()  # the step kernel's watchdog must not have fired in any timed step
+    tokens_agree = None
+    if tp and world > 1:
+        # every rank decoded the SAME greedy tokens (replicated lm_head over bit-identical all-reduced rows)
+        mine = st["seq"][start + 1:start + 1 + warmup + steps].clone()
+        allt = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allt, mine)
+        tokens_agree = all(bool(torch.equal(allt[0], t)) for t in allt)
+        assert tokens_agree, "tensor-parallel ranks decoded different tokens"
     kv_b = model.kv_caches[0][0].element_size()
     wbytes, kvbytes = algorithmic_bytes_per_step(eng, cfg, B, start + warmup + steps / 2 + 1, kv_b)
     replicas = 1 if tp else world  # tensor parallel: ONE model over all ranks (strong scaling); else independent replicas
     res = {"workload": workload, "ms_per_step": ms / steps, "tok_s": replicas * B * steps / (ms / 1e3),
            "launches_per_step": int(launches_per_step), "bytes_per_step": {"weights": int(wbytes), "kv": int(kvbytes)},
            "step_gbs": (wbytes + kvbytes) / (ms / steps) / 1e6, "clocks": clk.summary(), "B": B, "ctx": ctx}
+    if tokens_agree is not None:
+        res["tokens_agree"] = tokens_agree
 
     # ---- e2e: public API driven from the host; H2D token ids + D2H sampled ids every step -----------------------
     if with_e2e:
@@ -341,6 +354,38 @@ def run_prefill(preset, T, device, reps=3):
             "tflops": tf, "tensor_frac_of_sustained_peak": tf / peak, "flops": flops}
 
 
+def run_config0(device):
+    """BASELINE configs[0]: pythia-70m random init, greedy generate() of 128 tokens from a 16-token prompt.  The reference runs it
+    as-is on the host cores (fp32, baseline/_ref); beside it the same call through this repo's generate() on the GPU (bf16 weights,
+    fp32 activations; token parity of this configuration is pinned by tests/test_model_gpu.py against the reference's golden ids)."""
+    import torch
+
+    import lit_parrot_b200 as lp
+
+    ref = ref_run(["cpu-generate", "--preset", "pythia-70m", "--prompt", "16", "--tokens", "128", "--reps", "3"])
+    cfg = lp.Config.from_name("pythia-70m")
+    torch.manual_seed(1234)
+    with torch.device(device):
+        model = lp.GPT(cfg)
+    model.apply(model._init_weights)
+    model = model.to(torch.bfloat16).eval()
+    prompt = torch.randint(0, cfg.vocab_size, (16,), generator=torch.Generator().manual_seed(1)).to(torch.int32).to(device)
+    times = []
+    for i in range(4):
+        model.reset_cache()
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        out = lp.generate(model, prompt, 128, 128, temperature=1.0, top_k=1)
+        torch.cuda.synchronize(device)
+        if i:
+            times.append(time.perf_counter() - t0)
+    del model
+    torch.cuda.empty_cache()
+    return {"workload": "pythia-70m random init, greedy generate() 16 -> 128 tokens (BASELINE configs[0])", "reference_cpu": ref,
+            "ours_gpu": {"tok_s": 112 / min(times), "seconds": min(times), "new_tokens": 112, "tokens_head": out[:24].tolist(),
+                         "what": "lit_parrot_b200.generate on cuda:0, bf16 weights, wall clock incl. the 16-token prefill, best of 3"}}
+
+
 def time_step_kernel(eng, model, cfg, device, kv_elem_bytes, iters=64):
     """Batch-1 decode: the dominant kernel is the persistent step kernel (lp_decode_step = prologue + decode_step_kernel, one
     launch pair per token).  Timed alone with CUDA events on the launching stream, position fixed at the last one reached by the
@@ -411,6 +456,41 @@ def time_dominant_kernel(eng, cfg, B, device, iters=64):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def ref_available():
+    return os.path.isdir(os.path.join(REPO, "baseline", "_ref", "lit_gpt"))
+
+
+def ref_run(argv, timeout=600):
+    """The UNMODIFIED reference (baseline/_ref) in a subprocess (baseline/ref_runner.py): one JSON dict, or {"error": ...}."""
+    if not ref_available():
+        return {"error": "baseline/_ref is not installed (baseline/install_ref.sh needs /root/reference)"}
+    try:
+        r = subprocess.run([sys.executable, os.path.join(REPO, "baseline", "ref_runner.py"), *argv], capture_output=True, text=True,
+                           timeout=timeout, cwd=os.path.join(REPO, "baseline"))
+        lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": (r.stderr or r.stdout)[-300:]}
+        return json.loads(lines[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:300]}
+
+
+def cpu_reference_decode(workload, max_steps, warmup, budget_s=75.0):
+    """CPU arm: the reference's own CPU path for this workload on the box's host cores.  The unmodified reference
+    (baseline/_ref, kind "reference") where it can run the workload (float weights); the oracle port (kind "port") for the
+    quantised workloads (the reference builds per-row GPTQ layers only, lit_gpt/utils.py:72-74, and bitsandbytes is absent) and
+    wherever baseline/_ref is missing.  Returns (tok/s, steps, threads, description, kind)."""
+    preset, quant, tile, B, ctx = WORKLOADS[workload]
+    big = preset.endswith("70b-hf")  # fp32 70B does not fit host RAM: the port times a 4-layer slice
+    if quant is None and B == 1 and not big and ref_available():
+        r = ref_run(["cpu-decode", "--preset", preset, "--ctx", str(ctx), "--steps", str(max_steps), "--warmup", str(max(1, min(warmup, 2))),
+                     "--budget", str(budget_s)], timeout=budget_s * 4 + 600)
+        if "error" not in r and r.get("steps", 0) > 0:
+            return r["tok_s"], r["steps"], r["threads"], r["what"], "reference"
+    v, n, threads, desc = cpu_oracle_decode(workload, max_steps, warmup, budget_s)
+    return v, n, threads, desc, "port"
+
+
 def cpu_oracle_decode(workload, max_steps, warmup, budget_s=75.0):
     """The reference's CPU path (oracle port, torch CPU fp32, all host threads) on a bounded sample: short prefill,
     then decode steps at short context.  Returns (tok/s, steps timed, threads, description)."""
@@ -510,9 +590,10 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        v, n, threads, desc = cpu_oracle_decode(args.workload, args.steps, args.warmup)
+        v, n, threads, desc, kind = cpu_reference_decode(args.workload, args.steps, args.warmup)
+        base["config"]["workload"] += f" — CPU arm sample: {desc}"
         line = dict(base, impl="reference", value=v, steps=n, ms_per_step=1e3 * B / v, n_gpus=args.gpus,
-                    cpu_baseline={"value": v, "unit": "tok/s", "cores": threads, "kind": "port", "sample": desc},
+                    cpu_baseline={"value": v, "unit": "tok/s", "cores": threads, "kind": kind, "sample": desc},
                     e2e={"value": v, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0)
         line["dtype"] = "f32"
         print(json.dumps(line))
@@ -535,17 +616,35 @@ def main():
                                   with_kernel=False)
         except Exception as e:
             tp_res = {"workload": "llama2-70b-bf16-b1-tp", "error": repr(e)[:200]}
+        tp_n1 = None
+        if world > 1:
+            # the same model unsharded on ONE GPU (137 GB of 180) is the N = 1 point of the strong-scaling curve: rank 0 measures it
+            # in the same run (the other ranks wait), so that speed-up and efficiency of the sharded path are in the line itself
+            if rank == 0:
+                try:
+                    tp_n1 = run_workload("llama2-70b-bf16-b1-tp", min(args.steps, 32), min(args.warmup, 4), device, 0, 1, with_e2e=False,
+                                         with_kernel=False)
+                except Exception as e:
+                    tp_n1 = {"error": repr(e)[:200]}
+            dist.barrier()
     if not args.no_extras and world == 1:
         for w in EXTRAS:
             if w != args.workload:
                 try:
-                    extras.append(run_workload(w, args.steps, args.warmup, device, with_e2e=False))
+                    extras.append(run_workload(w, args.steps, args.warmup, device, with_e2e=(w == "llama2-7b-int4g128-b1")))
                 except Exception as e:  # an extra must never cost the headline line
                     extras.append({"workload": w, "error": repr(e)[:200]})
         try:
             extras.append(run_prefill("falcon-7b", 1792, device))  # 1792 + 256 decode tokens = block_size 2048
         except Exception as e:
             extras.append({"workload": "falcon-7b prefill", "error": repr(e)[:200]})
+        try:
+            extras.append(run_config0(device))  # BASELINE configs[0]: the reference as-is on CPU beside the same generate() here
+        except Exception as e:
+            extras.append({"workload": "pythia-70m configs[0]", "error": repr(e)[:200]})
+        # the library path on the same GPU: the unmodified reference, eager PyTorch CUDA bf16, same model / batch / context
+        r = ref_run(["cuda-decode", "--preset", preset, "--ctx", str(ctx), "--steps", str(min(args.steps, 64)), "--warmup", "8"])
+        extras.append({"workload": f"reference eager CUDA: {preset} bf16 decode, batch 1, context {ctx}", "reference_eager_cuda": r})
     if rank == 0:
         peak, peak_src = peaks()
         k = res["kernel"]
@@ -563,17 +662,30 @@ def main():
                           **{kk: tp_res[kk] for kk in ("tok_s", "ms_per_step", "launches_per_step", "bytes_per_step", "step_gbs", "error")
                              if kk in tp_res}}
             if "step_gbs" in tp_res:
-                line["tp"]["per_gpu_hbm_frac"] = tp_res["step_gbs"] / peak
+                line["tp"]["per_gpu_hbm_frac"] = tp_res["step_gbs"] / peak  # bytes of ONE rank's shard / step time
+            if "tokens_agree" in tp_res:
+                line["tp"]["all_ranks_same_tokens"] = tp_res["tokens_agree"]
+            if world > 1 and tp_n1 is not None:
+                if "tok_s" in tp_n1 and "tok_s" in tp_res:
+                    line["tp"]["n1_tok_s"] = tp_n1["tok_s"]
+                    line["tp"]["speedup_vs_n1"] = tp_res["tok_s"] / tp_n1["tok_s"]
+                    line["tp"]["efficiency"] = tp_res["tok_s"] / tp_n1["tok_s"] / world
+                else:
+                    line["tp"]["n1_error"] = tp_n1.get("error")
         if extras:
             line["also"] = [{kk: e[kk] for kk in e if kk in ("workload", "tok_s", "ms_per_step", "step_gbs", "launches_per_step",
                                                               "bytes_per_step", "kernel", "error", "ms", "prefill_tok_s", "tflops",
-                                                              "tensor_frac_of_sustained_peak")} for e in extras]
+                                                              "tensor_frac_of_sustained_peak", "e2e", "reference_eager_cuda",
+                                                              "reference_cpu", "ours_gpu")} for e in extras]
+            for e in line["also"]:
+                if "kernel" in e and e["kernel"].get("name", "").startswith("lp_decode_step"):
+                    e["kernel"]["traffic"] = ncu_traffic(e["workload"])  # DRAM bytes of the committed ncu capture of the default build
             for e in line["also"]:
                 if "step_gbs" in e:
                     e["step_frac"] = e["step_gbs"] / peak
         if not args.no_cpu_baseline and world == 1:
-            v, n, threads, desc = cpu_oracle_decode(args.workload, 24, 2, budget_s=25.0)
-            line["cpu_baseline"] = {"value": v, "unit": "tok/s", "cores": threads, "kind": "port", "sample": desc}
+            v, n, threads, desc, kind = cpu_reference_decode(args.workload, 24, 2, budget_s=25.0)
+            line["cpu_baseline"] = {"value": v, "unit": "tok/s", "cores": threads, "kind": kind, "sample": desc}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -210,7 +210,7 @@ int lp_attn_prefill(const float* q, const void* k_cache, const void* v_cache, in
  *        of them may overlap (parallel-residual blocks); the summation order of their partial sums is not fixed.
  * Covers fp32-activation mode, bf16 / GPTQ-int4 (tile-major aux2) weights, MHA / GQA / MQA with H <= #SMs, bf16 KV cache,
  * hs 64 / 128, batch 1; LP_ERR_UNSUPPORTED otherwise (callers then issue the per-op calls above). */
-typedef enum { LP_STEP_LINEAR = 0, LP_STEP_ATTENTION = 1, LP_STEP_EXCHANGE = 2 } lp_step_kind;
+typedef enum { LP_STEP_LINEAR = 0, LP_STEP_ATTENTION = 1, LP_STEP_EXCHANGE = 2, LP_STEP_SLAB = 3 } lp_step_kind;
 
 typedef struct {
   int32_t kind;            /* lp_step_kind */
@@ -240,7 +240,31 @@ typedef struct {
   void* tp_state;
   uint64_t tp_buf_offset;
   int32_t tp_pad_base, tp_rank, tp_size, reserved;
+  /* SLAB (column -> row pairing inside the GPU): out += W[:, c] . v for the input columns c whose values v THIS CTA produced in
+   * the op right before — slab_src 0: the SwiGLU outputs of the preceding LINEAR op (which sets keep_local: its epilogue leaves
+   * them in shared memory, `out` of that op is not written; dep = -1); slab_src 1: the attention output of the CTA's head (the
+   * preceding ATTENTION op; dep = that op: the P CTAs of a head wait for each other only).  Neither u nor the attention output
+   * travels through L2 and neither pair is a grid-wide dependency; the partial rows are added to `out` with vector reductions.
+   * W: the projection (GPTQ int4, group 128, packed aux2) for N, K, bias; slab_image / slab_meta from lp_decode_step_slab_build /
+   * lp_decode_step_slab_layout. */
+  const void* slab_image;
+  const void* slab_meta;
+  int32_t slab_src, keep_local;
 } lp_step_op;
+
+/* What one CTA of the step kernel streams for a SLAB op (filled by lp_decode_step_slab_layout; opaque to callers). */
+typedef struct {
+  int64_t off;
+  int32_t nunits, units_a, nseg, row0, nrb, unit0, group_a, stage_bytes;
+} lp_slab_meta;
+
+/* Load time.  lp_decode_step_slab_layout: which input columns every CTA of the step kernel owns for a projection [N, K] fed by
+ * src 0 (SwiGLU up-projection of `fc_tiles_or_heads` 16-row tiles, K = 8 * tiles) or src 1 (attention, `fc_tiles_or_heads` heads of
+ * size hs); writes *n_ctas records (max_ctas >= #SMs) and the image size.  lp_decode_step_slab_build: gathers W (LP_W_INT4 row
+ * major + packed tile-major aux2) into the per-CTA slab images (`meta_dev`: the records copied to the device). */
+int lp_decode_step_slab_layout(int src, int N, int K, int fc_tiles_or_heads, int hs, lp_slab_meta* meta, int max_ctas, int* n_ctas,
+                               size_t* image_bytes);
+int lp_decode_step_slab_build(const lp_weight* W, const lp_slab_meta* meta_dev, int n_ctas, void* image, void* stream);
 
 typedef struct {
   const int32_t* pos;        /* [1] device-side position of the token being decoded                               */

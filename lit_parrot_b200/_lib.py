@@ -19,7 +19,7 @@ LP_EPI_NONE, LP_EPI_GELU, LP_EPI_SWIGLU, LP_EPI_RESIDUAL = 0, 1, 2, 3
 LP_NORM_LAYERNORM, LP_NORM_RMS = 0, 1
 LP_ABI_VERSION = 5
 LP_WF_AUX_PACKED = 1
-LP_STEP_LINEAR, LP_STEP_ATTENTION, LP_STEP_EXCHANGE = 0, 1, 2
+LP_STEP_LINEAR, LP_STEP_ATTENTION, LP_STEP_EXCHANGE, LP_STEP_SLAB = 0, 1, 2, 3
 
 c_void_p, c_int, c_float, c_size_t, c_u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_uint64
 
@@ -40,7 +40,15 @@ class LpStepOp(ctypes.Structure):
                 ("eps", c_float), ("epilogue", ctypes.c_int32), ("residual", c_void_p), ("out", c_void_p),
                 ("qkv", c_void_p), ("k_cache", c_void_p), ("v_cache", c_void_p),
                 ("tp_buf_ptrs", c_void_p), ("tp_pad_ptrs", c_void_p), ("tp_state", c_void_p), ("tp_buf_offset", ctypes.c_uint64),
-                ("tp_pad_base", ctypes.c_int32), ("tp_rank", ctypes.c_int32), ("tp_size", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("tp_pad_base", ctypes.c_int32), ("tp_rank", ctypes.c_int32), ("tp_size", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("slab_image", c_void_p), ("slab_meta", c_void_p), ("slab_src", ctypes.c_int32), ("keep_local", ctypes.c_int32)]
+
+
+class LpSlabMeta(ctypes.Structure):
+    """struct lp_slab_meta"""
+
+    _fields_ = [("off", ctypes.c_int64)] + [(n, ctypes.c_int32) for n in
+                                            ("nunits", "units_a", "nseg", "row0", "nrb", "unit0", "group_a", "stage_bytes")]
 
 
 class LpStepGeom(ctypes.Structure):
@@ -96,6 +104,9 @@ PROTOTYPES = {
     "lp_decode_step_plan": (c_int, [ctypes.POINTER(LpStepOp), c_int, ctypes.POINTER(LpStepGeom), c_void_p, c_size_t,
                                     ctypes.POINTER(LpStepHandle)]),
     "lp_decode_step": (c_int, [ctypes.POINTER(LpStepHandle), c_void_p]),
+    "lp_decode_step_slab_layout": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(LpSlabMeta), c_int,
+                                           ctypes.POINTER(c_int), ctypes.POINTER(c_size_t)]),
+    "lp_decode_step_slab_build": (c_int, [ctypes.POINTER(LpWeight), c_void_p, c_int, c_void_p, c_void_p]),
     "lp_decode_step_status": (c_int, [ctypes.POINTER(LpStepHandle), ctypes.POINTER(ctypes.c_int32)]),
     "lp_decode_step_cooperative": (c_int, [ctypes.POINTER(LpStepHandle)]),
     "lp_debug_step_trace": (c_int, [c_void_p]),

@@ -36,7 +36,9 @@ constexpr int DS_EWARPS = 2;                                   // epilogue warps
 constexpr int DS_THREADS = (GS_CWARPS + 1 + DS_EWARPS + 1) * 32;   // consumers + producer warp + epilogue warps + watcher warp
 constexpr int DS_TILE_BAR_THREADS = DS_CTHREADS + 32;          // named barriers 2 / 3: the consumers arrive, one epilogue warp waits
 constexpr int DS_OPEND_THREADS = DS_CTHREADS + DS_EWARPS * 32; // named barrier 4: end of an op
-constexpr int DS_KIND_LINEAR = 0, DS_KIND_EXCHANGE = 2;
+constexpr int DS_KIND_LINEAR = 0, DS_KIND_EXCHANGE = 2, DS_KIND_SLAB = 3;
+constexpr int DS_SLAB_ROWS = 256;  // output rows per slab stage: one m16 tile per consumer warp
+constexpr int DS_SLAB_MAXU = 16;   // 8-column units of a CTA's slab (<= 128 input columns)
 constexpr int DS_MAX_TP = 8;
 constexpr int DS_NREC = 3;  // op records resident in shared memory: previous (its signal may still be pending), current, next
 constexpr int DS_RED_FLOATS = 2 * GS_CWARPS * 16 * 4;  // [2 parities][warps][16 rows][4 B-columns]
@@ -59,6 +61,12 @@ struct alignas(128) DsOp {
   int save_x, reuse_x;  // LayerNorm ops reading the same row back to back (parallel residual: QKV then FC): the first keeps the raw
                         // row and its statistics in shared memory, the second stages from there (no L2 round trip, no reductions)
   int streamk;  // in-place residual op: stages (not tiles) are split evenly over the CTAs, partial tiles are added atomically
+  // fused column->row pairs (DS_KIND_SLAB): this CTA multiplies the input columns it produced itself (its SwiGLU outputs, or the
+  // attention output of its head) with the matching K-slab of the following projection and adds the partial row into `out`
+  const unsigned char* slab_img;  // per-CTA slab images (lp_decode_step_slab_build)
+  int slab_src;    // 0: the CTA's outputs of the preceding LINEAR op (keep_local); 1: the attention output of the CTA's head
+  int keep_local;  // LINEAR: the epilogue leaves this CTA's outputs in shared memory (s_loc) instead of writing them to `out`
+  int hsync;       // ATTENTION feeding a slab / SLAB fed by attention: first of the H per-head arrival counters, else -1
   // tensor-parallel exchange (kind 2): out = residual + sum over ranks of the partial at buf_off of every rank's symmetric buffer
   const unsigned long long* tp_bufs;  // [tp] peer-mapped buffer addresses
   const unsigned long long* tp_pads;  // [tp] peer-mapped signal pads
@@ -67,8 +75,23 @@ struct alignas(128) DsOp {
   int tp_pad_base, tp_rank, tp_size, tp_use, tp_uses;  // tp_use: index of this exchange among the tp_uses of its slot per step
 };
 
+struct DsSlabMeta {  // == lp_slab_meta: what one CTA streams for a slab op
+  long long off;    // byte offset of the CTA's image
+  int nunits;       // 8-column units of the CTA (<= DS_SLAB_MAXU)
+  int units_a;      // units that belong to the first scale group (the rest to the next one)
+  int nseg;         // scale groups touched: 1 or 2
+  int row0, nrb;    // first output row, number of 256-row stages (0: no work)
+  int unit0;        // first unit (global index: column / 8)
+  int group_a;      // scale group of the first segment
+  int stage_bytes;  // (nunits + nseg) KB
+};
+static_assert(sizeof(DsSlabMeta) == 40 && sizeof(DsSlabMeta) == sizeof(lp_slab_meta), "lp_slab_meta layout");
+
 struct DsParams {
   const DsOp* ops;
+  const DsSlabMeta* slab_meta[2];  // [0]: MLP slabs, [1]: attention-projection slabs; one record per CTA, or NULL
+  int ncounters;                   // arrival counters: one per op + H per fused attention op
+  int dbg;                         // LP_DS_DEBUG bits (timing experiments, WRONG results): 1 no reds, 2 no stagger, 4 stores instead of reds
   unsigned* counters;  // [nops], zeroed by the prologue kernel of every step
   const int* pos;
   const float* cosT;
@@ -812,7 +835,7 @@ __device__ __forceinline__ void ds_linear(const DsParams& p, const DsOp& o, cons
 // Epilogue warp `e` finalises the tiles of parity e: cross-warp reduction of the 16 partial sums, digit / term recombination,
 // bias, activation, residual, store.  The consumers never stop for this: they drop their partials and stream on.
 __device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint32_t red_u32, const float* colscale, volatile int* done,
-                                                 const DsOp* s_ops) {
+                                                 const DsOp* s_ops, float* s_loc) {
   const int lane = threadIdx.x & 31;
   const int rr = lane & 15, half = lane >> 4;
   int gt = 0;
@@ -820,13 +843,15 @@ __device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint3
   for (int op = 0; op < p.nops; ++op) {
     const DsOp& o = s_ops[op % DS_NREC];
     const int signal = o.signal;
+    const int hsync = o.kind == DS_KIND_LINEAR || o.kind == DS_KIND_SLAB ? -1 : o.hsync;
     if (o.kind == DS_KIND_LINEAR) {
-      const int nks = o.nks, fmt = o.fmt, split = o.split, epi = o.epi, streamk = o.streamk;
+      const int nks = o.nks, fmt = o.fmt, split = o.split, epi = o.epi, streamk = o.streamk, keep_local = o.keep_local;
       const float* bias = o.bias;
       const float* residual = o.residual;
       float* out = o.out;
       int sb, se;
       ds_stage_range(o, sb, se);
+      const int loc0 = (sb / nks) * (GS_ROWS / 2);  // keep_local (SwiGLU): first output of this CTA
       for (int s0 = sb; s0 < se; ++gt) {
         const int tile = s0 / nks;
         const bool first = s0 == tile * nks;  // this CTA's part of the tile starts at K = 0: it adds the bias
@@ -866,7 +891,10 @@ __device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint3
           if (half == 0) atomicAdd(out + row, y);  // x += (partial) W . u, in place
         } else if (epi == LP_EPI_SWIGLU) {
           const float other = __shfl_xor_sync(0xffffffffu, y, 1);  // fc_2 row of the pair
-          if (half == 0 && (rr & 1) == 0) out[row >> 1] = silu(y) * other;
+          if (half == 0 && (rr & 1) == 0) {
+            if (keep_local) s_loc[(row >> 1) - loc0] = silu(y) * other;  // consumed by this CTA's slab op, never leaves the SM
+            else out[row >> 1] = silu(y) * other;
+          }
         } else if (half == 0) {
           if (epi == LP_EPI_GELU) y = gelu_erf(y);
           else if (epi == LP_EPI_RESIDUAL) y = __ldcg(residual + row) + y;
@@ -879,7 +907,11 @@ __device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint3
     // of this CTA (ordered before by the barrier).  The ~1 us of that fence is off the consumers' path: they are already staging
     // the next op.
     asm volatile("bar.sync 4, %0;\n" ::"n"(DS_OPEND_THREADS) : "memory");
-    if (e == 0 && lane == 0 && signal) ds_red_release(p.counters + op);
+    if (e == 0 && lane == 0) {
+      if (signal) ds_red_release(p.counters + op);
+      // attention feeding a slab: the P CTAs of a head only wait for each other (per-head counter), not for the grid
+      if (hsync >= 0 && (int)blockIdx.x < p.H * p.P) ds_red_release(p.counters + hsync + blockIdx.x / p.P);
+    }
   }
 }
 
@@ -1072,6 +1104,265 @@ __device__ __forceinline__ void ds_attention(const DsParams& p, const DsOp& o, c
 }
 
 
+struct DsSlabLoop {
+  uint32_t sc_off, ring_u32, bar0;
+  int nstages, stage_stride, nrb, stagger, dbg;
+  bool lane0, t0, t0e;  // t0e: t == 0 and g even: the lane that issues the 4-row reduction
+  float* out_row;
+  const float* bias;  // NULL, or the bias shifted to this lane's first row
+  float a_seg[2], zs0[2], zs1[2];
+};
+
+// Stage loop of ds_slab for NCHA chunks of the first scale group and NCH chunks in all.  Two stages at a time (the stage counts
+// are even): per stage a warp has ONE short dependent chain (wait -> loads -> IMMA -> IMMA -> fold -> shuffle -> red) and all 16
+// warps sit on the same stage, so interleaving the chains of two stages (same digit words, two weight tiles) overlaps them.
+template <int NCHA, int NCH>
+__device__ __forceinline__ void ds_slab_loop(const DsSlabLoop& L, const uint32_t (&woff)[3][2], const uint32_t (&doff)[3][2], int& rs_io,
+                                             int& rph_io) {
+  const uint32_t ML = 0x0F0F0F0Fu, MH = 0xF0F0F0F0u;
+  const uint32_t sc_off = L.sc_off, ring_u32 = L.ring_u32, bar0 = L.bar0;
+  const int nstages = L.nstages, stage_stride = L.stage_stride, nrb = L.nrb;
+  int rs = rs_io, rph = rph_io;
+  int rba = L.stagger;  // the pair (rba, rba + 1): nrb and the pair index are even, the stagger wraps as a whole pair
+  auto fold = [&](const int (&cl)[4], const int (&ch)[4], uint32_t stb, int sg, float (&acc)[4]) {
+    const uint2 sz = ds_lds64(stb + sc_off + (uint32_t)(sg * 1024));  // packed scale / zero of rows 2g, 2g + 1
+    const float s0 = __uint_as_float(sz.x & 0xffff0000u) * L.a_seg[sg], s1 = __uint_as_float(sz.y & 0xffff0000u) * L.a_seg[sg];
+    const float z0 = __uint_as_float(sz.x << 16), z1 = __uint_as_float(sz.y << 16);
+    // sum (q - z) s x = s * (sum q X - z * sum X), all integers exact in fp32
+    acc[0] = fmaf(s0, fmaf((float)ch[0], 0.0625f, fmaf(-z0, L.zs0[sg], (float)cl[0])), acc[0]);
+    acc[1] = fmaf(s0, fmaf((float)ch[1], 0.0625f, fmaf(-z0, L.zs1[sg], (float)cl[1])), acc[1]);
+    acc[2] = fmaf(s1, fmaf((float)ch[2], 0.0625f, fmaf(-z1, L.zs0[sg], (float)cl[2])), acc[2]);
+    acc[3] = fmaf(s1, fmaf((float)ch[3], 0.0625f, fmaf(-z1, L.zs1[sg], (float)cl[3])), acc[3]);
+  };
+  auto emit = [&](const float (&acc)[4], int rb) {
+    // digit recombination: lane t = 0 holds planes 0 and 1, lane t = 1 plane 2 of rows 2g, 2g + 1
+    float y0 = L.t0 ? fmaf(acc[1], 256.0f, acc[0]) : acc[0] * 65536.0f;
+    float y1 = L.t0 ? fmaf(acc[3], 256.0f, acc[2]) : acc[2] * 65536.0f;
+    y0 += __shfl_xor_sync(0xffffffffu, y0, 1);
+    y1 += __shfl_xor_sync(0xffffffffu, y1, 1);
+    // rows 2g, 2g + 1 of this lane and 2g + 2, 2g + 3 of lane g + 1 (4 lanes up): ONE 16-byte reduction per 4 rows
+    const float y2 = __shfl_down_sync(0xffffffffu, y0, 4), y3 = __shfl_down_sync(0xffffffffu, y1, 4);
+    if (L.t0e) {
+      float* dst = L.out_row + rb * DS_SLAB_ROWS;
+      float4 yy = make_float4(y0, y1, y2, y3);
+      if (L.bias) {
+        const float4 bb = *reinterpret_cast<const float4*>(L.bias + rb * DS_SLAB_ROWS);
+        yy.x += bb.x; yy.y += bb.y; yy.z += bb.z; yy.w += bb.w;
+      }
+      if (L.dbg & 4) *reinterpret_cast<float4*>(dst) = yy;
+      else if (!(L.dbg & 1))
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(dst), "f"(yy.x), "f"(yy.y), "f"(yy.z), "f"(yy.w) : "memory");
+    }
+  };
+  for (int i = 0; i < nrb; i += 2) {
+    int rs2 = rs + 1, rph2 = rph;
+    if (rs2 == nstages) { rs2 = 0; rph2 ^= 1; }
+    mbar_wait(bar0 + 8 * rs, rph);
+    mbar_wait(bar0 + 8 * rs2, rph2);
+    const uint32_t sta = ring_u32 + (uint32_t)(rs * stage_stride), stb = ring_u32 + (uint32_t)(rs2 * stage_stride);
+    float acca[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
+    int cla[4] = {0, 0, 0, 0}, cha[4] = {0, 0, 0, 0}, clb[4] = {0, 0, 0, 0}, chb[4] = {0, 0, 0, 0};
+    if (!(L.dbg & 32))
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const uint2 d0 = ds_lds64(doff[c][0]), d1 = ds_lds64(doff[c][1]);
+      const uint2 wa0 = ds_lds64(sta + woff[c][0]), wa1 = ds_lds64(sta + woff[c][1]);
+      const uint2 wb0 = ds_lds64(stb + woff[c][0]), wb1 = ds_lds64(stb + woff[c][1]);
+      if (!(L.dbg & 8)) {
+      gs_imma(cla, wa0.x & ML, wa0.y & ML, wa1.x & ML, wa1.y & ML, d0.x, d1.x);
+      gs_imma(clb, wb0.x & ML, wb0.y & ML, wb1.x & ML, wb1.y & ML, d0.x, d1.x);
+      gs_imma(cha, wa0.x & MH, wa0.y & MH, wa1.x & MH, wa1.y & MH, d0.y, d1.y);
+      gs_imma(chb, wb0.x & MH, wb0.y & MH, wb1.x & MH, wb1.y & MH, d0.y, d1.y);
+      } else {
+        cla[0] += wa0.x + wa1.y + d0.x; clb[0] += wb0.x + wb1.y + d1.x; cha[0] += wa0.y + wa1.x + d0.y; chb[0] += wb0.y + wb1.x + d1.y;
+      }
+      if ((c == NCHA - 1 || c == NCH - 1) && !(L.dbg & 16)) {  // compile time: last chunk of a scale group
+        fold(cla, cha, sta, c < NCHA ? 0 : 1, acca);
+        fold(clb, chb, stb, c < NCHA ? 0 : 1, accb);
+        if (c != NCH - 1) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) cla[q] = cha[q] = clb[q] = chb[q] = 0;
+        }
+      }
+    }
+    __syncwarp();
+    if (L.lane0) {
+      mbar_arrive(bar0 + 8 * (nstages + rs));
+      mbar_arrive(bar0 + 8 * (nstages + rs2));
+    }
+    rs = rs2;
+    rph = rph2;
+    if (++rs == nstages) { rs = 0; rph ^= 1; }
+    if (!(L.dbg & 64)) {
+      emit(acca, rba);
+      emit(accb, rba + 1);
+    } else if (cla[0] + clb[0] + cha[0] + chb[0] == 0x7fffffff) {
+      L.out_row[0] = acca[0] + accb[0];
+    }
+    rba += 2;
+    if (rba >= nrb) rba -= nrb;
+  }
+  rs_io = rs;
+  rph_io = rph;
+}
+
+// ------------------------------------------------------------------------------------------------ slab op (consumers)
+// out += W[:, cols] . v  for the input columns THIS CTA produced itself: its SwiGLU outputs of the preceding up-projection (72 / 80
+// columns of mlp.proj) or the attention output of its head (hs = 128 columns of attn.proj, rows split over the head's P CTAs).
+// The column -> row pairing of tensor parallelism applied inside one GPU: u / att never travel through L2, and fc -> mlp.proj,
+// attention -> attn.proj stop being grid-wide dependencies (5 -> 3 per Llama layer); what is left is ONE reduction of the partial
+// rows into the residual stream (red.global.add.v2.f32, staggered over the row blocks so that the CTAs hit different rows).
+//   weights: the CTA's slab image (lp_decode_step_slab_build): per 256-row stage [unit][128 row pairs][2 rows x 4 B] — a word holds
+//   the 8 int4 columns of one unit, row pair index XOR 4 * (unit & 3) (bank-conflict-free 64-bit loads) — then one KB of packed
+//   (bf16 scale << 16 | bf16 zero) words per scale group touched.  One 16-row m16n8k32 tile per warp and stage: MMA row g <-> output
+//   row 2g, row g + 8 <-> 2g + 1; k-quad t <-> unit c0 + t, the even columns of a unit go through the low-nibble IMMA, the odd
+//   ones through the high-nibble IMMA (w & 0xF0F0F0F0 = 16 q), B columns 0..2 = the three int8 digit planes of v.
+//   v: block fixed point per scale-group segment, X = rint(v * 2^22 / max|v_seg|), balanced base-256 digits (ds_stage_row).
+template <int HS, class WaitHs>
+__device__ __forceinline__ void ds_slab(const DsParams& p, const DsOp& o, const DsSlabMeta& mt, const DsAttnGeo<HS>& geo, DsRing& rg,
+                                        unsigned char* xs, float* s_loc, WaitHs wait_hs, unsigned long long* tr) {
+  const int nrb = mt.nrb;
+  if (nrb == 0) return;  // CTA-uniform: this CTA has no slab (e.g. the CTAs beyond H * P in an attention projection)
+  const int ctid = threadIdx.x, warp = ctid >> 5, lane = ctid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int nunits = mt.nunits, units_a = mt.units_a, nseg = mt.nseg;
+  uint32_t* dig = reinterpret_cast<uint32_t*>(xs);              // [3 planes][DS_SLAB_MAXU units][even word, odd word]
+  unsigned* s_am = reinterpret_cast<unsigned*>(xs + 384);       // [2] max|v| per segment (float bits)
+  int* s_sum = reinterpret_cast<int*>(xs + 392);                // [2][3] digit sums per segment and plane
+  if (o.slab_src == 1) {
+    // v = attention output of head h: merge the P sequence-split partials (m, l, o[hs]) once their CTAs have arrived
+    wait_hs();
+    if (tr && ctid == 0) tr[1] = gs_now();
+    constexpr int LDM = DsAttnGeo<HS>::LDM;
+    if (ctid < HS) {
+      const int h = blockIdx.x / p.P;
+      const int nvalid = (geo.nblk + geo.bpp - 1) / geo.bpp;
+      const float* base = p.part + (size_t)h * p.P * LDM;
+      float m[DS_MAXP], l[DS_MAXP], ov[DS_MAXP], mx = -CUDART_INF_F;
+#pragma unroll
+      for (int q = 0; q < DS_MAXP; ++q) {
+        m[q] = -CUDART_INF_F;
+        l[q] = ov[q] = 0.f;
+        if (q < nvalid) {
+          m[q] = __ldcg(base + q * LDM + HS);
+          l[q] = __ldcg(base + q * LDM + HS + 1);
+          ov[q] = __ldcg(base + q * LDM + ctid);
+        }
+        mx = fmaxf(mx, m[q]);
+      }
+      float L = 0.f, acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < DS_MAXP; ++q) {  // split order: deterministic
+        const float c = exp2f(m[q] - mx);
+        L = fmaf(l[q], c, L);
+        acc = fmaf(ov[q], c, acc);
+      }
+      s_loc[ctid] = acc / L;
+    }
+  }
+  if (ctid < 2) s_am[ctid] = 0u;
+  if (ctid < 6) s_sum[ctid] = 0;
+  if (ctid < 2) reinterpret_cast<uint32_t*>(xs + 416)[ctid] = 0u;  // an all-zero digit word pair for the empty k-quads of a chunk
+  gs_bar_consumers();
+  const int nval = nunits * 8;
+  float v = 0.f;
+  const int my_seg = (ctid >> 3) >= units_a ? 1 : 0;
+  if (ctid < nval) {
+    v = s_loc[ctid];
+    atomicMax(&s_am[my_seg], __float_as_uint(fabsf(v)));  // non-negative floats order like their bit patterns
+  }
+  gs_bar_consumers();
+  if (ctid < nval) {
+    const float am = __uint_as_float(s_am[my_seg]);
+    const float inv = am > 0.f ? 4194304.0f / am : 0.f;
+    const uint32_t z = (uint32_t)(__float2int_rn(v * inv) + 0x8080) ^ 0x8080u;  // bytes 0..2 = balanced digits (ds_stage_row)
+    const int unit = ctid >> 3, col = ctid & 7;
+    unsigned char* db = reinterpret_cast<unsigned char*>(dig);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const int b = (int)(signed char)((z >> (8 * d)) & 0xffu);
+      db[((d * DS_SLAB_MAXU + unit) * 2 + (col & 1)) * 4 + (col >> 1)] = (unsigned char)b;
+      if (b != 0) atomicAdd(&s_sum[my_seg * 3 + d], b);
+    }
+  }
+  gs_bar_consumers();
+  if (tr && ctid == 0) tr[2] = gs_now();
+  // per-lane constants of the two segments: activation scale, digit sums of this lane's accumulator columns (2t, 2t + 1)
+  float a_seg[2], zs0[2], zs1[2];
+#pragma unroll
+  for (int sg = 0; sg < 2; ++sg) {
+    a_seg[sg] = __uint_as_float(s_am[sg]) * (1.0f / 4194304.0f);
+    zs0[sg] = t == 0 ? (float)s_sum[sg * 3 + 0] : (float)s_sum[sg * 3 + 2];
+    zs1[sg] = t == 0 ? (float)s_sum[sg * 3 + 1] : 0.f;
+  }
+  // Chunks of 8 units (one low + one high IMMA each): ceil(units_a / 8) for the first scale group, then those of the second; at most
+  // 3 for 16 units.  Everything a lane needs per chunk is loop invariant: the byte offsets of its two weight words (k-quads t and
+  // t + 4) inside a stage and the addresses of the matching digit words — an empty k-quad reads unit 0's weights against the
+  // all-zero digit word, so the stage loop has no lane-divergent branch and no address arithmetic beyond `stage base + offset`.
+  const int plane = g < 3 ? g : 2;  // B column n = g: digit plane g; columns 3..7 feed accumulator columns nobody reads
+  const uint32_t dig_u32 = gs_smem_u32(dig), zero_u32 = gs_smem_u32(xs + 416);
+  const uint32_t pair_off = (uint32_t)(8 * warp + g);  // row pair of this lane inside the 256-row stage
+  const int nch_a = (units_a + 7) >> 3, nch = nch_a + (nseg > 1 ? (nunits - units_a + 7) >> 3 : 0);
+  uint32_t woff[3][2], doff[3][2];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int sg = c < nch_a ? 0 : 1, ci = c - (sg ? nch_a : 0);
+    const int ub = sg ? units_a : 0, ue = sg ? nunits : units_a;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int j = ub + 8 * ci + 4 * hf + t;
+      const bool valid = c < nch && j < ue;
+      const int jj = valid ? j : 0;
+      woff[c][hf] = ds_pin((uint32_t)(jj * 1024) + ((pair_off ^ (uint32_t)(4 * (jj & 3))) << 3));
+      doff[c][hf] = ds_pin(valid ? dig_u32 + (uint32_t)((plane * DS_SLAB_MAXU + j) * 8) : zero_u32);
+    }
+  }
+  const uint32_t ring_u32 = ds_pin(rg.ring_u32), bar0 = ds_pin(rg.bar0);
+  const int nstages = ds_pin(rg.nstages), stage_stride = ds_pin(rg.stage_stride);
+  const uint32_t sc_off = ds_pin((uint32_t)(nunits * 1024 + (16 * warp + 2 * g) * 4));
+  const bool lane0 = ds_pin(lane) == 0, t0 = ds_pin(t) == 0;
+  const int stagger = (p.dbg & 2) ? 0 : (2 * (o.slab_src == 1 ? (int)blockIdx.x / p.P : (int)blockIdx.x)) % nrb;  // whole stage pairs
+  const float* bias = o.bias;
+  const bool add_bias = bias && (o.slab_src == 1 ? (int)blockIdx.x / p.P == 0 : blockIdx.x == 0);
+  float* out_row = o.out + mt.row0 + 16 * warp + 2 * g;
+  int rs = rg.s, rph = rg.ph;
+  const uint32_t ML = 0x0F0F0F0Fu, MH = 0xF0F0F0F0u;
+  DsSlabLoop lp_;
+  lp_.sc_off = sc_off;
+  lp_.ring_u32 = ring_u32;
+  lp_.bar0 = bar0;
+  lp_.nstages = nstages;
+  lp_.stage_stride = stage_stride;
+  lp_.nrb = nrb;
+  lp_.stagger = stagger;
+  lp_.lane0 = lane0;
+  lp_.t0 = t0;
+  lp_.t0e = t0 && (g & 1) == 0;
+  lp_.out_row = out_row;
+  lp_.bias = add_bias ? bias - (o.out - out_row) : nullptr;  // indexed like out_row
+  lp_.dbg = p.dbg;
+#pragma unroll
+  for (int sg = 0; sg < 2; ++sg) {
+    lp_.a_seg[sg] = a_seg[sg];
+    lp_.zs0[sg] = zs0[sg];
+    lp_.zs1[sg] = zs1[sg];
+  }
+  // straight-line stage loops for the chunk patterns that occur (first scale group: 1 or 2 chunks, second: 0, 1 or 2)
+  const int pat = nch_a * 4 + nch;
+  if (pat == 1 * 4 + 1) ds_slab_loop<1, 1>(lp_, woff, doff, rs, rph);
+  else if (pat == 2 * 4 + 2) ds_slab_loop<2, 2>(lp_, woff, doff, rs, rph);
+  else if (pat == 1 * 4 + 2) ds_slab_loop<1, 2>(lp_, woff, doff, rs, rph);
+  else if (pat == 2 * 4 + 3) ds_slab_loop<2, 3>(lp_, woff, doff, rs, rph);
+  else ds_slab_loop<1, 3>(lp_, woff, doff, rs, rph);
+  rg.s = rs;
+  rg.ph = rph;
+  if (tr && ctid == 0) {
+    tr[5] = gs_now();
+    tr[7] = (unsigned long long)((nunits << 8) | nseg);
+  }
+  gs_bar_consumers();  // xs / s_loc are reused by the next op's staging
+}
+
 // ------------------------------------------------------------------------------------------------ tensor-parallel exchange op
 // One-shot all-reduce over NVLink peer memory inside the step kernel (the protocol of tp_allreduce.cu): the preceding linear op
 // wrote this rank's partial into its slot of the symmetric buffer; CTA 0 publishes the slot's next epoch to every peer, every
@@ -1140,6 +1431,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
   __shared__ float s_xstat[2];
   __shared__ __align__(128) unsigned char s_ops[DS_NREC * sizeof(DsOp)];  // op records: previous / current / next (see fetch_op)
   __shared__ int s_dep_ready;  // highest op index whose completion on ALL CTAs the watcher thread has observed
+  __shared__ int s_hs_ready;   // highest slab op whose head (the P CTAs that split its sequence) the watcher has seen arrive
+  __shared__ __align__(16) float s_loc[DS_SLAB_MAXU * 8];  // CTA-local input columns of a slab op (SwiGLU outputs / head output)
+  __shared__ DsSlabMeta s_meta[2];
   float* xraw = reinterpret_cast<float*>(xs + p.xs_bytes);  // raw activation row kept for a reuse_x op (may be empty)
   const uint32_t red_u32 = gs_smem_u32(red), xs_u32 = gs_smem_u32(xs);
 
@@ -1159,6 +1453,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
     }
     done[0] = done[1] = 0;
     s_dep_ready = -1;
+    s_hs_ready = -1;
+    for (int k = 0; k < 2; ++k) {
+      if (p.slab_meta[k]) s_meta[k] = p.slab_meta[k][blockIdx.x];
+      else s_meta[k].nrb = 0;
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -1176,13 +1475,16 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
       int waited = -1;
       bool dead = false;
       for (int op = 0; op < p.nops; ++op) {
-        const int dep = __ldg(p.deps + op);
-        if (dep <= waited) continue;
+        int dep = __ldg(p.deps + op);
+        const bool hs = dep <= -2;  // a slab fed by attention waits for the P CTAs of its head (counter -2 - dep + head)
+        if (hs && (int)blockIdx.x >= p.H * p.P) continue;  // no head, no slab
+        if (!hs && dep <= waited) continue;
         if (!dead) {
-          const unsigned* ctr = p.counters + dep;
+          const unsigned* ctr = p.counters + (hs ? -2 - dep + (int)blockIdx.x / p.P : dep);
+          const unsigned target = hs ? (unsigned)p.P : gridDim.x;
           unsigned it = 0, seen;
           const unsigned long long t0 = gs_now();
-          while ((seen = ds_ld_relaxed(ctr)) < gridDim.x) {
+          while ((seen = ds_ld_relaxed(ctr)) < target) {
             if (p.timeout_ns) {  // a timer read per poll is noise next to the poll's own L2 round trip
               const bool expired = gs_now() - t0 > p.timeout_ns;
               if (expired || ((++it & 15u) == 0 && ds_ld_relaxed(p.err) != 0u)) {
@@ -1194,15 +1496,19 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
           }
           (void)ds_ld_acquire(ctr);
         }
-        waited = dep;
-        ds_sts_release(&s_dep_ready, dep);
+        if (hs) {
+          ds_sts_release(&s_hs_ready, op);
+        } else {
+          waited = dep;
+          ds_sts_release(&s_dep_ready, dep);
+        }
       }
       return;
     }
   }
   if (warp > GS_CWARPS) {
     pdl_wait();
-    ds_epilogue_warp(p, warp - GS_CWARPS - 1, red_u32, colscale, done, reinterpret_cast<const DsOp*>(s_ops));
+    ds_epilogue_warp(p, warp - GS_CWARPS - 1, red_u32, colscale, done, reinterpret_cast<const DsOp*>(s_ops), s_loc);
     return;
   }
   if (warp == GS_CWARPS) {
@@ -1292,6 +1598,21 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
             ++tile;
           }
         }
+      } else if (o.kind == DS_KIND_SLAB) {
+        const DsSlabMeta& mt = s_meta[o.slab_src];
+        const int nrb = mt.nrb;
+        if (nrb > 0) {
+          const unsigned char* img = o.slab_img + mt.off;
+          const int stagger = (p.dbg & 2) ? 0 : (2 * (o.slab_src == 1 ? (int)blockIdx.x / p.P : (int)blockIdx.x)) % nrb;
+          for (int i = 0; i < nrb; ++i) {
+            int rb = i + stagger;
+            if (rb >= nrb) rb -= nrb;
+            wait_empty();
+            mbar_expect_tx(rg.full(), (uint32_t)mt.stage_bytes);
+            bulk_g2s(rg.ring_u32 + (uint32_t)rg.s * rg.stage_stride, img + (size_t)rb * mt.stage_bytes, (uint32_t)mt.stage_bytes, rg.full());
+            rg.advance();
+          }
+        }
       } else if (o.kind != DS_KIND_EXCHANGE) {
         if (!have_geo) {
           pdl_wait();  // the position is written by the previous step's sampler
@@ -1373,6 +1694,12 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
     };
     if (o.kind == DS_KIND_LINEAR) {
       ds_linear<HS>(p, o, geo, rg, red_u32, colscale, xsum, xs_u32, done, s_stat, tr, gt, wait_dep, xraw, s_xstat, have_xraw);
+    } else if (o.kind == DS_KIND_SLAB) {
+      auto wait_hs = [&]() {
+        while (ds_lds_acquire(&s_hs_ready) < op) {}
+      };
+      have_xraw = false;
+      ds_slab<HS>(p, o, s_meta[o.slab_src], geo, rg, xs, s_loc, wait_hs, tr);
     } else if (o.kind == DS_KIND_EXCHANGE) {
       wait_dep();
       ds_exchange(p, o, op, o.tp_state == p.tp_state1 ? tp_epoch[1] : tp_epoch[0]);
@@ -1384,6 +1711,31 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
     // the epilogue warps have written this op's rows; one of their lanes signals the op after this barrier
     asm volatile("bar.sync 4, %0;\n" ::"n"(DS_OPEND_THREADS) : "memory");
     if (tr && threadIdx.x == 0) tr[3] = gs_now();
+  }
+}
+
+// Load time: slab images of a projection whose input columns stay inside the CTA that produced them (ds_slab).  One CTA of this
+// kernel writes one step-kernel CTA's image: per 256-row stage [unit][row pair ^ 4 (unit & 3)][2 rows] words of 8 int4 columns,
+// then the packed scale / zero words of the one or two scale groups the CTA's columns touch.
+__global__ void slab_build_kernel(const uint32_t* __restrict__ rows32, int row_words, const uint32_t* __restrict__ aux2, int ngroups,
+                                  const DsSlabMeta* __restrict__ meta, uint32_t* __restrict__ image) {
+  const DsSlabMeta mt = meta[blockIdx.x];
+  const int stage_words = mt.stage_bytes / 4;
+  uint32_t* img = image + mt.off / 4;
+  for (int w = threadIdx.x; w < mt.nrb * stage_words; w += blockDim.x) {
+    const int rb = w / stage_words, r = w - rb * stage_words;
+    uint32_t v;
+    if (r < mt.nunits * DS_SLAB_ROWS) {
+      const int unit = r / DS_SLAB_ROWS, pos = r % DS_SLAB_ROWS;
+      const int pr = (pos >> 1) ^ (4 * (unit & 3));
+      const int row = mt.row0 + rb * DS_SLAB_ROWS + 2 * pr + (pos & 1);
+      v = rows32[(size_t)row * row_words + mt.unit0 + unit];
+    } else {
+      const int q = r - mt.nunits * DS_SLAB_ROWS, sg = q / DS_SLAB_ROWS;
+      const int row = mt.row0 + rb * DS_SLAB_ROWS + q % DS_SLAB_ROWS;
+      v = aux2[((size_t)(row >> 4) * ngroups + mt.group_a + sg) * 16 + (row & 15)];  // tile-major [N/16][groups][16 rows]
+    }
+    img[w] = v;
   }
 }
 
@@ -1405,7 +1757,8 @@ __global__ void decode_step_prep_kernel(const void* __restrict__ idx, int idx64,
 // ------------------------------------------------------------------------------------------------ host side
 struct DsHostPlan {  // lp_step_handle, opaque to the caller
   uint32_t magic;
-  int nops, nstages, stage_stride, xsum_floats, hs, H, G, P, n_elem, max_seq, E, wte_dtype, idx64, grid, i4pair, l2_ahead, xs_bytes, coop;
+  int nops, nstages, stage_stride, xsum_floats, hs, H, G, P, n_elem, max_seq, E, wte_dtype, idx64, grid, i4pair, l2_ahead, xs_bytes, coop, ncounters;
+  const DsSlabMeta* slab_meta[2];
   unsigned long long timeout_ns;
   const int* deps;
   unsigned* err;
@@ -1429,7 +1782,7 @@ constexpr uint32_t DS_MAGIC = 0x4c504453u;
 
 static unsigned long long* g_ds_trace = nullptr;
 
-constexpr size_t DS_SMEM_OPTIN = 225 * 1024;  // 227 KB per CTA minus the static block (statistics, op records: < 2 KB)
+constexpr size_t DS_SMEM_OPTIN = 224 * 1024;  // 227 KB per CTA minus the static block (statistics, op records, slab vector: < 3 KB)
 
 template <int HS>
 static int ds_prepare(int device) {  // per DEVICE: the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
@@ -1503,8 +1856,8 @@ static int ds_probe_coop(const DsHostPlan& h, int device) {
 
 extern "C" {
 
-/* op records | arrival counters [n] | dependency list [n] | error record [8] */
-size_t lp_decode_step_plan_bytes(int n_ops) { return n_ops > 0 ? (size_t)n_ops * sizeof(lp::DsOp) + (size_t)n_ops * 8 + 256 : 0; }
+/* op records | arrival counters [n + H per fused attention op] | dependency list [n] | error record [8] */
+size_t lp_decode_step_plan_bytes(int n_ops) { return n_ops > 0 ? (size_t)n_ops * (sizeof(lp::DsOp) + 8 + 160) + 256 : 0; }
 
 size_t lp_decode_step_workspace_bytes(int H, int hs) { return (size_t)H * lp::DS_MAXP * (hs + 4) * 4; }
 
@@ -1528,6 +1881,8 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
   if (gm->H > grid) return LP_ERR_UNSUPPORTED;
 
   std::vector<DsOp> dev(n_ops);
+  const DsSlabMeta* slab_meta[2] = {nullptr, nullptr};
+  int n_hsync = 0;
   unsigned int* tp_state[2] = {nullptr, nullptr};
   int tp_uses[2] = {0, 0};
   int stage_stride = GS_KB * GS_BLK_BYTES, xsum_floats = 0;
@@ -1540,8 +1895,40 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
     d.kind = s.kind;
     d.dep = s.dep;
     d.signal = 0;
+    d.hsync = -1;
     if (s.dep >= i || s.dep < -1) return LP_ERR_INVALID_ARG;
     if (s.dep >= 0) dev[s.dep].signal = 1;
+    if (s.kind == LP_STEP_SLAB) {
+      // out += W[:, this CTA's columns] . (what this CTA produced in the op before): see ds_slab
+      if (!s.W || !s.out || !s.slab_image || !s.slab_meta || i == 0 || s.slab_src < 0 || s.slab_src > 1) return LP_ERR_INVALID_ARG;
+      const lp_weight& W = *s.W;
+      if (W.fmt != LP_W_INT4 || W.group != 128 || !(W.flags & LP_WF_AUX_PACKED) || W.N % DS_SLAB_ROWS) return LP_ERR_UNSUPPORTED;
+      const lp_step_op& prev = ops[i - 1];
+      if (s.slab_src == 0) {  // columns = SwiGLU outputs of the preceding up-projection, kept in shared memory
+        if (prev.kind != LP_STEP_LINEAR || !prev.keep_local || prev.epilogue != LP_EPI_SWIGLU || !prev.W || prev.W->N != 2 * W.K ||
+            s.dep != -1)
+          return LP_ERR_INVALID_ARG;
+      } else {  // columns = attention output of the CTA's head
+        if (prev.kind != LP_STEP_ATTENTION || gm->hs != 128 || W.K != gm->H * gm->hs || s.dep != i - 1) return LP_ERR_INVALID_ARG;
+        if (gm->H * std::max(1, std::min(DS_MAXP, grid / gm->H)) > grid) return LP_ERR_UNSUPPORTED;
+        dev[i - 1].hsync = n_ops + n_hsync * gm->H;  // H per-head counters behind the per-op ones
+        dev[i - 1].signal = 0;                       // nobody waits for the attention op grid-wide
+        d.hsync = dev[i - 1].hsync;
+        d.dep = -2 - d.hsync;                        // watcher: wait for the P CTAs of this CTA's head
+        ++n_hsync;
+      }
+      if (slab_meta[s.slab_src] && slab_meta[s.slab_src] != s.slab_meta) return LP_ERR_UNSUPPORTED;  // one layout per source kind
+      slab_meta[s.slab_src] = reinterpret_cast<const DsSlabMeta*>(s.slab_meta);
+      d.kind = DS_KIND_SLAB;
+      d.slab_img = reinterpret_cast<const unsigned char*>(s.slab_image);
+      d.slab_src = s.slab_src;
+      d.out = s.out;
+      d.bias = W.bias;
+      d.N = W.N;
+      d.K = W.K;
+      stage_stride = std::max(stage_stride, (DS_SLAB_MAXU + 1) * 1024);
+      continue;
+    }
     if (s.kind == LP_STEP_EXCHANGE) {
       if (!s.tp_buf_ptrs || !s.tp_pad_ptrs || !s.tp_state || !s.out || s.tp_size < 1 || s.tp_size > DS_MAX_TP || s.tp_rank < 0 ||
           s.tp_rank >= s.tp_size || s.dep < 0)
@@ -1644,6 +2031,10 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
     d.nks = (d.nkb + GS_KB - 1) / GS_KB;
     d.ntiles = W.N / GS_ROWS;
     d.x_attn = s.x_is_attention ? 1 : 0;
+    d.keep_local = s.keep_local ? 1 : 0;
+    if (d.keep_local && (s.epilogue != LP_EPI_SWIGLU || i + 1 >= n_ops || ops[i + 1].kind != LP_STEP_SLAB || ops[i + 1].slab_src != 0 ||
+                         (W.N / GS_ROWS + grid - 1) / grid > DS_SLAB_MAXU))
+      return LP_ERR_INVALID_ARG;
     // in-place residual (x += W . u): evenly split stages, atomic accumulation (see ds_stage_range)
     d.streamk = (s.epilogue == LP_EPI_RESIDUAL && s.residual == s.out) ? 1 : 0;
     stage_stride = std::max(stage_stride, (GS_KB * GS_BLK_BYTES + aux_stage + 1023) / 1024 * 1024);
@@ -1720,8 +2111,12 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
   h.smem = (size_t)ns * stage_stride + tail + 1024;
   h.ops_dev = reinterpret_cast<const DsOp*>(plan_dev);
   h.counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(plan_dev) + (size_t)n_ops * sizeof(DsOp));
-  h.deps = reinterpret_cast<const int*>(h.counters + n_ops);
-  h.err = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(plan_dev) + ((size_t)n_ops * (sizeof(DsOp) + 8) + 15) / 16 * 16);
+  h.ncounters = n_ops + n_hsync * gm->H;
+  h.deps = reinterpret_cast<const int*>(h.counters + h.ncounters);
+  h.err = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(plan_dev) + ((size_t)n_ops * sizeof(DsOp) + (size_t)(h.ncounters + n_ops) * 4 + 15) / 16 * 16);
+  if ((size_t)(reinterpret_cast<char*>(h.err) - reinterpret_cast<char*>(plan_dev)) + 32 > plan_bytes) return LP_ERR_WORKSPACE;
+  h.slab_meta[0] = slab_meta[0];
+  h.slab_meta[1] = slab_meta[1];
   h.pos = gm->pos;
   h.cosT = gm->cos;
   h.sinT = gm->sin;
@@ -1763,7 +2158,7 @@ int lp_decode_step(const lp_step_handle* handle, void* stream) {
   memcpy(&h, handle, sizeof(h));
   if (h.magic != DS_MAGIC) return LP_ERR_INVALID_ARG;
   int rc = launch(decode_step_prep_kernel, dim3((h.E + 1023) / 1024), dim3(256), 0, stream, h.idx, h.idx64, h.idx_offset, h.wte, h.wte_dtype,
-                  h.x0, h.E, h.counters, h.nops);
+                  h.x0, h.E, h.counters, h.ncounters);
   if (rc != LP_OK) return rc;
   DsParams p;
   p.ops = h.ops_dev;
@@ -1788,10 +2183,80 @@ int lp_decode_step(const lp_step_handle* handle, void* stream) {
   p.xs_bytes = h.xs_bytes;
   p.deps = h.deps;
   p.err = h.err;
+  p.slab_meta[0] = h.slab_meta[0];
+  p.slab_meta[1] = h.slab_meta[1];
+  p.ncounters = h.ncounters;
+  {
+    static const char* dbg_env = getenv("LP_DS_DEBUG");
+    p.dbg = dbg_env ? atoi(dbg_env) : 0;
+  }
   p.timeout_ns = h.timeout_ns;
   p.tp_state0 = h.tp_state0;
   p.tp_state1 = h.tp_state1;
   return h.hs == 128 ? ds_launch<128>(p, h, stream) : ds_launch<64>(p, h, stream);
+}
+
+int lp_decode_step_slab_layout(int src, int N, int K, int fc_tiles_or_heads, int hs, lp_slab_meta* meta, int max_ctas, int* n_ctas,
+                               size_t* image_bytes) {
+  using namespace lp;
+  if (!meta || !n_ctas || !image_bytes || N <= 0 || K <= 0 || src < 0 || src > 1 || fc_tiles_or_heads <= 0) return LP_ERR_INVALID_ARG;
+  const int grid = num_sms();
+  if (max_ctas < grid) return LP_ERR_WORKSPACE;
+  if (N % DS_SLAB_ROWS || K % 128) return LP_ERR_UNSUPPORTED;
+  long long off = 0;
+  for (int c = 0; c < grid; ++c) {
+    DsSlabMeta mt;
+    memset(&mt, 0, sizeof(mt));
+    if (src == 0) {
+      // the CTA's tiles of the up-projection (ds_stage_range, whole tiles): one 16-row SwiGLU tile = 8 outputs = one unit
+      const int tiles = fc_tiles_or_heads;
+      if (tiles * 8 != K) return LP_ERR_INVALID_ARG;
+      const int t0 = (int)((long long)tiles * c / grid), t1 = (int)((long long)tiles * (c + 1) / grid);
+      mt.unit0 = t0;
+      mt.nunits = t1 - t0;
+      mt.row0 = 0;
+      mt.nrb = mt.nunits > 0 ? N / DS_SLAB_ROWS : 0;
+      if (mt.nrb & 1) return LP_ERR_UNSUPPORTED;  // the consumers take the stages in pairs
+    } else {
+      // CTA c = (head c / P, sequence split c % P): the head's hs columns, rows split over its P CTAs
+      const int H = fc_tiles_or_heads;
+      if (hs != 128 || H * hs != K || H > grid) return LP_ERR_UNSUPPORTED;
+      const int P = std::max(1, std::min(DS_MAXP, grid / H));
+      if ((N / P) % (2 * DS_SLAB_ROWS)) return LP_ERR_UNSUPPORTED;  // the consumers take the stages in pairs
+      if (c < H * P) {
+        mt.unit0 = (c / P) * (hs / 8);
+        mt.nunits = hs / 8;
+        mt.row0 = (c % P) * (N / P);
+        mt.nrb = N / P / DS_SLAB_ROWS;
+      }
+    }
+    if (mt.nunits > DS_SLAB_MAXU) return LP_ERR_UNSUPPORTED;
+    if (mt.nrb > 0) {
+      mt.group_a = mt.unit0 / 16;
+      const int boundary = (mt.group_a + 1) * 16;  // first unit of the next 128-column scale group
+      mt.units_a = std::min(mt.nunits, boundary - mt.unit0);
+      mt.nseg = mt.units_a < mt.nunits ? 2 : 1;
+      mt.stage_bytes = (mt.nunits + mt.nseg) * 1024;
+      mt.off = off;
+      off += (long long)mt.nrb * mt.stage_bytes;
+    }
+    memcpy(&meta[c], &mt, sizeof(mt));
+  }
+  *n_ctas = grid;
+  *image_bytes = (size_t)off;
+  return LP_OK;
+}
+
+int lp_decode_step_slab_build(const lp_weight* W, const lp_slab_meta* meta_dev, int n_ctas, void* image, void* stream) {
+  using namespace lp;
+  if (!W || !meta_dev || !image || n_ctas <= 0) return LP_ERR_INVALID_ARG;
+  if (W->fmt != LP_W_INT4 || W->group != 128 || !(W->flags & LP_WF_AUX_PACKED) || !W->aux2 || !W->w) return LP_ERR_UNSUPPORTED;
+  const int row_words = (int)(lp_int4_row_bytes(W->K) / 4);
+  slab_build_kernel<<<n_ctas, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint32_t*>(W->w), row_words, reinterpret_cast<const uint32_t*>(W->aux2), (W->K + 127) / 128,
+      reinterpret_cast<const DsSlabMeta*>(meta_dev), reinterpret_cast<uint32_t*>(image));
+  LP_CUDA_TRY(cudaGetLastError());
+  return LP_OK;
 }
 
 int lp_decode_step_status(const lp_step_handle* handle, int32_t info[8]) {

@@ -136,6 +136,7 @@ class Engine:
         self.use_step_kernel = os.environ.get("LP_DECODE_STEP", "1") != "0" and bool(getattr(model, "use_step_kernel", True))
         self._steps: Dict[Tuple, Optional[Tuple]] = {}
         self._flag = torch.zeros(1, dtype=torch.int32).pin_memory()  # mapped host word written by lp_validate_inputs
+        self._slabs = None  # fused column->row pairs of the step kernel: None = not decided yet, False = not applicable
 
     # ------------------------------------------------------------------ bookkeeping
     def set_rope(self, rope) -> None:
@@ -155,6 +156,46 @@ class Engine:
         self._graphs.clear()
         self._steps.clear()
 
+    # ------------------------------------------------------------------ slab images of the fused pairs (load time)
+    def _build_slabs(self):
+        """Sequential-residual SwiGLU models with GPTQ int4 g128 weights (bf16-exact scales) and 128-wide heads — Llama-2 —
+        run attention -> attn.proj and fc -> mlp.proj as column->row pairs INSIDE each CTA of the step kernel (SLAB ops): the
+        projections are re-laid out once into per-CTA K-slab images (lp_decode_step_slab_build).  LP_DS_FUSE=0 keeps the five-op
+        layer (A/B measurements).  Returns (meta_mlp, meta_att) device tensors, or False."""
+        if self._slabs is not None:
+            return self._slabs
+        self._slabs = False
+        cfg, lib = self.cfg, self.lib
+        if (os.environ.get("LP_DS_FUSE", "1") == "0" or self.tp is not None or cfg.parallel_residual
+                or self.act != _lib.LP_EPI_SWIGLU or cfg.head_size != 128):
+            return False
+        for L in self.layers:
+            for m in (L.proj, L.mlp_proj):
+                if (m.fmt != _lib.LP_W_INT4 or m.rec.group != 128 or not (m.rec.flags & _lib.LP_WF_AUX_PACKED) or not m.rec.aux2
+                        or m.rec.bias):
+                    return False
+            if L.fc.fmt != _lib.LP_W_INT4 or L.fc.N != 2 * L.mlp_proj.K:
+                return False
+        E, I, H = cfg.n_embd, cfg.intermediate_size, cfg.n_head
+        metas = []
+        for src, (N, K, arg, hs) in enumerate(((E, I, (2 * I) // 16, 0), (E, E, H, cfg.head_size))):
+            rec = (_lib.LpSlabMeta * 256)()
+            n, nbytes = ctypes.c_int(0), ctypes.c_size_t(0)
+            rc = lib.lp_decode_step_slab_layout(src, N, K, arg, hs, rec, 256, ctypes.byref(n), ctypes.byref(nbytes))
+            if rc == -2:
+                return False
+            _lib.check(rc, "lp_decode_step_slab_layout")
+            raw = bytes(rec)[: n.value * ctypes.sizeof(_lib.LpSlabMeta)]
+            metas.append((torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device), n.value, nbytes.value))
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        for L in self.layers:
+            for name, W, (meta, n, nbytes) in (("mlp_slab", L.mlp_proj, metas[0]), ("att_slab", L.proj, metas[1])):
+                img = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.device)
+                _lib.check(lib.lp_decode_step_slab_build(W.ref, meta.data_ptr(), n, img.data_ptr(), stream), "lp_decode_step_slab_build")
+                setattr(L, name, img)
+        self._slabs = (metas[0][0], metas[1][0])
+        return self._slabs
+
     # ------------------------------------------------------------------ batch-1 decode step as one persistent kernel
     def _step_plan(self, b: Dict[str, torch.Tensor], idx_ptr: int, idx64: int, idx_off: Optional[int], pos_ptr: int, caches):
         """Op table of one decode step (same op order as `_run`) -> lp_decode_step_plan.  Returns the handle, or None when the
@@ -171,9 +212,10 @@ class Engine:
         x, qkv, xmid, u, logits = (b[k].data_ptr() for k in ("x", "qkv", "xmid", "u", "logits"))
         ops: List[_lib.LpStepOp] = []
 
-        def linear(W, src, norm, epi, res, dst, dep, from_attn=False):
+        def linear(W, src, norm, epi, res, dst, dep, from_attn=False, keep_local=False):
             op = _lib.LpStepOp()
             op.kind, op.dep, op.W = _lib.LP_STEP_LINEAR, dep, ctypes.pointer(W.rec)
+            op.keep_local = int(keep_local)
             op.x, op.x_is_attention = (None if from_attn else src), int(from_attn)
             op.norm_kind = -1
             if norm is not None:
@@ -189,6 +231,15 @@ class Engine:
             ops.append(op)
             return len(ops) - 1
 
+        def slab(W, src_kind, image, meta, dep):
+            """x += W[:, columns this CTA produced itself] . v: the second half of a column->row pair (SLAB op)."""
+            op = _lib.LpStepOp()
+            op.kind, op.dep, op.W, op.norm_kind = _lib.LP_STEP_SLAB, dep, ctypes.pointer(W.rec), -1
+            op.slab_src, op.slab_image, op.slab_meta, op.out = src_kind, image.data_ptr(), meta.data_ptr(), x
+            ops.append(op)
+            return len(ops) - 1
+
+        slabs = self._build_slabs()
         tp = self.tp
         n_exch = [0]
 
@@ -224,6 +275,13 @@ class Engine:
                 if cfg.shared_attention_norm:
                     return self._steps.setdefault(key, None)
                 i_att = attention(li, i_qkv)
+                if slabs:
+                    # three grid-wide dependencies per layer instead of five: the head's CTAs apply attn.proj to their own head,
+                    # every CTA applies mlp.proj to its own SwiGLU outputs; both add partial rows into x
+                    i_proj = slab(L.proj, 1, L.att_slab, slabs[1], i_att)
+                    linear(L.fc, x, (L.n2_w, L.n2_b), self.act, None, u, i_proj, keep_local=True)
+                    last = slab(L.mlp_proj, 0, L.mlp_slab, slabs[0], -1)
+                    continue
                 i_proj = row_parallel(L.proj, None, i_att, from_attn=True)
                 i_fc = linear(L.fc, x, (L.n2_w, L.n2_b), self.act, None, u, i_proj)
                 last = row_parallel(L.mlp_proj, u, i_fc)

@@ -35,9 +35,11 @@ def _stream() -> int:
 # ------------------------------------------------------------------------------------------------
 # GPTQ int4
 # ------------------------------------------------------------------------------------------------
-def rtn_int4_params(w: torch.Tensor, tile_cols: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+def rtn_int4_params(w: torch.Tensor, tile_cols: int, scale_dtype: Optional[torch.dtype] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Round-to-nearest int4 on the reference's asymmetric min/max grid (quantize/gptq.py:313-347), per output row
-    and per group of `tile_cols` columns.  Returns (q uint8 (N, K) values 0..15, scales (N, n_tiles), zeros)."""
+    and per group of `tile_cols` columns.  Returns (q uint8 (N, K) values 0..15, scales (N, n_tiles), zeros).
+    `scale_dtype`: the dtype the scales are STORED in (the reference keeps them in the model dtype, gptq.py:223-226 — bf16 under
+    `bf16-true`); they are rounded to it before the weights are quantised against them, so q, scale, zero stay self-consistent."""
     N, K = w.shape
     if tile_cols == -1:
         tile_cols = K
@@ -55,6 +57,8 @@ def rtn_int4_params(w: torch.Tensor, tile_cols: int) -> Tuple[torch.Tensor, torc
     lo = torch.where(dead, torch.full_like(lo, -1.0), lo)
     hi = torch.where(dead, torch.full_like(hi, 1.0), hi)
     scales = (hi - lo) / 15
+    if scale_dtype is not None:
+        scales = scales.to(scale_dtype).float()
     zeros = torch.round(-lo / scales)
     q = torch.clamp(torch.round(g / scales[:, :, None]) + zeros[:, :, None], 0, 15).to(torch.uint8)
     return q.view(N, -1)[:, :K].contiguous(), scales, zeros
@@ -110,9 +114,9 @@ class ColBlockQuantizedLinear(torch.nn.Module):
         q = weight.clamp_(min=0, max=15).to(dtype=torch.uint8)
         self.quant_weight.copy_(q[:, 0::2] | (q[:, 1::2] << 4))
 
-    def quantize_rtn_(self, weight: torch.Tensor) -> "ColBlockQuantizedLinear":
+    def quantize_rtn_(self, weight: torch.Tensor, scale_dtype: Optional[torch.dtype] = None) -> "ColBlockQuantizedLinear":
         """Fill the buffers from a float weight by round-to-nearest on the reference grid."""
-        q, scales, zeros = rtn_int4_params(weight.to(self.quant_weight.device), self.tile_cols)
+        q, scales, zeros = rtn_int4_params(weight.to(self.quant_weight.device), self.tile_cols, scale_dtype)
         self.scales.copy_(scales)
         self.zeros.copy_(zeros)
         self.quant_weight.copy_(q[:, 0::2] | (q[:, 1::2] << 4))

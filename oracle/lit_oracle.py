@@ -239,9 +239,11 @@ def generate(model, idx: Tensor, max_returned_tokens: int, max_seq_length: Optio
 # ----------------------------------------------------------------------------------------------
 # weight-only quantisation formats
 # ----------------------------------------------------------------------------------------------
-def gptq_find_params(w: Tensor, bits: int = 4) -> Tuple[Tensor, Tensor]:
+def gptq_find_params(w: Tensor, bits: int = 4, scale_dtype: Optional[torch.dtype] = None) -> Tuple[Tensor, Tensor]:
     """Asymmetric per-row min/max grid of one column tile: quantize/gptq.py:317-347
-    (perchannel=True, sym=False).  Returns (scale, zero) of shape (rows, 1); zero is an integer-valued float."""
+    (perchannel=True, sym=False).  Returns (scale, zero) of shape (rows, 1); zero is an integer-valued float.
+    `scale_dtype`: the dtype the scale buffer is stored in (the model dtype, gptq.py:223-226: bf16 under bf16-true); the scale is
+    rounded to it BEFORE the zero point and the weights are quantised against it, so (q, scale, zero) stay self-consistent."""
     maxq = 2 ** bits - 1
     z = torch.zeros(w.shape[0])
     lo = torch.minimum(w.min(1)[0], z)
@@ -249,6 +251,8 @@ def gptq_find_params(w: Tensor, bits: int = 4) -> Tuple[Tensor, Tensor]:
     dead = (lo == 0) & (hi == 0)
     lo[dead], hi[dead] = -1, +1
     scale = (hi - lo) / maxq
+    if scale_dtype is not None:
+        scale = scale.to(scale_dtype).float()
     zero = torch.round(-lo / scale)
     return scale.reshape(-1, 1), zero.reshape(-1, 1)
 
@@ -270,7 +274,7 @@ def gptq_pack(w: Tensor, scales: Tensor, zeros: Tensor, tile_cols: int, bits: in
     return packed
 
 
-def gptq_rtn_quantize(w: Tensor, tile_cols: int, bits: int = 4):
+def gptq_rtn_quantize(w: Tensor, tile_cols: int, bits: int = 4, scale_dtype: Optional[torch.dtype] = None):
     """Round-to-nearest group quantiser built from the reference's own grid (find_params_weight) and
     its own quantise step q = clamp(round(w/scale) + zero, 0, maxq) (gptq.py:313-315), packed with the
     reference's nibble layout.  (The GPTQ error-propagation solver, gptq.py:365-445, is offline and out
@@ -284,7 +288,7 @@ def gptq_rtn_quantize(w: Tensor, tile_cols: int, bits: int = 4):
     q = torch.empty_like(w, dtype=torch.float32)
     for j in range(n_tiles):
         sl = slice(j * tile_cols, (j + 1) * tile_cols)
-        s, z = gptq_find_params(w[:, sl].float(), bits)
+        s, z = gptq_find_params(w[:, sl].float(), bits, scale_dtype)
         scales[:, j : j + 1], zeros[:, j : j + 1] = s, z
         q[:, sl] = torch.clamp(torch.round(w[:, sl].float() / s) + z, 0, maxq)
     per = 8 // bits

@@ -32,7 +32,7 @@ def bf16_model(kw, seed):
     return cfg, m, om
 
 
-def int4_model(kw, seed, tile=128):
+def int4_model(kw, seed, tile=128, scale_dtype=None):
     cfg = lp.Config(**kw)
     fsd = O.random_state_dict(cfg, seed=seed, perturb_norm=True)
     with lp.quantization("gptq.int4", gptq_tile_cols=tile):
@@ -40,7 +40,7 @@ def int4_model(kw, seed, tile=128):
     qsd = {}
     for k, v in fsd.items():
         if v.dim() == 2 and "wte" not in k:
-            packed, scales, zeros = O.gptq_rtn_quantize(v, tile)
+            packed, scales, zeros = O.gptq_rtn_quantize(v, tile, scale_dtype=scale_dtype)
             base = k[: -len(".weight")]
             qsd[base + ".quant_weight"], qsd[base + ".scales"], qsd[base + ".zeros"] = packed, scales, zeros
         else:
@@ -55,7 +55,7 @@ def step_kernel_used(m) -> bool:
     return any(v is not None for v in m._engine._steps.values())
 
 
-def teacher_forced(m, om, cfg, prompt_len, steps, max_seq, seed=5):
+def teacher_forced(m, om, cfg, prompt_len, steps, max_seq, seed=5, prompt_atol=5e-4):
     g = torch.Generator().manual_seed(seed)
     toks = torch.randint(0, cfg.padded_vocab_size, (prompt_len + steps,), generator=g)
     pos = torch.arange(prompt_len)
@@ -63,7 +63,7 @@ def teacher_forced(m, om, cfg, prompt_len, steps, max_seq, seed=5):
     got = m._forward_impl(toks[:prompt_len].view(1, -1).to(DEV), max_seq, pos.to(DEV), raw_logits=True)[0, -1].float().cpu()
     # the 60-row prompt runs on the swap-AB GEMM with two bf16 terms per activation (2^-17 relative per product) and atomically
     # accumulated split-K partials (order varies from run to run): observed 1.2e-4 .. 2.0e-4; north star 2e-2
-    torch.testing.assert_close(got, want, rtol=0, atol=5e-4)
+    torch.testing.assert_close(got, want, rtol=0, atol=prompt_atol)
     worst = 0.0
     for i in range(prompt_len, prompt_len + steps):
         p = torch.tensor([i])
@@ -294,3 +294,48 @@ def test_out_of_range_inputs_raise_like_the_reference():
         m(good[:, :1], 64, torch.tensor([10], device=DEV))
     m(good[:, :1], 64, torch.tensor([10], device=DEV))
     m._engine.check_step_health()
+
+
+# Llama-style, hs 128, wide enough for the fused column->row pairs (SLAB ops): E / P = 512 rows (one stage pair) per head CTA;
+# I = 2816 gives the 148 CTAs 2-3 SwiGLU units each, some of them straddling a 128-column scale group; I = 1024 leaves CTAs
+# without any unit; I = 18944 is the 16-unit maximum
+LLAMA_SLAB = dict(block_size=256, vocab_size=320, padding_multiple=64, n_layer=3, n_head=16, n_embd=2048, rotary_percentage=1.0,
+                  parallel_residual=False, bias=False, _norm_class="RMSNorm", _mlp_class="LLaMAMLP", intermediate_size=2816)
+
+
+def slab_ops_used(m) -> bool:
+    return bool(m._engine._slabs)
+
+
+@pytest.mark.parametrize("inter", [2816, 1024, 18944], ids=["2-3_units", "some_ctas_empty", "16_units"])
+def test_step_kernel_fused_slabs_int4(inter):
+    """GPTQ int4 g128 with bf16-exact scales (the storage of a bf16 checkpoint): attention -> attn.proj and fc -> mlp.proj run as
+    column->row pairs inside each CTA (SLAB ops).  Teacher-forced logits against the oracle, across key-tile and split boundaries."""
+    cfg, m, om = int4_model(dict(LLAMA_SLAB, intermediate_size=inter, n_layer=2 if inter > 4096 else 3), 65, scale_dtype=torch.bfloat16)
+    # (the 40-row prompt goes through the 2-term tensor-core GEMM: its error grows with the width, 6e-4 observed at E = 2048)
+    teacher_forced(m, om, cfg, prompt_len=40, steps=70, max_seq=256, prompt_atol=2e-3)
+    assert step_kernel_used(m) and slab_ops_used(m)
+    m._engine.check_step_health()
+
+
+def test_step_kernel_fused_slabs_match_unfused(monkeypatch):
+    """Same weights through the fused (3 grid dependencies per layer) and the five-op table (LP_DS_FUSE=0): greedy tokens identical
+    to the oracle on both, logits of the two within 2e-4 of each other."""
+    cfg, m, om = int4_model(LLAMA_SLAB, 66, scale_dtype=torch.bfloat16)
+    prompt = torch.randint(0, cfg.padded_vocab_size, (12,), generator=torch.Generator().manual_seed(7)).to(torch.int32)
+    want = O.generate(om, prompt, 100, 100, top_k=1, argmax_ties=True)
+    out = lp.generate(m, prompt.to(DEV), 100, 100, top_k=1)
+    assert torch.equal(out.cpu(), want), f"first mismatch at {int((out.cpu() != want).nonzero()[0])}"
+    assert slab_ops_used(m)
+    monkeypatch.setenv("LP_DS_FUSE", "0")
+    cfg2, m2, _ = int4_model(LLAMA_SLAB, 66, scale_dtype=torch.bfloat16)
+    out2 = lp.generate(m2, prompt.to(DEV), 100, 100, top_k=1)
+    assert torch.equal(out2.cpu(), want) and step_kernel_used(m2) and not slab_ops_used(m2)
+    for mm in (m, m2):
+        mm.reset_cache()
+        mm._forward_impl(want[:60].view(1, -1).to(DEV), 100, torch.arange(60, device=DEV), last_only=True, raw_logits=True)
+    for i in range(60, 70):
+        p = torch.tensor([i], device=DEV)
+        a = m._forward_impl(want[i].view(1, 1).to(DEV), 100, p, raw_logits=True)[0, -1].float().cpu()
+        b = m2._forward_impl(want[i].view(1, 1).to(DEV), 100, p, raw_logits=True)[0, -1].float().cpu()
+        torch.testing.assert_close(a, b, rtol=0, atol=2e-4)

@@ -97,8 +97,13 @@ def test_stablelm3b_widths_2k_context_and_wrap():
     _decode_and_compare(m, om, cfg, start, 16, max_seq)
 
 
-def test_llama7b_int4_g128_widths_2k_context_and_wrap():
-    """The north-star configuration's shapes: GPTQ int4, group 128, K 11008 (86 groups) in mlp.proj, 32 MHA heads -> 4 splits."""
+@pytest.mark.parametrize("fused", [True, False], ids=["fused_slabs", "five_op_layer"])
+def test_llama7b_int4_g128_widths_2k_context_and_wrap(fused, monkeypatch):
+    """The north-star configuration's shapes: GPTQ int4, group 128, K 11008 (86 groups) in mlp.proj, 32 MHA heads -> 4 splits.
+    Scales bf16-exact as in a bf16 checkpoint.  `fused`: attention -> attn.proj and fc -> mlp.proj as column->row pairs inside the
+    CTAs (the default, what bench.py times); otherwise the five-op layer (LP_DS_FUSE=0: K = 11008 staged through 86 groups)."""
+    if not fused:
+        monkeypatch.setenv("LP_DS_FUSE", "0")
     cfg = lp.Config.from_name("Llama-2-7b-hf", n_layer=2)
     fsd = O.random_state_dict(cfg, seed=73, perturb_norm=True)
     with lp.quantization("gptq.int4", gptq_tile_cols=128):
@@ -106,7 +111,7 @@ def test_llama7b_int4_g128_widths_2k_context_and_wrap():
     qsd, dense = {}, {}
     for k, v in fsd.items():
         if v.dim() == 2 and "wte" not in k:
-            packed, scales, zeros = O.gptq_rtn_quantize(v, 128)
+            packed, scales, zeros = O.gptq_rtn_quantize(v, 128, scale_dtype=torch.bfloat16)
             base = k[: -len(".weight")]
             qsd[base + ".quant_weight"], qsd[base + ".scales"], qsd[base + ".zeros"] = packed, scales, zeros
             dense[k] = O.gptq_dequant(packed, scales, zeros, torch.float32, tile_cols=128)  # == the per-call dequant of O.linear
@@ -119,6 +124,7 @@ def test_llama7b_int4_g128_widths_2k_context_and_wrap():
     max_seq, start = 2048, 2038
     _install_kv(m, om, cfg, _synthetic_kv(cfg, cfg.n_query_groups, max_seq, start, 173), max_seq)
     _decode_and_compare(m, om, cfg, start, 16, max_seq)
+    assert bool(m._engine._slabs) == fused
 
 
 def test_llama70b_tp8_local_shard_2k_context_and_wrap():

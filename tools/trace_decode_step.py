@@ -34,6 +34,12 @@ lib.lp_debug_step_trace(None)
 t = trace.cpu().double()
 par = cfg.parallel_residual
 names = ["qkv", "fc", "attn", "proj", "mlp.proj"] if par else ["qkv", "attn", "proj", "fc", "mlp.proj"]
+eng = model._get_engine(dev)
+if eng._slabs:
+    names = ["qkv", "attn", "proj*slab", "fc", "mlp*slab"]
+import ctypes  # noqa: E402
+ent = next(v for v in eng._steps.values() if v is not None)
+print("cooperative launch:", lib.lp_decode_step_cooperative(ctypes.byref(ent[0])), " fused slabs:", bool(eng._slabs))
 first = 5 * layer
 t0 = t[first, :, 0].min()
 print(f"{wl}: layers {layer}-{layer + 1}; us relative to the first CTA entering {names[0]}({layer}); [min,max] over CTAs")
