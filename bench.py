@@ -204,7 +204,7 @@ def run_workload(workload, steps, warmup, device, rank=0, world=1, with_e2e=True
     for k, v in model.kv_caches:
         k[:, :, :start].normal_(0, 1)
         v[:, :, :start].normal_(0, 1)
-    gen = torch.Generator(device="cpu").manual_seed(1 + rank)
+    gen = torch.Generator(device="cpu").manual_seed(1 + (0 if tp else rank))  # tensor parallel: ONE sequence over all ranks
     tok0 = torch.randint(0, cfg.vocab_size, (B, 1), generator=gen)
 
     def sync_barrier():

@@ -839,6 +839,10 @@ __device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint3
   const int lane = threadIdx.x & 31;
   const int rr = lane & 15, half = lane >> 4;
   int gt = 0;
+  // tensor parallel: epoch counters of the two exchange slots as of the start of this step (the senders publish epoch + use + 1)
+  unsigned int tp_epoch[2] = {0u, 0u};
+  if (p.tp_state0) tp_epoch[0] = *reinterpret_cast<volatile unsigned int*>(p.tp_state0);
+  if (p.tp_state1) tp_epoch[1] = *reinterpret_cast<volatile unsigned int*>(p.tp_state1);
   asm volatile("bar.sync 4, %0;\n" ::"n"(DS_OPEND_THREADS) : "memory");  // record of op 0 is in shared memory
   for (int op = 0; op < p.nops; ++op) {
     const DsOp& o = s_ops[op % DS_NREC];
@@ -846,6 +850,9 @@ __device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint3
     const int hsync = o.kind == DS_KIND_LINEAR || o.kind == DS_KIND_SLAB ? -1 : o.hsync;
     if (o.kind == DS_KIND_LINEAR) {
       const int nks = o.nks, fmt = o.fmt, split = o.split, epi = o.epi, streamk = o.streamk, keep_local = o.keep_local;
+      const int push = o.tp_size;  // > 0: row-parallel sender of a tensor-parallel exchange (see ds_exchange)
+      const unsigned long long* push_bufs = o.tp_bufs;
+      const unsigned long long push_off = o.tp_buf_off;
       const float* bias = o.bias;
       const float* residual = o.residual;
       float* out = o.out;
@@ -895,6 +902,13 @@ __device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint3
             if (keep_local) s_loc[(row >> 1) - loc0] = silu(y) * other;  // consumed by this CTA's slab op, never leaves the SM
             else out[row >> 1] = silu(y) * other;
           }
+        } else if (push > 0) {
+          // this rank's partial of 16 rows -> slot [s][rank] of every rank's buffer (64 contiguous bytes per peer)
+          if (half == 0) {
+#pragma unroll
+            for (int r = 0; r < DS_MAX_TP; ++r)
+              if (r < push) reinterpret_cast<float*>(push_bufs[r] + push_off)[row] = y;
+          }
         } else if (half == 0) {
           if (epi == LP_EPI_GELU) y = gelu_erf(y);
           else if (epi == LP_EPI_RESIDUAL) y = __ldcg(residual + row) + y;
@@ -907,7 +921,23 @@ __device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint3
     // of this CTA (ordered before by the barrier).  The ~1 us of that fence is off the consumers' path: they are already staging
     // the next op.
     asm volatile("bar.sync 4, %0;\n" ::"n"(DS_OPEND_THREADS) : "memory");
-    if (e == 0 && lane == 0) {
+    if (e == 0 && lane == 0 && o.kind == DS_KIND_LINEAR && o.tp_size > 0) {
+      // sender side of the push exchange: the remote stores of THIS CTA are made visible system-wide, then the CTA arrives; the
+      // last one to arrive has thereby observed everybody's fence and publishes the epoch to every rank (itself included)
+      __threadfence_system();
+      unsigned old;
+      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;\n" : "=r"(old) : "l"(p.counters + op) : "memory");
+      if (old == gridDim.x - 1) {
+        const unsigned int epoch = (o.tp_state == p.tp_state1 ? tp_epoch[1] : tp_epoch[0]) + (unsigned)o.tp_use + 1u;
+        // ONE system-scope fence, then the tp flag stores back to back (relaxed): a st.release.sys per peer would pay the fence
+        // — an NVLink round trip — tp times in a row (measured: 16 us per exchange at tp = 8)
+        __threadfence_system();
+        for (int r = 0; r < o.tp_size; ++r) {
+          unsigned int* flag = reinterpret_cast<unsigned int*>(o.tp_pads[r]) + o.tp_pad_base + o.tp_rank;
+          asm volatile("st.relaxed.sys.global.u32 [%0], %1;\n" ::"l"(flag), "r"(epoch) : "memory");
+        }
+      }
+    } else if (e == 0 && lane == 0) {
       if (signal) ds_red_release(p.counters + op);
       // attention feeding a slab: the P CTAs of a head only wait for each other (per-head counter), not for the grid
       if (hsync >= 0 && (int)blockIdx.x < p.H * p.P) ds_red_release(p.counters + hsync + blockIdx.x / p.P);
@@ -1364,43 +1394,44 @@ __device__ __forceinline__ void ds_slab(const DsParams& p, const DsOp& o, const 
 }
 
 // ------------------------------------------------------------------------------------------------ tensor-parallel exchange op
-// One-shot all-reduce over NVLink peer memory inside the step kernel (the protocol of tp_allreduce.cu): the preceding linear op
-// wrote this rank's partial into its slot of the symmetric buffer; CTA 0 publishes the slot's next epoch to every peer, every
-// CTA waits until all peers have published it, then reduces ITS slice of the row (n / #CTAs floats) over all ranks in rank order
-// — bit-identical on every rank — adds the residual and stores it locally.  The epoch counter is the one the per-op kernel uses,
-// so prefill (per-op path) and decode (this kernel) can alternate; it is advanced once per step by the last exchange of a slot.
+// One-shot all-reduce over NVLink peer memory inside the step kernel, PUSH style.  The row-parallel linear op before it is the
+// sender: its tile epilogue stores every finished 16-row piece of this rank's partial straight into slot [s][rank] of EVERY rank's
+// symmetric buffer (remote st.global over NVLink, overlapped with the rest of the op), and the LAST CTA to finish the op — it sees
+// all others through the op's arrival counter, each of which fenced at system scope before arriving — publishes the slot's epoch
+// in every peer's signal pad (st.release.sys).  This op is the receiver: it waits on LOCAL flags (one per source rank), then every
+// CTA reduces ITS slice of the row (n / #CTAs floats) over the tp partials found in LOCAL memory, in rank order — bit-identical on
+// every rank — adds the residual and stores it.  One NVLink traversal on the critical path (the flag; the data went ahead of it)
+// instead of three (flag, remote-load request, remote-load reply).  Two slots alternate: a rank can be at most one exchange ahead of
+// its slowest peer, and a peer publishes exchange k + 1 only after all its CTAs finished reading exchange k.  The epoch counter of a
+// slot is advanced once per step by its last exchange; buffers, flags and counters of this protocol are disjoint from those of
+// lp_tp_allreduce_residual (the per-op pull kernel of prefill / batches), so the two may alternate freely.
 __device__ __forceinline__ void ds_exchange(const DsParams& p, const DsOp& o, int op, unsigned int epoch0) {
   const int tid = threadIdx.x, tp = o.tp_size;
   const unsigned int epoch = epoch0 + (unsigned)o.tp_use + 1u;
   if (tid < tp) {
-    if (blockIdx.x == 0) {  // publish to peer `tid` (and to ourselves): this rank's partial is complete (dependency wait above)
-      __threadfence_system();
-      unsigned int* flag = reinterpret_cast<unsigned int*>(o.tp_pads[tid]) + o.tp_pad_base + o.tp_rank;
-      asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(flag), "r"(epoch) : "memory");
-    }
     const unsigned int* mine = reinterpret_cast<const unsigned int*>(o.tp_pads[o.tp_rank]) + o.tp_pad_base + tid;
     unsigned int v, it = 0;
     const unsigned long long t0 = gs_now();
-    do {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(mine) : "memory");
+    do {  // relaxed polls of the local pad word, one acquire fence at the end
+      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(mine) : "memory");
       if ((int)(v - epoch) < 0 && p.timeout_ns) {  // a peer GPU that never publishes: watchdog (ds_report)
         const bool expired = gs_now() - t0 > p.timeout_ns;
         if (expired) ds_report(p.err, DS_ERR_EXCHANGE_TIMEOUT, op, tid, v);
         if (expired || ((++it & 15u) == 0 && ds_ld_relaxed(p.err) != 0u)) break;
       }
     } while ((int)(v - epoch) < 0);
+    asm volatile("fence.acq_rel.sys;\n" ::: "memory");
   }
   gs_bar_consumers();
   const int n4 = o.N / 4;
+  const float4* local = reinterpret_cast<const float4*>(o.tp_bufs[o.tp_rank] + o.tp_buf_off);  // [tp][N] partials of this slot
   const int i0 = (int)((long long)n4 * blockIdx.x / gridDim.x), i1 = (int)((long long)n4 * (blockIdx.x + 1) / gridDim.x);
   for (int i = i0 + tid; i < i1; i += DS_CTHREADS) {
     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < DS_MAX_TP; ++r) {
       if (r < tp) {
-        const float4* src = reinterpret_cast<const float4*>(o.tp_bufs[r] + o.tp_buf_off) + i;
-        float4 v;
-        asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src));
+        const float4 v = __ldcg(local + (size_t)r * n4 + i);  // written by rank r over NVLink: read at L2, never through L1
         if (r == 0) sum = v;
         else { sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w; }
       }
@@ -1934,6 +1965,7 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
           s.tp_rank >= s.tp_size || s.dep < 0)
         return LP_ERR_INVALID_ARG;
       if (gm->E % 4 || s.tp_buf_offset % 16) return LP_ERR_UNSUPPORTED;
+      if (i == 0 || ops[i - 1].kind != LP_STEP_LINEAR || ops[i - 1].tp_size != s.tp_size || s.dep != i - 1) return LP_ERR_INVALID_ARG;
       d.kind = DS_KIND_EXCHANGE;
       d.tp_bufs = reinterpret_cast<const unsigned long long*>(s.tp_buf_ptrs);
       d.tp_pads = reinterpret_cast<const unsigned long long*>(s.tp_pad_ptrs);
@@ -2032,6 +2064,31 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
     d.ntiles = W.N / GS_ROWS;
     d.x_attn = s.x_is_attention ? 1 : 0;
     d.keep_local = s.keep_local ? 1 : 0;
+    if (s.tp_size > 0) {
+      // row-parallel SENDER of a push exchange: the tile epilogue stores this rank's partial into slot [s][rank] of every rank's
+      // symmetric buffer (tp_buf_offset addresses that slot) and the last CTA publishes the epoch (see ds_exchange)
+      if (!s.tp_buf_ptrs || !s.tp_pad_ptrs || !s.tp_state || s.tp_size > DS_MAX_TP || s.tp_rank < 0 || s.tp_rank >= s.tp_size ||
+          s.epilogue != LP_EPI_NONE || i + 1 >= n_ops || ops[i + 1].kind != LP_STEP_EXCHANGE || ops[i + 1].tp_state != s.tp_state)
+        return LP_ERR_INVALID_ARG;
+      if (s.tp_buf_offset % 16) return LP_ERR_UNSUPPORTED;
+      d.tp_bufs = reinterpret_cast<const unsigned long long*>(s.tp_buf_ptrs);
+      d.tp_pads = reinterpret_cast<const unsigned long long*>(s.tp_pad_ptrs);
+      d.tp_state = reinterpret_cast<unsigned int*>(s.tp_state);
+      d.tp_buf_off = s.tp_buf_offset;
+      d.tp_pad_base = s.tp_pad_base;
+      d.tp_rank = s.tp_rank;
+      d.tp_size = s.tp_size;
+      // same use index as the exchange that follows (which takes and advances it)
+      if (!tp_state[0] || tp_state[0] == d.tp_state) {
+        tp_state[0] = d.tp_state;
+        d.tp_use = tp_uses[0];
+      } else if (!tp_state[1] || tp_state[1] == d.tp_state) {
+        tp_state[1] = d.tp_state;
+        d.tp_use = tp_uses[1];
+      } else {
+        return LP_ERR_UNSUPPORTED;
+      }
+    }
     if (d.keep_local && (s.epilogue != LP_EPI_SWIGLU || i + 1 >= n_ops || ops[i + 1].kind != LP_STEP_SLAB || ops[i + 1].slab_src != 0 ||
                          (W.N / GS_ROWS + grid - 1) / grid > DS_SLAB_MAXU))
       return LP_ERR_INVALID_ARG;

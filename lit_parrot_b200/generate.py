@@ -115,6 +115,53 @@ def _generate_on_device(model, idx, max_returned_tokens, max_seq_length, tempera
     return out
 
 
+def device_token_stream(model, idx, max_returned_tokens, max_seq_length, temperature, top_k):
+    """The tokens of `_generate_on_device` one at a time (host ints): the streaming form the chat front end needs
+    (chat/base.py:57-95).  Same prefill, same captured decode step; the sampled id is read back after every replay."""
+    if not temperature > 0:
+        raise ValueError("temperature must be > 0 (use top_k=1 for greedy decoding)")
+    cfg = model.config
+    if max_returned_tokens > cfg.block_size:
+        raise IndexError(f"max_returned_tokens {max_returned_tokens} exceeds the RoPE table (block_size {cfg.block_size})")
+    device = idx.device
+    T = idx.size(0)
+    logits = model._forward_impl(idx.view(1, -1), max_seq_length, torch.arange(0, T, device=device), last_only=True, raw_logits=True)
+    eng = model._get_engine(device)
+    st = eng.gen_state(max(cfg.block_size, max_returned_tokens))
+    seq, pos, step, tok = st["seq"], st["pos"], st["step"], st["tok"]
+    seq[:T].copy_(idx)
+    pos.fill_(T - 1)
+    seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+    _calls[seed] = _calls.get(seed, 0) + 1
+    step.fill_((_calls[seed] * 8192) % (1 << 30))
+    k = 0 if top_k is None else min(int(top_k), cfg.padded_vocab_size)
+    _lib.check(eng.lib.lp_sample(logits.data_ptr(), 1, cfg.padded_vocab_size, float(temperature), k, seed, step.data_ptr(),
+                                 tok.data_ptr(), seq.data_ptr(), pos.data_ptr(), torch.cuda.current_stream(device).cuda_stream),
+               "lp_sample")
+    yield int(seq[T])
+    replay = eng.decode_step(model.kv_caches, float(temperature), k, seed)
+    for n in range(max_returned_tokens - T - 1):
+        replay()
+        yield int(seq[T + 1 + n])
+    eng.check_step_health()
+
+
+def foreign_token_stream(model, idx, max_returned_tokens, max_seq_length, temperature, top_k):
+    """chat/base.py:57-73 for models that are not ours (the model does all the arithmetic)."""
+    T = idx.size(0)
+    input_pos = torch.arange(0, T, device=idx.device)
+    for _ in range(max_returned_tokens - T):
+        logits = model(idx.view(1, -1), max_seq_length, input_pos)
+        logits = logits[0, -1] / temperature
+        if top_k is not None:
+            v, _ = torch.topk(logits, min(top_k, logits.size(-1)))
+            logits = torch.where(logits < v[[-1]], -float("Inf"), logits)
+        probs = torch.nn.functional.softmax(logits, dim=-1)
+        idx = torch.multinomial(probs, num_samples=1)
+        input_pos = input_pos[-1:] + 1
+        yield int(idx)
+
+
 def _generate_foreign(model, idx, max_returned_tokens, max_seq_length, temperature, top_k, eos_id) -> torch.Tensor:
     """generate/base.py:113-159 for models that are not ours (host loop; the model does all the arithmetic)."""
     T = idx.size(0)

@@ -53,13 +53,19 @@ class TPContext:
         self.group = group
         self.rank, self.size = dist.get_rank(group), dist.get_world_size(group)
         self.slot_floats = max_rows * n_embd
-        self.buf = symm.empty(2 * self.slot_floats, dtype=torch.float32, device=device)
+        self.n_embd = n_embd
+        # [2 slots][max_rows * E]: pull protocol of the per-op kernel (lp_tp_allreduce_residual: prefill, batches > 1), then
+        # [2 slots][size ranks][E]: push protocol of the step kernel (batch-1 decode; every rank's partial lands in every buffer)
+        self.push_off = 2 * self.slot_floats * 4
+        self.buf = symm.empty(2 * self.slot_floats + 2 * self.size * n_embd, dtype=torch.float32, device=device)
         self.hdl = symm.rendezvous(self.buf, group)
-        if self.hdl.signal_pad_size < 2 * self.size * 4:
+        if self.hdl.signal_pad_size < 4 * self.size * 4:
             raise RuntimeError("symmetric-memory signal pad too small")
         self.buf_ptrs = self.hdl.buffer_ptrs_dev      # device arrays of `size` peer-mapped addresses
         self.pad_ptrs = self.hdl.signal_pad_ptrs_dev
-        self.state = torch.zeros(2, 2, dtype=torch.int32, device=device)  # per slot: epoch, CTA ticket
+        self.state = torch.zeros(2, 2, dtype=torch.int32, device=device)  # pull protocol, per slot: epoch, CTA ticket
+        self.push_state = torch.zeros(2, 2, dtype=torch.int32, device=device)  # push protocol, per slot: epoch, -
+        self.push_pad = 2 * self.size  # first signal-pad word of the push protocol (the pull protocol owns [0, 2 * size))
         self.slot = 0
         self.count = 0
         dist.barrier(group)
@@ -84,8 +90,12 @@ class LoopbackTPContext:
         self.group = None
         self.rank, self.size = 0, 1
         self.slot_floats = max_rows * n_embd
-        self.buf = torch.zeros(2 * self.slot_floats, dtype=torch.float32, device=device)
+        self.n_embd = n_embd
+        self.push_off = 2 * self.slot_floats * 4
+        self.buf = torch.zeros(2 * self.slot_floats + 2 * n_embd, dtype=torch.float32, device=device)
         self.pad = torch.zeros(64, dtype=torch.int32, device=device)
+        self.push_state = torch.zeros(2, 2, dtype=torch.int32, device=device)
+        self.push_pad = 2
         self._ptrs = torch.tensor([self.buf.data_ptr(), self.pad.data_ptr()], dtype=torch.int64, device=device)
         self.buf_ptrs = self._ptrs.data_ptr()
         self.pad_ptrs = self._ptrs.data_ptr() + 8

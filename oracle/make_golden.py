@@ -325,15 +325,97 @@ def checkpoint_cases():
     print(f"[golden] checkpoint dir {d.name}: fp32 + gptq.int4 files written, reference reload logits stored")
 
 
+def cli_cases():
+    """SURVEY §8 f3 — the callers on the other side of generate(): the reference's Tokenizer (lit_gpt/tokenizer.py), the streaming
+    chat generate with stop sequences (chat/base.py:20-95) and prompt_config (chat/base.py:202-290), driven here UNMODIFIED:
+    * a tiny HF-tokenizers vocabulary (word level, 96 entries = the tiny checkpoint's vocab) is written into ckpt_tiny_llama/, which
+      thereby becomes a complete checkpoint directory (check_valid_checkpoint_dir passes);
+    * encode / decode round trips, the token streams chat.generate yields for scripted next-token sequences (a stub model whose
+      logits are one-hot, so multinomial is deterministic), and the (template, stop ids) pairs of every model family are stored
+      in tests/golden/cli_golden.json."""
+    import json
+    from pathlib import Path
+
+    from tokenizers import Tokenizer as HFTokenizer
+    from tokenizers.models import WordLevel
+    from tokenizers.pre_tokenizers import WhitespaceSplit
+
+    import chat.base as ref_chat  # reference
+    from lit_gpt import Tokenizer  # reference
+
+    assert ref_chat.__file__.startswith(REF), ref_chat.__file__
+    d = Path(OUT) / "ckpt_tiny_llama"
+    words = ["<|endoftext|>", "<|SYSTEM|>", "<|ASSISTANT|>", "<|USER|>", "<", ">:", "human", "bot", "Q", ":", "Question", "A",
+             "Label", "User", "[UNK]"]
+    words += [f"w{i}" for i in range(len(words), 96)]
+    tok = HFTokenizer(WordLevel({w: i for i, w in enumerate(words)}, unk_token="[UNK]"))
+    tok.pre_tokenizer = WhitespaceSplit()
+    tok.save(str(d / "tokenizer.json"))
+    with open(d / "tokenizer_config.json", "w") as fp:
+        json.dump({"bos_token": "<|endoftext|>", "eos_token": "<|endoftext|>"}, fp)
+    t = Tokenizer(d)
+    gold = {"vocab_size": t.vocab_size, "bos_id": t.bos_id, "eos_id": t.eos_id, "backend": t.backend, "encode": [], "decode": []}
+    for text, kw in (("w20 w21 human : w95", {}), ("Q : w30 unknownword A :", {"bos": True}), ("w40 w41 w42 w43", {"eos": True}),
+                     ("w50 w51 w52 w53 w54", {"bos": True, "eos": True, "max_length": 4}), ("", {})):
+        ids = t.encode(text, **kw)
+        gold["encode"].append({"text": text, "kw": kw, "ids": ids.tolist(), "dtype": str(ids.dtype)})
+    for ids in ([20, 21, 6, 9, 95], [0], [33]):
+        gold["decode"].append({"ids": ids, "text": t.decode(torch.tensor(ids))})
+    gold["decode"].append({"ids": 33, "text": t.decode(torch.tensor(33))})  # 0-dim tensor
+
+    class Scripted(torch.nn.Module):
+        """next-token script: call i returns logits whose arg-max (with probability 1) is script[i]"""
+
+        def __init__(self, script, vocab=96):
+            super().__init__()
+            self.script, self.vocab, self.calls = script, vocab, 0
+
+        def forward(self, idx, max_seq_length, input_pos):
+            lg = torch.zeros(1, idx.size(1), self.vocab)
+            lg[0, -1, self.script[self.calls]] = 1e4
+            self.calls += 1
+            return lg
+
+    gold["chat"] = []
+    cases = [
+        ([20, 21, 22, 0, 23], ([0],), 12),                       # single-token stop
+        ([20, 4, 6, 21, 4, 6, 5, 30], ([0], [4, 6, 5], [4, 7, 5]), 12),   # 3-token stop with a false start, held-back prefix
+        ([20, 21, 22, 23, 24, 25, 26], ([0], [8, 9]), 6),        # budget runs out: the held-back token is never yielded
+        ([8, 9, 20], ([0], [8, 9]), 10),                         # stop sequence right at the start
+        ([20, 21, 22], (), 5),                                   # no stop tokens at all
+        ([30, 0], ([0], [4, 6, 5]), 9),                          # short stop hits while the long buffer is not full yet
+    ]
+    for script, stops, max_ret in cases:
+        prompt = torch.tensor([15, 16], dtype=torch.int32)
+        script = script + [40] * 16
+        stream = list(ref_chat.generate(Scripted(script), prompt, max_ret, max_ret, temperature=1.0, top_k=None, stop_tokens=stops))
+        gold["chat"].append({"script": script, "stops": [list(s) for s in stops], "max_returned_tokens": max_ret,
+                             "yields": [y.tolist() for y in stream], "ndims": [y.ndim for y in stream]})
+    gold["prompt_config"] = []
+    for name in ("checkpoints/stabilityai/stablelm-tuned-alpha-3b", "checkpoints/togethercomputer/RedPajama-INCITE-Chat-3B-v1",
+                 "checkpoints/togethercomputer/RedPajama-INCITE-Instruct-3B-v1", "checkpoints/tiiuae/falcon-7b-instruct",
+                 "checkpoints/lmsys/vicuna-7b-v1.3", "checkpoints/lmsys/longchat-7b-16k", "checkpoints/meta-llama/Llama-2-7b-chat-hf",
+                 "checkpoints/stabilityai/FreeWilly2", "checkpoints/EleutherAI/pythia-70m"):
+        sp, stops = ref_chat.prompt_config(Path(name), t)
+        gold["prompt_config"].append({"name": name, "system_prompt": sp, "stop_tokens": [list(x) for x in stops]})
+    with open(os.path.join(OUT, "cli_golden.json"), "w") as fp:
+        json.dump(gold, fp, indent=1)
+    print(f"[golden] cli: tokenizer files in {d.name}, {len(gold['chat'])} chat streams, {len(gold['prompt_config'])} prompt configs")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
     if "--only-checkpoint" in sys.argv:
         checkpoint_cases()
         sys.exit(0)
+    if "--only-cli" in sys.argv:
+        cli_cases()
+        sys.exit(0)
     preset_table()
     tiny_cases()
     gptq_cases()
     pythia70m()
     checkpoint_cases()
+    cli_cases()
     print("[golden] all fixtures written to", OUT)

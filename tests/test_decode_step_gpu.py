@@ -182,9 +182,10 @@ def test_real_width_llama7b_two_layers_step_kernel():
 
 
 def test_step_kernel_exchange_op_self():
-    """The tensor-parallel EXCHANGE op of the step kernel on ONE GPU (tp = 1: the 'peer' buffers are this GPU's own): a hand-built
-    op table  part0 = W0.x | x += part0 | part1 = W1.x | x += part1 | logits = Wl.x , run twice (the slot epochs advance and are
-    shared with lp_tp_allreduce_residual, which is run in between)."""
+    """The tensor-parallel push exchange of the step kernel on ONE GPU (tp = 1: the only 'peer' is this GPU's own buffer): a
+    hand-built op table  W0.x -> slot 0 | x += slot 0 | W1.x -> slot 1 | x += slot 1 | logits = Wl.x , run three times (the
+    sender publishes epoch + 1 per use, the receiver waits for it on the local pad, the last exchange of a slot advances the
+    epoch counter) with the per-op pull kernel (its own buffer / pad words / state) run in between."""
     import ctypes
 
     from lit_parrot_b200 import _lib
@@ -199,27 +200,33 @@ def test_step_kernel_exchange_op_self():
     pos = torch.zeros(1, dtype=torch.int32, device=DEV)
     x = torch.zeros(E, device=DEV)
     logits = torch.zeros(V, device=DEV)
-    buf = torch.zeros(2 * E, device=DEV)                       # two exchange slots
-    pad = torch.zeros(64, dtype=torch.int32, device=DEV)      # signal pad: slot s -> flags [s * tp, (s + 1) * tp)
-    state = torch.zeros(2, 2, dtype=torch.int32, device=DEV)
+    buf = torch.zeros(3 * E, device=DEV)                      # push slots 0 / 1 ([1 rank][E] each), then a pull-protocol slot
+    pad = torch.zeros(64, dtype=torch.int32, device=DEV)      # push: words 0, 1 (slot s, rank 0); pull: word 8
+    state = torch.zeros(2, 2, dtype=torch.int32, device=DEV)  # push protocol
+    pull_state = torch.zeros(2, dtype=torch.int32, device=DEV)
     bufs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device=DEV)
     pads = torch.tensor([pad.data_ptr()], dtype=torch.int64, device=DEV)
     recs = [_lib.LpWeight(w.data_ptr(), None, None, None, None, _lib.LP_W_BF16, w.shape[0], E, 0, 0, 0) for w in (*W, Wl)]
     ops = (_lib.LpStepOp * 5)()
 
-    def lin(i, rec, out, dep):
+    def tp_fields(o, slot):
+        o.tp_buf_ptrs, o.tp_pad_ptrs, o.tp_state = bufs.data_ptr(), pads.data_ptr(), state[slot].data_ptr()
+        o.tp_buf_offset, o.tp_pad_base, o.tp_rank, o.tp_size = slot * E * 4, slot, 0, 1
+
+    def lin(i, rec, out, dep, slot=None):
         ops[i].kind, ops[i].dep, ops[i].W, ops[i].x, ops[i].norm_kind = _lib.LP_STEP_LINEAR, dep, ctypes.pointer(rec), x.data_ptr(), -1
         ops[i].epilogue, ops[i].out = _lib.LP_EPI_NONE, out
+        if slot is not None:
+            tp_fields(ops[i], slot)  # sender of the push exchange that follows
 
     def exch(i, slot, dep):
         ops[i].kind, ops[i].dep, ops[i].norm_kind = _lib.LP_STEP_EXCHANGE, dep, -1
-        ops[i].tp_buf_ptrs, ops[i].tp_pad_ptrs, ops[i].tp_state = bufs.data_ptr(), pads.data_ptr(), state[slot].data_ptr()
-        ops[i].tp_buf_offset, ops[i].tp_pad_base, ops[i].tp_rank, ops[i].tp_size = slot * E * 4, slot * 1, 0, 1
+        tp_fields(ops[i], slot)
         ops[i].residual, ops[i].out = x.data_ptr(), x.data_ptr()
 
-    lin(0, recs[0], buf.data_ptr(), -1)
+    lin(0, recs[0], buf.data_ptr(), -1, slot=0)
     exch(1, 0, 0)
-    lin(2, recs[1], buf.data_ptr() + E * 4, 1)
+    lin(2, recs[1], buf.data_ptr() + E * 4, 1, slot=1)
     exch(3, 1, 2)
     lin(4, recs[2], logits.data_ptr(), 3)
     ws = torch.zeros(lib.lp_decode_step_workspace_bytes(1, 64), dtype=torch.uint8, device=DEV)
@@ -241,13 +248,15 @@ def test_step_kernel_exchange_op_self():
         torch.cuda.synchronize()
         torch.testing.assert_close(logits, want, rtol=1e-4, atol=1e-4)
         torch.testing.assert_close(x, x2.float(), rtol=1e-4, atol=1e-4)
-        # a per-op exchange on slot 0 in between (the prefill path): same epoch counter
+        # the per-op pull exchange in between (prefill path): disjoint slot, pad word and state
+        buf[2 * E:].copy_(torch.arange(E, device=DEV).float())
         tmp = torch.zeros(E, device=DEV)
-        _lib.check(lib.lp_tp_allreduce_residual(bufs.data_ptr(), pads.data_ptr(), 0, 1, 0, 0, state[0].data_ptr(), E, None, tmp.data_ptr(), 0,
-                                                stream), "lp_tp_allreduce_residual")
+        _lib.check(lib.lp_tp_allreduce_residual(bufs.data_ptr(), pads.data_ptr(), 0, 1, 2 * E * 4, 8, pull_state.data_ptr(), E, None,
+                                                tmp.data_ptr(), 0, stream), "lp_tp_allreduce_residual")
         torch.cuda.synchronize()
-        torch.testing.assert_close(tmp, buf[:E])
-    assert state[0, 0].item() == 6 and state[1, 0].item() == 3  # slot 0: 3 in-kernel + 3 per-op exchanges; slot 1: 3
+        torch.testing.assert_close(tmp, buf[2 * E:])
+    assert state[0, 0].item() == 3 and state[1, 0].item() == 3 and pull_state[0].item() == 3
+    assert lib.lp_decode_step_status(ctypes.byref(handle), None) == 0
 
 
 def test_step_kernel_watchdog_reports_instead_of_hanging(monkeypatch):
