@@ -71,8 +71,15 @@ def test_model_file_selection_and_errors(tmp_path):
     assert ck.checkpoint_file(CKPT, "gptq.int4").name == "lit_model_gptq.4bit.pth"
     with pytest.raises(ValueError, match="quantize/gptq.py"):
         ck.checkpoint_file(tmp_path, "gptq.int4")
+    ck.check_valid_checkpoint_dir(CKPT)  # complete since the tokenizer files were added (oracle/make_golden.py::cli_cases)
+    import shutil
+
+    part = tmp_path / "partial"
+    part.mkdir()
+    for f in ("lit_model.pth", "lit_config.json"):
+        shutil.copy(CKPT / f, part / f)
     with pytest.raises(SystemExit) as e:
-        ck.check_valid_checkpoint_dir(CKPT)  # the fixture has no tokenizer files
+        ck.check_valid_checkpoint_dir(part)  # no tokenizer files
     assert "tokenizer_config.json" in str(e.value) and "lit_model.pth" not in str(e.value).split("missing the files")[1]
     with pytest.raises(SystemExit, match="is not a checkpoint directory"):
         ck.check_valid_checkpoint_dir(tmp_path / "absent")
