@@ -77,7 +77,7 @@ def test_model_file_selection_and_errors(tmp_path):
     part = tmp_path / "partial"
     part.mkdir()
     for f in ("lit_model.pth", "lit_config.json"):
-        shutil.copy(CKPT / f, part / f)
+        shutil.copy(os.path.join(CKPT, f), part / f)
     with pytest.raises(SystemExit) as e:
         ck.check_valid_checkpoint_dir(part)  # no tokenizer files
     assert "tokenizer_config.json" in str(e.value) and "lit_model.pth" not in str(e.value).split("missing the files")[1]
