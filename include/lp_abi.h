@@ -67,12 +67,15 @@ typedef enum { LP_NORM_LAYERNORM = 0, LP_NORM_RMS = 1 } lp_norm_kind;
                               otherwise a float2 {scale, zero}.  Packed is exact when the scales are bf16-representable
                               (a bf16 checkpoint) and halves the scale/zero traffic: 0.5 + 4/128 bytes per weight.   */
 
+#define LP_WF_AUX_TILED 2  /* NF4: aux2 holds the absmax values TILE-MAJOR [N/16][ceil(K/2048) K-stages][32 blocks][16 rows] fp32 (zero
+                              padded), the layout the step kernel fetches with one 2 KB bulk copy per stage                       */
+
 /* One linear layer's weights.  `aux0`/`aux1`: INT4 -> scales/zeros; NF4 -> absmax/unused; INT8 -> row scales. */
 typedef struct {
   const void* w;
   const float* aux0;
   const float* aux1;
-  const void* aux2;    /* INT4, optional: scale/zero pairs TILE-MAJOR [N/16][n_groups][16 rows] (see flags), the layout
+  const void* aux2;    /* NF4, optional: tile-major absmax (LP_WF_AUX_TILED).  INT4, optional: scale/zero pairs TILE-MAJOR [N/16][n_groups][16 rows] (see flags), the layout
                           the streaming kernel fetches with one bulk copy per stage; NULL -> exact CUDA-core kernel   */
   const float* bias;   /* fp32 [N] or NULL                                                              */
   int32_t fmt;         /* lp_wfmt                                                                       */
@@ -208,7 +211,7 @@ int lp_attn_prefill(const float* q, const void* k_cache, const void* v_cache, in
  *        CTA then wrote the rows it reads); checked by lp_decode_step_plan.  residual == out (x += W . u in place) is the
  *        preferred form: such ops are split over the CTAs at 16 KB-stage granularity and accumulate with atomic adds, so two
  *        of them may overlap (parallel-residual blocks); the summation order of their partial sums is not fixed.
- * Covers fp32-activation mode, bf16 / GPTQ-int4 (tile-major aux2) weights, MHA / GQA / MQA with H <= #SMs, bf16 KV cache,
+ * Covers fp32-activation mode, bf16 / GPTQ-int4 (tile-major aux2) / bnb NF4 (tile-major absmax) / row-wise int8 weights, MHA / GQA / MQA with H <= #SMs, bf16 KV cache,
  * hs 64 / 128, batch 1; LP_ERR_UNSUPPORTED otherwise (callers then issue the per-op calls above). */
 typedef enum { LP_STEP_LINEAR = 0, LP_STEP_ATTENTION = 1, LP_STEP_EXCHANGE = 2, LP_STEP_SLAB = 3 } lp_step_kind;
 

@@ -19,6 +19,7 @@ LP_EPI_NONE, LP_EPI_GELU, LP_EPI_SWIGLU, LP_EPI_RESIDUAL = 0, 1, 2, 3
 LP_NORM_LAYERNORM, LP_NORM_RMS = 0, 1
 LP_ABI_VERSION = 5
 LP_WF_AUX_PACKED = 1
+LP_WF_AUX_TILED = 2
 LP_STEP_LINEAR, LP_STEP_ATTENTION, LP_STEP_EXCHANGE, LP_STEP_SLAB = 0, 1, 2, 3
 
 c_void_p, c_int, c_float, c_size_t, c_u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_uint64

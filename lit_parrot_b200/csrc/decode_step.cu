@@ -408,7 +408,8 @@ __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDe
     }
   }
   if (tr && ctid == 0) tr[5] = gs_now();  // normalised
-  if (fmt == LP_W_INT4) {
+  if (fmt == LP_W_INT4 || fmt == LP_W_INT8) {
+    const bool natural = fmt == LP_W_INT8;  // int8 weights: digit bytes in column order; int4: even / odd columns split (nibble IMMAs)
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
       const int k = ctid * 8 + i * STRIDE;
@@ -429,7 +430,18 @@ __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDe
         for (int q = 0; q < 8; ++q) z[q] = (uint32_t)(__float2int_rn(x[i][q] * inv) + 0x8080) ^ 0x8080u;
         // 4 x 4 byte transposes: digit d of columns 0,2,4,6 (IMMA a0/a1 side) and of columns 1,3,5,7 (a2/a3 side)
         uint32_t lo[3], hi[3];
-        {
+        if (natural) {  // words of columns 0..3 and 4..7
+          const uint32_t u0 = __byte_perm(z[0], z[1], 0x5140), u1 = __byte_perm(z[2], z[3], 0x5140);
+          const uint32_t u2 = __byte_perm(z[0], z[1], 0x7362), u3 = __byte_perm(z[2], z[3], 0x7362);
+          lo[0] = __byte_perm(u0, u1, 0x5410);
+          lo[1] = __byte_perm(u0, u1, 0x7632);
+          lo[2] = __byte_perm(u2, u3, 0x5410);
+          const uint32_t v0 = __byte_perm(z[4], z[5], 0x5140), v1 = __byte_perm(z[6], z[7], 0x5140);
+          const uint32_t v2 = __byte_perm(z[4], z[5], 0x7362), v3 = __byte_perm(z[6], z[7], 0x7362);
+          hi[0] = __byte_perm(v0, v1, 0x5410);
+          hi[1] = __byte_perm(v0, v1, 0x7632);
+          hi[2] = __byte_perm(v2, v3, 0x5410);
+        } else {
           const uint32_t u0 = __byte_perm(z[0], z[2], 0x5140), u1 = __byte_perm(z[4], z[6], 0x5140);
           const uint32_t u2 = __byte_perm(z[0], z[2], 0x7362), u3 = __byte_perm(z[4], z[6], 0x7362);
           lo[0] = __byte_perm(u0, u1, 0x5410);
@@ -446,9 +458,9 @@ __device__ __forceinline__ void ds_stage_row(const DsOp& o, LoadX load_x, WaitDe
         for (int d = 0; d < 3; ++d) {
           // 16-column pair of groups (A, B) -> [A.even | B.even | A.odd | B.odd]: the B operands of the low-nibble and the
           // high-nibble IMMA are then adjacent registers of one 128-bit load
-          const uint32_t a16 = xs_u32 + (uint32_t)(d * ldx + (k & ~15) + ((k & 8) >> 1));
+          const uint32_t a16 = natural ? xs_u32 + (uint32_t)(d * ldx + k) : xs_u32 + (uint32_t)(d * ldx + (k & ~15) + ((k & 8) >> 1));
           asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(a16), "r"(lo[d]) : "memory");
-          asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(a16 + 8), "r"(hi[d]) : "memory");
+          asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(a16 + (natural ? 4 : 8)), "r"(hi[d]) : "memory");
           int sd = __dp4a((int)lo[d], 0x01010101, 0);  // digit sum of the thread's 8 columns
           sd = __dp4a((int)hi[d], 0x01010101, sd);
 #pragma unroll
@@ -745,10 +757,120 @@ __device__ __forceinline__ void ds_linear_main_i4pair(const DsOp& o, DsRing& rg,
   rg.s = adv % nstages;
 }
 
+// Main loops of the bitsandbytes formats (quantize/bnb.py:18-75; arithmetic restated from the published formats, parity unpinned):
+//   INT8  row-wise int8 weights: IMMA m16n8k32 s8 x s8 against the three int8 digit planes of the activations (no unpack at
+//         all: the weight bytes ARE the A operand); per 128-column K-block the integer sums are scaled by the block's activation
+//         scale, the row scale (SCB / 127) is applied by the tile epilogue.
+//   NF4   4-bit codes into the 16-entry normal-float table, fp32 absmax per 64 weights: every code goes through a shared-memory
+//         table (two copies, lanes alternate: bank-conflict free) that yields the bf16 hi and lo terms of its value
+//         (hi + lo = the fp32 table entry to 2^-17); the HMMA loop of the bf16 format then runs on those terms against the bf16
+//         terms of the activations, one accumulator per 64-weight block, scaled by the block's absmax.
+__device__ __forceinline__ void gs_imma_s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int FMT>
+__device__ __forceinline__ void ds_linear_main_bnb(const DsOp& o, DsRing& rg, uint32_t red_u32, uint32_t xsum_u32, uint32_t xs_u32,
+                                                   uint32_t tbl_u32, volatile int* done, int sb, int se, int& gt) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int nks = o.nks, split = o.split, ldx = o.ldx, nkb = o.nkb;
+  const int kbl = warp >> 1, sub0 = warp & 1;
+  const int bcol = g < split ? g : split - 1;  // B columns >= split only feed accumulator columns nobody reads
+  const int nunits = se - sb;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool lane0 = ds_pin(lane) == 0;
+  const uint32_t ring_u32 = ds_pin(rg.ring_u32), bar0 = ds_pin(rg.bar0);
+  const int nstages = ds_pin(rg.nstages), stage_stride = ds_pin(rg.stage_stride);
+  const uint32_t wrow = ds_pin((uint32_t)(kbl * GS_BLK_BYTES + g * 128));  // tile row g of this warp's K-block (row g + 8: + 1024)
+  const uint32_t sw = ds_pin((uint32_t)(g & 7));                           // 128-byte swizzle: 16-byte chunk index ^ (row & 7)
+  const uint32_t tb = ds_pin(tbl_u32 + (uint32_t)((lane & 1) * 64));       // NF4 table copy of this lane
+  int rs = rg.s, rph = rg.ph;
+  int ks = sb % nks;  // the first tile may start in the middle (stream-K ops)
+  for (int u = 0; u < nunits; ++u) {
+    mbar_wait(bar0 + 8 * rs, rph);
+    const uint32_t st = ring_u32 + (uint32_t)(rs * stage_stride);
+    const int kb = ks * GS_KB + kbl;  // K-block of the row
+    if (kb < nkb) {
+      if (FMT == LP_W_INT8) {
+        // K-block = 128 weights; this warp: columns [64 sub0, 64 sub0 + 64) = two k32 steps
+        int c[4] = {0, 0, 0, 0};
+        const uint32_t xb = xs_u32 + (uint32_t)(bcol * ldx + kb * 128 + sub0 * 64 + 4 * t);
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const uint32_t c0 = (uint32_t)(4 * sub0 + 2 * s2);
+          const uint32_t a0 = ds_lds32(st + wrow + (((c0) ^ sw) << 4) + 4 * t), a1 = ds_lds32(st + wrow + 1024 + (((c0) ^ sw) << 4) + 4 * t);
+          const uint32_t a2 = ds_lds32(st + wrow + (((c0 + 1) ^ sw) << 4) + 4 * t), a3 = ds_lds32(st + wrow + 1024 + (((c0 + 1) ^ sw) << 4) + 4 * t);
+          const uint32_t b0 = ds_lds32(xb + s2 * 32), b1 = ds_lds32(xb + s2 * 32 + 16);
+          gs_imma_s8(c, a0, a1, a2, a3, b0, b1);
+        }
+        const float ag = __uint_as_float(ds_lds32(xsum_u32 + (uint32_t)(kb * 4 + 3) * 4));  // activation scale of this 128-column block
+        acc[0] = fmaf(ag, (float)c[0], acc[0]);
+        acc[1] = fmaf(ag, (float)c[1], acc[1]);
+        acc[2] = fmaf(ag, (float)c[2], acc[2]);
+        acc[3] = fmaf(ag, (float)c[3], acc[3]);
+      } else {
+        // K-block = 256 weights = 128 bytes; this warp: bytes [64 sub0, 64 sub0 + 64) = 8 k16 groups = 2 absmax blocks
+        const uint32_t xb = xs_u32 + (uint32_t)(bcol * ldx + kb * 256 + sub0 * 128 + 2 * t) * 2;
+        const uint32_t am = st + GS_KB * GS_BLK_BYTES + (uint32_t)(((kbl * 4 + sub0 * 2) * 16 + g) * 4);
+        const uint32_t sh = (uint32_t)(8 * t);
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          float ab[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const int q = blk * 4 + qq;
+            const uint32_t off = ((((uint32_t)(4 * sub0 + (q >> 1))) ^ sw) << 4) + (uint32_t)(8 * (q & 1));
+            const uint2 w0 = ds_lds64(st + wrow + off), w1 = ds_lds64(st + wrow + 1024 + off);
+            // bytes t (k = 2t, 2t + 1) and t + 4 (k = 2t + 8, 2t + 9) of the group, rows g and g + 8; first weight in the HIGH nibble
+            uint32_t areg[2][4];
+            const uint32_t by[4] = {(w0.x >> sh) & 0xffu, (w1.x >> sh) & 0xffu, (w0.y >> sh) & 0xffu, (w1.y >> sh) & 0xffu};
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const uint32_t le = ds_lds32(tb + ((by[r] >> 2) & 0x3cu)), lo = ds_lds32(tb + ((by[r] << 2) & 0x3cu));
+              areg[0][r] = __byte_perm(le, lo, 0x5410);  // bf16 hi terms of (k even, k odd)
+              areg[1][r] = __byte_perm(le, lo, 0x7632);  // bf16 lo terms
+            }
+            const uint32_t b0 = ds_lds32(xb + (uint32_t)(q * 32)), b1 = ds_lds32(xb + (uint32_t)(q * 32 + 16));
+            gs_mma(ab, areg[0][0], areg[0][1], areg[0][2], areg[0][3], b0, b1);
+            gs_mma(ab, areg[1][0], areg[1][1], areg[1][2], areg[1][3], b0, b1);
+          }
+          const float m0 = __uint_as_float(ds_lds32(am + (uint32_t)(blk * 64))), m1 = __uint_as_float(ds_lds32(am + (uint32_t)(blk * 64 + 32)));
+          acc[0] = fmaf(m0, ab[0], acc[0]);
+          acc[1] = fmaf(m0, ab[1], acc[1]);
+          acc[2] = fmaf(m1, ab[2], acc[2]);
+          acc[3] = fmaf(m1, ab[3], acc[3]);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane0) mbar_arrive(bar0 + 8 * (nstages + rs));
+    if (++rs == nstages) { rs = 0; rph ^= 1; }
+    if (++ks == nks || u == nunits - 1) {  // end of the tile, or of this CTA's part of it (as in ds_linear_main)
+      ks = 0;
+      const int par = gt & 1;
+      while (done[par] < (gt >> 1)) {}
+      if (t < 2) {
+        const uint32_t r = red_u32 + (uint32_t)(((par * GS_CWARPS + warp) * 16 + g) * 4 + 2 * t) * 4;
+        ds_sts64f(r, acc[0], acc[1]);
+        ds_sts64f(r + 8 * 4 * 4, acc[2], acc[3]);
+      }
+      acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+      if (par == 0) asm volatile("bar.arrive 2, %0;\n" ::"n"(DS_TILE_BAR_THREADS) : "memory");
+      else asm volatile("bar.arrive 3, %0;\n" ::"n"(DS_TILE_BAR_THREADS) : "memory");
+      ++gt;
+    }
+  }
+  rg.s = rs;
+  rg.ph = rph;
+}
+
 template <int HS, class WaitDep>
 __device__ __forceinline__ void ds_linear(const DsParams& p, const DsOp& o, const DsAttnGeo<HS>& geo, DsRing& rg, uint32_t red_u32,
                                           float* colscale, float* xsum, uint32_t xs_u32, volatile int* done, float* s_stat,
-                                          unsigned long long* tr, int& gt, WaitDep wait_dep, float* xraw, float* xstat, bool& have_xraw) {
+                                          unsigned long long* tr, int& gt, WaitDep wait_dep, float* xraw, float* xstat, bool& have_xraw,
+                                          uint32_t tbl_u32) {
   int sb, se;
   ds_stage_range(o, sb, se);
   if (se == sb) {  // CTA-uniform: nothing to compute, but later ops rely on the (cumulative) dependency
@@ -818,14 +940,16 @@ __device__ __forceinline__ void ds_linear(const DsParams& p, const DsOp& o, cons
       for (int w = 0; w < GS_CWARPS; ++w) ss += s_stat[2 * GS_CWARPS + w];
       post = 1.0f / sqrtf(ss / (float)o.K + o.eps);
     }
-    const bool i4 = o.fmt == LP_W_INT4;
+    const bool i4 = o.fmt == LP_W_INT4 || o.fmt == LP_W_INT8;  // int8 digit planes of the activations
     colscale[0] = post;
     colscale[1] = i4 ? 256.0f * post : post;
     colscale[2] = i4 ? 65536.0f * post : post;
     if (tr) tr[2] = gs_now();
   }
   const uint32_t xsum_u32 = gs_smem_u32(xsum);
-  if (o.fmt == LP_W_BF16) ds_linear_main<LP_W_BF16, false>(o, rg, red_u32, xsum_u32, xs_u32, done, sb, se, gt);
+  if (o.fmt == LP_W_INT8) ds_linear_main_bnb<LP_W_INT8>(o, rg, red_u32, xsum_u32, xs_u32, tbl_u32, done, sb, se, gt);
+  else if (o.fmt == LP_W_NF4) ds_linear_main_bnb<LP_W_NF4>(o, rg, red_u32, xsum_u32, xs_u32, tbl_u32, done, sb, se, gt);
+  else if (o.fmt == LP_W_BF16) ds_linear_main<LP_W_BF16, false>(o, rg, red_u32, xsum_u32, xs_u32, done, sb, se, gt);
   else if (p.i4pair && o.aux_bytes == 4) ds_linear_main_i4pair<true>(o, rg, red_u32, xsum_u32, xs_u32, done, sb, se, gt, p.i4pair == 2);
   else if (p.i4pair) ds_linear_main_i4pair<false>(o, rg, red_u32, xsum_u32, xs_u32, done, sb, se, gt, p.i4pair == 2);
   else if (o.aux_bytes == 4) ds_linear_main<LP_W_INT4, true>(o, rg, red_u32, xsum_u32, xs_u32, done, sb, se, gt);
@@ -855,6 +979,7 @@ __device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint3
       const unsigned long long push_off = o.tp_buf_off;
       const float* bias = o.bias;
       const float* residual = o.residual;
+      const float* rowscale = reinterpret_cast<const float*>(o.aux2);  // INT8 only
       float* out = o.out;
       int sb, se;
       ds_stage_range(o, sb, se);
@@ -882,10 +1007,11 @@ __device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint3
         __syncwarp();
         if (lane == 0) done[e] = (gt >> 1) + 1;  // the partial sums are in registers: the buffer may be rewritten
         float y;
-        if (fmt == LP_W_INT4) {  // digit 0 (smallest) first
+        if (fmt == LP_W_INT4 || fmt == LP_W_INT8) {  // digit 0 (smallest) first
           y = c0 * colscale[0];
           y = fmaf(c1, colscale[1], y);
           y = fmaf(c2, colscale[2], y);
+          if (fmt == LP_W_INT8) y *= rowscale[tile * GS_ROWS + rr];  // SCB / 127 of the output row
         } else {  // last (smallest) bf16 term first
           y = split == 3 ? c2 : 0.f;
           y += c1;
@@ -1133,6 +1259,11 @@ __device__ __forceinline__ void ds_attention(const DsParams& p, const DsOp& o, c
   }
 }
 
+
+__constant__ float c_ds_nf4[16] = {-1.0f, -0.6961928009986877f, -0.5250730514526367f, -0.39491748809814453f,
+                                    -0.28444138169288635f, -0.18477343022823334f, -0.09105003625154495f, 0.0f,
+                                    0.07958029955625534f, 0.16093020141124725f, 0.24611230194568634f, 0.33791524171829224f,
+                                    0.44070982933044434f, 0.5626170039176941f, 0.7229568362236023f, 1.0f};
 
 struct DsSlabLoop {
   uint32_t sc_off, ring_u32, bar0;
@@ -1465,6 +1596,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
   __shared__ int s_hs_ready;   // highest slab op whose head (the P CTAs that split its sequence) the watcher has seen arrive
   __shared__ __align__(16) float s_loc[DS_SLAB_MAXU * 8];  // CTA-local input columns of a slab op (SwiGLU outputs / head output)
   __shared__ DsSlabMeta s_meta[2];
+  __shared__ __align__(128) uint32_t s_nf4[32];  // two copies of {bf16 hi term | bf16 lo term << 16} of the 16 NF4 values
   float* xraw = reinterpret_cast<float*>(xs + p.xs_bytes);  // raw activation row kept for a reuse_x op (may be empty)
   const uint32_t red_u32 = gs_smem_u32(red), xs_u32 = gs_smem_u32(xs);
 
@@ -1484,6 +1616,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
     }
     done[0] = done[1] = 0;
     s_dep_ready = -1;
+    for (int k = 0; k < 32; ++k) {
+      const float v = c_ds_nf4[k & 15];
+      const uint32_t hi = gs_bf16_bits(v), lo = gs_bf16_bits(v - __uint_as_float(hi << 16));
+      s_nf4[k] = hi | (lo << 16);
+    }
     s_hs_ready = -1;
     for (int k = 0; k < 2; ++k) {
       if (p.slab_meta[k]) s_meta[k] = p.slab_meta[k][blockIdx.x];
@@ -1619,10 +1756,13 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
             g_begin = c_begin / gp128;
             aux_len = (uint32_t)((c_end + gp128 - 1) / gp128 - g_begin) * 16 * aux_bytes;
           }
+          if (fmt == LP_W_NF4) aux_len = 2048;  // absmax of the stage: [32 blocks of 64 weights][16 rows] floats, tile-major
           mbar_expect_tx(rg.full(), GS_KB * GS_BLK_BYTES + aux_len);
           tma_load_3d(dst, &o.map, 0, tile * GS_ROWS, ks * GS_KB, rg.full());
           if (fmt == LP_W_INT4)
             bulk_g2s(dst + GS_KB * GS_BLK_BYTES, aux2 + ((size_t)tile * ngroups + g_begin) * 16 * aux_bytes, aux_len, rg.full());
+          else if (fmt == LP_W_NF4)
+            bulk_g2s(dst + GS_KB * GS_BLK_BYTES, aux2 + ((size_t)tile * nks + ks) * 2048, 2048, rg.full());
           rg.advance();
           if (++ks == nks) {
             ks = 0;
@@ -1724,7 +1864,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const DsPara
       if (tr && threadIdx.x == 0) tr[1] = gs_now();
     };
     if (o.kind == DS_KIND_LINEAR) {
-      ds_linear<HS>(p, o, geo, rg, red_u32, colscale, xsum, xs_u32, done, s_stat, tr, gt, wait_dep, xraw, s_xstat, have_xraw);
+      ds_linear<HS>(p, o, geo, rg, red_u32, colscale, xsum, xs_u32, done, s_stat, tr, gt, wait_dep, xraw, s_xstat, have_xraw,
+                    gs_smem_u32(s_nf4));
     } else if (o.kind == DS_KIND_SLAB) {
       auto wait_hs = [&]() {
         while (ds_lds_acquire(&s_hs_ready) < op) {}
@@ -2000,7 +2141,7 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
     if (s.kind != LP_STEP_LINEAR || !s.W || !s.out) return LP_ERR_INVALID_ARG;
     const lp_weight& W = *s.W;
     if (!W.w || W.N <= 0 || W.K <= 0) return LP_ERR_INVALID_ARG;
-    if (W.fmt != LP_W_BF16 && W.fmt != LP_W_INT4) return LP_ERR_UNSUPPORTED;
+    if (W.fmt != LP_W_BF16 && W.fmt != LP_W_INT4 && W.fmt != LP_W_NF4 && W.fmt != LP_W_INT8) return LP_ERR_UNSUPPORTED;
     if (W.N % GS_ROWS || W.K % 16 || W.K > 6 * DS_CTHREADS * 8 || (reinterpret_cast<uintptr_t>(W.w) & 15)) return LP_ERR_UNSUPPORTED;
     if (s.epilogue < LP_EPI_NONE || s.epilogue > LP_EPI_RESIDUAL) return LP_ERR_INVALID_ARG;
     if (s.epilogue == LP_EPI_RESIDUAL && !s.residual) return LP_ERR_INVALID_ARG;
@@ -2018,6 +2159,25 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
       d.ldx = kpad + 8;
       d.gp128 = 1;
       xs_bytes = std::max(xs_bytes, (size_t)d.split * d.ldx * 2);
+    } else if (W.fmt == LP_W_NF4) {
+      // bitsandbytes NF4: rows of K / 2 bytes, absmax per 64 weights TILE-MAJOR in aux2 ([N/16][K-stages][32 blocks][16 rows]
+      // floats, LP_WF_AUX_TILED): one 2 KB bulk copy per stage behind the 16 KB of codes
+      if (K % 256 || W.group != 64 || !W.aux2 || !(W.flags & LP_WF_AUX_TILED)) return LP_ERR_UNSUPPORTED;
+      row_bytes = (size_t)K / 2;
+      d.split = ((size_t)3 * K * 2 > 48 * 1024) ? 2 : 3;
+      d.ldx = kpad + 8;
+      d.gp128 = 1;
+      aux_stage = 2048;
+      xs_bytes = std::max(xs_bytes, (size_t)d.split * d.ldx * 2);
+    } else if (W.fmt == LP_W_INT8) {
+      // row-wise int8: rows of K bytes, row scales (SCB / 127) in aux0, applied by the tile epilogue
+      if (K % 128 || !W.aux0) return LP_ERR_UNSUPPORTED;
+      row_bytes = (size_t)K;
+      d.split = 3;
+      d.ldx = kpad + 16;
+      d.gp128 = 1;
+      xs_bytes = std::max(xs_bytes, (size_t)3 * d.ldx);
+      xsum_floats = std::max(xsum_floats, (K + 127) / 128 * 8);
     } else {
       if (W.group <= 0 || W.group % 128 || !W.aux2) return LP_ERR_UNSUPPORTED;
       row_bytes = (size_t)kpad / 2;
@@ -2053,7 +2213,7 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
     d.bias = W.bias;
     d.nw = s.norm_kind >= 0 ? s.norm_w : nullptr;
     d.nb = s.norm_kind >= 0 ? s.norm_b : nullptr;
-    d.aux2 = W.aux2;
+    d.aux2 = W.fmt == LP_W_INT8 ? reinterpret_cast<const void*>(W.aux0) : W.aux2;  // INT8: the row scales ride in aux2
     d.eps = s.eps;
     d.norm_kind = s.norm_kind >= 0 ? s.norm_kind : -1;
     d.epi = s.epilogue;

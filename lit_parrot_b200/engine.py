@@ -38,7 +38,9 @@ class PackedLinear:
         """Bytes a decode step must stream for this layer (weights + scales/zeros/absmax).  When the tile-major
         scale/zero buffer (aux2) exists it is what the streaming kernel reads instead of aux0/aux1."""
         w, _bias, aux0, aux1, aux2 = self.keep
-        aux = (aux2,) if aux2 is not None else (aux0, aux1)
+        # int4: aux2 (tile-major scale / zero words) replaces aux0 / aux1; NF4: aux2 is aux0 (absmax) re-tiled with zero padding,
+        # the canonical count is aux0
+        aux = (aux2,) if (aux2 is not None and self.fmt != _lib.LP_W_NF4) else (aux0, aux1)
         return sum(t.numel() * t.element_size() for t in (w, *aux) if t is not None)
 
 

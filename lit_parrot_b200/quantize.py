@@ -204,6 +204,20 @@ def nf4_quantize(w: torch.Tensor, blocksize: int = 64) -> Tuple[torch.Tensor, to
     return packed, absmax
 
 
+def tile_major_absmax(absmax: torch.Tensor, N: int, K: int, blocksize: int) -> Tuple[Optional[torch.Tensor], int]:
+    """NF4 absmax (one fp32 per `blocksize` consecutive weights of the flattened matrix) in the layout the step kernel fetches with
+    one bulk copy per 16-row x 2048-column stage: [N/16 tiles][K-stages][32 blocks][16 rows], zero padded.  (None, 0) when the
+    shape is not covered (the exact CUDA-core kernel is used then)."""
+    if blocksize != 64 or N % 16 or K % 256:
+        return None, 0
+    nblk = K // 64
+    nks = -(-nblk // 32)
+    a = absmax.detach().float().view(N // 16, 16, nblk)
+    if nks * 32 != nblk:
+        a = torch.cat((a, a.new_zeros(N // 16, 16, nks * 32 - nblk)), dim=2)
+    return a.view(N // 16, 16, nks, 32).permute(0, 2, 3, 1).contiguous(), _lib.LP_WF_AUX_TILED
+
+
 class Linear4bit(torch.nn.Linear):
     """NF4 weight-only linear.  Holds a float `weight` until the first forward (so float checkpoints load), then
     the weight is quantised on the GPU and replaced by the packed uint8 codes, as bitsandbytes does on `.cuda()`."""
@@ -236,8 +250,9 @@ class Linear4bit(torch.nn.Linear):
     def lp_pack(self):
         packed, absmax = self._quantized()
         bias = None if self.bias is None else self.bias.detach().float().contiguous()
+        aux2, flags = tile_major_absmax(absmax, self.out_features, self.in_features, self.blocksize)
         return _packed_linear(packed.contiguous(), _lib.LP_W_NF4, self.out_features, self.in_features, bias=bias, aux0=absmax,
-                              group=self.blocksize)
+                              group=self.blocksize, aux2=aux2, flags=flags)
 
     def lp_pack_pair(self, other: "Linear4bit"):
         pa, aa = self._quantized()
@@ -248,7 +263,8 @@ class Linear4bit(torch.nn.Linear):
         bias = None
         if self.bias is not None:
             bias = torch.stack((self.bias.detach().float(), other.bias.detach().float()), dim=1).reshape(-1).contiguous()
-        return _packed_linear(inter, _lib.LP_W_NF4, 2 * N, K, bias=bias, aux0=am, group=self.blocksize)
+        aux2, flags = tile_major_absmax(am, 2 * N, K, self.blocksize)
+        return _packed_linear(inter, _lib.LP_W_NF4, 2 * N, K, bias=bias, aux0=am, group=self.blocksize, aux2=aux2, flags=flags)
 
 
 class InferenceLinear8bitLt(torch.nn.Linear):

@@ -348,3 +348,36 @@ def test_step_kernel_fused_slabs_match_unfused(monkeypatch):
         a = m._forward_impl(want[i].view(1, 1).to(DEV), 100, p, raw_logits=True)[0, -1].float().cpu()
         b = m2._forward_impl(want[i].view(1, 1).to(DEV), 100, p, raw_logits=True)[0, -1].float().cpu()
         torch.testing.assert_close(a, b, rtol=0, atol=2e-4)
+
+
+def bnb_model(kw, mode, seed, cache_bf16=True):
+    """bitsandbytes-style weights (NF4 / row-wise int8, restated formats: parity unpinned) + the oracle on the dequantised weights."""
+    cfg = lp.Config(**kw) if isinstance(kw, dict) else kw
+    fsd = {k: v.bfloat16().float() for k, v in O.random_state_dict(cfg, seed=seed, perturb_norm=True).items()}
+    with lp.quantization(mode):
+        m = lp.GPT(cfg)
+    m.load_state_dict(fsd)
+    m = m.to(DEV).eval()
+    m.kv_cache_dtype = torch.bfloat16
+    dsd = {}
+    for k, v in fsd.items():
+        if v.dim() == 2 and "wte" not in k:
+            dsd[k] = O.nf4_dequantize(*O.nf4_quantize(v), v.shape) if mode == "bnb.nf4" else O.int8_dequantize(*O.int8_quantize(v))
+        else:
+            dsd[k] = v
+    return cfg, m, O.OracleGPT(cfg, dsd, kv_round=torch.bfloat16)
+
+
+# widths that the streaming formats of the step kernel cover: K % 256 == 0 for NF4 (256 codes per 128-byte K-block)
+LLAMA_BNB = dict(LLAMA, n_embd=512, n_head=4, intermediate_size=768)
+NEOX_BNB = dict(NEOX, n_embd=512, n_head=4)
+
+
+@pytest.mark.parametrize("mode", ["bnb.nf4", "bnb.int8"])
+@pytest.mark.parametrize("kw,seed", [(LLAMA_BNB, 81), (NEOX_BNB, 82)], ids=["llama", "neox"])
+def test_step_kernel_logits_bnb_formats(mode, kw, seed):
+    """NF4 (shared-memory table -> bf16 terms -> HMMA) and row-wise int8 (IMMA s8 x s8) through the persistent step kernel."""
+    cfg, m, om = bnb_model(kw, mode, seed)
+    teacher_forced(m, om, cfg, prompt_len=40, steps=50, max_seq=256, prompt_atol=2e-3)
+    assert step_kernel_used(m), "bnb formats did not go through lp_decode_step"
+    m._engine.check_step_health()

@@ -127,6 +127,29 @@ def test_llama7b_int4_g128_widths_2k_context_and_wrap(fused, monkeypatch):
     assert bool(m._engine._slabs) == fused
 
 
+@pytest.mark.parametrize("mode", ["bnb.nf4", "bnb.int8"])
+def test_llama7b_bnb_widths_2k_context_and_wrap(mode):
+    """BASELINE configs[2], the bnb side: Llama-2-7b widths with NF4 (blocksize 64) / row-wise int8 weights through the step kernel
+    (K 11008 = 43 K-blocks of 256 codes: ragged last stage; absmax tile-major with zero padding)."""
+    cfg = lp.Config.from_name("Llama-2-7b-hf", n_layer=2)
+    fsd = {k: v.bfloat16().float() for k, v in O.random_state_dict(cfg, seed=75, perturb_norm=True).items()}
+    with lp.quantization(mode):
+        m = lp.GPT(cfg)
+    m.load_state_dict(fsd)
+    m = m.to(DEV).eval()
+    m.kv_cache_dtype = torch.bfloat16
+    dense = {}
+    for k, v in fsd.items():
+        if v.dim() == 2 and "wte" not in k:
+            dense[k] = O.nf4_dequantize(*O.nf4_quantize(v), v.shape) if mode == "bnb.nf4" else O.int8_dequantize(*O.int8_quantize(v))
+        else:
+            dense[k] = v
+    om = O.OracleGPT(cfg, dense, kv_round=torch.bfloat16)
+    max_seq, start = 2048, 2040
+    _install_kv(m, om, cfg, _synthetic_kv(cfg, cfg.n_query_groups, max_seq, start, 175), max_seq)
+    _decode_and_compare(m, om, cfg, start, 12, max_seq)
+
+
 def test_llama70b_tp8_local_shard_2k_context_and_wrap():
     """Rank 0's shard of Llama-2-70b at tp = 8 (E 8192, 8 local heads on ONE KV group, QKV 1280 rows, attn.proj K 1024, I 3584)
     run alone on one GPU: the in-kernel EXCHANGE op sums a single partial (LoopbackTPContext).  Oracle: the full-width model
