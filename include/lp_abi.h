@@ -235,14 +235,14 @@ typedef struct {
   void* k_cache;
   void* v_cache;
   /* EXCHANGE (tensor parallelism): out = residual + sum over the tp ranks r of the [E] partial of rank r — a one-shot all-reduce
-   * over NVLink peer memory inside the step kernel, PUSH style.  Sender = the row-parallel LINEAR op right before it (epilogue
-   * NONE, `dep` of the exchange): it carries the same tp_* fields with tp_size > 0, and its tile epilogue stores this rank's partial
-   * into every rank's symmetric buffer at tp_buf_offset (= slot base + tp_rank * E * 4 for the sender); the last CTA of that op
-   * publishes the slot's epoch in every rank's signal pad [tp_pad_base + tp_rank].  Receiver = this op: waits on its LOCAL pad
-   * words [tp_pad_base .. + tp_size), reduces the tp partials found in its LOCAL buffer at tp_buf_offset (= slot base; partial r
-   * at + r * E * 4) in rank order, adds `residual`, writes `out`.  `tp_state`: two zero-initialised uint32 per slot (epoch, -),
-   * owned by the library afterwards.  At most two slots (state pointers), used alternately.  Buffers, pad words and state are
-   * NOT shared with lp_tp_allreduce_residual (the per-op pull kernel): give the two protocols disjoint regions. */
+   * over NVLink peer memory inside the step kernel, PUSH style with the flag in the data.  Sender = the row-parallel LINEAR op
+   * right before it (epilogue NONE, `dep` of the exchange): it carries the same tp_* fields with tp_size > 0, and its tile epilogue
+   * stores this rank's partial into every rank's symmetric buffer at tp_buf_offset (= slot base + tp_rank * E * 8 for the sender)
+   * as 8-byte {value, epoch} pairs.  Receiver = this op: polls the pairs of its slice in its LOCAL buffer at tp_buf_offset (= slot
+   * base; rank r's pairs at + r * E * 8) until they carry the slot's epoch, adds them in rank order, adds `residual`, writes `out`.
+   * A slot therefore holds tp * E * 8 bytes.  `tp_state`: two zero-initialised uint32 per slot (epoch, -), owned by the library
+   * afterwards.  At most two slots (state pointers), used alternately.  tp_pad_* are unused by this protocol.  Buffers and state
+   * are NOT shared with lp_tp_allreduce_residual (the per-op pull kernel): give the two protocols disjoint regions. */
   const void* tp_buf_ptrs;
   const void* tp_pad_ptrs;
   void* tp_state;

@@ -977,6 +977,7 @@ __device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint3
       const int push = o.tp_size;  // > 0: row-parallel sender of a tensor-parallel exchange (see ds_exchange)
       const unsigned long long* push_bufs = o.tp_bufs;
       const unsigned long long push_off = o.tp_buf_off;
+      const float push_tag = __uint_as_float((o.tp_state == p.tp_state1 ? tp_epoch[1] : tp_epoch[0]) + (unsigned)o.tp_use + 1u);
       const float* bias = o.bias;
       const float* residual = o.residual;
       const float* rowscale = reinterpret_cast<const float*>(o.aux2);  // INT8 only
@@ -1029,11 +1030,12 @@ __device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint3
             else out[row >> 1] = silu(y) * other;
           }
         } else if (push > 0) {
-          // this rank's partial of 16 rows -> slot [s][rank] of every rank's buffer (64 contiguous bytes per peer)
+          // this rank's partial of 16 rows -> slot [s][rank] of every rank's buffer as {value, epoch} pairs (128 contiguous
+          // bytes per peer; 8-byte stores: whoever sees the epoch sees the value)
           if (half == 0) {
 #pragma unroll
             for (int r = 0; r < DS_MAX_TP; ++r)
-              if (r < push) reinterpret_cast<float*>(push_bufs[r] + push_off)[row] = y;
+              if (r < push) reinterpret_cast<float2*>(push_bufs[r] + push_off)[row] = make_float2(y, push_tag);
           }
         } else if (half == 0) {
           if (epi == LP_EPI_GELU) y = gelu_erf(y);
@@ -1047,23 +1049,7 @@ __device__ __forceinline__ void ds_epilogue_warp(const DsParams& p, int e, uint3
     // of this CTA (ordered before by the barrier).  The ~1 us of that fence is off the consumers' path: they are already staging
     // the next op.
     asm volatile("bar.sync 4, %0;\n" ::"n"(DS_OPEND_THREADS) : "memory");
-    if (e == 0 && lane == 0 && o.kind == DS_KIND_LINEAR && o.tp_size > 0) {
-      // sender side of the push exchange: the remote stores of THIS CTA are made visible system-wide, then the CTA arrives; the
-      // last one to arrive has thereby observed everybody's fence and publishes the epoch to every rank (itself included)
-      __threadfence_system();
-      unsigned old;
-      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;\n" : "=r"(old) : "l"(p.counters + op) : "memory");
-      if (old == gridDim.x - 1) {
-        const unsigned int epoch = (o.tp_state == p.tp_state1 ? tp_epoch[1] : tp_epoch[0]) + (unsigned)o.tp_use + 1u;
-        // ONE system-scope fence, then the tp flag stores back to back (relaxed): a st.release.sys per peer would pay the fence
-        // — an NVLink round trip — tp times in a row (measured: 16 us per exchange at tp = 8)
-        __threadfence_system();
-        for (int r = 0; r < o.tp_size; ++r) {
-          unsigned int* flag = reinterpret_cast<unsigned int*>(o.tp_pads[r]) + o.tp_pad_base + o.tp_rank;
-          asm volatile("st.relaxed.sys.global.u32 [%0], %1;\n" ::"l"(flag), "r"(epoch) : "memory");
-        }
-      }
-    } else if (e == 0 && lane == 0) {
+    if (e == 0 && lane == 0) {
       if (signal) ds_red_release(p.counters + op);
       // attention feeding a slab: the P CTAs of a head only wait for each other (per-head counter), not for the grid
       if (hsync >= 0 && (int)blockIdx.x < p.H * p.P) ds_red_release(p.counters + hsync + blockIdx.x / p.P);
@@ -1525,53 +1511,54 @@ __device__ __forceinline__ void ds_slab(const DsParams& p, const DsOp& o, const 
 }
 
 // ------------------------------------------------------------------------------------------------ tensor-parallel exchange op
-// One-shot all-reduce over NVLink peer memory inside the step kernel, PUSH style.  The row-parallel linear op before it is the
-// sender: its tile epilogue stores every finished 16-row piece of this rank's partial straight into slot [s][rank] of EVERY rank's
-// symmetric buffer (remote st.global over NVLink, overlapped with the rest of the op), and the LAST CTA to finish the op — it sees
-// all others through the op's arrival counter, each of which fenced at system scope before arriving — publishes the slot's epoch
-// in every peer's signal pad (st.release.sys).  This op is the receiver: it waits on LOCAL flags (one per source rank), then every
-// CTA reduces ITS slice of the row (n / #CTAs floats) over the tp partials found in LOCAL memory, in rank order — bit-identical on
-// every rank — adds the residual and stores it.  One NVLink traversal on the critical path (the flag; the data went ahead of it)
-// instead of three (flag, remote-load request, remote-load reply).  Two slots alternate: a rank can be at most one exchange ahead of
-// its slowest peer, and a peer publishes exchange k + 1 only after all its CTAs finished reading exchange k.  The epoch counter of a
-// slot is advanced once per step by its last exchange; buffers, flags and counters of this protocol are disjoint from those of
-// lp_tp_allreduce_residual (the per-op pull kernel of prefill / batches), so the two may alternate freely.
+// One-shot all-reduce over NVLink peer memory inside the step kernel: PUSH style, flag in the data (the LL protocol of NCCL).
+// The row-parallel linear op before it is the sender: its tile epilogue stores every finished 16-row piece of this rank's partial
+// straight into slot [s][rank] of EVERY rank's symmetric buffer as 8-byte {value, epoch} pairs (remote st.global.v2 over NVLink:
+// an aligned 8-byte store is single-copy atomic, so a reader that sees the epoch sees the value), overlapped with the rest of the
+// op.  No fence, no flag, no counter crosses the link.  This op is the receiver: every CTA polls ITS slice of the row
+// (n / #CTAs elements x tp ranks, LOCAL memory) until all tags carry the slot's epoch, adds the tp values in rank order —
+// bit-identical on every rank — plus the residual and stores the row.  One NVLink traversal on the critical path (the pull protocol
+// of round 1 had three: flag, remote-load request, reply; a flag-after-data push still pays a system-scope fence per CTA and a
+// flag store per peer: measured 15-22 us per exchange at tp = 8).  `dep` = the sender op keeps the LOCAL ordering: this rank's x
+// may only be overwritten when all its CTAs are done reading it.  Two slots alternate; a slot's epoch grows by one per use, so
+// stale pairs of the previous use never match.  A rank can be at most one exchange ahead of its slowest peer (it needs that peer's
+// pairs to get past an exchange), so a slot is never rewritten while a peer still reads it.  Buffers and state of this protocol
+// are disjoint from lp_tp_allreduce_residual (the per-op pull kernel of prefill / batches): the two may alternate freely.
 __device__ __forceinline__ void ds_exchange(const DsParams& p, const DsOp& o, int op, unsigned int epoch0) {
   const int tid = threadIdx.x, tp = o.tp_size;
   const unsigned int epoch = epoch0 + (unsigned)o.tp_use + 1u;
-  if (tid < tp) {
-    const unsigned int* mine = reinterpret_cast<const unsigned int*>(o.tp_pads[o.tp_rank]) + o.tp_pad_base + tid;
-    unsigned int v, it = 0;
+  const int n = o.N;
+  const float2* local = reinterpret_cast<const float2*>(o.tp_bufs[o.tp_rank] + o.tp_buf_off);  // [tp][n] {value, epoch} pairs
+  const int i0 = (int)((long long)n * blockIdx.x / gridDim.x), i1 = (int)((long long)n * (blockIdx.x + 1) / gridDim.x);
+  for (int i = i0 + tid; i < i1; i += DS_CTHREADS) {
+    float2 v[DS_MAX_TP];
+    unsigned it = 0;
     const unsigned long long t0 = gs_now();
-    do {  // relaxed polls of the local pad word, one acquire fence at the end
-      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(mine) : "memory");
-      if ((int)(v - epoch) < 0 && p.timeout_ns) {  // a peer GPU that never publishes: watchdog (ds_report)
+    bool ok;
+    do {
+      ok = true;
+#pragma unroll
+      for (int r = 0; r < DS_MAX_TP; ++r) {
+        if (r < tp) {
+          const float2* src = local + (size_t)r * n + i;
+          asm volatile("ld.relaxed.sys.global.v2.f32 {%0,%1}, [%2];\n" : "=f"(v[r].x), "=f"(v[r].y) : "l"(src) : "memory");
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < DS_MAX_TP; ++r)
+        if (r < tp) ok &= __float_as_uint(v[r].y) == epoch;
+      if (!ok && p.timeout_ns) {  // a peer GPU that never delivers: watchdog (ds_report)
         const bool expired = gs_now() - t0 > p.timeout_ns;
-        if (expired) ds_report(p.err, DS_ERR_EXCHANGE_TIMEOUT, op, tid, v);
+        if (expired) ds_report(p.err, DS_ERR_EXCHANGE_TIMEOUT, op, i, __float_as_uint(v[0].y));
         if (expired || ((++it & 15u) == 0 && ds_ld_relaxed(p.err) != 0u)) break;
       }
-    } while ((int)(v - epoch) < 0);
-    asm volatile("fence.acq_rel.sys;\n" ::: "memory");
-  }
-  gs_bar_consumers();
-  const int n4 = o.N / 4;
-  const float4* local = reinterpret_cast<const float4*>(o.tp_bufs[o.tp_rank] + o.tp_buf_off);  // [tp][N] partials of this slot
-  const int i0 = (int)((long long)n4 * blockIdx.x / gridDim.x), i1 = (int)((long long)n4 * (blockIdx.x + 1) / gridDim.x);
-  for (int i = i0 + tid; i < i1; i += DS_CTHREADS) {
-    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    } while (!ok);
+    float sum = v[0].x;
 #pragma unroll
-    for (int r = 0; r < DS_MAX_TP; ++r) {
-      if (r < tp) {
-        const float4 v = __ldcg(local + (size_t)r * n4 + i);  // written by rank r over NVLink: read at L2, never through L1
-        if (r == 0) sum = v;
-        else { sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w; }
-      }
-    }
-    if (o.residual) {
-      const float4 rv = ds_ldcg4(o.residual + 4 * i);
-      sum.x += rv.x; sum.y += rv.y; sum.z += rv.z; sum.w += rv.w;
-    }
-    *reinterpret_cast<float4*>(o.out + 4 * i) = sum;
+    for (int r = 1; r < DS_MAX_TP; ++r)
+      if (r < tp) sum += v[r].x;
+    if (o.residual) sum += __ldcg(o.residual + i);
+    o.out[i] = sum;
   }
   // the last exchange of this slot in the step advances the shared epoch counter (every CTA read it at kernel start)
   if (blockIdx.x == 0 && tid == 0 && o.tp_use == o.tp_uses - 1) o.tp_state[0] = epoch0 + (unsigned)o.tp_uses;

@@ -248,19 +248,19 @@ class Engine:
         def row_parallel(W, src, dep, from_attn=False):
             """x += src . W^T.  Single GPU: in place (stage-granular split, atomic accumulation).  Tensor parallel: W is a column
             shard, the product a partial sum.  PUSH exchange: the linear op stores its partial into slot [s][rank] of EVERY rank's
-            symmetric buffer as its tiles finish and publishes the slot's epoch; the EXCHANGE op waits on local flags, adds the
-            tp partials found in local memory and the residual (one-shot NVLink all-reduce inside the kernel, one traversal)."""
+            symmetric buffer as {value, epoch} pairs while its tiles finish; the EXCHANGE op polls its slice of those pairs in local
+            memory, adds the tp values and the residual (one-shot NVLink all-reduce inside the kernel, one traversal, no fence)."""
             if tp is None:
                 return linear(W, src, None, _lib.LP_EPI_RESIDUAL, x, x, dep, from_attn=from_attn)
             slot = n_exch[0] % 2
             n_exch[0] += 1
-            slot_base = tp.push_off + slot * tp.size * E * 4
+            slot_base = tp.push_off + slot * tp.size * E * 8  # {value, epoch} pairs: 8 bytes per element
             pad_base = tp.push_pad + slot * tp.size
             state = tp.push_state[slot].data_ptr()
-            i_part = linear(W, src, None, _lib.LP_EPI_NONE, None, tp.buf.data_ptr() + slot_base + tp.rank * E * 4, dep, from_attn=from_attn)
+            i_part = linear(W, src, None, _lib.LP_EPI_NONE, None, tp.buf.data_ptr() + slot_base + tp.rank * E * 8, dep, from_attn=from_attn)
             snd = ops[i_part]
             snd.tp_buf_ptrs, snd.tp_pad_ptrs, snd.tp_state = tp.buf_ptrs, tp.pad_ptrs, state
-            snd.tp_buf_offset, snd.tp_pad_base, snd.tp_rank, snd.tp_size = slot_base + tp.rank * E * 4, pad_base, tp.rank, tp.size
+            snd.tp_buf_offset, snd.tp_pad_base, snd.tp_rank, snd.tp_size = slot_base + tp.rank * E * 8, pad_base, tp.rank, tp.size
             op = _lib.LpStepOp()
             op.kind, op.dep, op.norm_kind = _lib.LP_STEP_EXCHANGE, i_part, -1
             op.tp_buf_ptrs, op.tp_pad_ptrs, op.tp_state = tp.buf_ptrs, tp.pad_ptrs, state

@@ -55,9 +55,11 @@ class TPContext:
         self.slot_floats = max_rows * n_embd
         self.n_embd = n_embd
         # [2 slots][max_rows * E]: pull protocol of the per-op kernel (lp_tp_allreduce_residual: prefill, batches > 1), then
-        # [2 slots][size ranks][E]: push protocol of the step kernel (batch-1 decode; every rank's partial lands in every buffer)
+        # [2 slots][size ranks][E] {value, epoch} pairs: push protocol of the step kernel (batch-1 decode; every rank's partial
+        # lands in every buffer, 8 bytes per element)
         self.push_off = 2 * self.slot_floats * 4
-        self.buf = symm.empty(2 * self.slot_floats + 2 * self.size * n_embd, dtype=torch.float32, device=device)
+        self.buf = symm.empty(2 * self.slot_floats + 2 * self.size * n_embd * 2, dtype=torch.float32, device=device)
+        self.buf.zero_()
         self.hdl = symm.rendezvous(self.buf, group)
         if self.hdl.signal_pad_size < 4 * self.size * 4:
             raise RuntimeError("symmetric-memory signal pad too small")
@@ -92,7 +94,7 @@ class LoopbackTPContext:
         self.slot_floats = max_rows * n_embd
         self.n_embd = n_embd
         self.push_off = 2 * self.slot_floats * 4
-        self.buf = torch.zeros(2 * self.slot_floats + 2 * n_embd, dtype=torch.float32, device=device)
+        self.buf = torch.zeros(2 * self.slot_floats + 2 * n_embd * 2, dtype=torch.float32, device=device)
         self.pad = torch.zeros(64, dtype=torch.int32, device=device)
         self.push_state = torch.zeros(2, 2, dtype=torch.int32, device=device)
         self.push_pad = 2

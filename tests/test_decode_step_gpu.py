@@ -200,7 +200,7 @@ def test_step_kernel_exchange_op_self():
     pos = torch.zeros(1, dtype=torch.int32, device=DEV)
     x = torch.zeros(E, device=DEV)
     logits = torch.zeros(V, device=DEV)
-    buf = torch.zeros(3 * E, device=DEV)                      # push slots 0 / 1 ([1 rank][E] each), then a pull-protocol slot
+    buf = torch.zeros(5 * E, device=DEV)                      # push slots 0 / 1 ([1 rank][E] {value, epoch} pairs each), then a pull slot
     pad = torch.zeros(64, dtype=torch.int32, device=DEV)      # push: words 0, 1 (slot s, rank 0); pull: word 8
     state = torch.zeros(2, 2, dtype=torch.int32, device=DEV)  # push protocol
     pull_state = torch.zeros(2, dtype=torch.int32, device=DEV)
@@ -211,7 +211,7 @@ def test_step_kernel_exchange_op_self():
 
     def tp_fields(o, slot):
         o.tp_buf_ptrs, o.tp_pad_ptrs, o.tp_state = bufs.data_ptr(), pads.data_ptr(), state[slot].data_ptr()
-        o.tp_buf_offset, o.tp_pad_base, o.tp_rank, o.tp_size = slot * E * 4, slot, 0, 1
+        o.tp_buf_offset, o.tp_pad_base, o.tp_rank, o.tp_size = slot * E * 8, slot, 0, 1
 
     def lin(i, rec, out, dep, slot=None):
         ops[i].kind, ops[i].dep, ops[i].W, ops[i].x, ops[i].norm_kind = _lib.LP_STEP_LINEAR, dep, ctypes.pointer(rec), x.data_ptr(), -1
@@ -226,7 +226,7 @@ def test_step_kernel_exchange_op_self():
 
     lin(0, recs[0], buf.data_ptr(), -1, slot=0)
     exch(1, 0, 0)
-    lin(2, recs[1], buf.data_ptr() + E * 4, 1, slot=1)
+    lin(2, recs[1], buf.data_ptr() + E * 8, 1, slot=1)
     exch(3, 1, 2)
     lin(4, recs[2], logits.data_ptr(), 3)
     ws = torch.zeros(lib.lp_decode_step_workspace_bytes(1, 64), dtype=torch.uint8, device=DEV)
@@ -249,12 +249,12 @@ def test_step_kernel_exchange_op_self():
         torch.testing.assert_close(logits, want, rtol=1e-4, atol=1e-4)
         torch.testing.assert_close(x, x2.float(), rtol=1e-4, atol=1e-4)
         # the per-op pull exchange in between (prefill path): disjoint slot, pad word and state
-        buf[2 * E:].copy_(torch.arange(E, device=DEV).float())
+        buf[4 * E:].copy_(torch.arange(E, device=DEV).float())
         tmp = torch.zeros(E, device=DEV)
-        _lib.check(lib.lp_tp_allreduce_residual(bufs.data_ptr(), pads.data_ptr(), 0, 1, 2 * E * 4, 8, pull_state.data_ptr(), E, None,
+        _lib.check(lib.lp_tp_allreduce_residual(bufs.data_ptr(), pads.data_ptr(), 0, 1, 4 * E * 4, 8, pull_state.data_ptr(), E, None,
                                                 tmp.data_ptr(), 0, stream), "lp_tp_allreduce_residual")
         torch.cuda.synchronize()
-        torch.testing.assert_close(tmp, buf[2 * E:])
+        torch.testing.assert_close(tmp, buf[4 * E:])
     assert state[0, 0].item() == 3 and state[1, 0].item() == 3 and pull_state[0].item() == 3
     assert lib.lp_decode_step_status(ctypes.byref(handle), None) == 0
 
