@@ -1530,35 +1530,35 @@ __device__ __forceinline__ void ds_exchange(const DsParams& p, const DsOp& o, in
   const int n = o.N;
   const float2* local = reinterpret_cast<const float2*>(o.tp_bufs[o.tp_rank] + o.tp_buf_off);  // [tp][n] {value, epoch} pairs
   const int i0 = (int)((long long)n * blockIdx.x / gridDim.x), i1 = (int)((long long)n * (blockIdx.x + 1) / gridDim.x);
-  for (int i = i0 + tid; i < i1; i += DS_CTHREADS) {
-    float2 v[DS_MAX_TP];
-    unsigned it = 0;
-    const unsigned long long t0 = gs_now();
-    bool ok;
-    do {
-      ok = true;
-#pragma unroll
-      for (int r = 0; r < DS_MAX_TP; ++r) {
-        if (r < tp) {
-          const float2* src = local + (size_t)r * n + i;
-          asm volatile("ld.relaxed.sys.global.v2.f32 {%0,%1}, [%2];\n" : "=f"(v[r].x), "=f"(v[r].y) : "l"(src) : "memory");
+  // one thread per (element, rank): 8 neighbouring lanes hold the tp pairs of one element, every thread polls ONE pair (all loads of
+  // the slice are in flight at once: the op is a single L2 / NVLink latency, not tp of them), then a fixed shuffle tree adds them —
+  // the same tree on every GPU, so the sums are bit-identical across ranks (rank order within the tree: ((0+1)+(2+3))+((4+5)+(6+7)))
+  for (int base = i0; base < i1; base += DS_CTHREADS / DS_MAX_TP) {
+    const int i = base + (tid >> 3), r = tid & (DS_MAX_TP - 1);
+    float val = 0.f;
+    if (i < i1 && r < tp) {
+      const float2* src = local + (size_t)r * n + i;
+      float2 v;
+      unsigned it = 0;
+      const unsigned long long t0 = gs_now();
+      for (;;) {
+        asm volatile("ld.relaxed.sys.global.v2.f32 {%0,%1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "l"(src) : "memory");
+        if (__float_as_uint(v.y) == epoch) break;
+        if (p.timeout_ns) {  // a peer GPU that never delivers: watchdog (ds_report)
+          const bool expired = gs_now() - t0 > p.timeout_ns;
+          if (expired) ds_report(p.err, DS_ERR_EXCHANGE_TIMEOUT, op, r, __float_as_uint(v.y));
+          if (expired || ((++it & 15u) == 0 && ds_ld_relaxed(p.err) != 0u)) break;
         }
       }
-#pragma unroll
-      for (int r = 0; r < DS_MAX_TP; ++r)
-        if (r < tp) ok &= __float_as_uint(v[r].y) == epoch;
-      if (!ok && p.timeout_ns) {  // a peer GPU that never delivers: watchdog (ds_report)
-        const bool expired = gs_now() - t0 > p.timeout_ns;
-        if (expired) ds_report(p.err, DS_ERR_EXCHANGE_TIMEOUT, op, i, __float_as_uint(v[0].y));
-        if (expired || ((++it & 15u) == 0 && ds_ld_relaxed(p.err) != 0u)) break;
-      }
-    } while (!ok);
-    float sum = v[0].x;
-#pragma unroll
-    for (int r = 1; r < DS_MAX_TP; ++r)
-      if (r < tp) sum += v[r].x;
-    if (o.residual) sum += __ldcg(o.residual + i);
-    o.out[i] = sum;
+      val = v.x;
+    }
+    val += __shfl_xor_sync(0xffffffffu, val, 1);
+    val += __shfl_xor_sync(0xffffffffu, val, 2);
+    val += __shfl_xor_sync(0xffffffffu, val, 4);
+    if (i < i1 && r == 0) {
+      if (o.residual) val += __ldcg(o.residual + i);
+      o.out[i] = val;
+    }
   }
   // the last exchange of this slot in the step advances the shared epoch counter (every CTA read it at kernel start)
   if (blockIdx.x == 0 && tid == 0 && o.tp_use == o.tp_uses - 1) o.tp_state[0] = epoch0 + (unsigned)o.tp_uses;

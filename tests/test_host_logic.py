@@ -1,5 +1,6 @@
 """Host-side logic that needs no GPU: module tree / state-dict contract, plug-in switch, error behaviour,
 generate() driving a foreign (CPU) model with the reference's semantics."""
+import os
 from unittest import mock
 
 import numpy as np
@@ -126,3 +127,21 @@ def test_generate_foreign_eos_cut():
     first = int((full[3:] == eos).nonzero()[0]) + 3
     cut = lp.generate(model, prompt, 20, top_k=1, eos_id=eos)
     assert torch.equal(cut, full[:first])  # idx[:input_pos] excludes the EOS itself (generate/base.py:156-157)
+
+
+def test_step_kernel_register_budget():
+    """decode_step_kernel is ONE function holding every op kind of the step (linear formats, attention, slab, exchange); its register
+    allocation is global, and an innocent-looking change in a cold path once pushed spills into the hot loops (stablelm-3b 690 ->
+    640 tok/s with 626 instead of 264 bytes of spill stores).  Keep the spill volume of the shipped source under watch."""
+    import re
+    import subprocess
+
+    from lit_parrot_b200 import build as b
+
+    src = os.path.join(b.CSRC, "decode_step.cu")
+    cmd = [b._nvcc(), *b.NVCC_FLAGS, "-Xptxas=-v", "-c", src, "-o", os.devnull]
+    out = subprocess.run(cmd, capture_output=True, text=True).stderr
+    blocks = re.findall(r"Function properties for (\S*decode_step_kernel\S*)\s+(\d+) bytes stack frame, (\d+) bytes spill stores", out)
+    assert len(blocks) == 2, out[-2000:]
+    for name, _stack, stores in blocks:
+        assert int(stores) <= 400, f"{name}: {stores} bytes of spill stores (budget 400; 264 when this test was written)"
