@@ -1,0 +1,9 @@
+"""`python generate/adapter_v2.py` (reference: generate/adapter_v2.py) backed by lit_parrot_b200."""
+from lit_parrot_b200.cli_finetuned import generate_prompt  # noqa: F401
+from lit_parrot_b200.cli_finetuned import main_adapter_v2 as main  # noqa: F401
+from lit_parrot_b200.generate import generate  # noqa: F401
+
+if __name__ == "__main__":
+    from lit_parrot_b200.cli import CLI
+
+    CLI(main)

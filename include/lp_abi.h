@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LP_ABI_VERSION 5
+#define LP_ABI_VERSION 6
 
 typedef enum {
   LP_OK = 0,
@@ -83,6 +83,8 @@ typedef struct {
   int32_t group;       /* INT4: columns per scale/zero group (K for per-row); NF4: blocksize            */
   int32_t flags;       /* LP_WF_*                                                                        */
   int32_t reserved;
+  const float* out_bias;   /* adapter-v2 (lit_gpt/adapter_v2.py:34-35), fp32 [N] or NULL: y = out_scale * ((x.W^T + bias) + out_bias),  */
+  const float* out_scale;  /* evaluated in that order BEFORE the epilogue's activation / residual (bf16 mode: rounded after each step) */
 } lp_weight;
 
 int lp_abi_version(void);
@@ -156,6 +158,10 @@ int lp_split_bf16(const float* x, void* out_bf16, int rows, int K, int nterms, i
                   const float* norm_b, float eps, int round_bf16, void* stream);
 int lp_gemm_bf16_tc(const void* x_terms, int nterms, int M, const void* w_bf16, int N, int K, const float* bias, int epilogue,
                     const float* residual, float* out_f32, void* out_bf16, int out_terms, int round_bf16, void* stream);
+/* The same with the adapter-v2 output affine of lp_weight (out_bias / out_scale, fp32 [N] or NULL). */
+int lp_gemm_bf16_tc_affine(const void* x_terms, int nterms, int M, const void* w_bf16, int N, int K, const float* bias,
+                           const float* out_bias, const float* out_scale, int epilogue, const float* residual, float* out_f32,
+                           void* out_bf16, int out_terms, int round_bf16, void* stream);
 /* W in any lp_wfmt -> dense bf16 [N, K] (int4 / NF4 rounded to bf16 like the reference's bf16 dequantisation). */
 int lp_dequant_bf16(const lp_weight* W, void* out_bf16, void* stream);
 
@@ -197,6 +203,23 @@ int lp_attn_decode_fused(const float* qkv, const float* cos, const float* sin, c
 int lp_set_attn_prefill_path(int path);
 int lp_attn_prefill(const float* q, const void* k_cache, const void* v_cache, int kv_dtype, const int32_t* pos, float* out, int B,
                     int T, int H, int G, int hs, int max_seq, float scale, int round_bf16, void* stream);
+
+/* LLaMA-Adapter prefix attention (lit_gpt/adapter.py:234-254): for every query row r = b*T + t and head h
+ *   out[r, h, :] += gating[h] * softmax(scale * q_rot[r, h] . ak[g(h)]^T) . av[g(h)]
+ * over the aT adaption-prompt keys (no mask), added to the causal attention output `out` [B*T, H*hs] in place.  q is taken
+ * from the raw QKV projection (layout of lp_rope_kv_append) and rotated here with the row's RoPE entries (pos int32 [T]); the prefix
+ * keys / values ak, av fp32 [G, aT, hs] are the k / v parts of attn.attn(adapter_wte.weight), NOT rotated (adapter.py:238-249:
+ * the reference caches them as adapter_kv_cache).  gating fp32 [H] (gating_factor (1, H, 1, 1)).  aT <= 64, hs <= 256. */
+int lp_adapter_attn(const float* qkv, const float* cos, const float* sin, const int32_t* pos, const float* ak, const float* av,
+                    const float* gating, float* out, int B, int T, int H, int G, int hs, int n_elem, int aT, float scale,
+                    int round_bf16, void* stream);
+
+/* load time: merged-LoRA weights (lit_gpt/lora.py:154-164, 338-361): W[N, K] += scaling * (B[N, r] . A[r, K]) restricted to the
+ * rows listed in `rows` (int32 [n_rows], NULL = all N rows; LoRAQKVLinear.zero_pad scatters the update to lora_ind),
+ * W in fp32 or bf16 (w_dtype: lp_dtype; the sum is rounded once to the stored dtype, like `weight.data += delta`).
+ * B_rows fp32 [n_rows, r] row-major, A fp32 [r, K]. */
+int lp_lora_merge(void* W, int w_dtype, int N, int K, const float* B_rows, const float* A, int r, const int32_t* rows, int n_rows,
+                  float scaling, void* stream);
 
 /* ---- the whole single-token decode step (batch 1) as ONE persistent kernel ------------------------------------------
  * replaces GPT.forward for T == 1 (model.py:63-111 -> Block.forward 158-180 -> CausalSelfAttention.forward 194-254 -> MLP

@@ -17,7 +17,7 @@ LP_F32, LP_BF16 = 0, 1
 LP_W_F32, LP_W_BF16, LP_W_INT4, LP_W_NF4, LP_W_INT8 = 0, 1, 2, 3, 4
 LP_EPI_NONE, LP_EPI_GELU, LP_EPI_SWIGLU, LP_EPI_RESIDUAL = 0, 1, 2, 3
 LP_NORM_LAYERNORM, LP_NORM_RMS = 0, 1
-LP_ABI_VERSION = 5
+LP_ABI_VERSION = 6
 LP_WF_AUX_PACKED = 1
 LP_WF_AUX_TILED = 2
 LP_STEP_LINEAR, LP_STEP_ATTENTION, LP_STEP_EXCHANGE, LP_STEP_SLAB = 0, 1, 2, 3
@@ -30,7 +30,7 @@ class LpWeight(ctypes.Structure):
 
     _fields_ = [("w", c_void_p), ("aux0", c_void_p), ("aux1", c_void_p), ("aux2", c_void_p), ("bias", c_void_p),
                 ("fmt", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32), ("group", ctypes.c_int32),
-                ("flags", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("flags", ctypes.c_int32), ("reserved", ctypes.c_int32), ("out_bias", c_void_p), ("out_scale", c_void_p)]
 
 
 class LpStepOp(ctypes.Structure):
@@ -88,6 +88,11 @@ PROTOTYPES = {
     "lp_split_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p]),
     "lp_gemm_bf16_tc": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                 c_int, c_void_p]),
+    "lp_gemm_bf16_tc_affine": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                       c_void_p, c_int, c_int, c_void_p]),
+    "lp_adapter_attn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "lp_lora_merge": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_float, c_void_p]),
     "lp_dequant_bf16": (c_int, [ctypes.POINTER(LpWeight), c_void_p, c_void_p]),
     "lp_rope_kv_append": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

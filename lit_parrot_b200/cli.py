@@ -106,13 +106,20 @@ def main(
 
 
 def CLI(fn, argv=None):
-    """`jsonargparse.CLI(main)` for the two entry points: positional / --keyword arguments from the function signature."""
+    """`jsonargparse.CLI(main)` for the entry points: every parameter of the function is a `--name value` option (jsonargparse
+    turns parameters with defaults into options); the first parameter may also be given positionally."""
     sig = inspect.signature(fn)
     ap = argparse.ArgumentParser(description=(fn.__doc__ or "").strip().splitlines()[0] if fn.__doc__ else None)
+    first = None
     for name, p in sig.parameters.items():
         typ = {int: int, float: float, str: str, Path: Path}.get(type(p.default), str)
-        if p.kind is inspect.Parameter.KEYWORD_ONLY:
-            ap.add_argument(f"--{name}", type=typ, default=p.default)
-        else:
-            ap.add_argument(name, type=typ, nargs="?", default=p.default)
-    return fn(**vars(ap.parse_args(argv)))
+        ap.add_argument(f"--{name}", type=typ, default=p.default)
+        if first is None and p.kind is not inspect.Parameter.KEYWORD_ONLY:
+            first = name
+            ap.add_argument(f"{name}_positional", type=typ, nargs="?", default=None, metavar=name)
+    args = vars(ap.parse_args(argv))
+    if first is not None:
+        pos = args.pop(f"{first}_positional")
+        if pos is not None:
+            args[first] = pos
+    return fn(**args)

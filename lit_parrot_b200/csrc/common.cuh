@@ -55,6 +55,14 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 __device__ __forceinline__ float maybe_round(float v, int round_bf16) { return round_bf16 ? bf16_round(v) : v; }
 
+// adapter-v2 output affine (lit_gpt/adapter_v2.py:34-35): adapter_scale * (linear(x) + adapter_bias), `y` = linear(x) incl. its own
+// bias (already rounded in bf16 mode); each step rounded where the reference's bf16-true run rounds
+__device__ __forceinline__ float out_affine(float y, const float* __restrict__ ob, const float* __restrict__ os, int n, int round_bf16) {
+  if (ob) y = maybe_round(y + ob[n], round_bf16);
+  if (os) y = maybe_round(os[n] * y, round_bf16);
+  return y;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

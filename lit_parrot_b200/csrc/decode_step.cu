@@ -2062,6 +2062,7 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
       if (!s.W || !s.out || !s.slab_image || !s.slab_meta || i == 0 || s.slab_src < 0 || s.slab_src > 1) return LP_ERR_INVALID_ARG;
       const lp_weight& W = *s.W;
       if (W.fmt != LP_W_INT4 || W.group != 128 || !(W.flags & LP_WF_AUX_PACKED) || W.N % DS_SLAB_ROWS) return LP_ERR_UNSUPPORTED;
+      if (W.out_bias || W.out_scale) return LP_ERR_UNSUPPORTED;  // adapter-v2 models take the per-op path
       const lp_step_op& prev = ops[i - 1];
       if (s.slab_src == 0) {  // columns = SwiGLU outputs of the preceding up-projection, kept in shared memory
         if (prev.kind != LP_STEP_LINEAR || !prev.keep_local || prev.epilogue != LP_EPI_SWIGLU || !prev.W || prev.W->N != 2 * W.K ||
@@ -2129,6 +2130,7 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
     const lp_weight& W = *s.W;
     if (!W.w || W.N <= 0 || W.K <= 0) return LP_ERR_INVALID_ARG;
     if (W.fmt != LP_W_BF16 && W.fmt != LP_W_INT4 && W.fmt != LP_W_NF4 && W.fmt != LP_W_INT8) return LP_ERR_UNSUPPORTED;
+    if (W.out_bias || W.out_scale) return LP_ERR_UNSUPPORTED;  // adapter-v2 output affine: the per-op kernels carry it
     if (W.N % GS_ROWS || W.K % 16 || W.K > 6 * DS_CTHREADS * 8 || (reinterpret_cast<uintptr_t>(W.w) & 15)) return LP_ERR_UNSUPPORTED;
     if (s.epilogue < LP_EPI_NONE || s.epilogue > LP_EPI_RESIDUAL) return LP_ERR_INVALID_ARG;
     if (s.epilogue == LP_EPI_RESIDUAL && !s.residual) return LP_ERR_INVALID_ARG;

@@ -145,6 +145,8 @@ __device__ long long g_tc_debug[4];
 
 struct TcParams {
   const float* bias;      // [N] or NULL
+  const float* out_bias;  // adapter-v2 output affine (lp_weight.out_bias / out_scale), [N] or NULL
+  const float* out_scale;
   const float* residual;  // [M, N] or NULL
   float* out_f32;         // [M, Nout] or NULL
   __nv_bfloat16* out_bf;  // [out_terms][M, Nout] bf16 split of the result, or NULL
@@ -169,6 +171,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tac
         float t = __uint_as_float(v[j]);
         if (p.bias && n < p.N) t += p.bias[n];
         y[j] = maybe_round(t, p.round_bf16);
+        if ((p.out_bias || p.out_scale) && n < p.N) y[j] = out_affine(y[j], p.out_bias, p.out_scale, n, p.round_bf16);
       }
       int ncols = 32, ocol = n0 + c0;
       if (swiglu) {  // W rows interleaved: column 2i = fc_1 row i, 2i+1 = fc_2 row i (model.py:298-300)
@@ -585,6 +588,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 // ---------------------------------------------------------------------------------------------------------------------
 struct TcSwapParams {
   const float* bias;
+  const float* out_bias;  // adapter-v2 output affine, [N] or NULL
+  const float* out_scale;
   const float* residual;
   float* out_f32;
   __nv_bfloat16* out_bf;
@@ -736,6 +741,9 @@ gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       tc_mbar_wait(acc_full(a), (it >> 1) & 1);
       tc_fence_after();
       const float bias = (p.bias && n < p.N && first) ? p.bias[n] : 0.f;
+      const bool affine = p.out_bias || p.out_scale;  // adapter-v2: scale * ((acc + bias) + out_bias); K-split partials: biases once
+      const float obv = (p.out_bias && n < p.N && first) ? p.out_bias[n] : 0.f;
+      const float osv = (p.out_scale && n < p.N) ? p.out_scale[n] : 1.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < p.NB; c0 += 32) {
         // the accumulator holds one column block per activation term (term t of batch row m: column t*NB + m): add them
@@ -754,6 +762,7 @@ gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           const int m = c0 + j;  // batch row (warp-uniform)
           if (m < p.M) {
             float y = maybe_round(acc[j] + bias, p.round_bf16);
+            if (affine) y = maybe_round(osv * maybe_round(y + obv, p.round_bf16), p.round_bf16);
             int oc = n;
             bool store = n < p.N;
             if (swiglu) {  // W rows interleaved: row 2i = fc_1 row i, 2i+1 = fc_2 row i (model.py:298-300): neighbouring lanes
@@ -1112,6 +1121,13 @@ int lp_split_bf16(const float* x, void* out_bf16, int rows, int K, int nterms, i
 
 int lp_gemm_bf16_tc(const void* x_terms, int nterms, int M, const void* w_bf16, int N, int K, const float* bias, int epilogue,
                     const float* residual, float* out_f32, void* out_bf16, int out_terms, int round_bf16, void* stream) {
+  return lp_gemm_bf16_tc_affine(x_terms, nterms, M, w_bf16, N, K, bias, nullptr, nullptr, epilogue, residual, out_f32, out_bf16, out_terms,
+                                round_bf16, stream);
+}
+
+int lp_gemm_bf16_tc_affine(const void* x_terms, int nterms, int M, const void* w_bf16, int N, int K, const float* bias,
+                           const float* out_bias, const float* out_scale, int epilogue, const float* residual, float* out_f32,
+                           void* out_bf16, int out_terms, int round_bf16, void* stream) {
   if (!x_terms || !w_bf16 || M <= 0 || N <= 0 || K <= 0 || nterms < 1 || nterms > 3) return LP_ERR_INVALID_ARG;
   if (!out_f32 && !out_bf16) return LP_ERR_INVALID_ARG;
   if (out_bf16 && (out_terms < 1 || out_terms > 3)) return LP_ERR_INVALID_ARG;
@@ -1123,6 +1139,8 @@ int lp_gemm_bf16_tc(const void* x_terms, int nterms, int M, const void* w_bf16, 
     // decode batches: swap-AB (weights = 128-row A operand, batch = N of the MMA), see gemm_tc_swap_kernel
     lp::TcSwapParams q;
     q.bias = bias;
+    q.out_bias = out_bias;
+    q.out_scale = out_scale;
     q.residual = residual;
     q.out_f32 = out_f32;
     q.out_bf = reinterpret_cast<__nv_bfloat16*>(out_bf16);
@@ -1183,7 +1201,7 @@ int lp_gemm_bf16_tc(const void* x_terms, int nterms, int M, const void* w_bf16, 
     const CUtensorMap* mw2 = lp::tc_cached_map(w_bf16, N, K, 128);
     if (mx2 && mw2) {
       lp::TcParams q;
-      q.bias = bias; q.residual = residual; q.out_f32 = out_f32; q.out_bf = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+      q.bias = bias; q.out_bias = out_bias; q.out_scale = out_scale; q.residual = residual; q.out_f32 = out_f32; q.out_bf = reinterpret_cast<__nv_bfloat16*>(out_bf16);
       q.M = M; q.N = N; q.K = K; q.epi = epilogue; q.round_bf16 = round_bf16; q.nterms = nterms; q.out_terms = out_terms;
       q.debug = 0; q.l2_ahead = 0;
       return lp::tc_launch_pair(*mx2, *mw2, q, stream);
@@ -1195,6 +1213,8 @@ int lp_gemm_bf16_tc(const void* x_terms, int nterms, int M, const void* w_bf16, 
   if (!mx || !mw) return LP_ERR_UNSUPPORTED;
   lp::TcParams p;
   p.bias = bias;
+  p.out_bias = out_bias;
+  p.out_scale = out_scale;
   p.residual = residual;
   p.out_f32 = out_f32;
   p.out_bf = reinterpret_cast<__nv_bfloat16*>(out_bf16);

@@ -186,6 +186,8 @@ linear_fma_kernel(const float* __restrict__ x, int m_actual, lp_weight W, int ep
     }
     y0 = maybe_round(y0, round_bf16);
     y1 = maybe_round(y1, round_bf16);
+    y0 = out_affine(y0, W.out_bias, W.out_scale, r0, round_bf16);
+    y1 = out_affine(y1, W.out_bias, W.out_scale, has1 ? r0 + 1 : r0, round_bf16);
     if (epi == LP_EPI_SWIGLU) {
       // rows (2i, 2i+1) = (fc_1 row i, fc_2 row i): silu(a) * b, each step rounded in bf16 mode (model.py:300)
       const float a = maybe_round(silu(y0), round_bf16);

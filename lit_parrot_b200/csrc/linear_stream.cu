@@ -464,6 +464,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) linear_stream_kernel(const __gr
         const int row = tile * GS_ROWS + rr;
         if (p.W.bias) y += p.W.bias[row];
         y = maybe_round(y, p.round_bf16);
+        y = out_affine(y, p.W.out_bias, p.W.out_scale, row, p.round_bf16);
         if (p.epi == LP_EPI_SWIGLU) {
           const float other = __shfl_xor_sync(0xffffffffu, y, 1);  // fc_2 row of the pair
           if (half == 0 && (rr & 1) == 0) {

@@ -26,11 +26,14 @@ class PackedLinear:
 
     def __init__(self, w: torch.Tensor, fmt: int, N: int, K: int, bias: Optional[torch.Tensor] = None,
                  aux0: Optional[torch.Tensor] = None, aux1: Optional[torch.Tensor] = None, group: int = 0,
-                 aux2: Optional[torch.Tensor] = None, flags: int = 0) -> None:
+                 aux2: Optional[torch.Tensor] = None, flags: int = 0, out_bias: Optional[torch.Tensor] = None,
+                 out_scale: Optional[torch.Tensor] = None) -> None:
         assert w.is_contiguous()
         self.keep = (w, bias, aux0, aux1, aux2)
+        self.affine = (out_bias, out_scale)  # adapter v2: scale * (linear(x) + bias), fp32 [N] each (adapter_v2.py:34-35)
         self.N, self.K, self.fmt = N, K, fmt
-        self.rec = LpWeight(_ptr(w), _ptr(aux0), _ptr(aux1), _ptr(aux2), _ptr(bias), fmt, N, K, group, flags, 0)
+        self.rec = LpWeight(_ptr(w), _ptr(aux0), _ptr(aux1), _ptr(aux2), _ptr(bias), fmt, N, K, group, flags, 0, _ptr(out_bias),
+                            _ptr(out_scale))
         self.ref = ctypes.byref(self.rec)
 
     @property
@@ -58,7 +61,8 @@ def pack_linear(mod: torch.nn.Module) -> PackedLinear:
     if not w.is_contiguous():
         w = w.contiguous()
         mod.weight.data = w
-    return PackedLinear(w, _FMT_OF_DTYPE[w.dtype], w.shape[0], w.shape[1], bias=_f32(getattr(mod, "bias", None)))
+    return PackedLinear(w, _FMT_OF_DTYPE[w.dtype], w.shape[0], w.shape[1], bias=_f32(getattr(mod, "bias", None)),
+                        out_bias=_f32(getattr(mod, "adapter_bias", None)), out_scale=_f32(getattr(mod, "adapter_scale", None)))
 
 
 def pack_swiglu(fc_1: torch.nn.Module, fc_2: torch.nn.Module) -> PackedLinear:
@@ -81,10 +85,13 @@ def pack_swiglu(fc_1: torch.nn.Module, fc_2: torch.nn.Module) -> PackedLinear:
         inter[1::2].copy_(w2)
         fc_1.weight.data = inter[0::2]
         fc_2.weight.data = inter[1::2]
-    bias = None
-    if getattr(fc_1, "bias", None) is not None:
-        bias = torch.stack((fc_1.bias.data.float(), fc_2.bias.data.float()), dim=1).reshape(-1).contiguous()
-    return PackedLinear(inter, _FMT_OF_DTYPE[inter.dtype], 2 * I, E, bias=bias)
+    def pair(name):  # per-row vectors of the two layers, interleaved like the rows
+        if getattr(fc_1, name, None) is None:
+            return None
+        return torch.stack((getattr(fc_1, name).data.float(), getattr(fc_2, name).data.float()), dim=1).reshape(-1).contiguous()
+
+    return PackedLinear(inter, _FMT_OF_DTYPE[inter.dtype], 2 * I, E, bias=pair("bias"), out_bias=pair("adapter_bias"),
+                        out_scale=pair("adapter_scale"))
 
 
 class _Layer:
@@ -126,6 +133,10 @@ class Engine:
             else:
                 L.fc = pack_linear(blk.mlp.fc)
             L.mlp_proj = pack_linear(blk.mlp.proj)
+            # LLaMA-Adapter (lit_gpt/adapter.py:171-177): adaption prompt embedding + per-head gate of the adapted layers
+            L.adapter = None
+            if hasattr(blk.attn, "adapter_wte"):
+                L.adapter = dict(wte=_f32(blk.attn.adapter_wte.weight), gate=_f32(blk.attn.gating_factor).reshape(-1).contiguous(), kv=None)
             self.layers.append(L)
         self.lnf_w, self.lnf_b = _f32(model.transformer.ln_f.weight), _f32(getattr(model.transformer.ln_f, "bias", None))
         self.lm_head = pack_linear(model.lm_head)
@@ -135,7 +146,12 @@ class Engine:
         self._scratch: Optional[Tuple] = None
         self._consecutive = False
         # batch-1 decode: the whole step as one persistent kernel (lp_decode_step) where the library covers the model
-        self.use_step_kernel = os.environ.get("LP_DECODE_STEP", "1") != "0" and bool(getattr(model, "use_step_kernel", True))
+        self.has_adapter = any(L.adapter is not None for L in self.layers)
+        if self.has_adapter and self.tp is not None:
+            raise NotImplementedError("adapter models are not sharded tensor-parallel")
+        # adapter models take the per-op path (the prefix attention is its own launch; the v2 output affine is refused by the plan)
+        self.use_step_kernel = (os.environ.get("LP_DECODE_STEP", "1") != "0" and bool(getattr(model, "use_step_kernel", True))
+                                and not self.has_adapter)
         self._steps: Dict[Tuple, Optional[Tuple]] = {}
         self._flag = torch.zeros(1, dtype=torch.int32).pin_memory()  # mapped host word written by lp_validate_inputs
         self._slabs = None  # fused column->row pairs of the step kernel: None = not decided yet, False = not applicable
@@ -157,6 +173,49 @@ class Engine:
     def drop_graphs(self) -> None:
         self._graphs.clear()
         self._steps.clear()
+
+    # ------------------------------------------------------------------ LLaMA-Adapter prefix keys / values (load time)
+    def _adapter_kv(self, L, stream: int):
+        """(ak, av) fp32 [G, aT, hs] of an adapted layer: the k / v parts of attn.attn(adapter_wte.weight) (adapter.py:238-249, incl.
+        the v2 output affine of attn.attn), computed once — the reference caches them as `adapter_kv_cache` as well."""
+        ad = L.adapter
+        if ad["kv"] is None:
+            cfg = self.cfg
+            aT, G, qpk, hs = ad["wte"].shape[0], cfg.n_query_groups, cfg.q_per_kv, cfg.head_size
+            pre = torch.empty((aT, cfg.qkv_rows), device=self.device, dtype=torch.float32)
+            for r0 in range(0, aT, 8):  # lp_linear rows per call
+                m = min(8, aT - r0)
+                _lib.check(self.lib.lp_linear(ad["wte"][r0:].data_ptr(), m, L.qkv.ref, _lib.LP_EPI_NONE, None, pre[r0:].data_ptr(),
+                                              self.round, stream), "lp_linear(adapter prefix)")
+            pre = pre.view(aT, G, qpk + 2, hs)
+            ad["kv"] = (pre[:, :, qpk].permute(1, 0, 2).contiguous(), pre[:, :, qpk + 1].permute(1, 0, 2).contiguous())
+        return ad["kv"]
+
+    def drop_adapter_kv(self) -> None:
+        for L in self.layers:
+            if L.adapter is not None:
+                L.adapter["kv"] = None
+        self.drop_graphs()
+
+    def adapter_kv_views(self):
+        """What the reference keeps in `GPT.adapter_kv_caches` (adapter.py:103-107): per layer (ak, av) as (1, G, aT, hs), or None."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        out = []
+        for L in self.layers:
+            if L.adapter is None:
+                out.append(None)
+            else:
+                ak, av = self._adapter_kv(L, stream)
+                out.append((ak.unsqueeze(0), av.unsqueeze(0)))
+        return out
+
+    def _adapter_attn(self, L, qkv: int, pos_ptr: int, att: int, B: int, T: int, scale: float, stream: int) -> None:
+        """att += gating * softmax(q . ak^T * scale) . av over the adaption prompt (adapter.py:251-254)."""
+        cfg = self.cfg
+        ak, av = self._adapter_kv(L, stream)
+        _lib.check(self.lib.lp_adapter_attn(qkv, _ptr(self.cos), _ptr(self.sin), pos_ptr, ak.data_ptr(), av.data_ptr(),
+                                            L.adapter["gate"].data_ptr(), att, B, T, cfg.n_head, cfg.n_query_groups, cfg.head_size,
+                                            cfg.rope_n_elem, ak.shape[1], scale, self.round, stream), "lp_adapter_attn")
 
     # ------------------------------------------------------------------ slab images of the fused pairs (load time)
     def _build_slabs(self):
@@ -474,6 +533,8 @@ class Engine:
                 chk(lib.lp_rope_kv_append(qkv, _ptr(self.cos), _ptr(self.sin), pos_ptr, q, kc, vc, kvd, B, T, H, G, hs,
                                           cfg.rope_n_elem, max_seq, r, stream), "lp_rope_kv_append")
                 self._attention_rows(q, kc, vc, kvd, pos_ptr, att, ws, ws_bytes, B, T, max_seq, scale, stream)
+            if L.adapter is not None:
+                self._adapter_attn(L, qkv, pos_ptr, att, B, T, scale, stream)
             if cfg.parallel_residual:
                 # x + attn(n1) + mlp(n2), n2 = n1 when the norm is shared (model.py:169-171); both GEMVs read the old x
                 n2w, n2b = (L.n1_w, L.n1_b) if cfg.shared_attention_norm else (L.n2_w, L.n2_b)
@@ -535,8 +596,8 @@ class Engine:
         chk(lib.lp_embed(idx_ptr, idx64, None, self.wte.data_ptr(), _KV_OF_DTYPE[self.wte.dtype], x, rows, E, r, stream), "lp_embed")
 
         def gemm(terms, W, epi, res, out_f32, out_bf=None):
-            chk(lib.lp_gemm_bf16_tc(terms, nt, rows, self._bf16_weight(W, stream), W.N, W.K, W.rec.bias, epi, res, out_f32, out_bf,
-                                    nt, r, stream), "lp_gemm_bf16_tc")
+            chk(lib.lp_gemm_bf16_tc_affine(terms, nt, rows, self._bf16_weight(W, stream), W.N, W.K, W.rec.bias, W.rec.out_bias,
+                                           W.rec.out_scale, epi, res, out_f32, out_bf, nt, r, stream), "lp_gemm_bf16_tc")
 
         def norm_split(src, nw, nb, dst):
             chk(lib.lp_split_bf16(src, dst, rows, E, nt, nk, _ptr(nw), _ptr(nb), cfg.norm_eps, r, stream), "lp_split_bf16")
@@ -555,6 +616,8 @@ class Engine:
                 chk(lib.lp_rope_kv_append(qkv, _ptr(self.cos), _ptr(self.sin), pos_ptr, q, kc, vc, kvd, B, T, H, G, hs, cfg.rope_n_elem,
                                           max_seq, r, stream), "lp_rope_kv_append")
                 self._attention_rows(q, kc, vc, kvd, pos_ptr, att, ws, ws_bytes, B, T, max_seq, scale, stream)
+            if L.adapter is not None:
+                self._adapter_attn(L, qkv, pos_ptr, att, B, T, scale, stream)
             chk(lib.lp_split_bf16(att, t_att, rows, E, nt, -1, None, None, 0.0, 0, stream), "lp_split_bf16")
             if cfg.parallel_residual:
                 if not cfg.shared_attention_norm:

@@ -116,7 +116,7 @@ class GPT(nn.Module):
         self.transformer = nn.ModuleDict(
             dict(
                 wte=nn.Embedding(config.padded_vocab_size, config.n_embd),
-                h=nn.ModuleList(Block(config) for _ in range(config.n_layer)),
+                h=nn.ModuleList(self._make_block(config, i) for i in range(config.n_layer)),
                 ln_f=config.norm_class(config.n_embd, eps=config.norm_eps),
             )
         )
@@ -129,6 +129,10 @@ class GPT(nn.Module):
         self.use_cuda_graph = True
         self.tp_context = None           # lit_parrot_b200.tp.TPContext when config.tp_size > 1
         self._engine = None
+
+    def _make_block(self, config: Config, block_idx: int) -> nn.Module:
+        """Hook of the adapter / LoRA variants (lit_gpt/adapter.py:43, lit_gpt/lora.py:500): they build their own Block."""
+        return Block(config)
 
     # ------------------------------------------------------------------ reference-compatible helpers
     def _init_weights(self, module: nn.Module) -> None:

@@ -66,7 +66,10 @@ def linear(x: Tensor, sd: Dict[str, Tensor], prefix: str) -> Tensor:
     if prefix + ".quant_weight" in sd:
         w = gptq_dequant(sd[prefix + ".quant_weight"], sd[prefix + ".scales"], sd[prefix + ".zeros"], dtype=x.dtype)
         return F.linear(x, w, sd.get(prefix + ".bias"))
-    return F.linear(x, sd[prefix + ".weight"], sd.get(prefix + ".bias"))
+    y = F.linear(x, sd[prefix + ".weight"], sd.get(prefix + ".bias"))
+    if prefix + ".adapter_scale" in sd:  # adapter v2 (lit_gpt/adapter_v2.py:34-35): adapter_scale * (linear(x) + adapter_bias)
+        y = sd[prefix + ".adapter_scale"] * (y + sd[prefix + ".adapter_bias"])
+    return y
 
 
 def mlp(cfg, x: Tensor, sd: Dict[str, Tensor], prefix: str) -> Tensor:
@@ -114,6 +117,21 @@ def attention(cfg, x: Tensor, sd: Dict[str, Tensor], prefix: str, cos: Tensor, s
         kv = (k, v)
     scale = 1.0 / math.sqrt(hs)  # model.py:259
     y = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=0.0, scale=scale, is_causal=mask is None)
+    if prefix + ".adapter_wte.weight" in sd:
+        # LLaMA-Adapter (lit_gpt/adapter.py:234-254): attention of the same (rotated) q over the aT adaption-prompt positions,
+        # whose k / v are the k / v parts of attn.attn(adapter_wte.weight) — NOT rotated, no mask — gated per head
+        prefix_emb = sd[prefix + ".adapter_wte.weight"]
+        aT = prefix_emb.size(0)
+        aqkv = linear(prefix_emb.reshape(1, aT, C), sd, prefix + ".attn")
+        aqkv = aqkv.view(1, aT, G, qpk + 2, hs).permute(0, 2, 3, 1, 4)
+        _, ak, av = aqkv.split((qpk, 1, 1), dim=2)
+        if G != 1:
+            ak = ak.repeat_interleave(qpk, dim=2)
+            av = av.repeat_interleave(qpk, dim=2)
+        ak, av = ak.reshape(1, -1, aT, hs), av.reshape(1, -1, aT, hs)
+        amask = torch.ones(T, aT, dtype=torch.bool)
+        ay = F.scaled_dot_product_attention(q, ak, av, attn_mask=amask, dropout_p=0.0, scale=scale)
+        y = y + sd[prefix + ".gating_factor"] * ay
     y = y.transpose(1, 2).contiguous().view(B, T, C)  # model.py:249
     return linear(y, sd, prefix + ".proj"), kv
 
@@ -425,3 +443,81 @@ def random_state_dict(cfg, seed: int = 1234, dtype=torch.float32, perturb_norm: 
             t = 0.02 * torch.randn(shp, generator=g) if perturb_norm else torch.zeros(shp)
         sd[k] = t.to(dtype)
     return sd
+
+
+# ----------------------------------------------------------------------------------------------
+# merged-LoRA weights (lit_gpt/lora.py)
+# ----------------------------------------------------------------------------------------------
+def lora_merge_state_dict(cfg, sd: Dict[str, Tensor], r: int, alpha: float, enable_qkv: Tuple[bool, bool, bool]) -> Dict[str, Tensor]:
+    """`merge_lora_weights` (lora.py:676-680) on a state dict: every `X.lora_A` / `X.lora_B` pair is folded into `X.weight` and
+    dropped.  Plain layers (lora.py:154-164): W += (B @ A) * alpha / r.  The fused QKV layer (lora.py:338-361):
+    delta = conv1d(A[None], B[..., None], groups = #enabled) * alpha / r — lora_B's rows cut into #enabled EQUAL blocks, block j
+    times rows [j r, (j + 1) r) of lora_A — scattered to the rows `lora_ind` = [q rows 0..E) + [k rows E..E+kv) + [v rows E+kv..)
+    of the enabled parts (lora.py:275-294), zero elsewhere (zero_pad, lora.py:296-336)."""
+    out = {k: v.clone() for k, v in sd.items() if ".lora_" not in k}
+    scaling = alpha / r
+    E = cfg.n_embd
+    kv = E // (cfg.n_head // cfg.n_query_groups)
+    for key in sd:
+        if not key.endswith(".lora_A"):
+            continue
+        base = key[: -len(".lora_A")]
+        A, Bm, W = sd[key], sd[base + ".lora_B"], out[base + ".weight"]
+        if base.endswith(".attn.attn"):
+            ng = sum(enable_qkv)
+            delta = F.conv1d(A.unsqueeze(0), Bm.unsqueeze(-1), groups=ng).squeeze(0) * scaling
+            spans = [(0, E)] * enable_qkv[0] + [(E, E + kv)] * enable_qkv[1] + [(E + kv, W.size(0))] * enable_qkv[2]
+            ind = torch.cat([torch.arange(a, b) for a, b in spans])
+            pad = torch.zeros_like(W)
+            pad.index_copy_(0, ind, delta.to(W.dtype))
+            out[base + ".weight"] = W + pad
+        else:
+            out[base + ".weight"] = W + (Bm @ A) * scaling
+    return out
+
+
+def adapter_extra_state(cfg, seed: int, start_layer: int, aT: int, v2: bool) -> Dict[str, Tensor]:
+    """Seeded adapter parameters for tests (the reference initialises the gate to zero and the v2 affine to identity, which would
+    test nothing): `adapter_wte.weight` N(0, 0.5), `gating_factor` N(0, 1) for layers >= start_layer (adapter.py:171-177); with
+    `v2` an `adapter_bias` N(0, 0.1) / `adapter_scale` 1 + N(0, 0.3) per linear layer incl. lm_head (adapter_v2.py:38-52)."""
+    g = torch.Generator().manual_seed(seed)
+    out: Dict[str, Tensor] = {}
+    for l in range(cfg.n_layer):
+        if l >= start_layer:
+            out[f"transformer.h.{l}.attn.adapter_wte.weight"] = torch.randn((aT, cfg.n_embd), generator=g) * 0.5
+            out[f"transformer.h.{l}.attn.gating_factor"] = torch.randn((1, cfg.n_head, 1, 1), generator=g)
+    if v2:
+        for k, shp in state_dict_shapes(cfg).items():
+            if len(shp) == 2 and k.endswith(".weight") and "wte" not in k:
+                base = k[: -len(".weight")]
+                out[base + ".adapter_bias"] = torch.randn(shp[0], generator=g) * 0.1
+                out[base + ".adapter_scale"] = 1.0 + torch.randn(shp[0], generator=g) * 0.3
+    return out
+
+
+def lora_extra_state(cfg, seed: int, r: int, enable_qkv: Tuple[bool, bool, bool], to_projection: bool, to_mlp: bool,
+                     to_head: bool) -> Dict[str, Tensor]:
+    """Seeded `lora_A` (r [* #enabled], in) / `lora_B` (rows, r) ~ N(0, 0.05) for the layers that carry LoRA (lora.py:479-673)."""
+    g = torch.Generator().manual_seed(seed)
+    out: Dict[str, Tensor] = {}
+    E = cfg.n_embd
+    kv = E // (cfg.n_head // cfg.n_query_groups)
+
+    def pair(base, rows, cols, ra):
+        out[base + ".lora_A"] = torch.randn((ra, cols), generator=g) * 0.05
+        out[base + ".lora_B"] = torch.randn((rows, r), generator=g) * 0.05
+
+    shapes = state_dict_shapes(cfg)
+    for l in range(cfg.n_layer):
+        p = f"transformer.h.{l}"
+        if any(enable_qkv):
+            pair(p + ".attn.attn", E * enable_qkv[0] + kv * enable_qkv[1] + kv * enable_qkv[2], E, r * sum(enable_qkv))
+        if to_projection:
+            pair(p + ".attn.proj", E, E, r)
+        if to_mlp:
+            for name in (("fc_1", "fc_2", "proj") if cfg._mlp_class == "LLaMAMLP" else ("fc", "proj")):
+                o, i = shapes[f"{p}.mlp.{name}.weight"]
+                pair(f"{p}.mlp.{name}", o, i, r)
+    if to_head:
+        pair("lm_head", cfg.padded_vocab_size, E, r)
+    return out

@@ -403,6 +403,98 @@ def cli_cases():
     print(f"[golden] cli: tokenizer files in {d.name}, {len(gold['chat'])} chat streams, {len(gold['prompt_config'])} prompt configs")
 
 
+FINETUNED = {
+    # name: (kind, TINY base config, extra Config kwargs)
+    "adapter_neox": ("adapter", "neox", dict(adapter_prompt_length=10, adapter_start_layer=1)),
+    "adapter_llama_gqa": ("adapter", "llama_gqa", dict(adapter_prompt_length=10, adapter_start_layer=1)),
+    "adapter_v2_llama_mha": ("adapter_v2", "llama_mha", dict(adapter_prompt_length=10, adapter_start_layer=1)),
+    "adapter_v2_falcon_mqa": ("adapter_v2", "falcon_mqa", dict(adapter_prompt_length=6, adapter_start_layer=0)),
+    "lora_llama_gqa": ("lora", "llama_gqa", dict(r=4, alpha=8, to_query=True, to_key=False, to_value=True, to_projection=True,
+                                                 to_mlp=True, to_head=True)),
+    "lora_neox": ("lora", "neox", dict(r=2, alpha=4, to_query=True, to_key=True, to_value=True, to_projection=False, to_mlp=False,
+                                       to_head=False)),
+}
+
+
+@torch.no_grad()
+def finetuned_cases():
+    """LLaMA-Adapter, Adapter v2 and merged-LoRA inference of the UNMODIFIED reference (lit_gpt/adapter.py,
+    adapter_v2.py, lora.py) on tiny seeded models -> tests/golden/ft_*.npz; the oracle must reproduce them."""
+    import lit_gpt.adapter as ref_adapter
+    import lit_gpt.adapter_v2 as ref_adapter_v2
+    import lit_gpt.lora as ref_lora
+
+    for name, (kind, base, extra) in FINETUNED.items():
+        kw = dict(TINY[base])
+        seed = 1234
+        ocfg = oracle_cfg(kw)
+        sd = oracle.random_state_dict(ocfg, seed=seed, perturb_norm=True)
+        if kind == "lora":
+            cfg = ref_lora.Config(**kw, **extra)
+            model = ref_lora.GPT(cfg)
+            qkv_en = (extra["to_query"], extra["to_key"], extra["to_value"])
+            sd.update(oracle.lora_extra_state(ocfg, seed + 1, extra["r"], qkv_en, extra["to_projection"], extra["to_mlp"], extra["to_head"]))
+        else:
+            cfg = ref_adapter.Config(**kw, **extra)
+            model = ref_adapter.GPT(cfg)
+            if kind == "adapter_v2":
+                ref_adapter_v2.add_adapter_v2_parameters_to_linear_layers(model)
+            sd.update(oracle.adapter_extra_state(ocfg, seed + 1, extra["adapter_start_layer"], extra["adapter_prompt_length"],
+                                                 kind == "adapter_v2"))
+        res = model.load_state_dict(sd, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys, res
+        model.eval()
+        osd = sd
+        if kind == "lora":
+            ref_lora.merge_lora_weights(model)
+            osd = oracle.lora_merge_state_dict(ocfg, sd, extra["r"], extra["alpha"], qkv_en)
+            merged = {k: v for k, v in model.state_dict().items() if ".lora_" not in k}
+            assert set(merged) == set(osd)
+            for k in merged:
+                check(f"{name}/merged/{k}", osd[k], merged[k], 0.0)
+        g = torch.Generator().manual_seed(1)
+        B, T, steps, max_seq = 2, 7, 8, 32
+        idx = torch.randint(0, cfg.padded_vocab_size, (B, T), generator=g)
+        ref_full = model(idx)
+        model.reset_cache()
+        pos = torch.arange(T)
+        ref_prefill = model(idx, max_seq, pos)
+        forced = torch.randint(0, cfg.padded_vocab_size, (steps, B, 1), generator=g)
+        ref_steps = []
+        for s_ in range(steps):
+            pos = pos[-1:] + 1
+            ref_steps.append(model(forced[s_], max_seq, pos))
+        ref_steps = torch.stack(ref_steps)
+        model.reset_cache()
+        prompt = torch.randint(0, cfg.padded_vocab_size, (5,), generator=g, dtype=torch.int64).to(torch.int32)
+        ref_gen = ref_generate.generate(model, prompt, 30, 30, temperature=1.0, top_k=1)
+        model.reset_cache()
+
+        om = oracle.OracleGPT(ocfg, osd)
+        d1 = check(name + "/full", om(idx), ref_full, 2e-6)
+        om.reset_cache()
+        pos = torch.arange(T)
+        d2 = check(name + "/prefill", om(idx, max_seq, pos), ref_prefill, 2e-6)
+        for s_ in range(steps):
+            pos = pos[-1:] + 1
+            check(name + f"/step{s_}", om(forced[s_], max_seq, pos), ref_steps[s_], 2e-6)
+        om.reset_cache()
+        og = oracle.generate(om, prompt, 30, 30, temperature=1.0, top_k=1, argmax_ties=True)
+        assert torch.equal(og, ref_gen), (name, og, ref_gen)
+        # the adapter must matter: the same model without it decodes something else
+        if kind != "lora":
+            plain = oracle.OracleGPT(ocfg, {k: v for k, v in sd.items() if "adapter" not in k and "gating" not in k})
+            assert (plain(idx) - ref_full).abs().max() > 1e-3
+        print(f"[golden] {name}: oracle == reference (max diff {max(d1, d2):.1e}); tokens equal")
+        np.savez_compressed(
+            os.path.join(OUT, f"ft_{name}.npz"), kind=kind, base=base,
+            cfg_keys=np.array(list(kw.keys())), cfg_vals=np.array([repr(v) for v in kw.values()]),
+            extra_keys=np.array(list(extra.keys())), extra_vals=np.array([repr(v) for v in extra.values()]),
+            seed=seed, sd_sha256=sd_digest(sd), idx=idx.numpy(), max_seq=max_seq, forced=forced.numpy(), ref_full=ref_full.numpy(),
+            ref_prefill=ref_prefill.numpy(), ref_steps=ref_steps.numpy(), prompt=prompt.numpy(), ref_gen=ref_gen.numpy(),
+        )
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -412,10 +504,14 @@ if __name__ == "__main__":
     if "--only-cli" in sys.argv:
         cli_cases()
         sys.exit(0)
+    if "--only-finetuned" in sys.argv:
+        finetuned_cases()
+        sys.exit(0)
     preset_table()
     tiny_cases()
     gptq_cases()
     pythia70m()
     checkpoint_cases()
     cli_cases()
+    finetuned_cases()
     print("[golden] all fixtures written to", OUT)
