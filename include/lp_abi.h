@@ -221,6 +221,31 @@ int lp_adapter_attn(const float* qkv, const float* cos, const float* sin, const 
 int lp_lora_merge(void* W, int w_dtype, int N, int K, const float* B_rows, const float* A, int r, const int32_t* rows, int n_rows,
                   float scaling, void* stream);
 
+/* ---- GPTQ quantiser on the device (quantize/gptq.py:267-431, GPTQQuantizer) -------------------------------------------------------
+ * lp_gptq_hessian_update — collect_input_stats (gptq.py:349-363): H[K, K] = keep * H + (x_scale * X)^T (x_scale * X), X fp32
+ *   [rows, K] the layer's inputs of one calibration batch; callers pass keep = n / (n + b), x_scale = sqrt(2 / (n + b)).  The update
+ *   is ONE tcgen05 GEMM with the tokens as the reduction dimension: the scaled X is transposed and split into `terms` (2 or 3)
+ *   bf16 terms whose pairwise products (3 or 6, the rest is below 2^-17 / 2^-25 relative) are laid side by side along the
+ *   reduction.  K % 8 == 0.  workspace: lp_gptq_hessian_workspace_bytes(rows, K, terms).
+ * lp_gptq_find_params — find_params_weight (gptq.py:318-347), per-channel: for every row and every group gi in [group_first,
+ *   group_first + n_groups) the min / max of W[row, gi * group : (gi + 1) * group] -> scales / zeros [N, ld] at column gi.
+ * lp_gptq_block_sweep — the inner loop of quantize() (gptq.py:400-419) for the block of `count` <= 128 columns starting at i1:
+ *   reads W[:, i1 : i1 + count] (not modified) and the upper Cholesky factor Hinv [K, K] of the inverse Hessian, writes the
+ *   de-quantised values Q[:, i1 : i1 + count], the scaled errors Err [N, 128] and adds the block's loss per row to loss_rows [N].
+ *   fp32 with the reference's operation order: same inputs -> bit-identical codes.
+ * lp_gptq_trailing_update — W[:, i1 + count :] -= Err[:, :count] . Hinv[i1 : i1 + count, i1 + count :] (gptq.py:424).
+ * The Cholesky factorisations in between (gptq.py:387-391) are cuSOLVER calls issued by the host side. */
+size_t lp_gptq_hessian_workspace_bytes(int rows, int K, int terms);
+int lp_gptq_hessian_update(float* H, int K, const float* x, int rows, float keep, float x_scale, int terms, void* workspace,
+                           size_t workspace_bytes, void* stream);
+int lp_gptq_find_params(const float* W, int N, int K, int group_first, int n_groups, int group, int maxq, int sym, float* scales,
+                        float* zeros, int ld, void* stream);
+int lp_gptq_block_sweep(const float* W, int N, int K, int i1, int count, const float* Hinv, const float* scales, const float* zeros,
+                        int ld, int group, int maxq, float* Q, float* Err, float* loss_rows, void* stream);
+int lp_gptq_trailing_update(float* W, int N, int K, int i1, int count, const float* Hinv, const float* Err, void* stream);
+/* out[i] = silu(a[i]) * b[i] (LLaMAMLP, model.py:298-300) where fc_1 / fc_2 are separate layers (calibration forward of the quantiser). */
+int lp_swiglu(const float* a, const float* b, float* out, size_t n, int round_bf16, void* stream);
+
 /* ---- the whole single-token decode step (batch 1) as ONE persistent kernel ------------------------------------------
  * replaces GPT.forward for T == 1 (model.py:63-111 -> Block.forward 158-180 -> CausalSelfAttention.forward 194-254 -> MLP
  * 284-301): the caller describes the step once as an ordered table of ops — LINEAR (lp_norm_linear semantics, M = 1),

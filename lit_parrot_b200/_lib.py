@@ -93,6 +93,13 @@ PROTOTYPES = {
     "lp_adapter_attn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "lp_lora_merge": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_float, c_void_p]),
+    "lp_gptq_hessian_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "lp_gptq_hessian_update": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_float, c_int, c_void_p, c_size_t, c_void_p]),
+    "lp_gptq_find_params": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "lp_gptq_block_sweep": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                    c_void_p, c_void_p, c_void_p]),
+    "lp_gptq_trailing_update": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "lp_swiglu": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "lp_dequant_bf16": (c_int, [ctypes.POINTER(LpWeight), c_void_p, c_void_p]),
     "lp_rope_kv_append": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "liblitparrot_b200.so")
-SOURCES = ["runtime.cu", "elementwise.cu", "linear.cu", "linear_fma.cu", "linear_stream.cu", "decode_step.cu", "gemm_tc.cu", "tp_allreduce.cu", "attention.cu", "attention_decode.cu", "attention_tc.cu", "sample.cu", "adapter.cu"]
+SOURCES = ["runtime.cu", "elementwise.cu", "linear.cu", "linear_fma.cu", "linear_stream.cu", "decode_step.cu", "gemm_tc.cu", "tp_allreduce.cu", "attention.cu", "attention_decode.cu", "attention_tc.cu", "sample.cu", "adapter.cu", "gptq.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-I", INCLUDE, "-I", CSRC] + (
     [f"-DGS_CWARPS_DEF={os.environ['LP_GS_CWARPS']}"] if os.environ.get("LP_GS_CWARPS") else [])

@@ -521,3 +521,116 @@ def lora_extra_state(cfg, seed: int, r: int, enable_qkv: Tuple[bool, bool, bool]
     if to_head:
         pair("lm_head", cfg.padded_vocab_size, E, r)
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# GPTQ quantiser (quantize/gptq.py:267-431), CPU restatement
+# ----------------------------------------------------------------------------------------------
+def gptq_hessian(batches: List[Tensor]) -> Tuple[Tensor, int]:
+    """collect_input_stats (gptq.py:349-363) over a list of input batches [b, T, K] (or [T, K]): running
+    H = H * n / (n + b) + (sqrt(2 / (n + b)) X)^T (sqrt(2 / (n + b)) X) with n counted in sequences."""
+    H, n = None, 0
+    for inp in batches:
+        if inp.dim() == 2:
+            inp = inp.unsqueeze(0)
+        b = inp.shape[0]
+        x = inp.reshape(-1, inp.shape[-1]).t()
+        if H is None:
+            H = torch.zeros((x.shape[0], x.shape[0]))
+        H *= n / (n + b)
+        n += b
+        x = math.sqrt(2 / n) * x.float()
+        H += x.matmul(x.t())
+    return H, n
+
+
+def gptq_find_params(x: Tensor, maxq: int, sym: bool = False) -> Tuple[Tensor, Tensor]:
+    """find_params_weight (gptq.py:318-347), perchannel=True: per-row grid of x [N, cols] -> (scale, zero) [N, 1]."""
+    tmp = torch.zeros(x.shape[0])
+    xmin = torch.minimum(x.min(1)[0], tmp)
+    xmax = torch.maximum(x.max(1)[0], tmp)
+    if sym:
+        xmax = torch.maximum(torch.abs(xmin), xmax)
+        neg = xmin < 0
+        xmin[neg] = -xmax[neg]
+    both = (xmin == 0) & (xmax == 0)
+    xmin[both] = -1
+    xmax[both] = +1
+    scale = (xmax - xmin) / maxq
+    zero = torch.full_like(scale, (maxq + 1) / 2) if sym else torch.round(-xmin / scale)
+    return scale.reshape(-1, 1), zero.reshape(-1, 1)
+
+
+def gptq_quantize_layer(weight: Tensor, H: Tensor, bits: int = 4, blocksize: int = 128, percdamp: float = 0.01, groupsize: int = -1,
+                        actorder: bool = False, sym: bool = False):
+    """GPTQQuantizer.quantize (gptq.py:365-431) on a weight [N, K] and its Hessian [K, K].  Returns the de-quantised weights Q,
+    the per-group (scales, zeros) [N, n_groups], the summed loss and the upper Cholesky factor of the inverse Hessian (in the
+    permuted column order when actorder)."""
+    maxq = 2 ** bits - 1
+    W = weight.detach().to(dtype=torch.float, copy=True)
+    N, K = W.shape
+    tile = K if groupsize == -1 else groupsize
+    scales = torch.zeros((N, (K + tile - 1) // tile))
+    zeros = torch.zeros_like(scales)
+    scale, zero = gptq_find_params(W, maxq, sym)  # gptq.py:368-370
+    scales[:] = scale
+    zeros[:] = zero
+    H = H.clone()
+    dead = torch.diag(H) == 0
+    H[dead, dead] = 1
+    W[:, dead] = 0
+    if actorder:  # gptq.py:378-381
+        perm = torch.argsort(torch.diag(H), descending=True)
+        W = W[:, perm]
+        H = H[perm][:, perm]
+    Losses = torch.zeros_like(W)
+    Q = torch.zeros_like(W)
+    damp = percdamp * torch.mean(torch.diag(H))
+    diag = torch.arange(K)
+    H[diag, diag] += damp
+    H = torch.linalg.cholesky(H)
+    H = torch.cholesky_inverse(H)
+    Hinv = torch.linalg.cholesky(H, upper=True)
+    for i1 in range(0, K, blocksize):  # gptq.py:393-424
+        i2 = min(i1 + blocksize, K)
+        W1 = W[:, i1:i2].clone()
+        Q1 = torch.zeros_like(W1)
+        Err1 = torch.zeros_like(W1)
+        Losses1 = torch.zeros_like(W1)
+        Hinv1 = Hinv[i1:i2, i1:i2]
+        for i in range(i2 - i1):
+            w = W1[:, i]
+            d = Hinv1[i, i]
+            if groupsize != -1 and (i1 + i) % groupsize == 0:  # the group's grid from the CURRENT global W (not W1)
+                scale, zero = gptq_find_params(W[:, (i1 + i):(i1 + i + groupsize)], maxq, sym)
+                scales[:, (i1 + i) // groupsize] = scale.squeeze(1)
+                zeros[:, (i1 + i) // groupsize] = zero.squeeze(1)
+            q = torch.clamp(torch.round(w.unsqueeze(1) / scale) + zero, 0, maxq)  # quantize_weight, gptq.py:313-316
+            q = (scale * (q - zero)).squeeze(1)
+            Q1[:, i] = q
+            Losses1[:, i] = (w - q) ** 2 / d ** 2
+            err1 = (w - q) / d
+            W1[:, i:] -= err1.unsqueeze(1).matmul(Hinv1[i, i:].unsqueeze(0))
+            Err1[:, i] = err1
+        Q[:, i1:i2] = Q1
+        Losses[:, i1:i2] = Losses1 / 2
+        W[:, i2:] -= Err1.matmul(Hinv[i1:i2, i2:])
+    if actorder:
+        Q = Q[:, torch.argsort(perm)]
+    return Q, scales, zeros, torch.sum(Losses).item(), Hinv
+
+
+def gptq_codes(Q: Tensor, scales: Tensor, zeros: Tensor, tile_cols: int, bits: int = 4) -> Tensor:
+    """The integer codes pack_weight stores (gptq.py:233-241): trunc(clamp(Q / scale + zero)), per column group."""
+    K = Q.shape[1]
+    cols = torch.arange(K) // (K if tile_cols == -1 else tile_cols)
+    return (Q / scales[:, cols] + zeros[:, cols]).clamp_(0, 2 ** bits - 1).to(torch.uint8)
+
+
+def gptq_case_inputs(N: int, K: int, shapes, seed: int = 77) -> Tuple[Tensor, List[Tensor]]:
+    """Seeded layer weight [N, K] ~ N(0, 0.05) and correlated calibration batches [(b, T, K)] (a random mixing matrix, so the
+    Hessian is far from diagonal) shared by oracle/make_golden.py::quantizer_cases and the tests."""
+    g = torch.Generator().manual_seed(seed)
+    W = torch.randn((N, K), generator=g) * 0.05
+    mix = torch.randn((K, K), generator=g) / math.sqrt(K) + torch.eye(K)
+    return W, [torch.randn((int(b), int(T), K), generator=g) @ mix for b, T in shapes]

@@ -11,6 +11,7 @@ oracle/lit_oracle.py reproduces every stored output (bit-for-bit where the op or
 The GPU box has no /root/reference: tests there only read the committed fixtures.
 """
 import hashlib
+import math
 import os
 import sys
 
@@ -495,6 +496,73 @@ def finetuned_cases():
         )
 
 
+QUANTIZER_CASES = {
+    # name: (N, K, groupsize, actorder, batches of (b, T))
+    # groupsize != -1 cannot be run: the reference raises at gptq.py:409-411 (`self.scales[:, j] = scale` with scale (N, 1)); its
+    # own callers only use groupsize = -1 with actorder (gptq.py:499, 536, 596).  The grouped path is covered by the oracle alone.
+    "perrow": (48, 256, -1, False, [(2, 16), (1, 16), (3, 16)]),
+    "perrow_actorder": (40, 192, -1, True, [(2, 24), (2, 24)]),
+    "oneblock": (64, 128, -1, False, [(2, 40)]),
+}
+
+
+@torch.no_grad()
+def quantizer_cases():
+    """the UNMODIFIED reference's GPTQQuantizer (quantize/gptq.py:267-431) on seeded layers and inputs ->
+    tests/golden/gptq_quantizer_*.npz, and its blockwise_quantization (442-548) on a tiny model -> gptq_blockwise_*.npz; the oracle
+    restatement must reproduce both."""
+    import contextlib
+    import io
+
+    for name, (N, K, gs, act, shapes) in QUANTIZER_CASES.items():
+        lin = torch.nn.Linear(K, N, bias=False)
+        W, batches = oracle.gptq_case_inputs(N, K, shapes, seed=77)
+        lin.weight.data.copy_(W)
+        gq = ref_gptq.GPTQQuantizer(lin, bits=4, groupsize=gs, actorder=act)
+        for x in batches:
+            gq.collect_input_stats(None, (x,), None)
+        H_ref = gq.H.clone()
+        qmod, err = gq.quantize()
+        codes = torch.empty((N, K), dtype=torch.uint8)
+        codes[:, 0::2] = qmod.quant_weight & 0xF
+        codes[:, 1::2] = qmod.quant_weight >> 4
+        H_o, n_o = oracle.gptq_hessian(batches)
+        check(name + "/H", H_o, H_ref, 0.0)
+        Q_o, sc_o, ze_o, err_o, Hinv_o = oracle.gptq_quantize_layer(W, H_o, groupsize=gs, actorder=act)
+        check(name + "/scales", sc_o, qmod.scales, 0.0)
+        check(name + "/zeros", ze_o, qmod.zeros, 0.0)
+        assert torch.equal(oracle.gptq_codes(Q_o, sc_o, ze_o, gs), codes), name
+        assert abs(err_o - err) <= 1e-6 * abs(err), (err_o, err)
+        print(f"[golden] gptq quantizer {name}: oracle == reference (codes, grids, Hessian); error {err:.4f}")
+        np.savez_compressed(os.path.join(OUT, f"gptq_quantizer_{name}.npz"), N=N, K=K, groupsize=gs, actorder=act,
+                            shapes=np.array(shapes), seed=77, W=W.numpy(), H=H_ref.numpy(), Hinv=Hinv_o.numpy(), codes=codes.numpy(),
+                            scales=qmod.scales.numpy(), zeros=qmod.zeros.numpy(), error=err, nsamples=n_o)
+
+    for base, gs in (("llama_mha", -1), ("neox", -1)):
+        kw = dict(TINY[base])
+        if "intermediate_size" in kw:
+            kw["intermediate_size"] = 192  # in_features of every int4 layer a multiple of 32 (the kernels' K granularity)
+        cfg, model, sd = build_reference(kw, 1234)
+        gg = torch.Generator().manual_seed(5)
+        n_samples = 24  # 1152 calibration tokens: every Hessian (K <= 256) is well conditioned
+        samples = torch.randint(0, cfg.padded_vocab_size, (n_samples, cfg.block_size), generator=gg)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref_gptq.blockwise_quantization(model, samples, "cpu", bits=4, groupsize=gs)
+        qsd = {k: v.clone() for k, v in model.state_dict().items()}
+        idx = torch.randint(0, cfg.padded_vocab_size, (2, 9), generator=gg)
+        model.reset_cache()
+        ref_logits = model(idx)
+        om = oracle.OracleGPT(oracle_cfg(kw), qsd)
+        check(f"blockwise_{base}/logits", om(idx), ref_logits, 1e-5)
+        plain = oracle.OracleGPT(oracle_cfg(kw), sd)(idx)
+        out = {k.replace(".", "__"): v.numpy() for k, v in qsd.items() if v is not None}
+        print(f"[golden] gptq blockwise {base} (groupsize {gs}): {len(qsd)} tensors; quantised vs fp32 logits max diff "
+              f"{(plain - ref_logits).abs().max():.3f}")
+        np.savez_compressed(os.path.join(OUT, f"gptq_blockwise_{base}.npz"), groupsize=gs, seed=1234, samples=samples.numpy(),
+                            idx=idx.numpy(), ref_logits=ref_logits.numpy(), plain_logits=plain.numpy(),
+                            cfg_keys=np.array(list(kw.keys())), cfg_vals=np.array([repr(v) for v in kw.values()]), **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -503,6 +571,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--only-cli" in sys.argv:
         cli_cases()
+        sys.exit(0)
+    if "--only-quantizer" in sys.argv:
+        quantizer_cases()
         sys.exit(0)
     if "--only-finetuned" in sys.argv:
         finetuned_cases()
@@ -514,4 +585,5 @@ if __name__ == "__main__":
     checkpoint_cases()
     cli_cases()
     finetuned_cases()
+    quantizer_cases()
     print("[golden] all fixtures written to", OUT)
