@@ -544,7 +544,7 @@ def gptq_hessian(batches: List[Tensor]) -> Tuple[Tensor, int]:
     return H, n
 
 
-def gptq_find_params(x: Tensor, maxq: int, sym: bool = False) -> Tuple[Tensor, Tensor]:
+def gptq_row_grid(x: Tensor, maxq: int, sym: bool = False) -> Tuple[Tensor, Tensor]:
     """find_params_weight (gptq.py:318-347), perchannel=True: per-row grid of x [N, cols] -> (scale, zero) [N, 1]."""
     tmp = torch.zeros(x.shape[0])
     xmin = torch.minimum(x.min(1)[0], tmp)
@@ -572,7 +572,7 @@ def gptq_quantize_layer(weight: Tensor, H: Tensor, bits: int = 4, blocksize: int
     tile = K if groupsize == -1 else groupsize
     scales = torch.zeros((N, (K + tile - 1) // tile))
     zeros = torch.zeros_like(scales)
-    scale, zero = gptq_find_params(W, maxq, sym)  # gptq.py:368-370
+    scale, zero = gptq_row_grid(W, maxq, sym)  # gptq.py:368-370
     scales[:] = scale
     zeros[:] = zero
     H = H.clone()
@@ -602,7 +602,7 @@ def gptq_quantize_layer(weight: Tensor, H: Tensor, bits: int = 4, blocksize: int
             w = W1[:, i]
             d = Hinv1[i, i]
             if groupsize != -1 and (i1 + i) % groupsize == 0:  # the group's grid from the CURRENT global W (not W1)
-                scale, zero = gptq_find_params(W[:, (i1 + i):(i1 + i + groupsize)], maxq, sym)
+                scale, zero = gptq_row_grid(W[:, (i1 + i):(i1 + i + groupsize)], maxq, sym)
                 scales[:, (i1 + i) // groupsize] = scale.squeeze(1)
                 zeros[:, (i1 + i) // groupsize] = zero.squeeze(1)
             q = torch.clamp(torch.round(w.unsqueeze(1) / scale) + zero, 0, maxq)  # quantize_weight, gptq.py:313-316
