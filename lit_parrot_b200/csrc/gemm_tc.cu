@@ -156,7 +156,7 @@ struct TcParams {
 };
 
 // Epilogue of one 128 x BN accumulator tile held in TMEM at `tacc`: warp quarter q owns lanes [32 q, +32) = rows m0 + 32 q + lane.
-template <int BN>
+template <int BN, bool AFF>
 __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tacc, int m0, int n0, int q, int lane, bool swiglu, int nout) {
   const int row = m0 + q * 32 + lane;
 #pragma unroll 1
@@ -171,7 +171,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tac
         float t = __uint_as_float(v[j]);
         if (p.bias && n < p.N) t += p.bias[n];
         y[j] = maybe_round(t, p.round_bf16);
-        if ((p.out_bias || p.out_scale) && n < p.N) y[j] = out_affine(y[j], p.out_bias, p.out_scale, n, p.round_bf16);
+        if (AFF && n < p.N) y[j] = out_affine(y[j], p.out_bias, p.out_scale, n, p.round_bf16);
       }
       int ncols = 32, ocol = n0 + c0;
       if (swiglu) {  // W rows interleaved: column 2i = fc_1 row i, 2i+1 = fc_2 row i (model.py:298-300)
@@ -233,7 +233,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tac
 // CL = 2: the CTAs of a 2-CTA cluster work on neighbouring M tiles of the SAME N tile (tiles_m even) in lock step and share the W
 // tile: each loads one half of its rows and multicasts it to both, which cuts the L2 -> SM traffic the kernel is bound by from
 // (nterms * 16 + BN / 8) KB to (nterms * 16 + BN / 16) KB per k-block.  A ring slot is free once BOTH CTAs' MMAs have read it.
-template <int BN, int CL>
+template <int BN, int CL, bool AFF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p, int nstages) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -383,7 +383,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     if (p.debug & 4) tc_mbar_wait(acc_full(a), (it >> 1) & 1);
     else tc_mbar_wait_sleep(acc_full(a), (it >> 1) & 1, 256);
     tc_fence_after();
-    if (!(p.debug & 1)) tc_epilogue_tile<BN>(p, tmem + a * BN, m0, n0, q, lane, swiglu, nout);
+    if (!(p.debug & 1)) tc_epilogue_tile<BN, AFF>(p, tmem + a * BN, m0, n0, q, lane, swiglu, nout);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(acc_empty(a)) : "memory");  // TMEM buffer may be reused
@@ -440,6 +440,7 @@ __device__ __forceinline__ void tc_commit2(uint32_t bar) {  // arrives on the ba
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
+template <bool AFF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p, int nstages) {
   constexpr int BN = 256;                        // N of the pair's tile; each CTA stages BN / 2 rows of W
@@ -558,7 +559,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       const int m0 = (tile % tiles_m) * 2 * TC_BM + (int)rank * TC_BM, n0 = (tile / tiles_m) * BN;
       tc_mbar_wait(acc_full(a), (it >> 1) & 1);
       tc_fence_after();
-      tc_epilogue_tile<BN>(p, tmem + a * BN, m0, n0, q, lane, swiglu, nout);
+      tc_epilogue_tile<BN, AFF>(p, tmem + a * BN, m0, n0, q, lane, swiglu, nout);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {  // the accumulator may be reused: tell the leader
@@ -595,9 +596,49 @@ struct TcSwapParams {
   __nv_bfloat16* out_bf;
   int M, N, K, epi, round_bf16, nterms, out_terms, NB, ksplit, KB;
   int fuse;  // M % 16 == 0: the terms are one stacked B operand (N_mma = nterms * NB), their columns are added in the epilogue
+  int streamk;  // accumulate-in-place ops: the (tile, K-stage) sequence is cut into gridDim.x EQUAL ranges, one per CTA (a range may
+                // end in the middle of a tile and continue in the next one); partial tiles are added atomically
+};
+
+// The work of one CTA of gemm_tc_swap_kernel as a list of segments (tile, K-stage range).  Unit mode: units u = tile * ksplit + ks,
+// u = blockIdx.x, + gridDim.x, ...  Stream mode (p.streamk): the CTA's contiguous range of the tile-major stage sequence.
+template <bool SK>
+struct SwapWork {
+  int nk, ksplit, nunits, u;
+  long long cur, end;
+  __device__ __forceinline__ void init(const TcSwapParams& p, int nk_, int tiles_n) {
+    nk = nk_;
+    ksplit = p.ksplit;
+    nunits = tiles_n * p.ksplit;
+    u = blockIdx.x;
+    if (SK) {
+      const long long S = (long long)tiles_n * nk_;
+      cur = S * blockIdx.x / gridDim.x;
+      end = S * (blockIdx.x + 1) / gridDim.x;
+    }
+  }
+  __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1) {
+    if (SK) {
+      if (cur >= end) return false;
+      tile = (int)(cur / nk);
+      kb0 = (int)(cur - (long long)tile * nk);
+      const long long e = min(end, (long long)(tile + 1) * nk);
+      kb1 = kb0 + (int)(e - cur);
+      cur = e;
+      return true;
+    }
+    if (u >= nunits) return false;
+    tile = u / ksplit;
+    const int ks = u % ksplit;
+    kb0 = (int)((long long)nk * ks / ksplit);
+    kb1 = (int)((long long)nk * (ks + 1) / ksplit);
+    u += gridDim.x;
+    return true;
+  }
 };
 constexpr int TC_SWAP_ACC = 256;  // TMEM columns per accumulator (nterms * NB <= 192), two accumulators
 
+template <bool AFF, bool SK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcSwapParams p, int nstages) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -611,7 +652,6 @@ gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = (p.K / TC_BK + KB - 1) / KB;  // stages along K (K % 64 == 0; slabs past the end are zero-filled by TMA)
   const int tiles_n = (p.N + TC_BM - 1) / TC_BM;
-  const int nunits = tiles_n * p.ksplit;
   const uint32_t bar0 = tc_smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8 * s; };
   auto empty_bar = [&](int s) { return bar0 + 8 * (12 + s); };
@@ -644,9 +684,11 @@ gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     if (lane == 0) {
       int s = 0, ph = 0;
       bool waited = false;
-      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
-        const int n0 = (u / p.ksplit) * TC_BM, ks = u % p.ksplit;
-        const int kb0 = (int)((long long)nk * ks / p.ksplit), kb1 = (int)((long long)nk * (ks + 1) / p.ksplit);
+      SwapWork<SK> wk;
+      wk.init(p, nk, tiles_n);
+      int tile, kb0, kb1;
+      while (wk.next(tile, kb0, kb1)) {
+        const int n0 = tile * TC_BM;
         // every CTA needs the same activation slabs: start the K loop at a CTA-dependent offset (and wrap) so that the CTAs read
         // different slabs at any one time instead of the same few L2 lines
         const int nkb = kb1 - kb0, rot = (int)((blockIdx.x * 5u) % (unsigned)nkb);
@@ -679,9 +721,10 @@ gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       const uint32_t bslab = (uint32_t)(p.fuse ? p.nterms * XB : XB) >> 4;  // distance of consecutive K slabs of one B operand
       const uint32_t bterm = (uint32_t)(KB * XB) >> 4;                  // distance of the terms (unfused layout)
       int s = 0, ph = 0, it = 0;
-      for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++it) {
-        const int ks = u % p.ksplit;
-        const int kb0 = (int)((long long)nk * ks / p.ksplit), kb1 = (int)((long long)nk * (ks + 1) / p.ksplit);
+      SwapWork<SK> wk;
+      wk.init(p, nk, tiles_n);
+      int tile, kb0, kb1;
+      for (; wk.next(tile, kb0, kb1); ++it) {
         const int a = it & 1;
         tc_mbar_wait(acc_empty(a), ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -732,18 +775,21 @@ gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const int q = warp & 3;
     const bool swiglu = p.epi == LP_EPI_SWIGLU;
     const int nout = swiglu ? p.N / 2 : p.N;
-    const bool atomic = p.ksplit > 1;
+    const bool atomic = p.ksplit > 1 || SK;
     int it = 0;
-    for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++it) {
+    SwapWork<SK> wk;
+    wk.init(p, nk, tiles_n);
+    int tile, kb0, kb1;
+    for (; wk.next(tile, kb0, kb1); ++it) {
       const int a = it & 1;
-      const int n = (u / p.ksplit) * TC_BM + q * 32 + lane;  // weight row = output column
-      const bool first = (u % p.ksplit) == 0;
+      const int n = tile * TC_BM + q * 32 + lane;  // weight row = output column
+      const bool first = kb0 == 0;  // this CTA's part of the tile starts at K = 0: it adds the biases
       tc_mbar_wait(acc_full(a), (it >> 1) & 1);
       tc_fence_after();
       const float bias = (p.bias && n < p.N && first) ? p.bias[n] : 0.f;
-      const bool affine = p.out_bias || p.out_scale;  // adapter-v2: scale * ((acc + bias) + out_bias); K-split partials: biases once
-      const float obv = (p.out_bias && n < p.N && first) ? p.out_bias[n] : 0.f;
-      const float osv = (p.out_scale && n < p.N) ? p.out_scale[n] : 1.f;
+      // adapter-v2 (compile-time variant): scale * ((acc + bias) + out_bias); K-split partials: the biases once
+      const float obv = (AFF && p.out_bias && n < p.N && first) ? p.out_bias[n] : 0.f;
+      const float osv = (AFF && p.out_scale && n < p.N) ? p.out_scale[n] : 1.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < p.NB; c0 += 32) {
         // the accumulator holds one column block per activation term (term t of batch row m: column t*NB + m): add them
@@ -762,7 +808,7 @@ gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           const int m = c0 + j;  // batch row (warp-uniform)
           if (m < p.M) {
             float y = maybe_round(acc[j] + bias, p.round_bf16);
-            if (affine) y = maybe_round(osv * maybe_round(y + obv, p.round_bf16), p.round_bf16);
+            if (AFF) y = maybe_round(osv * maybe_round(y + obv, p.round_bf16), p.round_bf16);
             int oc = n;
             bool store = n < p.N;
             if (swiglu) {  // W rows interleaved: row 2i = fc_1 row i, 2i+1 = fc_2 row i (model.py:298-300): neighbouring lanes
@@ -1001,10 +1047,10 @@ static const CUtensorMap* tc_cached_map3(const void* ptr, int rows, int K, int b
   return &cache.emplace(key, m).first->second;
 }
 
-template <int BN, int CL>
-static int tc_launch(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, void* stream) {
+template <int BN, int CL, bool AFF>
+static int tc_launch_v(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, void* stream) {
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, CL>;
+  auto kern = gemm_tc_kernel<BN, CL, AFF>;
   if (!attr_set) {
     LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
@@ -1049,9 +1095,10 @@ static std::atomic<int> g_gemm_pair{[] {
   return e ? atoi(e) : 1;
 }()};
 
-static int tc_launch_pair(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, void* stream) {
+template <bool AFF>
+static int tc_launch_pair_v(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, void* stream) {
   static bool attr_set = false;
-  auto kern = gemm_tc_pair_kernel;
+  auto kern = gemm_tc_pair_kernel<AFF>;
   if (!attr_set) {
     LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
@@ -1081,9 +1128,10 @@ static int tc_launch_pair(const CUtensorMap& mx, const CUtensorMap& mw, const Tc
   return LP_OK;
 }
 
-static int tc_launch_swap(const CUtensorMap& mx, const CUtensorMap& mw, const TcSwapParams& p, void* stream) {
+template <bool AFF, bool SK>
+static int tc_launch_swap_v(const CUtensorMap& mx, const CUtensorMap& mw, const TcSwapParams& p, void* stream) {
   static bool attr_set = false;
-  auto kern = gemm_tc_swap_kernel;
+  auto kern = gemm_tc_swap_kernel<AFF, SK>;
   if (!attr_set) {
     LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
@@ -1093,9 +1141,24 @@ static int tc_launch_swap(const CUtensorMap& mx, const CUtensorMap& mw, const Tc
   if (nstages > 12) nstages = 12;
   if (nstages < 2) return LP_ERR_UNSUPPORTED;
   const size_t smem = (size_t)nstages * stage_bytes + 1024;
-  const int nunits = ((p.N + TC_BM - 1) / TC_BM) * p.ksplit;
-  const int grid = nunits < num_sms() ? nunits : num_sms();
+  const int tiles = (p.N + TC_BM - 1) / TC_BM;
+  const long long nunits = p.streamk ? (long long)tiles * ((p.K / TC_BK + p.KB - 1) / p.KB) : (long long)tiles * p.ksplit;
+  const int grid = nunits < num_sms() ? (int)nunits : num_sms();
   return launch(kern, dim3(grid), dim3(TC_THREADS), smem, stream, mx, mw, p, nstages);
+}
+
+// Run-time selection of the compile-time variants: AFF = adapter-v2 output affine in the epilogue, SK = stream-K work split.
+static int tc_launch_swap(const CUtensorMap& mx, const CUtensorMap& mw, const TcSwapParams& p, void* stream) {
+  const bool aff = p.out_bias || p.out_scale;
+  if (p.streamk) return aff ? tc_launch_swap_v<true, true>(mx, mw, p, stream) : tc_launch_swap_v<false, true>(mx, mw, p, stream);
+  return aff ? tc_launch_swap_v<true, false>(mx, mw, p, stream) : tc_launch_swap_v<false, false>(mx, mw, p, stream);
+}
+template <int BN, int CL>
+static int tc_launch(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, void* stream) {
+  return (p.out_bias || p.out_scale) ? tc_launch_v<BN, CL, true>(mx, mw, p, stream) : tc_launch_v<BN, CL, false>(mx, mw, p, stream);
+}
+static int tc_launch_pair(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, void* stream) {
+  return (p.out_bias || p.out_scale) ? tc_launch_pair_v<true>(mx, mw, p, stream) : tc_launch_pair_v<false>(mx, mw, p, stream);
 }
 
 }  // namespace lp
@@ -1163,12 +1226,23 @@ int lp_gemm_bf16_tc_affine(const void* x_terms, int nterms, int M, const void* w
       if (kb_env == 1 || kb_env == 2 || kb_env == 4) q.KB = kb_env;
     }
     q.ksplit = 1;
+    q.streamk = 0;
     const int tiles_n = (N + lp::TC_BM - 1) / lp::TC_BM, nk = (K / lp::TC_BK + q.KB - 1) / q.KB;
-    if (epilogue == LP_EPI_RESIDUAL && residual == out_f32 && !out_bf16 && !round_bf16 && tiles_n < lp::num_sms()) {
-      // x += W . u in place: split K so that every SM streams weights; partial sums are added atomically
-      int ks = (lp::num_sms() + tiles_n - 1) / tiles_n;
-      while (ks > 1 && nk / ks < 2) --ks;
-      q.ksplit = ks > 8 ? 8 : ks;
+    if (epilogue == LP_EPI_RESIDUAL && residual == out_f32 && !out_bf16 && !round_bf16) {
+      // x += W . u in place: partial sums are added atomically, so the work can be cut anywhere along K.  The (tile, K-stage)
+      // sequence is split into one equal range per SM (stream-K): every SM streams the same number of weight bytes whatever the
+      // tile count (32 tiles of n_embd rows, 96 of a QKV matrix, ...).  LP_SWAP_STREAMK=0: the older unit split (A/B).
+      static const bool sk_env = [] {
+        const char* e = getenv("LP_SWAP_STREAMK");
+        return !(e && e[0] == '0');
+      }();
+      if (sk_env && tiles_n < lp::num_sms() && (long long)tiles_n * nk >= lp::num_sms()) {
+        q.streamk = 1;
+      } else if (tiles_n < lp::num_sms()) {
+        int ks = (lp::num_sms() + tiles_n - 1) / tiles_n;
+        while (ks > 1 && nk / ks < 2) --ks;
+        q.ksplit = ks > 8 ? 8 : ks;
+      }
     }
     const CUtensorMap* mx = lp::tc_cached_map3(x_terms, nterms * M, K, q.fuse ? nterms * q.NB : q.NB, q.KB);
     const CUtensorMap* mw = lp::tc_cached_map3(w_bf16, N, K, lp::TC_BM, q.KB);

@@ -286,7 +286,10 @@ def test_attention_against_sdpa(lib, kvdt, B, T, H, G, hs, max_seq, p0):
 @pytest.mark.parametrize("B,H,G,hs,n_elem,max_seq,p0", [
     (1, 8, 8, 64, 16, 64, 0), (1, 8, 8, 64, 16, 64, 63), (2, 32, 32, 128, 32, 2048, 1500), (1, 71, 1, 64, 64, 512, 300),
     (2, 64, 8, 128, 128, 1024, 1023), (1, 32, 32, 128, 128, 2048, 2047), (1, 8, 8, 64, 64, 48, 200), (3, 128, 8, 64, 64, 200, 130),
-    (1, 64, 2, 128, 128, 300, 77), (32, 32, 32, 128, 32, 256, 100)])
+    (1, 64, 2, 128, 128, 300, 77), (32, 32, 32, 128, 32, 256, 100),
+    # more (batch, group) CTAs than the chip holds at once (no split; a wave-aware split count was measured SLOWER at B = 32:
+    # 5.65 -> 5.78 ms per step — a partially filled tail wave still saturates HBM, the merge pass does not pay)
+    (19, 16, 16, 128, 128, 1024, 1000), (32, 32, 32, 128, 32, 2048, 2047), (40, 16, 16, 64, 16, 512, 300)])
 def test_attention_decode_fused(lib, B, H, G, hs, n_elem, max_seq, p0):
     """lp_attn_decode_fused (RoPE + append + split-K tensor-core attention + merge in one launch) against the reference
     op sequence (model.py:208-249) in float64 on the same bf16 cache.  p0 >= max_seq: ring / sliding-window case."""
@@ -475,10 +478,12 @@ def test_gemm_bf16_tc(lib, nterms, M, N, K):
         torch.testing.assert_close(terms.float().sum(0), want, rtol=2 ** (-8 * nterms + 1), atol=1e-5)
 
 
-@pytest.mark.parametrize("M,N,K", [(32, 4096, 4096), (9, 512, 16384), (64, 4544, 18176), (17, 256, 192)])
+@pytest.mark.parametrize("M,N,K", [(32, 4096, 4096), (9, 512, 16384), (64, 4544, 18176), (17, 256, 192), (32, 12288, 4096),
+                                   (32, 4096, 16384), (24, 6144, 2048), (48, 8192, 8192)])
 def test_gemm_bf16_tc_inplace_residual_split_k(lib, M, N, K):
-    """Decode batches (M <= 64): swap-AB kernel; x += u . W^T + b in place is split along K over several CTAs that
-    accumulate atomically (the summation order of the <= 8 partial sums is not fixed: tolerance, not bit-equality)."""
+    """Decode batches (M <= 64): swap-AB kernel; x += u . W^T + b in place is split along K — stream-K: the (tile, K-stage)
+    sequence is cut into one equal range per SM, a range may straddle two tiles — over CTAs that accumulate atomically (the
+    summation order of the partial sums is not fixed: tolerance, not bit-equality)."""
     u = f32(M, K, seed=11)
     w = f32(N, K, seed=12, scale=0.05).bfloat16()
     bias = f32(N, seed=13)
