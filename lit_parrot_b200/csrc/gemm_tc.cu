@@ -638,6 +638,25 @@ struct SwapWork {
 };
 constexpr int TC_SWAP_ACC = 256;  // TMEM columns per accumulator (nterms * NB <= 192), two accumulators
 
+// out-of-line activations for one-shot epilogues (code size, see gemm_tc_swap_kernel)
+__device__ __noinline__ float tc_gelu(float v) { return gelu_erf(v); }
+__device__ __noinline__ float tc_silu(float v) { return silu(v); }
+
+// Tuning aid, compiled in with -DLP_SWAP_TRACE only (tools/trace_swap.py): globaltimer stamps per CTA
+// [entry, set-up done, first loads issued, first stage landed, last MMA committed, accumulator seen by the epilogue, epilogue done, exit]
+#ifdef LP_SWAP_TRACE
+__device__ unsigned long long g_swap_trace[4 * 256 * 12];  // the last four launches
+__device__ unsigned int g_swap_count[256];
+__device__ __forceinline__ unsigned long long tc_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+#define SWT(i) g_swap_trace[(s_hist * 256 + blockIdx.x) * 12 + (i)] = tc_now()
+#else
+#define SWT(i) (void)0
+#endif
+
 template <bool AFF, bool SK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcSwapParams p, int nstages) {
@@ -650,6 +669,13 @@ gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   __shared__ uint32_t s_tmem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef LP_SWAP_TRACE
+  __shared__ unsigned int s_hist_sm;
+  if (threadIdx.x == 0) s_hist_sm = atomicAdd(&g_swap_count[blockIdx.x], 1u) & 3u;
+  __syncthreads();
+  const unsigned int s_hist = s_hist_sm;
+#endif
+  if (threadIdx.x == 0) SWT(0);
   const int nk = (p.K / TC_BK + KB - 1) / KB;  // stages along K (K % 64 == 0; slabs past the end are zero-filled by TMA)
   const int tiles_n = (p.N + TC_BM - 1) / TC_BM;
   const uint32_t bar0 = tc_smem_u32(bars);
@@ -678,6 +704,7 @@ gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
+  if (threadIdx.x == 0) SWT(1);
 
   if (warp == 0) {
     // ===== TMA producer: the weights do not depend on the preceding kernel, the activation terms do =====
@@ -701,6 +728,7 @@ gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           if (!waited) {
             pdl_wait();
             waited = true;
+            SWT(2);
           }
           if (p.fuse) {  // all terms in one copy: rows [0, nterms*M) of the stacked [nterms*M, K] tensor, slabs [kk][nterms*NB rows]
             tc_tma_3d(dst + KB * A_BYTES, &map_x, 0, 0, kb * KB, full_bar(s));
@@ -733,6 +761,9 @@ gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         for (int kb = kb0; kb < kb1; ++kb) {
           tc_mbar_wait(full_bar(s), ph);
           tc_fence_after();
+#ifdef LP_SWAP_TRACE
+          if (it == 0 && kb == kb0) SWT(3);
+#endif
           const uint32_t st = ring + (uint32_t)s * stage_bytes;
           uint32_t a_lo = tc_desc_lo(st);
           uint32_t b_lo = tc_desc_lo(st + KB * A_BYTES);
@@ -765,6 +796,7 @@ gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           if (++s == nstages) { s = 0; ph ^= 1; }
         }
         tc_commit(acc_full(a));
+        SWT(4);
       }
     }
   }
@@ -786,6 +818,7 @@ gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       const bool first = kb0 == 0;  // this CTA's part of the tile starts at K = 0: it adds the biases
       tc_mbar_wait(acc_full(a), (it >> 1) & 1);
       tc_fence_after();
+      if (threadIdx.x == 64) SWT(5);
       const float bias = (p.bias && n < p.N && first) ? p.bias[n] : 0.f;
       // adapter-v2 (compile-time variant): scale * ((acc + bias) + out_bias); K-split partials: the biases once
       const float obv = (AFF && p.out_bias && n < p.N && first) ? p.out_bias[n] : 0.f;
@@ -803,44 +836,68 @@ gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(v[j]);
         }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int m = c0 + j;  // batch row (warp-uniform)
-          if (m < p.M) {
-            float y = maybe_round(acc[j] + bias, p.round_bf16);
-            if (AFF) y = maybe_round(osv * maybe_round(y + obv, p.round_bf16), p.round_bf16);
-            int oc = n;
-            bool store = n < p.N;
-            if (swiglu) {  // W rows interleaved: row 2i = fc_1 row i, 2i+1 = fc_2 row i (model.py:298-300): neighbouring lanes
-              const float other = __shfl_xor_sync(0xffffffffu, y, 1);
-              y = maybe_round(maybe_round(silu(y), p.round_bf16) * other, p.round_bf16);
-              oc = n >> 1;
-              store = store && (n & 1) == 0;
-            } else if (p.epi == LP_EPI_GELU) {
-              y = maybe_round(gelu_erf(y), p.round_bf16);
-            } else if (p.epi == LP_EPI_RESIDUAL && !atomic && store) {
-              y = maybe_round(p.residual[(size_t)m * nout + oc] + y, p.round_bf16);
-            }
-            if (store) {
-              if (atomic) {
-                atomicAdd(p.out_f32 + (size_t)m * nout + oc, y);  // in place: x += partial
-              } else {
-                if (p.out_f32) p.out_f32[(size_t)m * nout + oc] = y;
-                if (p.out_bf) {
-                  for (int t = 0; t < p.out_terms; ++t) {
-                    const __nv_bfloat16 hb = __float2bfloat16_rn(y);
-                    p.out_bf[((size_t)t * p.M + m) * nout + oc] = hb;
-                    y -= __bfloat162float(hb);
-                  }
-                }
+#ifdef LP_SWAP_TRACE
+        if (threadIdx.x == 64) SWT(8);
+#endif
+        // The tail runs ONCE per tile, as straight-line code over the 32 accumulator registers.  It is written as a sequence of
+        // short uniform passes (one per step of the epilogue, the activation out of line) instead of one unrolled body holding
+        // every variant: that body was ~16 k instructions, and a launch whose CTAs own a single tile spent as long fetching
+        // them (all SMs walking the same cold instruction lines in lock step: 20 us) as streaming its weights (18 us).
+        const bool rb = p.round_bf16 != 0;
+#define SWAP_PASS(expr)                   \
+  _Pragma("unroll") for (int j = 0; j < 32; ++j) { expr; }
+#define SWAP_ROUND() \
+  if (rb) SWAP_PASS(acc[j] = bf16_round(acc[j]))
+        SWAP_PASS(acc[j] += bias)
+        SWAP_ROUND()
+        if (AFF) {
+          SWAP_PASS(acc[j] += obv)
+          SWAP_ROUND()
+          SWAP_PASS(acc[j] *= osv)
+          SWAP_ROUND()
+        }
+        int oc = n;
+        bool store = n < p.N;
+        if (swiglu) {  // W rows interleaved: row 2i = fc_1 row i, 2i+1 = fc_2 row i (model.py:298-300): neighbouring lanes
+          SWAP_PASS(const float other = __shfl_xor_sync(0xffffffffu, acc[j], 1); acc[j] = maybe_round(tc_silu(acc[j]), p.round_bf16) * other)
+          SWAP_ROUND()
+          oc = n >> 1;
+          store = store && (n & 1) == 0;
+        } else if (p.epi == LP_EPI_GELU) {
+          SWAP_PASS(acc[j] = tc_gelu(acc[j]))
+          SWAP_ROUND()
+        } else if (p.epi == LP_EPI_RESIDUAL && !atomic) {
+          if (store) SWAP_PASS(if (c0 + j < p.M) acc[j] += p.residual[(size_t)(c0 + j) * nout + oc])
+          SWAP_ROUND()
+        }
+        if (store) {
+          if (atomic) {
+            SWAP_PASS(if (c0 + j < p.M) atomicAdd(p.out_f32 + (size_t)(c0 + j) * nout + oc, acc[j]))  // in place: x += partial
+          } else {
+            if (p.out_f32) SWAP_PASS(if (c0 + j < p.M) p.out_f32[(size_t)(c0 + j) * nout + oc] = acc[j])
+            if (p.out_bf) {
+#pragma unroll 1
+              for (int t = 0; t < p.out_terms; ++t) {
+                __nv_bfloat16* dst = p.out_bf + (size_t)t * p.M * nout + oc;
+                SWAP_PASS(if (c0 + j < p.M) {
+                  const __nv_bfloat16 hb = __float2bfloat16_rn(acc[j]);
+                  dst[(size_t)(c0 + j) * nout] = hb;
+                  acc[j] -= __bfloat162float(hb);
+                })
               }
             }
           }
         }
+#undef SWAP_PASS
+#undef SWAP_ROUND
       }
+#ifdef LP_SWAP_TRACE
+      if (threadIdx.x == 64) SWT(9);
+#endif
       tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(acc_empty(a)) : "memory");
+      if (threadIdx.x == 64) SWT(6);
     }
   }
   __syncthreads();
@@ -848,6 +905,7 @@ gemm_tc_swap_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(2 * TC_SWAP_ACC) : "memory");
   }
+  if (threadIdx.x == 0) SWT(7);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1164,6 +1222,12 @@ static int tc_launch_pair(const CUtensorMap& mx, const CUtensorMap& mw, const Tc
 }  // namespace lp
 
 extern "C" {
+
+#ifdef LP_SWAP_TRACE
+int lp_debug_swap_trace(unsigned long long* out, int n) {  // tuning builds only (tools/trace_swap.py)
+  return cudaMemcpyFromSymbol(out, lp::g_swap_trace, sizeof(unsigned long long) * (n < 12288 ? n : 12288)) == cudaSuccess ? LP_OK : LP_ERR_CUDA;
+}
+#endif
 
 int lp_debug_gemm_stats(long long* out4) {  // {cycles, ns, k-blocks, -} of the last LP_GEMM_DEBUG=2 launch (CTA 0)
   return cudaMemcpyFromSymbol(out4, lp::g_tc_debug, 4 * sizeof(long long)) == cudaSuccess ? LP_OK : LP_ERR_CUDA;

@@ -27,8 +27,11 @@ def timeit(fn, iters=40, warm=5):
 
 print(f"{'M,N,K':24s} {'terms':>5s} {'epi':>4s} {'us':>8s} {'GB/s':>7s}  torch.matmul us")
 for M in [int(v) for v in os.environ.get("KBENCH_M", "16,32,64").split(",")]:
-    for N, K, epi in [(12288, 4096, 0), (16384, 4096, 1), (4096, 4096, 3), (4096, 16384, 3), (50688, 4096, 0)]:
-        nt = 2
+    shapes = [(12288, 4096, 0), (16384, 4096, 1), (4096, 4096, 3), (4096, 16384, 3), (50688, 4096, 0)]
+    if os.environ.get("KBENCH_SHAPES"):  # "N,K,epi;N,K,epi;..."
+        shapes = [tuple(int(v) for v in t.split(",")) for t in os.environ["KBENCH_SHAPES"].split(";")]
+    for N, K, epi in shapes:
+        nt = int(os.environ.get("KBENCH_TERMS", "2"))
         x = torch.randn(M, K, device=DEV)
         w = [torch.randn(N, K, device=DEV, dtype=torch.bfloat16) * 0.02 for _ in range(6)]  # 6 x >= 33 MB: beyond L2 in rotation
         out = torch.zeros(M, N, device=DEV)
