@@ -354,6 +354,38 @@ def run_prefill(preset, T, device, reps=3):
             "tflops": tf, "tensor_frac_of_sustained_peak": tf / peak, "flops": flops}
 
 
+def run_gptq_quantizer(device, n_samples=8):
+    """the device GPTQ quantiser (reference quantize/gptq.py, published: 850 s for the 32 layers of falcon-7b with 128
+    samples on an A100, tutorials/quantize.md:114-117) on ONE Llama-2-7b-width block + lm_head, random-init bf16 weights,
+    `n_samples` synthetic calibration sequences of 2048 tokens, group size 128."""
+    import torch
+
+    import lit_parrot_b200 as lp
+    from lit_parrot_b200 import gptq
+
+    cfg = lp.Config.from_name("Llama-2-7b-hf", n_layer=1, block_size=2048)
+    torch.manual_seed(1234)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with torch.device(device):
+            m = lp.GPT(cfg)
+    finally:
+        torch.set_default_dtype(prev)
+    m.apply(m._init_weights)
+    m.eval()
+    samples = torch.randint(0, cfg.vocab_size, (n_samples, cfg.block_size), generator=torch.Generator().manual_seed(1))
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    gptq.blockwise_quantization(m, samples, device, bits=4, groupsize=128, batch=8, verbose=False)
+    torch.cuda.synchronize(device)
+    dt = time.perf_counter() - t0
+    del m
+    torch.cuda.empty_cache()
+    return {"workload": f"GPTQ quantiser: 1 Llama-2-7b block (5 linear layers) + lm_head, int4 g128, {n_samples} x 2048 calibration tokens",
+            "ms": dt * 1e3}
+
+
 def run_config0(device):
     """BASELINE configs[0]: pythia-70m random init, greedy generate() of 128 tokens from a 16-token prompt.  The reference runs it
     as-is on the host cores (fp32, baseline/_ref); beside it the same call through this repo's generate() on the GPU (bf16 weights,
@@ -638,6 +670,10 @@ def main():
             extras.append(run_prefill("falcon-7b", 1792, device))  # 1792 + 256 decode tokens = block_size 2048
         except Exception as e:
             extras.append({"workload": "falcon-7b prefill", "error": repr(e)[:200]})
+        try:
+            extras.append(run_gptq_quantizer(device))
+        except Exception as e:
+            extras.append({"workload": "GPTQ quantiser", "error": repr(e)[:200]})
         try:
             extras.append(run_config0(device))  # BASELINE configs[0]: the reference as-is on CPU beside the same generate() here
         except Exception as e:
