@@ -437,13 +437,13 @@ static size_t ad_smem_bytes() {
 
 template <int HS>
 static int ad_launch(const AttnDecParams& p, int B, int head_tiles, void* stream) {
-  static bool attr_set = false;  // idempotent; a benign race sets it twice
+  static std::atomic<unsigned long long> attr_set{0};  // one bit per device
   auto kern = attn_decode_fused_kernel<HS>;
   const size_t smem = ad_smem_bytes<HS>();
-  if (!attr_set) {
+  if (needs_device_setup(attr_set)) {
     LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
+    mark_device_setup(attr_set);
   }
   return launch(kern, dim3(B * p.G, p.n_splits, head_tiles), dim3(AD_THREADS), smem, stream, p);
 }
@@ -703,12 +703,12 @@ attn_prefill_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict
 template <int HS>
 static int ap_launch(const float* q, const void* kc, const void* vc, const int* pos, float* out, int B, int T, int H, int G, int max_seq,
                      float scale, int exact, int round_bf16, void* stream) {
-  static bool attr_set = false;
+  static std::atomic<unsigned long long> attr_set{0};  // one bit per device
   auto kern = attn_prefill_kernel<HS>;
   const size_t smem = (size_t)AD_STAGES * 2 * AD_TILE * HS * 2;
-  if (!attr_set) {
+  if (needs_device_setup(attr_set)) {
     LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    mark_device_setup(attr_set);
   }
   return launch(kern, dim3((T + 63) / 64, H, B), dim3(AD_THREADS), smem, stream, q, reinterpret_cast<const __nv_bfloat16*>(kc),
                 reinterpret_cast<const __nv_bfloat16*>(vc), pos, out, T, H, G, max_seq, scale * 1.4426950408889634f, exact, round_bf16);

@@ -359,15 +359,15 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
 
 template <int HS>
 static int at_launch(const CUtensorMap& mk, const CUtensorMap& mv, const AtParams& p, void* stream) {
-  static bool attr_set = false;
+  static std::atomic<unsigned long long> attr_set{0};  // one bit per device
   auto kern = attn_prefill_tc_kernel<HS>;
   constexpr int SL = HS / 64;
   // q terms + 2 stages of K and V + P terms: hs 128 fp32 mode 161 KB (one CTA per SM), bf16 mode 113 KB (two per SM: one CTA's
   // softmax overlaps the other's MMAs); hs 64: 97 / 65 KB (two / three per SM)
   const size_t smem = (size_t)p.nterms * SL * AT_BM * 128 + 4 * SL * AT_BN * 128 + (size_t)p.nterms * AT_BM * 128 + 1024;
-  if (!attr_set) {
+  if (needs_device_setup(attr_set)) {
     LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * SL * AT_BM * 128 + 4 * SL * AT_BN * 128 + 2 * AT_BM * 128 + 1024)));
-    attr_set = true;
+    mark_device_setup(attr_set);
   }
   return launch(kern, dim3((p.T + AT_BM - 1) / AT_BM, p.H, p.B), dim3(AT_THREADS), smem, stream, mk, mv, p);
 }

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "lp_abi.h"
 
 namespace lp {
@@ -13,6 +15,18 @@ namespace lp {
 // host side: error plumbing + launch helper with Programmatic Dependent Launch (PDL)
 // ---------------------------------------------------------------------------------------------
 void set_cuda_error(cudaError_t e, const char* what);
+
+// One-time set-up PER DEVICE (cudaFuncSetAttribute is per device; a process may drive several GPUs): `mask` holds one bit per
+// device ordinal.  Callers test, configure, then mark — two threads racing configure twice, which is harmless.
+inline bool needs_device_setup(const std::atomic<unsigned long long>& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  return !(mask.load(std::memory_order_acquire) & (1ull << (dev & 63)));
+}
+inline void mark_device_setup(std::atomic<unsigned long long>& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) mask.fetch_or(1ull << (dev & 63), std::memory_order_release);
+}
 bool pdl_enabled();
 int num_sms();
 void count_launch();

@@ -1107,11 +1107,11 @@ static const CUtensorMap* tc_cached_map3(const void* ptr, int rows, int K, int b
 
 template <int BN, int CL, bool AFF>
 static int tc_launch_v(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, void* stream) {
-  static bool attr_set = false;
+  static std::atomic<unsigned long long> attr_set{0};  // one bit per device
   auto kern = gemm_tc_kernel<BN, CL, AFF>;
-  if (!attr_set) {
+  if (needs_device_setup(attr_set)) {
     LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
+    mark_device_setup(attr_set);
   }
   const int stage_bytes = p.nterms * TC_BM * TC_BK * 2 + BN * TC_BK * 2;
   int nstages = (212 * 1024) / stage_bytes;
@@ -1155,11 +1155,11 @@ static std::atomic<int> g_gemm_pair{[] {
 
 template <bool AFF>
 static int tc_launch_pair_v(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, void* stream) {
-  static bool attr_set = false;
+  static std::atomic<unsigned long long> attr_set{0};  // one bit per device
   auto kern = gemm_tc_pair_kernel<AFF>;
-  if (!attr_set) {
+  if (needs_device_setup(attr_set)) {
     LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
+    mark_device_setup(attr_set);
   }
   const int stage_bytes = p.nterms * TC_BM * TC_BK * 2 + 128 * TC_BK * 2;
   int nstages = (212 * 1024) / stage_bytes;
@@ -1188,11 +1188,11 @@ static int tc_launch_pair_v(const CUtensorMap& mx, const CUtensorMap& mw, const 
 
 template <bool AFF, bool SK>
 static int tc_launch_swap_v(const CUtensorMap& mx, const CUtensorMap& mw, const TcSwapParams& p, void* stream) {
-  static bool attr_set = false;
+  static std::atomic<unsigned long long> attr_set{0};  // one bit per device
   auto kern = gemm_tc_swap_kernel<AFF, SK>;
-  if (!attr_set) {
+  if (needs_device_setup(attr_set)) {
     LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
+    mark_device_setup(attr_set);
   }
   const int stage_bytes = p.KB * (TC_BM * TC_BK * 2 + p.nterms * p.NB * TC_BK * 2);
   int nstages = (212 * 1024) / stage_bytes;

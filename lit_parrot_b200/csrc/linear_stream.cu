@@ -560,14 +560,14 @@ static size_t gs_tail_smem(int fmt, int NB, int K, int ncols, int ldx) {
 
 template <int FMT, int NB>
 static int gs_launch(const CUtensorMap& map, const GsParams& p, size_t smem, int grid, void* stream) {
-  static bool attr_set = false;
+  static std::atomic<unsigned long long> attr_set{0};  // one bit per device
   auto kern = linear_stream_kernel<FMT, NB>;
-  if (!attr_set) {
+  if (needs_device_setup(attr_set)) {
     LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)));
     // keep the SM's L1/shared split at maximum shared memory: otherwise the carve-out is sized for ONE CTA of this kernel
     // and the next kernel's CTAs (PDL) cannot become resident before this one drains
     LP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
+    mark_device_setup(attr_set);
   }
   return launch(kern, dim3(grid), dim3(GS_THREADS), smem, stream, map, p);
 }

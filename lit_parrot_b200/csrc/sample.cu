@@ -139,14 +139,22 @@ sample_kernel(const float* __restrict__ logits, int V, float temperature, int to
 constexpr int GREEDY_CTAS = 32;
 constexpr int GREEDY_THREADS = 256;
 constexpr int GREEDY_MAX_ROWS = 256;
-static Best* g_greedy_part = nullptr;   // [GREEDY_MAX_ROWS][GREEDY_CTAS]
-static unsigned int* g_greedy_ticket = nullptr;  // [GREEDY_MAX_ROWS]
+// scratch of the arg-max reduction, one set PER DEVICE (lp_init(device) allocates the current device's)
+static Best* g_greedy_part_dev[64] = {};          // [GREEDY_MAX_ROWS][GREEDY_CTAS]
+static unsigned int* g_greedy_ticket_dev[64] = {};  // [GREEDY_MAX_ROWS]
+static int cur_dev() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d & 63;
+}
+static Best*& greedy_part() { return g_greedy_part_dev[cur_dev()]; }
+static unsigned int*& greedy_ticket() { return g_greedy_ticket_dev[cur_dev()]; }
 
 int init_sample() {
-  if (g_greedy_part) return LP_OK;
-  LP_CUDA_TRY(cudaMalloc(&g_greedy_part, sizeof(Best) * GREEDY_MAX_ROWS * GREEDY_CTAS));
-  LP_CUDA_TRY(cudaMalloc(&g_greedy_ticket, sizeof(unsigned int) * (GREEDY_MAX_ROWS + 1)));  // + 1: sample_kernel's row ticket
-  LP_CUDA_TRY(cudaMemset(g_greedy_ticket, 0, sizeof(unsigned int) * (GREEDY_MAX_ROWS + 1)));
+  if (greedy_part()) return LP_OK;
+  LP_CUDA_TRY(cudaMalloc(&greedy_part(), sizeof(Best) * GREEDY_MAX_ROWS * GREEDY_CTAS));
+  LP_CUDA_TRY(cudaMalloc(&greedy_ticket(), sizeof(unsigned int) * (GREEDY_MAX_ROWS + 1)));  // + 1: sample_kernel's row ticket
+  LP_CUDA_TRY(cudaMemset(greedy_ticket(), 0, sizeof(unsigned int) * (GREEDY_MAX_ROWS + 1)));
   return LP_OK;
 }
 
@@ -205,10 +213,10 @@ extern "C" int lp_sample(const float* logits, int rows, int V, float temperature
                          int32_t* token_out, int32_t* seq_buf, int32_t* pos_inout, void* stream) {
   if (!logits || !token_out || rows <= 0 || V <= 0 || !(temperature > 0.f) || top_k < 0) return LP_ERR_INVALID_ARG;
   if (seq_buf && (rows != 1 || !pos_inout)) return LP_ERR_INVALID_ARG;  // pos_inout alone (any rows): just advance
-  if (rows > 1 && step && !lp::g_greedy_ticket) return LP_ERR_INVALID_ARG;  // lp_init() allocates the row ticket
-  if (top_k == 1 && rows <= lp::GREEDY_MAX_ROWS && lp::g_greedy_part)
+  if (rows > 1 && step && !lp::greedy_ticket()) return LP_ERR_INVALID_ARG;  // lp_init() allocates the row ticket
+  if (top_k == 1 && rows <= lp::GREEDY_MAX_ROWS && lp::greedy_part())
     return lp::launch(lp::greedy_kernel, dim3(lp::GREEDY_CTAS, rows), dim3(lp::GREEDY_THREADS), 0, stream, logits, V, temperature, step,
-                      token_out, seq_buf, pos_inout, lp::g_greedy_part, lp::g_greedy_ticket);
+                      token_out, seq_buf, pos_inout, lp::greedy_part(), lp::greedy_ticket());
   return lp::launch(lp::sample_kernel, dim3(rows), dim3(lp::SAMPLE_THREADS), 0, stream, logits, V, temperature, top_k, seed, step,
-                    token_out, seq_buf, pos_inout, lp::g_greedy_ticket ? lp::g_greedy_ticket + lp::GREEDY_MAX_ROWS : nullptr);
+                    token_out, seq_buf, pos_inout, lp::greedy_ticket() ? lp::greedy_ticket() + lp::GREEDY_MAX_ROWS : nullptr);
 }
