@@ -64,7 +64,9 @@ def build(preset, device, dtype, quant=None):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["cpu-generate", "cpu-decode", "cuda-decode"])
+    ap.add_argument("mode", choices=["cpu-generate", "cpu-decode", "cuda-decode", "cuda-logits"])
+    ap.add_argument("--job", default=None, help="cuda-logits: torch file {config: kwargs, state_dict, idx, prompt, new_tokens}")
+    ap.add_argument("--out", default=None, help="cuda-logits: torch file to write the results to")
     ap.add_argument("--preset", default="pythia-70m")
     ap.add_argument("--prompt", type=int, default=16)
     ap.add_argument("--tokens", type=int, default=128)
@@ -104,6 +106,38 @@ def main():
         out.update(tok_s=new / min(times), seconds=min(times), new_tokens=new, tokens_head=y[:24].tolist(),
                    what=f"reference generate() as-is: {args.preset} fp32 random init on CPU, {args.prompt}-token prompt -> {args.tokens} "
                         f"tokens, top_k=1, best of {args.reps} after 1 warm-up, {threads} threads")
+        print(json.dumps(out))
+        return
+    if args.mode == "cuda-logits":
+        # Parity aid: the reference on the GPU on GIVEN weights — full-forward logits and a greedy generation in
+        # fp32 (matmul precision "highest": no TF32) and under bf16-true (parameters, activations and KV cache in bf16, eager kernels)
+        import generate.base as gb
+        import lit_gpt
+
+        job = torch.load(args.job)
+        device = torch.device("cuda", 0)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        torch.set_float32_matmul_precision("highest")
+        res = {}
+        for tag, dtype in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+            prev = torch.get_default_dtype()
+            torch.set_default_dtype(dtype)  # the rope-cache dtype rule follows the default dtype (model.py:325-326), as under Fabric bf16-true
+            try:
+                model = lit_gpt.GPT(lit_gpt.Config(**job["config"]))
+                model.load_state_dict(job["state_dict"], strict=True)
+                model = model.to(device=device, dtype=dtype).eval()
+                with torch.no_grad():
+                    res["logits_" + tag] = model(job["idx"].to(device)).float().cpu()
+                    model.reset_cache()
+                    n = job["prompt"].numel() + int(job["new_tokens"])
+                    res["gen_" + tag] = gb.generate(model, job["prompt"].to(device), n, n, temperature=1.0, top_k=1).cpu()
+            finally:
+                torch.set_default_dtype(prev)
+            del model
+            torch.cuda.empty_cache()
+        torch.save(res, args.out)
+        out.update(what="reference logits / greedy tokens in fp32 and bf16-true on the given weights", keys=sorted(res))
         print(json.dumps(out))
         return
     cuda = args.mode == "cuda-decode"

@@ -1,0 +1,41 @@
+"""deep models in bf16.  The north-star tolerance (logits max-abs 2e-2, cosine > 0.999, 64 identical greedy
+tokens) is below the reference's own bf16 noise for 24-layer models, so two claims are tested against the UNMODIFIED reference run
+on the same GPU (baseline/_ref, eager PyTorch, subprocess; tools/bf16_noise_floor.py):
+  * default mode (fp32 activations over the bf16 weights, bf16 KV cache) meets the north-star tolerance against the reference in
+    fp32 and decodes the same 64 greedy tokens;
+  * precision="bf16" is as close to the reference in fp32 as the reference's own bf16-true run is (the noise floor).
+"""
+import importlib.util
+import os
+
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _tool():
+    spec = importlib.util.spec_from_file_location("bf16_noise_floor", os.path.join(REPO, "tools", "bf16_noise_floor.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_deep_model_against_the_reference_noise_floor(which):
+    if not os.path.isdir(os.path.join(REPO, "baseline", "_ref", "lit_gpt")):
+        pytest.skip("baseline/_ref (the unmodified reference, installed by __graft_entry__.build()) is not present")
+    tool = _tool()
+    name, kw = list(tool.CASES.items())[which]
+    lines = []
+    res = tool.run_case(name, kw, torch.device("cuda", 0), lines)
+    print("\n".join(lines))
+    floor = res["reference bf16-true vs reference fp32   (the noise floor)"]
+    bf16 = res["this repo precision='bf16' vs reference fp32"]
+    dflt = res["this repo fp32 activations (default) vs reference fp32"]
+    # default mode: the north-star tolerance itself, and token-exact for the first 64 tokens
+    assert dflt[0] <= 2e-2 and dflt[1] > 0.999 and dflt[2] == 64, dflt
+    # bf16-faithful mode: not further from the fp32 reference than the reference's own bf16 run (25 % slack: one sample of a noise)
+    assert bf16[0] <= 1.25 * floor[0] and (1 - bf16[1]) <= 1.25 * (1 - floor[1]), (bf16, floor)
+    assert floor[0] > 2e-2  # the premise: the reference's own bf16 noise exceeds the north-star tolerance on a deep model
