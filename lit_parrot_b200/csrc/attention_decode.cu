@@ -633,15 +633,15 @@ attn_prefill_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
     const float base0 = (mn0 == -CUDART_INF_F) ? 0.f : mn0, base1 = (mn1 == -CUDART_INF_F) ? 0.f : mn1;
-    const float corr0 = exp2f(m0 - base0), corr1 = exp2f(m1 - base1);
+    const float corr0 = fast_ex2(m0 - base0), corr1 = fast_ex2(m1 - base1);
     m0 = mn0;
     m1 = mn1;
     uint32_t ph[NT][2], pl[NT][2];
     float ls0 = 0.f, ls1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      float p0 = exp2f(S[nt][0] - base0), p1 = exp2f(S[nt][1] - base0);
-      float p2 = exp2f(S[nt][2] - base1), p3 = exp2f(S[nt][3] - base1);
+      float p0 = fast_ex2(S[nt][0] - base0), p1 = fast_ex2(S[nt][1] - base0);
+      float p2 = fast_ex2(S[nt][2] - base1), p3 = fast_ex2(S[nt][3] - base1);
       split2(p0, p1, ph[nt][0], pl[nt][0]);
       split2(p2, p3, ph[nt][1], pl[nt][1]);
       if (!exact) {  // the row sum uses the probabilities that are actually multiplied with V

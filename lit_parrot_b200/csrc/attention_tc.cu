@@ -284,11 +284,11 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
       mx = fmaxf(mx, s_mx[j & 1][ch ^ 1][r]);
       const float m_new = fmaxf(m_run, mx);             // finite from tile 0 on (key 0 is visible to every row)
       const float base = m_new == -CUDART_INF_F ? 0.f : m_new;
-      const float corr = exp2f(m_run - base);           // 0 for the first tile
+      const float corr = fast_ex2(m_run - base);           // 0 for the first tile
       float ls = 0.f;
 #pragma unroll
       for (int i = 0; i < HC; ++i) {
-        sc[i] = exp2f(sc[i] - base);
+        sc[i] = fast_ex2(sc[i] - base);
         ls += sc[i];
       }
       l_run = fmaf(l_run, corr, ls);  // partial row sum of this column half; the halves are added at the end

@@ -77,6 +77,14 @@ __device__ __forceinline__ float out_affine(float y, const float* __restrict__ o
   return y;
 }
 
+// 2^x as ONE MUFU instruction (ex2.approx.ftz: results below 2^-126 flush to zero, 2 ulp).  exp2f() wraps the same instruction in a
+// range fix-up (compare, halve, square: 3 more instructions per element) that a softmax probability does not need.
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -116,6 +116,56 @@ __global__ void rope_kv_kernel(const float* __restrict__ qkv, const float* __res
   }
 }
 
+// The same, four dims per thread (hs % 4 == 0, n_elem % 8 == 0: the rotation partner of an aligned group of four is an aligned
+// group of four): 16-byte loads / stores, one index division per four elements.  Same arithmetic per element (bit-identical);
+// the scalar kernel above took 44 us per falcon-7b layer at T = 1792 (4 % of the prefill) for 70 MB of traffic.
+template <typename KV>
+__global__ void __launch_bounds__(256) rope_kv_vec4_kernel(const float* __restrict__ qkv, const float* __restrict__ cosT,
+                                                           const float* __restrict__ sinT, const int* __restrict__ pos,
+                                                           float* __restrict__ q_out, KV* __restrict__ kc, KV* __restrict__ vc, int T, int H,
+                                                           int G, int hs, int n_elem, int max_seq, int round_bf16) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int row = blockIdx.x;
+  const int b = row / T, t = row % T;
+  const int qpk = H / G;
+  const int p = pos[t];
+  const int hs4 = hs >> 2, half = n_elem >> 1;
+  const float* rowp = qkv + (size_t)row * (H + 2 * G) * hs;
+  for (int e = threadIdx.x; e < (H + 2 * G) * hs4; e += blockDim.x) {
+    const int slot_in_row = e / hs4, d = (e - slot_in_row * hs4) << 2;
+    const int g = slot_in_row / (qpk + 2), j = slot_in_row - g * (qpk + 2);
+    const float* src = rowp + (size_t)slot_in_row * hs;
+    float4 v = *reinterpret_cast<const float4*>(src + d);
+    if (j <= qpk && d < n_elem) {  // q heads and the k head are rotated, v is not
+      const bool lo = d < half;
+      float4 pr = *reinterpret_cast<const float4*>(src + (lo ? d + half : d - half));
+      if (lo) pr = make_float4(-pr.x, -pr.y, -pr.z, -pr.w);
+      const float4 c = *reinterpret_cast<const float4*>(cosT + (size_t)p * n_elem + d);
+      const float4 s = *reinterpret_cast<const float4*>(sinT + (size_t)p * n_elem + d);
+      v.x = maybe_round(__fadd_rn(__fmul_rn(v.x, c.x), __fmul_rn(pr.x, s.x)), round_bf16);
+      v.y = maybe_round(__fadd_rn(__fmul_rn(v.y, c.y), __fmul_rn(pr.y, s.y)), round_bf16);
+      v.z = maybe_round(__fadd_rn(__fmul_rn(v.z, c.z), __fmul_rn(pr.z, s.z)), round_bf16);
+      v.w = maybe_round(__fadd_rn(__fmul_rn(v.w, c.w), __fmul_rn(pr.w, s.w)), round_bf16);
+    }
+    if (j < qpk) {
+      *reinterpret_cast<float4*>(q_out + (size_t)row * H * hs + (size_t)(g * qpk + j) * hs + d) = v;
+    } else {
+      const int slot = p % max_seq;
+      KV* dst = (j == qpk ? kc : vc) + (((size_t)b * G + g) * max_seq + slot) * hs + d;
+      if constexpr (sizeof(KV) == 2) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), c2 = __floats2bfloat162_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&a);
+        pk.y = *reinterpret_cast<const uint32_t*>(&c2);
+        *reinterpret_cast<uint2*>(dst) = pk;
+      } else {
+        *reinterpret_cast<float4*>(dst) = v;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // GPTQ storage (uint8 (N, K/2), strides (1, N)) -> row-major [N, Kp/2], zero padded
 // ---------------------------------------------------------------------------------------------
@@ -205,6 +255,14 @@ int lp_rope_kv_append(const float* qkv, const float* cos, const float* sin, cons
   if (B <= 0 || T <= 0 || H <= 0 || G <= 0 || H % G || hs <= 0 || hs > 1024 || n_elem < 0 || n_elem > hs || ((n_elem & 1) && n_elem != 1) || max_seq <= 0)
     return LP_ERR_INVALID_ARG;
   dim3 grid(B * T), block(256);
+  const bool vec4 = hs % 4 == 0 && n_elem % 8 == 0 && !((uintptr_t)qkv & 15) && !((uintptr_t)q_out & 15) && !((uintptr_t)k_cache & 15) &&
+                    !((uintptr_t)v_cache & 15) && (n_elem == 0 || (!((uintptr_t)cos & 15) && !((uintptr_t)sin & 15)));
+  if (vec4 && kv_dtype == LP_F32)
+    return lp::launch(lp::rope_kv_vec4_kernel<float>, grid, block, 0, stream, qkv, cos, sin, pos, q_out, (float*)k_cache, (float*)v_cache,
+                      T, H, G, hs, n_elem, max_seq, round_bf16);
+  if (vec4 && kv_dtype == LP_BF16)
+    return lp::launch(lp::rope_kv_vec4_kernel<__nv_bfloat16>, grid, block, 0, stream, qkv, cos, sin, pos, q_out,
+                      (__nv_bfloat16*)k_cache, (__nv_bfloat16*)v_cache, T, H, G, hs, n_elem, max_seq, round_bf16);
   if (kv_dtype == LP_F32)
     return lp::launch(lp::rope_kv_kernel<float>, grid, block, 0, stream, qkv, cos, sin, pos, q_out, (float*)k_cache, (float*)v_cache,
                       T, H, G, hs, n_elem, max_seq, round_bf16);

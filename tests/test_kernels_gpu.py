@@ -224,7 +224,8 @@ def test_embed(lib, wdtype):
 
 
 @pytest.mark.parametrize("kvdt", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("B,T,H,G,hs,n_elem", [(1, 1, 8, 8, 64, 16), (2, 5, 8, 2, 128, 128), (1, 3, 71, 1, 64, 64), (3, 4, 4, 4, 16, 4)])
+@pytest.mark.parametrize("B,T,H,G,hs,n_elem", [(1, 1, 8, 8, 64, 16), (2, 5, 8, 2, 128, 128), (1, 3, 71, 1, 64, 64), (3, 4, 4, 4, 16, 4),
+                                              (2, 6, 32, 32, 128, 32), (1, 7, 6, 3, 20, 8)])  # 16-byte path and the scalar path (n_elem % 8)
 def test_rope_kv_append(lib, kvdt, B, T, H, G, hs, n_elem):
     max_seq, block = 16, 64
     qpk = H // G
