@@ -285,7 +285,7 @@ def run_workload(workload, steps, warmup, device, rank=0, world=1, with_e2e=True
             h_out.copy_(t, non_blocking=True)
             cur.synchronize()
             n_idx[:, 0] = n_out
-            n_pos += 1
+            n_pos[0] += 1
 
         for _ in range(warmup):
             e2e_step()
