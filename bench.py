@@ -272,14 +272,18 @@ def run_workload(workload, steps, warmup, device, rank=0, world=1, with_e2e=True
         # host-side bookkeeping through numpy views of the pinned buffers; the device-side input tensors are allocated once
         # (a caller's serving loop does the same): per step the timed region still holds the H2D copy of the ids and the position,
         # the forward through the public API, the sampler, the D2H copy of the sampled ids and the synchronisation
-        n_idx, n_pos, n_out = h_idx.numpy(), h_pos.numpy(), h_out.numpy()
-        x = torch.empty_like(h_idx, device=device)
-        p = torch.empty_like(h_pos, device=device)
+        # token ids and the position share ONE pinned int64 buffer and one device buffer: a single H2D copy per step
+        h_in = torch.empty(B + 1, dtype=torch.int64).pin_memory()
+        h_in[:B] = h_idx[:, 0]
+        h_in[B] = h_pos[0]
+        d_in = torch.empty(B + 1, dtype=torch.int64, device=device)
+        x, p = d_in[:B].view(B, 1), d_in[B:]
+        n_in, n_out = h_in.numpy(), h_out.numpy()
+        n_idx, n_pos = n_in[:B].reshape(B, 1), n_in[B:]
         cur = torch.cuda.current_stream(device)
 
         def e2e_step():
-            x.copy_(h_idx, non_blocking=True)
-            p.copy_(h_pos, non_blocking=True)
+            d_in.copy_(h_in, non_blocking=True)
             lg = model(x, ctx, p)
             t = lp.sample(lg[:, -1], 1.0, 1)
             h_out.copy_(t, non_blocking=True)

@@ -117,6 +117,12 @@ int lp_init(int device);
 int lp_validate_inputs(void* idx, int idx_is_int64, int n_idx, int vocab, int32_t* pos, int n_pos, int block_size, int32_t* flag,
                        void* stream);
 
+/* The same check fused with staging a step's inputs for a replayed graph: idx_src (int32 / int64 [n_idx]) -> idx_dst int64, pos_src
+ * (int32 / int64 [n_pos]) -> pos_dst int32, clamped and flagged like lp_validate_inputs.  One launch per decode step instead of two
+ * device copies and a check (GPT.forward with T == 1, model.py:88-99). */
+int lp_stage_inputs(const void* idx_src, int idx_is_int64, int n_idx, const void* pos_src, int pos_is_int64, int n_pos, int64_t* idx_dst,
+                    int32_t* pos_dst, int vocab, int block_size, int32_t* flag, void* stream);
+
 /* replaces nn.Embedding `self.transformer.wte(idx)` (model.py:99).  idx: int32 or int64 [rows]; if idx_offset is
  * non-NULL the rows are idx[*idx_offset + r] (device-side position, so a captured decode step can be replayed). */
 int lp_embed(const void* idx, int idx_is_int64, const int32_t* idx_offset, const void* wte, int wte_dtype, float* out,

@@ -211,9 +211,42 @@ __global__ void validate_inputs_kernel(void* idx, int idx64, int n_idx, int voca
   if (bad) atomicOr(flag, bad);
 }
 
+// The same check fused with the copy of a step's inputs into the static buffers a captured graph reads: idx (int32 / int64) ->
+// int64 [n_idx], pos (int32 / int64) -> int32 [n_pos].  One launch instead of two device copies and a check.
+__global__ void stage_inputs_kernel(const void* __restrict__ idx_src, int idx64, int n_idx, const void* __restrict__ pos_src, int pos64,
+                                    int n_pos, long long* __restrict__ idx_dst, int* __restrict__ pos_dst, int vocab, int block_size,
+                                    int* flag) {
+  int bad = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_idx; i += gridDim.x * blockDim.x) {
+    long long t = idx64 ? reinterpret_cast<const long long*>(idx_src)[i] : (long long)reinterpret_cast<const int*>(idx_src)[i];
+    if (t < 0 || t >= vocab) { bad |= 1; t = t < 0 ? 0 : vocab - 1; }
+    idx_dst[i] = t;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pos; i += gridDim.x * blockDim.x) {
+    long long q = pos64 ? reinterpret_cast<const long long*>(pos_src)[i] : (long long)reinterpret_cast<const int*>(pos_src)[i];
+    if (q < 0 || q >= block_size) { bad |= 2; q = q < 0 ? 0 : block_size - 1; }
+    pos_dst[i] = (int)q;
+  }
+  if (bad) atomicOr(flag, bad);
+}
+
 }  // namespace lp
 
 extern "C" {
+
+int lp_stage_inputs(const void* idx_src, int idx_is_int64, int n_idx, const void* pos_src, int pos_is_int64, int n_pos, int64_t* idx_dst,
+                    int32_t* pos_dst, int vocab, int block_size, int32_t* flag, void* stream) {
+  if (!flag || vocab <= 0 || block_size <= 0 || n_idx <= 0 || n_pos <= 0 || !idx_src || !pos_src || !idx_dst || !pos_dst)
+    return LP_ERR_INVALID_ARG;
+  const int n = n_idx > n_pos ? n_idx : n_pos;
+  const int grid = (n + 255) / 256 < 64 ? (n + 255) / 256 : 64;
+  lp::stage_inputs_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(idx_src, idx_is_int64, n_idx, pos_src, pos_is_int64, n_pos,
+                                                                                    reinterpret_cast<long long*>(idx_dst), pos_dst, vocab,
+                                                                                    block_size, flag);
+  LP_CUDA_TRY(cudaGetLastError());
+  lp::count_launch();
+  return LP_OK;
+}
 
 int lp_validate_inputs(void* idx, int idx_is_int64, int n_idx, int vocab, int32_t* pos, int n_pos, int block_size, int32_t* flag,
                        void* stream) {

@@ -768,12 +768,19 @@ class Engine:
             self._graphs[key] = g
         graph, b, s_idx, s_pos = g
         self._raise_if_flagged()  # an out-of-range id / position of an EARLIER replay (seen without a sync: mapped host flag)
-        s_idx.copy_(idx.reshape(-1))
-        s_pos.copy_(pos.reshape(-1))
-        # replayed path, inputs stay on the device: range check + clamp there (lp_validate_inputs), reported at the next call
-        _lib.check(self.lib.lp_validate_inputs(s_idx.data_ptr(), 1, B, V, s_pos.data_ptr(), 1, self.cfg.block_size,
-                                               self._flag.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream),
-                   "lp_validate_inputs")
+        # replayed path, inputs stay on the device: ONE launch copies them into the graph's static buffers and range-checks /
+        # clamps them there (lp_stage_inputs); a violation is reported at the next call
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if (idx.dtype in (torch.int32, torch.int64) and pos.dtype in (torch.int32, torch.int64) and idx.is_contiguous()
+                and pos.is_contiguous() and idx.device == self.device and pos.device == self.device):
+            _lib.check(self.lib.lp_stage_inputs(idx.data_ptr(), int(idx.dtype == torch.int64), B, pos.data_ptr(),
+                                                int(pos.dtype == torch.int64), 1, s_idx.data_ptr(), s_pos.data_ptr(), V,
+                                                self.cfg.block_size, self._flag.data_ptr(), stream), "lp_stage_inputs")
+        else:
+            s_idx.copy_(idx.reshape(-1))
+            s_pos.copy_(pos.reshape(-1))
+            _lib.check(self.lib.lp_validate_inputs(s_idx.data_ptr(), 1, B, V, s_pos.data_ptr(), 1, self.cfg.block_size,
+                                                   self._flag.data_ptr(), stream), "lp_validate_inputs")
         if graph is None:
             self._run(b, s_idx.data_ptr(), 1, None, s_pos.data_ptr(), caches, B, 1, torch.cuda.current_stream(self.device).cuda_stream)
         else:
