@@ -391,6 +391,10 @@ int lp_tp_allreduce_residual(const void* buf_ptrs_dev, const void* pad_ptrs_dev,
  * (index, *step, row)) — so a captured decode step can be replayed without host round trips (generate/base.py:147-153). */
 int lp_sample(const float* logits, int rows, int V, float temperature, int top_k, uint64_t seed, int32_t* step,
               int32_t* token_out, int32_t* seq_buf, int32_t* pos_inout, void* stream);
+/* The same on bf16 logits [rows, V] — what GPT.forward returns for a bf16 checkpoint (model.py:111 in the parameter dtype): no
+ * conversion pass in front of the sampler. */
+int lp_sample_bf16(const void* logits_bf16, int rows, int V, float temperature, int top_k, uint64_t seed, int32_t* step,
+                   int32_t* token_out, int32_t* seq_buf, int32_t* pos_inout, void* stream);
 
 /* load-time: reference GPTQ storage (uint8 (N, K/2) with strides (1, N), quantize/gptq.py:216-222) ->
  * LP_W_INT4 layout.  dst holds N * lp_int4_row_bytes(K) bytes. */

@@ -128,6 +128,7 @@ PROTOTYPES = {
     "lp_tp_allreduce_residual": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                          c_void_p]),
     "lp_sample": (c_int, [c_void_p, c_int, c_int, c_float, c_int, c_u64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lp_sample_bf16": (c_int, [c_void_p, c_int, c_int, c_float, c_int, c_u64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lp_int4_row_bytes": (c_size_t, [c_int]),
     "lp_repack_gptq_int4": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }

@@ -41,8 +41,13 @@ __device__ __forceinline__ Best better(Best a, Best b) {
   return a;
 }
 
+// logits as the model hands them out: fp32, or bf16 (the parameter dtype of a bf16 checkpoint: what GPT.forward returns)
+__device__ __forceinline__ float lg_f(float v) { return v; }
+__device__ __forceinline__ float lg_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename LT>
 __global__ void __launch_bounds__(SAMPLE_THREADS)
-sample_kernel(const float* __restrict__ logits, int V, float temperature, int top_k, uint64_t seed, int* __restrict__ step,
+sample_kernel(const LT* __restrict__ logits, int V, float temperature, int top_k, uint64_t seed, int* __restrict__ step,
               int* __restrict__ token_out, int* __restrict__ seq_buf, int* __restrict__ pos_inout, unsigned int* __restrict__ ticket) {
   __shared__ unsigned int hist[256];
   __shared__ unsigned int s_prefix, s_krem;
@@ -50,7 +55,7 @@ sample_kernel(const float* __restrict__ logits, int V, float temperature, int to
   pdl_wait();
   pdl_launch_dependents();
   const int row = blockIdx.x, tid = threadIdx.x;
-  const float* lg = logits + (size_t)row * V;
+  const LT* lg = logits + (size_t)row * V;
   const bool greedy = (top_k == 1);
 
   uint32_t thr_key = 0;  // keep everything
@@ -67,7 +72,7 @@ sample_kernel(const float* __restrict__ logits, int V, float temperature, int to
       const uint32_t prefix = s_prefix;
       const uint32_t mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
       for (int i = tid; i < V; i += SAMPLE_THREADS) {
-        const uint32_t k = float_key(lg[i] / temperature);
+        const uint32_t k = float_key(lg_f(lg[i]) / temperature);
         if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 0xff], 1u);
       }
       __syncthreads();
@@ -89,7 +94,7 @@ sample_kernel(const float* __restrict__ logits, int V, float temperature, int to
   const int st = step ? *step : 0;
   Best best = {-CUDART_INF_F, 0x7fffffff};
   for (int i = tid; i < V; i += SAMPLE_THREADS) {
-    float l = lg[i] / temperature;
+    float l = lg_f(lg[i]) / temperature;
     if (!greedy) {
       if (float_key(l) < thr_key) continue;
       const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)st, (uint32_t)row, 0u),
@@ -158,17 +163,18 @@ int init_sample() {
   return LP_OK;
 }
 
+template <typename LT>
 __global__ void __launch_bounds__(GREEDY_THREADS)
-greedy_kernel(const float* __restrict__ logits, int V, float temperature, int* __restrict__ step, int* __restrict__ token_out,
+greedy_kernel(const LT* __restrict__ logits, int V, float temperature, int* __restrict__ step, int* __restrict__ token_out,
               int* __restrict__ seq_buf, int* __restrict__ pos_inout, Best* __restrict__ part, unsigned int* __restrict__ ticket) {
   __shared__ Best s_best[GREEDY_THREADS / 32];
   __shared__ int s_last;
   pdl_wait();
   pdl_launch_dependents();
   const int row = blockIdx.y, tid = threadIdx.x;
-  const float* lg = logits + (size_t)row * V;
+  const LT* lg = logits + (size_t)row * V;
   Best best = {-CUDART_INF_F, 0x7fffffff};
-  for (int i = blockIdx.x * GREEDY_THREADS + tid; i < V; i += GREEDY_CTAS * GREEDY_THREADS) best = better(best, Best{lg[i] / temperature, i});
+  for (int i = blockIdx.x * GREEDY_THREADS + tid; i < V; i += GREEDY_CTAS * GREEDY_THREADS) best = better(best, Best{lg_f(lg[i]) / temperature, i});
   auto block_best = [&](Best b) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) b = better(b, Best{__shfl_xor_sync(0xffffffffu, b.v, o), __shfl_xor_sync(0xffffffffu, b.i, o)});
@@ -209,14 +215,26 @@ greedy_kernel(const float* __restrict__ logits, int V, float temperature, int* _
 
 }  // namespace lp
 
-extern "C" int lp_sample(const float* logits, int rows, int V, float temperature, int top_k, uint64_t seed, int32_t* step,
-                         int32_t* token_out, int32_t* seq_buf, int32_t* pos_inout, void* stream) {
+template <typename LT>
+static int sample_launch(const LT* logits, int rows, int V, float temperature, int top_k, uint64_t seed, int32_t* step, int32_t* token_out,
+                         int32_t* seq_buf, int32_t* pos_inout, void* stream) {
   if (!logits || !token_out || rows <= 0 || V <= 0 || !(temperature > 0.f) || top_k < 0) return LP_ERR_INVALID_ARG;
   if (seq_buf && (rows != 1 || !pos_inout)) return LP_ERR_INVALID_ARG;  // pos_inout alone (any rows): just advance
   if (rows > 1 && step && !lp::greedy_ticket()) return LP_ERR_INVALID_ARG;  // lp_init() allocates the row ticket
   if (top_k == 1 && rows <= lp::GREEDY_MAX_ROWS && lp::greedy_part())
-    return lp::launch(lp::greedy_kernel, dim3(lp::GREEDY_CTAS, rows), dim3(lp::GREEDY_THREADS), 0, stream, logits, V, temperature, step,
+    return lp::launch(lp::greedy_kernel<LT>, dim3(lp::GREEDY_CTAS, rows), dim3(lp::GREEDY_THREADS), 0, stream, logits, V, temperature, step,
                       token_out, seq_buf, pos_inout, lp::greedy_part(), lp::greedy_ticket());
-  return lp::launch(lp::sample_kernel, dim3(rows), dim3(lp::SAMPLE_THREADS), 0, stream, logits, V, temperature, top_k, seed, step,
+  return lp::launch(lp::sample_kernel<LT>, dim3(rows), dim3(lp::SAMPLE_THREADS), 0, stream, logits, V, temperature, top_k, seed, step,
                     token_out, seq_buf, pos_inout, lp::greedy_ticket() ? lp::greedy_ticket() + lp::GREEDY_MAX_ROWS : nullptr);
+}
+
+extern "C" int lp_sample(const float* logits, int rows, int V, float temperature, int top_k, uint64_t seed, int32_t* step,
+                         int32_t* token_out, int32_t* seq_buf, int32_t* pos_inout, void* stream) {
+  return sample_launch<float>(logits, rows, V, temperature, top_k, seed, step, token_out, seq_buf, pos_inout, stream);
+}
+
+extern "C" int lp_sample_bf16(const void* logits_bf16, int rows, int V, float temperature, int top_k, uint64_t seed, int32_t* step,
+                              int32_t* token_out, int32_t* seq_buf, int32_t* pos_inout, void* stream) {
+  return sample_launch<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(logits_bf16), rows, V, temperature, top_k, seed, step, token_out,
+                                      seq_buf, pos_inout, stream);
 }

@@ -55,14 +55,17 @@ def sample(logits: torch.Tensor, temperature: float = 1.0, top_k: Optional[int] 
     int32 token ids (rows,).  ``step``: optional int32 device counter that keys the Philox stream."""
     if logits.device.type != "cuda":
         raise RuntimeError("lit_parrot_b200.sample runs on CUDA only")
-    lg = logits.reshape(-1, logits.shape[-1]).float().contiguous()
+    lg = logits.reshape(-1, logits.shape[-1])
+    if lg.dtype != torch.bfloat16:  # bf16 logits (what GPT.forward returns for a bf16 checkpoint) are read as they are
+        lg = lg.float()
+    lg = lg.contiguous()
     lib = _lib.init(lg.device.index)
     out = torch.empty(lg.shape[0], dtype=torch.int32, device=lg.device)
     seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
     k = 0 if top_k is None else min(int(top_k), lg.shape[1])
-    _lib.check(lib.lp_sample(lg.data_ptr(), lg.shape[0], lg.shape[1], float(temperature), k, seed,
-                             None if step is None else step.data_ptr(), out.data_ptr(), None, None,
-                             torch.cuda.current_stream(lg.device).cuda_stream), "lp_sample")
+    fn = lib.lp_sample_bf16 if lg.dtype == torch.bfloat16 else lib.lp_sample
+    _lib.check(fn(lg.data_ptr(), lg.shape[0], lg.shape[1], float(temperature), k, seed, None if step is None else step.data_ptr(),
+                  out.data_ptr(), None, None, torch.cuda.current_stream(lg.device).cuda_stream), "lp_sample")
     return out
 
 

@@ -362,6 +362,29 @@ def test_sample_greedy_and_topk(lib):
     assert int(pos) == 3 and int(seq[3]) == int(lg[0].argmax()) == int(one)
 
 
+def test_sample_bf16_logits_match_fp32_of_the_same_values(lib):
+    """lp_sample_bf16 (the logits GPT.forward returns for a bf16 checkpoint, no conversion pass): same tokens as lp_sample on the
+    same values widened to fp32 — greedy incl. the lowest-index tie break, and the seeded top-k draws one for one."""
+    import lit_parrot_b200 as lp
+
+    V = 50304
+    lg16 = f32(3, V, seed=5).bfloat16()
+    lg16[0, 100] = lg16[0, 40000] = 12.0  # exact tie -> lowest index
+    lg32 = lg16.float()
+    a = torch.zeros(3, dtype=torch.int32, device=DEV)
+    b = torch.zeros_like(a)
+    for k, temp in ((1, 1.0), (7, 0.8), (0, 1.3)):
+        sa, sb = torch.zeros(1, dtype=torch.int32, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV)
+        for _ in range(4):
+            _lib.check(lib.lp_sample_bf16(lg16.data_ptr(), 3, V, temp, k, 77, sa.data_ptr(), a.data_ptr(), None, None, stream()))
+            _lib.check(lib.lp_sample(lg32.data_ptr(), 3, V, temp, k, 77, sb.data_ptr(), b.data_ptr(), None, None, stream()))
+            assert torch.equal(a, b) and int(sa) == int(sb)
+        if k == 1:
+            assert int(a[0]) == 100
+    # the Python entry point takes either dtype
+    assert torch.equal(lp.sample(lg16, 1.0, 1), lp.sample(lg32, 1.0, 1))
+
+
 def test_sample_batched_step_advances(lib):
     """Multi-row launches advance the Philox step once per launch (the noise is keyed by (index, step, row)): replaying the same
     launch on the same logits must draw fresh noise every time, and a rewound step must reproduce the earlier draw."""
