@@ -19,7 +19,7 @@ from lit_parrot_b200 import adapter as lp_adapter
 from lit_parrot_b200 import adapter_v2 as lp_adapter_v2
 from lit_parrot_b200 import lora as lp_lora
 from oracle import lit_oracle as O
-from helpers import GOLDEN, t
+from helpers import GOLDEN, cosine, t
 
 FT = ["adapter_neox", "adapter_llama_gqa", "adapter_v2_llama_mha", "adapter_v2_falcon_mqa", "lora_llama_gqa", "lora_neox"]
 DEV = "cuda:0"
@@ -291,3 +291,37 @@ def test_generate_cli_mains_on_tiny_checkpoint(tmp_path):
         plain = O.generate(O.OracleGPT(cfg, base_sd), prompt_ids, n, n, top_k=1, eos_id=tok.eos_id, argmax_ties=True)
         assert not torch.equal(plain, want), "the fine-tuned weights must change the continuation for this test to mean anything"
         assert "Time for inference:" in err.getvalue() and "Memory used:" in err.getvalue()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,preset", [("adapter_v2", "Llama-2-7b-hf"), ("adapter", "stablelm-base-alpha-3b")])
+def test_adapter_models_at_real_widths(kind, preset):
+    """The adapter paths at the widths of the benchmarked models (two layers deep, bf16 weights, fp32 activations): Llama-2-7b with
+    Adapter v2 (out_bias / out_scale through the tcgen05 GEMM on 24 prompt rows and the streaming GEMV on the decode rows, SwiGLU
+    vectors interleaved, 11008-wide MLP) and stablelm-3b with the v1 prefix (32 heads of 128, 25 % rotary, LayerNorm + biases,
+    V 50688): cached prefill + teacher-forced decode steps against the oracle on the same bf16-rounded weights and bf16 cache."""
+    kw = dict(lp.name_to_config[preset], n_layer=2, block_size=64)
+    extra = dict(adapter_prompt_length=10, adapter_start_layer=0)
+    cfg = lp.Config(**kw)
+    sd = {k: v.bfloat16() for k, v in O.random_state_dict(cfg, seed=21, perturb_norm=True).items()}
+    sd.update({k: v.bfloat16() for k, v in O.adapter_extra_state(cfg, 22, 0, 10, kind == "adapter_v2").items()})
+    m = build(kind, kw, extra, sd, dtype=torch.bfloat16, device=DEV)
+    om = O.OracleGPT(cfg, {k: v.float() for k, v in sd.items()}, kv_round=torch.bfloat16)
+    g = torch.Generator().manual_seed(4)
+    idx = torch.randint(0, cfg.vocab_size, (1, 24), generator=g)
+    pos = torch.arange(24)
+    got = m._forward_impl(idx.to(DEV), 64, pos.to(DEV), raw_logits=True).cpu()
+    want = om(idx, 64, pos)
+    # tolerance of the real-shape tests (test_real_shapes_gpu.py): 2e-3 of the logit scale — k / v are rounded to bf16 on append on
+    # both sides, and a last-bit difference of an fp32 value flips that rounding now and then
+    scale = want.abs().max().item()
+    tol = 2e-3 * max(scale, 1.0)
+    torch.testing.assert_close(got, want, rtol=0, atol=tol)
+    assert cosine(got, want) > 0.99999
+    for s in range(4):
+        tok = torch.randint(0, cfg.vocab_size, (1, 1), generator=g)
+        pos = pos[-1:] + 1
+        got = m._forward_impl(tok.to(DEV), 64, pos.to(DEV), raw_logits=True).cpu()
+        torch.testing.assert_close(got, om(tok, 64, pos), rtol=0, atol=tol)
+    plain = O.OracleGPT(cfg, {k: v.float() for k, v in sd.items() if "adapter" not in k and "gating" not in k}, kv_round=torch.bfloat16)
+    assert (plain(idx, 64, torch.arange(24)) - want).abs().max().item() > 10 * tol  # the adapter matters

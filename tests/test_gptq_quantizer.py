@@ -277,3 +277,36 @@ def test_quantize_cli_main_writes_a_loadable_checkpoint(tmp_path):
     got = model(idx).cpu()
     want = O.OracleGPT(cfg, {k: v for k, v in out.items() if v is not None})(idx.cpu())
     torch.testing.assert_close(got, want, rtol=0, atol=3e-5)
+
+
+@pytest.mark.gpu
+def test_quantize_layer_at_llama7b_width_against_oracle():
+    """One 4096 x 4096 layer (32 sweep blocks, 32 groups of 128, 31 trailing updates) with the Hessian of 6144 correlated
+    calibration tokens, bf16 layer weights: the device quantiser against the oracle restatement run on the host.  With ~0.3 % of
+    the weights on a grid midpoint within rounding noise, nearly every 4096-column row sees a flip somewhere and drifts from there
+    (rows are independent, a flip changes every later weight of its row through the error feedback), so the bar at this size is
+    statistical: >= 95 % identical codes and the same quantisation loss (1 %)."""
+    N, K, gs = 4096, 4096, 128
+    g = torch.Generator().manual_seed(9)
+    W = (torch.randn((N, K), generator=g) * 0.02).bfloat16().float()
+    mix = torch.randn((K, K), generator=g) / (K ** 0.5) * 0.5 + torch.eye(K)
+    batches = [(torch.randn((4, 512, K), generator=g) @ mix) for _ in range(3)]  # 6144 tokens: a full-rank Hessian
+    lin = torch.nn.Linear(K, N, bias=False)
+    lin.weight.data.copy_(W)
+    gq = lp_gptq.GPTQQuantizer(lin.to(DEV).bfloat16(), bits=4, groupsize=gs)
+    for x in batches:
+        gq.collect_input_stats(None, (x.to(DEV),), None)
+    H_dev = gq.H.cpu().clone()
+    qmod, err = gq.quantize()
+    H, _ = O.gptq_hessian(batches)
+    h_err = (H_dev - H).abs().max().item() / H.abs().max().item()
+    print(f"Hessian 4096 x 4096 over 6144 tokens: max deviation {h_err:.2e} of max|H| (both sides accumulate 6144 fp32 terms)")
+    assert h_err <= 3e-5
+    Q, sc, ze, err_o, _ = O.gptq_quantize_layer(W, H, groupsize=gs)
+    got, want = _codes(qmod).int(), O.gptq_codes(Q, sc, ze, gs).int()
+    same = (got == want).float().mean().item()
+    row_same = (got == want).all(dim=1)
+    frac_rows = row_same.float().mean().item()
+    print(f"4096 x 4096 g128: identical codes {same:.4%}, rows identical end to end {frac_rows:.2%}, loss {err:.3f} vs oracle {err_o:.3f}")
+    assert qmod.scales.dtype == torch.bfloat16  # stored in the weight's dtype (gptq.py:300-304)
+    assert same >= 0.95 and abs(err - err_o) <= 1e-2 * err_o and (got - want).abs().float().mean().item() < 0.1
