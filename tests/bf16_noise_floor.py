@@ -7,7 +7,9 @@ This tool measures both sides on the same B200: the UNMODIFIED reference (baseli
 weights in fp32 (no TF32) and under bf16-true, and this repo's GPT on the same weights in its two modes.  Weights: seeded random
 init, pre-rounded to bf16 so that every run multiplies the same stored values.
 
-    python tools/bf16_noise_floor.py [--out profiles/r3_bf16_noise_floor.txt]
+    python tests/bf16_noise_floor.py [--out profiles/r3_bf16_noise_floor.txt]
+
+Lives under tests/ because it draws its seeded weights from the oracle (test infrastructure).
 """
 import argparse
 import json
@@ -93,7 +95,7 @@ def main():
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
-    lines = [f"bf16 noise floor on {torch.cuda.get_device_name(0)} (torch {torch.__version__}); tools/bf16_noise_floor.py"]
+    lines = [f"bf16 noise floor on {torch.cuda.get_device_name(0)} (torch {torch.__version__}); tests/bf16_noise_floor.py"]
     allres = {}
     for name, kw in CASES.items():
         allres[name] = run_case(name, kw, dev, lines)

@@ -1,6 +1,6 @@
 """deep models in bf16.  The north-star tolerance (logits max-abs 2e-2, cosine > 0.999, 64 identical greedy
 tokens) is below the reference's own bf16 noise for 24-layer models, so two claims are tested against the UNMODIFIED reference run
-on the same GPU (baseline/_ref, eager PyTorch, subprocess; tools/bf16_noise_floor.py):
+on the same GPU (baseline/_ref, eager PyTorch, subprocess; tests/bf16_noise_floor.py):
   * default mode (fp32 activations over the bf16 weights, bf16 KV cache) meets the north-star tolerance against the reference in
     fp32 and decodes the same 64 greedy tokens;
   * precision="bf16" is as close to the reference in fp32 as the reference's own bf16-true run is (the noise floor).
@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _tool():
-    spec = importlib.util.spec_from_file_location("bf16_noise_floor", os.path.join(REPO, "tools", "bf16_noise_floor.py"))
+    spec = importlib.util.spec_from_file_location("bf16_noise_floor", os.path.join(REPO, "tests", "bf16_noise_floor.py"))
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
     return m
