@@ -336,6 +336,13 @@ class Engine:
                 i_fc = linear(L.fc, x, n2, self.act, None, u, last)   # reads the old x: streams right behind the QKV weights
                 i_att = attention(li, i_qkv)
                 # x += attn.proj(att); x += mlp.proj(u): both in place (atomic accumulation, stage-granular split), no barrier
+                if tp is None and os.environ.get("LP_DS_PROJ_LAST", "1") != "0":
+                    # mlp.proj FIRST: its input (u) has been complete since fc, so a CTA streams its 4x larger weights the moment it
+                    # leaves the attention op, while the slower heads finish; attn.proj, which needs every head's partials (a
+                    # grid-wide dependency), runs last, when they have long arrived.  (LP_DS_PROJ_LAST=0: reference order, for A/B.)
+                    row_parallel(L.mlp_proj, u, i_fc)
+                    last = row_parallel(L.proj, None, i_att, from_attn=True)
+                    continue
                 i_proj = row_parallel(L.proj, None, i_att, from_attn=True)
                 last = row_parallel(L.mlp_proj, u, i_fc if tp is None else max(i_fc, i_proj))
             else:

@@ -1,0 +1,13 @@
+#!/bin/bash
+export PYTHONUNBUFFERED=1
+for w in stablelm-3b-bf16-b1 falcon-7b-bf16-b1; do
+for v in 0 1 0 1; do
+LP_DS_PROJ_LAST=$v timeout 300 python bench.py --workload $w --steps 32 --warmup 8 --no-extras --no-cpu-baseline > gpurun_out/r3t.log 2>&1
+python - $w $v <<'PY'
+import json, sys
+d = json.loads(open('gpurun_out/r3t.log').read().strip().splitlines()[-1])
+print(sys.argv[1], 'proj_last', sys.argv[2], 'tok/s', round(d['value'],1), 'kernel', d['roofline']['kernel'][-22:], 'frac', round(d['roofline']['frac'],4))
+PY
+done
+done
+timeout 900 python -m pytest tests/test_decode_step_gpu.py tests/test_real_shapes_gpu.py tests/test_model_gpu.py -q -m gpu -x 2>&1 | tail -3
