@@ -71,6 +71,48 @@ class ClockSampler:
 
     def __init__(self, index: int) -> None:
         self.rows, self.proc, self.index = [], None, index
+        self.nvml = None
+
+    def _nvml_handle(self):
+        """NVML handle of CUDA device `index` (by UUID: the two enumerations differ under CUDA_VISIBLE_DEVICES), or None."""
+        try:
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(self.index).uuid))
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            return pynvml, h
+        except Exception:
+            return None
+
+    def sample_until(self, event, max_samples: int = 200) -> None:
+        """In-process NVML samples WHILE the GPU works through the queued timed steps (the nvidia-smi poller below needs ~100 ms
+        to deliver its first line, longer than a short timed region): one sample at once, then until `event` has completed."""
+        if self.nvml is None:
+            self.nvml = self._nvml_handle() or False
+        if not self.nvml:
+            return
+        nv, h = self.nvml
+        n = 0
+        while True:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                flag = lambda bit: "Active" if rs & bit else "Not Active"  # noqa: E731
+                self.rows.append([str(sm), str(mx), "", flag(0x8), flag(0x40), flag(0x20), flag(0x4)])  # hw, hw-thermal, sw-thermal, sw power cap
+            except Exception:
+                return
+            n += 1
+            if event.query() or n >= max_samples:
+                return
+            time.sleep(0.002)
 
     def __enter__(self):
         try:
@@ -235,6 +277,7 @@ def run_workload(workload, steps, warmup, device, rank=0, world=1, with_e2e=True
         for _ in range(steps):
             replay()
         e1.record()
+        clk.sample_until(e1)  # clocks / throttle reasons while the queued steps execute
         sync_barrier()
     ms = e0.elapsed_time(e1)
     if world > 1:
