@@ -264,7 +264,9 @@ int lp_swiglu(const float* a, const float* b, float* out, size_t n, int round_bf
  *   residual: must be covered by `dep`, be a step input, or be the output of an earlier LINEAR op with the same N (the same
  *        CTA then wrote the rows it reads); checked by lp_decode_step_plan.  residual == out (x += W . u in place) is the
  *        preferred form: such ops are split over the CTAs at 16 KB-stage granularity and accumulate with atomic adds, so two
- *        of them may overlap (parallel-residual blocks); the summation order of their partial sums is not fixed.
+ *        of them may overlap (parallel-residual blocks); the summation order of their partial sums is not fixed.  An op without a
+ *        residual can use the same form on a zeroed buffer of its own (residual == out inside geom.zero_ptr .. + zero_bytes):
+ *        every SM then streams the same number of weight bytes whatever the tile count (QKV: 768 tiles on 148 SMs = 6 vs 5.19).
  * Covers fp32-activation mode, bf16 / GPTQ-int4 (tile-major aux2) / bnb NF4 (tile-major absmax) / row-wise int8 weights, MHA / GQA / MQA with H <= #SMs, bf16 KV cache,
  * hs 64 / 128, batch 1; LP_ERR_UNSUPPORTED otherwise (callers then issue the per-op calls above). */
 typedef enum { LP_STEP_LINEAR = 0, LP_STEP_ATTENTION = 1, LP_STEP_EXCHANGE = 2, LP_STEP_SLAB = 3 } lp_step_kind;
@@ -340,6 +342,8 @@ typedef struct {
   size_t workspace_bytes;
   int32_t idx_is_int64, wte_dtype, E, H, G, hs, n_elem, max_seq, kv_dtype;
   float scale;               /* softmax scale, 1/sqrt(hs)                                                         */
+  void* zero_ptr;            /* optional: zero_bytes (multiple of 16) cleared by the step's prologue before any op runs —      */
+  size_t zero_bytes;         /* outputs of LINEAR ops that accumulate in place into a buffer of their own (see below)      */
 } lp_step_geom;
 
 typedef struct { uint64_t opaque[32]; } lp_step_handle;  /* filled by lp_decode_step_plan; plain data, copyable */

@@ -59,7 +59,7 @@ class LpStepGeom(ctypes.Structure):
                 ("cos", c_void_p), ("sin", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
                 ("idx_is_int64", ctypes.c_int32), ("wte_dtype", ctypes.c_int32), ("E", ctypes.c_int32), ("H", ctypes.c_int32),
                 ("G", ctypes.c_int32), ("hs", ctypes.c_int32), ("n_elem", ctypes.c_int32), ("max_seq", ctypes.c_int32),
-                ("kv_dtype", ctypes.c_int32), ("scale", c_float)]
+                ("kv_dtype", ctypes.c_int32), ("scale", c_float), ("zero_ptr", c_void_p), ("zero_bytes", c_size_t)]
 
 
 class LpStepHandle(ctypes.Structure):

@@ -1901,9 +1901,13 @@ __global__ void slab_build_kernel(const uint32_t* __restrict__ rows32, int row_w
 // Prologue of a step: x = wte[token] (model.py:99), arrival counters = 0.
 __global__ void decode_step_prep_kernel(const void* __restrict__ idx, int idx64, const int* __restrict__ idx_offset,
                                         const void* __restrict__ wte, int wte_dtype, float* __restrict__ x, int E,
-                                        unsigned* __restrict__ counters, int nops) {
+                                        unsigned* __restrict__ counters, int nops, float4* __restrict__ zero, size_t zero_n4) {
   pdl_launch_dependents();  // the step kernel prefetches weights while the previous step's sampler is still running
   pdl_wait();
+  // outputs of ops that accumulate in place into a buffer of their own (QKV rows split stream-K): cleared here, the step kernel's
+  // consumers pass their own griddepcontrol.wait only when this grid has completed
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < zero_n4; i += (size_t)gridDim.x * blockDim.x)
+    zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int at = idx_offset ? idx_offset[0] : 0;
   const long long tok = idx64 ? reinterpret_cast<const long long*>(idx)[at] : (long long)reinterpret_cast<const int*>(idx)[at];
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x)
@@ -1935,6 +1939,8 @@ struct DsHostPlan {  // lp_step_handle, opaque to the caller
   float* x0;
   unsigned int* tp_state0;
   unsigned int* tp_state1;
+  void* zero_ptr;
+  size_t zero_bytes;
 };
 static_assert(sizeof(DsHostPlan) <= sizeof(lp_step_handle), "lp_step_handle too small");
 constexpr uint32_t DS_MAGIC = 0x4c504453u;
@@ -2331,6 +2337,9 @@ int lp_decode_step_plan(const lp_step_op* ops, int n_ops, const lp_step_geom* gm
   h.idx_offset = gm->idx_offset;
   h.wte = gm->wte;
   h.x0 = gm->x0;
+  h.zero_ptr = gm->zero_ptr;
+  h.zero_bytes = gm->zero_ptr ? gm->zero_bytes : 0;
+  if (h.zero_bytes % 16 || (reinterpret_cast<uintptr_t>(h.zero_ptr) & 15)) return LP_ERR_INVALID_ARG;
   h.tp_state0 = tp_state[0];
   h.tp_state1 = tp_state[1];
   // load-time copy of the op table, the dependency list and a clean error record (synchronous: the staging vectors die at return)
@@ -2363,8 +2372,10 @@ int lp_decode_step(const lp_step_handle* handle, void* stream) {
   DsHostPlan h;
   memcpy(&h, handle, sizeof(h));
   if (h.magic != DS_MAGIC) return LP_ERR_INVALID_ARG;
-  int rc = launch(decode_step_prep_kernel, dim3((h.E + 1023) / 1024), dim3(256), 0, stream, h.idx, h.idx64, h.idx_offset, h.wte, h.wte_dtype,
-                  h.x0, h.E, h.counters, h.ncounters);
+  const size_t zero_n4 = h.zero_bytes / 16;
+  const int prep_grid = std::max((h.E + 1023) / 1024, (int)std::min<size_t>((zero_n4 + 2047) / 2048, (size_t)num_sms()));
+  int rc = launch(decode_step_prep_kernel, dim3(prep_grid), dim3(256), 0, stream, h.idx, h.idx64, h.idx_offset, h.wte, h.wte_dtype, h.x0,
+                  h.E, h.counters, h.ncounters, reinterpret_cast<float4*>(h.zero_ptr), zero_n4);
   if (rc != LP_OK) return rc;
   DsParams p;
   p.ops = h.ops_dev;

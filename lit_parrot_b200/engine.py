@@ -303,6 +303,12 @@ class Engine:
         slabs = self._build_slabs()
         tp = self.tp
         n_exch = [0]
+        # QKV rows accumulate in place (stream-K split: every SM streams the same number of weight bytes whatever the tile count)
+        # into a zeroed buffer of their own per layer; the step's prologue clears them (lp_step_geom.zero_ptr).  LP_DS_QKV_SK=0:
+        # whole tiles per CTA into the shared qkv buffer, for A/B.
+        qkv_rows = cfg.qkv_rows_local
+        qkv_sk = os.environ.get("LP_DS_QKV_SK", "1") != "0" and qkv_rows % 4 == 0
+        qkv_all = torch.zeros((cfg.n_layer, qkv_rows), dtype=torch.float32, device=self.device) if qkv_sk else None
 
         def row_parallel(W, src, dep, from_attn=False):
             """x += src . W^T.  Single GPU: in place (stage-granular split, atomic accumulation).  Tensor parallel: W is a column
@@ -329,8 +335,14 @@ class Engine:
             return len(ops) - 1
 
         last = -1
+        qkv_shared = qkv
         for li, L in enumerate(self.layers):
-            i_qkv = linear(L.qkv, x, (L.n1_w, L.n1_b), _lib.LP_EPI_NONE, None, qkv, last)
+            if qkv_sk:
+                qkv = qkv_all[li].data_ptr()
+                i_qkv = linear(L.qkv, x, (L.n1_w, L.n1_b), _lib.LP_EPI_RESIDUAL, qkv, qkv, last)
+            else:
+                qkv = qkv_shared
+                i_qkv = linear(L.qkv, x, (L.n1_w, L.n1_b), _lib.LP_EPI_NONE, None, qkv, last)
             if cfg.parallel_residual:
                 n2 = (L.n1_w, L.n1_b) if cfg.shared_attention_norm else (L.n2_w, L.n2_b)
                 i_fc = linear(L.fc, x, n2, self.act, None, u, last)   # reads the old x: streams right behind the QKV weights
@@ -372,13 +384,15 @@ class Engine:
         gm.idx_is_int64, gm.wte_dtype = idx64, _KV_OF_DTYPE[self.wte.dtype]
         gm.E, gm.H, gm.G, gm.hs, gm.n_elem, gm.max_seq = E, H, G, hs, cfg.rope_n_elem, max_seq
         gm.kv_dtype, gm.scale = _KV_OF_DTYPE[caches[0][0].dtype], 1.0 / math.sqrt(hs)
+        if qkv_all is not None:
+            gm.zero_ptr, gm.zero_bytes = qkv_all.data_ptr(), qkv_all.numel() * 4
         handle = _lib.LpStepHandle()
         rc = lib.lp_decode_step_plan(arr, n, ctypes.byref(gm), plan.data_ptr(), plan.numel(), ctypes.byref(handle))
         if rc == -2:
             self._steps[key] = None
             return None
         _lib.check(rc, "lp_decode_step_plan")
-        self._steps[key] = (handle, plan, ws, arr, n)
+        self._steps[key] = (handle, plan, ws, arr, n, qkv_all)
         return handle
 
     def _raise_if_flagged(self) -> None:
