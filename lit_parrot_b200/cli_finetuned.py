@@ -1,5 +1,5 @@
 """The reference's instruction-tuned entry points: ``python generate/adapter.py``, ``generate/adapter_v2.py``
-(reference generate/adapter.py:23-129, generate/adapter_v2.py:25-132) and ``generate/lora.py`` (generate/lora.py:28-146).  Same
+(reference generate/adapter.py:23-129, generate/adapter_v2.py:25-132), ``generate/lora.py`` (generate/lora.py:28-146) and ``generate/full.py`` (generate/full.py:23-117).  Same
 arguments, same checkpoint files (base ``lit_model.pth`` + the fine-tuned adapter / LoRA file, merged into one state dict), same
 Alpaca prompt (scripts/prepare_alpaca.py:141-155), same output lines.  One process drives one B200 (see cli.py)."""
 import json
@@ -15,6 +15,8 @@ from lit_parrot_b200 import adapter_v2 as _adapter_v2
 from lit_parrot_b200 import lora as _lora
 from lit_parrot_b200.checkpoint import check_valid_checkpoint_dir, lazy_load
 from lit_parrot_b200.cli import _QUANT, _param_dtype
+from lit_parrot_b200.config import Config
+from lit_parrot_b200.model import GPT as BaseGPT
 from lit_parrot_b200.generate import generate
 from lit_parrot_b200.tokenizer import Tokenizer
 from lit_parrot_b200.utils import quantization
@@ -45,12 +47,16 @@ def _run(kind: str, prompt: str, input: str, extra_path: Path, checkpoint_dir: P
         cfg_json = json.load(fp)
     if kind == "lora":
         config, model_cls = _lora.Config(**lora_kwargs, **cfg_json), _lora.GPT
+    elif kind == "full":
+        if quantize is not None:
+            raise NotImplementedError  # generate/full.py:68-70: quantised fully fine-tuned checkpoints are not supported upstream either
+        config, model_cls = Config(**cfg_json), BaseGPT
     else:
         config, model_cls = _adapter.Config(**cfg_json), _adapter.GPT
     model_file = "lit_model_gptq.4bit.pth" if quantize == "gptq.int4" else "lit_model.pth"
     if quantize == "gptq.int4" and not (checkpoint_dir / model_file).is_file():
         raise ValueError("Please run `python quantize/gptq.py` first")
-    checkpoint_path = checkpoint_dir / model_file
+    checkpoint_path = extra_path if kind == "full" else checkpoint_dir / model_file  # full: the fine-tuned file holds every weight
     print(f"Loading model {str(checkpoint_path)!r} with {config.__dict__}", file=sys.stderr)
     t0 = time.time()
     prev = torch.get_default_dtype()
@@ -66,7 +72,8 @@ def _run(kind: str, prompt: str, input: str, extra_path: Path, checkpoint_dir: P
     t0 = time.time()
     with lazy_load(checkpoint_path) as checkpoint, lazy_load(extra_path) as extra:
         sd = dict(checkpoint.get("model", checkpoint))
-        sd.update(extra.get("model", extra))
+        if kind != "full":
+            sd.update(extra.get("model", extra))
         model.load_state_dict(sd, strict=quantize is None)
     print(f"Time to load the model weights: {time.time() - t0:.02f} seconds.", file=sys.stderr)
     model = model.eval().to(device)
@@ -107,6 +114,15 @@ def main_adapter_v2(prompt: str = "What food do lamas eat?", input: str = "",
     """Generates a response based on a given instruction and an optional input (GPT-AdapterV2 checkpoints, generate/adapter_v2.py:25)."""
     _run("adapter_v2", prompt, input, adapter_path, checkpoint_dir, quantize, max_new_tokens, top_k, temperature, strategy, devices,
          precision)
+
+
+def main_full(prompt: str = "What food do lamas eat?", input: str = "",
+              finetuned_path: Path = Path("out/full/alpaca/lit_model_finetuned.pth"),
+              checkpoint_dir: Path = Path("checkpoints/stabilityai/stablelm-base-alpha-3b"), quantize: Optional[str] = None,
+              max_new_tokens: int = 100, top_k: int = 200, temperature: float = 0.8, strategy: str = "auto", devices: int = 1,
+              precision: str = "bf16-true") -> None:
+    """Generates a response based on a given instruction and an optional input (fully fine-tuned checkpoints, generate/full.py:23)."""
+    _run("full", prompt, input, finetuned_path, checkpoint_dir, quantize, max_new_tokens, top_k, temperature, strategy, devices, precision)
 
 
 # module-level LoRA hyper-parameters of generate/lora.py:19-27 (they must match the fine-tuning run)

@@ -129,6 +129,11 @@ def test_drop_in_import_paths_and_cli_surface():
             "devices", "precision"]  # generate/adapter.py:23-35, generate/adapter_v2.py:25-37
     assert list(inspect.signature(ga.main).parameters) == want and list(inspect.signature(ga2.main).parameters) == want
     assert list(inspect.signature(gl.main).parameters) == [w if w != "adapter_path" else "lora_path" for w in want]  # generate/lora.py:28-40
+    import generate.full as gf
+
+    assert list(inspect.signature(gf.main).parameters) == [w if w != "adapter_path" else "finetuned_path" for w in want]  # generate/full.py:23-35
+    with pytest.raises((NotImplementedError, RuntimeError)):  # quantised fully fine-tuned checkpoints: NotImplementedError upstream too
+        gf.main("x", "", Path("nope.pth"), Path(GOLDEN) / "ckpt_tiny_llama", "bnb.nf4")
     # scripts/prepare_alpaca.py:141-155
     assert cf.generate_prompt({"instruction": "Do it", "input": ""}) == (
         "Below is an instruction that describes a task. Write a response that appropriately completes the request.\n\n"
@@ -270,21 +275,25 @@ def test_generate_cli_mains_on_tiny_checkpoint(tmp_path):
     tok = Tokenizer(ckpt)
     prompt_ids = tok.encode(cf.generate_prompt({"instruction": "w20 w21", "input": ""}))
     assert "### Response:" in tok.decode(prompt_ids)
-    for kind in ("adapter_v2", "lora"):  # (Config defaults start the v1 prefix at layer 2: a 2-layer checkpoint has none)
-        if kind == "lora":
+    for kind in ("adapter_v2", "lora", "full"):  # (Config defaults start the v1 prefix at layer 2: a 2-layer checkpoint has none)
+        if kind == "full":  # a fully fine-tuned checkpoint: every weight in the one file (here: the base weights perturbed)
+            gfull = torch.Generator().manual_seed(3)
+            extra = {k: (v + 0.02 * torch.randn(v.shape, generator=gfull)) if v.dim() == 2 else v.clone() for k, v in base_sd.items()}
+        elif kind == "lora":
             extra = O.lora_extra_state(cfg, 7, cf.lora_r, (True, False, True), False, False, False)
         else:
             extra = O.adapter_extra_state(cfg, 7, 2, 10, True)
         path = tmp_path / f"{kind}.pth"
         torch.save({"model": extra} if kind == "lora" else extra, path)
         out, err = io.StringIO(), io.StringIO()
-        main = {"adapter_v2": cf.main_adapter_v2, "lora": cf.main_lora}[kind]
+        main = {"adapter_v2": cf.main_adapter_v2, "lora": cf.main_lora, "full": cf.main_full}[kind]
         with redirect_stdout(out), redirect_stderr(err):
             main("w20 w21", "", path, ckpt, None, 12, 1, 1.0, "auto", 1, "32-true")
         sd = dict(base_sd)
         sd.update(extra)
         if kind == "lora":
             sd = O.lora_merge_state_dict(cfg, sd, cf.lora_r, cf.lora_alpha, (True, False, True))
+        sd = {k: v.float() for k, v in sd.items()}
         n = prompt_ids.numel() + 12
         want = O.generate(O.OracleGPT(cfg, sd), prompt_ids, n, n, top_k=1, eos_id=tok.eos_id, argmax_ties=True)
         assert out.getvalue().strip() == tok.decode(want).split("### Response:")[1].strip(), kind
