@@ -112,7 +112,7 @@ def CLI(fn, argv=None):
     ap = argparse.ArgumentParser(description=(fn.__doc__ or "").strip().splitlines()[0] if fn.__doc__ else None)
     first = None
     for name, p in sig.parameters.items():
-        typ = {int: int, float: float, str: str, Path: Path}.get(type(p.default), str)
+        typ = Path if isinstance(p.default, Path) else {int: int, float: float, str: str}.get(type(p.default), str)
         ap.add_argument(f"--{name}", type=typ, default=p.default)
         if first is None and p.kind is not inspect.Parameter.KEYWORD_ONLY:
             first = name

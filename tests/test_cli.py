@@ -83,6 +83,23 @@ def test_cli_argument_surface_and_errors(tmp_path):
     assert gb.main is cli.main and cb.main is chat.main and cb.generate is chat.generate
 
 
+def test_cli_helper_parses_like_jsonargparse():
+    """`CLI(main)`: every parameter is a `--name value` option (jsonargparse turns parameters with defaults into options, so the
+    reference is run as `python generate/base.py --prompt "Hello" --checkpoint_dir ...`); the first one may also be positional."""
+    seen = {}
+
+    def fn(prompt: str = "Hello", *, max_new_tokens: int = 50, temperature: float = 0.8, checkpoint_dir: Path = Path("x")):
+        """doc"""
+        seen.update(prompt=prompt, max_new_tokens=max_new_tokens, temperature=temperature, checkpoint_dir=checkpoint_dir)
+
+    cli.CLI(fn, ["--prompt", "a b", "--max_new_tokens", "7", "--checkpoint_dir", "ckpt/dir"])
+    assert seen == dict(prompt="a b", max_new_tokens=7, temperature=0.8, checkpoint_dir=Path("ckpt/dir"))
+    cli.CLI(fn, ["positional prompt", "--temperature", "0.5"])
+    assert seen["prompt"] == "positional prompt" and seen["temperature"] == 0.5 and seen["max_new_tokens"] == 50
+    with pytest.raises(SystemExit):
+        cli.CLI(fn, ["--no_such_option", "1"])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("quantize", [None, "gptq.int4"])
 def test_generate_cli_main_on_tiny_checkpoint(quantize):
