@@ -145,3 +145,30 @@ def test_step_kernel_register_budget():
     assert len(blocks) == 2, out[-2000:]
     for name, _stack, stores in blocks:
         assert int(stores) <= 400, f"{name}: {stores} bytes of spill stores (budget 400; 264 when this test was written)"
+
+
+def test_swap_gemm_code_footprint():
+    """gemm_tc_swap_kernel runs its tile epilogue ONCE per CTA on single-tile shapes; as one unrolled body holding every variant it was
+    17.2 k SASS instructions and a launch spent as long fetching them (20 us, all SMs walking the same cold lines in lock step) as
+    streaming its weights (18 us).  The pass-structured epilogue is 5.2 k; keep the whole kernel under 8 k."""
+    import re
+    import subprocess
+
+    from lit_parrot_b200 import build as b
+
+    obj = os.path.join(b.HERE, "build", "gemm_tc.o")
+    src = os.path.join(b.CSRC, "gemm_tc.cu")
+    if not os.path.exists(obj) or os.path.getmtime(obj) < os.path.getmtime(src):
+        subprocess.run([b._nvcc(), *b.NVCC_FLAGS, "-c", src, "-o", obj], check=True, capture_output=True)
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    counts, name = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+        elif name and re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+\S", line):
+            counts[name] = counts.get(name, 0) + 1
+    swap = {k: v for k, v in counts.items() if "gemm_tc_swap_kernel" in k}
+    assert len(swap) == 4, sorted(counts)  # <affine, stream-K> variants
+    for k, v in swap.items():
+        assert v < 8000, f"{k}: {v} SASS instructions (5.2 k when this test was written)"
